@@ -1,0 +1,169 @@
+// 2048 board as a 64-bit nibble bitboard held in registers.
+//
+// Cell i = 4*row + col (row-major, same order as Pgx's flat board) lives in bits [4i, 4i+4) and
+// stores the exponent e (0 = empty, e = tile 2^e).  Row r is bits [16r, 16r+16).  All four rows (or
+// columns) of a move are processed at once with SWAR arithmetic on the whole word: a move toward
+// lower cell indices ("Left": stride 4 bits, "Up": stride 16 bits) is three conditional one-cell
+// shifts, one merge pass, two more shifts; Right/Down run the same code on the nibble-reversed
+// board.  There is no lookup table: the shared-memory row table of classic bitboard 2048 costs
+// 128 KiB + bank conflicts, while the SWAR move is ~140 integer instructions -- small next to the
+// ~850 instructions of Threefry per env-step.
+//
+// Replaces Pgx 2.6.0's 2048 _step/_slide_and_merge/_can_slide_left/_add_random_num/observe as called
+// from src/runs/batch_runner.py:34-35,107,128 of the reference (actions 0=Left 1=Up 2=Right 3=Down).
+#pragma once
+#include <cstdint>
+
+#include "g2048_rng.cuh"
+
+namespace g2048 {
+
+typedef unsigned long long u64;
+
+constexpr u64 NIB_LSB = 0x1111111111111111ull;
+
+// bit 0 of every nibble = (nibble != 0)
+__device__ __forceinline__ u64 nonzero_lsb(u64 x) {
+    u64 t = x | (x >> 1);
+    t |= t >> 2;
+    return t & NIB_LSB;
+}
+
+// 0xF in every nibble whose lsb is set in t (t has only nibble lsbs)
+__device__ __forceinline__ u64 spread_nibble(u64 t) { return (t << 4) - t; }
+
+// reverse the 16 nibbles: cell i <-> cell 15 - i (a 180 degree turn of the board)
+__device__ __forceinline__ u64 reverse_nibbles(u64 x) {
+    uint32_t lo = (uint32_t)x, hi = (uint32_t)(x >> 32);
+    lo = __byte_perm(lo, 0, 0x0123);
+    hi = __byte_perm(hi, 0, 0x0123);
+    lo = ((lo & 0x0F0F0F0Fu) << 4) | ((lo >> 4) & 0x0F0F0F0Fu);
+    hi = ((hi & 0x0F0F0F0Fu) << 4) | ((hi >> 4) & 0x0F0F0F0Fu);
+    return ((u64)lo << 32) | hi;
+}
+
+// Slide + merge toward lower cell indices along lines of stride `s` bits (4: rows, i.e. Left;
+// 16: columns, i.e. Up).  `has_lower` marks the cells that have a neighbour at p - s in their line.
+// Returns the moved board; `reward` gets sum of 2^(e+1) over merges (Pgx: the merged tile's value);
+// `overflow` is set if a 2^15 pair merged (the result does not fit a nibble).
+__device__ __forceinline__ u64 slide_merge_low(u64 x, int s, u64 has_lower, uint32_t& reward, bool& overflow) {
+#define G2048_COMPRESS_ONCE()                                          \
+    {                                                                  \
+        const u64 empty = ~spread_nibble(nonzero_lsb(x));              \
+        const u64 mv = x & (empty << s) & has_lower;                   \
+        x = (x ^ mv) | (mv >> s);                                      \
+    }
+    G2048_COMPRESS_ONCE()
+    G2048_COMPRESS_ONCE()
+    G2048_COMPRESS_ONCE()
+    // merge pass: pair (p, p+s) merges iff equal, non-empty and p was not consumed by (p-s, p)
+    const u64 has_upper = has_lower >> s;
+    const u64 nz = nonzero_lsb(x);
+    const u64 eq = ~nonzero_lsb(x ^ (x >> s)) & nz & has_upper & NIB_LSB;  // lsb flags at p
+    // position in line: line0 = cells with no lower neighbour
+    const u64 line0 = ~has_lower & NIB_LSB;
+    const u64 m0 = eq & line0;
+    const u64 m1 = eq & (line0 << s) & ~(m0 << s);
+    const u64 m2 = eq & (line0 << (2 * s)) & ~(m1 << s);
+    u64 m = m0 | m1 | m2;
+    reward = 0;
+    if (m) {
+        u64 mm = m;
+        do {
+            const int p = __ffsll((long long)mm) - 1;
+            const uint32_t v = (uint32_t)(x >> p) & 15u;
+            overflow |= (v == 15u);
+            reward += 2u << v;
+            mm &= mm - 1;
+        } while (mm);
+        x += m;                              // merged cell: e -> e + 1
+        x &= ~(spread_nibble(m) << s);       // its partner disappears
+        G2048_COMPRESS_ONCE()
+        G2048_COMPRESS_ONCE()
+    }
+#undef G2048_COMPRESS_ONCE
+    return x;
+}
+
+// Pgx _step's board part: rot90(board, action) -> slide/merge left -> rotate back.
+__device__ __forceinline__ u64 move_board(u64 x, int action, uint32_t& reward, bool& overflow) {
+    const bool rev = action >= 2;            // Right = Left on the reversed board, Down = Up on it
+    if (rev) x = reverse_nibbles(x);
+    const bool vertical = action & 1;
+    const int s = vertical ? 16 : 4;
+    const u64 has_lower = vertical ? 0xFFFFFFFFFFFF0000ull : 0xFFF0FFF0FFF0FFF0ull;
+    x = slide_merge_low(x, s, has_lower, reward, overflow);
+    if (rev) x = reverse_nibbles(x);
+    return x;
+}
+
+// Exact legal-action mask, bit a = (move(board, a) != board): a line can move toward a side iff
+// some adjacent pair along it is (empty, tile) in that order, or two equal tiles.
+__device__ __forceinline__ uint32_t legal_mask(u64 x) {
+    const u64 nz = nonzero_lsb(x);
+    const u64 H = 0x0111011101110111ull;     // pairs (p, p+1 col) for col 0..2
+    const u64 V = 0x0000111111111111ull;     // pairs (p, p+1 row) for row 0..2
+    const u64 nzr = nz >> 4, nzd = nz >> 16;
+    const u64 eqh = ~nonzero_lsb(x ^ (x >> 4)) & nz;
+    const u64 eqv = ~nonzero_lsb(x ^ (x >> 16)) & nz;
+    const u64 left = ((~nz & nzr) | eqh) & H;
+    const u64 right = ((nz & ~nzr) | eqh) & H;
+    const u64 up = ((~nz & nzd) | eqv) & V;
+    const u64 down = ((nz & ~nzd) | eqv) & V;
+    return (left ? 1u : 0u) | (up ? 2u : 0u) | (right ? 4u : 0u) | (down ? 8u : 0u);
+}
+
+// index (0-based cell) of the k-th (1-based) set flag of `flags` (nibble-lsb flags), branch free
+__device__ __forceinline__ int kth_flag_cell(u64 flags, int k) {
+    uint32_t lo = (uint32_t)flags, hi = (uint32_t)(flags >> 32);
+    int base = 0;
+    int c = __popc(lo);
+    uint32_t w = lo;
+    if (k > c) { k -= c; w = hi; base = 8; }
+    c = __popc(w & 0xFFFFu);
+    if (k > c) { k -= c; w >>= 16; base += 4; }
+    c = __popc(w & 0xFFu);
+    if (k > c) { k -= c; w >>= 8; base += 2; }
+    c = (int)(w & 1u);
+    if (k > c) { base += 1; }
+    return base;
+}
+
+// Pgx _add_random_num given the two 32-bit draws behind uniform(k1) and uniform(k2):
+//   pos = choice(arange(16), p=(board==0)) = searchsorted_left(cumsum_f32(empty), n_empty*(1-u))
+//       = the ceil(fl32(n_empty * (1-u)))-th empty cell in row-major order, 1-based;
+//   val = 2 (a 4-tile) iff 1.0f*(1-u') > 0.9f, else 1.
+// With u = f - 1 for f in [1,2): 1 - u = m * 2^-23 exactly, m = 2^23 - (bits >> 9).
+__device__ __forceinline__ u64 spawn_tile(u64 x, uint32_t bits_pos, uint32_t bits_val) {
+    const u64 empties = ~nonzero_lsb(x) & NIB_LSB;
+    const int n_empty = __popcll(empties);
+    const float one_minus_u = __fsub_rn(1.0f, unit_float(bits_pos));
+    const float r = __fmul_rn((float)n_empty, one_minus_u);
+    int k = (int)ceilf(r);
+    // a full board (only reachable through the illegal-action path) leaves searchsorted at cell 0
+    const int cell = (n_empty == 0) ? 0 : kth_flag_cell(empties, k);
+    const uint32_t m_val = 0x800000u - (bits_val >> 9);
+    const u64 val = (m_val > 7549747u) ? 2ull : 1ull;  // m * 2^-23 > 0.9f = 15099494 * 2^-24
+    return (x & ~(0xFull << (4 * cell))) | (val << (4 * cell));
+}
+
+__device__ __forceinline__ uint32_t max_exponent(u64 x) {
+    uint32_t m = 0;
+#pragma unroll
+    for (int i = 0; i < 16; ++i) m = max(m, (uint32_t)(x >> (4 * i)) & 15u);
+    return m;
+}
+
+// Pgx score bookkeeping without per-step rewards: sum over tiles of (e - 1) * 2^e equals the sum of
+// all merge rewards that built the board from spawned 2-tiles; every spawned 4-tile overcounts by 4.
+__device__ __forceinline__ uint32_t board_potential(u64 x) {
+    uint32_t f = 0;
+#pragma unroll
+    for (int i = 0; i < 16; ++i) {
+        const uint32_t e = (uint32_t)(x >> (4 * i)) & 15u;
+        f += e ? ((e - 1u) << e) : 0u;
+    }
+    return f;
+}
+
+}  // namespace g2048

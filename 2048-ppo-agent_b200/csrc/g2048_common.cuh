@@ -1,0 +1,42 @@
+// Shared host-side helpers of libg2048.so: error reporting and launch geometry.
+#pragma once
+#include <cuda_runtime.h>
+
+#include <cstdint>
+#include <cstdio>
+
+#include "../../include/g2048.h"
+
+namespace g2048 {
+
+// last error text for g2048_last_error(); thread_local so concurrent callers do not race
+extern thread_local char g_last_error[512];
+
+inline int fail_arg(const char* what) {
+    snprintf(g_last_error, sizeof(g_last_error), "g2048: invalid argument: %s", what);
+    return G2048_ERR_INVALID;
+}
+
+inline int check_cuda(cudaError_t e, const char* where) {
+    if (e == cudaSuccess) return G2048_OK;
+    snprintf(g_last_error, sizeof(g_last_error), "g2048: CUDA error in %s: %s", where, cudaGetErrorString(e));
+    return (int)e;
+}
+
+#define G2048_CHECK_LAUNCH(where) \
+    do { int _rc = ::g2048::check_cuda(cudaGetLastError(), where); if (_rc) return _rc; } while (0)
+
+#define G2048_REQUIRE(cond, what) \
+    do { if (!(cond)) return ::g2048::fail_arg(what); } while (0)
+
+struct DeviceInfo {
+    int sm_count;
+    int device;
+};
+
+// SM count of the current device (cached per device)
+int sm_count();
+
+inline unsigned blocks_for(int64_t n, int threads) { return (unsigned)((n + threads - 1) / threads); }
+
+}  // namespace g2048

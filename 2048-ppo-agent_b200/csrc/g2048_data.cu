@@ -1,0 +1,422 @@
+// HBM-bound record kernels: one-hot observation expansion, (T,B) -> (B,T) unpacking, the ragged
+// env-major compaction of RolloutBuffer.store_batch, and the small reductions around them.
+// Every kernel streams: coalesced reads, 128-bit coalesced stores, no re-reads.
+#include <cuda_bf16.h>
+
+#include "g2048_common.cuh"
+
+namespace g2048 {
+
+typedef unsigned long long u64;
+
+// ------------------------------------------------------------------------------------------------
+// one-hot observation: (n,16,31) of T.  One thread writes one 16-byte chunk; a chunk of V elements
+// (V <= 16 < 31) overlaps at most two cells, so it holds at most two ones.
+// Algorithmic bytes per board: 8 read + 496*sizeof(T) written (f32: 1992 B).
+// ------------------------------------------------------------------------------------------------
+template <typename T> struct OneHotChunk;
+
+template <> struct OneHotChunk<float> {
+    static constexpr int V = 4;
+    __device__ static uint4 make(int rel0, int rel1) {
+        const uint32_t one = 0x3F800000u;
+        uint4 o;
+        o.x = (rel0 == 0 || rel1 == 0) ? one : 0u;
+        o.y = (rel0 == 1 || rel1 == 1) ? one : 0u;
+        o.z = (rel0 == 2 || rel1 == 2) ? one : 0u;
+        o.w = (rel0 == 3 || rel1 == 3) ? one : 0u;
+        return o;
+    }
+};
+
+template <> struct OneHotChunk<__nv_bfloat16> {
+    static constexpr int V = 8;
+    __device__ static uint32_t word(int rel, int w) {
+        return ((rel >> 1) == w) ? (0x3F80u << (16 * (rel & 1))) : 0u;  // rel < 0 never matches w >= 0
+    }
+    __device__ static uint4 make(int rel0, int rel1) {
+        uint4 o;
+        o.x = word(rel0, 0) | word(rel1, 0);
+        o.y = word(rel0, 1) | word(rel1, 1);
+        o.z = word(rel0, 2) | word(rel1, 2);
+        o.w = word(rel0, 3) | word(rel1, 3);
+        return o;
+    }
+};
+
+template <> struct OneHotChunk<uint8_t> {
+    static constexpr int V = 16;
+    __device__ static uint32_t word(int rel, int w) { return ((rel >> 2) == w) ? (1u << (8 * (rel & 3))) : 0u; }
+    __device__ static uint4 make(int rel0, int rel1) {
+        uint4 o;
+        o.x = word(rel0, 0) | word(rel1, 0);
+        o.y = word(rel0, 1) | word(rel1, 1);
+        o.z = word(rel0, 2) | word(rel1, 2);
+        o.w = word(rel0, 3) | word(rel1, 3);
+        return o;
+    }
+};
+
+template <typename T>
+__global__ void __launch_bounds__(256)
+expand_obs_kernel(const u64* __restrict__ boards, int64_t n, uint4* __restrict__ out, int64_t rows, int64_t n_cols) {
+    constexpr int V = OneHotChunk<T>::V;
+    constexpr int CPB = 496 / V;  // chunks per board
+    const int64_t total = n * CPB;
+    for (int64_t g = (int64_t)blockIdx.x * blockDim.x + threadIdx.x; g < total; g += (int64_t)gridDim.x * blockDim.x) {
+        const int64_t bi = g / CPB;
+        const int q = (int)(g - bi * CPB);
+        int64_t src = bi;
+        if (rows > 0) {  // out is env-major (col, row); records are time-major (row, col)
+            const int64_t col = bi / rows;
+            const int64_t row = bi - col * rows;
+            src = row * n_cols + col;
+        }
+        const u64 b = __ldg(&boards[src]);
+        const int j0 = q * V;
+        const int c0 = j0 / 31;
+        const int e0 = (int)(b >> (4 * c0)) & 15;
+        const int c1 = min(c0 + 1, 15);
+        const int e1 = (int)(b >> (4 * c1)) & 15;
+        int rel0 = 31 * c0 + e0 - j0;
+        int rel1 = (c0 < 15) ? (31 * (c0 + 1) + e1 - j0) : -1;
+        if (rel0 < 0 || rel0 >= V) rel0 = -64;
+        if (rel1 < 0 || rel1 >= V) rel1 = -64;
+        __stcs(&out[g], OneHotChunk<T>::make(rel0, rel1));
+    }
+}
+
+// ------------------------------------------------------------------------------------------------
+// (T,B) time-major records -> (B,T) env-major reference arrays, 32x32 tiles through shared memory
+// so that both the reads (along B) and the writes (along T) are coalesced.
+// ------------------------------------------------------------------------------------------------
+__global__ void __launch_bounds__(256)
+unpack_records_kernel(const uint8_t* __restrict__ meta, const float* __restrict__ rewards,
+                      const float* __restrict__ log_probs, const float* __restrict__ values, int64_t t_steps, int64_t n,
+                      int32_t* __restrict__ o_actions, uchar4* __restrict__ o_masks, uint8_t* __restrict__ o_term,
+                      float* __restrict__ o_rewards, float* __restrict__ o_log_probs, float* __restrict__ o_values) {
+    __shared__ uint8_t s_meta[32][33];
+    __shared__ float s_r[32][33], s_lp[32][33], s_v[32][33];
+    const int64_t e0 = (int64_t)blockIdx.x * 32, t0 = (int64_t)blockIdx.y * 32;
+    const int tx = threadIdx.x & 31, ty = threadIdx.x >> 5;  // 32 x 8
+    for (int k = ty; k < 32; k += 8) {
+        const int64_t t = t0 + k, e = e0 + tx;
+        if (t < t_steps && e < n) {
+            const int64_t i = t * n + e;
+            s_meta[k][tx] = meta ? meta[i] : 0;
+            if (rewards) s_r[k][tx] = rewards[i];
+            if (log_probs) s_lp[k][tx] = log_probs[i];
+            if (values) s_v[k][tx] = values[i];
+        }
+    }
+    __syncthreads();
+    for (int k = ty; k < 32; k += 8) {
+        const int64_t e = e0 + k, t = t0 + tx;
+        if (t < t_steps && e < n) {
+            const int64_t o = e * t_steps + t;
+            const uint32_t m = s_meta[tx][k];
+            if (o_actions) o_actions[o] = (int32_t)(m & 3u);
+            if (o_masks) o_masks[o] = make_uchar4((m >> 2) & 1u, (m >> 3) & 1u, (m >> 4) & 1u, (m >> 5) & 1u);
+            if (o_term) o_term[o] = (uint8_t)((m >> 6) & 1u);
+            if (o_rewards && rewards) o_rewards[o] = s_r[tx][k];
+            if (o_log_probs && log_probs) o_log_probs[o] = s_lp[tx][k];
+            if (o_values && values) o_values[o] = s_v[tx][k];
+        }
+    }
+}
+
+// first done + 1 per env, 0 if the env never terminated within t_steps (rollout_buffer.py:168-175)
+__global__ void __launch_bounds__(256)
+episode_lengths_kernel(const uint8_t* __restrict__ meta, int64_t t_steps, int64_t n, uint32_t* __restrict__ lengths) {
+    const int64_t e = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
+    if (e >= n) return;
+    uint32_t len = 0;
+    for (int64_t t = 0; t < t_steps; ++t) {
+        if (meta[t * n + e] & 0x40u) {
+            len = (uint32_t)t + 1u;
+            break;
+        }
+    }
+    lengths[e] = len;
+}
+
+// single-CTA exclusive scan (n + 1 outputs).  B is at most a few million: not a hot kernel.
+__global__ void __launch_bounds__(1024)
+exclusive_scan_kernel(const uint32_t* __restrict__ in, int64_t n, long long* __restrict__ out) {
+    __shared__ long long s_warp[32];
+    __shared__ long long s_carry;
+    if (threadIdx.x == 0) s_carry = 0;
+    __syncthreads();
+    const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
+    for (int64_t base = 0; base < n; base += 1024) {
+        const int64_t i = base + threadIdx.x;
+        const long long x = (i < n) ? (long long)in[i] : 0;
+        long long incl = x;
+        for (int off = 1; off < 32; off <<= 1) {
+            const long long y = __shfl_up_sync(0xFFFFFFFFu, incl, off);
+            if (lane >= off) incl += y;
+        }
+        if (lane == 31) s_warp[warp] = incl;
+        __syncthreads();
+        if (warp == 0) {
+            long long w = s_warp[lane];
+            for (int off = 1; off < 32; off <<= 1) {
+                const long long y = __shfl_up_sync(0xFFFFFFFFu, w, off);
+                if (lane >= off) w += y;
+            }
+            s_warp[lane] = w;  // inclusive over warps
+        }
+        __syncthreads();
+        const long long carry = s_carry;
+        const long long before = carry + (warp ? s_warp[warp - 1] : 0) + incl - x;
+        if (i < n) out[i] = before;
+        __syncthreads();
+        if (threadIdx.x == 1023) s_carry = before + x;
+        __syncthreads();
+    }
+    if (threadIdx.x == 0) out[n] = s_carry;
+}
+
+// ragged compaction: flat[out_base + offsets[e] + t] = rec[t][e] for t < lengths[e]
+__global__ void __launch_bounds__(256)
+compact_records_kernel(const u64* __restrict__ rec_boards, const uint8_t* __restrict__ rec_meta,
+                       const float* __restrict__ rec_rewards, const float* __restrict__ rec_log_probs,
+                       const float* __restrict__ rec_values, int64_t t_steps, int64_t n,
+                       const uint32_t* __restrict__ lengths, const long long* __restrict__ offsets, int64_t out_base,
+                       u64* __restrict__ boards, uint8_t* __restrict__ meta, float* __restrict__ rewards,
+                       float* __restrict__ log_probs, float* __restrict__ values) {
+    const int64_t e = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
+    if (e >= n) return;
+    const int64_t len = lengths[e];
+    const int64_t t_begin = (int64_t)blockIdx.y * 32;
+    const int64_t t_end = min(min(t_begin + 32, t_steps), len);
+    const int64_t dst0 = out_base + offsets[e];
+    for (int64_t t = t_begin; t < t_end; ++t) {
+        const int64_t i = t * n + e, o = dst0 + t;
+        if (boards) boards[o] = rec_boards[i];
+        if (meta) meta[o] = rec_meta[i];
+        if (rewards) rewards[o] = rec_rewards[i];
+        if (log_probs && rec_log_probs) log_probs[o] = rec_log_probs[i];
+        if (values && rec_values) values[o] = rec_values[i];
+    }
+}
+
+__global__ void __launch_bounds__(256)
+unpack_flat_meta_kernel(const uint8_t* __restrict__ meta, int64_t n, float4* __restrict__ actions_onehot,
+                        uchar4* __restrict__ masks, uint8_t* __restrict__ term) {
+    const int64_t i = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
+    if (i >= n) return;
+    const uint32_t m = meta[i];
+    const uint32_t a = m & 3u;
+    if (actions_onehot)
+        actions_onehot[i] = make_float4(a == 0 ? 1.f : 0.f, a == 1 ? 1.f : 0.f, a == 2 ? 1.f : 0.f, a == 3 ? 1.f : 0.f);
+    if (masks) masks[i] = make_uchar4((m >> 2) & 1u, (m >> 3) & 1u, (m >> 4) & 1u, (m >> 5) & 1u);
+    if (term) term[i] = (uint8_t)((m >> 6) & 1u);
+}
+
+// status byte -> pgx State fields: legal_action_mask (n,4) and terminated (n)
+__global__ void __launch_bounds__(256)
+unpack_status_kernel(const uint8_t* __restrict__ status, int64_t n, uchar4* __restrict__ masks,
+                     uint8_t* __restrict__ term) {
+    const int64_t i = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
+    if (i >= n) return;
+    const uint32_t m = status[i];
+    if (masks) masks[i] = make_uchar4(m & 1u, (m >> 1) & 1u, (m >> 2) & 1u, (m >> 3) & 1u);
+    if (term) term[i] = (uint8_t)((m >> 4) & 1u);
+}
+
+// one-hot observation (n,16,31) -> bitboard: the inverse of expand_obs, i.e. the
+// `observations.argmax(-1)` of src/runs/run_actions_max_tile.py:61-63.  One thread per cell,
+// 16 consecutive lanes assemble one board with shuffles.
+template <typename T>
+__global__ void __launch_bounds__(256)
+pack_obs_kernel(const T* __restrict__ obs, int64_t n, u64* __restrict__ boards) {
+    const int64_t g = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;  // cell index
+    const int64_t total = n * 16;
+    u64 part = 0;
+    if (g < total) {
+        const T* cell = obs + g * 31;
+        int best = 0;
+        float best_v = (float)cell[0];
+        for (int c = 1; c < 31; ++c) {
+            const float v = (float)cell[c];
+            if (v > best_v) {  // argmax, first index on ties
+                best_v = v;
+                best = c;
+            }
+        }
+        part = (u64)(best & 15) << (4 * (int)(g & 15));
+    }
+    for (int off = 8; off > 0; off >>= 1) part |= __shfl_xor_sync(0xFFFFFFFFu, part, off);
+    if (g < total && (g & 15) == 0) boards[g >> 4] = part;
+}
+
+// per feature row: (count, mean, population variance) in fp64, two passes like numpy's mean / var
+__global__ void __launch_bounds__(1024)
+row_moments_kernel(const double* __restrict__ x, int64_t n, double* __restrict__ out) {
+    __shared__ double s_red[32];
+    __shared__ double s_mean;
+    const double* row = x + (int64_t)blockIdx.x * n;
+    const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
+    auto block_sum = [&](double v) -> double {
+        for (int off = 16; off > 0; off >>= 1) v += __shfl_down_sync(0xFFFFFFFFu, v, off);
+        __syncthreads();
+        if (lane == 0) s_red[warp] = v;
+        __syncthreads();
+        double t = 0.0;
+        if (warp == 0) {
+            t = s_red[lane];
+            for (int off = 16; off > 0; off >>= 1) t += __shfl_down_sync(0xFFFFFFFFu, t, off);
+        }
+        return t;  // valid in thread 0
+    };
+    double acc = 0.0;
+    for (int64_t i = threadIdx.x; i < n; i += blockDim.x) acc += row[i];
+    const double total = block_sum(acc);
+    if (threadIdx.x == 0) s_mean = total / (double)n;
+    __syncthreads();
+    const double mean = s_mean;
+    acc = 0.0;
+    for (int64_t i = threadIdx.x; i < n; i += blockDim.x) {
+        const double d = row[i] - mean;
+        acc += d * d;
+    }
+    const double ss = block_sum(acc);
+    if (threadIdx.x == 0) {
+        out[3 * blockIdx.x + 0] = (double)n;
+        out[3 * blockIdx.x + 1] = mean;
+        out[3 * blockIdx.x + 2] = ss / (double)n;
+    }
+}
+
+}  // namespace g2048
+
+using namespace g2048;
+
+static inline bool aligned16(const void* p) { return ((uintptr_t)p & 15u) == 0; }
+
+extern "C" int g2048_expand_obs(const uint64_t* d_boards, int64_t n, int dtype, void* d_out, int64_t rows,
+                                int64_t n_cols, void* stream) {
+    G2048_REQUIRE(n >= 0 && rows >= 0 && (rows == 0 || (n_cols > 0 && rows * n_cols == n)), "expand_obs: shape");
+    if (n == 0) return G2048_OK;
+    G2048_REQUIRE(d_boards && d_out && aligned16(d_out), "expand_obs: pointers (out must be 16-byte aligned)");
+    const int sms = sm_count();
+    if (sms <= 0) return fail_arg("expand_obs: no device");
+    cudaStream_t st = (cudaStream_t)stream;
+    auto grid_for = [&](int64_t chunks) {
+        int64_t g = (chunks + 255) / 256;
+        const int64_t cap = (int64_t)sms * 8 * 4;  // a few waves of 8 resident CTAs per SM
+        return (unsigned)(g < cap ? g : cap);
+    };
+    switch (dtype) {
+        case G2048_OBS_F32:
+            expand_obs_kernel<float><<<grid_for(n * 124), 256, 0, st>>>((const u64*)d_boards, n, (uint4*)d_out, rows, n_cols);
+            break;
+        case G2048_OBS_BF16:
+            expand_obs_kernel<__nv_bfloat16><<<grid_for(n * 62), 256, 0, st>>>((const u64*)d_boards, n, (uint4*)d_out, rows, n_cols);
+            break;
+        case G2048_OBS_BOOL:
+            expand_obs_kernel<uint8_t><<<grid_for(n * 31), 256, 0, st>>>((const u64*)d_boards, n, (uint4*)d_out, rows, n_cols);
+            break;
+        default:
+            return fail_arg("expand_obs: dtype");
+    }
+    G2048_CHECK_LAUNCH("expand_obs");
+    return G2048_OK;
+}
+
+extern "C" int g2048_unpack_records(const uint8_t* d_rec_meta, const float* d_rec_rewards,
+                                    const float* d_rec_log_probs, const float* d_rec_values, int64_t t_steps, int64_t n,
+                                    int32_t* d_actions, uint8_t* d_masks, uint8_t* d_terminations, float* d_rewards,
+                                    float* d_log_probs, float* d_values, void* stream) {
+    G2048_REQUIRE(t_steps >= 0 && n >= 0, "unpack_records: shape");
+    if (t_steps == 0 || n == 0) return G2048_OK;
+    G2048_REQUIRE(d_rec_meta || !(d_actions || d_masks || d_terminations), "unpack_records: meta");
+    const dim3 grid((unsigned)((n + 31) / 32), (unsigned)((t_steps + 31) / 32));
+    G2048_REQUIRE(grid.y <= 65535u, "unpack_records: too many steps");
+    unpack_records_kernel<<<grid, 256, 0, (cudaStream_t)stream>>>(d_rec_meta, d_rec_rewards, d_rec_log_probs,
+                                                                 d_rec_values, t_steps, n, d_actions, (uchar4*)d_masks,
+                                                                 d_terminations, d_rewards, d_log_probs, d_values);
+    G2048_CHECK_LAUNCH("unpack_records");
+    return G2048_OK;
+}
+
+extern "C" int g2048_episode_lengths(const uint8_t* d_rec_meta, int64_t t_steps, int64_t n, uint32_t* d_lengths,
+                                     void* stream) {
+    G2048_REQUIRE(t_steps >= 0 && n >= 0, "episode_lengths: shape");
+    if (n == 0) return G2048_OK;
+    G2048_REQUIRE(d_lengths && (d_rec_meta || t_steps == 0), "episode_lengths: pointers");
+    episode_lengths_kernel<<<blocks_for(n, 256), 256, 0, (cudaStream_t)stream>>>(d_rec_meta, t_steps, n, d_lengths);
+    G2048_CHECK_LAUNCH("episode_lengths");
+    return G2048_OK;
+}
+
+extern "C" int g2048_exclusive_scan(const uint32_t* d_in, int64_t n, int64_t* d_out, void* stream) {
+    G2048_REQUIRE(n >= 0 && d_out && (d_in || n == 0), "exclusive_scan");
+    exclusive_scan_kernel<<<1, 1024, 0, (cudaStream_t)stream>>>(d_in, n, (long long*)d_out);
+    G2048_CHECK_LAUNCH("exclusive_scan");
+    return G2048_OK;
+}
+
+extern "C" int g2048_compact_records(const uint64_t* d_rec_boards, const uint8_t* d_rec_meta,
+                                     const float* d_rec_rewards, const float* d_rec_log_probs,
+                                     const float* d_rec_values, int64_t t_steps, int64_t n, const uint32_t* d_lengths,
+                                     const int64_t* d_offsets, int64_t out_base, uint64_t* d_boards, uint8_t* d_meta,
+                                     float* d_rewards, float* d_log_probs, float* d_values, void* stream) {
+    G2048_REQUIRE(t_steps >= 0 && n >= 0 && out_base >= 0, "compact_records: shape");
+    if (t_steps == 0 || n == 0) return G2048_OK;
+    G2048_REQUIRE(d_lengths && d_offsets, "compact_records: lengths/offsets");
+    G2048_REQUIRE((!d_boards || d_rec_boards) && (!d_meta || d_rec_meta) && (!d_rewards || d_rec_rewards),
+                  "compact_records: sources");
+    const dim3 grid(blocks_for(n, 256), (unsigned)((t_steps + 31) / 32));
+    G2048_REQUIRE(grid.y <= 65535u, "compact_records: too many steps");
+    compact_records_kernel<<<grid, 256, 0, (cudaStream_t)stream>>>(
+        (const u64*)d_rec_boards, d_rec_meta, d_rec_rewards, d_rec_log_probs, d_rec_values, t_steps, n, d_lengths,
+        (const long long*)d_offsets, out_base, (u64*)d_boards, d_meta, d_rewards, d_log_probs, d_values);
+    G2048_CHECK_LAUNCH("compact_records");
+    return G2048_OK;
+}
+
+extern "C" int g2048_unpack_flat_meta(const uint8_t* d_meta, int64_t n, float* d_actions_onehot, uint8_t* d_masks,
+                                      uint8_t* d_terminations, void* stream) {
+    G2048_REQUIRE(n >= 0, "unpack_flat_meta: n");
+    if (n == 0) return G2048_OK;
+    G2048_REQUIRE(d_meta && (!d_actions_onehot || aligned16(d_actions_onehot)), "unpack_flat_meta: pointers");
+    unpack_flat_meta_kernel<<<blocks_for(n, 256), 256, 0, (cudaStream_t)stream>>>(
+        d_meta, n, (float4*)d_actions_onehot, (uchar4*)d_masks, d_terminations);
+    G2048_CHECK_LAUNCH("unpack_flat_meta");
+    return G2048_OK;
+}
+
+extern "C" int g2048_unpack_status(const uint8_t* d_status, int64_t n, uint8_t* d_masks, uint8_t* d_terminated,
+                                   void* stream) {
+    G2048_REQUIRE(n >= 0, "unpack_status: n");
+    if (n == 0) return G2048_OK;
+    G2048_REQUIRE(d_status, "unpack_status: pointers");
+    unpack_status_kernel<<<blocks_for(n, 256), 256, 0, (cudaStream_t)stream>>>(d_status, n, (uchar4*)d_masks,
+                                                                              d_terminated);
+    G2048_CHECK_LAUNCH("unpack_status");
+    return G2048_OK;
+}
+
+extern "C" int g2048_pack_obs(const void* d_obs, int dtype, int64_t n, uint64_t* d_boards, void* stream) {
+    G2048_REQUIRE(n >= 0, "pack_obs: n");
+    if (n == 0) return G2048_OK;
+    G2048_REQUIRE(d_obs && d_boards, "pack_obs: pointers");
+    const unsigned g = blocks_for(n * 16, 256);
+    cudaStream_t st = (cudaStream_t)stream;
+    if (dtype == G2048_OBS_BOOL) pack_obs_kernel<uint8_t><<<g, 256, 0, st>>>((const uint8_t*)d_obs, n, (u64*)d_boards);
+    else if (dtype == G2048_OBS_F32) pack_obs_kernel<float><<<g, 256, 0, st>>>((const float*)d_obs, n, (u64*)d_boards);
+    else return fail_arg("pack_obs: dtype");
+    G2048_CHECK_LAUNCH("pack_obs");
+    return G2048_OK;
+}
+
+extern "C" int g2048_row_moments(const double* d_x, int64_t n_features, int64_t n, double* d_out, void* stream) {
+    G2048_REQUIRE(n_features >= 0 && n > 0 && n_features <= 0x7FFFFFFF, "row_moments: shape");
+    if (n_features == 0) return G2048_OK;
+    G2048_REQUIRE(d_x && d_out, "row_moments: pointers");
+    row_moments_kernel<<<(unsigned)n_features, 1024, 0, (cudaStream_t)stream>>>(d_x, n, d_out);
+    G2048_CHECK_LAUNCH("row_moments");
+    return G2048_OK;
+}

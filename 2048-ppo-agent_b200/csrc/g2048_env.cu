@@ -1,0 +1,553 @@
+// Env kernels: init, step, built-in policies, the persistent play-to-termination kernel and the
+// lock-step recorded rollout.  All state of an env (board, mask, keys, counters) lives in the
+// registers of the one thread that owns it; HBM sees only records and per-episode results.
+#include "g2048_board.cuh"
+#include "g2048_common.cuh"
+#include "g2048_env.cuh"
+
+namespace g2048 {
+
+thread_local char g_last_error[512] = "";
+
+int sm_count() {
+    static int cached[64] = {0};
+    int dev = 0;
+    if (cudaGetDevice(&dev) != cudaSuccess || dev < 0 || dev >= 64) return -1;
+    if (cached[dev] == 0) {
+        int n = 0;
+        if (cudaDeviceGetAttribute(&n, cudaDevAttrMultiProcessorCount, dev) != cudaSuccess) return -1;
+        cached[dev] = n;
+    }
+    return cached[dev];
+}
+
+// ------------------------------------------------------------------------------------------------
+// small kernels
+// ------------------------------------------------------------------------------------------------
+__global__ void threefry_kernel(const uint2* __restrict__ keys, const uint2* __restrict__ ctrs, int64_t n,
+                                uint2* __restrict__ out) {
+    const int64_t i = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
+    if (i >= n) return;
+    const Key y = threefry2x32(Key{keys[i].x, keys[i].y}, ctrs[i].x, ctrs[i].y);
+    out[i] = make_uint2(y.a, y.b);
+}
+
+// key, sub = split(key), n_sub times.  Sequential by nature; the two children of a split are
+// independent blocks, so one thread has ILP 2.  ~0.3 us per split.
+template <int MODE>
+__global__ void chain_kernel(uint32_t* key_io, int64_t n_sub, uint2* __restrict__ subs) {
+    if (blockIdx.x != 0 || threadIdx.x != 0) return;
+    Key k{key_io[0], key_io[1]};
+    for (int64_t i = 0; i < n_sub; ++i) {
+        Key nk, sub;
+        split2<MODE>(k, nk, sub);
+        subs[i] = make_uint2(sub.a, sub.b);
+        k = nk;
+    }
+    key_io[0] = k.a;
+    key_io[1] = k.b;
+}
+
+template <int MODE>
+__global__ void split_keys_kernel(const uint32_t* __restrict__ sub, uint32_t batch_global, uint32_t env_lo, int64_t n,
+                                  uint2* __restrict__ keys) {
+    const int64_t i = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
+    if (i >= n) return;
+    const Key k = env_key<MODE>(sub, batch_global, env_lo, i);
+    keys[i] = make_uint2(k.a, k.b);
+}
+
+template <int MODE>
+__global__ void env_init_kernel(const uint32_t* __restrict__ sub, uint32_t batch_global, uint32_t env_lo, int64_t n,
+                                u64* __restrict__ boards, uint8_t* __restrict__ status) {
+    const int64_t i = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
+    if (i >= n) return;
+    const Key k = env_key<MODE>(sub, batch_global, env_lo, i);
+    const EnvState s = env_init<MODE>(k);
+    boards[i] = s.board;
+    status[i] = (uint8_t)s.status;
+}
+
+template <int MODE>
+__global__ void env_step_kernel(u64* __restrict__ boards, uint8_t* __restrict__ status,
+                                const int32_t* __restrict__ actions, const uint32_t* __restrict__ sub,
+                                uint32_t batch_global, uint32_t env_lo, int64_t n, float* __restrict__ rewards) {
+    const int64_t i = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
+    if (i >= n) return;
+    EnvState s{boards[i], status[i]};
+    const Key k = env_key<MODE>(sub, batch_global, env_lo, i);
+    const float r = env_step<MODE>(s, actions[i] & 3, k);
+    boards[i] = s.board;
+    status[i] = (uint8_t)s.status;
+    if (rewards) rewards[i] = r;
+}
+
+__global__ void env_step_draws_kernel(u64* __restrict__ boards, uint8_t* __restrict__ status,
+                                      const int32_t* __restrict__ actions, const uint32_t* __restrict__ bits_pos,
+                                      const uint32_t* __restrict__ bits_val, int64_t n, float* __restrict__ rewards) {
+    const int64_t i = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
+    if (i >= n) return;
+    EnvState s{boards[i], status[i]};
+    const float r = env_step_draws(s, actions[i] & 3, bits_pos[i], bits_val[i]);
+    boards[i] = s.board;
+    status[i] = (uint8_t)s.status;
+    if (rewards) rewards[i] = r;
+}
+
+template <int MODE, int POLICY>
+__global__ void act_kernel(const uint8_t* __restrict__ status, const uint32_t* __restrict__ sub, uint32_t batch_global,
+                           uint32_t env_lo, int64_t n, int32_t* __restrict__ actions, float* __restrict__ log_probs) {
+    const int64_t i = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
+    if (i >= n) return;
+    const uint32_t lm = status[i] & G2048_STATUS_MASK;
+    int a;
+    if (POLICY == G2048_POLICY_RANDOM) {
+        const Key k = env_key<MODE>(sub, batch_global, env_lo, i);
+        a = act_random<MODE>(k, lm);
+        if (log_probs) log_probs[i] = act_random_log_prob(lm);
+    } else {
+        a = act_drul(lm);
+    }
+    actions[i] = a;
+}
+
+// ------------------------------------------------------------------------------------------------
+// persistent play-to-termination kernel
+// ------------------------------------------------------------------------------------------------
+// Each lane owns one env at a time and keeps it in registers until it terminates.  Finished lanes
+// park until REFILL_MIN lanes of the warp are free (or the warp has nothing else to do), then the
+// warp claims that many envs from a global queue with one atomic and initialises them together,
+// so the divergent init path is paid once per ~REFILL_MIN episodes instead of once per episode.
+constexpr int PLAY_THREADS = 256;
+constexpr int REFILL_MIN = 6;
+
+template <int MODE, int POLICY>
+__global__ void __launch_bounds__(PLAY_THREADS)
+play_kernel(const uint2* __restrict__ subs, int64_t n_subs, uint32_t batch_global, uint32_t env_lo, uint32_t n,
+            unsigned long long* __restrict__ work, u64* __restrict__ final_boards, uint32_t* __restrict__ lengths,
+            uint32_t* __restrict__ scores, unsigned long long* __restrict__ stats) {
+    __shared__ unsigned long long s_stats[G2048_PLAY_STATS_WORDS];
+    for (int i = threadIdx.x; i < G2048_PLAY_STATS_WORDS; i += blockDim.x) s_stats[i] = 0ull;
+    __syncthreads();
+
+    const unsigned lane = threadIdx.x & 31u;
+    const Key init_sub{subs[0].x, subs[0].y};
+    const uint32_t max_steps = (uint32_t)((n_subs - 1) / 2);
+
+    // per-lane env state
+    EnvState s{0ull, 0u};
+    uint32_t e = 0, t = 0, score = 0;
+    bool active = false;
+    bool exhausted = false;  // warp-uniform: the queue has no more envs
+
+    // per-lane statistics, flushed once at the end
+    uint32_t st_episodes = 0, st_cut = 0, st_ovf = 0, st_longest = 0;
+    unsigned long long st_steps = 0, st_score = 0, st_tile = 0, st_tile2 = 0;
+
+    while (true) {
+        const unsigned idle = __ballot_sync(0xFFFFFFFFu, !active);
+        if (idle) {
+            const int n_idle = __popc(idle);
+            if (!exhausted && (n_idle >= REFILL_MIN || idle == 0xFFFFFFFFu)) {
+                unsigned long long base = 0;
+                if (lane == 0) base = atomicAdd(work, (unsigned long long)n_idle);
+                base = __shfl_sync(0xFFFFFFFFu, base, 0);
+                if (base + (unsigned long long)n_idle >= (unsigned long long)n) exhausted = true;
+                if (!active) {
+                    const unsigned long long mine = base + (unsigned long long)__popc(idle & ((1u << lane) - 1u));
+                    if (mine < (unsigned long long)n) {
+                        e = (uint32_t)mine;
+                        s = env_init<MODE>(split_at<MODE>(init_sub, batch_global, env_lo + e));
+                        t = 0;
+                        score = 0;
+                        active = true;
+                    }
+                }
+            }
+            if (__ballot_sync(0xFFFFFFFFu, active) == 0u) break;  // exhausted and nothing running
+        }
+        if (active) {
+            const uint2 sa = __ldg(&subs[1 + 2 * (int64_t)t]);
+            const uint2 ss = __ldg(&subs[2 + 2 * (int64_t)t]);
+            const uint32_t lm = s.status & G2048_STATUS_MASK;
+            int a;
+            if (POLICY == G2048_POLICY_RANDOM) {
+                a = act_random<MODE>(split_at<MODE>(Key{sa.x, sa.y}, batch_global, env_lo + e), lm);
+            } else {
+                a = act_drul(lm);
+            }
+            const float r = env_step<MODE>(s, a, split_at<MODE>(Key{ss.x, ss.y}, batch_global, env_lo + e));
+            score += (r > 0.0f) ? (uint32_t)r : 0u;
+            ++t;
+            const bool done = (s.status & G2048_STATUS_DONE) != 0u;
+            const bool cut = !done && t >= max_steps;
+            if (done || cut) {
+                if (final_boards) final_boards[e] = s.board;
+                if (lengths) lengths[e] = t;
+                if (scores) scores[e] = score;
+                const uint32_t me = max_exponent(s.board);
+                const unsigned long long tile = 1ull << me;
+                st_episodes += 1;
+                st_steps += t;
+                st_score += score;
+                st_cut += cut ? 1u : 0u;
+                st_ovf += (s.status & G2048_STATUS_OVERFLOW) ? 1u : 0u;
+                st_longest = max(st_longest, t);
+                st_tile += tile;
+                st_tile2 += tile * tile;
+                atomicAdd(&s_stats[16 + me], 1ull);
+                active = false;
+            }
+        }
+    }
+
+    atomicAdd(&s_stats[0], (unsigned long long)st_episodes);
+    atomicAdd(&s_stats[1], st_steps);
+    atomicAdd(&s_stats[2], st_score);
+    atomicAdd(&s_stats[3], (unsigned long long)st_cut);
+    atomicAdd(&s_stats[4], (unsigned long long)st_ovf);
+    atomicMax(&s_stats[5], (unsigned long long)st_longest);
+    atomicAdd(&s_stats[6], st_tile);
+    atomicAdd(&s_stats[7], st_tile2);
+    __syncthreads();
+    for (int i = threadIdx.x; i < G2048_PLAY_STATS_WORDS; i += blockDim.x) {
+        const unsigned long long v = s_stats[i];
+        if (v) {
+            if (i == 5) atomicMax(&stats[i], v);
+            else atomicAdd(&stats[i], v);
+        }
+    }
+}
+
+// ------------------------------------------------------------------------------------------------
+// lock-step recorded rollout (trajectory mode)
+// ------------------------------------------------------------------------------------------------
+template <int MODE, int POLICY>
+__global__ void __launch_bounds__(256)
+rollout_steps_kernel(u64* __restrict__ boards, uint8_t* __restrict__ status, const uint2* __restrict__ subs,
+                     int n_steps, uint32_t t0, uint32_t batch_global, uint32_t env_lo, int64_t n,
+                     u64* __restrict__ rec_boards, uint8_t* __restrict__ rec_meta, float* __restrict__ rec_rewards,
+                     float* __restrict__ rec_log_probs, unsigned long long* __restrict__ counters) {
+    const int64_t i = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
+    if (i >= n) return;
+    EnvState s{boards[i], status[i]};
+    const uint32_t e = env_lo + (uint32_t)i;
+    unsigned long long live_steps = 0, reward_sum = 0;
+    for (int t = 0; t < n_steps; ++t) {
+        const uint2 sa = __ldg(&subs[2 * t]);
+        const uint2 ss = __ldg(&subs[2 * t + 1]);
+        const uint32_t lm = s.status & G2048_STATUS_MASK;
+        const bool was_done = (s.status & G2048_STATUS_DONE) != 0u;
+        int a;
+        float lp = 0.0f;
+        if (POLICY == G2048_POLICY_RANDOM) {
+            a = act_random<MODE>(split_at<MODE>(Key{sa.x, sa.y}, batch_global, e), lm);
+            lp = act_random_log_prob(lm);
+        } else {
+            a = act_drul(lm);
+        }
+        const u64 pre = s.board;
+        const float r = env_step<MODE>(s, a, split_at<MODE>(Key{ss.x, ss.y}, batch_global, e));
+        const bool done = (s.status & G2048_STATUS_DONE) != 0u;
+        const int64_t o = (int64_t)t * n + i;
+        rec_boards[o] = pre;
+        rec_meta[o] = (uint8_t)((uint32_t)a | (lm << 2) | (done ? 0x40u : 0u));
+        rec_rewards[o] = r;
+        if (rec_log_probs) rec_log_probs[o] = lp;
+        if (!was_done) {
+            live_steps += 1;
+            if (r > 0.0f) reward_sum += (unsigned long long)r;
+            if (done) {
+                atomicAdd(&counters[0], 1ull);
+                atomicMax(&counters[1], (unsigned long long)(t0 + (uint32_t)t + 1u));
+            }
+        }
+    }
+    boards[i] = s.board;
+    status[i] = (uint8_t)s.status;
+    // warp-aggregate the two sums
+    for (int off = 16; off > 0; off >>= 1) {
+        live_steps += __shfl_down_sync(0xFFFFFFFFu, live_steps, off);
+        reward_sum += __shfl_down_sync(0xFFFFFFFFu, reward_sum, off);
+    }
+    if ((threadIdx.x & 31) == 0) {
+        if (live_steps) atomicAdd(&counters[2], live_steps);
+        if (reward_sum) atomicAdd(&counters[3], reward_sum);
+    }
+}
+
+// ------------------------------------------------------------------------------------------------
+// integer-issue probe
+// ------------------------------------------------------------------------------------------------
+__global__ void int_peak_kernel(int iters, uint32_t* __restrict__ sink) {
+    uint32_t a0 = threadIdx.x, b0 = blockIdx.x + 1u, a1 = a0 ^ 0x9E3779B9u, b1 = b0 + 0x7F4A7C15u;
+    uint32_t a2 = a0 + 17u, b2 = b0 ^ 0x85EBCA6Bu, a3 = a1 + 29u, b3 = b1 ^ 0xC2B2AE35u;
+#pragma unroll 1
+    for (int i = 0; i < iters; ++i) {
+#define G2048_MIX(a, b, r) a += b; b = rotl32(b, r); b ^= a;
+        G2048_MIX(a0, b0, 13) G2048_MIX(a1, b1, 13) G2048_MIX(a2, b2, 13) G2048_MIX(a3, b3, 13)
+        G2048_MIX(a0, b0, 15) G2048_MIX(a1, b1, 15) G2048_MIX(a2, b2, 15) G2048_MIX(a3, b3, 15)
+        G2048_MIX(a0, b0, 26) G2048_MIX(a1, b1, 26) G2048_MIX(a2, b2, 26) G2048_MIX(a3, b3, 26)
+        G2048_MIX(a0, b0, 6) G2048_MIX(a1, b1, 6) G2048_MIX(a2, b2, 6) G2048_MIX(a3, b3, 6)
+#undef G2048_MIX
+    }
+    sink[(size_t)blockIdx.x * blockDim.x + threadIdx.x] = a0 ^ b0 ^ a1 ^ b1 ^ a2 ^ b2 ^ a3 ^ b3;
+}
+
+}  // namespace g2048
+
+// =================================================================================================
+// C ABI
+// =================================================================================================
+using namespace g2048;
+
+#define DISPATCH_MODE(rng_mode, CALL)                                   \
+    if ((rng_mode) == G2048_RNG_PARTITIONABLE) { CALL(G2048_RNG_PARTITIONABLE); } \
+    else { CALL(G2048_RNG_ORIGINAL); }
+
+static inline bool valid_mode(int m) { return m == G2048_RNG_ORIGINAL || m == G2048_RNG_PARTITIONABLE; }
+static inline bool valid_batch(int64_t batch_global, int64_t env_lo, int64_t n) {
+    return batch_global > 0 && batch_global <= 0x7FFFFFFFll && env_lo >= 0 && n >= 0 && env_lo + n <= batch_global;
+}
+// batch_global == 0: d_sub is an explicit (n,2) key array
+static inline bool valid_batch_or_keys(int64_t batch_global, int64_t env_lo, int64_t n) {
+    return (batch_global == 0 && env_lo == 0 && n >= 0) || valid_batch(batch_global, env_lo, n);
+}
+
+extern "C" int g2048_version(void) { return 100; }
+extern "C" const char* g2048_last_error(void) { return g_last_error; }
+extern "C" int g2048_device_sm_count(void) { return sm_count(); }
+
+extern "C" int g2048_threefry2x32(const uint32_t* d_keys, const uint32_t* d_ctrs, int64_t n, uint32_t* d_out,
+                                  void* stream) {
+    G2048_REQUIRE(n >= 0 && (n == 0 || (d_keys && d_ctrs && d_out)), "threefry2x32");
+    if (n == 0) return G2048_OK;
+    threefry_kernel<<<blocks_for(n, 256), 256, 0, (cudaStream_t)stream>>>((const uint2*)d_keys, (const uint2*)d_ctrs, n,
+                                                                         (uint2*)d_out);
+    G2048_CHECK_LAUNCH("threefry2x32");
+    return G2048_OK;
+}
+
+extern "C" int g2048_chain_advance(uint32_t* d_key_io, int rng_mode, int64_t n_sub, uint32_t* d_subs, void* stream) {
+    G2048_REQUIRE(d_key_io && valid_mode(rng_mode) && n_sub >= 0 && (n_sub == 0 || d_subs), "chain_advance");
+    if (n_sub == 0) return G2048_OK;
+#define CALL(M) chain_kernel<M><<<1, 32, 0, (cudaStream_t)stream>>>(d_key_io, n_sub, (uint2*)d_subs)
+    DISPATCH_MODE(rng_mode, CALL)
+#undef CALL
+    G2048_CHECK_LAUNCH("chain_advance");
+    return G2048_OK;
+}
+
+extern "C" int g2048_split_keys(const uint32_t* d_sub, int64_t batch_global, int64_t env_lo, int64_t n, int rng_mode,
+                                uint32_t* d_keys, void* stream) {
+    G2048_REQUIRE(d_sub && valid_mode(rng_mode) && valid_batch_or_keys(batch_global, env_lo, n), "split_keys");
+    if (n == 0) return G2048_OK;
+    G2048_REQUIRE(d_keys, "split_keys: d_keys");
+#define CALL(M)                                                                                         \
+    split_keys_kernel<M><<<blocks_for(n, 256), 256, 0, (cudaStream_t)stream>>>(d_sub, (uint32_t)batch_global, \
+                                                                              (uint32_t)env_lo, n, (uint2*)d_keys)
+    DISPATCH_MODE(rng_mode, CALL)
+#undef CALL
+    G2048_CHECK_LAUNCH("split_keys");
+    return G2048_OK;
+}
+
+extern "C" int g2048_env_init(const uint32_t* d_sub, int64_t batch_global, int64_t env_lo, int64_t n, int rng_mode,
+                              uint64_t* d_boards, uint8_t* d_status, void* stream) {
+    G2048_REQUIRE(d_sub && valid_mode(rng_mode) && valid_batch_or_keys(batch_global, env_lo, n), "env_init");
+    if (n == 0) return G2048_OK;
+    G2048_REQUIRE(d_boards && d_status, "env_init: outputs");
+#define CALL(M)                                                                                        \
+    env_init_kernel<M><<<blocks_for(n, 256), 256, 0, (cudaStream_t)stream>>>(d_sub, (uint32_t)batch_global,  \
+                                                                            (uint32_t)env_lo, n, (u64*)d_boards, d_status)
+    DISPATCH_MODE(rng_mode, CALL)
+#undef CALL
+    G2048_CHECK_LAUNCH("env_init");
+    return G2048_OK;
+}
+
+extern "C" int g2048_env_step(uint64_t* d_boards, uint8_t* d_status, const int32_t* d_actions, const uint32_t* d_sub,
+                              int64_t batch_global, int64_t env_lo, int64_t n, int rng_mode, float* d_rewards,
+                              void* stream) {
+    G2048_REQUIRE(d_sub && valid_mode(rng_mode) && valid_batch_or_keys(batch_global, env_lo, n), "env_step");
+    if (n == 0) return G2048_OK;
+    G2048_REQUIRE(d_boards && d_status && d_actions, "env_step: state/actions");
+#define CALL(M)                                                                                         \
+    env_step_kernel<M><<<blocks_for(n, 256), 256, 0, (cudaStream_t)stream>>>(                            \
+        (u64*)d_boards, d_status, d_actions, d_sub, (uint32_t)batch_global, (uint32_t)env_lo, n, d_rewards)
+    DISPATCH_MODE(rng_mode, CALL)
+#undef CALL
+    G2048_CHECK_LAUNCH("env_step");
+    return G2048_OK;
+}
+
+extern "C" int g2048_env_step_draws(uint64_t* d_boards, uint8_t* d_status, const int32_t* d_actions,
+                                    const uint32_t* d_bits_pos, const uint32_t* d_bits_val, int64_t n,
+                                    float* d_rewards, void* stream) {
+    G2048_REQUIRE(n >= 0, "env_step_draws: n");
+    if (n == 0) return G2048_OK;
+    G2048_REQUIRE(d_boards && d_status && d_actions && d_bits_pos && d_bits_val, "env_step_draws: pointers");
+    env_step_draws_kernel<<<blocks_for(n, 256), 256, 0, (cudaStream_t)stream>>>((u64*)d_boards, d_status, d_actions,
+                                                                               d_bits_pos, d_bits_val, n, d_rewards);
+    G2048_CHECK_LAUNCH("env_step_draws");
+    return G2048_OK;
+}
+
+extern "C" int g2048_act(int policy, const uint8_t* d_status, const uint32_t* d_sub, int64_t batch_global,
+                         int64_t env_lo, int64_t n, int rng_mode, int32_t* d_actions, float* d_log_probs,
+                         void* stream) {
+    G2048_REQUIRE(policy == G2048_POLICY_RANDOM || policy == G2048_POLICY_DRUL, "act: policy");
+    G2048_REQUIRE(valid_mode(rng_mode) && valid_batch_or_keys(batch_global, env_lo, n), "act");
+    if (n == 0) return G2048_OK;
+    G2048_REQUIRE(d_status && d_actions && (policy == G2048_POLICY_DRUL || d_sub), "act: pointers");
+    const unsigned g = blocks_for(n, 256);
+    cudaStream_t st = (cudaStream_t)stream;
+    if (policy == G2048_POLICY_RANDOM) {
+#define CALL(M) act_kernel<M, G2048_POLICY_RANDOM><<<g, 256, 0, st>>>(d_status, d_sub, (uint32_t)batch_global, (uint32_t)env_lo, n, d_actions, d_log_probs)
+        DISPATCH_MODE(rng_mode, CALL)
+#undef CALL
+    } else {
+        act_kernel<G2048_RNG_PARTITIONABLE, G2048_POLICY_DRUL><<<g, 256, 0, st>>>(d_status, d_sub, (uint32_t)batch_global,
+                                                                                 (uint32_t)env_lo, n, d_actions, nullptr);
+    }
+    G2048_CHECK_LAUNCH("act");
+    return G2048_OK;
+}
+
+template <int MODE, int POLICY>
+static int launch_play(const uint32_t* d_subs, int64_t n_subs, int64_t batch_global, int64_t env_lo, int64_t n,
+                       uint64_t* d_work, uint64_t* d_final_boards, uint32_t* d_lengths, uint32_t* d_scores,
+                       uint64_t* d_stats, cudaStream_t st) {
+    int per_sm = 0;
+    int rc = check_cuda(cudaOccupancyMaxActiveBlocksPerMultiprocessor(&per_sm, play_kernel<MODE, POLICY>, PLAY_THREADS, 0),
+                        "play: occupancy");
+    if (rc) return rc;
+    const int sms = sm_count();
+    if (sms <= 0 || per_sm <= 0) return fail_arg("play: no device");
+    int64_t grid = (int64_t)sms * per_sm;
+    const int64_t needed = (n + PLAY_THREADS - 1) / PLAY_THREADS;
+    if (grid > needed) grid = needed;
+    play_kernel<MODE, POLICY><<<(unsigned)grid, PLAY_THREADS, 0, st>>>(
+        (const uint2*)d_subs, n_subs, (uint32_t)batch_global, (uint32_t)env_lo, (uint32_t)n,
+        (unsigned long long*)d_work, (u64*)d_final_boards, d_lengths, d_scores, (unsigned long long*)d_stats);
+    return check_cuda(cudaGetLastError(), "play");
+}
+
+extern "C" int g2048_play(int policy, const uint32_t* d_subs, int64_t n_subs, int64_t batch_global, int64_t env_lo,
+                          int64_t n, int rng_mode, uint64_t* d_work, uint64_t* d_final_boards, uint32_t* d_lengths,
+                          uint32_t* d_scores, uint64_t* d_stats, void* stream) {
+    G2048_REQUIRE(policy == G2048_POLICY_RANDOM || policy == G2048_POLICY_DRUL, "play: policy");
+    G2048_REQUIRE(valid_mode(rng_mode) && valid_batch(batch_global, env_lo, n), "play: batch");
+    G2048_REQUIRE(n_subs >= 3 && d_subs && d_work && d_stats, "play: pointers");
+    if (n == 0) return G2048_OK;
+    cudaStream_t st = (cudaStream_t)stream;
+#define ARGS d_subs, n_subs, batch_global, env_lo, n, d_work, d_final_boards, d_lengths, d_scores, d_stats, st
+    if (policy == G2048_POLICY_RANDOM) {
+        if (rng_mode == G2048_RNG_PARTITIONABLE) return launch_play<G2048_RNG_PARTITIONABLE, G2048_POLICY_RANDOM>(ARGS);
+        return launch_play<G2048_RNG_ORIGINAL, G2048_POLICY_RANDOM>(ARGS);
+    }
+    if (rng_mode == G2048_RNG_PARTITIONABLE) return launch_play<G2048_RNG_PARTITIONABLE, G2048_POLICY_DRUL>(ARGS);
+    return launch_play<G2048_RNG_ORIGINAL, G2048_POLICY_DRUL>(ARGS);
+#undef ARGS
+}
+
+extern "C" int g2048_play_host(int policy, uint64_t seed, uint32_t* h_key_io, int64_t batch_global, int64_t env_lo,
+                               int64_t n, int rng_mode, uint64_t* h_final_boards, uint32_t* h_lengths,
+                               uint32_t* h_scores, uint64_t* h_stats) {
+    G2048_REQUIRE(policy == G2048_POLICY_RANDOM || policy == G2048_POLICY_DRUL, "play_host: policy");
+    G2048_REQUIRE(valid_mode(rng_mode) && valid_batch(batch_global, env_lo, n), "play_host: batch");
+    uint32_t key[2] = {(uint32_t)(seed >> 32), (uint32_t)(seed & 0xFFFFFFFFull)};
+    if (h_key_io) { key[0] = h_key_io[0]; key[1] = h_key_io[1]; }
+
+    int rc = G2048_OK;
+    cudaStream_t st = nullptr;
+    uint32_t* d_key = nullptr;
+    uint32_t* d_subs = nullptr;
+    uint64_t *d_work = nullptr, *d_stats = nullptr, *d_boards = nullptr;
+    uint32_t *d_len = nullptr, *d_score = nullptr;
+    uint64_t stats[G2048_PLAY_STATS_WORDS];
+    int64_t max_steps = 2048;  // grown on demand
+#define TRY(expr, where) do { rc = check_cuda((expr), where); if (rc) goto done; } while (0)
+    TRY(cudaStreamCreateWithFlags(&st, cudaStreamNonBlocking), "play_host: stream");
+    TRY(cudaMalloc(&d_key, 2 * sizeof(uint32_t)), "play_host: malloc");
+    TRY(cudaMalloc(&d_work, 2 * sizeof(uint64_t)), "play_host: malloc");
+    TRY(cudaMalloc(&d_stats, sizeof(stats)), "play_host: malloc");
+    if (h_final_boards && n) TRY(cudaMalloc(&d_boards, n * sizeof(uint64_t)), "play_host: malloc");
+    if (h_lengths && n) TRY(cudaMalloc(&d_len, n * sizeof(uint32_t)), "play_host: malloc");
+    if (h_scores && n) TRY(cudaMalloc(&d_score, n * sizeof(uint32_t)), "play_host: malloc");
+    while (true) {
+        const int64_t n_subs = 1 + 2 * max_steps;
+        TRY(cudaMalloc(&d_subs, n_subs * 2 * sizeof(uint32_t)), "play_host: malloc subs");
+        TRY(cudaMemcpyAsync(d_key, key, sizeof(key), cudaMemcpyHostToDevice, st), "play_host: h2d key");
+        TRY(cudaMemsetAsync(d_work, 0, 2 * sizeof(uint64_t), st), "play_host: memset");
+        TRY(cudaMemsetAsync(d_stats, 0, sizeof(stats), st), "play_host: memset");
+        rc = g2048_chain_advance(d_key, rng_mode, n_subs, d_subs, st);
+        if (rc) goto done;
+        rc = g2048_play(policy, d_subs, n_subs, batch_global, env_lo, n, rng_mode, d_work, d_boards, d_len, d_score,
+                        d_stats, st);
+        if (rc) goto done;
+        TRY(cudaMemcpyAsync(stats, d_stats, sizeof(stats), cudaMemcpyDeviceToHost, st), "play_host: d2h stats");
+        TRY(cudaStreamSynchronize(st), "play_host: sync");
+        if (stats[3] == 0 || max_steps >= (1 << 20)) break;
+        cudaFree(d_subs);
+        d_subs = nullptr;
+        max_steps *= 4;  // some episode outlived the chain: replay with a longer one
+    }
+    if (h_final_boards && n) TRY(cudaMemcpy(h_final_boards, d_boards, n * sizeof(uint64_t), cudaMemcpyDeviceToHost), "play_host: d2h");
+    if (h_lengths && n) TRY(cudaMemcpy(h_lengths, d_len, n * sizeof(uint32_t), cudaMemcpyDeviceToHost), "play_host: d2h");
+    if (h_scores && n) TRY(cudaMemcpy(h_scores, d_score, n * sizeof(uint32_t), cudaMemcpyDeviceToHost), "play_host: d2h");
+    if (h_stats) for (int i = 0; i < G2048_PLAY_STATS_WORDS; ++i) h_stats[i] = stats[i];
+    if (h_key_io) {
+        // the reference's runner holds the chain key after 1 + 2*T splits, T = longest episode
+        uint32_t k2[2] = {key[0], key[1]};
+        const int64_t used = 1 + 2 * (int64_t)stats[5];
+        TRY(cudaMemcpy(d_key, k2, sizeof(k2), cudaMemcpyHostToDevice), "play_host: h2d key");
+        rc = g2048_chain_advance(d_key, rng_mode, used, d_subs, nullptr);
+        if (rc) goto done;
+        TRY(cudaMemcpy(h_key_io, d_key, sizeof(k2), cudaMemcpyDeviceToHost), "play_host: d2h key");
+    }
+done:
+#undef TRY
+    cudaFree(d_key); cudaFree(d_subs); cudaFree(d_work); cudaFree(d_stats);
+    cudaFree(d_boards); cudaFree(d_len); cudaFree(d_score);
+    if (st) cudaStreamDestroy(st);
+    return rc;
+}
+
+extern "C" int g2048_rollout_steps(int policy, uint64_t* d_boards, uint8_t* d_status, const uint32_t* d_subs,
+                                   int64_t n_steps, int64_t t0, int64_t batch_global, int64_t env_lo, int64_t n,
+                                   int rng_mode, uint64_t* d_rec_boards, uint8_t* d_rec_meta, float* d_rec_rewards,
+                                   float* d_rec_log_probs, uint64_t* d_counters, void* stream) {
+    G2048_REQUIRE(policy == G2048_POLICY_RANDOM || policy == G2048_POLICY_DRUL, "rollout_steps: policy");
+    G2048_REQUIRE(valid_mode(rng_mode) && valid_batch(batch_global, env_lo, n), "rollout_steps: batch");
+    G2048_REQUIRE(n_steps >= 0 && n_steps <= 0x7FFFFFFF && t0 >= 0, "rollout_steps: steps");
+    if (n == 0 || n_steps == 0) return G2048_OK;
+    G2048_REQUIRE(d_boards && d_status && d_subs && d_rec_boards && d_rec_meta && d_rec_rewards && d_counters,
+                  "rollout_steps: pointers");
+    const unsigned g = blocks_for(n, 256);
+    cudaStream_t st = (cudaStream_t)stream;
+#define CALL_P(M, P)                                                                                          \
+    rollout_steps_kernel<M, P><<<g, 256, 0, st>>>((u64*)d_boards, d_status, (const uint2*)d_subs, (int)n_steps,    \
+                                                  (uint32_t)t0, (uint32_t)batch_global, (uint32_t)env_lo, n,        \
+                                                  (u64*)d_rec_boards, d_rec_meta, d_rec_rewards, d_rec_log_probs,   \
+                                                  (unsigned long long*)d_counters)
+    if (policy == G2048_POLICY_RANDOM) {
+#define CALL(M) CALL_P(M, G2048_POLICY_RANDOM)
+        DISPATCH_MODE(rng_mode, CALL)
+#undef CALL
+    } else {
+#define CALL(M) CALL_P(M, G2048_POLICY_DRUL)
+        DISPATCH_MODE(rng_mode, CALL)
+#undef CALL
+    }
+#undef CALL_P
+    G2048_CHECK_LAUNCH("rollout_steps");
+    return G2048_OK;
+}
+
+extern "C" int g2048_int_peak_probe(int blocks, int threads, int iters, uint32_t* d_sink, void* stream) {
+    G2048_REQUIRE(blocks > 0 && threads > 0 && threads <= 1024 && iters > 0 && d_sink, "int_peak_probe");
+    int_peak_kernel<<<blocks, threads, 0, (cudaStream_t)stream>>>(iters, d_sink);
+    G2048_CHECK_LAUNCH("int_peak_probe");
+    return G2048_OK;
+}

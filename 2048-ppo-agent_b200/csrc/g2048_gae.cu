@@ -1,0 +1,352 @@
+// GAE / returns and their normalisation (src/ppo/data_loader.py:103-130 and :61-67).
+//
+// The reference walks the flat buffer backwards one step at a time.  The recurrence only couples
+// steps of the same episode (a `done` resets the carry), so the kernels parallelise ACROSS
+// episodes and keep the reference's exact fp32 operation order INSIDE each episode:
+//     delta = (r[t] + gamma * last_v) - V[t];   gae = delta + (gamma*lambda) * gae
+// (no FMA contraction: the library is built with --fmad=false).  Results are therefore bit-identical
+// to the reference, not merely within tolerance.  The kernels are HBM-bound streams:
+// 9 B read + 8 B written per step.
+#include "g2048_common.cuh"
+
+namespace g2048 {
+
+constexpr int GAE_TILE = 1024;
+constexpr int GAE_THREADS = 128;
+constexpr int GAE_ITEMS = GAE_TILE / GAE_THREADS;  // 8 consecutive steps per thread for segment discovery
+
+struct GaeScratch {
+    unsigned int ticket;
+    unsigned int pad[3];
+    // followed by n_tiles {flag, head_gae} pairs
+};
+
+__device__ __forceinline__ void block_sum4(double v[4], double* s_red /* [4][4] */, double* __restrict__ moments) {
+    const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
+#pragma unroll
+    for (int k = 0; k < 4; ++k) {
+        double x = v[k];
+        for (int off = 16; off > 0; off >>= 1) x += __shfl_down_sync(0xFFFFFFFFu, x, off);
+        if (lane == 0) s_red[k * 4 + warp] = x;
+    }
+    __syncthreads();
+    if (threadIdx.x < 4) {
+        const int k = threadIdx.x;
+        const double t = s_red[k * 4 + 0] + s_red[k * 4 + 1] + s_red[k * 4 + 2] + s_red[k * 4 + 3];
+        atomicAdd(&moments[1 + k], t);
+    }
+}
+
+// One CTA per tile of 1024 consecutive steps, tiles taken from the END of the buffer by ticket.
+//   1. coalesced loads of r, V, done into shared memory (+ V of the step after the tile);
+//   2. warp-shuffle prefix sum of per-thread done counts -> ordered list of episode ends;
+//   3. one thread per episode end walks its episode backwards inside shared memory;
+//   4. the steps after the tile's last `done` belong to an episode that ends in a later tile:
+//      one thread waits for that tile's first-step gae (published through global memory, decoupled
+//      look-back of depth one) and walks them;
+//   5. coalesced stores of adv / ret, fp64 moment sums for the normalisation.
+__global__ void __launch_bounds__(GAE_THREADS)
+gae_flat_kernel(const float* __restrict__ rewards, const float* __restrict__ values, const uint8_t* __restrict__ dones,
+                int64_t n, int64_t n_tiles, float gamma, float gamma_lambda, float* __restrict__ adv,
+                float* __restrict__ ret, GaeScratch* scratch, double* __restrict__ moments) {
+    __shared__ float s_r[GAE_TILE];
+    __shared__ float s_v[GAE_TILE + 1];
+    __shared__ float s_adv[GAE_TILE];
+    __shared__ uint8_t s_d[GAE_TILE];
+    __shared__ unsigned short s_end[GAE_TILE];  // ordered positions of done steps
+    __shared__ int s_warp_count[GAE_THREADS / 32];
+    __shared__ double s_red[16];
+    __shared__ unsigned int s_ticket;
+
+    volatile unsigned int* flags = (volatile unsigned int*)(scratch + 1);
+    volatile float* heads = (volatile float*)((unsigned int*)(scratch + 1) + n_tiles);
+
+    if (threadIdx.x == 0) s_ticket = atomicAdd(&scratch->ticket, 1u);
+    __syncthreads();
+    const int64_t tile = n_tiles - 1 - (int64_t)s_ticket;  // memory-order index of this tile
+    const int64_t lo = tile * GAE_TILE;
+    const int len = (int)min((int64_t)GAE_TILE, n - lo);
+
+    for (int i = threadIdx.x; i < GAE_TILE; i += GAE_THREADS) {
+        const bool in = i < len;
+        s_r[i] = in ? rewards[lo + i] : 0.0f;
+        s_v[i] = in ? values[lo + i] : 0.0f;
+        s_d[i] = in ? dones[lo + i] : (uint8_t)0;
+    }
+    if (threadIdx.x == 0) s_v[len] = (lo + len < n) ? values[lo + len] : 0.0f;  // V of the next step (0 past the end)
+    __syncthreads();
+
+    // ordered list of done positions
+    const int base = threadIdx.x * GAE_ITEMS;
+    unsigned int bits = 0;
+#pragma unroll
+    for (int k = 0; k < GAE_ITEMS; ++k) bits |= (s_d[base + k] ? 1u : 0u) << k;
+    const int cnt = __popc(bits);
+    const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
+    int incl = cnt;
+    for (int off = 1; off < 32; off <<= 1) {
+        const int y = __shfl_up_sync(0xFFFFFFFFu, incl, off);
+        if (lane >= off) incl += y;
+    }
+    if (lane == 31) s_warp_count[warp] = incl;
+    __syncthreads();
+    int before = incl - cnt;
+    int n_done = 0;
+#pragma unroll
+    for (int w = 0; w < GAE_THREADS / 32; ++w) {
+        if (w < warp) before += s_warp_count[w];
+        n_done += s_warp_count[w];
+    }
+    {
+        unsigned int b = bits;
+        int slot = before;
+        while (b) {
+            const int k = __ffs(b) - 1;
+            s_end[slot++] = (unsigned short)(base + k);
+            b &= b - 1;
+        }
+    }
+    __syncthreads();
+
+    // walk one episode (or episode fragment) backwards: steps (first, last], carry given
+    auto walk = [&](int last, int first_excl, float last_gae, float last_v) {
+        for (int t = last; t > first_excl; --t) {
+            if (s_d[t]) {
+                last_v = 0.0f;
+                last_gae = 0.0f;
+            }
+            const float v = s_v[t];
+            const float delta = (s_r[t] + gamma * last_v) - v;
+            last_gae = delta + gamma_lambda * last_gae;
+            s_adv[t] = last_gae;
+            last_v = v;
+        }
+    };
+
+    // episodes that end inside the tile; episode 0 also fixes the tile's first-step gae
+    for (int s = threadIdx.x; s < n_done; s += GAE_THREADS) {
+        const int last = s_end[s];
+        const int first_excl = s ? (int)s_end[s - 1] : -1;
+        walk(last, first_excl, 0.0f, 0.0f);
+        if (s == 0) {
+            heads[tile] = s_adv[0];
+            __threadfence();
+            flags[tile] = 1u;
+        }
+    }
+    // trailing fragment: continues an episode that ends in a later tile (or is cut by the buffer end)
+    if (threadIdx.x == GAE_THREADS - 1) {
+        const int first_excl = n_done ? (int)s_end[n_done - 1] : -1;
+        if (first_excl < len - 1) {
+            float carry = 0.0f;
+            if (lo + len < n) {
+                while (flags[tile + 1] == 0u) __nanosleep(64);
+                __threadfence();
+                carry = heads[tile + 1];
+            }
+            walk(len - 1, first_excl, carry, s_v[len]);
+        }
+        if (n_done == 0) {
+            heads[tile] = s_adv[0];
+            __threadfence();
+            flags[tile] = 1u;
+        }
+    }
+    __syncthreads();
+
+    double m[4] = {0.0, 0.0, 0.0, 0.0};
+    for (int i = threadIdx.x; i < len; i += GAE_THREADS) {
+        const float a = s_adv[i];
+        const float rt = a + s_v[i];
+        adv[lo + i] = a;
+        ret[lo + i] = rt;
+        m[0] += (double)a;
+        m[1] += (double)a * (double)a;
+        m[2] += (double)rt;
+        m[3] += (double)rt * (double)rt;
+    }
+    if (moments) {
+        block_sum4(m, s_red, moments);
+        if (threadIdx.x == 0) atomicAdd(&moments[0], (double)len);
+    }
+}
+
+// Time-major (T,B) records: one lane per env, loads batched 8 steps ahead so that enough bytes
+// are in flight; coalesced along B.
+constexpr int GAE_TM_UNROLL = 8;
+
+__global__ void __launch_bounds__(128)
+gae_time_major_kernel(const float* __restrict__ rewards, const float* __restrict__ values,
+                      const uint8_t* __restrict__ meta, int64_t t_steps, int64_t n,
+                      const float* __restrict__ bootstrap, float gamma, float gamma_lambda, float* __restrict__ adv,
+                      float* __restrict__ ret, double* __restrict__ moments) {
+    __shared__ double s_red[16];
+    const int64_t e = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
+    double m[4] = {0.0, 0.0, 0.0, 0.0};
+    if (e < n) {
+        float last_v = bootstrap ? bootstrap[e] : 0.0f;
+        float last_gae = 0.0f;
+        int64_t t = t_steps - 1;
+        while (t >= 0) {
+            float r[GAE_TM_UNROLL], v[GAE_TM_UNROLL];
+            uint8_t d[GAE_TM_UNROLL];
+            const int cnt = (int)min((int64_t)GAE_TM_UNROLL, t + 1);
+#pragma unroll
+            for (int k = 0; k < GAE_TM_UNROLL; ++k) {
+                if (k < cnt) {
+                    const int64_t i = (t - k) * n + e;
+                    r[k] = __ldcs(&rewards[i]);
+                    v[k] = __ldcs(&values[i]);
+                    d[k] = __ldcs(&meta[i]);
+                }
+            }
+#pragma unroll
+            for (int k = 0; k < GAE_TM_UNROLL; ++k) {
+                if (k < cnt) {
+                    if (d[k] & 0x40u) {
+                        last_v = 0.0f;
+                        last_gae = 0.0f;
+                    }
+                    const float delta = (r[k] + gamma * last_v) - v[k];
+                    last_gae = delta + gamma_lambda * last_gae;
+                    const float rt = last_gae + v[k];
+                    const int64_t i = (t - k) * n + e;
+                    __stcs(&adv[i], last_gae);
+                    __stcs(&ret[i], rt);
+                    last_v = v[k];
+                    m[0] += (double)last_gae;
+                    m[1] += (double)last_gae * (double)last_gae;
+                    m[2] += (double)rt;
+                    m[3] += (double)rt * (double)rt;
+                }
+            }
+            t -= cnt;
+        }
+    }
+    if (moments) {
+        block_sum4(m, s_red, moments);
+        if (threadIdx.x == 0) {
+            const int64_t first = (int64_t)blockIdx.x * blockDim.x;
+            const int64_t envs = min((int64_t)blockDim.x, n - first);
+            atomicAdd(&moments[0], (double)(envs * t_steps));
+        }
+    }
+}
+
+// x = (x - mean) / (std_unbiased + 1e-8), 128-bit accesses on the aligned body
+__global__ void __launch_bounds__(256)
+normalize_kernel(float* __restrict__ x, int64_t n, const double* __restrict__ moments, int which) {
+    const double cnt = moments[0];
+    const double sum = moments[which], sumsq = moments[which + 1];
+    const double mean_d = sum / cnt;
+    const double var_d = (sumsq - sum * mean_d) / (cnt - 1.0);
+    const float mean = (float)mean_d;
+    const float denom = (float)sqrt(var_d > 0.0 ? var_d : 0.0) + 1e-8f;
+    const int64_t stride = (int64_t)gridDim.x * blockDim.x;
+    const int64_t tid = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
+    // head up to 16-byte alignment, vector body, tail
+    const int64_t head = min(n, (int64_t)((16 - ((uintptr_t)x & 15u)) & 15u) / 4);
+    for (int64_t i = tid; i < head; i += stride) x[i] = (x[i] - mean) / denom;
+    float4* xv = (float4*)(x + head);
+    const int64_t nv = (n - head) / 4;
+    for (int64_t i = tid; i < nv; i += stride) {
+        float4 v = xv[i];
+        v.x = (v.x - mean) / denom;
+        v.y = (v.y - mean) / denom;
+        v.z = (v.z - mean) / denom;
+        v.w = (v.w - mean) / denom;
+        xv[i] = v;
+    }
+    for (int64_t i = head + nv * 4 + tid; i < n; i += stride) x[i] = (x[i] - mean) / denom;
+}
+
+}  // namespace g2048
+
+using namespace g2048;
+
+extern "C" int64_t g2048_gae_flat_scratch_bytes(int64_t n) {
+    const int64_t n_tiles = (n + GAE_TILE - 1) / GAE_TILE;
+    return (int64_t)sizeof(GaeScratch) + n_tiles * 8;
+}
+
+extern "C" int g2048_gae_flat(const float* d_rewards, const float* d_values, const uint8_t* d_dones, int64_t n,
+                              double gamma, double lambda_gae, float* d_adv, float* d_ret, void* d_scan_state,
+                              double* d_moments, void* stream) {
+    G2048_REQUIRE(n >= 0, "gae_flat: n");
+    if (n == 0) return G2048_OK;
+    G2048_REQUIRE(d_rewards && d_values && d_dones && d_adv && d_ret && d_scan_state, "gae_flat: pointers");
+    const int64_t n_tiles = (n + GAE_TILE - 1) / GAE_TILE;
+    G2048_REQUIRE(n_tiles <= 0x7FFFFFFFll, "gae_flat: too many steps");
+    gae_flat_kernel<<<(unsigned)n_tiles, GAE_THREADS, 0, (cudaStream_t)stream>>>(
+        d_rewards, d_values, d_dones, n, n_tiles, (float)gamma, (float)(gamma * lambda_gae), d_adv, d_ret,
+        (GaeScratch*)d_scan_state, d_moments);
+    G2048_CHECK_LAUNCH("gae_flat");
+    return G2048_OK;
+}
+
+extern "C" int g2048_gae_time_major(const float* d_rewards, const float* d_values, const uint8_t* d_rec_meta,
+                                    int64_t t_steps, int64_t n, const float* d_bootstrap, double gamma,
+                                    double lambda_gae, float* d_adv, float* d_ret, double* d_moments, void* stream) {
+    G2048_REQUIRE(t_steps >= 0 && n >= 0, "gae_time_major: shape");
+    if (t_steps == 0 || n == 0) return G2048_OK;
+    G2048_REQUIRE(d_rewards && d_values && d_rec_meta && d_adv && d_ret, "gae_time_major: pointers");
+    gae_time_major_kernel<<<blocks_for(n, 128), 128, 0, (cudaStream_t)stream>>>(
+        d_rewards, d_values, d_rec_meta, t_steps, n, d_bootstrap, (float)gamma, (float)(gamma * lambda_gae), d_adv,
+        d_ret, d_moments);
+    G2048_CHECK_LAUNCH("gae_time_major");
+    return G2048_OK;
+}
+
+extern "C" int g2048_normalize(float* d_x, int64_t n, const double* d_moments, int which, void* stream) {
+    G2048_REQUIRE(n >= 0 && (which == 1 || which == 3), "normalize: arguments");
+    if (n == 0) return G2048_OK;
+    G2048_REQUIRE(d_x && d_moments, "normalize: pointers");
+    const int sms = sm_count();
+    if (sms <= 0) return fail_arg("normalize: no device");
+    int64_t g = (n / 4 + 255) / 256 + 1;
+    const int64_t cap = (int64_t)sms * 8 * 4;
+    if (g > cap) g = cap;
+    normalize_kernel<<<(unsigned)g, 256, 0, (cudaStream_t)stream>>>(d_x, n, d_moments, which);
+    G2048_CHECK_LAUNCH("normalize");
+    return G2048_OK;
+}
+
+extern "C" int g2048_gae_host(const float* h_rewards, const float* h_values, const uint8_t* h_dones, int64_t n,
+                              double gamma, double lambda_gae, int normalize, float* h_adv, float* h_ret) {
+    G2048_REQUIRE(n >= 0, "gae_host: n");
+    if (n == 0) return G2048_OK;
+    G2048_REQUIRE(h_rewards && h_values && h_dones && h_adv && h_ret, "gae_host: pointers");
+    int rc = G2048_OK;
+    float *d_r = nullptr, *d_v = nullptr, *d_a = nullptr, *d_t = nullptr;
+    uint8_t* d_d = nullptr;
+    void* d_s = nullptr;
+    double* d_m = nullptr;
+    const int64_t sb = g2048_gae_flat_scratch_bytes(n);
+#define TRY(expr, where) do { rc = check_cuda((expr), where); if (rc) goto done; } while (0)
+    TRY(cudaMalloc(&d_r, n * 4), "gae_host: malloc");
+    TRY(cudaMalloc(&d_v, n * 4), "gae_host: malloc");
+    TRY(cudaMalloc(&d_a, n * 4), "gae_host: malloc");
+    TRY(cudaMalloc(&d_t, n * 4), "gae_host: malloc");
+    TRY(cudaMalloc(&d_d, n), "gae_host: malloc");
+    TRY(cudaMalloc(&d_s, sb), "gae_host: malloc");
+    TRY(cudaMalloc(&d_m, 6 * sizeof(double)), "gae_host: malloc");
+    TRY(cudaMemcpy(d_r, h_rewards, n * 4, cudaMemcpyHostToDevice), "gae_host: h2d");
+    TRY(cudaMemcpy(d_v, h_values, n * 4, cudaMemcpyHostToDevice), "gae_host: h2d");
+    TRY(cudaMemcpy(d_d, h_dones, n, cudaMemcpyHostToDevice), "gae_host: h2d");
+    TRY(cudaMemset(d_s, 0, sb), "gae_host: memset");
+    TRY(cudaMemset(d_m, 0, 6 * sizeof(double)), "gae_host: memset");
+    rc = g2048_gae_flat(d_r, d_v, d_d, n, gamma, lambda_gae, d_a, d_t, d_s, d_m, nullptr);
+    if (rc) goto done;
+    if (normalize) {
+        rc = g2048_normalize(d_a, n, d_m, 1, nullptr);
+        if (rc) goto done;
+        rc = g2048_normalize(d_t, n, d_m, 3, nullptr);
+        if (rc) goto done;
+    }
+    TRY(cudaMemcpy(h_adv, d_a, n * 4, cudaMemcpyDeviceToHost), "gae_host: d2h");
+    TRY(cudaMemcpy(h_ret, d_t, n * 4, cudaMemcpyDeviceToHost), "gae_host: d2h");
+done:
+#undef TRY
+    cudaFree(d_r); cudaFree(d_v); cudaFree(d_a); cudaFree(d_t); cudaFree(d_d); cudaFree(d_s); cudaFree(d_m);
+    return rc;
+}

@@ -1,0 +1,120 @@
+"""ctypes binding of libg2048.so (the C ABI declared in include/g2048.h).
+
+The library is the product: there is no Python / PyTorch / CPU fallback anywhere in this
+package.  If the shared object is missing the import of this module fails loudly; if no CUDA
+device is present every compute call raises ``RuntimeError``.
+"""
+from __future__ import annotations
+
+import ctypes as C
+import os
+import re
+from pathlib import Path
+
+import torch
+
+PKG_ROOT = Path(__file__).resolve().parent.parent  # .../2048-ppo-agent_b200
+REPO_ROOT = PKG_ROOT.parent
+LIB_PATH = Path(os.environ.get("G2048_LIB", PKG_ROOT / "libg2048.so"))
+HEADER_PATH = REPO_ROOT / "include" / "g2048.h"
+
+RNG_ORIGINAL = 0
+RNG_PARTITIONABLE = 1
+POLICY_RANDOM = 0
+POLICY_DRUL = 1
+STATUS_MASK = 0x0F
+STATUS_DONE = 0x10
+STATUS_OVERFLOW = 0x20
+OBS_BOOL, OBS_F32, OBS_BF16 = 0, 1, 2
+PLAY_STATS_WORDS = 32
+
+if not LIB_PATH.exists():
+    raise ImportError(
+        f"{LIB_PATH} not found: build the CUDA extension first (python -c 'import __graft_entry__ as g; g.build()' "
+        "or make -C 2048-ppo-agent_b200/csrc).  There is no fallback implementation."
+    )
+
+lib = C.CDLL(str(LIB_PATH))
+
+_P = C.c_void_p
+_I64 = C.c_int64
+_INT = C.c_int
+_DBL = C.c_double
+_U64 = C.c_uint64
+
+_SIGNATURES = {
+    "g2048_version": (_INT, []),
+    "g2048_last_error": (C.c_char_p, []),
+    "g2048_device_sm_count": (_INT, []),
+    "g2048_threefry2x32": (_INT, [_P, _P, _I64, _P, _P]),
+    "g2048_chain_advance": (_INT, [_P, _INT, _I64, _P, _P]),
+    "g2048_split_keys": (_INT, [_P, _I64, _I64, _I64, _INT, _P, _P]),
+    "g2048_env_init": (_INT, [_P, _I64, _I64, _I64, _INT, _P, _P, _P]),
+    "g2048_env_step": (_INT, [_P, _P, _P, _P, _I64, _I64, _I64, _INT, _P, _P]),
+    "g2048_env_step_draws": (_INT, [_P, _P, _P, _P, _P, _I64, _P, _P]),
+    "g2048_act": (_INT, [_INT, _P, _P, _I64, _I64, _I64, _INT, _P, _P, _P]),
+    "g2048_play": (_INT, [_INT, _P, _I64, _I64, _I64, _I64, _INT, _P, _P, _P, _P, _P, _P]),
+    "g2048_play_host": (_INT, [_INT, _U64, _P, _I64, _I64, _I64, _INT, _P, _P, _P, _P]),
+    "g2048_rollout_steps": (_INT, [_INT, _P, _P, _P, _I64, _I64, _I64, _I64, _I64, _INT, _P, _P, _P, _P, _P, _P]),
+    "g2048_policy_step": (_INT, [_P, _P, _P, _P, _INT, _INT, _INT, _P, _P, _I64, _I64, _I64, _INT, _P, _P, _P, _P, _P, _P, _P]),
+    "g2048_sample_logits": (_INT, [_P, _P, _INT, _INT, _P, _I64, _I64, _I64, _INT, _P, _P, _P, _P]),
+    "g2048_evaluate_logits": (_INT, [_P, _P, _INT, _P, _I64, _P, _P, _P]),
+    "g2048_expand_obs": (_INT, [_P, _I64, _INT, _P, _I64, _I64, _P]),
+    "g2048_pack_obs": (_INT, [_P, _INT, _I64, _P, _P]),
+    "g2048_unpack_status": (_INT, [_P, _I64, _P, _P, _P]),
+    "g2048_unpack_records": (_INT, [_P, _P, _P, _P, _I64, _I64, _P, _P, _P, _P, _P, _P, _P]),
+    "g2048_episode_lengths": (_INT, [_P, _I64, _I64, _P, _P]),
+    "g2048_exclusive_scan": (_INT, [_P, _I64, _P, _P]),
+    "g2048_compact_records": (_INT, [_P, _P, _P, _P, _P, _I64, _I64, _P, _P, _I64, _P, _P, _P, _P, _P, _P]),
+    "g2048_unpack_flat_meta": (_INT, [_P, _I64, _P, _P, _P, _P]),
+    "g2048_gae_flat_scratch_bytes": (_I64, [_I64]),
+    "g2048_gae_flat": (_INT, [_P, _P, _P, _I64, _DBL, _DBL, _P, _P, _P, _P, _P]),
+    "g2048_gae_time_major": (_INT, [_P, _P, _P, _I64, _I64, _P, _DBL, _DBL, _P, _P, _P, _P]),
+    "g2048_normalize": (_INT, [_P, _I64, _P, _INT, _P]),
+    "g2048_gae_host": (_INT, [_P, _P, _P, _I64, _DBL, _DBL, _INT, _P, _P]),
+    "g2048_row_moments": (_INT, [_P, _I64, _I64, _P, _P]),
+    "g2048_int_peak_probe": (_INT, [_INT, _INT, _INT, _P, _P]),
+}
+
+for _name, (_res, _args) in _SIGNATURES.items():
+    _fn = getattr(lib, _name)  # AttributeError here = the .so is stale / incomplete
+    _fn.restype = _res
+    _fn.argtypes = _args
+
+
+def declared_symbols() -> list[str]:
+    """Entry points declared in include/g2048.h (used by the CPU-side export test)."""
+    text = HEADER_PATH.read_text()
+    return sorted(set(re.findall(r"\b(g2048_[a-z0-9_]+)\s*\(", text)))
+
+
+def last_error() -> str:
+    return lib.g2048_last_error().decode()
+
+
+def check(rc: int, what: str) -> None:
+    if rc != 0:
+        raise RuntimeError(f"{what} failed (code {rc}): {last_error()}")
+
+
+def require_cuda() -> torch.device:
+    if not torch.cuda.is_available():
+        raise RuntimeError("g2048 needs a CUDA device (sm_100a); there is no CPU fallback")
+    return torch.device("cuda", torch.cuda.current_device())
+
+
+def ptr(t: torch.Tensor | None) -> int | None:
+    """Device (or host) pointer of a contiguous tensor, None passes NULL."""
+    if t is None:
+        return None
+    if not t.is_contiguous():
+        raise ValueError("g2048 kernels need contiguous tensors")
+    return t.data_ptr()
+
+
+def stream_ptr() -> int:
+    return torch.cuda.current_stream().cuda_stream
+
+
+def call(name: str, *args) -> None:
+    check(getattr(lib, name)(*args), name)

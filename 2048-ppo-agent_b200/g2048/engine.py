@@ -1,0 +1,349 @@
+"""Tensor-level wrappers over the C ABI: each function launches exactly one libg2048 kernel on
+torch's current stream.  PyTorch is used for device memory and streams only.
+
+Boards travel as ``torch.int64`` tensors holding the uint64 bitboard bits; keys and sub keys as
+``torch.int32`` tensors holding uint32 words (shape (..., 2)).
+"""
+from __future__ import annotations
+
+import os
+
+import numpy as np
+import torch
+
+from . import _native as N
+from ._native import call, ptr, stream_ptr
+
+RNG_ORIGINAL = N.RNG_ORIGINAL
+RNG_PARTITIONABLE = N.RNG_PARTITIONABLE
+POLICY_RANDOM = N.POLICY_RANDOM
+POLICY_DRUL = N.POLICY_DRUL
+
+
+def resolve_rng_mode(mode=None) -> int:
+    """None -> $G2048_THREEFRY_PARTITIONABLE (default 1, like the pinned jax 0.5.3)."""
+    if mode is None:
+        env = os.environ.get("G2048_THREEFRY_PARTITIONABLE", os.environ.get("JAX_THREEFRY_PARTITIONABLE", "1"))
+        return RNG_PARTITIONABLE if env.strip().lower() not in ("0", "false", "off", "no") else RNG_ORIGINAL
+    if isinstance(mode, str):
+        m = mode.lower()
+        if m in ("partitionable", "1", "true"):
+            return RNG_PARTITIONABLE
+        if m in ("original", "0", "false"):
+            return RNG_ORIGINAL
+        raise ValueError(f"unknown rng_mode {mode!r}")
+    return RNG_PARTITIONABLE if int(mode) else RNG_ORIGINAL
+
+
+def key_words(seed: int) -> tuple[int, int]:
+    """jax.random.key(seed) -> (hi, lo) uint32 words."""
+    seed = int(seed) & 0xFFFFFFFFFFFFFFFF
+    return (seed >> 32) & 0xFFFFFFFF, seed & 0xFFFFFFFF
+
+
+def words_tensor(words, device) -> torch.Tensor:
+    """uint32 words -> int32 device tensor with the same bits."""
+    arr = np.asarray(words, dtype=np.uint32)
+    return torch.from_numpy(arr.view(np.int32).copy()).to(device)
+
+
+def words_numpy(t: torch.Tensor) -> np.ndarray:
+    return t.detach().cpu().numpy().view(np.uint32)
+
+
+def boards_numpy(t: torch.Tensor) -> np.ndarray:
+    """int64 bitboards -> (..., 16) uint8 exponents (host)."""
+    x = t.detach().cpu().numpy().view(np.uint64)
+    return ((x[..., None] >> (np.arange(16, dtype=np.uint64) * np.uint64(4))) & np.uint64(15)).astype(np.uint8)
+
+
+def pack_boards(exponents) -> np.ndarray:
+    """(..., 16) exponents -> uint64 bitboards viewed as int64 (host)."""
+    b = np.asarray(exponents, dtype=np.uint64)
+    return (b << (np.arange(16, dtype=np.uint64) * np.uint64(4))).sum(axis=-1).astype(np.uint64).view(np.int64)
+
+
+def _i32(t):
+    assert t.dtype == torch.int32, t.dtype
+    return t
+
+
+# ------------------------------------------------------------------------------------------- RNG
+def threefry2x32(keys: torch.Tensor, ctrs: torch.Tensor) -> torch.Tensor:
+    N.require_cuda()
+    out = torch.empty_like(keys)
+    call("g2048_threefry2x32", ptr(_i32(keys)), ptr(_i32(ctrs)), keys.shape[0], ptr(out), stream_ptr())
+    return out
+
+
+def chain_advance(key_io: torch.Tensor, rng_mode: int, n_sub: int, out: torch.Tensor | None = None) -> torch.Tensor:
+    """Advances key_io (2 words, in place) n_sub times; returns the (n_sub, 2) sub keys."""
+    N.require_cuda()
+    if out is None:
+        out = torch.empty((n_sub, 2), dtype=torch.int32, device=key_io.device)
+    call("g2048_chain_advance", ptr(_i32(key_io)), rng_mode, n_sub, ptr(out), stream_ptr())
+    return out
+
+
+def split_keys(sub: torch.Tensor, batch_global: int, env_lo: int, n: int, rng_mode: int) -> torch.Tensor:
+    N.require_cuda()
+    out = torch.empty((n, 2), dtype=torch.int32, device=sub.device)
+    call("g2048_split_keys", ptr(_i32(sub)), batch_global, env_lo, n, rng_mode, ptr(out), stream_ptr())
+    return out
+
+
+# ------------------------------------------------------------------------------------------- env
+def env_init(sub: torch.Tensor, batch_global: int, env_lo: int, n: int, rng_mode: int):
+    """-> boards (n,) int64, status (n,) uint8.  batch_global=0: `sub` is an explicit (n,2) key array."""
+    dev = N.require_cuda() if not sub.is_cuda else sub.device
+    boards = torch.empty(n, dtype=torch.int64, device=dev)
+    status = torch.empty(n, dtype=torch.uint8, device=dev)
+    call("g2048_env_init", ptr(_i32(sub)), batch_global, env_lo, n, rng_mode, ptr(boards), ptr(status), stream_ptr())
+    return boards, status
+
+
+def env_step(boards, status, actions, sub, batch_global: int, env_lo: int, rng_mode: int) -> torch.Tensor:
+    """In place on boards/status; returns rewards (n,) float32."""
+    n = boards.shape[0]
+    rewards = torch.empty(n, dtype=torch.float32, device=boards.device)
+    call("g2048_env_step", ptr(boards), ptr(status), ptr(_i32(actions)), ptr(_i32(sub)), batch_global, env_lo, n,
+         rng_mode, ptr(rewards), stream_ptr())
+    return rewards
+
+
+def env_step_draws(boards, status, actions, bits_pos, bits_val) -> torch.Tensor:
+    n = boards.shape[0]
+    rewards = torch.empty(n, dtype=torch.float32, device=boards.device)
+    call("g2048_env_step_draws", ptr(boards), ptr(status), ptr(_i32(actions)), ptr(_i32(bits_pos)), ptr(_i32(bits_val)),
+         n, ptr(rewards), stream_ptr())
+    return rewards
+
+
+def act(policy: int, status, sub, batch_global: int, env_lo: int, rng_mode: int):
+    """-> actions int32 (n,), log_probs float32 (n,) or None (act_drul)."""
+    n = status.shape[0]
+    actions = torch.empty(n, dtype=torch.int32, device=status.device)
+    log_probs = torch.empty(n, dtype=torch.float32, device=status.device) if policy == POLICY_RANDOM else None
+    call("g2048_act", policy, ptr(status), ptr(sub), batch_global, env_lo, n, rng_mode, ptr(actions), ptr(log_probs),
+         stream_ptr())
+    return actions, log_probs
+
+
+# ------------------------------------------------------------------------------------------- fused loops
+STAT_NAMES = ("episodes", "env_steps", "score_sum", "cut_short", "overflowed", "longest", "tile_sum", "tile_sq_sum")
+
+
+def play(policy: int, subs: torch.Tensor, batch_global: int, env_lo: int, n: int, rng_mode: int,
+         per_env: bool = True, stats: torch.Tensor | None = None):
+    """Persistent play-to-termination kernel.  Returns dict(final_boards, lengths, scores, stats)."""
+    dev = subs.device
+    work = torch.zeros(2, dtype=torch.int64, device=dev)
+    if stats is None:
+        stats = torch.zeros(N.PLAY_STATS_WORDS, dtype=torch.int64, device=dev)
+    boards = lengths = scores = None
+    if per_env:
+        boards = torch.empty(n, dtype=torch.int64, device=dev)
+        lengths = torch.empty(n, dtype=torch.int32, device=dev)
+        scores = torch.empty(n, dtype=torch.int32, device=dev)
+    call("g2048_play", policy, ptr(_i32(subs)), subs.shape[0], batch_global, env_lo, n, rng_mode, ptr(work),
+         ptr(boards), ptr(lengths), ptr(scores), ptr(stats), stream_ptr())
+    return dict(final_boards=boards, lengths=lengths, scores=scores, stats=stats)
+
+
+def play_stats_dict(stats: torch.Tensor) -> dict:
+    s = stats.detach().cpu().numpy().astype(np.uint64)
+    out = {k: int(s[i]) for i, k in enumerate(STAT_NAMES)}
+    out["max_tile_hist"] = {1 << e: int(s[16 + e]) for e in range(16) if s[16 + e]}
+    return out
+
+
+def play_host(policy: int, seed: int, batch_global: int, rng_mode: int, env_lo: int = 0, n: int | None = None,
+              key: np.ndarray | None = None, per_env: bool = True):
+    """The host-buffer C entry point (numpy in / numpy out; copies and syncs inside the call)."""
+    N.require_cuda()
+    n = batch_global - env_lo if n is None else n
+    boards = np.empty(n, np.uint64) if per_env else None
+    lengths = np.empty(n, np.uint32) if per_env else None
+    scores = np.empty(n, np.uint32) if per_env else None
+    stats = np.zeros(N.PLAY_STATS_WORDS, np.uint64)
+    key_io = None if key is None else np.ascontiguousarray(key, np.uint32)
+    as_p = lambda a: None if a is None else a.ctypes.data  # noqa: E731
+    call("g2048_play_host", policy, int(seed) & 0xFFFFFFFFFFFFFFFF, as_p(key_io), batch_global, env_lo, n, rng_mode,
+         as_p(boards), as_p(lengths), as_p(scores), as_p(stats))
+    return dict(final_boards=boards, lengths=lengths, scores=scores, stats=stats, key=key_io)
+
+
+def rollout_steps(policy: int, boards, status, subs, n_steps: int, t0: int, batch_global: int, env_lo: int,
+                  rng_mode: int, rec_boards, rec_meta, rec_rewards, rec_log_probs, counters) -> None:
+    n = boards.shape[0]
+    call("g2048_rollout_steps", policy, ptr(boards), ptr(status), ptr(_i32(subs)), n_steps, t0, batch_global, env_lo, n,
+         rng_mode, ptr(rec_boards), ptr(rec_meta), ptr(rec_rewards), ptr(rec_log_probs), ptr(counters), stream_ptr())
+
+
+# ------------------------------------------------------------------------------------------- policy logits
+def policy_step(boards, status, logits, values, use_mask: bool, sample: bool, auto_reset: bool, sub_act, sub_step,
+                batch_global: int, env_lo: int, rng_mode: int, rec_boards=None, rec_meta=None, rec_rewards=None,
+                rec_log_probs=None, rec_values=None, actions_out=None) -> None:
+    n = boards.shape[0]
+    assert logits.dtype == torch.float32 and logits.shape == (n, 4)
+    if values is not None:
+        assert values.dtype == torch.float32 and values.numel() == n
+    call("g2048_policy_step", ptr(boards), ptr(status), ptr(logits), ptr(values), int(use_mask), int(sample),
+         int(auto_reset), ptr(sub_act), ptr(sub_step), batch_global, env_lo, n, rng_mode, ptr(rec_boards),
+         ptr(rec_meta), ptr(rec_rewards), ptr(rec_log_probs), ptr(rec_values), ptr(actions_out), stream_ptr())
+
+
+def sample_logits(logits, status, use_mask: bool, sample: bool, sub_act, batch_global: int, env_lo: int,
+                  rng_mode: int, want_entropy: bool = False):
+    n = logits.shape[0]
+    assert logits.dtype == torch.float32 and logits.shape == (n, 4)
+    actions = torch.empty(n, dtype=torch.int32, device=logits.device)
+    log_probs = torch.empty(n, dtype=torch.float32, device=logits.device)
+    entropy = torch.empty(n, dtype=torch.float32, device=logits.device) if want_entropy else None
+    call("g2048_sample_logits", ptr(logits), ptr(status), int(use_mask), int(sample), ptr(sub_act), batch_global,
+         env_lo, n, rng_mode, ptr(actions), ptr(log_probs), ptr(entropy), stream_ptr())
+    return actions, log_probs, entropy
+
+
+def evaluate_logits(logits, mask_bits, use_mask: bool, actions):
+    n = logits.shape[0]
+    assert logits.dtype == torch.float32 and logits.shape == (n, 4)
+    log_probs = torch.empty(n, dtype=torch.float32, device=logits.device)
+    entropy = torch.empty(n, dtype=torch.float32, device=logits.device)
+    call("g2048_evaluate_logits", ptr(logits), ptr(mask_bits), int(use_mask), ptr(_i32(actions)), n, ptr(log_probs),
+         ptr(entropy), stream_ptr())
+    return log_probs, entropy
+
+
+# ------------------------------------------------------------------------------------------- records
+_OBS_DTYPES = {torch.bool: N.OBS_BOOL, torch.uint8: N.OBS_BOOL, torch.float32: N.OBS_F32, torch.bfloat16: N.OBS_BF16}
+
+
+def expand_obs(boards: torch.Tensor, dtype=torch.float32, rows: int = 0, n_cols: int = 0, out=None) -> torch.Tensor:
+    """One-hot (n,16,31).  rows/n_cols > 0: boards are (rows, n_cols) time-major, output is env-major."""
+    n = boards.numel()
+    if out is None:
+        out = torch.empty((n, 16, 31), dtype=dtype, device=boards.device)
+    call("g2048_expand_obs", ptr(boards), n, _OBS_DTYPES[dtype], ptr(out), rows, n_cols, stream_ptr())
+    return out
+
+
+def pack_obs(obs: torch.Tensor) -> torch.Tensor:
+    """One-hot (n,16,31) bool/uint8/float32 -> (n,) int64 bitboards (argmax over channels)."""
+    n = obs.numel() // 496
+    code = N.OBS_F32 if obs.dtype == torch.float32 else _OBS_DTYPES[obs.dtype]
+    if code == N.OBS_BF16:
+        raise ValueError("pack_obs takes bool/uint8/float32 observations")
+    boards = torch.empty(n, dtype=torch.int64, device=obs.device)
+    call("g2048_pack_obs", ptr(obs), code, n, ptr(boards), stream_ptr())
+    return boards
+
+
+def unpack_status(status: torch.Tensor):
+    """status bytes -> (legal_action_mask (n,4) bool, terminated (n,) bool)."""
+    n = status.shape[0]
+    masks = torch.empty((n, 4), dtype=torch.bool, device=status.device)
+    term = torch.empty(n, dtype=torch.bool, device=status.device)
+    call("g2048_unpack_status", ptr(status), n, ptr(masks), ptr(term), stream_ptr())
+    return masks, term
+
+
+def unpack_records(rec_meta, rec_rewards, rec_log_probs, rec_values, t_steps: int, n: int):
+    """(T,B) time-major records -> dict of (B,T) env-major reference arrays (device)."""
+    dev = rec_meta.device
+    out = dict(
+        actions=torch.empty((n, t_steps), dtype=torch.int32, device=dev),
+        action_masks=torch.empty((n, t_steps, 4), dtype=torch.bool, device=dev),
+        terminations=torch.empty((n, t_steps), dtype=torch.bool, device=dev),
+        rewards=torch.empty((n, t_steps), dtype=torch.float32, device=dev),
+        log_probs=torch.empty((n, t_steps), dtype=torch.float32, device=dev) if rec_log_probs is not None else None,
+        values=torch.empty((n, t_steps), dtype=torch.float32, device=dev) if rec_values is not None else None,
+    )
+    call("g2048_unpack_records", ptr(rec_meta), ptr(rec_rewards), ptr(rec_log_probs), ptr(rec_values), t_steps, n,
+         ptr(out["actions"]), ptr(out["action_masks"]), ptr(out["terminations"]), ptr(out["rewards"]),
+         ptr(out["log_probs"]), ptr(out["values"]), stream_ptr())
+    return out
+
+
+def episode_lengths(rec_meta, t_steps: int, n: int) -> torch.Tensor:
+    out = torch.empty(n, dtype=torch.int32, device=rec_meta.device)
+    call("g2048_episode_lengths", ptr(rec_meta), t_steps, n, ptr(out), stream_ptr())
+    return out
+
+
+def exclusive_scan(x: torch.Tensor) -> torch.Tensor:
+    out = torch.empty(x.shape[0] + 1, dtype=torch.int64, device=x.device)
+    call("g2048_exclusive_scan", ptr(_i32(x)), x.shape[0], ptr(out), stream_ptr())
+    return out
+
+
+def compact_records(rec_boards, rec_meta, rec_rewards, rec_log_probs, rec_values, t_steps: int, n: int, lengths,
+                    offsets, out_base: int, boards, meta, rewards, log_probs, values) -> None:
+    call("g2048_compact_records", ptr(rec_boards), ptr(rec_meta), ptr(rec_rewards), ptr(rec_log_probs),
+         ptr(rec_values), t_steps, n, ptr(lengths), ptr(offsets), out_base, ptr(boards), ptr(meta), ptr(rewards),
+         ptr(log_probs), ptr(values), stream_ptr())
+
+
+def unpack_flat_meta(meta: torch.Tensor):
+    n = meta.shape[0]
+    dev = meta.device
+    actions = torch.empty((n, 4), dtype=torch.float32, device=dev)
+    masks = torch.empty((n, 4), dtype=torch.bool, device=dev)
+    term = torch.empty(n, dtype=torch.bool, device=dev)
+    call("g2048_unpack_flat_meta", ptr(meta), n, ptr(actions), ptr(masks), ptr(term), stream_ptr())
+    return actions, masks, term
+
+
+# ------------------------------------------------------------------------------------------- GAE
+def gae_flat(rewards, values, dones, gamma: float, lambda_gae: float, want_moments: bool = True):
+    """-> adv, ret (n,) float32, moments (6,) float64 or None.  dones: uint8/bool (n,)."""
+    n = rewards.shape[0]
+    dev = rewards.device
+    adv = torch.empty(n, dtype=torch.float32, device=dev)
+    ret = torch.empty(n, dtype=torch.float32, device=dev)
+    scratch = torch.zeros(int(N.lib.g2048_gae_flat_scratch_bytes(n)), dtype=torch.uint8, device=dev)
+    moments = torch.zeros(6, dtype=torch.float64, device=dev) if want_moments else None
+    call("g2048_gae_flat", ptr(rewards), ptr(values), ptr(dones), n, float(gamma), float(lambda_gae), ptr(adv),
+         ptr(ret), ptr(scratch), ptr(moments), stream_ptr())
+    return adv, ret, moments
+
+
+def gae_time_major(rec_rewards, rec_values, rec_meta, t_steps: int, n: int, bootstrap, gamma: float,
+                   lambda_gae: float, want_moments: bool = True):
+    dev = rec_rewards.device
+    adv = torch.empty((t_steps, n), dtype=torch.float32, device=dev)
+    ret = torch.empty((t_steps, n), dtype=torch.float32, device=dev)
+    moments = torch.zeros(6, dtype=torch.float64, device=dev) if want_moments else None
+    call("g2048_gae_time_major", ptr(rec_rewards), ptr(rec_values), ptr(rec_meta), t_steps, n, ptr(bootstrap),
+         float(gamma), float(lambda_gae), ptr(adv), ptr(ret), ptr(moments), stream_ptr())
+    return adv, ret, moments
+
+
+def normalize_(x: torch.Tensor, moments: torch.Tensor, which: int) -> torch.Tensor:
+    call("g2048_normalize", ptr(x), x.numel(), ptr(moments), which, stream_ptr())
+    return x
+
+
+def gae_host(rewards: np.ndarray, values: np.ndarray, dones: np.ndarray, gamma: float, lambda_gae: float,
+             normalize: bool):
+    N.require_cuda()
+    r = np.ascontiguousarray(rewards, np.float32)
+    v = np.ascontiguousarray(values, np.float32)
+    d = np.ascontiguousarray(dones, np.uint8)
+    adv = np.empty_like(r)
+    ret = np.empty_like(r)
+    call("g2048_gae_host", r.ctypes.data, v.ctypes.data, d.ctypes.data, r.shape[0], float(gamma), float(lambda_gae),
+         int(normalize), adv.ctypes.data, ret.ctypes.data)
+    return adv, ret
+
+
+def row_moments(x: torch.Tensor) -> torch.Tensor:
+    """(F, n) float64 -> (F, 3): count, mean, population variance."""
+    assert x.dtype == torch.float64 and x.dim() == 2
+    out = torch.empty((x.shape[0], 3), dtype=torch.float64, device=x.device)
+    call("g2048_row_moments", ptr(x), x.shape[0], x.shape[1], ptr(out), stream_ptr())
+    return out
+
+
+def int_peak_probe(blocks: int, threads: int, iters: int, sink: torch.Tensor) -> None:
+    call("g2048_int_peak_probe", blocks, threads, iters, ptr(sink), stream_ptr())

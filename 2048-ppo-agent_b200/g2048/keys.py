@@ -1,0 +1,91 @@
+"""jax.random-style keys on the device: ``key(seed)``, ``split(key, n)`` and the runner's chain.
+
+A key is two uint32 words, stored in an int32 tensor of shape (2,) (a batch of keys: (n, 2)).
+Replaces jax.random.key / jax.random.split as used at src/runs/batch_runner.py:32,105-106,118-119.
+"""
+from __future__ import annotations
+
+import numpy as np
+import torch
+
+from . import _native as N
+from . import engine as E
+
+
+def key(seed: int, device=None) -> torch.Tensor:
+    """jax.random.key(seed)."""
+    device = N.require_cuda() if device is None else device
+    return E.words_tensor(list(E.key_words(seed)), device)
+
+
+def as_key_tensor(k, device=None) -> torch.Tensor:
+    """Accepts a tensor / numpy array / sequence of uint32 words; returns an int32 device tensor."""
+    device = N.require_cuda() if device is None else device
+    if isinstance(k, torch.Tensor):
+        if k.dtype != torch.int32:
+            k = torch.from_numpy(k.detach().cpu().numpy().astype(np.uint32).view(np.int32))
+        return k.to(device).contiguous()
+    return E.words_tensor(np.asarray(k, dtype=np.uint64).astype(np.uint32), device)
+
+
+def split(k, num: int = 2, rng_mode=None) -> torch.Tensor:
+    """jax.random.split(key, num) -> (num, 2)."""
+    k = as_key_tensor(k)
+    return E.split_keys(k, num, 0, num, E.resolve_rng_mode(rng_mode))
+
+
+class KeyChain:
+    """The runner's ``key, sub = split(key)`` chain, generated ahead of time on the device.
+
+    Sub keys are produced in blocks by one small kernel (the chain is sequential by
+    construction) and consumed by the rollout kernels straight from device memory, so a run
+    never waits on the host for keys.  ``peek(n)`` returns the next n sub keys without
+    consuming them; ``consume(n)`` advances (a run consumes 1 + 2*T of them, T known only
+    after the run).  ``key`` is the chain key the reference's runner would hold now.
+    """
+
+    BLOCK = 8192
+
+    def __init__(self, seed_or_key, rng_mode: int, device=None):
+        self.device = N.require_cuda() if device is None else torch.device(device)
+        self.rng_mode = rng_mode
+        if isinstance(seed_or_key, (int, np.integer)):
+            words = np.array(E.key_words(int(seed_or_key)), dtype=np.uint32)
+        else:
+            words = np.asarray(seed_or_key, dtype=np.uint32).reshape(2).copy()
+        self._base_key = words  # chain key at absolute position self._base_pos
+        self._base_pos = 0  # number of splits consumed so far
+        self._subs = torch.empty((0, 2), dtype=torch.int32, device=self.device)  # subs from _base_pos on
+        self._tip = E.words_tensor(words, self.device)  # chain key after all generated subs
+
+    def peek(self, n: int) -> torch.Tensor:
+        have = self._subs.shape[0]
+        if n > have:
+            extra = max(n - have, self.BLOCK)
+            new = E.chain_advance(self._tip, self.rng_mode, extra)
+            self._subs = torch.cat([self._subs, new]) if have else new
+        return self._subs[:n]
+
+    def consume(self, n: int) -> None:
+        if n <= 0:
+            return
+        self.peek(n)
+        # the chain key after n more splits: replay from the base key (cheap, and only done here)
+        base = E.words_tensor(self._base_key, self.device)
+        E.chain_advance(base, self.rng_mode, n)
+        self._base_key = E.words_numpy(base).copy()
+        self._base_pos += n
+        self._subs = self._subs[n:]
+
+    def next_sub(self) -> torch.Tensor:
+        sub = self.peek(1)[0].clone()
+        self.consume(1)
+        return sub
+
+    @property
+    def key(self) -> np.ndarray:
+        return self._base_key.copy()
+
+    @property
+    def position(self) -> int:
+        return self._base_pos

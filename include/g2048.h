@@ -1,0 +1,259 @@
+/* libg2048 -- C ABI of the B200 (sm_100a) rollout engine for 2048.
+ *
+ * This is the drop-in boundary for the one hot path of michaelriedl/2048-ppo-agent: the batched
+ * 2048 env step fused with action selection, rollout-buffer writes and GAE.  The reference has no
+ * FFI of its own (it is pure Python on Pgx/JAX); each entry point below names the reference code
+ * it replaces (paths relative to the reference repo root).  INTEGRATION.md shows the ctypes
+ * binding a maintainer adds on the reference side.
+ *
+ * Conventions
+ *   - Plain pointers and sizes only; no torch / jax types.  Every `d_` pointer is DEVICE memory
+ *     on the current CUDA device, every `h_` pointer is HOST memory.  Nothing is allocated or
+ *     freed by `d_` entry points; work is enqueued on `stream` (a cudaStream_t passed as void*,
+ *     NULL = legacy default stream) and the call returns without synchronising.
+ *     `*_host` entry points take host buffers, do their own device allocation + H2D/D2H copies
+ *     and synchronise before returning.
+ *   - Return value: 0 on success, G2048_ERR_INVALID (-1) for a bad argument, otherwise the
+ *     cudaError_t that was raised.  g2048_last_error() gives the text.  There is no CPU
+ *     fallback: without a CUDA device every compute entry point fails.
+ *   - Board: uint64 nibble bitboard, cell i = 4*row + col in bits [4i, 4i+4), value = exponent
+ *     (0 empty, e = tile 2^e, Pgx's own encoding).  Status byte per env: bits 0-3 = legal-action
+ *     mask as Pgx exposes it (bit a = action a legal; all four set on a terminal state),
+ *     bit 4 = terminated, bit 5 = sticky "tile 2^16 needed" overflow flag.
+ *   - Actions: 0 = Left, 1 = Up, 2 = Right, 3 = Down (src/actions/act_drul.py:8,39-40).
+ *   - Keys: a jax.random key is two uint32 words (hi, lo).  `rng_mode` selects the Threefry
+ *     counter layout: G2048_RNG_ORIGINAL (jax_threefry_partitionable=False) or
+ *     G2048_RNG_PARTITIONABLE (=True, default of the pinned jax==0.5.3).
+ *   - Env indices are GLOBAL: a shard owns envs [env_lo, env_lo + n) of a batch of
+ *     `batch_global` envs, and per-env keys are split(sub, batch_global)[env index], so results
+ *     do not depend on how the batch is sharded over GPUs.  Entry points that take one sub key
+ *     (`d_sub`) also accept batch_global == 0 (with env_lo == 0): `d_sub` is then an explicit
+ *     (n,2) array of per-env keys, exactly what jax.vmap(act_fn)(keys, obs, mask) receives.
+ *     The fused loops (g2048_play, g2048_rollout_steps) need batch_global > 0.
+ */
+#ifndef G2048_H_
+#define G2048_H_
+
+#include <stdint.h>
+
+#ifdef __cplusplus
+extern "C" {
+#endif
+
+#define G2048_OK 0
+#define G2048_ERR_INVALID (-1)
+
+#define G2048_RNG_ORIGINAL 0
+#define G2048_RNG_PARTITIONABLE 1
+
+#define G2048_POLICY_RANDOM 0 /* src/actions/act_randomly.py:40-56 */
+#define G2048_POLICY_DRUL 1   /* src/actions/act_drul.py:40-49 */
+
+#define G2048_STATUS_MASK 0x0F
+#define G2048_STATUS_DONE 0x10
+#define G2048_STATUS_OVERFLOW 0x20
+
+#define G2048_OBS_BOOL 0 /* uint8 0/1, the layout of pgx State.observation (4,4,31) bool */
+#define G2048_OBS_F32 1  /* float32, what RolloutBuffer.get_buffer_data / PPOAgent consume */
+#define G2048_OBS_BF16 2
+
+/* number of uint64 slots of the play statistics block, see g2048_play */
+#define G2048_PLAY_STATS_WORDS 32
+
+int g2048_version(void);
+const char* g2048_last_error(void);
+/* SM count of the current device, or a negative error */
+int g2048_device_sm_count(void);
+
+/* ---- RNG (replaces jax.random.key/split at src/runs/batch_runner.py:32,105-106,118-119,126-127) */
+
+/* Threefry-2x32-20 blocks: out[i] = TF(key[i]; ctr[i]); all (n,2) uint32.  Test hook / KATs. */
+int g2048_threefry2x32(const uint32_t* d_keys, const uint32_t* d_ctrs, int64_t n, uint32_t* d_out, void* stream);
+
+/* The runner's chain `key, sub = split(key)` advanced n_sub times on the device:
+ * d_subs[(n_sub,2)] receives the successive sub keys, d_key_io[2] the advanced chain key. */
+int g2048_chain_advance(uint32_t* d_key_io, int rng_mode, int64_t n_sub, uint32_t* d_subs, void* stream);
+
+/* keys[i] = split(*d_sub, batch_global)[env_lo + i], i < n: the per-env keys the reference hands
+ * to vmap(act_fn) / vmap(env.step).  Only needed when a caller-supplied policy wants real keys. */
+int g2048_split_keys(const uint32_t* d_sub, int64_t batch_global, int64_t env_lo, int64_t n, int rng_mode,
+                     uint32_t* d_keys, void* stream);
+
+/* ---- env (replaces pgx "2048" init/step via jit(vmap(...)) at src/runs/batch_runner.py:34-35,107,128) */
+
+/* env.init(split(*d_sub, batch_global)[env_lo + i]) -> board, status (rewards 0, not terminated) */
+int g2048_env_init(const uint32_t* d_sub, int64_t batch_global, int64_t env_lo, int64_t n, int rng_mode,
+                   uint64_t* d_boards, uint8_t* d_status, void* stream);
+
+/* env.step(state, action, split(*d_sub, batch_global)[env_lo + i]) in place.
+ * d_rewards (n) float32 as pgx State.rewards[:,0]; frozen envs get 0, an action illegal under the
+ * pre-step mask gets -1 and terminates.  d_actions int32. */
+int g2048_env_step(uint64_t* d_boards, uint8_t* d_status, const int32_t* d_actions, const uint32_t* d_sub,
+                   int64_t batch_global, int64_t env_lo, int64_t n, int rng_mode, float* d_rewards, void* stream);
+
+/* Same step with the spawn's two 32-bit draws supplied per env (position draw, value draw) instead
+ * of a key: the "identical actions and spawn draws" form the bit-exactness contract is stated in. */
+int g2048_env_step_draws(uint64_t* d_boards, uint8_t* d_status, const int32_t* d_actions,
+                         const uint32_t* d_bits_pos, const uint32_t* d_bits_val, int64_t n, float* d_rewards,
+                         void* stream);
+
+/* vmap(act_randomly | act_drul)(split(*d_sub, batch_global)[env_lo + i], obs, mask):
+ * d_actions int32 (n); d_log_probs float32 (n) or NULL (act_drul returns None). */
+int g2048_act(int policy, const uint8_t* d_status, const uint32_t* d_sub, int64_t batch_global, int64_t env_lo,
+              int64_t n, int rng_mode, int32_t* d_actions, float* d_log_probs, void* stream);
+
+/* ---- fused loops */
+
+/* Play envs [env_lo, env_lo+n) of BatchRunner(seed).run_*(batch_global) to termination inside ONE
+ * persistent kernel (src/runs/batch_runner.py:105-136 with act_randomly / act_drul, and the
+ * max-tile reduction of src/runs/run_actions_max_tile.py:61-69).  Lanes that finish an episode
+ * pull the next env, so no lane idles on a frozen env.
+ *   d_subs: chain sub keys, [0] = init, [1+2t] = act keys of loop step t, [2+2t] = step keys;
+ *           n_subs of them are valid (episodes longer than (n_subs-1)/2 set stats[3]).
+ *   d_work: uint64[2] scratch, zeroed by the caller: [0] = env queue head, [1] unused.
+ *   d_final_boards / d_lengths / d_scores: per-env outputs (n), each may be NULL.
+ *           length = loop steps until terminated (first done index + 1), score = sum of rewards.
+ *   d_stats: uint64[G2048_PLAY_STATS_WORDS], ACCUMULATED into (caller zeroes):
+ *           [0] episodes, [1] env-steps, [2] sum of scores, [3] envs cut short by n_subs,
+ *           [4] envs with the overflow flag, [5] longest episode, [6] sum max_tile, [7] sum max_tile^2,
+ *           [16+e] episodes whose max tile is 2^e (e = 0..15). */
+int g2048_play(int policy, const uint32_t* d_subs, int64_t n_subs, int64_t batch_global, int64_t env_lo, int64_t n,
+               int rng_mode, uint64_t* d_work, uint64_t* d_final_boards, uint32_t* d_lengths, uint32_t* d_scores,
+               uint64_t* d_stats, void* stream);
+
+/* Host-buffer form of the same call (the reference-facing entry: run_actions_max_tile's inner
+ * run).  seed -> jax.random.key(seed); h_key_io (2 words, may be NULL) overrides the seed with an
+ * explicit chain key and receives the key the reference's runner would hold afterwards.
+ * h_* outputs may be NULL.  Copies H2D/D2H and synchronises. */
+int g2048_play_host(int policy, uint64_t seed, uint32_t* h_key_io, int64_t batch_global, int64_t env_lo, int64_t n,
+                    int rng_mode, uint64_t* h_final_boards, uint32_t* h_lengths, uint32_t* h_scores,
+                    uint64_t* h_stats);
+
+/* Lock-step recorded rollout: `n_steps` loop steps of src/runs/batch_runner.py:117-136 for
+ * act_randomly / act_drul in one kernel, state kept in registers in between.
+ * Records are time-major (row t_local of each array has n entries):
+ *   d_rec_boards uint64  pre-step board            (observation stored at :121,130)
+ *   d_rec_meta   uint8   bits 0-1 action, 2-5 pre-step legal mask, 6 post-step done
+ *   d_rec_rewards float32 post-step reward; d_rec_log_probs float32 (random only, else NULL)
+ * d_subs points at the act sub key of the first of these steps (pairs act, step).
+ * d_counters uint64[4] accumulated: [0] envs that terminated in this call, [1] max over envs of
+ * (first-done loop step + 1) (atomicMax), [2] env-steps of live envs, [3] sum of rewards > 0.
+ * t0 = loop step index of the first step (for [1]). */
+int g2048_rollout_steps(int policy, uint64_t* d_boards, uint8_t* d_status, const uint32_t* d_subs, int64_t n_steps,
+                        int64_t t0, int64_t batch_global, int64_t env_lo, int64_t n, int rng_mode,
+                        uint64_t* d_rec_boards, uint8_t* d_rec_meta, float* d_rec_rewards, float* d_rec_log_probs,
+                        uint64_t* d_counters, void* stream);
+
+/* ---- policy-logit sampling fused with the step and the rollout-buffer write
+ * (src/ppo/torch_action_wrapper.py:84-102 + src/ppo/ppo_agent.py:117-121 + env.step + the
+ * bookkeeping of src/runs/batch_runner.py:130-136).  One loop step:
+ *   logits (n,4) f32 straight from the network; if use_mask: logits - 1e8*(1-mask);
+ *   clip to >= -FLT_MAX; action = categorical(split(*d_sub_act,B)[e], logits) or argmax;
+ *   log_prob = logits[a] - logsumexp(logits); step with split(*d_sub_step,B)[e];
+ *   record row: pre-step board, meta, reward, log_prob, value (copied from d_values, may be NULL).
+ * auto_reset != 0: a finished env is re-initialised with init(split(step_key)[1]) after the step
+ * (pgx.experimental.auto_reset semantics: done/reward of the finishing step are kept). */
+int g2048_policy_step(uint64_t* d_boards, uint8_t* d_status, const float* d_logits, const float* d_values,
+                      int use_mask, int sample, int auto_reset, const uint32_t* d_sub_act, const uint32_t* d_sub_step,
+                      int64_t batch_global, int64_t env_lo, int64_t n, int rng_mode, uint64_t* d_rec_boards,
+                      uint8_t* d_rec_meta, float* d_rec_rewards, float* d_rec_log_probs, float* d_rec_values,
+                      int32_t* d_actions_out, void* stream);
+
+/* Only the sampling part (A6/A7), for parity tests and for callers that step separately. */
+int g2048_sample_logits(const float* d_logits, const uint8_t* d_status, int use_mask, int sample,
+                        const uint32_t* d_sub_act, int64_t batch_global, int64_t env_lo, int64_t n, int rng_mode,
+                        int32_t* d_actions, float* d_log_probs, float* d_entropy, void* stream);
+
+/* log_prob / entropy of GIVEN actions under (masked) logits: PPOAgent.evaluate_actions'
+ * Categorical part (src/ppo/ppo_agent.py:182-189). */
+int g2048_evaluate_logits(const float* d_logits, const uint8_t* d_mask_bits, int use_mask, const int32_t* d_actions,
+                          int64_t n, float* d_log_probs, float* d_entropy, void* stream);
+
+/* ---- observation / record materialisation (HBM-bound) */
+
+/* One-hot observation of n boards: out[i, cell, c] = (exponent(cell) == c), (n,16,31) = pgx
+ * observe() flattened as src/runs/run_actions_max_tile.py:61 and RolloutBuffer do.  dtype = G2048_OBS_*.
+ * If row_stride_boards > 0 the boards are read as a (rows, n_cols) time-major record matrix and
+ * written env-major: out index = col * rows + row (the (B,T,...) stacking of batch_runner.py:138). */
+int g2048_expand_obs(const uint64_t* d_boards, int64_t n, int dtype, void* d_out, int64_t rows, int64_t n_cols,
+                     void* stream);
+
+/* Inverse of g2048_expand_obs: argmax over the 31 channels of every cell (the
+ * `observations.argmax(-1)` of src/runs/run_actions_max_tile.py:61-63).  dtype BOOL or F32. */
+int g2048_pack_obs(const void* d_obs, int dtype, int64_t n, uint64_t* d_boards, void* stream);
+
+/* status byte -> pgx State.legal_action_mask (n,4) uint8 and State.terminated (n) uint8 */
+int g2048_unpack_status(const uint8_t* d_status, int64_t n, uint8_t* d_masks, uint8_t* d_terminated, void* stream);
+
+/* Unpack time-major (T,B) record rows into the reference's env-major (B,T) arrays
+ * (src/runs/batch_runner.py:138-144): actions int32, masks uint8 (B,T,4), terminations uint8,
+ * rewards / log_probs / values float32 transposed.  Any output may be NULL. */
+int g2048_unpack_records(const uint8_t* d_rec_meta, const float* d_rec_rewards, const float* d_rec_log_probs,
+                         const float* d_rec_values, int64_t t_steps, int64_t n, int32_t* d_actions, uint8_t* d_masks,
+                         uint8_t* d_terminations, float* d_rewards, float* d_log_probs, float* d_values,
+                         void* stream);
+
+/* RolloutBuffer.store_batch (src/ppo/rollout_buffer.py:164-187): per-env kept length
+ * (first done + 1, or 0 if the env never terminated in t_steps) from the time-major meta. */
+int g2048_episode_lengths(const uint8_t* d_rec_meta, int64_t t_steps, int64_t n, uint32_t* d_lengths, void* stream);
+
+/* exclusive prefix sum of n uint32 into int64 offsets (n+1 entries, last = total) */
+int g2048_exclusive_scan(const uint32_t* d_in, int64_t n, int64_t* d_out, void* stream);
+
+/* Ragged env-major compaction of time-major records into flat packed arrays (what
+ * store_batch + get_buffer_data produce, src/ppo/rollout_buffer.py:164-206, minus the one-hot
+ * expansion): flat index = d_offsets[e] + t for t < d_lengths[e].  out_base is added to every
+ * flat index (appending after earlier batches).  Outputs may be NULL. */
+int g2048_compact_records(const uint64_t* d_rec_boards, const uint8_t* d_rec_meta, const float* d_rec_rewards,
+                          const float* d_rec_log_probs, const float* d_rec_values, int64_t t_steps, int64_t n,
+                          const uint32_t* d_lengths, const int64_t* d_offsets, int64_t out_base,
+                          uint64_t* d_boards, uint8_t* d_meta, float* d_rewards, float* d_log_probs, float* d_values,
+                          void* stream);
+
+/* flat packed meta -> reference-format columns: actions one-hot f32 (N,4), masks uint8 (N,4),
+ * terminations uint8 (N) (src/ppo/ppo_trainer.py:197-202, rollout_buffer.py:199-205) */
+int g2048_unpack_flat_meta(const uint8_t* d_meta, int64_t n, float* d_actions_onehot, uint8_t* d_masks,
+                           uint8_t* d_terminations, void* stream);
+
+/* ---- GAE (src/ppo/data_loader.py:103-130) and normalisation (:61-67) */
+
+/* Flat buffer, reverse segmented scan: if done[t]: last_v = last_gae = 0;
+ * delta = r[t] + gamma*last_v - V[t]; gae = delta + gamma*lambda*gae; adv[t]=gae; ret[t]=gae+V[t].
+ * Single pass, decoupled look-back across CTAs.  d_scan_state: scratch of
+ * g2048_gae_flat_scratch_bytes(n) bytes, zeroed by the caller.  d_moments (double[6], may be NULL,
+ * ACCUMULATED): [0] n, [1] sum adv, [2] sum adv^2, [3] sum ret, [4] sum ret^2, [5] unused. */
+int64_t g2048_gae_flat_scratch_bytes(int64_t n);
+int g2048_gae_flat(const float* d_rewards, const float* d_values, const uint8_t* d_dones, int64_t n, double gamma,
+                   double lambda_gae, float* d_adv, float* d_ret, void* d_scan_state, double* d_moments, void* stream);
+
+/* Time-major (T,B) buffer, one lane per env, exactly the reference's operation order per env;
+ * d_bootstrap (n) float32 or NULL is V(s_T) for envs whose last step is not done (fixed-horizon
+ * rollouts with auto-reset; the reference itself never bootstraps). */
+int g2048_gae_time_major(const float* d_rewards, const float* d_values, const uint8_t* d_rec_meta, int64_t t_steps,
+                         int64_t n, const float* d_bootstrap, double gamma, double lambda_gae, float* d_adv,
+                         float* d_ret, double* d_moments, void* stream);
+
+/* x = (x - mean) / (std + 1e-8) in place with mean / unbiased std from the moments block
+ * (sum at d_moments[which], sum of squares at [which+1], count at [0]); which = 1 (adv) or 3 (ret). */
+int g2048_normalize(float* d_x, int64_t n, const double* d_moments, int which, void* stream);
+
+/* Host-buffer GAE + normalisation (the PPODataset.__init__ path) */
+int g2048_gae_host(const float* h_rewards, const float* h_values, const uint8_t* h_dones, int64_t n, double gamma,
+                   double lambda_gae, int normalize, float* h_adv, float* h_ret);
+
+/* ---- statistics (src/stats/running_stats_vec.py:55-87) */
+
+/* per feature row of x (F, n) float64: count, mean, population variance -> d_out (F,3) double */
+int g2048_row_moments(const double* d_x, int64_t n_features, int64_t n, double* d_out, void* stream);
+
+/* ---- measurement helpers */
+
+/* Integer-issue roofline probe: every thread runs `iters` dependent-chain rounds of the Threefry
+ * instruction mix (ADD / SHF.L.W / LOP3) on `chains` independent chains; writes one word per
+ * thread so nothing is optimised away.  Instructions executed = blocks*threads*iters*chains*3. */
+int g2048_int_peak_probe(int blocks, int threads, int iters, uint32_t* d_sink, void* stream);
+
+#ifdef __cplusplus
+}
+#endif
+#endif /* G2048_H_ */
