@@ -32,7 +32,8 @@ __device__ __forceinline__ void block_sum4(double v[4], double* s_red /* [4][4] 
     __syncthreads();
     if (threadIdx.x < 4) {
         const int k = threadIdx.x;
-        const double t = s_red[k * 4 + 0] + s_red[k * 4 + 1] + s_red[k * 4 + 2] + s_red[k * 4 + 3];
+        double t = 0.0;
+        for (int w = 0; w < (int)(blockDim.x >> 5); ++w) t += s_red[k * 4 + w];
         atomicAdd(&moments[1 + k], t);
     }
 }
@@ -40,7 +41,8 @@ __device__ __forceinline__ void block_sum4(double v[4], double* s_red /* [4][4] 
 // One CTA per tile of 1024 consecutive steps, tiles taken from the END of the buffer by ticket.
 //   1. coalesced loads of r, V, done into shared memory (+ V of the step after the tile);
 //   2. warp-shuffle prefix sum of per-thread done counts -> ordered list of episode ends;
-//   3. one thread per episode end walks its episode backwards inside shared memory;
+//   3. delta[t] for every step in parallel; then one thread per episode end walks its episode
+//      backwards inside shared memory with one multiply-add per step;
 //   4. the steps after the tile's last `done` belong to an episode that ends in a later tile:
 //      one thread waits for that tile's first-step gae (published through global memory, decoupled
 //      look-back of depth one) and walks them;
@@ -76,6 +78,16 @@ gae_flat_kernel(const float* __restrict__ rewards, const float* __restrict__ val
     if (threadIdx.x == 0) s_v[len] = (lo + len < n) ? values[lo + len] : 0.0f;  // V of the next step (0 past the end)
     __syncthreads();
 
+    // delta[t] = (r[t] + gamma * V[t+1]) - V[t], with V[t+1] := 0 after a done step -- elementwise, so
+    // every thread helps; the serial part below is then one multiply-add per step.
+    float delta_reg[GAE_ITEMS];
+#pragma unroll
+    for (int k = 0; k < GAE_ITEMS; ++k) {
+        const int i = threadIdx.x + k * GAE_THREADS;
+        const float next_v = s_d[i] ? 0.0f : s_v[i + 1];
+        delta_reg[k] = (s_r[i] + gamma * next_v) - s_v[i];
+    }
+
     // ordered list of done positions
     const int base = threadIdx.x * GAE_ITEMS;
     unsigned int bits = 0;
@@ -89,7 +101,9 @@ gae_flat_kernel(const float* __restrict__ rewards, const float* __restrict__ val
         if (lane >= off) incl += y;
     }
     if (lane == 31) s_warp_count[warp] = incl;
-    __syncthreads();
+    __syncthreads();  // also: every s_r[i] has been read into delta_reg
+#pragma unroll
+    for (int k = 0; k < GAE_ITEMS; ++k) s_r[threadIdx.x + k * GAE_THREADS] = delta_reg[k];
     int before = incl - cnt;
     int n_done = 0;
 #pragma unroll
@@ -108,18 +122,23 @@ gae_flat_kernel(const float* __restrict__ rewards, const float* __restrict__ val
     }
     __syncthreads();
 
-    // walk one episode (or episode fragment) backwards: steps (first, last], carry given
-    auto walk = [&](int last, int first_excl, float last_gae, float last_v) {
-        for (int t = last; t > first_excl; --t) {
-            if (s_d[t]) {
-                last_v = 0.0f;
-                last_gae = 0.0f;
+    // walk one episode (or fragment) backwards over steps (first_excl, last]: gae = delta + gl * gae.
+    // A done step starts with gae = 0, which is what the reference's reset computes (delta + gl * 0).
+    auto walk = [&](int last, int first_excl, float g) {
+        int t = last;
+        for (; t - 8 >= first_excl; t -= 8) {
+            float d[8];
+#pragma unroll
+            for (int k = 0; k < 8; ++k) d[k] = s_r[t - k];
+#pragma unroll
+            for (int k = 0; k < 8; ++k) {
+                g = d[k] + gamma_lambda * g;
+                s_adv[t - k] = g;
             }
-            const float v = s_v[t];
-            const float delta = (s_r[t] + gamma * last_v) - v;
-            last_gae = delta + gamma_lambda * last_gae;
-            s_adv[t] = last_gae;
-            last_v = v;
+        }
+        for (; t > first_excl; --t) {
+            g = s_r[t] + gamma_lambda * g;
+            s_adv[t] = g;
         }
     };
 
@@ -127,7 +146,7 @@ gae_flat_kernel(const float* __restrict__ rewards, const float* __restrict__ val
     for (int s = threadIdx.x; s < n_done; s += GAE_THREADS) {
         const int last = s_end[s];
         const int first_excl = s ? (int)s_end[s - 1] : -1;
-        walk(last, first_excl, 0.0f, 0.0f);
+        walk(last, first_excl, 0.0f);
         if (s == 0) {
             heads[tile] = s_adv[0];
             __threadfence();
@@ -140,11 +159,11 @@ gae_flat_kernel(const float* __restrict__ rewards, const float* __restrict__ val
         if (first_excl < len - 1) {
             float carry = 0.0f;
             if (lo + len < n) {
-                while (flags[tile + 1] == 0u) __nanosleep(64);
+                while (flags[tile + 1] == 0u) __nanosleep(32);
                 __threadfence();
                 carry = heads[tile + 1];
             }
-            walk(len - 1, first_excl, carry, s_v[len]);
+            walk(len - 1, first_excl, carry);
         }
         if (n_done == 0) {
             heads[tile] = s_adv[0];
@@ -171,11 +190,12 @@ gae_flat_kernel(const float* __restrict__ rewards, const float* __restrict__ val
     }
 }
 
-// Time-major (T,B) records: one lane per env, loads batched 8 steps ahead so that enough bytes
-// are in flight; coalesced along B.
-constexpr int GAE_TM_UNROLL = 8;
+// Time-major (T,B) records: one lane per env, loads batched 16 steps ahead so that enough bytes
+// are in flight even at B = 64 K (one lane per env is all the parallelism there is); coalesced along B.
+constexpr int GAE_TM_UNROLL = 16;
+constexpr int GAE_TM_THREADS = 64;
 
-__global__ void __launch_bounds__(128)
+__global__ void __launch_bounds__(GAE_TM_THREADS)
 gae_time_major_kernel(const float* __restrict__ rewards, const float* __restrict__ values,
                       const uint8_t* __restrict__ meta, int64_t t_steps, int64_t n,
                       const float* __restrict__ bootstrap, float gamma, float gamma_lambda, float* __restrict__ adv,
@@ -277,6 +297,11 @@ extern "C" int g2048_gae_flat(const float* d_rewards, const float* d_values, con
     G2048_REQUIRE(d_rewards && d_values && d_dones && d_adv && d_ret && d_scan_state, "gae_flat: pointers");
     const int64_t n_tiles = (n + GAE_TILE - 1) / GAE_TILE;
     G2048_REQUIRE(n_tiles <= 0x7FFFFFFFll, "gae_flat: too many steps");
+    static bool carveout_set = false;  // 14 CTAs of 15.5 KiB per SM need the shared-memory-heavy L1 split
+    if (!carveout_set) {
+        cudaFuncSetAttribute(gae_flat_kernel, cudaFuncAttributePreferredSharedMemoryCarveout, cudaSharedmemCarveoutMaxShared);
+        carveout_set = true;
+    }
     gae_flat_kernel<<<(unsigned)n_tiles, GAE_THREADS, 0, (cudaStream_t)stream>>>(
         d_rewards, d_values, d_dones, n, n_tiles, (float)gamma, (float)(gamma * lambda_gae), d_adv, d_ret,
         (GaeScratch*)d_scan_state, d_moments);
@@ -290,7 +315,7 @@ extern "C" int g2048_gae_time_major(const float* d_rewards, const float* d_value
     G2048_REQUIRE(t_steps >= 0 && n >= 0, "gae_time_major: shape");
     if (t_steps == 0 || n == 0) return G2048_OK;
     G2048_REQUIRE(d_rewards && d_values && d_rec_meta && d_adv && d_ret, "gae_time_major: pointers");
-    gae_time_major_kernel<<<blocks_for(n, 128), 128, 0, (cudaStream_t)stream>>>(
+    gae_time_major_kernel<<<blocks_for(n, GAE_TM_THREADS), GAE_TM_THREADS, 0, (cudaStream_t)stream>>>(
         d_rewards, d_values, d_rec_meta, t_steps, n, d_bootstrap, (float)gamma, (float)(gamma * lambda_gae), d_adv,
         d_ret, d_moments);
     G2048_CHECK_LAUNCH("gae_time_major");

@@ -1,0 +1,121 @@
+"""GAE / returns / normalisation and the PPO dataset -- the reference's src/ppo/data_loader.py.
+
+``compute_gae`` is the device path: flat packed buffer in, advantages and returns out, the
+reverse recurrence of data_loader.py:103-130 run by ``g2048_gae_flat`` (bit-identical to the
+reference's fp32 loop) and the global normalisation of :61-67 by ``g2048_normalize``; under
+``torch.distributed`` the normalisation moments are all-reduced so that a sharded buffer is
+normalised with the global mean / std.
+
+``PPODataset`` / ``create_ppo_dataloader`` keep the reference's constructor and item schema.
+"""
+from __future__ import annotations
+
+from typing import Dict
+
+import numpy as np
+import torch
+from torch.utils.data import DataLoader, Dataset
+
+from .. import _native as N
+from .. import engine as E
+
+
+def compute_gae(rewards: torch.Tensor, values: torch.Tensor, terminations: torch.Tensor, gamma: float = 0.99,
+                lambda_gae: float = 0.95, normalize: bool = True, group=None):
+    """Flat device buffers (N,) -> (advantages, returns) float32 device tensors.
+
+    terminations: uint8 / bool, or the packed meta bytes (bit 6 = done) with ``terminations_is_meta``
+    handled by the caller through ``meta_to_dones``.
+    """
+    dones = terminations if terminations.dtype == torch.uint8 else terminations.to(torch.uint8)
+    adv, ret, moments = E.gae_flat(rewards.contiguous(), values.contiguous(), dones.contiguous(), gamma, lambda_gae)
+    if normalize:
+        if group is not None or (torch.distributed.is_available() and torch.distributed.is_initialized()
+                                 and torch.distributed.get_world_size() > 1):
+            from ..dist import allreduce_sum_
+
+            allreduce_sum_(moments, group)
+        E.normalize_(adv, moments, 1)
+        E.normalize_(ret, moments, 3)
+    return adv, ret
+
+
+def meta_to_dones(meta: torch.Tensor) -> torch.Tensor:
+    """Packed meta bytes -> uint8 done flags."""
+    _, _, term = E.unpack_flat_meta(meta)
+    return term.view(torch.uint8)
+
+
+class PPODataset(Dataset):
+    """Dataset over RolloutBuffer data with GAE advantages and returns (data_loader.py:8-166)."""
+
+    def __init__(self, buffer_data: Dict[str, np.ndarray], gamma: float = 0.99, lambda_gae: float = 0.95,
+                 max_samples_per_epoch: int = None, shuffle_on_reset: bool = False):
+        self.gamma = gamma
+        self.lambda_gae = lambda_gae
+        self.max_samples_per_epoch = max_samples_per_epoch
+        self.shuffle_on_reset = shuffle_on_reset
+
+        self.observations = torch.from_numpy(buffer_data["observations"]).float()
+        self.actions = torch.from_numpy(buffer_data["actions"]).float()
+        self.action_masks = torch.from_numpy(buffer_data["action_masks"]).bool()
+        self.rewards = torch.from_numpy(buffer_data["rewards"]).float()
+        self.values = torch.from_numpy(buffer_data["values"]).float()
+        self.log_probs = torch.from_numpy(buffer_data["log_probs"]).float()
+        self.terminations = torch.from_numpy(buffer_data["terminations"]).bool()
+
+        # advantages and returns: raw (as _compute_gae_returns gives them) and normalised
+        self.raw_advantages, self.raw_returns = self._compute_gae_returns()
+        adv, ret = E.gae_host(self.rewards.numpy(), self.values.numpy(), self.terminations.numpy().astype(np.uint8),
+                              gamma, lambda_gae, True) if len(self.rewards) else (np.zeros(0, np.float32),) * 2
+        self.advantages = torch.from_numpy(adv)
+        self.returns = torch.from_numpy(ret)
+
+        self.total_length = len(self.observations)
+        if self.max_samples_per_epoch is None or self.max_samples_per_epoch >= self.total_length:
+            self.length = self.total_length
+            self.active_indices = None
+        else:
+            self.length = self.max_samples_per_epoch
+            self.active_indices = self._sample_indices()
+
+    def _sample_indices(self) -> torch.Tensor:
+        return torch.randperm(self.total_length)[: self.length]
+
+    def reset_epoch(self):
+        if self.shuffle_on_reset and self.active_indices is not None:
+            self.active_indices = self._sample_indices()
+
+    def _compute_gae_returns(self):
+        """Un-normalised advantages / returns (data_loader.py:103-130) through the CUDA kernel."""
+        if len(self.rewards) == 0:
+            return torch.zeros_like(self.rewards), torch.zeros_like(self.rewards)
+        adv, ret = E.gae_host(self.rewards.numpy(), self.values.numpy(), self.terminations.numpy().astype(np.uint8),
+                              self.gamma, self.lambda_gae, False)
+        return torch.from_numpy(adv), torch.from_numpy(ret)
+
+    def __len__(self) -> int:
+        return self.length
+
+    def __getitem__(self, idx: int) -> Dict[str, torch.Tensor]:
+        actual_idx = self.active_indices[idx] if self.active_indices is not None else idx
+        return {
+            "observations": self.observations[actual_idx],
+            "actions": self.actions[actual_idx],
+            "action_masks": self.action_masks[actual_idx],
+            "rewards": self.rewards[actual_idx],
+            "values": self.values[actual_idx],
+            "log_probs": self.log_probs[actual_idx],
+            "terminations": self.terminations[actual_idx],
+            "advantages": self.advantages[actual_idx],
+            "returns": self.returns[actual_idx],
+        }
+
+
+def create_ppo_dataloader(buffer_data: Dict[str, np.ndarray], gamma: float = 0.99, lambda_gae: float = 0.95,
+                          batch_size: int = 32, shuffle: bool = True, drop_last: bool = True, num_workers: int = 0,
+                          max_samples_per_epoch: int = None, shuffle_on_reset: bool = False) -> DataLoader:
+    """Same factory as data_loader.py:169-223."""
+    dataset = PPODataset(buffer_data, gamma=gamma, lambda_gae=lambda_gae,
+                         max_samples_per_epoch=max_samples_per_epoch, shuffle_on_reset=shuffle_on_reset)
+    return DataLoader(dataset, batch_size=batch_size, shuffle=shuffle, drop_last=drop_last, num_workers=num_workers)

@@ -1,0 +1,153 @@
+"""RolloutBuffer -- the reference's src/ppo/rollout_buffer.py:4-206 backed by device memory.
+
+The reference appends one Python object per step (store_batch, :164-187) and converts the lists
+to arrays in get_buffer_data (:198-206; 2 017 bytes per step).  Here the buffer holds packed
+records on the GPU -- bitboard 8 B + meta 1 B + reward/value/log-prob 12 B per step -- filled by
+one compaction kernel per batch (``g2048_compact_records``: keep steps 0..first_done of every env,
+env-major), and the reference-format arrays are produced on demand by ``g2048_expand_obs`` /
+``g2048_unpack_flat_meta``.
+
+``store_packed(rollout)`` takes a ``BatchRunner.run_packed_batch`` result without leaving the
+device; ``store_batch(...)`` keeps the reference's numpy signature.
+"""
+from __future__ import annotations
+
+import numpy as np
+import torch
+
+from .. import _native as N
+from .. import engine as E
+
+
+class RolloutBuffer:
+    """Stores the trajectories of an environment/agent pair for PPO training."""
+
+    def __init__(self, observation_dim: int, observation_length: int | list | tuple, action_dim: int) -> None:
+        self.observation_dim = observation_dim
+        self.observation_length = observation_length
+        self.action_dim = action_dim
+        self.reset()
+
+    def reset(self):
+        """Resets the buffer to its initial state."""
+        self._parts = []  # list of (boards, meta, rewards, values, log_probs) flat device tensors
+        self.buffer_size = 0
+
+    # -- reference validation (rollout_buffer.py:58-126), same messages -------------------------
+    def _validate_and_reshape_observations(self, observations: np.ndarray) -> np.ndarray:
+        if isinstance(self.observation_length, (tuple, list)):
+            expected_obs_dims = (*self.observation_length, self.observation_dim)
+        else:
+            expected_obs_dims = (self.observation_length, self.observation_dim)
+        if len(observations.shape) < 2:
+            raise ValueError(
+                f"Observations must have at least 2 dimensions (batch_size, time_steps, ...), "
+                f"but got shape {observations.shape}"
+            )
+        batch_size, time_steps = observations.shape[:2]
+        if observations.shape[2:] == expected_obs_dims:
+            return observations
+        try:
+            expected_obs_elements = np.prod(expected_obs_dims)
+            flattened_obs = observations.reshape(batch_size, time_steps, -1)
+            if flattened_obs.shape[2] == expected_obs_elements:
+                return flattened_obs.reshape(batch_size, time_steps, *expected_obs_dims)
+            raise ValueError(
+                f"Cannot reshape observations from shape {observations.shape} to expected shape "
+                f"(batch_size, time_steps, {expected_obs_dims}). "
+                f"Flattened observations have {flattened_obs.shape[2]} elements per timestep "
+                f"but expected {expected_obs_elements} elements."
+            )
+        except Exception as e:
+            raise ValueError(
+                f"Failed to reshape observations from shape {observations.shape} to expected shape "
+                f"(batch_size, time_steps, {expected_obs_dims}). Error: {str(e)}"
+            )
+
+    # -- storing --------------------------------------------------------------------------------
+    def store_packed(self, rollout) -> int:
+        """Append a ``PackedRollout`` (time-major device records).  Returns the steps kept."""
+        t, b = rollout.t_steps, rollout.batch_size
+        return self._compact(rollout.boards, rollout.meta, rollout.rewards, rollout.log_probs, rollout.values, t, b)
+
+    def store_batch(self, observations, actions, action_masks, rewards, values, log_probs, terminations):
+        """Reference signature (rollout_buffer.py:128-187): env-major (B, T, ...) numpy arrays,
+        observations one-hot, actions one-hot (B,T,action_dim) or indices (B,T)."""
+        observations = self._validate_and_reshape_observations(np.asarray(observations))
+        dev = N.require_cuda()
+        b, t = observations.shape[:2]
+        if b == 0 or t == 0:
+            return 0
+        if self.observation_dim != 31 or int(np.prod(observations.shape[2:-1])) != 16:
+            raise ValueError("this buffer packs 2048 observations: (..., 16, 31) one-hot")
+        obs_t = torch.from_numpy(np.ascontiguousarray(observations)).to(dev)
+        if obs_t.dtype not in (torch.bool, torch.uint8, torch.float32):
+            obs_t = obs_t.to(torch.float32)
+        boards = E.pack_obs(obs_t.contiguous()).view(b, t)
+        actions = np.asarray(actions)
+        act_idx = actions.argmax(-1) if actions.ndim == 3 else actions
+        mask_bits = (np.asarray(action_masks).astype(np.uint8) * np.array([1, 2, 4, 8], np.uint8)).sum(-1)
+        meta = (act_idx.astype(np.uint8) & 3) | (mask_bits.astype(np.uint8) << 2) | (np.asarray(terminations).astype(np.uint8) << 6)
+        tm = lambda a, dt: torch.from_numpy(np.ascontiguousarray(np.asarray(a).T.astype(dt))).to(dev)  # noqa: E731
+        return self._compact(
+            boards.t().contiguous(), tm(meta, np.uint8), tm(rewards, np.float32),
+            None if log_probs is None else tm(log_probs, np.float32),
+            None if values is None else tm(values, np.float32), t, b,
+        )
+
+    def _compact(self, rec_boards, rec_meta, rec_rewards, rec_log_probs, rec_values, t, b) -> int:
+        dev = rec_meta.device
+        lengths = E.episode_lengths(rec_meta, t, b)
+        offsets = E.exclusive_scan(lengths)
+        total = int(offsets[-1].item())
+        if total == 0:
+            return 0
+        boards = torch.empty(total, dtype=torch.int64, device=dev)
+        meta = torch.empty(total, dtype=torch.uint8, device=dev)
+        rewards = torch.empty(total, dtype=torch.float32, device=dev)
+        # a policy without log-probs / values (act_drul, act_randomly) stores zeros, like float32(None) would not
+        log_probs = torch.zeros(total, dtype=torch.float32, device=dev)
+        values = torch.zeros(total, dtype=torch.float32, device=dev)
+        E.compact_records(rec_boards, rec_meta, rec_rewards, rec_log_probs, rec_values, t, b, lengths, offsets, 0,
+                          boards, meta, rewards, log_probs, values)
+        self._parts.append((boards, meta, rewards, values, log_probs))
+        self.buffer_size += total
+        return total
+
+    # -- reading --------------------------------------------------------------------------------
+    def get_packed(self) -> dict:
+        """Flat device tensors: boards int64, meta uint8, rewards / values / log_probs float32."""
+        if not self._parts:
+            dev = N.require_cuda()
+            z = lambda dt: torch.empty(0, dtype=dt, device=dev)  # noqa: E731
+            return dict(boards=z(torch.int64), meta=z(torch.uint8), rewards=z(torch.float32),
+                        values=z(torch.float32), log_probs=z(torch.float32))
+        if len(self._parts) > 1:
+            self._parts = [tuple(torch.cat([p[i] for p in self._parts]) for i in range(5))]
+        boards, meta, rewards, values, log_probs = self._parts[0]
+        return dict(boards=boards, meta=meta, rewards=rewards, values=values, log_probs=log_probs)
+
+    def get_buffer_data(self):
+        """Reference format (rollout_buffer.py:198-206): dict of numpy arrays."""
+        p = self.get_packed()
+        n = p["boards"].shape[0]
+        if n == 0:
+            return {
+                "observations": np.array([], dtype=np.float32), "actions": np.array([], dtype=np.float32),
+                "action_masks": np.array([], dtype=bool), "rewards": np.array([], dtype=np.float32),
+                "values": np.array([], dtype=np.float32), "log_probs": np.array([], dtype=np.float32),
+                "terminations": np.array([], dtype=bool),
+            }
+        obs = E.expand_obs(p["boards"], torch.float32)
+        onehot, masks, term = E.unpack_flat_meta(p["meta"])
+        if isinstance(self.observation_length, (tuple, list)):
+            obs = obs.view(n, *self.observation_length, self.observation_dim)
+        return {
+            "observations": obs.cpu().numpy(),
+            "actions": onehot.cpu().numpy(),
+            "action_masks": masks.cpu().numpy(),
+            "rewards": p["rewards"].cpu().numpy(),
+            "values": p["values"].cpu().numpy(),
+            "log_probs": p["log_probs"].cpu().numpy(),
+            "terminations": term.cpu().numpy(),
+        }

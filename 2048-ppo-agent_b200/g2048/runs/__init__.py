@@ -1,0 +1,5 @@
+from .batch_runner import BatchRunner, PackedRollout
+from .run_actions_batch import run_actions_batch
+from .run_actions_max_tile import run_actions_max_tile
+
+__all__ = ["BatchRunner", "PackedRollout", "run_actions_batch", "run_actions_max_tile"]

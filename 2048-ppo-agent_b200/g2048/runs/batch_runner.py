@@ -1,0 +1,283 @@
+"""BatchRunner -- same surface as the reference's src/runs/batch_runner.py:10-195, with the
+host `while` loop (three jitted dispatches and one blocking readback per step) replaced by
+libg2048 kernels that keep every env in registers.
+
+    runner = BatchRunner(init_seed=0, act_fn=act_randomly)
+    obs, actions, masks, log_probs, values, rewards, terminations = runner.run_actions_batch(1024)
+
+Which kernels run depends on the policy handed in as ``act_fn``:
+  * ``act_randomly`` / ``act_drul`` (objects with ``policy_id``): the fused lock-step kernel
+    ``g2048_rollout_steps`` records whole chunks of steps per launch; ``run_stats_batch`` uses the
+    persistent ``g2048_play`` kernel when only per-episode results are wanted.
+  * ``TorchActionFunction``: one network forward (PyTorch) + one ``g2048_policy_step`` launch per
+    step (mask, categorical sample, log-prob, env step and record write fused).
+  * any other callable ``(keys (B,2), obs (B,4,4,31) bool, mask (B,4) bool) -> (action, log_prob,
+    value)`` on torch tensors: per-step ``g2048_split_keys`` / ``g2048_env_step`` launches around it.
+
+Differences from the reference that a caller can see ("defects"):
+  * tensors are torch / numpy instead of jax arrays, keys are uint32 word pairs;
+  * ``log_probs`` / ``values`` are returned as ``None`` when the policy yields ``None`` (the
+    reference's np.stack on a list of None raises);
+  * ``rng_mode`` selects jax's Threefry counter layout (default: partitionable, as in jax 0.5.3).
+"""
+from __future__ import annotations
+
+from dataclasses import dataclass
+from typing import Callable
+
+import numpy as np
+import torch
+
+from .. import _native as N
+from .. import engine as E
+from ..keys import KeyChain
+from ..state import State
+
+ENV_ID = "2048"
+CHUNK_STEPS = 64
+
+
+@dataclass
+class PackedRollout:
+    """A finished run in the engine's own format: time-major (T, B) device records.
+
+    boards  int64  pre-step bitboards          meta   uint8  action | mask << 2 | done << 6
+    rewards float32 post-step                  log_probs / values float32 or None
+    final_boards / final_status: the state after the last step.
+    """
+
+    boards: torch.Tensor
+    meta: torch.Tensor
+    rewards: torch.Tensor
+    log_probs: torch.Tensor | None
+    values: torch.Tensor | None
+    final_boards: torch.Tensor
+    final_status: torch.Tensor
+    t_steps: int
+    batch_size: int
+    env_steps: int  # steps taken by live envs (what the reference's RolloutBuffer keeps)
+
+    def lengths(self) -> torch.Tensor:
+        return E.episode_lengths(self.meta, self.t_steps, self.batch_size)
+
+
+class BatchRunner:
+    """Runs batches of 2048 envs with an action function (reference: batch_runner.py:10-37)."""
+
+    def __init__(self, init_seed: int, act_fn: Callable = None, rng_mode=None, device=None,
+                 shard: tuple[int, int] | None = None):
+        """
+        init_seed : seed of the runner's key chain (jax.random.key(seed), batch_runner.py:32)
+        act_fn    : policy, see the module docstring; may be set later through ``.act_fn``
+        rng_mode  : None / "partitionable" / "original"
+        shard     : (rank, world) -- this process owns a contiguous slice of every batch; env
+                    indices stay global, so the union over ranks equals the single-GPU run.
+        """
+        self.device = N.require_cuda() if device is None else torch.device(device)
+        self.rng_mode = E.resolve_rng_mode(rng_mode)
+        self.chain = KeyChain(init_seed, self.rng_mode, self.device)
+        self.shard = shard
+        self._act_fn = act_fn
+
+    # -- reference surface ---------------------------------------------------------------------
+    @property
+    def key(self) -> np.ndarray:
+        """The chain key as two uint32 words (the reference's ``self.key``)."""
+        return self.chain.key
+
+    @property
+    def act_fn(self):
+        return self._act_fn
+
+    @act_fn.setter
+    def act_fn(self, act_fn: Callable):
+        self._act_fn = act_fn
+
+    def run_actions_batch(self, batch_size: int):
+        """-> (observations (B,T,4,4,31) bool, actions (B,T) int32, action_masks (B,T,4) bool,
+        log_probs (B,T) f32 | None, values (B,T) f32 | None, rewards (B,T) f32, terminations (B,T) bool),
+        numpy arrays stacked like batch_runner.py:138-154."""
+        ro = self.run_packed_batch(batch_size)
+        t, b = ro.t_steps, ro.batch_size
+        obs = E.expand_obs(ro.boards, torch.bool, rows=t, n_cols=b)
+        un = E.unpack_records(ro.meta, ro.rewards, ro.log_probs, ro.values, t, b)
+        to_np = lambda x: None if x is None else x.cpu().numpy()  # noqa: E731
+        return (
+            obs.cpu().numpy().reshape(b, t, 4, 4, 31),
+            to_np(un["actions"]),
+            to_np(un["action_masks"]),
+            to_np(un["log_probs"]),
+            to_np(un["values"]),
+            to_np(un["rewards"]),
+            to_np(un["terminations"]),
+        )
+
+    def run_rollout_batch(self, batch_size: int) -> list:
+        """-> list[State], the init state first (batch_runner.py:156-195)."""
+        return self._run(batch_size, keep_states=True)
+
+    # -- engine-native results -----------------------------------------------------------------
+    def run_packed_batch(self, batch_size: int) -> PackedRollout:
+        """Same run as ``run_actions_batch`` but the records stay packed on the device."""
+        return self._run(batch_size, keep_states=False)
+
+    def run_stats_batch(self, batch_size: int, per_env: bool = True) -> dict:
+        """Play to termination and return only per-episode results (final boards, lengths, scores)
+        and the reduced statistics block.  Built-in policies only: this is the persistent
+        ``g2048_play`` kernel."""
+        self._check(batch_size)
+        policy = getattr(self._act_fn, "policy_id", None)
+        if policy is None:
+            raise ValueError("run_stats_batch needs act_randomly or act_drul")
+        lo, n = self._range(batch_size)
+        max_steps = 2048
+        while True:
+            subs = self.chain.peek(1 + 2 * max_steps)
+            out = E.play(policy, subs, batch_size, lo, n, self.rng_mode, per_env=per_env)
+            stats = self._reduce_stats(out["stats"])
+            st = E.play_stats_dict(stats)
+            if st["cut_short"] == 0:
+                break
+            max_steps *= 4  # an episode outlived the keys that were generated: replay with more
+        self.chain.consume(1 + 2 * st["longest"])
+        out["stats"] = stats
+        out["summary"] = st
+        return out
+
+    # -- internals -----------------------------------------------------------------------------
+    def _check(self, batch_size: int) -> None:
+        if self._act_fn is None:
+            raise ValueError("The action function is not set.")
+        if not isinstance(batch_size, (int, np.integer)) or batch_size <= 0:
+            raise ValueError(f"batch_size must be a positive integer, got {batch_size!r}")
+
+    def _range(self, batch_size: int) -> tuple[int, int]:
+        if self.shard is None:
+            return 0, batch_size
+        rank, world = self.shard
+        lo = batch_size * rank // world
+        hi = batch_size * (rank + 1) // world
+        return lo, hi - lo
+
+    def _reduce_stats(self, stats: torch.Tensor) -> torch.Tensor:
+        if self.shard is None or self.shard[1] == 1:
+            return stats
+        from ..dist import allreduce_play_stats
+
+        return allreduce_play_stats(stats)
+
+    def _all_done(self, done_count: int, n: int) -> bool:
+        if self.shard is None or self.shard[1] == 1:
+            return done_count == n
+        from ..dist import all_ranks_true
+
+        return all_ranks_true(done_count == n, self.device)
+
+    def _run(self, batch_size: int, keep_states: bool):
+        self._check(batch_size)
+        lo, n = self._range(batch_size)
+        dev, mode = self.device, self.rng_mode
+        init_sub = self.chain.peek(1)[0]
+        boards, status = E.env_init(init_sub, batch_size, lo, n, mode)
+        states = [State(boards.clone(), status.clone(), torch.zeros(n, dtype=torch.float32, device=dev))] if keep_states else None
+        policy = getattr(self._act_fn, "policy_id", None)
+        is_net = hasattr(self._act_fn, "forward_logits")
+        counters = torch.zeros(4, dtype=torch.int64, device=dev)
+        chunks = []  # (boards, meta, rewards, log_probs, values) per chunk, time-major
+        t0 = 0
+        want_lp = policy != E.POLICY_DRUL
+        want_v = policy is None
+        while True:
+            # a run whose envs are all finished at init cannot happen (two tiles on an empty board)
+            steps = 1 if keep_states else CHUNK_STEPS
+            subs = self.chain.peek(1 + 2 * (t0 + steps))
+            rb = torch.empty((steps, n), dtype=torch.int64, device=dev)
+            rm = torch.empty((steps, n), dtype=torch.uint8, device=dev)
+            rr = torch.empty((steps, n), dtype=torch.float32, device=dev)
+            rl = torch.empty((steps, n), dtype=torch.float32, device=dev) if want_lp else None
+            rv = torch.empty((steps, n), dtype=torch.float32, device=dev) if want_v else None
+            if policy is not None:
+                E.rollout_steps(policy, boards, status, subs[1 + 2 * t0:], steps, t0, batch_size, lo, mode,
+                                rb, rm, rr, rl, counters)
+                done_total = int(counters[0].item())
+                if keep_states:
+                    states.append(State(boards.clone(), status.clone(), rr[0].clone()))
+            else:
+                done_total = None
+                for k in range(steps):
+                    t = t0 + k
+                    sub_act, sub_step = subs[1 + 2 * t], subs[2 + 2 * t]
+                    step_fn = self._net_step if is_net else self._callable_step
+                    rl_k, rv_k = step_fn(boards, status, sub_act, sub_step, batch_size, lo, mode, rb[k], rm[k], rr[k],
+                                         None if rl is None else rl[k], None if rv is None else rv[k])
+                    if rl_k is None:
+                        rl = None  # the policy returns no log-probs (like act_drul)
+                    if rv_k is None:
+                        rv = None
+                    if keep_states:
+                        states.append(State(boards.clone(), status.clone(), rr[k].clone()))
+                    # the reference checks `all done` after every step (batch_runner.py:117)
+                    done_now = int(((status & N.STATUS_DONE) != 0).sum().item())
+                    if self._all_done(done_now, n):
+                        steps_used = k + 1
+                        rb, rm, rr = rb[:steps_used], rm[:steps_used], rr[:steps_used]
+                        rl = None if rl is None else rl[:steps_used]
+                        rv = None if rv is None else rv[:steps_used]
+                        done_total = n
+                        break
+                else:
+                    steps_used = steps
+                steps = steps_used
+            chunks.append((rb, rm, rr, rl, rv))
+            t0 += steps
+            if policy is not None:
+                finished = self._all_done(done_total, n)
+            else:
+                finished = done_total == n
+            if finished:
+                break
+        if policy is not None:
+            t_total = int(counters[1].item())
+            if self.shard is not None and self.shard[1] > 1:
+                from ..dist import allreduce_max_int
+
+                t_total = allreduce_max_int(t_total, self.device)
+        else:
+            t_total = t0
+        self.chain.consume(1 + 2 * t_total)
+        if keep_states:
+            return states[: t_total + 1]
+        cat = lambda i: None if any(c[i] is None for c in chunks) else torch.cat([c[i] for c in chunks])[:t_total].contiguous()  # noqa: E731
+        rb, rm, rr, rl, rv = (cat(i) for i in range(5))
+        if policy is not None:
+            env_steps = int(counters[2].item())
+        else:
+            env_steps = int(E.episode_lengths(rm, t_total, n).sum().item())
+        return PackedRollout(rb, rm, rr, rl, rv, boards, status, t_total, n, env_steps)
+
+    def _net_step(self, boards, status, sub_act, sub_step, batch_size, lo, mode, rb, rm, rr, rl, rv):
+        fn = self._act_fn
+        obs = E.expand_obs(boards, fn.obs_dtype)
+        logits, values = fn.forward_logits(obs)
+        E.policy_step(boards, status, logits, values, fn.use_mask, fn.sample_actions, False, sub_act, sub_step,
+                      batch_size, lo, mode, rb, rm, rr, rl, rv)
+        return rl, rv
+
+    def _callable_step(self, boards, status, sub_act, sub_step, batch_size, lo, mode, rb, rm, rr, rl, rv):
+        n = boards.shape[0]
+        keys = E.split_keys(sub_act, batch_size, lo, n, mode)
+        obs = E.expand_obs(boards, torch.bool).view(n, 4, 4, 31)
+        mask, _ = E.unpack_status(status)
+        action, log_prob, value = self._act_fn(keys, obs, mask)
+        action = torch.as_tensor(action, device=boards.device).to(torch.int32).reshape(n).contiguous()
+        rb.copy_(boards)
+        pre_mask = status & N.STATUS_MASK
+        rewards = E.env_step(boards, status, action, sub_step, batch_size, lo, mode)
+        rr.copy_(rewards)
+        done = (status & N.STATUS_DONE) != 0
+        rm.copy_((action & 3).to(torch.uint8) | (pre_mask << 2) | (done.to(torch.uint8) << 6))
+        if log_prob is not None and rl is not None:
+            rl.copy_(torch.as_tensor(log_prob, device=boards.device).to(torch.float32).reshape(n))
+        if value is not None and rv is not None:
+            rv.copy_(torch.as_tensor(value, device=boards.device).to(torch.float32).reshape(n))
+        return (rl if log_prob is not None else None), (rv if value is not None else None)

@@ -1,0 +1,470 @@
+#!/usr/bin/env python
+"""Benchmark of the rollout hot path (contract: python bench.py --gpus N --steps K --warmup W).
+
+A "step" is one pass of the hot path over one batch: BASELINE.json's C5 workload -- a batch of 2048
+envs is played to termination under the random policy (act_randomly) by the persistent
+`g2048_play` kernel (key chain generated on the device inside the step), followed by the episode
+statistics reduction (NCCL all-reduce when N > 1).  Envs are sharded over the ranks with global env
+indices (weak scaling: 2^21 envs per GPU, 2^24 = C5's 16 M at N = 8).
+
+Prints ONE JSON line.  `value` is device-timed with everything resident in HBM; `e2e` is the same
+metric through the host-buffer C entry point `g2048_play_host` (its own allocations, H2D/D2H copies
+and synchronisation inside the timed region).  `roofline` is the dominant kernel (integer-issue
+bound), `roofline_hbm` lists the HBM-bound rollout-write / GAE kernels, `cpu_baseline` is the
+oracle's C port of the same workload on the host cores.
+
+`--impl reference` times the reference's CPU path.  The reference itself (Pgx on JAX) cannot be
+installed here (jax / pgx / torch2jax are not in the image and there is no network), so this arm
+runs the oracle's C restatement of it -- pinned to the reference's golden artefacts -- with all host
+threads, on a bounded sample of the same workload.
+"""
+from __future__ import annotations
+
+import argparse
+import json
+import os
+import statistics
+import subprocess
+import sys
+import threading
+import time
+from pathlib import Path
+
+ROOT = Path(__file__).resolve().parent
+for _p in (str(ROOT), str(ROOT / "2048-ppo-agent_b200")):
+    if _p not in sys.path:
+        sys.path.insert(0, _p)
+
+ENVS_PER_GPU = 1 << 21
+SEED = 2048
+MAX_STEPS = 2048  # loop steps of keys generated per batch (random episodes: < 600)
+ALG_INSTR = {"random": 990, "drul": 620}  # 74 int instr per Threefry block x 10 (5) + ~250 game logic
+CPU_SAMPLE_ENVS = 1 << 17
+REF_SAMPLE_ENVS = 1 << 16
+
+
+def parse_args():
+    ap = argparse.ArgumentParser()
+    ap.add_argument("--gpus", type=int, default=1)
+    ap.add_argument("--steps", type=int, default=10)
+    ap.add_argument("--warmup", type=int, default=3)
+    ap.add_argument("--impl", default="g2048", choices=["g2048", "reference"])
+    ap.add_argument("--policy", default="random", choices=["random", "drul"])
+    ap.add_argument("--envs-per-gpu", type=int, default=ENVS_PER_GPU)
+    ap.add_argument("--no-extras", action="store_true", help="skip the secondary kernel measurements")
+    return ap.parse_args()
+
+
+# ------------------------------------------------------------------------------------------ helpers
+class ClockSampler:
+    """nvidia-smi clocks / throttle reasons during the timed region (B200_PROFILING.md recipe)."""
+
+    QUERY = ("clocks.sm,clocks.max.sm,power.draw,clocks_event_reasons.hw_slowdown,"
+             "clocks_event_reasons.hw_thermal_slowdown,clocks_event_reasons.sw_thermal_slowdown,"
+             "clocks_event_reasons.sw_power_cap")
+
+    def __init__(self, gpu_index: int):
+        self.rows = []
+        self.proc = None
+        self.gpu_index = gpu_index
+
+    def start(self):
+        try:
+            self.proc = subprocess.Popen(
+                ["nvidia-smi", "-i", str(self.gpu_index), f"--query-gpu={self.QUERY}", "--format=csv,noheader,nounits", "-lms", "100"],
+                stdout=subprocess.PIPE, stderr=subprocess.DEVNULL, text=True)
+            threading.Thread(target=self._read, daemon=True).start()
+        except OSError:
+            self.proc = None
+
+    def _read(self):
+        for line in self.proc.stdout:
+            self.rows.append([c.strip() for c in line.split(",")])
+
+    def stop(self) -> dict:
+        if self.proc is None:
+            return {"sm_mhz": None, "sm_max_mhz": None, "reasons": ["nvidia-smi unavailable"]}
+        time.sleep(0.15)
+        self.proc.terminate()
+        sm, mx, reasons, power = [], [], set(), []
+        names = ["hw_slowdown", "hw_thermal_slowdown", "sw_thermal_slowdown", "sw_power_cap"]
+        for r in self.rows:
+            try:
+                sm.append(float(r[0]))
+                mx.append(float(r[1]))
+                power.append(float(r[2]))
+                for name, v in zip(names, r[3:7]):
+                    if v.lower().startswith("active"):
+                        reasons.add(name)
+            except (ValueError, IndexError):
+                continue
+        # samples under load only: the top half of the observed power draw
+        if sm:
+            cut = statistics.median(power)
+            loaded = [s for s, p in zip(sm, power) if p >= cut] or sm
+            return {"sm_mhz": statistics.median(loaded), "sm_max_mhz": max(mx), "reasons": sorted(reasons),
+                    "samples": len(sm), "power_w_max": max(power)}
+        return {"sm_mhz": None, "sm_max_mhz": None, "reasons": ["no samples"]}
+
+
+def measured_hbm_peak():
+    p = ROOT / "MEASURED_PEAKS.json"
+    if p.exists():
+        try:
+            return float(json.loads(p.read_text())["hbm_gbs"]), "measured (MEASURED_PEAKS.json)"
+        except (KeyError, ValueError):
+            pass
+    return 6650.0, "fallback (B200_PROFILING.md)"
+
+
+def oracle_play_rate(seed: int, batch_global: int, n_sample: int, policy: int, mode: int, min_seconds: float):
+    """Times the oracle's C port (OpenMP, all host threads) on envs [0, n_sample) of the batch."""
+    from oracle import c_oracle as CO
+
+    threads = CO.num_threads()
+    total_steps, t0, reps = 0, time.perf_counter(), 0
+    out = None
+    while True:
+        out = CO.play(seed, batch_global, policy, mode, env_lo=0, env_hi=n_sample, max_steps=MAX_STEPS)
+        total_steps += int(out["lengths"].sum())
+        reps += 1
+        if time.perf_counter() - t0 >= min_seconds:
+            break
+    dt = time.perf_counter() - t0
+    return total_steps / dt, threads, reps, out
+
+
+# ------------------------------------------------------------------------------------------ reference arm
+def run_reference(args, rank: int):
+    if rank != 0:
+        return
+    policy = 0 if args.policy == "random" else 1
+    batch_global = args.envs_per_gpu * args.gpus
+    n_sample = min(REF_SAMPLE_ENVS, batch_global)
+    from oracle import c_oracle as CO
+
+    times, steps_done = [], []
+    for i in range(args.warmup + args.steps):
+        t0 = time.perf_counter()
+        out = CO.play(SEED + i, batch_global, policy, 1, env_lo=0, env_hi=n_sample, max_steps=MAX_STEPS)
+        dt = time.perf_counter() - t0
+        if i >= args.warmup:
+            times.append(dt)
+            steps_done.append(int(out["lengths"].sum()))
+    value = sum(steps_done) / sum(times)
+    sample = (f"envs [0,{n_sample}) of the {batch_global}-env batch per step, played to termination by the oracle's C "
+              f"restatement of the Pgx/JAX path (jax, pgx, torch2jax absent from the image: the reference itself cannot run)")
+    line = {
+        "impl": "reference", "metric": "env_steps_per_sec", "value": value, "unit": "env-steps/s", "n_gpus": args.gpus,
+        "steps": args.steps, "warmup": args.warmup, "ms_per_step": 1e3 * sum(times) / len(times),
+        "higher_is_better": True, "scaling": "weak", "vs_baseline": None, "dtype": "u8/u32 integer", "data": "synthetic",
+        "config": workload_config(args, batch_global),
+        "cpu_baseline": {"value": value, "unit": "env-steps/s", "cores": CO.num_threads(), "kind": "port", "sample": sample},
+        "e2e": {"value": value, "unit": "env-steps/s", "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0},
+        "gpu_launches": 0,
+    }
+    print(json.dumps(line))
+
+
+def workload_config(args, batch_global):
+    return {
+        "workload": f"C5 throughput sweep: {args.policy}-policy 2048 envs played to termination + episode-stats reduction "
+                    f"(BASELINE.json configs[4]; {args.envs_per_gpu} envs per GPU, 2^24 at 8 GPUs)",
+        "policy": args.policy, "envs_per_gpu": args.envs_per_gpu, "global_batch": batch_global,
+        "rng": "threefry2x32 partitionable (jax 0.5.3 default)", "seed": SEED,
+        "l2": "L2 flushed (512 MiB write) between timed steps; the kernel's inputs are 32 KiB of keys, env state lives in registers",
+    }
+
+
+# ------------------------------------------------------------------------------------------ our arm
+def main():
+    args = parse_args()
+    rank = int(os.environ.get("RANK", "0"))
+    world = int(os.environ.get("WORLD_SIZE", "1"))
+    local_rank = int(os.environ.get("LOCAL_RANK", "0"))
+    if args.impl == "reference":
+        run_reference(args, rank)
+        return
+    if world != args.gpus and not (world == 1 and args.gpus == 1):
+        raise SystemExit(f"--gpus {args.gpus} needs WORLD_SIZE {args.gpus} (launch with torch.distributed.run); got {world}")
+
+    import numpy as np
+    import torch
+    import torch.distributed as dist
+
+    from g2048 import _native as N
+    from g2048 import engine as E
+
+    torch.cuda.set_device(local_rank)
+    dev = torch.device("cuda", local_rank)
+    if world > 1:
+        dist.init_process_group("nccl", device_id=dev)
+
+    policy_id = E.POLICY_RANDOM if args.policy == "random" else E.POLICY_DRUL
+    mode = E.RNG_PARTITIONABLE
+    n = args.envs_per_gpu
+    batch_global = n * world
+    lo = n * rank
+    n_subs = 1 + 2 * MAX_STEPS
+
+    flush_buf = torch.empty(512 << 20, dtype=torch.uint8, device=dev)
+    stats_all = []
+    launches = {"ours": 0}
+
+    # the inputs of a step (one 8-byte chain key per batch) are resident in HBM before the timed region
+    step_keys = [E.words_tensor(list(E.key_words(SEED + i)), dev) for i in range(args.warmup + args.steps)]
+
+    def one_step(i: int, per_env: bool = False):
+        """chain generation + persistent play kernel + stats reduction, all on the device."""
+        subs = E.chain_advance(step_keys[i], mode, n_subs)
+        out = E.play(policy_id, subs, batch_global, lo, n, mode, per_env=per_env)
+        launches["ours"] += 2
+        if world > 1:
+            longest = out["stats"][5:6].clone()
+            dist.all_reduce(out["stats"], op=dist.ReduceOp.SUM)
+            dist.all_reduce(longest, op=dist.ReduceOp.MAX)
+            out["stats"][5] = longest[0]
+        return out
+
+    def barrier():
+        torch.cuda.synchronize()
+        if world > 1:
+            dist.barrier()
+        torch.cuda.synchronize()
+
+    for i in range(args.warmup):
+        one_step(i)
+    barrier()
+
+    sampler = ClockSampler(local_rank)
+    if rank == 0:
+        sampler.start()
+    launches["ours"] = 0
+    events = []
+    barrier()
+    for i in range(args.steps):
+        flush_buf.fill_(i & 0xFF)  # L2 flush, outside the timed events
+        a, b = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+        a.record()
+        out = one_step(args.warmup + i)
+        b.record()
+        events.append((a, b))
+        stats_all.append(out["stats"])
+    barrier()
+    clocks = sampler.stop() if rank == 0 else None
+    gpu_launches = launches["ours"]
+    elapsed = sum(a.elapsed_time(b) for a, b in events) * 1e-3
+    t = torch.tensor([elapsed], dtype=torch.float64, device=dev)
+    if world > 1:
+        dist.all_reduce(t, op=dist.ReduceOp.MAX)
+    elapsed = float(t.item())
+    summaries = [E.play_stats_dict(s) for s in stats_all]
+    total_env_steps = sum(s["env_steps"] for s in summaries)  # after the all-reduce: whole-job totals
+    assert all(s["episodes"] == batch_global and s["cut_short"] == 0 and s["overflowed"] == 0 for s in summaries), summaries[0]
+    value = total_env_steps / elapsed
+
+    # ---- dominant kernel alone (play), CUDA events on the launching stream ------------------------
+    key = E.words_tensor(list(E.key_words(SEED)), dev)
+    subs = E.chain_advance(key, mode, n_subs)
+    E.play(policy_id, subs, batch_global, lo, n, mode, per_env=False)
+    torch.cuda.synchronize()
+    k_times, k_steps = [], 0
+    for _ in range(5):
+        flush_buf.fill_(1)
+        a, b = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+        work = torch.zeros(2, dtype=torch.int64, device=dev)
+        stats = torch.zeros(N.PLAY_STATS_WORDS, dtype=torch.int64, device=dev)
+        a.record()
+        N.call("g2048_play", policy_id, N.ptr(subs), n_subs, batch_global, lo, n, mode, N.ptr(work), None, None, None,
+               N.ptr(stats), N.stream_ptr())
+        b.record()
+        torch.cuda.synchronize()
+        k_times.append(a.elapsed_time(b) * 1e-3)
+        k_steps = int(stats[1].item())
+    k_time = statistics.mean(k_times)
+
+    # integer-issue peak: Threefry instruction mix, 4 independent chains per thread, full occupancy
+    sms = N.lib.g2048_device_sm_count()
+    blocks, threads, iters = sms * 8, 256, 20000
+    sink = torch.empty(blocks * threads, dtype=torch.int32, device=dev)
+    E.int_peak_probe(blocks, threads, iters, sink)
+    torch.cuda.synchronize()
+    p_times = []
+    for _ in range(3):
+        a, b = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+        a.record()
+        E.int_peak_probe(blocks, threads, iters, sink)
+        b.record()
+        torch.cuda.synchronize()
+        p_times.append(a.elapsed_time(b) * 1e-3)
+    int_peak = blocks * threads * iters * 48 / min(p_times) / 1e12  # 16 rounds x 3 instr per iteration
+    achieved = ALG_INSTR[args.policy] * k_steps / k_time / 1e12
+    roofline = {
+        "kernel": "play_kernel (g2048_play)", "bound": "int_issue", "achieved": achieved, "peak": int_peak,
+        "unit": "Tinstr/s", "frac": achieved / int_peak, "traffic": None,
+        "note": (f"algorithmic {ALG_INSTR[args.policy]} int instr per env-step (SURVEY 8d) x {k_steps} env-steps per launch / "
+                 f"{k_time * 1e3:.2f} ms; peak = live probe of the ADD/SHF/LOP3 Threefry mix on this GPU (of measured); "
+                 "the kernel keeps env state in registers, so HBM traffic is ~16 B per episode and not the bound"),
+        "kernel_ms": k_time * 1e3, "kernel_env_steps": k_steps,
+    }
+
+    # ---- end to end through the host-buffer C entry point ------------------------------------------
+    e2e_times, e2e_steps = [], 0
+    h_boards = np.empty(n, np.uint64)
+    h_len = np.empty(n, np.uint32)
+    h_score = np.empty(n, np.uint32)
+    h_stats = np.zeros(N.PLAY_STATS_WORDS, np.uint64)
+    for i in range(2 + min(args.steps, 5)):
+        barrier()
+        t0 = time.perf_counter()
+        N.call("g2048_play_host", policy_id, SEED + i, None, batch_global, lo, n, mode, h_boards.ctypes.data,
+               h_len.ctypes.data, h_score.ctypes.data, h_stats.ctypes.data)
+        dt = time.perf_counter() - t0
+        if i >= 2:
+            e2e_times.append(dt)
+            e2e_steps += int(h_stats[1])
+    te = torch.tensor([sum(e2e_times)], dtype=torch.float64, device=dev)
+    se = torch.tensor([e2e_steps], dtype=torch.int64, device=dev)
+    if world > 1:
+        dist.all_reduce(te, op=dist.ReduceOp.MAX)
+        dist.all_reduce(se, op=dist.ReduceOp.SUM)
+    e2e = {
+        "value": float(se.item()) / float(te.item()), "unit": "env-steps/s",
+        "h2d_bytes_per_step": 8, "d2h_bytes_per_step": int(16 * n + 8 * N.PLAY_STATS_WORDS),
+        "api": "g2048_play_host (C ABI, host buffers): device alloc + key H2D + chain + play + D2H of final boards, "
+               "lengths, scores and the statistics block + free, per call",
+    }
+
+    extras = {}
+    if not args.no_extras and rank == 0:
+        extras = secondary_measurements(E, N, torch, dev, flush_buf)
+
+    cpu_baseline = None
+    if rank == 0 and world == 1:
+        n_sample = min(CPU_SAMPLE_ENVS, batch_global)
+        rate, threads_used, reps, ref = oracle_play_rate(SEED, batch_global, n_sample, policy_id, 1, 10.0)
+        cpu_baseline = {
+            "value": rate, "unit": "env-steps/s", "cores": threads_used, "kind": "port",
+            "sample": f"envs [0,{n_sample}) of the same {batch_global}-env batch (seed {SEED}), {reps} repetitions, "
+                      "oracle C restatement with OpenMP on all host threads (Pgx/JAX not installable here)",
+        }
+        # the sample doubles as a parity check of the benchmarked workload itself
+        chk = E.play(policy_id, subs, batch_global, 0, n_sample, mode, per_env=True)
+        assert np.array_equal(chk["lengths"].cpu().numpy(), ref["lengths"]), "bench workload differs from the oracle"
+        assert np.array_equal(E.boards_numpy(chk["final_boards"]), ref["final_boards"]), "bench workload differs from the oracle"
+        cpu_baseline["parity_checked_envs"] = n_sample
+
+    if rank == 0:
+        line = {
+            "metric": "env_steps_per_sec", "value": value, "unit": "env-steps/s", "n_gpus": world, "steps": args.steps,
+            "warmup": args.warmup, "ms_per_step": 1e3 * elapsed / args.steps, "higher_is_better": True,
+            "scaling": "weak", "vs_baseline": None, "dtype": "u64 bitboard / u32 Threefry (integer)", "data": "synthetic",
+            "config": workload_config(args, batch_global), "clocks": clocks, "e2e": e2e, "gpu_launches": gpu_launches,
+            "roofline": roofline, "cpu_baseline": cpu_baseline,
+            "env_steps_per_step": total_env_steps / args.steps, "mean_episode_length": total_env_steps / args.steps / batch_global,
+        }
+        line.update(extras)
+        print(json.dumps(line))
+    if world > 1:
+        dist.barrier()
+        dist.destroy_process_group()
+
+
+def secondary_measurements(E, N, torch, dev, flush_buf) -> dict:
+    """HBM-bound kernels of the path (rollout write / observation / GAE) and the PPO-rollout step."""
+    hbm_peak, peak_src = measured_hbm_peak()
+
+    def timed(fn, reps=5):
+        fn()
+        torch.cuda.synchronize()
+        ts = []
+        for _ in range(reps):
+            flush_buf.fill_(3)
+            a, b = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+            a.record()
+            fn()
+            b.record()
+            torch.cuda.synchronize()
+            ts.append(a.elapsed_time(b) * 1e-3)
+        return statistics.mean(ts)
+
+    rows = []
+
+    def add(name, bytes_per_launch, seconds, note):
+        gbs = bytes_per_launch / seconds / 1e9
+        rows.append({"kernel": name, "bound": "hbm", "achieved": gbs, "peak": hbm_peak, "unit": "GB/s",
+                     "frac": gbs / hbm_peak, "traffic": None, "us": seconds * 1e6, "note": note})
+
+    # observation expansion: C3-sized rollout record (65536 envs x 16 steps of boards -> float32 one-hot)
+    n_b = 1 << 20
+    boards = torch.randint(0, 1 << 62, (n_b,), dtype=torch.int64, device=dev)
+    out_f32 = torch.empty((n_b, 16, 31), dtype=torch.float32, device=dev)
+    t = timed(lambda: N.call("g2048_expand_obs", N.ptr(boards), n_b, N.OBS_F32, N.ptr(out_f32), 0, 0, N.stream_ptr()))
+    add("expand_obs_kernel<float>", n_b * (8 + 1984), t, "2^20 boards -> (n,16,31) f32; 8 B read + 1984 B written per board")
+    del out_f32
+
+    # GAE on a flat buffer: C4-sized (2^26 steps), episodes ~300 steps
+    n_g = 1 << 26
+    r = torch.rand(n_g, device=dev)
+    v = torch.rand(n_g, device=dev)
+    d = (torch.rand(n_g, device=dev) < 1 / 300).to(torch.uint8)
+    adv = torch.empty(n_g, dtype=torch.float32, device=dev)
+    ret = torch.empty(n_g, dtype=torch.float32, device=dev)
+    scratch = torch.zeros(int(N.lib.g2048_gae_flat_scratch_bytes(n_g)), dtype=torch.uint8, device=dev)
+    mom = torch.zeros(6, dtype=torch.float64, device=dev)
+
+    def gae():
+        scratch.zero_()
+        N.call("g2048_gae_flat", N.ptr(r), N.ptr(v), N.ptr(d), n_g, 0.99, 0.95, N.ptr(adv), N.ptr(ret), N.ptr(scratch),
+               N.ptr(mom), N.stream_ptr())
+
+    t = timed(gae)
+    add("gae_flat_kernel", n_g * 17, t, "2^26 steps, done rate 1/300; 9 B read + 8 B written per step (SURVEY 8d)")
+    t = timed(lambda: N.call("g2048_normalize", N.ptr(adv), n_g, N.ptr(mom), 1, N.stream_ptr()))
+    add("normalize_kernel", n_g * 8, t, "2^26 steps in place; 4 B read + 4 B written per step")
+    del r, v, d, adv, ret
+
+    # GAE on time-major records: C3 (128 steps x 65536 envs)
+    t_steps, b = 128, 1 << 16
+    rr = torch.rand((t_steps, b), device=dev)
+    vv = torch.rand((t_steps, b), device=dev)
+    mm = ((torch.rand((t_steps, b), device=dev) < 1 / 300).to(torch.uint8) << 6)
+    adv2 = torch.empty((t_steps, b), dtype=torch.float32, device=dev)
+    ret2 = torch.empty((t_steps, b), dtype=torch.float32, device=dev)
+    t = timed(lambda: N.call("g2048_gae_time_major", N.ptr(rr), N.ptr(vv), N.ptr(mm), t_steps, b, None, 0.99, 0.95,
+                             N.ptr(adv2), N.ptr(ret2), N.ptr(mom), N.stream_ptr()))
+    add("gae_time_major_kernel", t_steps * b * 17, t, "C3: 128 x 65536 steps; launch-bound size (143 MB), also reported in us")
+
+    # PPO rollout step (C3): synthetic logits stand in for the policy network, which is outside the product path
+    mode = E.RNG_PARTITIONABLE
+    key = E.words_tensor([0, 3], dev)
+    subs = E.chain_advance(key, mode, 1 + 2 * t_steps)
+    pb, ps = E.env_init(subs[0], b, 0, b, mode)
+    logits = torch.randn((b, 4), device=dev)
+    values = torch.randn(b, device=dev)
+    rec_b = torch.empty((t_steps, b), dtype=torch.int64, device=dev)
+    rec_m = torch.empty((t_steps, b), dtype=torch.uint8, device=dev)
+    rec_r, rec_l, rec_v = (torch.empty((t_steps, b), dtype=torch.float32, device=dev) for _ in range(3))
+    obs = torch.empty((b, 16, 31), dtype=torch.float32, device=dev)
+
+    def ppo_rollout():
+        for k in range(t_steps):
+            N.call("g2048_expand_obs", N.ptr(pb), b, N.OBS_F32, N.ptr(obs), 0, 0, N.stream_ptr())
+            E.policy_step(pb, ps, logits, values, True, True, True, subs[1 + 2 * k], subs[2 + 2 * k], b, 0, mode,
+                          rec_b[k], rec_m[k], rec_r[k], rec_l[k], rec_v[k])
+        N.call("g2048_gae_time_major", N.ptr(rec_r), N.ptr(rec_v), N.ptr(rec_m), t_steps, b, None, 0.99, 0.95,
+               N.ptr(adv2), N.ptr(ret2), N.ptr(mom), N.stream_ptr())
+
+    t = timed(ppo_rollout, reps=3)
+    ppo = {
+        "config": "C3: 65536 envs x 128 steps, auto-reset, masked categorical sampling from synthetic logits "
+                  "(policy network = PyTorch/cuBLAS, outside the product path and not timed)",
+        "env_steps_per_sec": t_steps * b / t, "ms_per_rollout": t * 1e3,
+        "per_step_us": t * 1e6 / t_steps, "launches_per_rollout": 2 * t_steps + 1,
+        "kernels": "per step: expand_obs<f32> (network input) + policy_step (mask, sample, log-prob, env step, auto-reset, record write); then gae_time_major",
+    }
+    return {"roofline_hbm": rows, "hbm_peak_source": peak_src, "ppo_rollout": ppo}
+
+
+if __name__ == "__main__":
+    main()

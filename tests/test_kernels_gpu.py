@@ -417,7 +417,7 @@ def test_policy_step_equals_sample_then_step(E, mode):
 
 
 def test_policy_step_auto_reset_follows_pgx_wrapper(E):
-    mode, n = 1, 4096
+    mode, n = 1, 65536
     rng = np.random.default_rng(37)
     boards = rng.integers(1, 4, (n, 16))  # nearly dead boards: many terminate on this step
     masks, done, status = state_of(boards)
