@@ -46,7 +46,9 @@ __device__ __forceinline__ u64 reverse_nibbles(u64 x) {
 // 16: columns, i.e. Up).  `has_lower` marks the cells that have a neighbour at p - s in their line.
 // Returns the moved board; `reward` gets sum of 2^(e+1) over merges (Pgx: the merged tile's value);
 // `overflow` is set if a 2^15 pair merged (the result does not fit a nibble).
-__device__ __forceinline__ u64 slide_merge_low(u64 x, int s, u64 has_lower, uint32_t& reward, bool& overflow) {
+template <bool WANT_REWARD>
+__device__ __forceinline__ u64 slide_merge_low(u64 x, int s, u64 has_lower, u64 line_ge2, u64 line_eq3,
+                                               uint32_t& reward, bool& overflow) {
 #define G2048_COMPRESS_ONCE()                                          \
     {                                                                  \
         const u64 empty = ~spread_nibble(nonzero_lsb(x));              \
@@ -65,9 +67,9 @@ __device__ __forceinline__ u64 slide_merge_low(u64 x, int s, u64 has_lower, uint
     const u64 m0 = eq & line0;
     const u64 m1 = eq & (line0 << s) & ~(m0 << s);
     const u64 m2 = eq & (line0 << (2 * s)) & ~(m1 << s);
-    u64 m = m0 | m1 | m2;
+    const u64 m = m0 | m1 | m2;
     reward = 0;
-    if (m) {
+    if (WANT_REWARD && m) {
         u64 mm = m;
         do {
             const int p = __ffsll((long long)mm) - 1;
@@ -76,25 +78,41 @@ __device__ __forceinline__ u64 slide_merge_low(u64 x, int s, u64 has_lower, uint
             reward += 2u << v;
             mm &= mm - 1;
         } while (mm);
-        x += m;                              // merged cell: e -> e + 1
-        x &= ~(spread_nibble(m) << s);       // its partner disappears
-        G2048_COMPRESS_ONCE()
-        G2048_COMPRESS_ONCE()
     }
+    x += m;                                  // merged cell: e -> e + 1
+    const u64 hole = m << s;                 // lsb flags where the partner disappears
+    x &= ~spread_nibble(hole);
+    // close the holes: a cell moves down by exactly one step iff a hole lies below it in its line
+    // (holes sit at line positions 1..3; two holes are never both below a live cell)
+    const u64 below = ((hole << s) & line_ge2) | ((hole << (2 * s)) & line_eq3);
+    const u64 mv = x & spread_nibble(below);
+    x = (x ^ mv) | (mv >> s);
 #undef G2048_COMPRESS_ONCE
     return x;
 }
 
 // Pgx _step's board part: rot90(board, action) -> slide/merge left -> rotate back.
+// WANT_REWARD = false skips the per-merge reward sum (the persistent play kernel derives the score
+// from the final board instead, see board_potential) and leaves `reward` / `overflow` untouched.
+template <bool WANT_REWARD = true>
 __device__ __forceinline__ u64 move_board(u64 x, int action, uint32_t& reward, bool& overflow) {
     const bool rev = action >= 2;            // Right = Left on the reversed board, Down = Up on it
     if (rev) x = reverse_nibbles(x);
     const bool vertical = action & 1;
     const int s = vertical ? 16 : 4;
     const u64 has_lower = vertical ? 0xFFFFFFFFFFFF0000ull : 0xFFF0FFF0FFF0FFF0ull;
-    x = slide_merge_low(x, s, has_lower, reward, overflow);
+    const u64 line_ge2 = vertical ? 0x1111111100000000ull : 0x1100110011001100ull;  // lsb flags, line position >= 2
+    const u64 line_eq3 = vertical ? 0x1111000000000000ull : 0x1000100010001000ull;  // line position == 3
+    x = slide_merge_low<WANT_REWARD>(x, s, has_lower, line_ge2, line_eq3, reward, overflow);
     if (rev) x = reverse_nibbles(x);
     return x;
+}
+
+// true iff some cell holds exponent 15 (a 2^15 tile: the next merge would not fit a nibble)
+__device__ __forceinline__ bool has_max_nibble(u64 x) {
+    u64 t = x & (x >> 1);
+    t &= t >> 2;
+    return (t & NIB_LSB) != 0ull;
 }
 
 // Exact legal-action mask, bit a = (move(board, a) != board): a line can move toward a side iff

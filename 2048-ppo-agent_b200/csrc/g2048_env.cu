@@ -433,9 +433,11 @@ static int launch_play(const uint32_t* d_subs, int64_t n_subs, int64_t batch_glo
     return check_cuda(cudaGetLastError(), "play");
 }
 
-extern "C" int g2048_play(int policy, const uint32_t* d_subs, int64_t n_subs, int64_t batch_global, int64_t env_lo,
-                          int64_t n, int rng_mode, uint64_t* d_work, uint64_t* d_final_boards, uint32_t* d_lengths,
-                          uint32_t* d_scores, uint64_t* d_stats, void* stream) {
+// First-generation play kernel (park-and-refill, per-step reward loop).  Kept as a measured baseline
+// for the current kernel in g2048_play.cu; same arguments and results as g2048_play.
+extern "C" int g2048_play_v1(int policy, const uint32_t* d_subs, int64_t n_subs, int64_t batch_global, int64_t env_lo,
+                             int64_t n, int rng_mode, uint64_t* d_work, uint64_t* d_final_boards, uint32_t* d_lengths,
+                             uint32_t* d_scores, uint64_t* d_stats, void* stream) {
     G2048_REQUIRE(policy == G2048_POLICY_RANDOM || policy == G2048_POLICY_DRUL, "play: policy");
     G2048_REQUIRE(valid_mode(rng_mode) && valid_batch(batch_global, env_lo, n), "play: batch");
     G2048_REQUIRE(n_subs >= 3 && d_subs && d_work && d_stats, "play: pointers");

@@ -11,6 +11,10 @@
 
 namespace g2048 {
 
+#ifndef G2048_GAE_EXPERIMENT
+#define G2048_GAE_EXPERIMENT 0  // non-zero only in tools/probes/probe_gae.cu
+#endif
+
 constexpr int GAE_TILE = 1024;
 constexpr int GAE_THREADS = 128;
 constexpr int GAE_ITEMS = GAE_TILE / GAE_THREADS;  // 8 consecutive steps per thread for segment discovery
@@ -126,6 +130,10 @@ gae_flat_kernel(const float* __restrict__ rewards, const float* __restrict__ val
     // A done step starts with gae = 0, which is what the reference's reset computes (delta + gl * 0).
     auto walk = [&](int last, int first_excl, float g) {
         int t = last;
+#if G2048_GAE_EXPERIMENT & 1  // timing experiment (tools/probes/probe_gae.cu): no serial chain
+        s_adv[last] = g;
+        return;
+#endif
         for (; t - 8 >= first_excl; t -= 8) {
             float d[8];
 #pragma unroll
@@ -159,7 +167,9 @@ gae_flat_kernel(const float* __restrict__ rewards, const float* __restrict__ val
         if (first_excl < len - 1) {
             float carry = 0.0f;
             if (lo + len < n) {
+#if !(G2048_GAE_EXPERIMENT & 4)
                 while (flags[tile + 1] == 0u) __nanosleep(32);
+#endif
                 __threadfence();
                 carry = heads[tile + 1];
             }

@@ -1,0 +1,246 @@
+// Persistent play-to-termination kernel (second generation) -- the whole of
+// src/runs/batch_runner.py:105-136 for act_randomly / act_drul plus the max-tile reduction of
+// src/runs/run_actions_max_tile.py:61-69, for envs [env_lo, env_lo + n) of a global batch.
+//
+// What changed against g2048_play_v1 (ncu: ALU pipe 94.7 % busy, but only 23.2 of 32 lanes active):
+//   * No lane ever waits.  A lane that finishes an episode takes the next env from the queue at the
+//     top of the very next iteration, and the env's init (Pgx _init: two spawns on the empty board)
+//     runs as two ordinary loop iterations ("phase 0/1") through the SAME instruction stream as a
+//     game step, so initialising lanes do not diverge from playing lanes.  This works because the
+//     Threefry blocks a random-policy step hashes anyway -- TF(k; (0,i)), i < 4, under the per-env
+//     act key -- are exactly the blocks jax.random.split(k) is made of: an initialising lane feeds
+//     the env's init key in place of the act key and reads its spawn key r_phase out of the same
+//     blocks (both counter layouts).  The DRUL policy has no act-key work to share, so its
+//     initialising lanes hash one extra block under a short divergent branch.
+//   * No per-step reward.  The episode score is board_potential(final) - 4 * (#spawned 4-tiles),
+//     which equals the sum of Pgx's merge rewards; the divergent per-merge loop is gone.
+//   * Overflow (a 2^16 tile would be needed) is detected by looking for a 2^15 tile every 256 steps and
+//     at the end of the episode: a second 2^15 tile cannot be built in fewer steps than that.
+#include "g2048_board.cuh"
+#include "g2048_common.cuh"
+#include "g2048_env.cuh"
+
+namespace g2048 {
+
+constexpr int PLAY2_THREADS = 256;
+
+// The blocks of one key that both bits4() and split2() are made of.
+template <int MODE>
+struct KeyBlocks {
+    uint32_t bits[4];  // random_bits(key, (4,))
+    Key child[2];      // split(key, 2)
+};
+
+template <int MODE>
+__device__ __forceinline__ KeyBlocks<MODE> key_blocks(Key k) {
+    KeyBlocks<MODE> o;
+    if (MODE == G2048_RNG_PARTITIONABLE) {
+        Key y[4];
+#pragma unroll
+        for (uint32_t i = 0; i < 4; ++i) {
+            y[i] = threefry2x32(k, 0u, i);
+            o.bits[i] = y[i].a ^ y[i].b;
+        }
+        o.child[0] = y[0];
+        o.child[1] = y[1];
+    } else {
+        const Key y0 = threefry2x32(k, 0u, 2u);
+        const Key y1 = threefry2x32(k, 1u, 3u);
+        o.bits[0] = y0.a;
+        o.bits[1] = y1.a;
+        o.bits[2] = y0.b;
+        o.bits[3] = y1.b;
+        o.child[0] = Key{y0.a, y1.a};
+        o.child[1] = Key{y0.b, y1.b};
+    }
+    return o;
+}
+
+__device__ __forceinline__ int argmax_bits_legal(const uint32_t bits[4], uint32_t legal) {
+    const uint32_t allowed = (legal & 15u) ? (legal & 15u) : 15u;
+    int best = 0, best_v = -1;
+#pragma unroll
+    for (int i = 0; i < 4; ++i) {
+        const int v = ((allowed >> i) & 1u) ? (int)(bits[i] >> 9) : -1;
+        if (v > best_v) {
+            best_v = v;
+            best = i;
+        }
+    }
+    return best;
+}
+
+enum : uint32_t { PHASE_INIT0 = 0, PHASE_INIT1 = 1, PHASE_PLAY = 2, PHASE_NONE = 3 };
+
+template <int MODE, int POLICY>
+__global__ void __launch_bounds__(PLAY2_THREADS)
+play2_kernel(const uint2* __restrict__ subs, int64_t n_subs, uint32_t batch_global, uint32_t env_lo, uint32_t n,
+             unsigned long long* __restrict__ work, u64* __restrict__ final_boards, uint32_t* __restrict__ lengths,
+             uint32_t* __restrict__ scores, unsigned long long* __restrict__ stats) {
+    __shared__ unsigned long long s_stats[G2048_PLAY_STATS_WORDS];
+    for (int i = threadIdx.x; i < G2048_PLAY_STATS_WORDS; i += blockDim.x) s_stats[i] = 0ull;
+    __syncthreads();
+
+    const unsigned lane = threadIdx.x & 31u;
+    const uint2 init_sub = subs[0];
+    const uint32_t max_steps = (uint32_t)((n_subs - 1) / 2);
+
+    u64 board = 0ull;
+    uint32_t lm = 0, e = 0, t = 0, fours = 0, phase = PHASE_NONE;
+    bool seen15 = false;
+    bool exhausted = false;  // warp-uniform
+
+    uint32_t st_episodes = 0, st_cut = 0, st_ovf = 0, st_longest = 0;
+    unsigned long long st_steps = 0, st_score = 0, st_tile = 0, st_tile2 = 0;
+
+    while (true) {
+        // ---- hand the next envs of the queue to the lanes that have none --------------------------
+        const unsigned want = __ballot_sync(0xFFFFFFFFu, phase == PHASE_NONE);
+        if (want) {
+            if (!exhausted) {
+                const int cnt = __popc(want);
+                unsigned long long base = 0;
+                if (lane == 0) base = atomicAdd(work, (unsigned long long)cnt);
+                base = __shfl_sync(0xFFFFFFFFu, base, 0);
+                if (base + (unsigned long long)cnt >= (unsigned long long)n) exhausted = true;
+                if (phase == PHASE_NONE) {
+                    const unsigned long long mine = base + (unsigned long long)__popc(want & ((1u << lane) - 1u));
+                    if (mine < (unsigned long long)n) {
+                        e = (uint32_t)mine;
+                        board = 0ull;
+                        lm = 0;
+                        t = 0;
+                        fours = 0;
+                        seen15 = false;
+                        phase = PHASE_INIT0;
+                    }
+                }
+            }
+            if (__ballot_sync(0xFFFFFFFFu, phase != PHASE_NONE) == 0u) break;
+        }
+        if (phase == PHASE_NONE) continue;  // only at the tail of the launch, when the queue is empty
+
+        // ---- one iteration: a game step, or one of the two init spawns ------------------------------
+        const bool playing = phase == PHASE_PLAY;
+        const uint2 ss = __ldg(&subs[2 + 2 * (int64_t)t]);
+        int action;
+        Key kstep;
+        if (POLICY == G2048_POLICY_RANDOM) {
+            const uint2 sa = __ldg(&subs[1 + 2 * (int64_t)t]);
+            const Key head = playing ? Key{sa.x, sa.y} : Key{init_sub.x, init_sub.y};
+            const KeyBlocks<MODE> kb = key_blocks<MODE>(split_at<MODE>(head, batch_global, env_lo + e));
+            action = argmax_bits_legal(kb.bits, lm);
+            const Key kplay = split_at<MODE>(Key{ss.x, ss.y}, batch_global, env_lo + e);
+            const Key kinit = (phase == PHASE_INIT0) ? kb.child[0] : kb.child[1];
+            kstep = playing ? kplay : kinit;
+        } else {
+            action = act_drul(lm);
+            const Key head = playing ? Key{ss.x, ss.y} : Key{init_sub.x, init_sub.y};
+            kstep = split_at<MODE>(head, batch_global, env_lo + e);
+            if (!playing) {  // r_phase = split(init key)[phase]
+                Key c0, c1;
+                split2<MODE>(kstep, c0, c1);
+                kstep = (phase == PHASE_INIT0) ? c0 : c1;
+            }
+        }
+        Key k1, k2;
+        split2<MODE>(kstep, k1, k2);
+        const uint32_t bits_pos = bits_scalar<MODE>(k1);
+        const uint32_t bits_val = bits_scalar<MODE>(k2);
+
+        uint32_t unused_reward = 0;
+        bool unused_ovf = false;
+        const u64 moved = move_board<false>(board, action, unused_reward, unused_ovf);
+        board = spawn_tile(playing ? moved : board, bits_pos, bits_val);
+        fours += ((0x800000u - (bits_val >> 9)) > 7549747u) ? 1u : 0u;
+        lm = legal_mask(board);
+
+        if (!playing) {
+            phase += 1;  // INIT0 -> INIT1 -> PLAY
+            continue;
+        }
+        ++t;
+        const bool done = lm == 0u;
+        const bool cut = !done && t >= max_steps;
+        if ((t & 255u) == 0u || done || cut) seen15 |= has_max_nibble(board);
+        if (done || cut) {
+            const uint32_t score = board_potential(board) - 4u * fours;
+            if (final_boards) final_boards[e] = board;
+            if (lengths) lengths[e] = t;
+            if (scores) scores[e] = score;
+            const uint32_t me = max_exponent(board);
+            const unsigned long long tile = 1ull << me;
+            st_episodes += 1;
+            st_steps += t;
+            st_score += score;
+            st_cut += cut ? 1u : 0u;
+            st_ovf += seen15 ? 1u : 0u;
+            st_longest = max(st_longest, t);
+            st_tile += tile;
+            st_tile2 += tile * tile;
+            atomicAdd(&s_stats[16 + me], 1ull);
+            phase = PHASE_NONE;
+        }
+    }
+
+    atomicAdd(&s_stats[0], (unsigned long long)st_episodes);
+    atomicAdd(&s_stats[1], st_steps);
+    atomicAdd(&s_stats[2], st_score);
+    atomicAdd(&s_stats[3], (unsigned long long)st_cut);
+    atomicAdd(&s_stats[4], (unsigned long long)st_ovf);
+    atomicMax(&s_stats[5], (unsigned long long)st_longest);
+    atomicAdd(&s_stats[6], st_tile);
+    atomicAdd(&s_stats[7], st_tile2);
+    __syncthreads();
+    for (int i = threadIdx.x; i < G2048_PLAY_STATS_WORDS; i += blockDim.x) {
+        const unsigned long long v = s_stats[i];
+        if (v) {
+            if (i == 5) atomicMax(&stats[i], v);
+            else atomicAdd(&stats[i], v);
+        }
+    }
+}
+
+template <int MODE, int POLICY>
+static int launch_play2(const uint32_t* d_subs, int64_t n_subs, int64_t batch_global, int64_t env_lo, int64_t n,
+                        uint64_t* d_work, uint64_t* d_final_boards, uint32_t* d_lengths, uint32_t* d_scores,
+                        uint64_t* d_stats, cudaStream_t st) {
+    int per_sm = 0;
+    int rc = check_cuda(
+        cudaOccupancyMaxActiveBlocksPerMultiprocessor(&per_sm, play2_kernel<MODE, POLICY>, PLAY2_THREADS, 0),
+        "play: occupancy");
+    if (rc) return rc;
+    const int sms = sm_count();
+    if (sms <= 0 || per_sm <= 0) return fail_arg("play: no device");
+    int64_t grid = (int64_t)sms * per_sm;  // one wave of resident CTAs: the kernel is persistent
+    const int64_t needed = (n + PLAY2_THREADS - 1) / PLAY2_THREADS;
+    if (grid > needed) grid = needed;
+    play2_kernel<MODE, POLICY><<<(unsigned)grid, PLAY2_THREADS, 0, st>>>(
+        (const uint2*)d_subs, n_subs, (uint32_t)batch_global, (uint32_t)env_lo, (uint32_t)n,
+        (unsigned long long*)d_work, (u64*)d_final_boards, d_lengths, d_scores, (unsigned long long*)d_stats);
+    return check_cuda(cudaGetLastError(), "play");
+}
+
+}  // namespace g2048
+
+using namespace g2048;
+
+extern "C" int g2048_play(int policy, const uint32_t* d_subs, int64_t n_subs, int64_t batch_global, int64_t env_lo,
+                          int64_t n, int rng_mode, uint64_t* d_work, uint64_t* d_final_boards, uint32_t* d_lengths,
+                          uint32_t* d_scores, uint64_t* d_stats, void* stream) {
+    G2048_REQUIRE(policy == G2048_POLICY_RANDOM || policy == G2048_POLICY_DRUL, "play: policy");
+    G2048_REQUIRE(rng_mode == G2048_RNG_ORIGINAL || rng_mode == G2048_RNG_PARTITIONABLE, "play: rng_mode");
+    G2048_REQUIRE(batch_global > 0 && batch_global <= 0x7FFFFFFFll && env_lo >= 0 && n >= 0 && env_lo + n <= batch_global,
+                  "play: batch");
+    G2048_REQUIRE(n_subs >= 3 && d_subs && d_work && d_stats, "play: pointers");
+    if (n == 0) return G2048_OK;
+    cudaStream_t st = (cudaStream_t)stream;
+#define ARGS d_subs, n_subs, batch_global, env_lo, n, d_work, d_final_boards, d_lengths, d_scores, d_stats, st
+    if (policy == G2048_POLICY_RANDOM) {
+        if (rng_mode == G2048_RNG_PARTITIONABLE) return launch_play2<G2048_RNG_PARTITIONABLE, G2048_POLICY_RANDOM>(ARGS);
+        return launch_play2<G2048_RNG_ORIGINAL, G2048_POLICY_RANDOM>(ARGS);
+    }
+    if (rng_mode == G2048_RNG_PARTITIONABLE) return launch_play2<G2048_RNG_PARTITIONABLE, G2048_POLICY_DRUL>(ARGS);
+    return launch_play2<G2048_RNG_ORIGINAL, G2048_POLICY_DRUL>(ARGS);
+#undef ARGS
+}

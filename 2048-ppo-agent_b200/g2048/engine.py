@@ -134,8 +134,9 @@ STAT_NAMES = ("episodes", "env_steps", "score_sum", "cut_short", "overflowed", "
 
 
 def play(policy: int, subs: torch.Tensor, batch_global: int, env_lo: int, n: int, rng_mode: int,
-         per_env: bool = True, stats: torch.Tensor | None = None):
-    """Persistent play-to-termination kernel.  Returns dict(final_boards, lengths, scores, stats)."""
+         per_env: bool = True, stats: torch.Tensor | None = None, entry: str = "g2048_play"):
+    """Persistent play-to-termination kernel.  Returns dict(final_boards, lengths, scores, stats).
+    entry="g2048_play_v1" runs the first-generation kernel (A/B timing only)."""
     dev = subs.device
     work = torch.zeros(2, dtype=torch.int64, device=dev)
     if stats is None:
@@ -145,7 +146,7 @@ def play(policy: int, subs: torch.Tensor, batch_global: int, env_lo: int, n: int
         boards = torch.empty(n, dtype=torch.int64, device=dev)
         lengths = torch.empty(n, dtype=torch.int32, device=dev)
         scores = torch.empty(n, dtype=torch.int32, device=dev)
-    call("g2048_play", policy, ptr(_i32(subs)), subs.shape[0], batch_global, env_lo, n, rng_mode, ptr(work),
+    call(entry, policy, ptr(_i32(subs)), subs.shape[0], batch_global, env_lo, n, rng_mode, ptr(work),
          ptr(boards), ptr(lengths), ptr(scores), ptr(stats), stream_ptr())
     return dict(final_boards=boards, lengths=lengths, scores=scores, stats=stats)
 

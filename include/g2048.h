@@ -121,6 +121,12 @@ int g2048_play(int policy, const uint32_t* d_subs, int64_t n_subs, int64_t batch
                int rng_mode, uint64_t* d_work, uint64_t* d_final_boards, uint32_t* d_lengths, uint32_t* d_scores,
                uint64_t* d_stats, void* stream);
 
+/* First-generation play kernel (lanes park until six are free, per-step reward loop): identical
+ * arguments and results; kept so that the current kernel can be A/B-timed against it. */
+int g2048_play_v1(int policy, const uint32_t* d_subs, int64_t n_subs, int64_t batch_global, int64_t env_lo, int64_t n,
+                  int rng_mode, uint64_t* d_work, uint64_t* d_final_boards, uint32_t* d_lengths, uint32_t* d_scores,
+                  uint64_t* d_stats, void* stream);
+
 /* Host-buffer form of the same call (the reference-facing entry: run_actions_max_tile's inner
  * run).  seed -> jax.random.key(seed); h_key_io (2 words, may be NULL) overrides the seed with an
  * explicit chain key and receives the key the reference's runner would hold afterwards.

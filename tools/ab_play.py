@@ -1,0 +1,35 @@
+"""A/B of the play kernels (v1 vs current) on the same box, plus correctness cross-check."""
+import sys
+from pathlib import Path
+ROOT = Path(__file__).resolve().parent.parent
+sys.path[:0] = [str(ROOT), str(ROOT / "2048-ppo-agent_b200")]
+import numpy as np, torch
+from g2048 import engine as E
+
+def timed(fn, reps=3):
+    fn(); torch.cuda.synchronize()
+    best = 1e9
+    for _ in range(reps):
+        a, b = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+        a.record(); fn(); b.record(); torch.cuda.synchronize()
+        best = min(best, a.elapsed_time(b) * 1e-3)
+    return best
+
+for mode in (1, 0):
+    key = E.words_tensor([0, 7], "cuda")
+    subs = E.chain_advance(key, mode, 1 + 2 * 4096)
+    for policy, name in ((0, "random"), (1, "drul")):
+        n = 1 << 21
+        res = {}
+        for entry in ("g2048_play_v1", "g2048_play"):
+            out = {}
+            def run():
+                out.update(E.play(policy, subs, n, 0, n, mode, per_env=True, entry=entry))
+            t = timed(run)
+            st = E.play_stats_dict(out["stats"])
+            res[entry] = out
+            print(f"mode {mode} {name:6s} {entry:14s} n={n}: {st['env_steps'] / t / 1e9:7.3f} G env-steps/s ({t*1e3:.2f} ms) longest {st['longest']} ovf {st['overflowed']}")
+        a, b = res["g2048_play_v1"], res["g2048_play"]
+        same = all(torch.equal(a[k], b[k]) for k in ("final_boards", "lengths", "scores"))
+        sa, sb = a["stats"].clone(), b["stats"].clone()
+        print("   identical per-env results:", same, " identical stats:", torch.equal(sa, sb))
