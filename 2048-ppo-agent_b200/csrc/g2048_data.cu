@@ -295,7 +295,7 @@ using namespace g2048;
 
 static inline bool aligned16(const void* p) { return ((uintptr_t)p & 15u) == 0; }
 
-extern "C" int g2048_expand_obs(const uint64_t* d_boards, int64_t n, int dtype, void* d_out, int64_t rows,
+extern "C" int g2048_expand_obs_v1(const uint64_t* d_boards, int64_t n, int dtype, void* d_out, int64_t rows,
                                 int64_t n_cols, void* stream) {
     G2048_REQUIRE(n >= 0 && rows >= 0 && (rows == 0 || (n_cols > 0 && rows * n_cols == n)), "expand_obs: shape");
     if (n == 0) return G2048_OK;

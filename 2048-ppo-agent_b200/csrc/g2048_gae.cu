@@ -299,7 +299,7 @@ extern "C" int64_t g2048_gae_flat_scratch_bytes(int64_t n) {
     return (int64_t)sizeof(GaeScratch) + n_tiles * 8;
 }
 
-extern "C" int g2048_gae_flat(const float* d_rewards, const float* d_values, const uint8_t* d_dones, int64_t n,
+extern "C" int g2048_gae_flat_v1(const float* d_rewards, const float* d_values, const uint8_t* d_dones, int64_t n,
                               double gamma, double lambda_gae, float* d_adv, float* d_ret, void* d_scan_state,
                               double* d_moments, void* stream) {
     G2048_REQUIRE(n >= 0, "gae_flat: n");

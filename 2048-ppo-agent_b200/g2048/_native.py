@@ -61,6 +61,7 @@ _SIGNATURES = {
     "g2048_sample_logits": (_INT, [_P, _P, _INT, _INT, _P, _I64, _I64, _I64, _INT, _P, _P, _P, _P]),
     "g2048_evaluate_logits": (_INT, [_P, _P, _INT, _P, _I64, _P, _P, _P]),
     "g2048_expand_obs": (_INT, [_P, _I64, _INT, _P, _I64, _I64, _P]),
+    "g2048_expand_obs_v1": (_INT, [_P, _I64, _INT, _P, _I64, _I64, _P]),
     "g2048_pack_obs": (_INT, [_P, _INT, _I64, _P, _P]),
     "g2048_unpack_status": (_INT, [_P, _I64, _P, _P, _P]),
     "g2048_unpack_records": (_INT, [_P, _P, _P, _P, _I64, _I64, _P, _P, _P, _P, _P, _P, _P]),
@@ -70,6 +71,7 @@ _SIGNATURES = {
     "g2048_unpack_flat_meta": (_INT, [_P, _I64, _P, _P, _P, _P]),
     "g2048_gae_flat_scratch_bytes": (_I64, [_I64]),
     "g2048_gae_flat": (_INT, [_P, _P, _P, _I64, _DBL, _DBL, _P, _P, _P, _P, _P]),
+    "g2048_gae_flat_v1": (_INT, [_P, _P, _P, _I64, _DBL, _DBL, _P, _P, _P, _P, _P]),
     "g2048_gae_time_major": (_INT, [_P, _P, _P, _I64, _I64, _P, _DBL, _DBL, _P, _P, _P, _P]),
     "g2048_normalize": (_INT, [_P, _I64, _P, _INT, _P]),
     "g2048_gae_host": (_INT, [_P, _P, _P, _I64, _DBL, _DBL, _INT, _P, _P]),

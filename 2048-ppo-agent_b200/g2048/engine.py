@@ -220,12 +220,14 @@ def evaluate_logits(logits, mask_bits, use_mask: bool, actions):
 _OBS_DTYPES = {torch.bool: N.OBS_BOOL, torch.uint8: N.OBS_BOOL, torch.float32: N.OBS_F32, torch.bfloat16: N.OBS_BF16}
 
 
-def expand_obs(boards: torch.Tensor, dtype=torch.float32, rows: int = 0, n_cols: int = 0, out=None) -> torch.Tensor:
-    """One-hot (n,16,31).  rows/n_cols > 0: boards are (rows, n_cols) time-major, output is env-major."""
+def expand_obs(boards: torch.Tensor, dtype=torch.float32, rows: int = 0, n_cols: int = 0, out=None,
+               entry: str = "g2048_expand_obs") -> torch.Tensor:
+    """One-hot (n,16,31).  rows/n_cols > 0: boards are (rows, n_cols) time-major, output is env-major.
+    entry="g2048_expand_obs_v1" runs the first-generation kernel (A/B timing and tests)."""
     n = boards.numel()
     if out is None:
         out = torch.empty((n, 16, 31), dtype=dtype, device=boards.device)
-    call("g2048_expand_obs", ptr(boards), n, _OBS_DTYPES[dtype], ptr(out), rows, n_cols, stream_ptr())
+    call(entry, ptr(boards), n, _OBS_DTYPES[dtype], ptr(out), rows, n_cols, stream_ptr())
     return out
 
 
@@ -296,15 +298,17 @@ def unpack_flat_meta(meta: torch.Tensor):
 
 
 # ------------------------------------------------------------------------------------------- GAE
-def gae_flat(rewards, values, dones, gamma: float, lambda_gae: float, want_moments: bool = True):
-    """-> adv, ret (n,) float32, moments (6,) float64 or None.  dones: uint8/bool (n,)."""
+def gae_flat(rewards, values, dones, gamma: float, lambda_gae: float, want_moments: bool = True,
+             entry: str = "g2048_gae_flat"):
+    """-> adv, ret (n,) float32, moments (6,) float64 or None.  dones: uint8/bool (n,).
+    entry="g2048_gae_flat_v1" runs the first-generation kernel."""
     n = rewards.shape[0]
     dev = rewards.device
     adv = torch.empty(n, dtype=torch.float32, device=dev)
     ret = torch.empty(n, dtype=torch.float32, device=dev)
     scratch = torch.zeros(int(N.lib.g2048_gae_flat_scratch_bytes(n)), dtype=torch.uint8, device=dev)
     moments = torch.zeros(6, dtype=torch.float64, device=dev) if want_moments else None
-    call("g2048_gae_flat", ptr(rewards), ptr(values), ptr(dones), n, float(gamma), float(lambda_gae), ptr(adv),
+    call(entry, ptr(rewards), ptr(values), ptr(dones), n, float(gamma), float(lambda_gae), ptr(adv),
          ptr(ret), ptr(scratch), ptr(moments), stream_ptr())
     return adv, ret, moments
 

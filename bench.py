@@ -400,7 +400,7 @@ def secondary_measurements(E, N, torch, dev, flush_buf) -> dict:
     boards = torch.randint(0, 1 << 62, (n_b,), dtype=torch.int64, device=dev)
     out_f32 = torch.empty((n_b, 16, 31), dtype=torch.float32, device=dev)
     t = timed(lambda: N.call("g2048_expand_obs", N.ptr(boards), n_b, N.OBS_F32, N.ptr(out_f32), 0, 0, N.stream_ptr()))
-    add("expand_obs_kernel<float>", n_b * (8 + 1984), t, "2^20 boards -> (n,16,31) f32; 8 B read + 1984 B written per board")
+    add("expand_obs_tma_kernel<float>", n_b * (8 + 1984), t, "2^20 boards -> (n,16,31) f32; 8 B read + 1984 B written per board; bulk-copy (UBLKCP) stores")
     del out_f32
 
     # GAE on a flat buffer: C4-sized (2^26 steps), episodes ~300 steps
@@ -419,7 +419,7 @@ def secondary_measurements(E, N, torch, dev, flush_buf) -> dict:
                N.ptr(mom), N.stream_ptr())
 
     t = timed(gae)
-    add("gae_flat_kernel", n_g * 17, t, "2^26 steps, done rate 1/300; 9 B read + 8 B written per step (SURVEY 8d)")
+    add("gae_flat3_kernel", n_g * 17, t, "2^26 steps, done rate 1/300 (episodes ~300 steps); 9 B read + 8 B written per step (SURVEY 8d); bound by the serial per-episode recurrence, see DESIGN.md")
     t = timed(lambda: N.call("g2048_normalize", N.ptr(adv), n_g, N.ptr(mom), 1, N.stream_ptr()))
     add("normalize_kernel", n_g * 8, t, "2^26 steps in place; 4 B read + 4 B written per step")
     del r, v, d, adv, ret
@@ -456,11 +456,44 @@ def secondary_measurements(E, N, torch, dev, flush_buf) -> dict:
                N.ptr(adv2), N.ptr(ret2), N.ptr(mom), N.stream_ptr())
 
     t = timed(ppo_rollout, reps=3)
+
+    # the policy network's forward pass at the same batch (PyTorch / cuBLAS, outside the product path): a stand-in
+    # with the reference's default layer shapes (configs/model/transformer_combined.yaml: d_model 256, 8 heads,
+    # 4 layers, ff 1024, hidden 512, CLS reduction, 17 tokens), bf16 autocast as in configs/trainer/default.yaml
+    fwd_ms = None
+    try:
+        nn = torch.nn
+
+        class PolicyStandIn(nn.Module):
+            def __init__(self):
+                super().__init__()
+                self.embed = nn.Linear(31, 256, bias=False)
+                self.cls = nn.Parameter(torch.zeros(1, 1, 256))
+                layer = nn.TransformerEncoderLayer(256, 8, 1024, dropout=0.0, batch_first=True, norm_first=True)
+                self.encoder = nn.TransformerEncoder(layer, 4, enable_nested_tensor=False)
+                self.actor = nn.Sequential(nn.Linear(256, 512), nn.ReLU(), nn.Linear(512, 512), nn.ReLU(), nn.Linear(512, 4, bias=False))
+                self.critic = nn.Sequential(nn.Linear(256, 512), nn.ReLU(), nn.Linear(512, 512), nn.ReLU(), nn.Linear(512, 1, bias=False))
+
+            def forward(self, x):
+                h = self.embed(x)
+                h = torch.cat([self.cls.expand(h.shape[0], -1, -1), h], dim=1)
+                h = self.encoder(h)[:, 0]
+                return self.actor(h), self.critic(h)
+
+        net = PolicyStandIn().to(dev).eval()
+        with torch.no_grad(), torch.autocast("cuda", dtype=torch.bfloat16):
+            fwd = timed(lambda: net(obs), reps=3)
+        fwd_ms = fwd * 1e3
+        del net
+    except Exception as exc:  # the stand-in is context, not part of the product
+        fwd_ms = f"unavailable: {exc}"
     ppo = {
         "config": "C3: 65536 envs x 128 steps, auto-reset, masked categorical sampling from synthetic logits "
                   "(policy network = PyTorch/cuBLAS, outside the product path and not timed)",
         "env_steps_per_sec": t_steps * b / t, "ms_per_rollout": t * 1e3,
         "per_step_us": t * 1e6 / t_steps, "launches_per_rollout": 2 * t_steps + 1,
+        "policy_forward_ms_per_step": fwd_ms,
+        "policy_forward_note": "same-shaped PyTorch Transformer (3.96 M parameters, bf16 autocast, 65536 x 17 tokens), for scale only",
         "kernels": "per step: expand_obs<f32> (network input) + policy_step (mask, sample, log-prob, env step, auto-reset, record write); then gae_time_major",
     }
     return {"roofline_hbm": rows, "hbm_peak_source": peak_src, "ppo_rollout": ppo}

@@ -184,6 +184,10 @@ int g2048_evaluate_logits(const float* d_logits, const uint8_t* d_mask_bits, int
 int g2048_expand_obs(const uint64_t* d_boards, int64_t n, int dtype, void* d_out, int64_t rows, int64_t n_cols,
                      void* stream);
 
+/* First-generation kernel (one 16-byte chunk per thread, plain stores); same arguments. */
+int g2048_expand_obs_v1(const uint64_t* d_boards, int64_t n, int dtype, void* d_out, int64_t rows, int64_t n_cols,
+                        void* stream);
+
 /* Inverse of g2048_expand_obs: argmax over the 31 channels of every cell (the
  * `observations.argmax(-1)` of src/runs/run_actions_max_tile.py:61-63).  dtype BOOL or F32. */
 int g2048_pack_obs(const void* d_obs, int dtype, int64_t n, uint64_t* d_boards, void* stream);
@@ -225,12 +229,19 @@ int g2048_unpack_flat_meta(const uint8_t* d_meta, int64_t n, float* d_actions_on
 
 /* Flat buffer, reverse segmented scan: if done[t]: last_v = last_gae = 0;
  * delta = r[t] + gamma*last_v - V[t]; gae = delta + gamma*lambda*gae; adv[t]=gae; ret[t]=gae+V[t].
- * Single pass, decoupled look-back across CTAs.  d_scan_state: scratch of
+ * Single pass (one CTA per 6 144-step tile, one lane per episode, decoupled look-back of depth one
+ * across tiles); bit-identical to the reference loop.  d_scan_state: scratch of
  * g2048_gae_flat_scratch_bytes(n) bytes, zeroed by the caller.  d_moments (double[6], may be NULL,
  * ACCUMULATED): [0] n, [1] sum adv, [2] sum adv^2, [3] sum ret, [4] sum ret^2, [5] unused. */
 int64_t g2048_gae_flat_scratch_bytes(int64_t n);
 int g2048_gae_flat(const float* d_rewards, const float* d_values, const uint8_t* d_dones, int64_t n, double gamma,
                    double lambda_gae, float* d_adv, float* d_ret, void* d_scan_state, double* d_moments, void* stream);
+
+/* First-generation kernel (1 024-step tiles, every array staged in shared memory); same arguments.
+ * Kept so that the current kernel can be A/B-timed against it. */
+int g2048_gae_flat_v1(const float* d_rewards, const float* d_values, const uint8_t* d_dones, int64_t n, double gamma,
+                      double lambda_gae, float* d_adv, float* d_ret, void* d_scan_state, double* d_moments,
+                      void* stream);
 
 /* Time-major (T,B) buffer, one lane per env, exactly the reference's operation order per env;
  * d_bootstrap (n) float32 or NULL is V(s_T) for envs whose last step is not done (fixed-horizon

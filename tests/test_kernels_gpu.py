@@ -450,20 +450,25 @@ def test_policy_step_auto_reset_follows_pgx_wrapper(E):
 
 
 # ----------------------------------------------------------------------------------------- records
+@pytest.mark.parametrize("entry", ["g2048_expand_obs", "g2048_expand_obs_v1"])
 @pytest.mark.parametrize("dtype", [torch.float32, torch.bool, torch.bfloat16])
-def test_expand_obs_matches_oracle(E, dtype):
+def test_expand_obs_matches_oracle(E, dtype, entry):
     rng = np.random.default_rng(41)
-    n = 5000
+    for n in (1, 2, 3, 5, 31, 257):  # ragged image groups of the bulk-store kernel
+        b = rng.integers(0, 16, (n, 16))
+        got = E.expand_obs(dev(E.pack_boards(b)), dtype, entry=entry)
+        np.testing.assert_array_equal(got.float().cpu().numpy(), O.observe(b).reshape(n, 16, 31).astype(np.float32))
+    n = 70001
     boards = rng.integers(0, 16, (n, 16))
     boards[0] = 0
     boards[1] = 15
-    out = E.expand_obs(dev(E.pack_boards(boards)), dtype)
+    out = E.expand_obs(dev(E.pack_boards(boards)), dtype, entry=entry)
     want = O.observe(boards).reshape(n, 16, 31)
     np.testing.assert_array_equal(out.float().cpu().numpy(), want.astype(np.float32))
     # time-major records -> env-major (B, T) stacking of batch_runner.py:138
     t_steps, b = 7, 13
     rec = rng.integers(0, 12, (t_steps, b, 16))
-    out = E.expand_obs(dev(E.pack_boards(rec)), dtype, rows=t_steps, n_cols=b)
+    out = E.expand_obs(dev(E.pack_boards(rec)), dtype, rows=t_steps, n_cols=b, entry=entry)
     want = O.observe(rec.transpose(1, 0, 2).reshape(-1, 16)).reshape(b * t_steps, 16, 31)
     np.testing.assert_array_equal(out.float().cpu().numpy(), want.astype(np.float32))
 
@@ -515,11 +520,15 @@ def test_exclusive_scan_large(E):
 TAGS = ["default", "short_eps", "undiscounted", "lowlam", "open_tail", "two"]
 
 
+GAE_ENTRIES = ["g2048_gae_flat", "g2048_gae_flat_v1"]
+
+
+@pytest.mark.parametrize("entry", GAE_ENTRIES)
 @pytest.mark.parametrize("tag", TAGS)
-def test_gae_flat_is_bit_exact_vs_reference_fixture(E, golden_ppo, tag):
+def test_gae_flat_is_bit_exact_vs_reference_fixture(E, golden_ppo, tag, entry):
     g = golden_ppo
     gamma, lam = g[f"gae_{tag}_params"]
-    adv, ret, mom = E.gae_flat(dev(g[f"gae_{tag}_rewards"]), dev(g[f"gae_{tag}_values"]), dev(g[f"gae_{tag}_dones"].astype(np.uint8)), gamma, lam)
+    adv, ret, mom = E.gae_flat(dev(g[f"gae_{tag}_rewards"]), dev(g[f"gae_{tag}_values"]), dev(g[f"gae_{tag}_dones"].astype(np.uint8)), gamma, lam, entry=entry)
     np.testing.assert_array_equal(adv.cpu().numpy(), g[f"gae_{tag}_adv"])
     np.testing.assert_array_equal(ret.cpu().numpy(), g[f"gae_{tag}_ret"])
     # tolerance stated by north_star: 1e-5 relative in fp32
@@ -529,14 +538,16 @@ def test_gae_flat_is_bit_exact_vs_reference_fixture(E, golden_ppo, tag):
     np.testing.assert_allclose(ret.cpu().numpy(), g[f"gae_{tag}_ret_norm"], rtol=1e-5, atol=1e-6)
 
 
-@pytest.mark.parametrize("n,done_rate", [(1, 1.0), (1023, 0.01), (1024, 0.01), (1025, 0.0), (5000, 0.0), (300_000, 1 / 300), (2_000_000, 1 / 3000)])
-def test_gae_flat_matches_oracle_at_scale(E, n, done_rate):
+@pytest.mark.parametrize("entry", GAE_ENTRIES)
+@pytest.mark.parametrize("n,done_rate", [(1, 1.0), (1023, 0.01), (1024, 0.01), (1025, 0.0), (5000, 0.0), (6144, 0.5), (6145, 1.0),
+                                         (12288, 0.0), (18433, 0.002), (50_000, 0.7), (300_000, 1 / 300), (2_000_000, 1 / 3000)])
+def test_gae_flat_matches_oracle_at_scale(E, n, done_rate, entry):
     rng = np.random.default_rng(n)
     r = (rng.integers(0, 64, n) * 4 * (rng.random(n) < 0.4)).astype(np.float32)
     v = (rng.standard_normal(n) * 10).astype(np.float32)
     d = (rng.random(n) < done_rate).astype(np.uint8)
     want_a, want_r = CO.gae(r, v, d, 0.99, 0.95)
-    adv, ret, mom = E.gae_flat(dev(r), dev(v), dev(d), 0.99, 0.95)
+    adv, ret, mom = E.gae_flat(dev(r), dev(v), dev(d), 0.99, 0.95, entry=entry)
     np.testing.assert_array_equal(adv.cpu().numpy(), want_a)
     np.testing.assert_array_equal(ret.cpu().numpy(), want_r)
     m = mom.cpu().numpy()
@@ -578,6 +589,21 @@ def test_gae_time_major_matches_oracle_per_env(E):
             np.testing.assert_array_equal(ret[:, e], wr)
         assert mom[0].item() == t_steps * n
         np.testing.assert_allclose(mom[1].item(), adv.astype(np.float64).sum(), rtol=1e-9, atol=1e-6)
+
+
+def test_gae_flat_unaligned_views_and_nonbinary_dones(E):
+    rng = np.random.default_rng(53)
+    n = 40_000
+    r = (rng.integers(0, 64, n + 3) * 4).astype(np.float32)
+    v = rng.standard_normal(n + 3).astype(np.float32)
+    d = ((rng.random(n + 3) < 0.01) * rng.integers(1, 256, n + 3)).astype(np.uint8)  # any non-zero byte is a done
+    want_a, want_r = CO.gae(r[3:], v[3:], d[3:], 0.99, 0.95)
+    # 4-byte aligned but not 16-byte aligned views
+    adv, ret, _ = E.gae_flat(dev(r)[3:], dev(v)[3:], dev(d)[3:], 0.99, 0.95)
+    np.testing.assert_array_equal(adv.cpu().numpy(), want_a)
+    np.testing.assert_array_equal(ret.cpu().numpy(), want_r)
+    adv, ret, _ = E.gae_flat(dev(r[3:].copy()), dev(v[3:].copy()), dev(d[3:].copy()), 0.99, 0.95)
+    np.testing.assert_array_equal(adv.cpu().numpy(), want_a)
 
 
 def test_gae_host_entry_point(E, golden_ppo):

@@ -33,3 +33,22 @@ for mode in (1, 0):
         same = all(torch.equal(a[k], b[k]) for k in ("final_boards", "lengths", "scores"))
         sa, sb = a["stats"].clone(), b["stats"].clone()
         print("   identical per-env results:", same, " identical stats:", torch.equal(sa, sb))
+
+n = 1 << 26
+r = torch.rand(n, device="cuda"); v = torch.rand(n, device="cuda"); d = (torch.rand(n, device="cuda") < 1 / 300).to(torch.uint8)
+for rate in (1 / 300, 1 / 30, 1 / 3000):
+    d = (torch.rand(n, device="cuda") < rate).to(torch.uint8)
+    outs = {}
+    for entry in ("g2048_gae_flat_v1", "g2048_gae_flat"):
+        t = timed(lambda: outs.__setitem__(entry, E.gae_flat(r, v, d, 0.99, 0.95, entry=entry)))
+        print(f"{entry:18s} n=2^26 done rate {rate:.5f}: {n * 17 / t / 1e9:6.0f} GB/s ({t*1e6:.0f} us incl. scratch alloc)")
+    print("   identical:", torch.equal(outs["g2048_gae_flat_v1"][0], outs["g2048_gae_flat"][0]), torch.equal(outs["g2048_gae_flat_v1"][1], outs["g2048_gae_flat"][1]))
+boards = torch.randint(0, 2**62, (1 << 20,), device="cuda")
+for dt, sz in ((torch.float32, 4), (torch.bfloat16, 2), (torch.bool, 1)):
+    out = torch.empty((1 << 20, 16, 31), dtype=dt, device="cuda")
+    ref = None
+    for entry in ("g2048_expand_obs_v1", "g2048_expand_obs"):
+        t = timed(lambda: E.expand_obs(boards, dt, out=out, entry=entry))
+        same = "" if ref is None else f" identical: {torch.equal(ref.view(torch.uint8), out.view(torch.uint8))}"
+        ref = out.clone()
+        print(f"{entry:20s} {str(dt):15s}: {(1 << 20) * (496 * sz + 8) / t / 1e9:6.0f} GB/s ({t*1e6:.0f} us){same}")
