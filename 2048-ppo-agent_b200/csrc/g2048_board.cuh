@@ -152,17 +152,43 @@ __device__ __forceinline__ int kth_flag_cell(u64 flags, int k) {
 //       = the ceil(fl32(n_empty * (1-u)))-th empty cell in row-major order, 1-based;
 //   val = 2 (a 4-tile) iff 1.0f*(1-u') > 0.9f, else 1.
 // With u = f - 1 for f in [1,2): 1 - u = m * 2^-23 exactly, m = 2^23 - (bits >> 9).
-__device__ __forceinline__ u64 spawn_tile(u64 x, uint32_t bits_pos, uint32_t bits_val) {
+// The spawn decision alone: which cell (row-major index) and which exponent (1 or 2).
+__device__ __forceinline__ void spawn_select(u64 x, uint32_t bits_pos, uint32_t bits_val, int& cell, u64& val) {
     const u64 empties = ~nonzero_lsb(x) & NIB_LSB;
     const int n_empty = __popcll(empties);
     const float one_minus_u = __fsub_rn(1.0f, unit_float(bits_pos));
     const float r = __fmul_rn((float)n_empty, one_minus_u);
-    int k = (int)ceilf(r);
+    const int k = (int)ceilf(r);
     // a full board (only reachable through the illegal-action path) leaves searchsorted at cell 0
-    const int cell = (n_empty == 0) ? 0 : kth_flag_cell(empties, k);
+    cell = (n_empty == 0) ? 0 : kth_flag_cell(empties, k);
     const uint32_t m_val = 0x800000u - (bits_val >> 9);
-    const u64 val = (m_val > 7549747u) ? 2ull : 1ull;  // m * 2^-23 > 0.9f = 15099494 * 2^-24
+    val = (m_val > 7549747u) ? 2ull : 1ull;  // m * 2^-23 > 0.9f = 15099494 * 2^-24
+}
+
+__device__ __forceinline__ u64 spawn_tile(u64 x, uint32_t bits_pos, uint32_t bits_val) {
+    int cell;
+    u64 val;
+    spawn_select(x, bits_pos, bits_val, cell, val);
     return (x & ~(0xFull << (4 * cell))) | (val << (4 * cell));
+}
+
+// transpose of the 4x4 nibble matrix: cell (r, c) <-> cell (c, r)
+__device__ __forceinline__ u64 transpose_board(u64 x) {
+    u64 t = (x ^ (x >> 12)) & 0x0000F0F00000F0F0ull;
+    x ^= t ^ (t << 12);
+    t = (x ^ (x >> 24)) & 0x00000000FF00FF00ull;
+    x ^= t ^ (t << 24);
+    return x;
+}
+
+// reverse the nibble order inside each 16-bit row (mirror the board left <-> right)
+__device__ __forceinline__ u64 mirror_rows(u64 x) {
+    uint32_t lo = (uint32_t)x, hi = (uint32_t)(x >> 32);
+    lo = __byte_perm(lo, 0, 0x2301);
+    hi = __byte_perm(hi, 0, 0x2301);
+    lo = ((lo & 0x0F0F0F0Fu) << 4) | ((lo >> 4) & 0x0F0F0F0Fu);
+    hi = ((hi & 0x0F0F0F0Fu) << 4) | ((hi >> 4) & 0x0F0F0F0Fu);
+    return ((u64)hi << 32) | lo;
 }
 
 __device__ __forceinline__ uint32_t max_exponent(u64 x) {

@@ -461,58 +461,79 @@ extern "C" int g2048_play_host(int policy, uint64_t seed, uint32_t* h_key_io, in
     uint32_t key[2] = {(uint32_t)(seed >> 32), (uint32_t)(seed & 0xFFFFFFFFull)};
     if (h_key_io) { key[0] = h_key_io[0]; key[1] = h_key_io[1]; }
 
+    // Workspace of the calling thread on the current device: one stream and one grow-only device
+    // buffer, kept across calls so that a call costs copies and kernels, not cudaMalloc/cudaFree.
+    struct Workspace {
+        int device = -1;
+        cudaStream_t stream = nullptr;
+        uint8_t* buf = nullptr;
+        size_t bytes = 0;
+    };
+    static thread_local Workspace ws;
     int rc = G2048_OK;
-    cudaStream_t st = nullptr;
-    uint32_t* d_key = nullptr;
-    uint32_t* d_subs = nullptr;
-    uint64_t *d_work = nullptr, *d_stats = nullptr, *d_boards = nullptr;
-    uint32_t *d_len = nullptr, *d_score = nullptr;
+    int dev = 0;
     uint64_t stats[G2048_PLAY_STATS_WORDS];
-    int64_t max_steps = 2048;  // grown on demand
-#define TRY(expr, where) do { rc = check_cuda((expr), where); if (rc) goto done; } while (0)
-    TRY(cudaStreamCreateWithFlags(&st, cudaStreamNonBlocking), "play_host: stream");
-    TRY(cudaMalloc(&d_key, 2 * sizeof(uint32_t)), "play_host: malloc");
-    TRY(cudaMalloc(&d_work, 2 * sizeof(uint64_t)), "play_host: malloc");
-    TRY(cudaMalloc(&d_stats, sizeof(stats)), "play_host: malloc");
-    if (h_final_boards && n) TRY(cudaMalloc(&d_boards, n * sizeof(uint64_t)), "play_host: malloc");
-    if (h_lengths && n) TRY(cudaMalloc(&d_len, n * sizeof(uint32_t)), "play_host: malloc");
-    if (h_scores && n) TRY(cudaMalloc(&d_score, n * sizeof(uint32_t)), "play_host: malloc");
+    int64_t max_steps = 1024;  // grown on demand
+#define TRY(expr, where) do { rc = check_cuda((expr), where); if (rc) return rc; } while (0)
+    TRY(cudaGetDevice(&dev), "play_host: device");
+    if (ws.device != dev) {  // first call on this thread, or the thread switched device
+        ws = Workspace();
+        TRY(cudaStreamCreateWithFlags(&ws.stream, cudaStreamNonBlocking), "play_host: stream");
+        ws.device = dev;
+    }
+    cudaStream_t st = ws.stream;
+    const auto align256 = [](size_t x) { return (x + 255) & ~(size_t)255; };
     while (true) {
         const int64_t n_subs = 1 + 2 * max_steps;
-        TRY(cudaMalloc(&d_subs, n_subs * 2 * sizeof(uint32_t)), "play_host: malloc subs");
+        // layout: key | work | stats | subs | boards | lengths | scores
+        const size_t off_key = 0, off_work = 256, off_stats = 512, off_subs = 1024;
+        const size_t off_boards = off_subs + align256((size_t)n_subs * 8);
+        const size_t off_len = off_boards + align256(h_final_boards ? (size_t)n * 8 : 0);
+        const size_t off_score = off_len + align256(h_lengths ? (size_t)n * 4 : 0);
+        const size_t total = off_score + align256(h_scores ? (size_t)n * 4 : 0);
+        if (total > ws.bytes) {
+            if (ws.buf) cudaFree(ws.buf);
+            ws.buf = nullptr;
+            ws.bytes = 0;
+            TRY(cudaMalloc(&ws.buf, total), "play_host: malloc");
+            ws.bytes = total;
+        }
+        uint32_t* d_key = (uint32_t*)(ws.buf + off_key);
+        uint64_t* d_work = (uint64_t*)(ws.buf + off_work);
+        uint64_t* d_stats = (uint64_t*)(ws.buf + off_stats);
+        uint32_t* d_subs = (uint32_t*)(ws.buf + off_subs);
+        uint64_t* d_boards = h_final_boards ? (uint64_t*)(ws.buf + off_boards) : nullptr;
+        uint32_t* d_len = h_lengths ? (uint32_t*)(ws.buf + off_len) : nullptr;
+        uint32_t* d_score = h_scores ? (uint32_t*)(ws.buf + off_score) : nullptr;
         TRY(cudaMemcpyAsync(d_key, key, sizeof(key), cudaMemcpyHostToDevice, st), "play_host: h2d key");
-        TRY(cudaMemsetAsync(d_work, 0, 2 * sizeof(uint64_t), st), "play_host: memset");
-        TRY(cudaMemsetAsync(d_stats, 0, sizeof(stats), st), "play_host: memset");
+        TRY(cudaMemsetAsync(d_work, 0, 768, st), "play_host: memset");  // work + stats
         rc = g2048_chain_advance(d_key, rng_mode, n_subs, d_subs, st);
-        if (rc) goto done;
+        if (rc) return rc;
         rc = g2048_play(policy, d_subs, n_subs, batch_global, env_lo, n, rng_mode, d_work, d_boards, d_len, d_score,
                         d_stats, st);
-        if (rc) goto done;
+        if (rc) return rc;
+        // results are copied optimistically; a batch that outlived its keys is replayed below
         TRY(cudaMemcpyAsync(stats, d_stats, sizeof(stats), cudaMemcpyDeviceToHost, st), "play_host: d2h stats");
+        if (d_boards && n) TRY(cudaMemcpyAsync(h_final_boards, d_boards, n * sizeof(uint64_t), cudaMemcpyDeviceToHost, st), "play_host: d2h");
+        if (d_len && n) TRY(cudaMemcpyAsync(h_lengths, d_len, n * sizeof(uint32_t), cudaMemcpyDeviceToHost, st), "play_host: d2h");
+        if (d_score && n) TRY(cudaMemcpyAsync(h_scores, d_score, n * sizeof(uint32_t), cudaMemcpyDeviceToHost, st), "play_host: d2h");
         TRY(cudaStreamSynchronize(st), "play_host: sync");
         if (stats[3] == 0 || max_steps >= (1 << 20)) break;
-        cudaFree(d_subs);
-        d_subs = nullptr;
         max_steps *= 4;  // some episode outlived the chain: replay with a longer one
     }
-    if (h_final_boards && n) TRY(cudaMemcpy(h_final_boards, d_boards, n * sizeof(uint64_t), cudaMemcpyDeviceToHost), "play_host: d2h");
-    if (h_lengths && n) TRY(cudaMemcpy(h_lengths, d_len, n * sizeof(uint32_t), cudaMemcpyDeviceToHost), "play_host: d2h");
-    if (h_scores && n) TRY(cudaMemcpy(h_scores, d_score, n * sizeof(uint32_t), cudaMemcpyDeviceToHost), "play_host: d2h");
     if (h_stats) for (int i = 0; i < G2048_PLAY_STATS_WORDS; ++i) h_stats[i] = stats[i];
     if (h_key_io) {
         // the reference's runner holds the chain key after 1 + 2*T splits, T = longest episode
-        uint32_t k2[2] = {key[0], key[1]};
+        uint32_t* d_key = (uint32_t*)ws.buf;
+        uint32_t* d_subs = (uint32_t*)(ws.buf + 1024);
         const int64_t used = 1 + 2 * (int64_t)stats[5];
-        TRY(cudaMemcpy(d_key, k2, sizeof(k2), cudaMemcpyHostToDevice), "play_host: h2d key");
-        rc = g2048_chain_advance(d_key, rng_mode, used, d_subs, nullptr);
-        if (rc) goto done;
-        TRY(cudaMemcpy(h_key_io, d_key, sizeof(k2), cudaMemcpyDeviceToHost), "play_host: d2h key");
+        TRY(cudaMemcpyAsync(d_key, key, sizeof(key), cudaMemcpyHostToDevice, st), "play_host: h2d key");
+        rc = g2048_chain_advance(d_key, rng_mode, used, d_subs, st);
+        if (rc) return rc;
+        TRY(cudaMemcpyAsync(h_key_io, d_key, sizeof(key), cudaMemcpyDeviceToHost, st), "play_host: d2h key");
+        TRY(cudaStreamSynchronize(st), "play_host: sync");
     }
-done:
 #undef TRY
-    cudaFree(d_key); cudaFree(d_subs); cudaFree(d_work); cudaFree(d_stats);
-    cudaFree(d_boards); cudaFree(d_len); cudaFree(d_score);
-    if (st) cudaStreamDestroy(st);
     return rc;
 }
 

@@ -19,58 +19,11 @@
 #include "g2048_board.cuh"
 #include "g2048_common.cuh"
 #include "g2048_env.cuh"
+#include "g2048_play.cuh"
 
 namespace g2048 {
 
 constexpr int PLAY2_THREADS = 256;
-
-// The blocks of one key that both bits4() and split2() are made of.
-template <int MODE>
-struct KeyBlocks {
-    uint32_t bits[4];  // random_bits(key, (4,))
-    Key child[2];      // split(key, 2)
-};
-
-template <int MODE>
-__device__ __forceinline__ KeyBlocks<MODE> key_blocks(Key k) {
-    KeyBlocks<MODE> o;
-    if (MODE == G2048_RNG_PARTITIONABLE) {
-        Key y[4];
-#pragma unroll
-        for (uint32_t i = 0; i < 4; ++i) {
-            y[i] = threefry2x32(k, 0u, i);
-            o.bits[i] = y[i].a ^ y[i].b;
-        }
-        o.child[0] = y[0];
-        o.child[1] = y[1];
-    } else {
-        const Key y0 = threefry2x32(k, 0u, 2u);
-        const Key y1 = threefry2x32(k, 1u, 3u);
-        o.bits[0] = y0.a;
-        o.bits[1] = y1.a;
-        o.bits[2] = y0.b;
-        o.bits[3] = y1.b;
-        o.child[0] = Key{y0.a, y1.a};
-        o.child[1] = Key{y0.b, y1.b};
-    }
-    return o;
-}
-
-__device__ __forceinline__ int argmax_bits_legal(const uint32_t bits[4], uint32_t legal) {
-    const uint32_t allowed = (legal & 15u) ? (legal & 15u) : 15u;
-    int best = 0, best_v = -1;
-#pragma unroll
-    for (int i = 0; i < 4; ++i) {
-        const int v = ((allowed >> i) & 1u) ? (int)(bits[i] >> 9) : -1;
-        if (v > best_v) {
-            best_v = v;
-            best = i;
-        }
-    }
-    return best;
-}
-
-enum : uint32_t { PHASE_INIT0 = 0, PHASE_INIT1 = 1, PHASE_PLAY = 2, PHASE_NONE = 3 };
 
 template <int MODE, int POLICY>
 __global__ void __launch_bounds__(PLAY2_THREADS)
@@ -225,9 +178,24 @@ static int launch_play2(const uint32_t* d_subs, int64_t n_subs, int64_t batch_gl
 
 using namespace g2048;
 
+// Batches of at least this many envs go to the table kernel (g2048_play3.cu), whose per-CTA cost of
+// copying 192 KiB of tables into shared memory needs a long-running launch to amortise.
+constexpr int64_t PLAY_TABLES_MIN_ENVS = 32768;
+
 extern "C" int g2048_play(int policy, const uint32_t* d_subs, int64_t n_subs, int64_t batch_global, int64_t env_lo,
                           int64_t n, int rng_mode, uint64_t* d_work, uint64_t* d_final_boards, uint32_t* d_lengths,
                           uint32_t* d_scores, uint64_t* d_stats, void* stream) {
+    if (n >= PLAY_TABLES_MIN_ENVS)
+        return g2048_play_tables(policy, d_subs, n_subs, batch_global, env_lo, n, rng_mode, d_work, d_final_boards,
+                                 d_lengths, d_scores, d_stats, stream);
+    return g2048_play_swar(policy, d_subs, n_subs, batch_global, env_lo, n, rng_mode, d_work, d_final_boards,
+                           d_lengths, d_scores, d_stats, stream);
+}
+
+// SWAR kernel entry (no tables, any batch size): same arguments and results as g2048_play.
+extern "C" int g2048_play_swar(int policy, const uint32_t* d_subs, int64_t n_subs, int64_t batch_global,
+                               int64_t env_lo, int64_t n, int rng_mode, uint64_t* d_work, uint64_t* d_final_boards,
+                               uint32_t* d_lengths, uint32_t* d_scores, uint64_t* d_stats, void* stream) {
     G2048_REQUIRE(policy == G2048_POLICY_RANDOM || policy == G2048_POLICY_DRUL, "play: policy");
     G2048_REQUIRE(rng_mode == G2048_RNG_ORIGINAL || rng_mode == G2048_RNG_PARTITIONABLE, "play: rng_mode");
     G2048_REQUIRE(batch_global > 0 && batch_global <= 0x7FFFFFFFll && env_lo >= 0 && n >= 0 && env_lo + n <= batch_global,

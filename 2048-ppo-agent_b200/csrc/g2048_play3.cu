@@ -1,0 +1,314 @@
+// Persistent play-to-termination kernel, third generation: row tables in shared memory.
+//
+// ncu on the SWAR kernel (g2048_play.cu): ALU pipe 95 % busy, ~870 ALU instructions per env-step of
+// which only 400 are Threefry (the ROTATE and XOR of each round; the ADD goes to the FMA pipe) -- the
+// rest is board logic on 64-bit words, where every shift costs two ALU instructions.  This kernel
+// moves that logic off the ALU pipe:
+//   * the slide/merge of a row is ONE 16-bit load from a 65 536-entry table held in shared memory
+//     (128 KiB, built once per process, copied per CTA), as BASELINE.json's north_star suggests;
+//   * the exact legal-action mask is 8 byte loads from a second table (64 KiB): "this row can move
+//     left / right", looked up for the four rows of the board and the four rows of its transpose;
+//   * the lane keeps the board AND its transpose in registers, so a vertical move is a horizontal
+//     move on the transpose and every step pays exactly one 16-instruction transpose.
+// Shared-memory loads issue on the LSU pipe, which the kernel otherwise leaves idle.
+// 192 KiB of tables -> one CTA of 1 024 threads per SM (32 warps).  Same lane scheduling, init-as-two-
+// iterations trick, score-from-potential and results as g2048_play.cu (bit-identical; tested).
+#include "g2048_board.cuh"
+#include "g2048_common.cuh"
+#include "g2048_env.cuh"
+#include "g2048_play.cuh"
+
+namespace g2048 {
+
+constexpr int PLAY3_THREADS = 1024;
+constexpr int PLAY3_TABLE_BYTES = 65536 * 2 + 65536;
+constexpr int PLAY3_SMEM_BYTES = PLAY3_TABLE_BYTES + G2048_PLAY_STATS_WORDS * 8;
+
+__device__ uint16_t g_row_left[65536];  // row slid and merged toward nibble 0
+__device__ uint8_t g_row_flags[65536];  // bit 0: the row changes when moved toward nibble 0, bit 1: toward nibble 3
+
+__device__ __forceinline__ uint32_t row_left_scalar(uint32_t row) {
+    uint32_t tiles[4];
+    int n = 0;
+    for (int c = 0; c < 4; ++c) {
+        const uint32_t v = (row >> (4 * c)) & 15u;
+        if (v) tiles[n++] = v;
+    }
+    uint32_t out = 0;
+    int w = 0;
+    for (int j = 0; j < n; ++w) {
+        if (j + 1 < n && tiles[j] == tiles[j + 1]) {
+            out |= ((tiles[j] + 1u) & 15u) << (4 * w);  // 2^15 + 2^15 wraps; such envs are flagged by the caller
+            j += 2;
+        } else {
+            out |= tiles[j] << (4 * w);
+            j += 1;
+        }
+    }
+    return out;
+}
+
+__device__ __forceinline__ uint32_t row_mirror_scalar(uint32_t row) {
+    return ((row & 0xFu) << 12) | ((row & 0xF0u) << 4) | ((row >> 4) & 0xF0u) | ((row >> 12) & 0xFu);
+}
+
+__global__ void build_row_tables_kernel() {
+    const uint32_t row = blockIdx.x * blockDim.x + threadIdx.x;
+    if (row >= 65536u) return;
+    const uint32_t left = row_left_scalar(row);
+    const uint32_t right = row_mirror_scalar(row_left_scalar(row_mirror_scalar(row)));
+    g_row_left[row] = (uint16_t)left;
+    g_row_flags[row] = (uint8_t)((left != row ? 1u : 0u) | (right != row ? 2u : 0u));
+}
+
+template <int MODE, int POLICY>
+__global__ void __launch_bounds__(PLAY3_THREADS, 1)
+play3_kernel(const uint2* __restrict__ subs, int64_t n_subs, uint32_t batch_global, uint32_t env_lo, uint32_t n,
+             unsigned long long* __restrict__ work, u64* __restrict__ final_boards, uint32_t* __restrict__ lengths,
+             uint32_t* __restrict__ scores, unsigned long long* __restrict__ stats) {
+    extern __shared__ __align__(16) uint8_t smem_raw[];
+    const uint16_t* s_left = reinterpret_cast<const uint16_t*>(smem_raw);
+    const uint8_t* s_flags = smem_raw + 65536 * 2;
+    unsigned long long* s_stats = reinterpret_cast<unsigned long long*>(smem_raw + PLAY3_TABLE_BYTES);
+
+    {  // tables: global (L2) -> shared, 12 x 16 bytes per thread
+        const uint4* src_left = reinterpret_cast<const uint4*>(g_row_left);
+        const uint4* src_flags = reinterpret_cast<const uint4*>(g_row_flags);
+        uint4* dst = reinterpret_cast<uint4*>(smem_raw);
+        for (int i = threadIdx.x; i < 65536 * 2 / 16; i += PLAY3_THREADS) dst[i] = __ldg(&src_left[i]);
+        for (int i = threadIdx.x; i < 65536 / 16; i += PLAY3_THREADS) dst[65536 * 2 / 16 + i] = __ldg(&src_flags[i]);
+        for (int i = threadIdx.x; i < G2048_PLAY_STATS_WORDS; i += PLAY3_THREADS) s_stats[i] = 0ull;
+    }
+    __syncthreads();
+
+    const unsigned lane = threadIdx.x & 31u;
+    const uint2 init_sub = subs[0];
+    const uint32_t max_steps = (uint32_t)((n_subs - 1) / 2);
+
+    u64 board = 0ull, boardT = 0ull;  // the board and its transpose
+    uint32_t lm = 0, e = 0, t = 0, fours = 0, phase = PHASE_NONE;
+    bool seen15 = false;
+    bool exhausted = false;  // warp-uniform
+
+    uint32_t st_episodes = 0, st_cut = 0, st_ovf = 0, st_longest = 0;
+    unsigned long long st_steps = 0, st_score = 0, st_tile = 0, st_tile2 = 0;
+
+    while (true) {
+        // ---- hand the next envs of the queue to the lanes that have none --------------------------
+        const unsigned want = __ballot_sync(0xFFFFFFFFu, phase == PHASE_NONE);
+        if (want) {
+            if (!exhausted) {
+                const int cnt = __popc(want);
+                unsigned long long base = 0;
+                if (lane == 0) base = atomicAdd(work, (unsigned long long)cnt);
+                base = __shfl_sync(0xFFFFFFFFu, base, 0);
+                if (base + (unsigned long long)cnt >= (unsigned long long)n) exhausted = true;
+                if (phase == PHASE_NONE) {
+                    const unsigned long long mine = base + (unsigned long long)__popc(want & ((1u << lane) - 1u));
+                    if (mine < (unsigned long long)n) {
+                        e = (uint32_t)mine;
+                        board = 0ull;
+                        boardT = 0ull;
+                        lm = 0;
+                        t = 0;
+                        fours = 0;
+                        seen15 = false;
+                        phase = PHASE_INIT0;
+                    }
+                }
+            }
+            if (__ballot_sync(0xFFFFFFFFu, phase != PHASE_NONE) == 0u) break;
+        }
+        if (phase == PHASE_NONE) continue;  // only at the tail of the launch, when the queue is empty
+
+        // ---- keys: identical to g2048_play.cu ----------------------------------------------------------
+        const bool playing = phase == PHASE_PLAY;
+        const uint2 ss = __ldg(&subs[2 + 2 * (int64_t)t]);
+        int action;
+        Key kstep;
+        if (POLICY == G2048_POLICY_RANDOM) {
+            const uint2 sa = __ldg(&subs[1 + 2 * (int64_t)t]);
+            const Key head = playing ? Key{sa.x, sa.y} : Key{init_sub.x, init_sub.y};
+            const KeyBlocks<MODE> kb = key_blocks<MODE>(split_at<MODE>(head, batch_global, env_lo + e));
+            action = argmax_bits_legal(kb.bits, lm);
+            const Key kplay = split_at<MODE>(Key{ss.x, ss.y}, batch_global, env_lo + e);
+            const Key kinit = (phase == PHASE_INIT0) ? kb.child[0] : kb.child[1];
+            kstep = playing ? kplay : kinit;
+        } else {
+            action = act_drul(lm);
+            const Key head = playing ? Key{ss.x, ss.y} : Key{init_sub.x, init_sub.y};
+            kstep = split_at<MODE>(head, batch_global, env_lo + e);
+            if (!playing) {  // r_phase = split(init key)[phase]
+                Key c0, c1;
+                split2<MODE>(kstep, c0, c1);
+                kstep = (phase == PHASE_INIT0) ? c0 : c1;
+            }
+        }
+        Key k1, k2;
+        split2<MODE>(kstep, k1, k2);
+        const uint32_t bits_pos = bits_scalar<MODE>(k1);
+        const uint32_t bits_val = bits_scalar<MODE>(k2);
+
+        // ---- move: four table lookups on the board (Left/Right) or its transpose (Up/Down) -----------------
+        const bool vertical = (action & 1) != 0, rev = action >= 2;
+        u64 src = vertical ? boardT : board;
+        if (rev) src = mirror_rows(src);
+        const uint32_t slo = (uint32_t)src, shi = (uint32_t)(src >> 32);
+        const uint32_t m0 = s_left[slo & 0xFFFFu], m1 = s_left[slo >> 16];
+        const uint32_t m2 = s_left[shi & 0xFFFFu], m3 = s_left[shi >> 16];
+        u64 moved = ((u64)(m2 | (m3 << 16)) << 32) | (u64)(m0 | (m1 << 16));
+        if (rev) moved = mirror_rows(moved);
+        const u64 movedT = transpose_board(moved);
+        u64 nb = vertical ? movedT : moved;   // row-major board after the move
+        u64 nbT = vertical ? moved : movedT;  // its transpose
+        if (!playing) {  // the two init iterations only spawn
+            nb = board;
+            nbT = boardT;
+        }
+        // ---- spawn into both orientations -------------------------------------------------------------------
+        int cell;
+        u64 val;
+        spawn_select(nb, bits_pos, bits_val, cell, val);
+        const int cellT = ((cell & 3) << 2) | (cell >> 2);
+        board = nb | (val << (4 * cell));      // the chosen cell is empty (or, on a full board, only reachable
+        boardT = nbT | (val << (4 * cellT));   //  through illegal actions which these policies never take)
+        fours += (val == 2ull) ? 1u : 0u;
+        // ---- exact legal mask: "row can move left / right" for the 4 rows and the 4 columns -------------------
+        const uint32_t blo = (uint32_t)board, bhi = (uint32_t)(board >> 32);
+        const uint32_t tlo = (uint32_t)boardT, thi = (uint32_t)(boardT >> 32);
+        const uint32_t fb = s_flags[blo & 0xFFFFu] | s_flags[blo >> 16] | s_flags[bhi & 0xFFFFu] | s_flags[bhi >> 16];
+        const uint32_t ft = s_flags[tlo & 0xFFFFu] | s_flags[tlo >> 16] | s_flags[thi & 0xFFFFu] | s_flags[thi >> 16];
+        lm = (fb & 1u) | ((ft & 1u) << 1) | ((fb & 2u) << 1) | ((ft & 2u) << 2);  // Left, Up, Right, Down
+
+        if (!playing) {
+            phase += 1;  // INIT0 -> INIT1 -> PLAY
+            continue;
+        }
+        ++t;
+        const bool done = lm == 0u;
+        const bool cut = !done && t >= max_steps;
+        if ((t & 255u) == 0u || done || cut) seen15 |= has_max_nibble(board);
+        if (done || cut) {
+            const uint32_t score = board_potential(board) - 4u * fours;
+            if (final_boards) final_boards[e] = board;
+            if (lengths) lengths[e] = t;
+            if (scores) scores[e] = score;
+            const uint32_t me = max_exponent(board);
+            const unsigned long long tile = 1ull << me;
+            st_episodes += 1;
+            st_steps += t;
+            st_score += score;
+            st_cut += cut ? 1u : 0u;
+            st_ovf += seen15 ? 1u : 0u;
+            st_longest = max(st_longest, t);
+            st_tile += tile;
+            st_tile2 += tile * tile;
+            atomicAdd(&s_stats[16 + me], 1ull);
+            phase = PHASE_NONE;
+        }
+    }
+
+    atomicAdd(&s_stats[0], (unsigned long long)st_episodes);
+    atomicAdd(&s_stats[1], st_steps);
+    atomicAdd(&s_stats[2], st_score);
+    atomicAdd(&s_stats[3], (unsigned long long)st_cut);
+    atomicAdd(&s_stats[4], (unsigned long long)st_ovf);
+    atomicMax(&s_stats[5], (unsigned long long)st_longest);
+    atomicAdd(&s_stats[6], st_tile);
+    atomicAdd(&s_stats[7], st_tile2);
+    __syncthreads();
+    for (int i = threadIdx.x; i < G2048_PLAY_STATS_WORDS; i += blockDim.x) {
+        const unsigned long long v = s_stats[i];
+        if (v) {
+            if (i == 5) atomicMax(&stats[i], v);
+            else atomicAdd(&stats[i], v);
+        }
+    }
+}
+
+// tables are built once per device, the first time a table kernel is launched
+static int ensure_row_tables(cudaStream_t st) {
+    static bool built[64] = {false};
+    int dev = 0;
+    int rc = check_cuda(cudaGetDevice(&dev), "play: device");
+    if (rc) return rc;
+    if (dev < 0 || dev >= 64) return fail_arg("play: device index");
+    if (built[dev]) return G2048_OK;
+    build_row_tables_kernel<<<65536 / 256, 256, 0, st>>>();
+    rc = check_cuda(cudaGetLastError(), "play: build tables");
+    if (rc) return rc;
+    rc = check_cuda(cudaStreamSynchronize(st), "play: build tables");  // one-time: later launches may use other streams
+    if (rc) return rc;
+    built[dev] = true;
+    return G2048_OK;
+}
+
+__global__ void row_table_lookup_kernel(const uint16_t* __restrict__ rows, int64_t n, uint16_t* __restrict__ left,
+                                        uint8_t* __restrict__ flags) {
+    const int64_t i = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
+    if (i >= n) return;
+    left[i] = g_row_left[rows[i]];
+    flags[i] = g_row_flags[rows[i]];
+}
+
+template <int MODE, int POLICY>
+static int launch_play3(const uint32_t* d_subs, int64_t n_subs, int64_t batch_global, int64_t env_lo, int64_t n,
+                        uint64_t* d_work, uint64_t* d_final_boards, uint32_t* d_lengths, uint32_t* d_scores,
+                        uint64_t* d_stats, cudaStream_t st) {
+    int rc = ensure_row_tables(st);
+    if (rc) return rc;
+    static bool configured = false;
+    if (!configured) {
+        rc = check_cuda(cudaFuncSetAttribute(play3_kernel<MODE, POLICY>, cudaFuncAttributeMaxDynamicSharedMemorySize,
+                                             PLAY3_SMEM_BYTES), "play: shared memory attribute");
+        if (rc) return rc;
+        configured = true;
+    }
+    const int sms = sm_count();
+    if (sms <= 0) return fail_arg("play: no device");
+    int64_t grid = sms;  // one 1 024-thread CTA per SM, persistent
+    const int64_t needed = (n + PLAY3_THREADS - 1) / PLAY3_THREADS;
+    if (grid > needed) grid = needed;
+    play3_kernel<MODE, POLICY><<<(unsigned)grid, PLAY3_THREADS, PLAY3_SMEM_BYTES, st>>>(
+        (const uint2*)d_subs, n_subs, (uint32_t)batch_global, (uint32_t)env_lo, (uint32_t)n,
+        (unsigned long long*)d_work, (u64*)d_final_boards, d_lengths, d_scores, (unsigned long long*)d_stats);
+    return check_cuda(cudaGetLastError(), "play");
+}
+
+}  // namespace g2048
+
+using namespace g2048;
+
+// Test hook: the table entries of the given 16-bit rows (row = four nibbles, nibble 0 = column 0).
+extern "C" int g2048_row_table_lookup(const uint16_t* d_rows, int64_t n, uint16_t* d_left, uint8_t* d_flags,
+                                      void* stream) {
+    G2048_REQUIRE(n >= 0 && (n == 0 || (d_rows && d_left && d_flags)), "row_table_lookup");
+    if (n == 0) return G2048_OK;
+    int rc = ensure_row_tables((cudaStream_t)stream);
+    if (rc) return rc;
+    row_table_lookup_kernel<<<blocks_for(n, 256), 256, 0, (cudaStream_t)stream>>>(d_rows, n, d_left, d_flags);
+    G2048_CHECK_LAUNCH("row_table_lookup");
+    return G2048_OK;
+}
+
+// Table kernel entry: same arguments and results as g2048_play.  g2048_play itself dispatches here
+// for batches large enough to amortise the 192 KiB table copy per CTA.
+extern "C" int g2048_play_tables(int policy, const uint32_t* d_subs, int64_t n_subs, int64_t batch_global,
+                                 int64_t env_lo, int64_t n, int rng_mode, uint64_t* d_work, uint64_t* d_final_boards,
+                                 uint32_t* d_lengths, uint32_t* d_scores, uint64_t* d_stats, void* stream) {
+    G2048_REQUIRE(policy == G2048_POLICY_RANDOM || policy == G2048_POLICY_DRUL, "play: policy");
+    G2048_REQUIRE(rng_mode == G2048_RNG_ORIGINAL || rng_mode == G2048_RNG_PARTITIONABLE, "play: rng_mode");
+    G2048_REQUIRE(batch_global > 0 && batch_global <= 0x7FFFFFFFll && env_lo >= 0 && n >= 0 && env_lo + n <= batch_global,
+                  "play: batch");
+    G2048_REQUIRE(n_subs >= 3 && d_subs && d_work && d_stats, "play: pointers");
+    if (n == 0) return G2048_OK;
+    cudaStream_t st = (cudaStream_t)stream;
+#define ARGS d_subs, n_subs, batch_global, env_lo, n, d_work, d_final_boards, d_lengths, d_scores, d_stats, st
+    if (policy == G2048_POLICY_RANDOM) {
+        if (rng_mode == G2048_RNG_PARTITIONABLE) return launch_play3<G2048_RNG_PARTITIONABLE, G2048_POLICY_RANDOM>(ARGS);
+        return launch_play3<G2048_RNG_ORIGINAL, G2048_POLICY_RANDOM>(ARGS);
+    }
+    if (rng_mode == G2048_RNG_PARTITIONABLE) return launch_play3<G2048_RNG_PARTITIONABLE, G2048_POLICY_DRUL>(ARGS);
+    return launch_play3<G2048_RNG_ORIGINAL, G2048_POLICY_DRUL>(ARGS);
+#undef ARGS
+}

@@ -54,6 +54,9 @@ _SIGNATURES = {
     "g2048_env_step_draws": (_INT, [_P, _P, _P, _P, _P, _I64, _P, _P]),
     "g2048_act": (_INT, [_INT, _P, _P, _I64, _I64, _I64, _INT, _P, _P, _P]),
     "g2048_play": (_INT, [_INT, _P, _I64, _I64, _I64, _I64, _INT, _P, _P, _P, _P, _P, _P]),
+    "g2048_play_tables": (_INT, [_INT, _P, _I64, _I64, _I64, _I64, _INT, _P, _P, _P, _P, _P, _P]),
+    "g2048_play_swar": (_INT, [_INT, _P, _I64, _I64, _I64, _I64, _INT, _P, _P, _P, _P, _P, _P]),
+    "g2048_row_table_lookup": (_INT, [_P, _I64, _P, _P, _P]),
     "g2048_play_v1": (_INT, [_INT, _P, _I64, _I64, _I64, _I64, _INT, _P, _P, _P, _P, _P, _P]),
     "g2048_play_host": (_INT, [_INT, _U64, _P, _I64, _I64, _I64, _INT, _P, _P, _P, _P]),
     "g2048_rollout_steps": (_INT, [_INT, _P, _P, _P, _I64, _I64, _I64, _I64, _I64, _INT, _P, _P, _P, _P, _P, _P]),

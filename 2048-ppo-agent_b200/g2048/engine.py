@@ -151,6 +151,15 @@ def play(policy: int, subs: torch.Tensor, batch_global: int, env_lo: int, n: int
     return dict(final_boards=boards, lengths=lengths, scores=scores, stats=stats)
 
 
+def row_table_lookup(rows: torch.Tensor):
+    """Test hook: table entries (row moved left, move flags) of int16 rows."""
+    n = rows.shape[0]
+    left = torch.empty(n, dtype=torch.int16, device=rows.device)
+    flags = torch.empty(n, dtype=torch.uint8, device=rows.device)
+    call("g2048_row_table_lookup", ptr(rows), n, ptr(left), ptr(flags), stream_ptr())
+    return left, flags
+
+
 def play_stats_dict(stats: torch.Tensor) -> dict:
     s = stats.detach().cpu().numpy().astype(np.uint64)
     out = {k: int(s[i]) for i, k in enumerate(STAT_NAMES)}

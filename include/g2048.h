@@ -121,6 +121,20 @@ int g2048_play(int policy, const uint32_t* d_subs, int64_t n_subs, int64_t batch
                int rng_mode, uint64_t* d_work, uint64_t* d_final_boards, uint32_t* d_lengths, uint32_t* d_scores,
                uint64_t* d_stats, void* stream);
 
+/* The two kernels behind g2048_play, each with the same arguments and results: `_tables` keeps the
+ * row move / legality tables in shared memory (192 KiB per CTA; used for n >= 32768), `_swar` does
+ * the board logic with SWAR arithmetic in registers (no tables; small batches). */
+int g2048_play_tables(int policy, const uint32_t* d_subs, int64_t n_subs, int64_t batch_global, int64_t env_lo,
+                      int64_t n, int rng_mode, uint64_t* d_work, uint64_t* d_final_boards, uint32_t* d_lengths,
+                      uint32_t* d_scores, uint64_t* d_stats, void* stream);
+int g2048_play_swar(int policy, const uint32_t* d_subs, int64_t n_subs, int64_t batch_global, int64_t env_lo,
+                    int64_t n, int rng_mode, uint64_t* d_work, uint64_t* d_final_boards, uint32_t* d_lengths,
+                    uint32_t* d_scores, uint64_t* d_stats, void* stream);
+
+/* Test hook for the shared-memory tables of g2048_play_tables: for each 16-bit row (four nibbles, nibble 0 =
+ * column 0) the row slid/merged toward column 0 and the flags (bit 0: moves left, bit 1: moves right). */
+int g2048_row_table_lookup(const uint16_t* d_rows, int64_t n, uint16_t* d_left, uint8_t* d_flags, void* stream);
+
 /* First-generation play kernel (lanes park until six are free, per-step reward loop): identical
  * arguments and results; kept so that the current kernel can be A/B-timed against it. */
 int g2048_play_v1(int policy, const uint32_t* d_subs, int64_t n_subs, int64_t batch_global, int64_t env_lo, int64_t n,

@@ -276,12 +276,13 @@ def test_evaluate_logits_matches_reference_fixture(E, golden_ppo):
 
 
 # ----------------------------------------------------------------------------------------- fused loops
+@pytest.mark.parametrize("entry", ["g2048_play", "g2048_play_tables"])
 @pytest.mark.parametrize("policy,name", [(1, "drul"), (0, "random")])
-def test_play_reproduces_golden_svg(E, golden_svg, golden_hist, policy, name):
+def test_play_reproduces_golden_svg(E, golden_svg, golden_hist, policy, name, entry):
     want = golden_hist["svg_seed0_batch4_original_mode"][name]
     key = u32([0, 0])
     subs = E.chain_advance(key, 0, 1 + 2 * 1024)
-    out = E.play(policy, subs, 4, 0, 4, 0)
+    out = E.play(policy, subs, 4, 0, 4, 0, entry=entry)
     assert out["lengths"].cpu().tolist() == want["lengths"]
     assert out["scores"].cpu().tolist() == want["scores"]
     np.testing.assert_array_equal(E.boards_numpy(out["final_boards"]), golden_svg[f"{name}_boards"][-1])
@@ -303,15 +304,19 @@ def test_play_reproduces_png_histograms(E, golden_hist, policy, name):
     assert got == golden_hist[name]
 
 
+PLAY_ENTRIES = ["g2048_play", "g2048_play_tables", "g2048_play_swar", "g2048_play_v1"]
+
+
+@pytest.mark.parametrize("entry", PLAY_ENTRIES)
 @pytest.mark.parametrize("mode", MODES)
 @pytest.mark.parametrize("policy", [0, 1])
-def test_play_matches_oracle_and_is_shard_invariant(E, mode, policy):
-    n = 20000
+def test_play_matches_oracle_and_is_shard_invariant(E, mode, policy, entry):
+    n = 40000 if entry == "g2048_play" else 20000  # the dispatcher switches to the table kernel at 32768 envs
     seed = 1234
     want = CO.play(seed, n, policy, mode, max_steps=2048)
     key = u32(list(E.key_words(seed)))
     subs = E.chain_advance(key, mode, 1 + 2 * 2048)
-    out = E.play(policy, subs, n, 0, n, mode)
+    out = E.play(policy, subs, n, 0, n, mode, entry=entry)
     np.testing.assert_array_equal(E.boards_numpy(out["final_boards"]), want["final_boards"])
     np.testing.assert_array_equal(out["lengths"].cpu().numpy(), want["lengths"])
     np.testing.assert_array_equal(out["scores"].cpu().numpy(), want["scores"])
@@ -321,7 +326,7 @@ def test_play_matches_oracle_and_is_shard_invariant(E, mode, policy):
     assert st["tile_sum"] == int(tiles.sum()) and st["tile_sq_sum"] == int((tiles**2).sum())
     # shard [lo, lo+m) of the same global batch == the slice (what each GPU computes)
     lo, m = 7001, 5000
-    part = E.play(policy, subs, n, lo, m, mode)
+    part = E.play(policy, subs, n, lo, m, mode, entry=entry)
     np.testing.assert_array_equal(E.boards_numpy(part["final_boards"]), want["final_boards"][lo : lo + m])
     np.testing.assert_array_equal(part["lengths"].cpu().numpy(), want["lengths"][lo : lo + m])
 
@@ -339,11 +344,30 @@ def test_play_host_entry_point(E, golden_hist):
     np.testing.assert_array_equal(out["lengths"], ref["lengths"])
 
 
-def test_play_reports_cut_short(E):
+@pytest.mark.parametrize("entry", PLAY_ENTRIES)
+def test_play_reports_cut_short(E, entry):
     key = u32([0, 1])
     subs = E.chain_advance(key, 1, 1 + 2 * 20)  # only 20 loop steps of keys
-    st = E.play_stats_dict(E.play(0, subs, 64, 0, 64, 1)["stats"])
+    st = E.play_stats_dict(E.play(0, subs, 64, 0, 64, 1, entry=entry)["stats"])
     assert st["cut_short"] == 64 and st["longest"] == 20
+
+
+def test_row_tables_match_the_oracle_for_every_row(E):
+    """All 65 536 entries of the shared-memory tables behind g2048_play_tables against the oracle's move."""
+    rows = np.arange(65536, dtype=np.uint32)
+    cells = np.stack([(rows >> (4 * c)) & 15 for c in range(4)], axis=1).astype(np.int64)
+    left, flags = E.row_table_lookup(dev(rows.astype(np.uint16).view(np.int16)))
+    left = left.cpu().numpy().view(np.uint16).astype(np.uint32)
+    flags = flags.cpu().numpy()
+    boards = np.zeros((65536, 16), np.int64)
+    boards[:, :4] = cells
+    ok = cells.max(axis=1) < 15  # 2^15 + 2^15 does not fit a nibble: those envs are flagged, not represented
+    want_l, _ = O.move(boards[ok], np.zeros(ok.sum(), np.int64))
+    want_r, _ = O.move(boards[ok], np.full(ok.sum(), 2))
+    got_l = np.stack([(left[ok] >> (4 * c)) & 15 for c in range(4)], axis=1)
+    np.testing.assert_array_equal(got_l, want_l[:, :4])
+    np.testing.assert_array_equal(flags[ok] & 1, (want_l[:, :4] != cells[ok]).any(axis=1))
+    np.testing.assert_array_equal((flags[ok] >> 1) & 1, (want_r[:, :4] != cells[ok]).any(axis=1))
 
 
 @pytest.mark.parametrize("mode", MODES)

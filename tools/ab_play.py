@@ -21,7 +21,7 @@ for mode in (1, 0):
     for policy, name in ((0, "random"), (1, "drul")):
         n = 1 << 21
         res = {}
-        for entry in ("g2048_play_v1", "g2048_play"):
+        for entry in ("g2048_play_v1", "g2048_play_swar", "g2048_play_tables"):
             out = {}
             def run():
                 out.update(E.play(policy, subs, n, 0, n, mode, per_env=True, entry=entry))
@@ -29,7 +29,7 @@ for mode in (1, 0):
             st = E.play_stats_dict(out["stats"])
             res[entry] = out
             print(f"mode {mode} {name:6s} {entry:14s} n={n}: {st['env_steps'] / t / 1e9:7.3f} G env-steps/s ({t*1e3:.2f} ms) longest {st['longest']} ovf {st['overflowed']}")
-        a, b = res["g2048_play_v1"], res["g2048_play"]
+        a, b = res["g2048_play_swar"], res["g2048_play_tables"]
         same = all(torch.equal(a[k], b[k]) for k in ("final_boards", "lengths", "scores"))
         sa, sb = a["stats"].clone(), b["stats"].clone()
         print("   identical per-env results:", same, " identical stats:", torch.equal(sa, sb))
