@@ -121,6 +121,7 @@ def oracle_play_rate(seed: int, batch_global: int, n_sample: int, policy: int, m
     """Times the oracle's C port (OpenMP, all host threads) on envs [0, n_sample) of the batch."""
     from oracle import c_oracle as CO
 
+    CO.set_num_threads(os.cpu_count() or 1)  # torchrun exports OMP_NUM_THREADS=1; the baseline uses every host core
     threads = CO.num_threads()
     total_steps, t0, reps = 0, time.perf_counter(), 0
     out = None
@@ -143,6 +144,7 @@ def run_reference(args, rank: int):
     n_sample = min(REF_SAMPLE_ENVS, batch_global)
     from oracle import c_oracle as CO
 
+    CO.set_num_threads(os.cpu_count() or 1)  # torchrun exports OMP_NUM_THREADS=1; the reference arm uses every host core
     times, steps_done = [], []
     for i in range(args.warmup + args.steps):
         t0 = time.perf_counter()

@@ -8,7 +8,7 @@ from g2048 import engine as E
 
 dev = "cuda"
 mode = 1
-n = 1 << 20
+n = 1 << 21
 key = E.words_tensor([0, 2048], dev)
 subs = E.chain_advance(key, mode, 1 + 2 * 2048)
 for policy in (0, 1):
