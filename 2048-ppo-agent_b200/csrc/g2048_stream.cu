@@ -30,7 +30,8 @@ template <> struct ObsOne<uint8_t> { static __device__ uint8_t one() { return 1;
 
 template <typename T>
 __global__ void __launch_bounds__(OBS_THREADS)
-expand_obs_tma_kernel(const u64* __restrict__ boards, int64_t n, T* __restrict__ out, int64_t rows, int64_t n_cols) {
+expand_obs_tma_kernel(const u64* __restrict__ boards, int64_t n, T* __restrict__ out, int64_t rows, int64_t n_cols,
+                      const int64_t* __restrict__ indices) {
     constexpr int G = OBS_IMAGE_BYTES / (496 * (int)sizeof(T));  // boards per image
     constexpr int CELLS = 16 * G;
     constexpr int PER_LANE = (CELLS + 31) / 32;
@@ -75,6 +76,7 @@ expand_obs_tma_kernel(const u64* __restrict__ boards, int64_t n, T* __restrict__
                             const int64_t col = src / rows;
                             src = (src - col * rows) * n_cols + col;
                         }
+                        if (indices) src = __ldg(&indices[src]);  // gather: out[i] = onehot(boards[indices[i]])
                         const u64 b = __ldg(&boards[src]);
                         pos = g * 496 + 31 * cell + (int)((b >> (4 * cell)) & 15ull);
                         buf[pos] = ObsOne<T>::one();
@@ -100,8 +102,8 @@ using namespace g2048;
 
 static inline bool aligned16(const void* p) { return ((uintptr_t)p & 15u) == 0; }
 
-extern "C" int g2048_expand_obs(const uint64_t* d_boards, int64_t n, int dtype, void* d_out, int64_t rows,
-                                int64_t n_cols, void* stream) {
+static int launch_expand_obs(const uint64_t* d_boards, int64_t n, int dtype, void* d_out, int64_t rows, int64_t n_cols,
+                             const int64_t* d_indices, void* stream) {
     G2048_REQUIRE(n >= 0 && rows >= 0 && (rows == 0 || (n_cols > 0 && rows * n_cols == n)), "expand_obs: shape");
     if (n == 0) return G2048_OK;
     G2048_REQUIRE(d_boards && d_out && aligned16(d_out), "expand_obs: pointers (out must be 16-byte aligned)");
@@ -123,18 +125,67 @@ extern "C" int g2048_expand_obs(const uint64_t* d_boards, int64_t n, int dtype, 
     };
     switch (dtype) {
         case G2048_OBS_F32:
-            expand_obs_tma_kernel<float><<<grid_for(n), OBS_THREADS, OBS_SMEM_BYTES, st>>>((const u64*)d_boards, n, (float*)d_out, rows, n_cols);
+            expand_obs_tma_kernel<float><<<grid_for(n), OBS_THREADS, OBS_SMEM_BYTES, st>>>((const u64*)d_boards, n, (float*)d_out, rows, n_cols, d_indices);
             break;
         case G2048_OBS_BF16:
             expand_obs_tma_kernel<__nv_bfloat16><<<grid_for((n + 1) / 2), OBS_THREADS, OBS_SMEM_BYTES, st>>>(
-                (const u64*)d_boards, n, (__nv_bfloat16*)d_out, rows, n_cols);
+                (const u64*)d_boards, n, (__nv_bfloat16*)d_out, rows, n_cols, d_indices);
             break;
         case G2048_OBS_BOOL:
-            expand_obs_tma_kernel<uint8_t><<<grid_for((n + 3) / 4), OBS_THREADS, OBS_SMEM_BYTES, st>>>((const u64*)d_boards, n, (uint8_t*)d_out, rows, n_cols);
+            expand_obs_tma_kernel<uint8_t><<<grid_for((n + 3) / 4), OBS_THREADS, OBS_SMEM_BYTES, st>>>((const u64*)d_boards, n, (uint8_t*)d_out, rows, n_cols, d_indices);
             break;
         default:
             return fail_arg("expand_obs: dtype");
     }
     G2048_CHECK_LAUNCH("expand_obs");
+    return G2048_OK;
+}
+
+extern "C" int g2048_expand_obs(const uint64_t* d_boards, int64_t n, int dtype, void* d_out, int64_t rows,
+                                int64_t n_cols, void* stream) {
+    return launch_expand_obs(d_boards, n, dtype, d_out, rows, n_cols, nullptr, stream);
+}
+
+// ------------------------------------------------------------------------------------------------
+// minibatch gather (replaces PPODataset.__getitem__ + DataLoader collation,
+// src/ppo/data_loader.py:132-166,217-223, on the packed device buffer)
+// ------------------------------------------------------------------------------------------------
+namespace g2048 {
+__global__ void __launch_bounds__(256)
+gather_scalars_kernel(const int64_t* __restrict__ idx, int64_t m, const uint8_t* __restrict__ meta,
+                      const float* __restrict__ log_probs, const float* __restrict__ values,
+                      const float* __restrict__ adv, const float* __restrict__ ret, int64_t* __restrict__ o_actions,
+                      uchar4* __restrict__ o_masks, float* __restrict__ o_log_probs, float* __restrict__ o_values,
+                      float* __restrict__ o_adv, float* __restrict__ o_ret) {
+    const int64_t i = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
+    if (i >= m) return;
+    const int64_t s = __ldg(&idx[i]);
+    const uint32_t mt = meta ? meta[s] : 0u;
+    if (o_actions) o_actions[i] = (int64_t)(mt & 3u);
+    if (o_masks) o_masks[i] = make_uchar4((mt >> 2) & 1u, (mt >> 3) & 1u, (mt >> 4) & 1u, (mt >> 5) & 1u);
+    if (o_log_probs && log_probs) o_log_probs[i] = log_probs[s];
+    if (o_values && values) o_values[i] = values[s];
+    if (o_adv && adv) o_adv[i] = adv[s];
+    if (o_ret && ret) o_ret[i] = ret[s];
+}
+}  // namespace g2048
+
+extern "C" int g2048_gather_minibatch(const int64_t* d_indices, int64_t m, const uint64_t* d_boards,
+                                      const uint8_t* d_meta, const float* d_log_probs, const float* d_values,
+                                      const float* d_adv, const float* d_ret, int obs_dtype, void* d_obs,
+                                      int64_t* d_actions, uint8_t* d_masks, float* d_old_log_probs, float* d_old_values,
+                                      float* d_out_adv, float* d_out_ret, void* stream) {
+    G2048_REQUIRE(m >= 0, "gather_minibatch: m");
+    if (m == 0) return G2048_OK;
+    G2048_REQUIRE(d_indices, "gather_minibatch: indices");
+    if (d_obs) {
+        G2048_REQUIRE(d_boards, "gather_minibatch: boards");
+        int rc = launch_expand_obs(d_boards, m, obs_dtype, d_obs, 0, 0, d_indices, stream);
+        if (rc) return rc;
+    }
+    g2048::gather_scalars_kernel<<<blocks_for(m, 256), 256, 0, (cudaStream_t)stream>>>(
+        d_indices, m, d_meta, d_log_probs, d_values, d_adv, d_ret, d_actions, (uchar4*)d_masks, d_old_log_probs,
+        d_old_values, d_out_adv, d_out_ret);
+    G2048_CHECK_LAUNCH("gather_minibatch");
     return G2048_OK;
 }

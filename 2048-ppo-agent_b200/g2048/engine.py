@@ -306,6 +306,28 @@ def unpack_flat_meta(meta: torch.Tensor):
     return actions, masks, term
 
 
+def gather_minibatch(indices: torch.Tensor, packed: dict, adv: torch.Tensor | None, ret: torch.Tensor | None,
+                     obs_dtype=torch.float32) -> dict:
+    """Minibatch `indices` (int64, device) of a flat packed buffer (RolloutBuffer.get_packed()) as the
+    tensors a PPO update consumes; one observation kernel + one scalar-gather kernel."""
+    m = indices.shape[0]
+    dev = indices.device
+    out = dict(
+        observations=torch.empty((m, 16, 31), dtype=obs_dtype, device=dev),
+        actions=torch.empty(m, dtype=torch.int64, device=dev),
+        action_masks=torch.empty((m, 4), dtype=torch.bool, device=dev),
+        log_probs=torch.empty(m, dtype=torch.float32, device=dev),
+        values=torch.empty(m, dtype=torch.float32, device=dev),
+        advantages=torch.empty(m, dtype=torch.float32, device=dev) if adv is not None else None,
+        returns=torch.empty(m, dtype=torch.float32, device=dev) if ret is not None else None,
+    )
+    call("g2048_gather_minibatch", ptr(indices), m, ptr(packed["boards"]), ptr(packed["meta"]), ptr(packed["log_probs"]),
+         ptr(packed["values"]), ptr(adv), ptr(ret), _OBS_DTYPES[obs_dtype], ptr(out["observations"]), ptr(out["actions"]),
+         ptr(out["action_masks"]), ptr(out["log_probs"]), ptr(out["values"]), ptr(out["advantages"]), ptr(out["returns"]),
+         stream_ptr())
+    return out
+
+
 # ------------------------------------------------------------------------------------------- GAE
 def gae_flat(rewards, values, dones, gamma: float, lambda_gae: float, want_moments: bool = True,
              entry: str = "g2048_gae_flat"):

@@ -46,6 +46,72 @@ def meta_to_dones(meta: torch.Tensor) -> torch.Tensor:
     return term.view(torch.uint8)
 
 
+class DevicePPOBatches:
+    """On-device minibatch pipeline over the packed buffer.
+
+    Replaces ``PPODataset`` + ``DataLoader`` (data_loader.py:8-223) for the engine's own buffer format:
+    GAE and normalisation run once on the device (``compute_gae``), every minibatch is produced by
+    ``g2048_gather_minibatch`` -- the one-hot float observations exist only for the ``batch_size`` samples
+    of the current step (the reference materialises 1 984 B per stored step up front).  The random subset
+    per epoch (``max_samples_per_epoch`` / ``shuffle_on_reset``, :73-101) and the batch shuffle follow the
+    reference's semantics; batches are dicts of DEVICE tensors with the item keys of ``PPODataset``
+    (``actions`` are int64 indices -- the trainer's ``argmax`` of the one-hot, ppo_trainer.py:381).
+    """
+
+    def __init__(self, packed: dict, gamma: float = 0.99, lambda_gae: float = 0.95, batch_size: int = 32,
+                 shuffle: bool = True, drop_last: bool = True, max_samples_per_epoch: int = None,
+                 shuffle_on_reset: bool = False, obs_dtype=torch.float32, generator: torch.Generator = None,
+                 group=None):
+        self.packed = packed
+        self.batch_size = batch_size
+        self.shuffle = shuffle
+        self.drop_last = drop_last
+        self.max_samples_per_epoch = max_samples_per_epoch
+        self.shuffle_on_reset = shuffle_on_reset
+        self.obs_dtype = obs_dtype
+        self.generator = generator
+        self.device = packed["rewards"].device
+        self.total_length = packed["rewards"].shape[0]
+        self.dones = meta_to_dones(packed["meta"]) if self.total_length else packed["meta"]
+        if self.total_length:
+            self.advantages, self.returns = compute_gae(packed["rewards"], packed["values"], self.dones, gamma,
+                                                        lambda_gae, normalize=True, group=group)
+        else:
+            self.advantages = self.returns = packed["rewards"]
+        if max_samples_per_epoch is None or max_samples_per_epoch >= self.total_length:
+            self.length = self.total_length
+            self.active_indices = None
+        else:
+            self.length = max_samples_per_epoch
+            self.active_indices = self._sample_indices()
+
+    def _randperm(self, n: int) -> torch.Tensor:
+        return torch.randperm(n, device=self.device, generator=self.generator)
+
+    def _sample_indices(self) -> torch.Tensor:
+        return self._randperm(self.total_length)[: self.length]
+
+    def reset_epoch(self):
+        if self.shuffle_on_reset and self.active_indices is not None:
+            self.active_indices = self._sample_indices()
+
+    def __len__(self) -> int:
+        if self.drop_last:
+            return self.length // self.batch_size
+        return (self.length + self.batch_size - 1) // self.batch_size
+
+    def batch(self, indices: torch.Tensor) -> Dict[str, torch.Tensor]:
+        """The minibatch of the given buffer positions (int64 device tensor)."""
+        return E.gather_minibatch(indices.contiguous(), self.packed, self.advantages, self.returns, self.obs_dtype)
+
+    def __iter__(self):
+        order = self._randperm(self.length) if self.shuffle else torch.arange(self.length, device=self.device)
+        if self.active_indices is not None:
+            order = self.active_indices[order]
+        for b in range(len(self)):
+            yield self.batch(order[b * self.batch_size: (b + 1) * self.batch_size])
+
+
 class PPODataset(Dataset):
     """Dataset over RolloutBuffer data with GAE advantages and returns (data_loader.py:8-166)."""
 

@@ -321,7 +321,10 @@ def main():
     achieved = ALG_INSTR[args.policy] * k_steps / k_time / 1e12
     roofline = {
         "kernel": "play_kernel (g2048_play)", "bound": "int_issue", "achieved": achieved, "peak": int_peak,
-        "unit": "Tinstr/s", "frac": achieved / int_peak, "traffic": None,
+        "unit": "Tinstr/s", "frac": achieved / int_peak,
+        # dram__bytes_read.sum + dram__bytes_write.sum of one play3_kernel launch (profiles/r01_play_tables_kernel.csv):
+        # the 192 KiB of tables per CTA come from L2, per-episode results are not written in this leg
+        "traffic": 229632,
         "note": (f"algorithmic {ALG_INSTR[args.policy]} int instr per env-step (SURVEY 8d) x {k_steps} env-steps per launch / "
                  f"{k_time * 1e3:.2f} ms; peak = live probe of the ADD/SHF/LOP3 Threefry mix on this GPU (of measured); "
                  "the kernel keeps env state in registers, so HBM traffic is ~16 B per episode and not the bound"),
@@ -424,6 +427,18 @@ def secondary_measurements(E, N, torch, dev, flush_buf) -> dict:
     t = timed(lambda: N.call("g2048_expand_obs", N.ptr(boards), n_b, N.OBS_F32, N.ptr(out_f32), 0, 0, N.stream_ptr()))
     add("expand_obs_tma_kernel<float>", n_b * (8 + 1984), t, "2^20 boards -> (n,16,31) f32; 8 B read + 1984 B written per board; bulk-copy (UBLKCP) stores")
     del out_f32
+
+    # minibatch gather: 65536 random samples of a 2^22-step packed buffer -> float32 observations etc.
+    n_buf, m = 1 << 22, 1 << 16
+    packed = dict(boards=torch.randint(0, 1 << 62, (n_buf,), dtype=torch.int64, device=dev),
+                  meta=torch.randint(0, 127, (n_buf,), dtype=torch.uint8, device=dev),
+                  log_probs=torch.rand(n_buf, device=dev), values=torch.rand(n_buf, device=dev))
+    g_adv, g_ret = torch.rand(n_buf, device=dev), torch.rand(n_buf, device=dev)
+    idx = torch.randperm(n_buf, device=dev)[:m].contiguous()
+    t = timed(lambda: E.gather_minibatch(idx, packed, g_adv, g_ret))
+    add("gather_minibatch (expand_obs_tma<float> + gather_scalars)", m * (8 + 8 + 1 + 16 + 1984 + 8 + 4 + 16), t,
+        "65536 random samples: 33 B gathered + 2012 B written per sample; includes the output allocations")
+    del packed, g_adv, g_ret, idx
 
     # GAE on a flat buffer: C4-sized (2^26 steps), episodes ~300 steps
     n_g = 1 << 26

@@ -337,6 +337,44 @@ def test_compute_gae_on_a_real_packed_buffer(G):
     np.testing.assert_allclose(ret_n.cpu().numpy(), O.normalize(wr), rtol=1e-5, atol=1e-6)
 
 
+def test_device_minibatches_equal_the_reference_format_dataset(G):
+    """DevicePPOBatches (packed buffer, gather kernel) vs PPODataset over get_buffer_data() of the same buffer."""
+    ro = G.BatchRunner(21, G.act_randomly).run_packed_batch(96)
+    rb = G.RolloutBuffer(31, 16, 4)
+    rb.store_packed(ro)
+    packed = rb.get_packed()
+    packed["values"].copy_(torch.randn_like(packed["values"]))
+    ds = G.PPODataset(rb.get_buffer_data(), gamma=0.99, lambda_gae=0.95)
+    dl = G.DevicePPOBatches(packed, gamma=0.99, lambda_gae=0.95, batch_size=256, shuffle=True,
+                            generator=torch.Generator(device="cuda").manual_seed(3))
+    n = rb.buffer_size
+    assert len(dl) == n // 256 and dl.total_length == n == len(ds)
+    np.testing.assert_allclose(dl.advantages.cpu().numpy(), ds.advantages.numpy(), rtol=1e-5, atol=1e-6)
+    seen = []
+    for batch in dl:
+        assert batch["observations"].shape == (256, 16, 31) and batch["observations"].is_cuda
+        seen.append(batch)
+    assert len(seen) == len(dl)
+    # explicit indices: every field equals the dataset's items
+    idx = torch.randperm(n, device="cuda")[:500]
+    b = dl.batch(idx)
+    items = [ds[int(i)] for i in idx.cpu()]
+    for key in ("observations", "action_masks", "log_probs", "values"):
+        want = torch.stack([it[key] for it in items])
+        assert torch.equal(b[key].cpu(), want), key
+    np.testing.assert_array_equal(b["actions"].cpu().numpy(), torch.stack([it["actions"] for it in items]).argmax(-1).numpy())
+    np.testing.assert_allclose(b["advantages"].cpu().numpy(), torch.stack([it["advantages"] for it in items]).numpy(), rtol=1e-5, atol=1e-6)
+    np.testing.assert_allclose(b["returns"].cpu().numpy(), torch.stack([it["returns"] for it in items]).numpy(), rtol=1e-5, atol=1e-6)
+    # bf16 observations for an autocast forward, subset per epoch with reshuffle
+    sub = G.DevicePPOBatches(packed, batch_size=64, max_samples_per_epoch=640, shuffle_on_reset=True, obs_dtype=torch.bfloat16)
+    assert len(sub) == 10
+    first = sub.active_indices.clone()
+    sub.reset_epoch()
+    assert not torch.equal(first, sub.active_indices)
+    batch = next(iter(sub))
+    assert batch["observations"].dtype == torch.bfloat16 and float(batch["observations"].float().sum()) == 64 * 16
+
+
 # ------------------------------------------------------------------------------------- policy network path
 class TinyAgent(torch.nn.Module):
     """Same call signature as the reference's PPOAgent.forward (obs (B,16,31), mask|None)."""
