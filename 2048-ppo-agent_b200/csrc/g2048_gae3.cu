@@ -67,6 +67,9 @@ __device__ __forceinline__ int gae3_locate(const Gae3Smem& s, int k) {
 
 // gae = delta + gl * gae backwards over the steps (first_excl, last], in place
 __device__ __forceinline__ void gae3_walk(float* __restrict__ sg, int last, int first_excl, float g, float gl) {
+    // keep gamma*lambda in a register: left to itself ptxas re-loads it from the constant bank at the top of
+    // every trip (LDC, ~30 cycles) and the first multiply of the serial chain waits for it
+    asm volatile("" : "+f"(gl));
     int t = last;
     while (t > first_excl && (t & 3) != 3) {  // down to a 16-byte boundary
         g = sg[t] + gl * g;
@@ -236,7 +239,9 @@ gae_flat3_kernel(const float* __restrict__ rewards, const float* __restrict__ va
     if (role == 4) {
         // the first episode of the tile alone in its warp: the previous tile is waiting for its result
         if (lane == 0 && n_done > 0) {
+#ifndef G2048_GAE3_SKIP_SIDE_WALKS  // timing experiment only (tools/probes/probe_gae3.cu)
             gae3_walk(s.g, gae3_locate(s, 0), -1, 0.0f, gamma_lambda);
+#endif
             heads[tile] = s.g[0];
             __threadfence();
             flags[tile] = 1u;
@@ -254,7 +259,9 @@ gae_flat3_kernel(const float* __restrict__ rewards, const float* __restrict__ va
                     carry = heads[tile + 1];
                 }
                 GAE3_STAMP_ANY(9);   // look-back satisfied
+#ifndef G2048_GAE3_SKIP_SIDE_WALKS
                 gae3_walk(s.g, len - 1, first_excl, carry, gamma_lambda);
+#endif
                 GAE3_STAMP_ANY(10);  // tail walked
             }
             if (n_done == 0) {

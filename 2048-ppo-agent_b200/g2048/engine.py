@@ -296,6 +296,14 @@ def compact_records(rec_boards, rec_meta, rec_rewards, rec_log_probs, rec_values
          ptr(log_probs), ptr(values), stream_ptr())
 
 
+def meta_dones(meta: torch.Tensor) -> torch.Tensor:
+    """Packed meta bytes -> uint8 done flags only (no one-hot actions / masks are materialised)."""
+    n = meta.shape[0]
+    term = torch.empty(n, dtype=torch.uint8, device=meta.device)
+    call("g2048_unpack_flat_meta", ptr(meta), n, None, None, ptr(term), stream_ptr())
+    return term
+
+
 def unpack_flat_meta(meta: torch.Tensor):
     n = meta.shape[0]
     dev = meta.device

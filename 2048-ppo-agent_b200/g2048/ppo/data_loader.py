@@ -42,8 +42,7 @@ def compute_gae(rewards: torch.Tensor, values: torch.Tensor, terminations: torch
 
 def meta_to_dones(meta: torch.Tensor) -> torch.Tensor:
     """Packed meta bytes -> uint8 done flags."""
-    _, _, term = E.unpack_flat_meta(meta)
-    return term.view(torch.uint8)
+    return E.meta_dones(meta)
 
 
 class DevicePPOBatches:

@@ -93,6 +93,16 @@ class BatchRunner:
     def act_fn(self, act_fn: Callable):
         self._act_fn = act_fn
 
+    # -- checkpointing (the reference saves no env / RNG state, src/ppo/ppo_trainer.py:511-530) --
+    def state_dict(self) -> dict:
+        """Everything needed to continue the key chain exactly where it stands: two uint32 words."""
+        return {"key": [int(w) for w in self.chain.key], "position": int(self.chain.position), "rng_mode": int(self.rng_mode)}
+
+    def load_state_dict(self, state: dict) -> None:
+        self.rng_mode = int(state["rng_mode"])
+        self.chain = KeyChain(np.asarray(state["key"], dtype=np.uint32), self.rng_mode, self.device)
+        self.chain._base_pos = int(state.get("position", 0))
+
     def run_actions_batch(self, batch_size: int):
         """-> (observations (B,T,4,4,31) bool, actions (B,T) int32, action_masks (B,T,4) bool,
         log_probs (B,T) f32 | None, values (B,T) f32 | None, rewards (B,T) f32, terminations (B,T) bool),

@@ -67,6 +67,15 @@ def main() -> int:
     assert drul.shape == (285, 4, 16), drul.shape
     assert rand.shape == (123, 4, 16), rand.shape
     np.savez_compressed(OUT, drul_boards=drul, random_boards=rand)
+    # SHA-256 of the two files themselves: g2048.svg must regenerate them byte for byte (tests/test_svg.py)
+    import hashlib
+    import json
+
+    hashes = {"_source": "sha256 of assets/2048_{drul,random}_actions.svg of the reference repo (tests/golden/make_golden_svg.py)"}
+    for name in ("drul", "random"):
+        raw = (REF / f"2048_{name}_actions.svg").read_bytes()
+        hashes[name] = {"sha256": hashlib.sha256(raw).hexdigest(), "bytes": len(raw)}
+    (OUT.parent / "svg_sha256.json").write_text(json.dumps(hashes, indent=1))
     print("wrote", OUT, drul.shape, rand.shape)
     print("drul final env0:\n", drul[-1, 0].reshape(4, 4))
     print("random final env3:\n", rand[-1, 3].reshape(4, 4))

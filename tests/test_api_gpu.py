@@ -142,6 +142,18 @@ def test_run_actions_batch_matches_numpy_oracle(G, mode, policy):
         np.testing.assert_array_equal(runner.key, np.array(ref_chain.key, np.uint32))
 
 
+def test_runner_state_dict_resumes_the_key_chain(G):
+    a = G.BatchRunner(init_seed=9, act_fn=G.act_randomly)
+    a.run_packed_batch(16)
+    saved = a.state_dict()
+    want = a.run_packed_batch(16)
+    b = G.BatchRunner(init_seed=0, act_fn=G.act_randomly)
+    b.load_state_dict(saved)
+    got = b.run_packed_batch(16)
+    assert torch.equal(got.boards, want.boards) and torch.equal(got.meta, want.meta)
+    assert b.state_dict() == a.state_dict() and saved["position"] > 0
+
+
 def test_golden_svg_through_the_public_api(G, golden_svg):
     """run_actions_batch(0, 4, act_drul / act_randomly) == the frames of the reference's SVGs."""
     for fn, name in ((G.act_drul, "drul_boards"), (G.act_randomly, "random_boards")):
