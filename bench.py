@@ -538,7 +538,33 @@ def secondary_measurements(E, N, torch, dev, flush_buf) -> dict:
         "policy_forward_note": "same-shaped PyTorch Transformer (3.96 M parameters, bf16 autocast, 65536 x 17 tokens), for scale only",
         "kernels": "per step: expand_obs<f32> (network input) + policy_step (mask, sample, log-prob, env step, auto-reset, record write); then gae_time_major",
     }
-    return {"roofline_hbm": rows, "hbm_peak_source": peak_src, "ppo_rollout": ppo}
+    # C2: DRUL corner policy, 2^20 envs to termination, score / max-tile statistics reduced on the device
+    import g2048
+
+    n2 = 1 << 20
+    key2 = E.words_tensor([0, 0], dev)
+    subs2 = E.chain_advance(key2, mode, 1 + 2 * 2048)
+    st2 = {}
+    t = timed(lambda: st2.update(stats=E.play(E.POLICY_DRUL, subs2, n2, 0, n2, mode, per_env=False)["stats"]), reps=3)
+    s2 = E.play_stats_dict(st2["stats"])
+    c2 = {"config": "C2: act_drul, 2^20 envs to termination, seed 0", "env_steps_per_sec": s2["env_steps"] / t,
+          "ms": t * 1e3, "mean_episode_length": s2["env_steps"] / n2, "mean_score": s2["score_sum"] / n2,
+          "mean_max_tile": s2["tile_sum"] / n2, "max_tile_hist": {str(k): v for k, v in s2["max_tile_hist"].items()}}
+
+    # C1 through the reference-format API: BatchRunner(0, act_randomly).run_actions_batch(1024), numpy arrays out
+    # (observations (B,T,4,4,31) bool etc., i.e. including the one-hot materialisation and the D2H copies)
+    runner = g2048.BatchRunner(init_seed=0, act_fn=g2048.act_randomly)
+    runner.run_actions_batch(1024)
+    runner = g2048.BatchRunner(init_seed=0, act_fn=g2048.act_randomly)
+    torch.cuda.synchronize()
+    t0 = time.perf_counter()
+    out = runner.run_actions_batch(1024)
+    dt = time.perf_counter() - t0
+    first_done = out[6].argmax(axis=1) + 1
+    c1 = {"config": "C1: BatchRunner(0, act_randomly).run_actions_batch(1024), reference-format numpy outputs",
+          "seconds": dt, "loop_steps": int(out[0].shape[1]), "env_steps": int(first_done.sum()),
+          "env_steps_per_sec": float(first_done.sum() / dt), "output_bytes": int(sum(a.nbytes for a in out if a is not None))}
+    return {"roofline_hbm": rows, "hbm_peak_source": peak_src, "ppo_rollout": ppo, "c2_drul": c2, "c1_reference_api": c1}
 
 
 if __name__ == "__main__":

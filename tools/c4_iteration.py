@@ -43,7 +43,11 @@ def main():
     report = {"config": f"C4: {args.envs} envs to termination, random policy records, {args.epochs} epochs x minibatch {args.minibatch}"}
 
     runner = g2048.BatchRunner(init_seed=4, act_fn=g2048.act_randomly)
-    runner.run_packed_batch(1024)  # warm-up (table build, allocator)
+    warm = runner.run_packed_batch(1024)  # warm-up: table build, allocator, lazy loading of every kernel on the path
+    wb = g2048.RolloutBuffer(31, 16, 4)
+    wb.store_packed(warm)
+    for _ in g2048.DevicePPOBatches(wb.get_packed(), batch_size=256):
+        break
     rollout, t_roll = timed(lambda: runner.run_packed_batch(args.envs))
     report["rollout"] = {"seconds": t_roll, "loop_steps": rollout.t_steps, "env_steps": rollout.env_steps,
                          "env_steps_per_sec": rollout.env_steps / t_roll,
