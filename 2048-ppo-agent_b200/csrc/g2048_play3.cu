@@ -11,7 +11,7 @@
 //   * the lane keeps the board AND its transpose in registers, so a vertical move is a horizontal
 //     move on the transpose and every step pays exactly one 16-instruction transpose.
 // Shared-memory loads issue on the LSU pipe, which the kernel otherwise leaves idle.
-// 192 KiB of tables -> one CTA of 1 024 threads per SM (32 warps).  Same lane scheduling, init-as-two-
+// 192 KiB of tables -> one CTA of 512 threads per SM (16 warps keep the ALU pipe saturated).  Same lane scheduling, init-as-two-
 // iterations trick, score-from-potential and results as g2048_play.cu (bit-identical; tested).
 #include "g2048_board.cuh"
 #include "g2048_common.cuh"
@@ -20,7 +20,10 @@
 
 namespace g2048 {
 
-constexpr int PLAY3_THREADS = 1024;
+#ifndef G2048_PLAY3_THREADS
+#define G2048_PLAY3_THREADS 512
+#endif
+constexpr int PLAY3_THREADS = G2048_PLAY3_THREADS;  // one CTA per SM; 512 / 768 / 1024 threads measured within 3 % of each other, 512 best (shorter tail)
 constexpr int PLAY3_TABLE_BYTES = 65536 * 2 + 65536;
 constexpr int PLAY3_SMEM_BYTES = PLAY3_TABLE_BYTES + G2048_PLAY_STATS_WORDS * 8;
 
