@@ -76,33 +76,46 @@ __device__ __forceinline__ void gae3_walk(float* __restrict__ sg, int last, int 
         sg[t] = g;
         --t;
     }
-    // 4-step groups, two per trip, each loaded two groups ahead of its use so that the shared-memory
-    // round trip stays off the serial multiply-add chain
-#define GAE3_GROUP(q, at)                                        \
-    g = q.w + gl * g; q.w = g;                                   \
-    g = q.z + gl * g; q.z = g;                                   \
-    g = q.y + gl * g; q.y = g;                                   \
-    g = q.x + gl * g; q.x = g;                                   \
-    *reinterpret_cast<float4*>(&sg[(at)]) = q;
+    // 4-step groups.  Register discipline matters more than instruction count here: the STS.128 of a group
+    // holds its source registers until the (conflict-laden, queued) store is dispatched, so neither the
+    // serial chain nor the prefetching loads may write those registers soon after.  Inputs (i*, n*) and
+    // outputs (o*) therefore live in separate registers, the two input sets swap roles every half trip (no
+    // moves), and an output set is rewritten only two groups after its store was issued.
+#define GAE3_LD(at) (*reinterpret_cast<const float4*>(&sg[(at)]))
+#define GAE3_GROUP(in, out, at)                                  \
+    g = in.w + gl * g; out.w = g;                                \
+    g = in.z + gl * g; out.z = g;                                \
+    g = in.y + gl * g; out.y = g;                                \
+    g = in.x + gl * g; out.x = g;                                \
+    *reinterpret_cast<float4*>(&sg[(at)]) = out;
     if (t - 4 >= first_excl) {                // steps t-3 .. t are all inside the episode
-        float4 a = *reinterpret_cast<const float4*>(&sg[t - 3]);
-        float4 b = a;
-        if (t - 8 >= first_excl) b = *reinterpret_cast<const float4*>(&sg[t - 7]);
+        float4 i0 = GAE3_LD(t - 3), i1 = i0, n0 = i0, n1 = i0, o0, o1;
+        if (t - 8 >= first_excl) i1 = GAE3_LD(t - 7);
         while (true) {
-            const bool has_b = t - 8 >= first_excl, has_c = t - 12 >= first_excl;
-            float4 c = a, d = b;
-            if (has_c) c = *reinterpret_cast<const float4*>(&sg[t - 11]);
-            if (t - 16 >= first_excl) d = *reinterpret_cast<const float4*>(&sg[t - 15]);
-            GAE3_GROUP(a, t - 3)
-            if (!has_b) { t -= 4; break; }
-            GAE3_GROUP(b, t - 7)
-            t -= 8;
-            if (!has_c) break;
-            a = c;
-            b = d;
+            {   // consume i0, i1; fetch n0, n1 (two and three groups ahead)
+                const bool has1 = t - 8 >= first_excl, has2 = t - 12 >= first_excl;
+                if (has2) n0 = GAE3_LD(t - 11);
+                if (t - 16 >= first_excl) n1 = GAE3_LD(t - 15);
+                GAE3_GROUP(i0, o0, t - 3)
+                if (!has1) { t -= 4; break; }
+                GAE3_GROUP(i1, o1, t - 7)
+                t -= 8;
+                if (!has2) break;
+            }
+            {   // consume n0, n1; fetch i0, i1
+                const bool has1 = t - 8 >= first_excl, has2 = t - 12 >= first_excl;
+                if (has2) i0 = GAE3_LD(t - 11);
+                if (t - 16 >= first_excl) i1 = GAE3_LD(t - 15);
+                GAE3_GROUP(n0, o0, t - 3)
+                if (!has1) { t -= 4; break; }
+                GAE3_GROUP(n1, o1, t - 7)
+                t -= 8;
+                if (!has2) break;
+            }
         }
     }
 #undef GAE3_GROUP
+#undef GAE3_LD
     for (; t > first_excl; --t) {
         g = sg[t] + gl * g;
         sg[t] = g;
