@@ -1,0 +1,102 @@
+"""Every kernel and C entry once at small, ragged sizes, with every output tensor allocated through `T`
+(torch itself, or tests/test_guard_bands_gpu.py's guarded allocator that surrounds each output with canary bytes).
+
+compute-sanitizer is not available on the GPU pool, so out-of-bounds writes are looked for this way instead:
+odd sizes that do not divide any tile / vector width, canaries either side of every output, and (elsewhere in
+tests/) bit-exact comparison of the outputs with the oracle.
+"""
+import numpy as np
+import torch
+
+
+def run_all(E, g2048, T=torch, dev="cuda"):
+    for mode in (0, 1):
+        key = E.words_tensor([0, 5], dev)
+        subs = E.chain_advance(key, mode, 1 + 2 * 700)
+        E.split_keys(subs[0], 1000, 17, 333, mode)
+        E.threefry2x32(subs[:77].contiguous(), subs[100:177].contiguous())
+        boards, status = E.env_init(subs[0], 1000, 17, 333, mode)
+        a, _ = E.act(0, status, subs[1], 1000, 17, mode)
+        E.act(1, status, subs[1], 1000, 17, mode)
+        E.env_step(boards.clone(), status.clone(), a, subs[2], 1000, 17, mode)
+        E.env_step_draws(boards.clone(), status.clone(), a, torch.zeros(333, dtype=torch.int32, device=dev),
+                         torch.ones(333, dtype=torch.int32, device=dev))
+        for entry in ("g2048_play_swar", "g2048_play_v1"):
+            for policy in (0, 1):
+                E.play(policy, subs, 777, 100, 300, mode, entry=entry)
+        for policy in (0, 1):
+            E.play(policy, subs, 3001, 0, 3001, mode, entry="g2048_play_tables")
+            E.play(policy, subs, 3001, 1234, 1, mode, entry="g2048_play_tables")
+        counters = T.zeros(4, dtype=torch.int64, device=dev)
+        n, ch = 333, 5
+        rb = T.empty((ch, n), dtype=torch.int64, device=dev)
+        rm = T.empty((ch, n), dtype=torch.uint8, device=dev)
+        rr = T.empty((ch, n), dtype=torch.float32, device=dev)
+        rl = T.empty((ch, n), dtype=torch.float32, device=dev)
+        E.rollout_steps(0, boards, status, subs[3:], ch, 0, 1000, 17, mode, rb, rm, rr, rl, counters)
+        logits = torch.randn(n, 4, device=dev)
+        values = torch.randn(n, device=dev)
+        rv = T.empty(n, dtype=torch.float32, device=dev)
+        acts = T.empty(n, dtype=torch.int32, device=dev)
+        E.policy_step(boards, status, logits, values, True, True, True, subs[5], subs[6], 1000, 17, mode,
+                      rb[0], rm[0], rr[0], rl[0], rv, acts)
+        E.sample_logits(logits, status, True, True, subs[5], 1000, 17, mode, want_entropy=True)
+        E.evaluate_logits(logits, status, True, acts)
+        E.unpack_records(rm, rr, rl, None, ch, n)
+        lengths = E.episode_lengths(rm, ch, n)
+        offs = E.exclusive_scan(lengths)
+        tot = int(offs[-1].item())
+        if tot:
+            fb = T.empty(tot, dtype=torch.int64, device=dev)
+            fm = T.empty(tot, dtype=torch.uint8, device=dev)
+            fr = T.empty(tot, dtype=torch.float32, device=dev)
+            fl = T.empty(tot, dtype=torch.float32, device=dev)
+            fv = T.zeros(tot, dtype=torch.float32, device=dev)
+            E.compact_records(rb, rm, rr, rl, None, ch, n, lengths, offs, 0, fb, fm, fr, fl, fv)
+            E.unpack_flat_meta(fm)
+            E.meta_dones(fm)
+        for dt in (torch.float32, torch.bfloat16, torch.bool):
+            for entry in ("g2048_expand_obs", "g2048_expand_obs_v1"):
+                E.expand_obs(boards, dt, entry=entry)
+                E.expand_obs(rb, dt, rows=ch, n_cols=n, entry=entry)
+        obs = E.expand_obs(boards, torch.float32)
+        E.pack_obs(obs)
+        E.pack_obs(E.expand_obs(boards, torch.bool))
+        E.unpack_status(status)
+        E.row_table_lookup(torch.arange(0, 65536, 7, dtype=torch.int32, device=dev).to(torch.int16))
+    for n in (1, 5, 255, 6143, 6144, 6145, 20001):
+        r = torch.rand(n, device=dev)
+        v = torch.rand(n, device=dev)
+        d = (torch.rand(n, device=dev) < 0.01).to(torch.uint8)
+        for entry in ("g2048_gae_flat", "g2048_gae_flat_v1"):
+            adv, ret, mom = E.gae_flat(r, v, d, 0.99, 0.95, entry=entry)
+        E.normalize_(adv, mom, 1)
+        E.normalize_(ret, mom, 3)
+        if n > 8:
+            E.gae_flat(r[3:], v[3:], d[3:], 0.99, 0.95)  # views that are not 16-byte aligned
+    t_steps, n_envs = 37, 301
+    rr = torch.rand(t_steps, n_envs, device=dev)
+    vv = torch.rand(t_steps, n_envs, device=dev)
+    mm = (torch.rand(t_steps, n_envs, device=dev) < 0.05).to(torch.uint8) << 6
+    E.gae_time_major(rr, vv, mm, t_steps, n_envs, None, 0.99, 0.95)
+    E.gae_time_major(rr, vv, mm, t_steps, n_envs, torch.rand(n_envs, device=dev), 0.99, 0.95)
+    E.row_moments(torch.rand(3, 1001, dtype=torch.float64, device=dev))
+    packed = dict(boards=torch.randint(0, 1 << 62, (5000,), dtype=torch.int64, device=dev),
+                  meta=torch.randint(0, 127, (5000,), dtype=torch.uint8, device=dev),
+                  log_probs=torch.rand(5000, device=dev), values=torch.rand(5000, device=dev))
+    idx = torch.randperm(5000, device=dev)[:777].contiguous()
+    for dt in (torch.float32, torch.bfloat16):
+        E.gather_minibatch(idx, packed, torch.rand(5000, device=dev), torch.rand(5000, device=dev), obs_dtype=dt)
+    sink = T.empty(4 * 64, dtype=torch.int32, device=dev)
+    E.int_peak_probe(4, 64, 10, sink)
+    E.play_host(0, 3, 500, 1)
+    E.gae_host(np.random.rand(7000).astype(np.float32), np.random.rand(7000).astype(np.float32),
+               (np.random.rand(7000) < 0.01).astype(np.uint8), 0.99, 0.95, True)
+    runner = g2048.BatchRunner(1, g2048.act_randomly)
+    ro = runner.run_packed_batch(50)
+    buf = g2048.RolloutBuffer(31, 16, 4)
+    buf.store_packed(ro)
+    buf.get_buffer_data()
+    for _ in g2048.DevicePPOBatches(buf.get_packed(), batch_size=64):
+        pass
+    torch.cuda.synchronize()
