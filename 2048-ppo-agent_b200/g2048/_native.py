@@ -73,6 +73,11 @@ _SIGNATURES = {
     "g2048_compact_records": (_INT, [_P, _P, _P, _P, _P, _I64, _I64, _P, _P, _I64, _P, _P, _P, _P, _P, _P]),
     "g2048_unpack_flat_meta": (_INT, [_P, _I64, _P, _P, _P, _P]),
     "g2048_gather_minibatch": (_INT, [_P, _I64, _P, _P, _P, _P, _P, _P, _INT, _P, _P, _P, _P, _P, _P, _P, _P]),
+    "g2048_embed_boards": (_INT, [_P, _I64, _P, _P, _INT, _INT, _P, _P]),
+    "g2048_embed_boards_bulk": (_INT, [_P, _I64, _P, _P, _INT, _INT, _P, _P]),
+    "g2048_embed_boards_plain": (_INT, [_P, _I64, _P, _P, _INT, _INT, _P, _P]),
+    "g2048_embed_grad_scratch_bytes": (_I64, [_I64, _INT, _INT]),
+    "g2048_embed_boards_grad": (_INT, [_P, _I64, _P, _P, _INT, _INT, _P, _P, _P]),
     "g2048_gae_flat_scratch_bytes": (_I64, [_I64]),
     "g2048_gae_flat": (_INT, [_P, _P, _P, _I64, _DBL, _DBL, _P, _P, _P, _P, _P]),
     "g2048_gae_flat_v1": (_INT, [_P, _P, _P, _I64, _DBL, _DBL, _P, _P, _P, _P, _P]),

@@ -317,11 +317,12 @@ def unpack_flat_meta(meta: torch.Tensor):
 def gather_minibatch(indices: torch.Tensor, packed: dict, adv: torch.Tensor | None, ret: torch.Tensor | None,
                      obs_dtype=torch.float32) -> dict:
     """Minibatch `indices` (int64, device) of a flat packed buffer (RolloutBuffer.get_packed()) as the
-    tensors a PPO update consumes; one observation kernel + one scalar-gather kernel."""
+    tensors a PPO update consumes; one observation kernel + one scalar-gather kernel.  obs_dtype=None: no
+    observations -- the batch carries the gathered bitboards under "boards" for ppo.board_embedding."""
     m = indices.shape[0]
     dev = indices.device
     out = dict(
-        observations=torch.empty((m, 16, 31), dtype=obs_dtype, device=dev),
+        observations=torch.empty((m, 16, 31), dtype=obs_dtype, device=dev) if obs_dtype is not None else None,
         actions=torch.empty(m, dtype=torch.int64, device=dev),
         action_masks=torch.empty((m, 4), dtype=torch.bool, device=dev),
         log_probs=torch.empty(m, dtype=torch.float32, device=dev),
@@ -330,10 +331,44 @@ def gather_minibatch(indices: torch.Tensor, packed: dict, adv: torch.Tensor | No
         returns=torch.empty(m, dtype=torch.float32, device=dev) if ret is not None else None,
     )
     call("g2048_gather_minibatch", ptr(indices), m, ptr(packed["boards"]), ptr(packed["meta"]), ptr(packed["log_probs"]),
-         ptr(packed["values"]), ptr(adv), ptr(ret), _OBS_DTYPES[obs_dtype], ptr(out["observations"]), ptr(out["actions"]),
+         ptr(packed["values"]), ptr(adv), ptr(ret), _OBS_DTYPES[obs_dtype or torch.float32], ptr(out["observations"]), ptr(out["actions"]),
          ptr(out["action_masks"]), ptr(out["log_probs"]), ptr(out["values"]), ptr(out["advantages"]), ptr(out["returns"]),
          stream_ptr())
+    if obs_dtype is None:
+        del out["observations"]
+        out["boards"] = packed["boards"][indices]
     return out
+
+
+# ------------------------------------------------------------------------------------------- embedding
+def embed_boards(boards: torch.Tensor, table: torch.Tensor, indices: torch.Tensor | None = None, out=None,
+                 entry: str = "g2048_embed_boards") -> torch.Tensor:
+    """(n,16,d_model) = table[exponent of every cell]: Linear(31->d_model, bias=False) on the one-hot
+    observation without the observation.  table: (31, d_model) float32/bfloat16 contiguous (weight.T);
+    indices (int64): embed boards[indices].  entry="g2048_embed_boards_bulk" | "g2048_embed_boards_plain" pins the kernel."""
+    if table.dim() != 2 or table.shape[0] != 31 or not table.is_contiguous():
+        raise ValueError("table must be a contiguous (31, d_model) tensor")
+    n = boards.numel() if indices is None else indices.numel()
+    d_model = table.shape[1]
+    if out is None:
+        out = torch.empty((n, 16, d_model), dtype=table.dtype, device=boards.device)
+    call(entry, ptr(boards), n, ptr(indices), ptr(table), d_model, _OBS_DTYPES[table.dtype], ptr(out), stream_ptr())
+    return out
+
+
+def embed_boards_grad(boards: torch.Tensor, grad_out: torch.Tensor, indices: torch.Tensor | None = None) -> torch.Tensor:
+    """Gradient of embed_boards' table: (31, d_model) float32 (deterministic summation order)."""
+    n = boards.numel() if indices is None else indices.numel()
+    d_model = grad_out.shape[-1]
+    code = _OBS_DTYPES[grad_out.dtype]
+    nbytes = int(N.lib.g2048_embed_grad_scratch_bytes(n, d_model, code))
+    if nbytes < 0:
+        raise ValueError(f"embed_boards_grad: unsupported d_model {d_model} for {grad_out.dtype}")
+    scratch = torch.empty(max(nbytes, 16), dtype=torch.uint8, device=boards.device)
+    grad_table = torch.empty((31, d_model), dtype=torch.float32, device=boards.device)
+    call("g2048_embed_boards_grad", ptr(boards), n, ptr(indices), ptr(grad_out), d_model, code, ptr(grad_table),
+         ptr(scratch), stream_ptr())
+    return grad_table
 
 
 # ------------------------------------------------------------------------------------------- GAE

@@ -1,5 +1,7 @@
+from .board_embedding import BoardEmbedding, embed_boards, forward_from_boards
 from .data_loader import DevicePPOBatches, PPODataset, compute_gae, create_ppo_dataloader
 from .rollout_buffer import RolloutBuffer
 from .torch_action_wrapper import TorchActionFunction
 
-__all__ = ["DevicePPOBatches", "PPODataset", "RolloutBuffer", "TorchActionFunction", "compute_gae", "create_ppo_dataloader"]
+__all__ = ["BoardEmbedding", "DevicePPOBatches", "PPODataset", "RolloutBuffer", "TorchActionFunction", "compute_gae",
+           "create_ppo_dataloader", "embed_boards", "forward_from_boards"]

@@ -55,6 +55,8 @@ class DevicePPOBatches:
     per epoch (``max_samples_per_epoch`` / ``shuffle_on_reset``, :73-101) and the batch shuffle follow the
     reference's semantics; batches are dicts of DEVICE tensors with the item keys of ``PPODataset``
     (``actions`` are int64 indices -- the trainer's ``argmax`` of the one-hot, ppo_trainer.py:381).
+    ``obs_dtype=None`` leaves the observations out altogether: batches carry the 8-byte bitboards under
+    ``boards`` for ``board_embedding.forward_from_boards`` (the embedding becomes a row gather).
     """
 
     def __init__(self, packed: dict, gamma: float = 0.99, lambda_gae: float = 0.95, batch_size: int = 32,

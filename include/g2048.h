@@ -249,6 +249,31 @@ int g2048_gather_minibatch(const int64_t* d_indices, int64_t m, const uint64_t* 
                            int obs_dtype, void* d_obs, int64_t* d_actions, uint8_t* d_masks, float* d_old_log_probs,
                            float* d_old_values, float* d_out_adv, float* d_out_ret, void* stream);
 
+/* ---- packed boards -> input embedding (src/ppo/ppo_agent.py:60,108) */
+
+/* out[i, c, :] = table[exponent of cell c of board i, :] -- what Linear(31 -> d_model, bias=False) returns for the
+ * one-hot observation of the board, without the observation.  d_table: (31, d_model) row-major = the Linear's
+ * weight transposed, in `dtype` (G2048_OBS_F32 or G2048_OBS_BF16); d_out: (n, 16, d_model) in `dtype`.
+ * d_indices (int64, may be NULL): row i uses d_boards[d_indices[i]] (minibatch gather).  d_model * itemsize must
+ * be a multiple of 16 and the table must fit in shared memory (31 * d_model * itemsize <= 200 KiB).
+ * Two kernels: _bulk issues one shared->global bulk copy (cp.async.bulk) per cell straight from the table,
+ * _plain copies a row per warp with 16-byte stores; g2048_embed_boards picks by row size (rows under 1 KiB ->
+ * bulk), as measured on B200. */
+int g2048_embed_boards(const uint64_t* d_boards, int64_t n, const int64_t* d_indices, const void* d_table,
+                       int d_model, int dtype, void* d_out, void* stream);
+int g2048_embed_boards_bulk(const uint64_t* d_boards, int64_t n, const int64_t* d_indices, const void* d_table,
+                            int d_model, int dtype, void* d_out, void* stream);
+int g2048_embed_boards_plain(const uint64_t* d_boards, int64_t n, const int64_t* d_indices, const void* d_table,
+                             int d_model, int dtype, void* d_out, void* stream);
+
+/* Gradient of the table: d_grad_table[r, :] (float32 (31, d_model), overwritten) = sum over cells whose exponent
+ * is r of d_grad_out[cell, :] (d_grad_out: (n, 16, d_model) in `dtype`); rows 16..30 are zero.  Deterministic:
+ * per-CTA partial tables in d_scratch (g2048_embed_grad_scratch_bytes(n, d_model, dtype) bytes, 16-byte aligned,
+ * need not be zeroed) are added in a fixed order.  The scratch size query returns -1 for an unsupported d_model. */
+int64_t g2048_embed_grad_scratch_bytes(int64_t n, int d_model, int dtype);
+int g2048_embed_boards_grad(const uint64_t* d_boards, int64_t n, const int64_t* d_indices, const void* d_grad_out,
+                            int d_model, int dtype, float* d_grad_table, void* d_scratch, void* stream);
+
 /* ---- GAE (src/ppo/data_loader.py:103-130) and normalisation (:61-67) */
 
 /* Flat buffer, reverse segmented scan: if done[t]: last_v = last_gae = 0;

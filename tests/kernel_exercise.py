@@ -87,6 +87,14 @@ def run_all(E, g2048, T=torch, dev="cuda"):
     idx = torch.randperm(5000, device=dev)[:777].contiguous()
     for dt in (torch.float32, torch.bfloat16):
         E.gather_minibatch(idx, packed, torch.rand(5000, device=dev), torch.rand(5000, device=dev), obs_dtype=dt)
+    eb = packed["boards"][:301].contiguous()
+    for dt, d_model in ((torch.float32, 256), (torch.bfloat16, 256), (torch.float32, 12), (torch.bfloat16, 8)):
+        table = torch.randn(31, d_model, device=dev).to(dt)
+        for entry in ("g2048_embed_boards", "g2048_embed_boards_bulk", "g2048_embed_boards_plain"):
+            E.embed_boards(eb, table, entry=entry)
+            E.embed_boards(packed["boards"], table, idx, entry=entry)
+        E.embed_boards_grad(eb, torch.randn(301, 16, d_model, device=dev).to(dt))
+        E.embed_boards_grad(packed["boards"], torch.randn(777, 16, d_model, device=dev).to(dt), idx)
     sink = T.empty(4 * 64, dtype=torch.int32, device=dev)
     E.int_peak_probe(4, 64, 10, sink)
     E.play_host(0, 3, 500, 1)
