@@ -18,9 +18,22 @@ policy_step_kernel(u64* __restrict__ boards, uint8_t* __restrict__ status, const
                    const uint32_t* __restrict__ sub_act, const uint32_t* __restrict__ sub_step, uint32_t batch_global,
                    uint32_t env_lo, int64_t n, u64* __restrict__ rec_boards, uint8_t* __restrict__ rec_meta,
                    float* __restrict__ rec_rewards, float* __restrict__ rec_log_probs, float* __restrict__ rec_values,
-                   int32_t* __restrict__ actions_out) {
+                   int32_t* __restrict__ actions_out, const int32_t* __restrict__ step_index) {
     const int64_t i = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
     if (i >= n) return;
+    if (step_index) {
+        // graph-replay form: the step number lives in device memory; sub keys of step t sit 4 words further per
+        // step (act key, step key), the record slot n entries further
+        const int64_t t = *step_index;
+        sub_act += 4 * t;
+        sub_step += 4 * t;
+        const int64_t at = t * n;
+        if (rec_boards) rec_boards += at;
+        if (rec_meta) rec_meta += at;
+        if (rec_rewards) rec_rewards += at;
+        if (rec_log_probs) rec_log_probs += at;
+        if (rec_values) rec_values += at;
+    }
     EnvState s{boards[i], status[i]};
     // pgx.experimental.auto_reset: a state that finished on the previous step was already replaced
     // by a fresh one but still carries terminated=True; the wrapper clears it before stepping.
@@ -59,6 +72,8 @@ policy_step_kernel(u64* __restrict__ boards, uint8_t* __restrict__ status, const
     if (rec_values && values) rec_values[i] = values[i];
     if (actions_out) actions_out[i] = a;
 }
+
+__global__ void counter_add_kernel(int32_t* counter, int32_t delta) { *counter += delta; }
 
 template <int MODE>
 __global__ void __launch_bounds__(256)
@@ -105,11 +120,12 @@ static inline bool valid_batch(int64_t batch_global, int64_t env_lo, int64_t n) 
 }
 static inline bool aligned16(const void* p) { return ((uintptr_t)p & 15u) == 0; }
 
-extern "C" int g2048_policy_step(uint64_t* d_boards, uint8_t* d_status, const float* d_logits, const float* d_values,
-                                 int use_mask, int sample, int auto_reset, const uint32_t* d_sub_act,
-                                 const uint32_t* d_sub_step, int64_t batch_global, int64_t env_lo, int64_t n,
-                                 int rng_mode, uint64_t* d_rec_boards, uint8_t* d_rec_meta, float* d_rec_rewards,
-                                 float* d_rec_log_probs, float* d_rec_values, int32_t* d_actions_out, void* stream) {
+static int launch_policy_step(uint64_t* d_boards, uint8_t* d_status, const float* d_logits, const float* d_values,
+                              int use_mask, int sample, int auto_reset, const uint32_t* d_sub_act,
+                              const uint32_t* d_sub_step, const int32_t* d_step_index, int64_t batch_global,
+                              int64_t env_lo, int64_t n, int rng_mode, uint64_t* d_rec_boards, uint8_t* d_rec_meta,
+                              float* d_rec_rewards, float* d_rec_log_probs, float* d_rec_values, int32_t* d_actions_out,
+                              void* stream) {
     G2048_REQUIRE(valid_mode(rng_mode) && valid_batch(batch_global, env_lo, n), "policy_step: batch");
     if (n == 0) return G2048_OK;
     G2048_REQUIRE(d_boards && d_status && d_logits && d_sub_step && (d_sub_act || !sample), "policy_step: pointers");
@@ -121,14 +137,42 @@ extern "C" int g2048_policy_step(uint64_t* d_boards, uint8_t* d_status, const fl
         policy_step_kernel<G2048_RNG_PARTITIONABLE><<<g, 256, 0, st>>>(
             (u64*)d_boards, d_status, (const float4*)d_logits, d_values, use_mask, sample, auto_reset, sub_act,
             d_sub_step, (uint32_t)batch_global, (uint32_t)env_lo, n, (u64*)d_rec_boards, d_rec_meta, d_rec_rewards,
-            d_rec_log_probs, d_rec_values, d_actions_out);
+            d_rec_log_probs, d_rec_values, d_actions_out, d_step_index);
     } else {
         policy_step_kernel<G2048_RNG_ORIGINAL><<<g, 256, 0, st>>>(
             (u64*)d_boards, d_status, (const float4*)d_logits, d_values, use_mask, sample, auto_reset, sub_act,
             d_sub_step, (uint32_t)batch_global, (uint32_t)env_lo, n, (u64*)d_rec_boards, d_rec_meta, d_rec_rewards,
-            d_rec_log_probs, d_rec_values, d_actions_out);
+            d_rec_log_probs, d_rec_values, d_actions_out, d_step_index);
     }
     G2048_CHECK_LAUNCH("policy_step");
+    return G2048_OK;
+}
+
+extern "C" int g2048_policy_step(uint64_t* d_boards, uint8_t* d_status, const float* d_logits, const float* d_values,
+                                 int use_mask, int sample, int auto_reset, const uint32_t* d_sub_act,
+                                 const uint32_t* d_sub_step, int64_t batch_global, int64_t env_lo, int64_t n,
+                                 int rng_mode, uint64_t* d_rec_boards, uint8_t* d_rec_meta, float* d_rec_rewards,
+                                 float* d_rec_log_probs, float* d_rec_values, int32_t* d_actions_out, void* stream) {
+    return launch_policy_step(d_boards, d_status, d_logits, d_values, use_mask, sample, auto_reset, d_sub_act, d_sub_step,
+                              nullptr, batch_global, env_lo, n, rng_mode, d_rec_boards, d_rec_meta, d_rec_rewards,
+                              d_rec_log_probs, d_rec_values, d_actions_out, stream);
+}
+
+extern "C" int g2048_policy_step_at(uint64_t* d_boards, uint8_t* d_status, const float* d_logits, const float* d_values,
+                                    int use_mask, int sample, int auto_reset, const uint32_t* d_subs,
+                                    const int32_t* d_step_index, int64_t batch_global, int64_t env_lo, int64_t n,
+                                    int rng_mode, uint64_t* d_rec_boards, uint8_t* d_rec_meta, float* d_rec_rewards,
+                                    float* d_rec_log_probs, float* d_rec_values, int32_t* d_actions_out, void* stream) {
+    G2048_REQUIRE(d_subs && d_step_index, "policy_step_at: sub keys and step index");
+    return launch_policy_step(d_boards, d_status, d_logits, d_values, use_mask, sample, auto_reset, d_subs, d_subs + 2,
+                              d_step_index, batch_global, env_lo, n, rng_mode, d_rec_boards, d_rec_meta, d_rec_rewards,
+                              d_rec_log_probs, d_rec_values, d_actions_out, stream);
+}
+
+extern "C" int g2048_counter_add(int32_t* d_counter, int32_t delta, void* stream) {
+    G2048_REQUIRE(d_counter, "counter_add: pointer");
+    counter_add_kernel<<<1, 1, 0, (cudaStream_t)stream>>>(d_counter, delta);
+    G2048_CHECK_LAUNCH("counter_add");
     return G2048_OK;
 }
 

@@ -203,6 +203,28 @@ def policy_step(boards, status, logits, values, use_mask: bool, sample: bool, au
          ptr(rec_meta), ptr(rec_rewards), ptr(rec_log_probs), ptr(rec_values), ptr(actions_out), stream_ptr())
 
 
+def policy_step_at(boards, status, logits, values, use_mask: bool, sample: bool, auto_reset: bool, subs, step_index,
+                   batch_global: int, env_lo: int, rng_mode: int, rec_boards=None, rec_meta=None, rec_rewards=None,
+                   rec_log_probs=None, rec_values=None, actions_out=None) -> None:
+    """policy_step whose step number t is read from `step_index` (int32 device scalar): sub keys subs[2t], subs[2t+1]
+    and record slot t of the (steps, n) record tensors.  Every argument is replay-stable, so the launch can sit in
+    a captured CUDA graph; follow it with counter_add(step_index)."""
+    n = boards.shape[0]
+    assert logits.dtype == torch.float32 and logits.shape == (n, 4)
+    assert step_index.dtype == torch.int32 and subs.dtype == torch.int32
+    if values is not None:
+        assert values.dtype == torch.float32 and values.numel() == n
+    call("g2048_policy_step_at", ptr(boards), ptr(status), ptr(logits), ptr(values), int(use_mask), int(sample),
+         int(auto_reset), ptr(subs), ptr(step_index), batch_global, env_lo, n, rng_mode, ptr(rec_boards),
+         ptr(rec_meta), ptr(rec_rewards), ptr(rec_log_probs), ptr(rec_values), ptr(actions_out), stream_ptr())
+
+
+def counter_add(counter: torch.Tensor, delta: int = 1) -> None:
+    """counter (int32 device scalar) += delta, on the stream."""
+    assert counter.dtype == torch.int32
+    call("g2048_counter_add", ptr(counter), int(delta), stream_ptr())
+
+
 def sample_logits(logits, status, use_mask: bool, sample: bool, sub_act, batch_global: int, env_lo: int,
                   rng_mode: int, want_entropy: bool = False):
     n = logits.shape[0]

@@ -35,6 +35,7 @@ from ..state import State
 
 ENV_ID = "2048"
 CHUNK_STEPS = 64
+GRAPH_SYNC_STEPS = 8  # graph replays between `all done` tests; divides CHUNK_STEPS
 
 
 @dataclass
@@ -65,19 +66,25 @@ class BatchRunner:
     """Runs batches of 2048 envs with an action function (reference: batch_runner.py:10-37)."""
 
     def __init__(self, init_seed: int, act_fn: Callable = None, rng_mode=None, device=None,
-                 shard: tuple[int, int] | None = None):
+                 shard: tuple[int, int] | None = None, cuda_graph: bool = False):
         """
         init_seed : seed of the runner's key chain (jax.random.key(seed), batch_runner.py:32)
         act_fn    : policy, see the module docstring; may be set later through ``.act_fn``
         rng_mode  : None / "partitionable" / "original"
         shard     : (rank, world) -- this process owns a contiguous slice of every batch; env
                     indices stay global, so the union over ranks equals the single-GPU run.
+        cuda_graph: with a ``TorchActionFunction`` whose network runs on this GPU, capture one loop step
+                    (observation -> network forward -> sample + env.step + record) as a CUDA graph and replay it,
+                    with one host synchronisation per CHUNK_STEPS steps instead of one per step (SURVEY 8f
+                    rank 3).  Same records as the eager loop.
         """
         self.device = N.require_cuda() if device is None else torch.device(device)
         self.rng_mode = E.resolve_rng_mode(rng_mode)
         self.chain = KeyChain(init_seed, self.rng_mode, self.device)
         self.shard = shard
         self._act_fn = act_fn
+        self.cuda_graph = cuda_graph
+        self._graphs = {}  # (id(act_fn), batch_size, lo, n) -> captured step
 
     # -- reference surface ---------------------------------------------------------------------
     @property
@@ -192,6 +199,8 @@ class BatchRunner:
         states = [State(boards.clone(), status.clone(), torch.zeros(n, dtype=torch.float32, device=dev))] if keep_states else None
         policy = getattr(self._act_fn, "policy_id", None)
         is_net = hasattr(self._act_fn, "forward_logits")
+        if self.cuda_graph and is_net and not keep_states:
+            return self._run_net_graphed(batch_size, lo, n, boards, status)
         counters = torch.zeros(4, dtype=torch.int64, device=dev)
         chunks = []  # (boards, meta, rewards, log_probs, values) per chunk, time-major
         t0 = 0
@@ -264,6 +273,88 @@ class BatchRunner:
         else:
             env_steps = int(E.episode_lengths(rm, t_total, n).sum().item())
         return PackedRollout(rb, rm, rr, rl, rv, boards, status, t_total, n, env_steps)
+
+    # -- CUDA-graph form of the network-policy loop ---------------------------
+    def _captured_step(self, batch_size: int, lo: int, n: int) -> dict:
+        """Static buffers + one captured graph: expand_obs -> forward -> policy_step_at -> counter_add."""
+        fn = self._act_fn
+        cache_key = (id(fn), batch_size, lo, n)
+        g = self._graphs.get(cache_key)
+        if g is not None:
+            return g
+        dev, mode, steps = self.device, self.rng_mode, CHUNK_STEPS
+        net_dev, run_dev = torch.device(fn.device), torch.device(dev)
+        same_index = net_dev.index is None or run_dev.index is None or net_dev.index == run_dev.index
+        if net_dev.type != "cuda" or not same_index:
+            raise ValueError("cuda_graph=True needs the TorchActionFunction's network on the runner's GPU")
+        g = dict(
+            boards=torch.zeros(n, dtype=torch.int64, device=dev), status=torch.zeros(n, dtype=torch.uint8, device=dev),
+            obs=torch.empty((n, 16, 31), dtype=fn.obs_dtype, device=dev),
+            subs=torch.zeros((2 * steps, 2), dtype=torch.int32, device=dev),
+            step_index=torch.zeros((), dtype=torch.int32, device=dev),
+            rb=torch.empty((steps, n), dtype=torch.int64, device=dev), rm=torch.empty((steps, n), dtype=torch.uint8, device=dev),
+            rr=torch.empty((steps, n), dtype=torch.float32, device=dev), rl=torch.empty((steps, n), dtype=torch.float32, device=dev),
+            rv=torch.empty((steps, n), dtype=torch.float32, device=dev),
+        )
+
+        def step():
+            E.expand_obs(g["boards"], fn.obs_dtype, out=g["obs"])
+            logits, values = fn.forward_logits(g["obs"])
+            E.policy_step_at(g["boards"], g["status"], logits, values, fn.use_mask, fn.sample_actions, False, g["subs"],
+                             g["step_index"], batch_size, lo, mode, g["rb"], g["rm"], g["rr"], g["rl"], g["rv"])
+            E.counter_add(g["step_index"], 1)
+
+        # warm-up on a side stream (lazy module loading, cuBLAS workspaces, autotuning) before the capture
+        side = torch.cuda.Stream(device=dev)
+        side.wait_stream(torch.cuda.current_stream(dev))
+        with torch.cuda.stream(side):
+            for _ in range(3):
+                g["step_index"].zero_()
+                step()
+        torch.cuda.current_stream(dev).wait_stream(side)
+        torch.cuda.synchronize(dev)
+        graph = torch.cuda.CUDAGraph()
+        g["step_index"].zero_()
+        with torch.cuda.graph(graph):
+            step()
+        g["graph"] = graph
+        self._graphs[cache_key] = g
+        return g
+
+    def _run_net_graphed(self, batch_size: int, lo: int, n: int, boards, status) -> PackedRollout:
+        g = self._captured_step(batch_size, lo, n)
+        g["boards"].copy_(boards)
+        g["status"].copy_(status)
+        chunks, t0 = [], 0
+        while True:
+            subs = self.chain.peek(1 + 2 * (t0 + CHUNK_STEPS))
+            g["subs"].copy_(subs[1 + 2 * t0: 1 + 2 * (t0 + CHUNK_STEPS)])
+            g["step_index"].zero_()
+            # frozen envs do not change (env.step on a finished env is a no-op), so running past the reference's
+            # per-step `all done` test only appends records that are cut off below; the test (one host
+            # synchronisation) runs every GRAPH_SYNC_STEPS replays
+            finished, used = False, 0
+            while used < CHUNK_STEPS and not finished:
+                for _ in range(GRAPH_SYNC_STEPS):
+                    g["graph"].replay()
+                used += GRAPH_SYNC_STEPS
+                done_now = int(((g["status"] & N.STATUS_DONE) != 0).sum().item())
+                finished = self._all_done(done_now, n)
+            chunks.append(tuple(g[k][:used].clone() for k in ("rb", "rm", "rr", "rl", "rv")))
+            t0 += used
+            if finished:
+                break
+        rb, rm, rr, rl, rv = (torch.cat([c[i] for c in chunks]) for i in range(5))
+        lengths = E.episode_lengths(rm, t0, n)
+        t_total = int(lengths.max().item())
+        if self.shard is not None and self.shard[1] > 1:
+            from ..dist import allreduce_max_int
+
+            t_total = allreduce_max_int(t_total, self.device)
+        self.chain.consume(1 + 2 * t_total)
+        rb, rm, rr, rl, rv = (x[:t_total].contiguous() for x in (rb, rm, rr, rl, rv))
+        return PackedRollout(rb, rm, rr, rl, rv, g["boards"].clone(), g["status"].clone(), t_total, n,
+                             int(lengths.sum().item()))
 
     def _net_step(self, boards, status, sub_act, sub_step, batch_size, lo, mode, rb, rm, rr, rl, rv):
         fn = self._act_fn

@@ -442,6 +442,22 @@ def secondary_measurements(E, N, torch, dev, flush_buf) -> dict:
         "65536 random samples: 33 B gathered + 2012 B written per sample; includes the output allocations")
     del packed, g_adv, g_ret, idx
 
+    # packed boards -> input embedding: 2^18 boards, d_model 256 (configs/model/transformer_combined.yaml)
+    n_e, d_model = 1 << 18, 256
+    e_boards = boards[:n_e].contiguous()
+    for dt, item in ((torch.float32, 4), (torch.bfloat16, 2)):
+        table = torch.randn(31, d_model, device=dev).to(dt)
+        emb = torch.empty((n_e, 16, d_model), dtype=dt, device=dev)
+        name = str(dt).split(".")[-1]
+        t = timed(lambda: E.embed_boards(e_boards, table, out=emb))
+        add(f"embed_boards ({name})", n_e * (8 + 16 * d_model * item), t,
+            f"2^18 boards -> (n,16,256) {name}: the Linear(31,256) of the one-hot observation as a row gather; write-only traffic")
+        t = timed(lambda: E.embed_boards_grad(e_boards, emb))
+        add(f"embed_grad_partial_kernel + reduce ({name})", n_e * (8 + 16 * d_model * item), t,
+            "table gradient of the same; read-only traffic, deterministic two-kernel reduction")
+        del emb
+    del boards, e_boards
+
     # GAE on a flat buffer: C4-sized (2^26 steps), episodes ~300 steps
     n_g = 1 << 26
     r = torch.rand(n_g, device=dev)

@@ -179,6 +179,20 @@ int g2048_policy_step(uint64_t* d_boards, uint8_t* d_status, const float* d_logi
                       uint8_t* d_rec_meta, float* d_rec_rewards, float* d_rec_log_probs, float* d_rec_values,
                       int32_t* d_actions_out, void* stream);
 
+/* The same step with the step number read from device memory, so that ONE captured CUDA graph (observation ->
+ * network forward -> this kernel -> g2048_counter_add) can be replayed for every step of a rollout (SURVEY 8f
+ * rank 3).  t = *d_step_index; d_subs points at the chunk's first act sub key in the layout g2048_chain_advance
+ * writes (act key of step t at words [4t, 4t+2), step key at [4t+2, 4t+4)); the record pointers are the chunk's
+ * bases and slot t*n is written. */
+int g2048_policy_step_at(uint64_t* d_boards, uint8_t* d_status, const float* d_logits, const float* d_values,
+                         int use_mask, int sample, int auto_reset, const uint32_t* d_subs,
+                         const int32_t* d_step_index, int64_t batch_global, int64_t env_lo, int64_t n, int rng_mode,
+                         uint64_t* d_rec_boards, uint8_t* d_rec_meta, float* d_rec_rewards, float* d_rec_log_probs,
+                         float* d_rec_values, int32_t* d_actions_out, void* stream);
+
+/* *d_counter += delta on the stream (one thread): advances the device-resident step number between replays. */
+int g2048_counter_add(int32_t* d_counter, int32_t delta, void* stream);
+
 /* Only the sampling part (A6/A7), for parity tests and for callers that step separately. */
 int g2048_sample_logits(const float* d_logits, const uint8_t* d_status, int use_mask, int sample,
                         const uint32_t* d_sub_act, int64_t batch_global, int64_t env_lo, int64_t n, int rng_mode,

@@ -40,6 +40,10 @@ def run_all(E, g2048, T=torch, dev="cuda"):
         acts = T.empty(n, dtype=torch.int32, device=dev)
         E.policy_step(boards, status, logits, values, True, True, True, subs[5], subs[6], 1000, 17, mode,
                       rb[0], rm[0], rr[0], rl[0], rv, acts)
+        step_index = T.zeros((), dtype=torch.int32, device=dev)
+        E.counter_add(step_index, ch - 1)  # last record slot
+        E.policy_step_at(boards, status, logits, values, True, True, True, subs[7:].contiguous(), step_index, 1000, 17, mode,
+                         rb, rm, rr, rl, T.empty((ch, n), dtype=torch.float32, device=dev))
         E.sample_logits(logits, status, True, True, subs[5], 1000, 17, mode, want_entropy=True)
         E.evaluate_logits(logits, status, True, acts)
         E.unpack_records(rm, rr, rl, None, ch, n)
