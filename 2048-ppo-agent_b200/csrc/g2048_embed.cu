@@ -263,12 +263,16 @@ static int embed_forward(bool bulk, const uint64_t* d_boards, int64_t n, const i
     return G2048_OK;
 }
 
-// Measured on B200 (tools/bench_embed.py, 2^18 boards, d_model 256): 1 KiB rows -- plain stores 6.7 TB/s, bulk copies
-// 6.0 TB/s; 512-byte rows -- bulk copies 5.9 TB/s, plain stores 4.6 TB/s.
+// Measured on B200 (tools/bench_embed.py, tools/probes/embed_flush_probe.py; 2^18 boards, d_model 256; us):
+//                        f32 rows (1 KiB)            bf16 rows (512 B)
+//                        L2 warm   after L2 flush    L2 warm   after L2 flush
+//   bulk copies            704         694             364         352
+//   plain 16-byte stores   635         880             469         652
+// The plain stores lose 40 % when L2 is full of another kernel's dirty lines (the normal state inside a training
+// step); the bulk copies do not care, so they are the product path and the plain kernel stays for A/B runs.
 extern "C" int g2048_embed_boards(const uint64_t* d_boards, int64_t n, const int64_t* d_indices, const void* d_table,
                                   int d_model, int dtype, void* d_out, void* stream) {
-    const int row_bytes = d_model * (dtype == G2048_OBS_F32 ? 4 : 2);
-    return embed_forward(row_bytes < 1024, d_boards, n, d_indices, d_table, d_model, dtype, d_out, stream);
+    return embed_forward(true, d_boards, n, d_indices, d_table, d_model, dtype, d_out, stream);
 }
 
 extern "C" int g2048_embed_boards_bulk(const uint64_t* d_boards, int64_t n, const int64_t* d_indices, const void* d_table,
