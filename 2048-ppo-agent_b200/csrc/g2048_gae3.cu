@@ -18,18 +18,37 @@
 //            microseconds ago), returns = adv + V, 128-bit streaming stores, fp64 moments.
 // Only the 4 bytes per step that the walk needs live in shared memory (6 144 steps = 26 KiB per CTA).
 // HBM traffic stays at the algorithmic 9 B read + 8 B written per step.
+#include <cstdlib>
+
 #include "g2048_common.cuh"
 
 namespace g2048 {
 
-constexpr int GAE3_THREADS = 256;
-constexpr int GAE3_VEC_PER_THREAD = 6;                          // float4 groups per thread
-constexpr int GAE3_TILE = GAE3_THREADS * GAE3_VEC_PER_THREAD * 4;  // 6144 steps
-constexpr int GAE3_CHUNKS = GAE3_TILE / 32;                     // 192 done masks of 32 steps
-constexpr int GAE3_HALF = GAE3_VEC_PER_THREAD / 2;
+// Geometry (overridable for tools/probes/probe_gae3.cu).  Throughput is (steps resident per SM) / (tile latency),
+// and the latency is set by the longest episode of a tile, not by the tile's size: what counts is how many steps'
+// deltas fit an SM's shared memory and that enough CTAs are resident to hold them.
+#ifndef GAE3_THREADS_PER_CTA
+#define GAE3_THREADS_PER_CTA 256
+#endif
+#ifndef GAE3_TILE_STEPS
+#define GAE3_TILE_STEPS 6144
+#endif
 #ifndef GAE3_MIN_CTAS
 #define GAE3_MIN_CTAS 6
 #endif
+constexpr int GAE3_THREADS = GAE3_THREADS_PER_CTA;
+constexpr int GAE3_WARPS = GAE3_THREADS / 32;
+constexpr int GAE3_TILE = GAE3_TILE_STEPS;
+constexpr int GAE3_VEC_PER_THREAD = GAE3_TILE / (4 * GAE3_THREADS);  // float4 groups per thread
+constexpr int GAE3_BLOCKS = GAE3_TILE / 128;                    // 128-step blocks: one warp-wide float4 access each
+constexpr int GAE3_INFLIGHT = (GAE3_VEC_PER_THREAD % 3 == 0) ? 3 : 2;  // float4 groups a thread loads before it computes
+constexpr int GAE3_PASSES = GAE3_VEC_PER_THREAD / GAE3_INFLIGHT;
+static_assert(GAE3_WARPS == 4 || GAE3_WARPS == 8, "four or eight warps per CTA");
+static_assert(GAE3_VEC_PER_THREAD * 4 * GAE3_THREADS == GAE3_TILE && GAE3_PASSES * GAE3_INFLIGHT == GAE3_VEC_PER_THREAD, "tile shape");
+static_assert(GAE3_BLOCKS <= 64, "the prefix warp takes at most two blocks per lane");
+// warp roles in phase 2 (rotated over the warp schedulers with the ticket)
+constexpr int GAE3_ROLE_FIRST = GAE3_WARPS == 4 ? 1 : 4, GAE3_ROLE_TAIL = GAE3_WARPS == 4 ? 2 : 5;
+constexpr int GAE3_WALK_SLOTS = GAE3_WARPS - 2;
 
 #ifdef G2048_GAE_TIMELINE  // tools/probes/probe_gae3.cu only: per-CTA phase timestamps
 __device__ long long g_gae_timeline[16 * 65536];
@@ -46,81 +65,12 @@ struct Gae3Scratch {
 };
 
 struct Gae3Smem {
-    float g[GAE3_TILE];               // delta -> advantages, in place
-    uint32_t mask[GAE3_CHUNKS];       // done bits of each 32-step chunk
-    uint32_t pref[GAE3_CHUNKS + 1];   // exclusive prefix of popc(mask)
+    float g[GAE3_TILE];                 // delta -> advantages, in place
+    uint32_t ballot[4 * GAE3_BLOCKS];   // per 128-step block: ballot j has bit l set iff step 128*b + 4*l + j is a done
+    uint32_t pref[GAE3_BLOCKS + 1];     // exclusive prefix of the blocks' done counts
     double red[4 * (GAE3_THREADS / 32)];
     unsigned int ticket;
 };
-
-// position (in the tile) of the k-th done step, k < n_done
-__device__ __forceinline__ int gae3_locate(const Gae3Smem& s, int k) {
-    int lo = 0, hi = GAE3_CHUNKS - 1;  // largest j with pref[j] <= k
-    while (lo < hi) {
-        const int mid = (lo + hi + 1) >> 1;
-        if ((int)s.pref[mid] <= k) lo = mid; else hi = mid - 1;
-    }
-    uint32_t m = s.mask[lo];
-    for (int r = k - (int)s.pref[lo]; r > 0; --r) m &= m - 1;  // drop the r lowest set bits
-    return 32 * lo + (__ffs((int)m) - 1);
-}
-
-// gae = delta + gl * gae backwards over the steps (first_excl, last], in place
-__device__ __forceinline__ void gae3_walk(float* __restrict__ sg, int last, int first_excl, float g, float gl) {
-    // keep gamma*lambda in a register: left to itself ptxas re-loads it from the constant bank at the top of
-    // every trip (LDC, ~30 cycles) and the first multiply of the serial chain waits for it
-    asm volatile("" : "+f"(gl));
-    int t = last;
-    while (t > first_excl && (t & 3) != 3) {  // down to a 16-byte boundary
-        g = sg[t] + gl * g;
-        sg[t] = g;
-        --t;
-    }
-    // 4-step groups.  Register discipline matters more than instruction count here: the STS.128 of a group
-    // holds its source registers until the (conflict-laden, queued) store is dispatched, so neither the
-    // serial chain nor the prefetching loads may write those registers soon after.  Inputs (i*, n*) and
-    // outputs (o*) therefore live in separate registers, the two input sets swap roles every half trip (no
-    // moves), and an output set is rewritten only two groups after its store was issued.
-#define GAE3_LD(at) (*reinterpret_cast<const float4*>(&sg[(at)]))
-#define GAE3_GROUP(in, out, at)                                  \
-    g = in.w + gl * g; out.w = g;                                \
-    g = in.z + gl * g; out.z = g;                                \
-    g = in.y + gl * g; out.y = g;                                \
-    g = in.x + gl * g; out.x = g;                                \
-    *reinterpret_cast<float4*>(&sg[(at)]) = out;
-    if (t - 4 >= first_excl) {                // steps t-3 .. t are all inside the episode
-        float4 i0 = GAE3_LD(t - 3), i1 = i0, n0 = i0, n1 = i0, o0, o1;
-        if (t - 8 >= first_excl) i1 = GAE3_LD(t - 7);
-        while (true) {
-            {   // consume i0, i1; fetch n0, n1 (two and three groups ahead)
-                const bool has1 = t - 8 >= first_excl, has2 = t - 12 >= first_excl;
-                if (has2) n0 = GAE3_LD(t - 11);
-                if (t - 16 >= first_excl) n1 = GAE3_LD(t - 15);
-                GAE3_GROUP(i0, o0, t - 3)
-                if (!has1) { t -= 4; break; }
-                GAE3_GROUP(i1, o1, t - 7)
-                t -= 8;
-                if (!has2) break;
-            }
-            {   // consume n0, n1; fetch i0, i1
-                const bool has1 = t - 8 >= first_excl, has2 = t - 12 >= first_excl;
-                if (has2) i0 = GAE3_LD(t - 11);
-                if (t - 16 >= first_excl) i1 = GAE3_LD(t - 15);
-                GAE3_GROUP(n0, o0, t - 3)
-                if (!has1) { t -= 4; break; }
-                GAE3_GROUP(n1, o1, t - 7)
-                t -= 8;
-                if (!has2) break;
-            }
-        }
-    }
-#undef GAE3_GROUP
-#undef GAE3_LD
-    for (; t > first_excl; --t) {
-        g = sg[t] + gl * g;
-        sg[t] = g;
-    }
-}
 
 // bits 0..7 of b -> bit positions 0, 4, 8, ..., 28
 __device__ __forceinline__ uint32_t spread_bits4(uint32_t b) {
@@ -129,6 +79,88 @@ __device__ __forceinline__ uint32_t spread_bits4(uint32_t b) {
     x = (x | (x << 6)) & 0x03030303u;
     x = (x | (x << 3)) & 0x11111111u;
     return x;
+}
+
+// position (in the tile) of the k-th done step, k < n_done.  Runs once per episode, so the bit interleave of the
+// four ballots (step order inside a block is 4*lane + component) is done here and not by every warp in phase 1.
+__device__ __forceinline__ int gae3_locate(const Gae3Smem& s, int k) {
+    int lo = 0, hi = GAE3_BLOCKS - 1;  // largest b with pref[b] <= k
+    while (lo < hi) {
+        const int mid = (lo + hi + 1) >> 1;
+        if ((int)s.pref[mid] <= k) lo = mid; else hi = mid - 1;
+    }
+    const uint32_t b0 = s.ballot[4 * lo], b1 = s.ballot[4 * lo + 1], b2 = s.ballot[4 * lo + 2], b3 = s.ballot[4 * lo + 3];
+    int r = k - (int)s.pref[lo];
+    for (int c = 0; c < 4; ++c) {  // 32 steps (8 lanes x 4 components) at a time
+        const int sh = 8 * c;
+        uint32_t m = spread_bits4(b0 >> sh) | (spread_bits4(b1 >> sh) << 1) | (spread_bits4(b2 >> sh) << 2) |
+                     (spread_bits4(b3 >> sh) << 3);
+        const int cnt = __popc(m);
+        if (r < cnt) {
+            for (; r > 0; --r) m &= m - 1;  // drop the r lowest set bits
+            return 128 * lo + 32 * c + (__ffs((int)m) - 1);
+        }
+        r -= cnt;
+    }
+    return GAE3_TILE - 1;  // not reached for k < n_done
+}
+
+// gae = delta + gl * gae backwards over the steps (first_excl, last], in place
+__device__ __forceinline__ void gae3_walk(float* __restrict__ sg, int last, int first_excl, float g, float gl_in) {
+    // gamma*lambda in a register of its own: left alone, ptxas re-loads the kernel parameter from the constant bank
+    // at the top of every trip (LDC) and the first multiply of the serial chain waits for it
+    float gl;
+    asm volatile("mov.f32 %0, %1;" : "=f"(gl) : "f"(gl_in));
+    int t = last;
+    while (t > first_excl && (t & 3) != 3) {  // down to a 16-byte boundary
+        g = sg[t] + gl * g;
+        sg[t] = g;
+        --t;
+    }
+    // 4-step groups, 16 steps per trip.  ncu on the previous form (two 8-step half trips with swapped register
+    // sets) showed ptxas merging the halves back into one 8-step body with 12 register moves and 5.5 instructions
+    // per step; here every group of the trip has its own offset and its own registers, so there is nothing to
+    // merge: 4 LDS.128 + 16 FMUL + 16 FADD + 4 STS.128 + loop control.  The loads of the second half are issued
+    // before the first half's chain, those of the next trip's first half before the second half's chain; an
+    // output set is rewritten two groups after its store was issued (STS.128 holds its sources until dispatched).
+#define GAE3_LD(at) (*reinterpret_cast<const float4*>(&sg[(at)]))
+#define GAE3_GROUP(in, out, at)                                  \
+    g = in.w + gl * g; out.w = g;                                \
+    g = in.z + gl * g; out.z = g;                                \
+    g = in.y + gl * g; out.y = g;                                \
+    g = in.x + gl * g; out.x = g;                                \
+    *reinterpret_cast<float4*>(&sg[(at)]) = out;
+    if (t - 16 >= first_excl) {  // steps t-15 .. t are all inside the episode
+        float4 a0 = GAE3_LD(t - 3), a1 = GAE3_LD(t - 7), b0, b1, o0, o1;
+#pragma unroll 1
+        do {
+            b0 = GAE3_LD(t - 11);
+            b1 = GAE3_LD(t - 15);
+            GAE3_GROUP(a0, o0, t - 3)
+            GAE3_GROUP(a1, o1, t - 7)
+            const bool more = t - 32 >= first_excl;  // another full trip follows: fetch its first half now
+            if (more) {
+                a0 = GAE3_LD(t - 19);
+                a1 = GAE3_LD(t - 23);
+            }
+            GAE3_GROUP(b0, o0, t - 11)
+            GAE3_GROUP(b1, o1, t - 15)
+            t -= 16;
+            if (!more) break;
+        } while (true);
+    }
+    while (t - 4 >= first_excl) {  // at most three groups remain
+        const float4 in = GAE3_LD(t - 3);
+        float4 out;
+        GAE3_GROUP(in, out, t - 3)
+        t -= 4;
+    }
+#undef GAE3_GROUP
+#undef GAE3_LD
+    for (; t > first_excl; --t) {
+        g = sg[t] + gl * g;
+        sg[t] = g;
+    }
 }
 
 template <bool ALIGNED>
@@ -160,7 +192,7 @@ template <bool ALIGNED>
 __global__ void __launch_bounds__(GAE3_THREADS, GAE3_MIN_CTAS)
 gae_flat3_kernel(const float* __restrict__ rewards, const float* __restrict__ values, const uint8_t* __restrict__ dones,
                  int64_t n, int64_t n_tiles, float gamma, float gamma_lambda, float* __restrict__ adv,
-                 float* __restrict__ ret, Gae3Scratch* scratch, double* __restrict__ moments) {
+                 float* __restrict__ ret, Gae3Scratch* scratch, double* __restrict__ moments, int prefetch_tiles) {
     __shared__ __align__(16) Gae3Smem s;
     volatile unsigned int* flags = (volatile unsigned int*)(scratch + 1);
     volatile float* heads = (volatile float*)((unsigned int*)(scratch + 1) + n_tiles);
@@ -173,17 +205,33 @@ gae_flat3_kernel(const float* __restrict__ rewards, const float* __restrict__ va
     const int64_t lo = tile * GAE3_TILE;
     const int len = (int)min((int64_t)GAE3_TILE, n - lo);
     GAE3_STAMP(1);
+    // Only the CTAs that are in phase 1 have loads in flight, too few bytes to keep HBM busy.  So the inputs of the
+    // tile that will be taken `prefetch_tiles` tickets from now (about when this CTA's SM slot frees up) are pulled
+    // into L2 now: phase 1 then runs at L2 latency and DRAM sees a steady stream that no CTA waits for.
+    if (prefetch_tiles > 0 && warp == GAE3_WARPS - 1) {
+        const int64_t pt = tile - prefetch_tiles;  // a full tile if it exists (only the last tile can be short)
+        if (pt >= 0) {
+            const char* pr = reinterpret_cast<const char*>(rewards + pt * GAE3_TILE);
+            const char* pv = reinterpret_cast<const char*>(values + pt * GAE3_TILE);
+            const char* pd = reinterpret_cast<const char*>(dones + pt * GAE3_TILE);
+            for (int i = lane * 128; i < GAE3_TILE * 4; i += 32 * 128) {
+                asm volatile("prefetch.global.L2 [%0];" ::"l"(pr + i));
+                asm volatile("prefetch.global.L2 [%0];" ::"l"(pv + i));
+            }
+            for (int i = lane * 128; i < GAE3_TILE; i += 32 * 128) asm volatile("prefetch.global.L2 [%0];" ::"l"(pd + i));
+        }
+    }
 
     // ---- phase 1: delta into shared memory, done bits into ordered masks --------------------------------
     // thread t owns the 4 consecutive steps 4*(q*256 + t) .. +3 of group q; a warp covers 128 steps
 #pragma unroll
-    for (int h = 0; h < 2; ++h) {
-        float4 r[GAE3_HALF], v[GAE3_HALF];
-        uint32_t d[GAE3_HALF];
-        float vnext[GAE3_HALF];
+    for (int h = 0; h < GAE3_PASSES; ++h) {
+        float4 r[GAE3_INFLIGHT], v[GAE3_INFLIGHT];
+        uint32_t d[GAE3_INFLIGHT];
+        float vnext[GAE3_INFLIGHT];
 #pragma unroll
-        for (int k = 0; k < GAE3_HALF; ++k) {
-            const int i = 4 * ((h * GAE3_HALF + k) * GAE3_THREADS + tid);
+        for (int k = 0; k < GAE3_INFLIGHT; ++k) {
+            const int i = 4 * ((h * GAE3_INFLIGHT + k) * GAE3_THREADS + tid);
             const int valid = max(0, min(4, len - i));
             r[k] = gae3_load4<ALIGNED>(rewards, lo + i, valid);
             v[k] = gae3_load4<ALIGNED>(values, lo + i, valid);
@@ -192,8 +240,8 @@ gae_flat3_kernel(const float* __restrict__ rewards, const float* __restrict__ va
             vnext[k] = (lane == 31 && lo + i + 4 < n && i + 4 <= len + 3) ? __ldg(values + lo + i + 4) : 0.0f;
         }
 #pragma unroll
-        for (int k = 0; k < GAE3_HALF; ++k) {
-            const int q = h * GAE3_HALF + k;
+        for (int k = 0; k < GAE3_INFLIGHT; ++k) {
+            const int q = h * GAE3_INFLIGHT + k;
             const int i = 4 * (q * GAE3_THREADS + tid);
             const float from_next_lane = __shfl_down_sync(0xFFFFFFFFu, v[k].x, 1);
             const float v4 = (lane == 31) ? vnext[k] : from_next_lane;  // 0 past the end of the buffer
@@ -207,40 +255,33 @@ gae_flat3_kernel(const float* __restrict__ rewards, const float* __restrict__ va
             *reinterpret_cast<float4*>(&s.g[i]) = delta;
             const uint32_t b0 = __ballot_sync(0xFFFFFFFFu, d0), b1 = __ballot_sync(0xFFFFFFFFu, d1),
                            b2 = __ballot_sync(0xFFFFFFFFu, d2), b3 = __ballot_sync(0xFFFFFFFFu, d3);
-            if (lane < 4) {  // lane c assembles the mask of the warp's c-th 32-step chunk (lanes 8c .. 8c+7)
-                const int sh = 8 * lane;
-                const uint32_t m = spread_bits4(b0 >> sh) | (spread_bits4(b1 >> sh) << 1) |
-                                   (spread_bits4(b2 >> sh) << 2) | (spread_bits4(b3 >> sh) << 3);
-                s.mask[(q * GAE3_THREADS + 32 * warp) / 8 + lane] = m;
-            }
+            if (lane < 4)  // the four ballots of this 128-step block, as they are (gae3_locate interleaves them)
+                s.ballot[4 * (q * GAE3_WARPS + warp) + lane] = lane == 0 ? b0 : (lane == 1 ? b1 : (lane == 2 ? b2 : b3));
         }
     }
     __syncthreads();
     GAE3_STAMP(2);
-    // exclusive prefix over the 192 chunk counts (one warp, 6 chunks per lane)
+    // exclusive prefix over the blocks' done counts (one warp; lane l takes blocks l and 32 + l)
     if (warp == 0) {
-        uint32_t c[GAE3_CHUNKS / 32];
-        uint32_t sum = 0;
-#pragma unroll
-        for (int q = 0; q < GAE3_CHUNKS / 32; ++q) {
-            c[q] = (uint32_t)__popc(s.mask[lane * (GAE3_CHUNKS / 32) + q]);
-            sum += c[q];
+        uint32_t c0 = 0, c1 = 0;
+        if (lane < GAE3_BLOCKS)
+            c0 = __popc(s.ballot[4 * lane]) + __popc(s.ballot[4 * lane + 1]) + __popc(s.ballot[4 * lane + 2]) + __popc(s.ballot[4 * lane + 3]);
+        if (32 + lane < GAE3_BLOCKS) {
+            const int b = 32 + lane;
+            c1 = __popc(s.ballot[4 * b]) + __popc(s.ballot[4 * b + 1]) + __popc(s.ballot[4 * b + 2]) + __popc(s.ballot[4 * b + 3]);
         }
-        uint32_t incl = sum;
+        uint32_t i0 = c0, i1 = c1;
         for (int off = 1; off < 32; off <<= 1) {
-            const uint32_t y = __shfl_up_sync(0xFFFFFFFFu, incl, off);
-            if (lane >= off) incl += y;
+            const uint32_t y0 = __shfl_up_sync(0xFFFFFFFFu, i0, off), y1 = __shfl_up_sync(0xFFFFFFFFu, i1, off);
+            if (lane >= off) { i0 += y0; i1 += y1; }
         }
-        uint32_t run = incl - sum;
-#pragma unroll
-        for (int q = 0; q < GAE3_CHUNKS / 32; ++q) {
-            s.pref[lane * (GAE3_CHUNKS / 32) + q] = run;
-            run += c[q];
-        }
-        if (lane == 31) s.pref[GAE3_CHUNKS] = incl;
+        const uint32_t total0 = __shfl_sync(0xFFFFFFFFu, i0, 31);
+        if (lane < GAE3_BLOCKS) s.pref[lane] = i0 - c0;
+        if (32 + lane < GAE3_BLOCKS) s.pref[32 + lane] = total0 + i1 - c1;
+        if (lane == 31) s.pref[GAE3_BLOCKS] = total0 + i1;
     }
     __syncthreads();
-    const int n_done = (int)s.pref[GAE3_CHUNKS];
+    const int n_done = (int)s.pref[GAE3_BLOCKS];
     GAE3_STAMP(3);
 
     // ---- phase 2: one lane per episode ---------------------------------------------------------------------
@@ -248,8 +289,9 @@ gae_flat3_kernel(const float* __restrict__ rewards, const float* __restrict__ va
     // on one scheduler (timeline probe: with fixed roles the five "warp 0" walkers of an SM shared
     // scheduler 0 and the walk ran at 35 cycles per step), so the roles rotate with the ticket.
     const int rot = (int)(s.ticket & 3u);
-    const int role = (warp < 4) ? ((warp - rot) & 3) : 4 + ((warp - rot) & 3);  // 0-3, 6-7 walk; 4 first episode; 5 tail
-    if (role == 4) {
+    // eight warps: roles 0-3, 6-7 walk, 4 first episode, 5 tail; four warps: 0 and 3 walk, 1 first episode, 2 tail
+    const int role = (warp < 4) ? ((warp - rot) & 3) : 4 + ((warp - rot) & 3);
+    if (role == GAE3_ROLE_FIRST) {
         // the first episode of the tile alone in its warp: the previous tile is waiting for its result
         if (lane == 0 && n_done > 0) {
 #ifndef G2048_GAE3_SKIP_SIDE_WALKS  // timing experiment only (tools/probes/probe_gae3.cu)
@@ -260,14 +302,14 @@ gae_flat3_kernel(const float* __restrict__ rewards, const float* __restrict__ va
             flags[tile] = 1u;
             GAE3_STAMP_ANY(8);   // first episode published
         }
-    } else if (role == 5) {
+    } else if (role == GAE3_ROLE_TAIL) {
         // the steps after the tile's last done belong to an episode that ends in a later tile
         if (lane == 31) {
             const int first_excl = n_done ? gae3_locate(s, n_done - 1) : -1;
             if (first_excl < len - 1) {
                 float carry = 0.0f;
                 if (lo + len < n) {
-                    while (flags[tile + 1] == 0u) __nanosleep(20);
+                    while (flags[tile + 1] == 0u) __nanosleep(100);
                     __threadfence();
                     carry = heads[tile + 1];
                 }
@@ -284,10 +326,16 @@ gae_flat3_kernel(const float* __restrict__ rewards, const float* __restrict__ va
             }
         }
     } else {
-        // episodes 1.. : the first 32 on the role-0 warp, the next 32 on role 1, ... (six walking roles)
-        const int slot = role < 4 ? role : role - 2;
-        for (int e = 1 + 32 * slot + lane; e < n_done; e += 6 * 32) {
-            gae3_walk(s.g, gae3_locate(s, e), gae3_locate(s, e - 1), 0.0f, gamma_lambda);
+        // episodes 1.. : the first 32 on the first walking warp, the next 32 on the second, ...
+        const int slot = GAE3_WARPS == 4 ? (role == 0 ? 0 : 1) : (role < 4 ? role : role - 2);
+        for (int base = 1 + 32 * slot; base < n_done; base += GAE3_WALK_SLOTS * 32) {  // warp-uniform
+            const int e = base + lane;
+            const int end = e < n_done ? gae3_locate(s, e) : 0;
+            int prev = __shfl_up_sync(0xFFFFFFFFu, end, 1);  // the episode before mine ends where my neighbour's does
+            if (lane == 0) prev = gae3_locate(s, base - 1);
+#ifndef G2048_GAE3_SKIP_MAIN_WALKS  // timing experiment only
+            if (e < n_done) gae3_walk(s.g, end, prev, 0.0f, gamma_lambda);
+#endif
         }
         if (slot == 0 && lane == 0) GAE3_STAMP_ANY(11);  // the first walking warp finished its episodes
     }
@@ -297,16 +345,16 @@ gae_flat3_kernel(const float* __restrict__ rewards, const float* __restrict__ va
     // ---- phase 3: returns, stores, moments -------------------------------------------------------------------
     double m[4] = {0.0, 0.0, 0.0, 0.0};
 #pragma unroll
-    for (int h = 0; h < 2; ++h) {
-        float4 v[GAE3_HALF];
+    for (int h = 0; h < GAE3_PASSES; ++h) {
+        float4 v[GAE3_INFLIGHT];
 #pragma unroll
-        for (int k = 0; k < GAE3_HALF; ++k) {
-            const int i = 4 * ((h * GAE3_HALF + k) * GAE3_THREADS + tid);
+        for (int k = 0; k < GAE3_INFLIGHT; ++k) {
+            const int i = 4 * ((h * GAE3_INFLIGHT + k) * GAE3_THREADS + tid);
             v[k] = gae3_load4<ALIGNED>(values, lo + i, max(0, min(4, len - i)));  // L2 hit
         }
 #pragma unroll
-        for (int k = 0; k < GAE3_HALF; ++k) {
-            const int i = 4 * ((h * GAE3_HALF + k) * GAE3_THREADS + tid);
+        for (int k = 0; k < GAE3_INFLIGHT; ++k) {
+            const int i = 4 * ((h * GAE3_INFLIGHT + k) * GAE3_THREADS + tid);
             const int valid = max(0, min(4, len - i));
             if (valid > 0) {
                 const float4 a = *reinterpret_cast<const float4*>(&s.g[i]);
@@ -325,10 +373,13 @@ gae_flat3_kernel(const float* __restrict__ rewards, const float* __restrict__ va
 #pragma unroll
                 for (int j = 0; j < 4; ++j) {
                     if (j < valid) {
-                        m[0] += (double)aa[j];
-                        m[1] += (double)aa[j] * (double)aa[j];
-                        m[2] += (double)rr[j];
-                        m[3] += (double)rr[j] * (double)rr[j];
+#ifndef G2048_GAE3_SKIP_MOMENTS  // timing experiment only
+                        const double da = (double)aa[j], dr = (double)rr[j];
+                        m[0] += da;
+                        m[1] = __fma_rn(da, da, m[1]);  // the product of two floats is exact in double either way
+                        m[2] += dr;
+                        m[3] = __fma_rn(dr, dr, m[3]);
+#endif
                     }
                 }
             }
@@ -376,14 +427,24 @@ extern "C" int g2048_gae_flat(const float* d_rewards, const float* d_values, con
         configured = true;
     }
     cudaStream_t st = (cudaStream_t)stream;
+    // prefetch distance in tiles (G2048_GAE_PREFETCH overrides, 0 = off).  Swept on B200 with tools/probes/probe_gae3.cu
+    // at 2^26 steps: 0 -> 334 us, SMs/2 = 74 -> 312 us, 148 -> 315, 296 -> 320, 444 -> 338, 888 -> 372 (too early:
+    // the lines are gone again before their tile starts)
+    static int prefetch_tiles = -1;
+    if (prefetch_tiles < 0) {
+        const char* env = getenv("G2048_GAE_PREFETCH");
+        const int sms = sm_count();
+        prefetch_tiles = env ? atoi(env) : (sms > 0 ? sms / 2 : 0);
+        if (prefetch_tiles < 0) prefetch_tiles = 0;
+    }
     if (aligned) {
         gae_flat3_kernel<true><<<(unsigned)n_tiles, GAE3_THREADS, 0, st>>>(
             d_rewards, d_values, d_dones, n, n_tiles, (float)gamma, (float)(gamma * lambda_gae), d_adv, d_ret,
-            (Gae3Scratch*)d_scan_state, d_moments);
+            (Gae3Scratch*)d_scan_state, d_moments, prefetch_tiles);
     } else {
         gae_flat3_kernel<false><<<(unsigned)n_tiles, GAE3_THREADS, 0, st>>>(
             d_rewards, d_values, d_dones, n, n_tiles, (float)gamma, (float)(gamma * lambda_gae), d_adv, d_ret,
-            (Gae3Scratch*)d_scan_state, d_moments);
+            (Gae3Scratch*)d_scan_state, d_moments, prefetch_tiles);
     }
     G2048_CHECK_LAUNCH("gae_flat");
     return G2048_OK;
