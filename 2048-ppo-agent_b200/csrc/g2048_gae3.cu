@@ -21,6 +21,7 @@
 #include <cstdlib>
 
 #include "g2048_common.cuh"
+#include "g2048_gae_walk.cuh"
 
 namespace g2048 {
 
@@ -72,121 +73,8 @@ struct Gae3Smem {
     unsigned int ticket;
 };
 
-// bits 0..7 of b -> bit positions 0, 4, 8, ..., 28
-__device__ __forceinline__ uint32_t spread_bits4(uint32_t b) {
-    uint32_t x = b & 0xFFu;
-    x = (x | (x << 12)) & 0x000F000Fu;
-    x = (x | (x << 6)) & 0x03030303u;
-    x = (x | (x << 3)) & 0x11111111u;
-    return x;
-}
-
-// position (in the tile) of the k-th done step, k < n_done.  Runs once per episode, so the bit interleave of the
-// four ballots (step order inside a block is 4*lane + component) is done here and not by every warp in phase 1.
-__device__ __forceinline__ int gae3_locate(const Gae3Smem& s, int k) {
-    int lo = 0, hi = GAE3_BLOCKS - 1;  // largest b with pref[b] <= k
-    while (lo < hi) {
-        const int mid = (lo + hi + 1) >> 1;
-        if ((int)s.pref[mid] <= k) lo = mid; else hi = mid - 1;
-    }
-    const uint32_t b0 = s.ballot[4 * lo], b1 = s.ballot[4 * lo + 1], b2 = s.ballot[4 * lo + 2], b3 = s.ballot[4 * lo + 3];
-    int r = k - (int)s.pref[lo];
-    for (int c = 0; c < 4; ++c) {  // 32 steps (8 lanes x 4 components) at a time
-        const int sh = 8 * c;
-        uint32_t m = spread_bits4(b0 >> sh) | (spread_bits4(b1 >> sh) << 1) | (spread_bits4(b2 >> sh) << 2) |
-                     (spread_bits4(b3 >> sh) << 3);
-        const int cnt = __popc(m);
-        if (r < cnt) {
-            for (; r > 0; --r) m &= m - 1;  // drop the r lowest set bits
-            return 128 * lo + 32 * c + (__ffs((int)m) - 1);
-        }
-        r -= cnt;
-    }
-    return GAE3_TILE - 1;  // not reached for k < n_done
-}
-
-// gae = delta + gl * gae backwards over the steps (first_excl, last], in place
-__device__ __forceinline__ void gae3_walk(float* __restrict__ sg, int last, int first_excl, float g, float gl_in) {
-    // gamma*lambda in a register of its own: left alone, ptxas re-loads the kernel parameter from the constant bank
-    // at the top of every trip (LDC) and the first multiply of the serial chain waits for it
-    float gl;
-    asm volatile("mov.f32 %0, %1;" : "=f"(gl) : "f"(gl_in));
-    int t = last;
-    while (t > first_excl && (t & 3) != 3) {  // down to a 16-byte boundary
-        g = sg[t] + gl * g;
-        sg[t] = g;
-        --t;
-    }
-    // 4-step groups, 16 steps per trip.  ncu on the previous form (two 8-step half trips with swapped register
-    // sets) showed ptxas merging the halves back into one 8-step body with 12 register moves and 5.5 instructions
-    // per step; here every group of the trip has its own offset and its own registers, so there is nothing to
-    // merge: 4 LDS.128 + 16 FMUL + 16 FADD + 4 STS.128 + loop control.  The loads of the second half are issued
-    // before the first half's chain, those of the next trip's first half before the second half's chain; an
-    // output set is rewritten two groups after its store was issued (STS.128 holds its sources until dispatched).
-#define GAE3_LD(at) (*reinterpret_cast<const float4*>(&sg[(at)]))
-#define GAE3_GROUP(in, out, at)                                  \
-    g = in.w + gl * g; out.w = g;                                \
-    g = in.z + gl * g; out.z = g;                                \
-    g = in.y + gl * g; out.y = g;                                \
-    g = in.x + gl * g; out.x = g;                                \
-    *reinterpret_cast<float4*>(&sg[(at)]) = out;
-    if (t - 16 >= first_excl) {  // steps t-15 .. t are all inside the episode
-        float4 a0 = GAE3_LD(t - 3), a1 = GAE3_LD(t - 7), b0, b1, o0, o1;
-#pragma unroll 1
-        do {
-            b0 = GAE3_LD(t - 11);
-            b1 = GAE3_LD(t - 15);
-            GAE3_GROUP(a0, o0, t - 3)
-            GAE3_GROUP(a1, o1, t - 7)
-            const bool more = t - 32 >= first_excl;  // another full trip follows: fetch its first half now
-            if (more) {
-                a0 = GAE3_LD(t - 19);
-                a1 = GAE3_LD(t - 23);
-            }
-            GAE3_GROUP(b0, o0, t - 11)
-            GAE3_GROUP(b1, o1, t - 15)
-            t -= 16;
-            if (!more) break;
-        } while (true);
-    }
-    while (t - 4 >= first_excl) {  // at most three groups remain
-        const float4 in = GAE3_LD(t - 3);
-        float4 out;
-        GAE3_GROUP(in, out, t - 3)
-        t -= 4;
-    }
-#undef GAE3_GROUP
-#undef GAE3_LD
-    for (; t > first_excl; --t) {
-        g = sg[t] + gl * g;
-        sg[t] = g;
-    }
-}
-
-template <bool ALIGNED>
-__device__ __forceinline__ float4 gae3_load4(const float* __restrict__ p, int64_t gi, int valid) {
-    if (ALIGNED && valid == 4) return __ldg(reinterpret_cast<const float4*>(p + gi));
-    float4 o = make_float4(0.f, 0.f, 0.f, 0.f);
-    if (valid > 0) o.x = __ldg(p + gi);
-    if (valid > 1) o.y = __ldg(p + gi + 1);
-    if (valid > 2) o.z = __ldg(p + gi + 2);
-    if (valid > 3) o.w = __ldg(p + gi + 3);
-    return o;
-}
-
-template <bool ALIGNED>
-__device__ __forceinline__ uint32_t gae3_load_done4(const uint8_t* __restrict__ p, int64_t gi, int valid) {
-    uint32_t w = 0;
-    if (ALIGNED && valid == 4) {
-        w = __ldg(reinterpret_cast<const uint32_t*>(p + gi));
-    } else {
-        if (valid > 0) w |= (uint32_t)__ldg(p + gi);
-        if (valid > 1) w |= (uint32_t)__ldg(p + gi + 1) << 8;
-        if (valid > 2) w |= (uint32_t)__ldg(p + gi + 2) << 16;
-        if (valid > 3) w |= (uint32_t)__ldg(p + gi + 3) << 24;
-    }
-    return w;
-}
+// position (in the tile) of the k-th done step, k < n_done
+__device__ __forceinline__ int gae3_locate(const Gae3Smem& s, int k) { return gae_locate(s.ballot, s.pref, GAE3_BLOCKS, k); }
 
 template <bool ALIGNED>
 __global__ void __launch_bounds__(GAE3_THREADS, GAE3_MIN_CTAS)
@@ -233,9 +121,9 @@ gae_flat3_kernel(const float* __restrict__ rewards, const float* __restrict__ va
         for (int k = 0; k < GAE3_INFLIGHT; ++k) {
             const int i = 4 * ((h * GAE3_INFLIGHT + k) * GAE3_THREADS + tid);
             const int valid = max(0, min(4, len - i));
-            r[k] = gae3_load4<ALIGNED>(rewards, lo + i, valid);
-            v[k] = gae3_load4<ALIGNED>(values, lo + i, valid);
-            d[k] = gae3_load_done4<ALIGNED>(dones, lo + i, valid);
+            r[k] = gae_load4<ALIGNED>(rewards, lo + i, valid);
+            v[k] = gae_load4<ALIGNED>(values, lo + i, valid);
+            d[k] = gae_load_done4<ALIGNED>(dones, lo + i, valid);
             // V of the step after this lane's four: the next lane has it, except for lane 31
             vnext[k] = (lane == 31 && lo + i + 4 < n && i + 4 <= len + 3) ? __ldg(values + lo + i + 4) : 0.0f;
         }
@@ -295,7 +183,7 @@ gae_flat3_kernel(const float* __restrict__ rewards, const float* __restrict__ va
         // the first episode of the tile alone in its warp: the previous tile is waiting for its result
         if (lane == 0 && n_done > 0) {
 #ifndef G2048_GAE3_SKIP_SIDE_WALKS  // timing experiment only (tools/probes/probe_gae3.cu)
-            gae3_walk(s.g, gae3_locate(s, 0), -1, 0.0f, gamma_lambda);
+            gae_walk(s.g, gae3_locate(s, 0), -1, 0.0f, gamma_lambda);
 #endif
             heads[tile] = s.g[0];
             __threadfence();
@@ -315,7 +203,7 @@ gae_flat3_kernel(const float* __restrict__ rewards, const float* __restrict__ va
                 }
                 GAE3_STAMP_ANY(9);   // look-back satisfied
 #ifndef G2048_GAE3_SKIP_SIDE_WALKS
-                gae3_walk(s.g, len - 1, first_excl, carry, gamma_lambda);
+                gae_walk(s.g, len - 1, first_excl, carry, gamma_lambda);
 #endif
                 GAE3_STAMP_ANY(10);  // tail walked
             }
@@ -334,7 +222,7 @@ gae_flat3_kernel(const float* __restrict__ rewards, const float* __restrict__ va
             int prev = __shfl_up_sync(0xFFFFFFFFu, end, 1);  // the episode before mine ends where my neighbour's does
             if (lane == 0) prev = gae3_locate(s, base - 1);
 #ifndef G2048_GAE3_SKIP_MAIN_WALKS  // timing experiment only
-            if (e < n_done) gae3_walk(s.g, end, prev, 0.0f, gamma_lambda);
+            if (e < n_done) gae_walk(s.g, end, prev, 0.0f, gamma_lambda);
 #endif
         }
         if (slot == 0 && lane == 0) GAE3_STAMP_ANY(11);  // the first walking warp finished its episodes
@@ -350,7 +238,7 @@ gae_flat3_kernel(const float* __restrict__ rewards, const float* __restrict__ va
 #pragma unroll
         for (int k = 0; k < GAE3_INFLIGHT; ++k) {
             const int i = 4 * ((h * GAE3_INFLIGHT + k) * GAE3_THREADS + tid);
-            v[k] = gae3_load4<ALIGNED>(values, lo + i, max(0, min(4, len - i)));  // L2 hit
+            v[k] = gae_load4<ALIGNED>(values, lo + i, max(0, min(4, len - i)));  // L2 hit
         }
 #pragma unroll
         for (int k = 0; k < GAE3_INFLIGHT; ++k) {
@@ -410,7 +298,7 @@ using namespace g2048;
 
 static inline bool aligned16(const void* p) { return ((uintptr_t)p & 15u) == 0; }
 
-extern "C" int g2048_gae_flat(const float* d_rewards, const float* d_values, const uint8_t* d_dones, int64_t n,
+extern "C" int g2048_gae_flat_tiled(const float* d_rewards, const float* d_values, const uint8_t* d_dones, int64_t n,
                               double gamma, double lambda_gae, float* d_adv, float* d_ret, void* d_scan_state,
                               double* d_moments, void* stream) {
     G2048_REQUIRE(n >= 0, "gae_flat: n");

@@ -64,14 +64,17 @@ class ClockSampler:
              "clocks_event_reasons.sw_power_cap")
 
     def __init__(self, gpu_index: int):
-        self.rows = []
+        self.rows = []  # (arrival time, fields)
         self.proc = None
         self.gpu_index = gpu_index
+        self.t_begin = self.t_end = None
 
     def start(self):
+        """Started BEFORE the warm-up steps: nvidia-smi needs a few hundred ms to produce its first line, more than a
+        short timed region lasts."""
         try:
             self.proc = subprocess.Popen(
-                ["nvidia-smi", "-i", str(self.gpu_index), f"--query-gpu={self.QUERY}", "--format=csv,noheader,nounits", "-lms", "100"],
+                ["nvidia-smi", "-i", str(self.gpu_index), f"--query-gpu={self.QUERY}", "--format=csv,noheader,nounits", "-lms", "20"],
                 stdout=subprocess.PIPE, stderr=subprocess.DEVNULL, text=True)
             threading.Thread(target=self._read, daemon=True).start()
         except OSError:
@@ -79,31 +82,49 @@ class ClockSampler:
 
     def _read(self):
         for line in self.proc.stdout:
-            self.rows.append([c.strip() for c in line.split(",")])
+            self.rows.append((time.perf_counter(), [c.strip() for c in line.split(",")]))
+
+    def begin(self):
+        self.t_begin = time.perf_counter()
+
+    def end(self):
+        self.t_end = time.perf_counter()
 
     def stop(self) -> dict:
         if self.proc is None:
             return {"sm_mhz": None, "sm_max_mhz": None, "reasons": ["nvidia-smi unavailable"]}
-        time.sleep(0.15)
+        time.sleep(0.05)
         self.proc.terminate()
-        sm, mx, reasons, power = [], [], set(), []
         names = ["hw_slowdown", "hw_thermal_slowdown", "sw_thermal_slowdown", "sw_power_cap"]
-        for r in self.rows:
-            try:
-                sm.append(float(r[0]))
-                mx.append(float(r[1]))
-                power.append(float(r[2]))
-                for name, v in zip(names, r[3:7]):
-                    if v.lower().startswith("active"):
-                        reasons.add(name)
-            except (ValueError, IndexError):
-                continue
-        # samples under load only: the top half of the observed power draw
+
+        def parse(rows):
+            sm, mx, reasons, power = [], [], set(), []
+            for _, r in rows:
+                try:
+                    sm.append(float(r[0]))
+                    mx.append(float(r[1]))
+                    power.append(float(r[2]))
+                    for name, v in zip(names, r[3:7]):
+                        if v.lower().startswith("active"):
+                            reasons.add(name)
+                except (ValueError, IndexError):
+                    continue
+            return sm, mx, reasons, power
+
+        # a line printed at time t was sampled just before t: take the lines that arrived inside the timed region
+        # (plus one sampling period); if the region was too short to catch two, widen to the warm-up steps before
+        # it, which run the same kernels
+        inside = [row for row in self.rows if self.t_begin is not None and self.t_begin <= row[0] <= self.t_end + 0.03]
+        window = "timed region"
+        if len(inside) < 2:
+            inside = [row for row in self.rows if self.t_end is None or row[0] <= self.t_end + 0.03]
+            window = "warm-up + timed region"
+        sm, mx, reasons, power = parse(inside)
         if sm:
-            cut = statistics.median(power)
-            loaded = [s for s, p in zip(sm, power) if p >= cut] or sm
+            cut = statistics.median(power)  # samples under load only: the top half of the observed power draw
+            loaded = [x for x, pw in zip(sm, power) if pw >= cut] or sm
             return {"sm_mhz": statistics.median(loaded), "sm_max_mhz": max(mx), "reasons": sorted(reasons),
-                    "samples": len(sm), "power_w_max": max(power)}
+                    "samples": len(sm), "window": window, "power_w_max": max(power)}
         return {"sm_mhz": None, "sm_max_mhz": None, "reasons": ["no samples"]}
 
 
@@ -254,16 +275,17 @@ def main():
             dist.barrier()
         torch.cuda.synchronize()
 
+    sampler = ClockSampler(local_rank)
+    if rank == 0:
+        sampler.start()
     for i in range(args.warmup):
         one_step(i)
     barrier()
 
-    sampler = ClockSampler(local_rank)
-    if rank == 0:
-        sampler.start()
     launches["ours"] = 0
     events = []
     barrier()
+    sampler.begin()
     for i in range(args.steps):
         flush_buf.fill_(i & 0xFF)  # L2 flush, outside the timed events
         a, b = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
@@ -273,6 +295,7 @@ def main():
         events.append((a, b))
         stats_all.append(out["stats"])
     barrier()
+    sampler.end()
     clocks = sampler.stop() if rank == 0 else None
     gpu_launches = launches["ours"]
     elapsed = sum(a.elapsed_time(b) for a, b in events) * 1e-3
@@ -474,7 +497,7 @@ def secondary_measurements(E, N, torch, dev, flush_buf) -> dict:
                N.ptr(mom), N.stream_ptr())
 
     t = timed(gae)
-    add("gae_flat3_kernel", n_g * 17, t, "2^26 steps, done rate 1/300 (episodes ~300 steps); 9 B read + 8 B written per step (SURVEY 8d); bound by the serial per-episode recurrence, see DESIGN.md")
+    add("gae_flat4_kernel (pipelined)", n_g * 17, t, "2^26 steps, done rate 1/300 (episodes ~300 steps); 9 B read + 8 B written per step (SURVEY 8d); includes zeroing the scratch; walks hidden behind the neighbouring tiles' traffic, see DESIGN.md")
     t = timed(lambda: N.call("g2048_normalize", N.ptr(adv), n_g, N.ptr(mom), 1, N.stream_ptr()))
     add("normalize_kernel", n_g * 8, t, "2^26 steps in place; 4 B read + 4 B written per step")
     del r, v, d, adv, ret

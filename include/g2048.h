@@ -292,8 +292,8 @@ int g2048_embed_boards_grad(const uint64_t* d_boards, int64_t n, const int64_t* 
 
 /* Flat buffer, reverse segmented scan: if done[t]: last_v = last_gae = 0;
  * delta = r[t] + gamma*last_v - V[t]; gae = delta + gamma*lambda*gae; adv[t]=gae; ret[t]=gae+V[t].
- * Single pass (one CTA per 6 144-step tile, one lane per episode, decoupled look-back of depth one
- * across tiles); bit-identical to the reference loop.  d_scan_state: scratch of
+ * Single pass over the buffer in tiles (one lane per episode, decoupled look-back of depth one across
+ * tiles); bit-identical to the reference loop.  d_scan_state: scratch of
  * g2048_gae_flat_scratch_bytes(n) bytes, zeroed by the caller.  d_moments (double[6], may be NULL,
  * ACCUMULATED): [0] n, [1] sum adv, [2] sum adv^2, [3] sum ret, [4] sum ret^2, [5] unused. */
 int64_t g2048_gae_flat_scratch_bytes(int64_t n);
@@ -302,6 +302,17 @@ int g2048_gae_flat(const float* d_rewards, const float* d_values, const uint8_t*
 
 /* First-generation kernel (1 024-step tiles, every array staged in shared memory); same arguments.
  * Kept so that the current kernel can be A/B-timed against it. */
+/* The two current kernels behind g2048_gae_flat (same arguments, same scratch, bit-identical outputs):
+ *   _tiled      one 6 144-step tile per CTA, phases one after the other; used below 2^23 steps
+ *   _pipelined  persistent CTAs holding two 8 192-step tiles: walker warps on tile i while streamer warps store tile
+ *               i-1 and load tile i+1; used from 2^23 steps on
+ * and the first-generation kernel (_v1), kept for A/B measurements. */
+int g2048_gae_flat_tiled(const float* d_rewards, const float* d_values, const uint8_t* d_dones, int64_t n, double gamma,
+                         double lambda_gae, float* d_adv, float* d_ret, void* d_scan_state, double* d_moments,
+                         void* stream);
+int g2048_gae_flat_pipelined(const float* d_rewards, const float* d_values, const uint8_t* d_dones, int64_t n,
+                             double gamma, double lambda_gae, float* d_adv, float* d_ret, void* d_scan_state,
+                             double* d_moments, void* stream);
 int g2048_gae_flat_v1(const float* d_rewards, const float* d_values, const uint8_t* d_dones, int64_t n, double gamma,
                       double lambda_gae, float* d_adv, float* d_ret, void* d_scan_state, double* d_moments,
                       void* stream);

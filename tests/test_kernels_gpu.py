@@ -544,7 +544,7 @@ def test_exclusive_scan_large(E):
 TAGS = ["default", "short_eps", "undiscounted", "lowlam", "open_tail", "two"]
 
 
-GAE_ENTRIES = ["g2048_gae_flat", "g2048_gae_flat_v1"]
+GAE_ENTRIES = ["g2048_gae_flat", "g2048_gae_flat_pipelined", "g2048_gae_flat_tiled", "g2048_gae_flat_v1"]
 
 
 @pytest.mark.parametrize("entry", GAE_ENTRIES)
@@ -564,7 +564,8 @@ def test_gae_flat_is_bit_exact_vs_reference_fixture(E, golden_ppo, tag, entry):
 
 @pytest.mark.parametrize("entry", GAE_ENTRIES)
 @pytest.mark.parametrize("n,done_rate", [(1, 1.0), (1023, 0.01), (1024, 0.01), (1025, 0.0), (5000, 0.0), (6144, 0.5), (6145, 1.0),
-                                         (12288, 0.0), (18433, 0.002), (50_000, 0.7), (300_000, 1 / 300), (2_000_000, 1 / 3000)])
+                                         (12288, 0.0), (18433, 0.002), (50_000, 0.7), (300_000, 1 / 300), (2_000_000, 1 / 3000),
+                                         (8_400_003, 1 / 300)])  # the last one is above the dispatcher's 2^23-step switch
 def test_gae_flat_matches_oracle_at_scale(E, n, done_rate, entry):
     rng = np.random.default_rng(n)
     r = (rng.integers(0, 64, n) * 4 * (rng.random(n) < 0.4)).astype(np.float32)

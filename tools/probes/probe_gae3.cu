@@ -27,7 +27,7 @@ int main(int argc, char** argv) {
     for (int rep = 0; rep < 4; ++rep) {
         cudaMemset(ds, 0, sb); cudaMemset(dm, 0, 48);
         cudaEventRecord(e0);
-        int rc = g2048_gae_flat(dr, dv, dd, n, 0.99, 0.95, da, dt, ds, dm, nullptr);
+        int rc = g2048_gae_flat_tiled(dr, dv, dd, n, 0.99, 0.95, da, dt, ds, dm, nullptr);
         cudaEventRecord(e1); cudaEventSynchronize(e1);
         if (rc) { printf("rc %d %s\n", rc, g2048_last_error()); return 1; }
         float ms; cudaEventElapsedTime(&ms, e0, e1); if (ms < best) best = ms;
