@@ -25,7 +25,11 @@ namespace g2048 {
 #endif
 constexpr int G4_STREAM_THREADS = G4_STREAMERS;
 constexpr int G4_STREAM_WARPS = G4_STREAM_THREADS / 32;
-constexpr int G4_WALK_WARPS = 4;
+#ifndef G4_WALKER_WARPS
+#define G4_WALKER_WARPS 4
+#endif
+constexpr int G4_WALK_WARPS = G4_WALKER_WARPS;  // 4: two for whole episodes, first episode, tail; 2: whole episodes, first episode then tail
+static_assert(G4_WALK_WARPS == 4 || G4_WALK_WARPS == 2, "two or four walker warps");
 constexpr int G4_THREADS = G4_STREAM_THREADS + 32 * G4_WALK_WARPS;  // 384
 #ifndef G4_TILE_STEPS
 #define G4_TILE_STEPS 8192
@@ -73,6 +77,7 @@ __device__ __forceinline__ void g4_load_tile(G4Stage& st, int64_t tile, const fl
     const int lane = tid & 31, warp = tid >> 5;
     const int64_t lo = tile * G4_TILE;
     const int len = (int)min((int64_t)G4_TILE, n - lo);
+    const uint64_t keep = l2_policy_evict_last(), once = l2_policy_evict_first();
 #pragma unroll
     for (int h = 0; h < G4_PASSES; ++h) {
         float4 r[G4_INFLIGHT], v[G4_INFLIGHT];
@@ -82,8 +87,8 @@ __device__ __forceinline__ void g4_load_tile(G4Stage& st, int64_t tile, const fl
         for (int k = 0; k < G4_INFLIGHT; ++k) {
             const int i = 4 * ((h * G4_INFLIGHT + k) * G4_STREAM_THREADS + tid);
             const int valid = max(0, min(4, len - i));
-            r[k] = gae_load4<ALIGNED>(rewards, lo + i, valid);
-            v[k] = gae_load4<ALIGNED>(values, lo + i, valid);
+            r[k] = gae_load4_hint<ALIGNED>(rewards, lo + i, valid, once);
+            v[k] = gae_load4_hint<ALIGNED>(values, lo + i, valid, keep);  // read again when the tile is stored
             d[k] = gae_load_done4<ALIGNED>(dones, lo + i, valid);
             // V of the step after this lane's four: the next lane has it, except for lane 31
             vnext[k] = (lane == 31 && lo + i + 4 < n && i + 4 <= len + 3) ? __ldg(values + lo + i + 4) : 0.0f;
@@ -138,13 +143,14 @@ __device__ __forceinline__ void g4_store_tile(const G4Stage& st, int64_t tile, c
                                               float* __restrict__ adv, float* __restrict__ ret, double (&m)[4], int tid) {
     const int64_t lo = tile * G4_TILE;
     const int len = (int)min((int64_t)G4_TILE, n - lo);
+    const uint64_t once = l2_policy_evict_first();
 #pragma unroll
     for (int h = 0; h < G4_PASSES; ++h) {
         float4 v[G4_INFLIGHT];
 #pragma unroll
         for (int k = 0; k < G4_INFLIGHT; ++k) {
             const int i = 4 * ((h * G4_INFLIGHT + k) * G4_STREAM_THREADS + tid);
-            v[k] = gae_load4<ALIGNED>(values, lo + i, max(0, min(4, len - i)));
+            v[k] = gae_load4_hint<ALIGNED>(values, lo + i, max(0, min(4, len - i)), once);  // last use of the line
         }
 #pragma unroll
         for (int k = 0; k < G4_INFLIGHT; ++k) {
@@ -184,40 +190,45 @@ __device__ __forceinline__ void g4_walk_tile(G4Stage& st, int64_t tile, int64_t 
     const int64_t lo = tile * G4_TILE;
     const int len = (int)min((int64_t)G4_TILE, n - lo);
     const int n_done = (int)st.pref[G4_BLOCKS];
-    if (wwarp == 1) {
-        // the first episode of the tile alone in its warp: the previous tile is waiting for its result
-        if (lane == 0 && n_done > 0) {
-#ifndef G4_SKIP_WALKS  // timing experiment only (tools/probes/probe_gae4.cu)
-            gae_walk(st.g, gae_locate(st.ballot, st.pref, G4_BLOCKS, 0), -1, 0.0f, gamma_lambda);
-#endif
-            heads[tile] = st.g[0];
-            __threadfence();
-            flags[tile] = 1u;
-        }
-    } else if (wwarp == 2) {
-        // the steps after the tile's last done belong to an episode that ends in a later tile
+    const bool does_first = wwarp == 1, does_tail = G4_WALK_WARPS == 4 ? wwarp == 2 : wwarp == 1;
+    if (does_first || does_tail) {
         if (lane == 0) {
-            const int first_excl = n_done ? gae_locate(st.ballot, st.pref, G4_BLOCKS, n_done - 1) : -1;
-            if (first_excl < len - 1) {
-                float carry = 0.0f;
-                if (lo + len < n) {
-                    while (flags[tile + 1] == 0u) __nanosleep(100);
-                    __threadfence();
-                    carry = heads[tile + 1];
-                }
-#ifndef G4_SKIP_WALKS
-                gae_walk(st.g, len - 1, first_excl, carry, gamma_lambda);
+            // the first episode of the tile: the previous tile is waiting for its result
+            if (does_first && n_done > 0) {
+#ifndef G4_SKIP_WALKS  // timing experiment only (tools/probes/probe_gae4.cu)
+                gae_walk(st.g, gae_locate(st.ballot, st.pref, G4_BLOCKS, 0), -1, 0.0f, gamma_lambda);
 #endif
-            }
-            if (n_done == 0) {
                 heads[tile] = st.g[0];
                 __threadfence();
                 flags[tile] = 1u;
             }
+            // the steps after the tile's last done belong to an episode that ends in a later tile
+            if (does_tail) {
+                const int first_excl = n_done ? gae_locate(st.ballot, st.pref, G4_BLOCKS, n_done - 1) : -1;
+                if (first_excl < len - 1) {
+                    float carry = 0.0f;
+                    if (lo + len < n) {
+                        while (flags[tile + 1] == 0u) __nanosleep(100);
+                        __threadfence();
+                        carry = heads[tile + 1];
+                    }
+#ifndef G4_SKIP_WALKS
+                    gae_walk(st.g, len - 1, first_excl, carry, gamma_lambda);
+#else
+                    (void)carry;
+#endif
+                }
+                if (n_done == 0) {
+                    heads[tile] = st.g[0];
+                    __threadfence();
+                    flags[tile] = 1u;
+                }
+            }
         }
     } else {
+        constexpr int slots = G4_WALK_WARPS == 4 ? 2 : 1;
         const int slot = wwarp == 0 ? 0 : 1;
-        for (int base = 1 + 32 * slot; base < n_done; base += 2 * 32) {  // warp-uniform
+        for (int base = 1 + 32 * slot; base < n_done; base += slots * 32) {  // warp-uniform
             const int e = base + lane;
             const int end = e < n_done ? gae_locate(st.ballot, st.pref, G4_BLOCKS, e) : 0;
             int prev = __shfl_up_sync(0xFFFFFFFFu, end, 1);  // the episode before mine ends where my neighbour's does
@@ -253,7 +264,7 @@ gae_flat4_kernel(const float* __restrict__ rewards, const float* __restrict__ va
         const char* pd = reinterpret_cast<const char*>(dones + pt * G4_TILE);
         for (int i = lane * 128; i < G4_TILE * 4; i += 32 * 128) {
             asm volatile("prefetch.global.L2 [%0];" ::"l"(pr + i));
-            asm volatile("prefetch.global.L2 [%0];" ::"l"(pv + i));
+            asm volatile("prefetch.global.L2::evict_last [%0];" ::"l"(pv + i));
         }
         for (int i = lane * 128; i < G4_TILE; i += 32 * 128) asm volatile("prefetch.global.L2 [%0];" ::"l"(pd + i));
     };
@@ -376,6 +387,7 @@ extern "C" int g2048_gae_flat_pipelined(const float* d_rewards, const float* d_v
 //   steps        2^20   2^22   2^24   2^26
 //   tiled        30.6   35.1  109.1  312
 //   pipelined    33.3   40.4   88.6  269
+#ifndef G2048_GAE4_NO_DISPATCH  // tools/probes/probe_gae4.cu builds this file alone
 extern "C" int g2048_gae_flat_tiled(const float* d_rewards, const float* d_values, const uint8_t* d_dones, int64_t n,
                                     double gamma, double lambda_gae, float* d_adv, float* d_ret, void* d_scan_state,
                                     double* d_moments, void* stream);
@@ -387,3 +399,4 @@ extern "C" int g2048_gae_flat(const float* d_rewards, const float* d_values, con
         return g2048_gae_flat_pipelined(d_rewards, d_values, d_dones, n, gamma, lambda_gae, d_adv, d_ret, d_scan_state, d_moments, stream);
     return g2048_gae_flat_tiled(d_rewards, d_values, d_dones, n, gamma, lambda_gae, d_adv, d_ret, d_scan_state, d_moments, stream);
 }
+#endif

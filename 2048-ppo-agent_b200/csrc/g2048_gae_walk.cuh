@@ -109,6 +109,32 @@ __device__ __forceinline__ float4 gae_load4(const float* __restrict__ p, int64_t
     return o;
 }
 
+// L2 eviction policies (createpolicy): V is read twice, once for delta and about one pipeline iteration later for
+// ret = adv + V; ncu showed two thirds of the second reads going back to DRAM (11.6 B read per step instead of 9),
+// so V is loaded "evict last" the first time and "evict first" the second, like the streams that are read once.
+__device__ __forceinline__ uint64_t l2_policy_evict_last() {
+    uint64_t p;
+    asm volatile("createpolicy.fractional.L2::evict_last.b64 %0, 1.0;" : "=l"(p));
+    return p;
+}
+__device__ __forceinline__ uint64_t l2_policy_evict_first() {
+    uint64_t p;
+    asm volatile("createpolicy.fractional.L2::evict_first.b64 %0, 1.0;" : "=l"(p));
+    return p;
+}
+
+template <bool ALIGNED>
+__device__ __forceinline__ float4 gae_load4_hint(const float* __restrict__ p, int64_t gi, int valid, uint64_t policy) {
+    if (ALIGNED && valid == 4) {
+        float4 o;
+        asm volatile("ld.global.L2::cache_hint.v4.f32 {%0, %1, %2, %3}, [%4], %5;"
+                     : "=f"(o.x), "=f"(o.y), "=f"(o.z), "=f"(o.w)
+                     : "l"(p + gi), "l"(policy));
+        return o;
+    }
+    return gae_load4<ALIGNED>(p, gi, valid);
+}
+
 template <bool ALIGNED>
 __device__ __forceinline__ uint32_t gae_load_done4(const uint8_t* __restrict__ p, int64_t gi, int valid) {
     uint32_t w = 0;

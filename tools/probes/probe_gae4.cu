@@ -6,6 +6,7 @@
 #include <vector>
 #include <cuda_runtime.h>
 
+#define G2048_GAE4_NO_DISPATCH 1
 #include "../../2048-ppo-agent_b200/csrc/g2048_gae4.cu"
 namespace g2048 { thread_local char g_last_error[512] = ""; int sm_count() { int n = 0; cudaDeviceGetAttribute(&n, cudaDevAttrMultiProcessorCount, 0); return n; } }
 extern "C" int64_t g2048_gae_flat_scratch_bytes(int64_t n) { return 16 + ((n + 1023) / 1024) * 8; }
