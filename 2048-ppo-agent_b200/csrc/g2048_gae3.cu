@@ -104,12 +104,13 @@ gae_flat3_kernel(const float* __restrict__ rewards, const float* __restrict__ va
             const char* pd = reinterpret_cast<const char*>(dones + pt * GAE3_TILE);
             for (int i = lane * 128; i < GAE3_TILE * 4; i += 32 * 128) {
                 asm volatile("prefetch.global.L2 [%0];" ::"l"(pr + i));
-                asm volatile("prefetch.global.L2 [%0];" ::"l"(pv + i));
+                asm volatile("prefetch.global.L2::evict_last [%0];" ::"l"(pv + i));
             }
             for (int i = lane * 128; i < GAE3_TILE; i += 32 * 128) asm volatile("prefetch.global.L2 [%0];" ::"l"(pd + i));
         }
     }
 
+    const uint64_t keep = l2_policy_evict_last(), once = l2_policy_evict_first();
     // ---- phase 1: delta into shared memory, done bits into ordered masks --------------------------------
     // thread t owns the 4 consecutive steps 4*(q*256 + t) .. +3 of group q; a warp covers 128 steps
 #pragma unroll
@@ -121,8 +122,8 @@ gae_flat3_kernel(const float* __restrict__ rewards, const float* __restrict__ va
         for (int k = 0; k < GAE3_INFLIGHT; ++k) {
             const int i = 4 * ((h * GAE3_INFLIGHT + k) * GAE3_THREADS + tid);
             const int valid = max(0, min(4, len - i));
-            r[k] = gae_load4<ALIGNED>(rewards, lo + i, valid);
-            v[k] = gae_load4<ALIGNED>(values, lo + i, valid);
+            r[k] = gae_load4_hint<ALIGNED>(rewards, lo + i, valid, once);
+            v[k] = gae_load4_hint<ALIGNED>(values, lo + i, valid, keep);  // read again in phase 3
             d[k] = gae_load_done4<ALIGNED>(dones, lo + i, valid);
             // V of the step after this lane's four: the next lane has it, except for lane 31
             vnext[k] = (lane == 31 && lo + i + 4 < n && i + 4 <= len + 3) ? __ldg(values + lo + i + 4) : 0.0f;
@@ -238,7 +239,7 @@ gae_flat3_kernel(const float* __restrict__ rewards, const float* __restrict__ va
 #pragma unroll
         for (int k = 0; k < GAE3_INFLIGHT; ++k) {
             const int i = 4 * ((h * GAE3_INFLIGHT + k) * GAE3_THREADS + tid);
-            v[k] = gae_load4<ALIGNED>(values, lo + i, max(0, min(4, len - i)));  // L2 hit
+            v[k] = gae_load4_hint<ALIGNED>(values, lo + i, max(0, min(4, len - i)), once);  // L2 hit, last use
         }
 #pragma unroll
         for (int k = 0; k < GAE3_INFLIGHT; ++k) {

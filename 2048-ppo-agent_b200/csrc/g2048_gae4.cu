@@ -384,9 +384,9 @@ extern "C" int g2048_gae_flat_pipelined(const float* d_rewards, const float* d_v
 
 // g2048_gae_flat: the pipelined kernel from 2^23 steps on (a persistent CTA per two tiles needs enough tiles to fill
 // the device), the one-tile-per-CTA kernel below that.  Measured on B200, episodes of ~300 steps, us:
-//   steps        2^20   2^22   2^24   2^26
-//   tiled        30.6   35.1  109.1  312
-//   pipelined    33.3   40.4   88.6  269
+//   steps        2^20   2^22   2^23   2^24   2^26
+//   tiled        26.8   37.0   59.7   96.4  312
+//   pipelined    33.1   40.4   58.4   85.3  260
 #ifndef G2048_GAE4_NO_DISPATCH  // tools/probes/probe_gae4.cu builds this file alone
 extern "C" int g2048_gae_flat_tiled(const float* d_rewards, const float* d_values, const uint8_t* d_dones, int64_t n,
                                     double gamma, double lambda_gae, float* d_adv, float* d_ret, void* d_scan_state,
