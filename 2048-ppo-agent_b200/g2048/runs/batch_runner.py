@@ -84,7 +84,7 @@ class BatchRunner:
         self.shard = shard
         self._act_fn = act_fn
         self.cuda_graph = cuda_graph
-        self._graphs = {}  # (id(act_fn), batch_size, lo, n) -> captured step
+        self._graphs = {}  # (batch_size, lo, n) -> captured step of the current act_fn
 
     # -- reference surface ---------------------------------------------------------------------
     @property
@@ -278,9 +278,9 @@ class BatchRunner:
     def _captured_step(self, batch_size: int, lo: int, n: int) -> dict:
         """Static buffers + one captured graph: expand_obs -> forward -> policy_step_at -> counter_add."""
         fn = self._act_fn
-        cache_key = (id(fn), batch_size, lo, n)
+        cache_key = (batch_size, lo, n)
         g = self._graphs.get(cache_key)
-        if g is not None:
+        if g is not None and g["fn"] is fn:  # the entry keeps `fn` alive, so identity cannot be a recycled id
             return g
         dev, mode, steps = self.device, self.rng_mode, CHUNK_STEPS
         net_dev, run_dev = torch.device(fn.device), torch.device(dev)
@@ -288,6 +288,7 @@ class BatchRunner:
         if net_dev.type != "cuda" or not same_index:
             raise ValueError("cuda_graph=True needs the TorchActionFunction's network on the runner's GPU")
         g = dict(
+            fn=fn,
             boards=torch.zeros(n, dtype=torch.int64, device=dev), status=torch.zeros(n, dtype=torch.uint8, device=dev),
             obs=torch.empty((n, 16, 31), dtype=fn.obs_dtype, device=dev),
             subs=torch.zeros((2 * steps, 2), dtype=torch.int32, device=dev),

@@ -39,6 +39,21 @@ def test_graph_replay_gives_the_eager_records(batch):
     assert len(graphed._graphs) == 1
 
 
+def test_a_new_action_function_gets_a_new_graph():
+    import g2048
+    graphed = _runner(True)
+    a = graphed.run_packed_batch(16)
+    other = TinyAgent()
+    with torch.no_grad():
+        other.actor.weight.mul_(-3.0)
+    graphed.act_fn = g2048.TorchActionFunction(other, use_mask=True, sample_actions=True, device=torch.device("cuda"))
+    eager = g2048.BatchRunner(init_seed=9, act_fn=graphed.act_fn)
+    eager.load_state_dict(graphed.state_dict())  # same chain position as the graphed runner
+    b, c = graphed.run_packed_batch(16), eager.run_packed_batch(16)
+    assert torch.equal(b.meta, c.meta) and torch.equal(b.boards, c.boards)
+    assert a.t_steps > 0
+
+
 def test_graph_path_serves_the_reference_api():
     eager, graphed = _runner(False, use_mask=False), _runner(True, use_mask=False)
     out_a, out_b = eager.run_actions_batch(16), graphed.run_actions_batch(16)
