@@ -23,6 +23,8 @@ __device__ __forceinline__ void round_v(uint32_t& a, uint32_t& b, int r, int par
     if (V == 2) { a = add_mad(a, b); uint32_t lo, hi; mulwide(b, 1u << r, lo, hi); b = (lo | hi) ^ a; }
     if (V == 3) { if (parity) a = add_mad(a, b); else a += b; uint32_t lo, hi; mulwide(b, 1u << r, lo, hi); b = (lo | hi) ^ a; }
     if (V == 4) { a = add_mad(a, b); b = rotl_shf(b, r); b ^= a; }
+    if (V == 6) { a = add_mad(a, b); if (parity == 3) { uint32_t lo, hi; mulwide(b, 1u << r, lo, hi); b = (lo | hi) ^ a; } else { b = rotl_shf(b, r); b ^= a; } }  // every 4th rotate through the FMA pipe
+    if (V == 7) { a = add_mad(a, b); if (parity == 3) { uint32_t lo, hi; mulwide(b, 1u << r, lo, hi); b = add_mad(lo, hi) ^ a; } else { b = rotl_shf(b, r); b ^= a; } }  // same, halves joined by an add on the FMA pipe
     if (V == 5) { if (parity) { a += b; uint32_t lo, hi; mulwide(b, 1u << r, lo, hi); b = (lo | hi) ^ a; } else { a = add_mad(a, b); b = rotl_shf(b, r); b ^= a; } }
 }
 
@@ -37,7 +39,7 @@ __global__ void probe(int iters, uint32_t* sink) {
         for (int k = 0; k < 4; ++k) {
             const int rs[4] = {13, 15, 26, 6};
 #pragma unroll
-            for (int c = 0; c < CH; ++c) round_v<V>(a[c], b[c], rs[k], k & 1);
+            for (int c = 0; c < CH; ++c) round_v<V>(a[c], b[c], rs[k], V >= 6 ? k : (k & 1));
         }
     }
     uint32_t x = 0;
@@ -80,6 +82,8 @@ int main() {
     run<3, 4>("V3 alternating add/mad + IMAD.WIDE + LOP3", blocks);
     run<4, 4>("V4 mad-add + SHF + LOP3", blocks);
     run<5, 4>("V5 alternate (add,WIDE) / (mad,SHF)", blocks);
+    run<6, 4>("V6 mad-add; SHF x3 + IMAD.WIDE x1 per 4 rounds", blocks);
+    run<7, 4>("V7 same, halves joined by mad-add", blocks);
     run<0, 2>("V0", blocks); run<3, 2>("V3", blocks); run<5, 2>("V5", blocks);
     run<0, 8>("V0", blocks); run<3, 8>("V3", blocks); run<5, 8>("V5", blocks);
     return 0;
