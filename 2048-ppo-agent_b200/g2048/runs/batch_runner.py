@@ -84,7 +84,7 @@ class BatchRunner:
         self.shard = shard
         self._act_fn = act_fn
         self.cuda_graph = cuda_graph
-        self._graphs = {}  # (batch_size, lo, n) -> captured step of the current act_fn
+        self._graphs = {}  # (batch_size, lo, n, steps, auto_reset) -> captured step of the current act_fn
 
     # -- reference surface ---------------------------------------------------------------------
     @property
@@ -275,14 +275,15 @@ class BatchRunner:
         return PackedRollout(rb, rm, rr, rl, rv, boards, status, t_total, n, env_steps)
 
     # -- CUDA-graph form of the network-policy loop ---------------------------
-    def _captured_step(self, batch_size: int, lo: int, n: int) -> dict:
-        """Static buffers + one captured graph: expand_obs -> forward -> policy_step_at -> counter_add."""
+    def _captured_step(self, batch_size: int, lo: int, n: int, steps: int = CHUNK_STEPS, auto_reset: bool = False) -> dict:
+        """Static buffers + one captured graph: expand_obs -> forward -> policy_step_at -> counter_add.
+        `steps` record slots per chunk; auto_reset: pgx.experimental.auto_reset semantics (fixed-horizon rollouts)."""
         fn = self._act_fn
-        cache_key = (batch_size, lo, n)
+        cache_key = (batch_size, lo, n, steps, auto_reset)
         g = self._graphs.get(cache_key)
         if g is not None and g["fn"] is fn:  # the entry keeps `fn` alive, so identity cannot be a recycled id
             return g
-        dev, mode, steps = self.device, self.rng_mode, CHUNK_STEPS
+        dev, mode = self.device, self.rng_mode
         net_dev, run_dev = torch.device(fn.device), torch.device(dev)
         same_index = net_dev.index is None or run_dev.index is None or net_dev.index == run_dev.index
         if net_dev.type != "cuda" or not same_index:
@@ -301,7 +302,7 @@ class BatchRunner:
         def step():
             E.expand_obs(g["boards"], fn.obs_dtype, out=g["obs"])
             logits, values = fn.forward_logits(g["obs"])
-            E.policy_step_at(g["boards"], g["status"], logits, values, fn.use_mask, fn.sample_actions, False, g["subs"],
+            E.policy_step_at(g["boards"], g["status"], logits, values, fn.use_mask, fn.sample_actions, auto_reset, g["subs"],
                              g["step_index"], batch_size, lo, mode, g["rb"], g["rm"], g["rr"], g["rl"], g["rv"])
             E.counter_add(g["step_index"], 1)
 

@@ -94,3 +94,86 @@ def test_graph_needs_the_network_on_the_gpu():
     runner = g2048.BatchRunner(init_seed=1, act_fn=fn, cuda_graph=True)
     with pytest.raises(ValueError, match="network on the runner's GPU"):
         runner.run_packed_batch(4)
+
+
+# ---------------------------------------------------------------------------- fixed-horizon mode (config C3)
+def _fixed(graph: bool, n=300, seed=4):
+    import g2048
+    fn = g2048.TorchActionFunction(TinyAgent(), use_mask=True, sample_actions=True, device=torch.device("cuda"))
+    return g2048.FixedHorizonRunner(init_seed=seed, act_fn=fn, batch_size=n, cuda_graph=graph)
+
+
+def test_fixed_horizon_rollout_is_the_engine_loop_with_auto_reset():
+    """collect(T) == env_init + T x (expand_obs, forward, policy_step with auto_reset) on the reference's key chain."""
+    from g2048 import engine as E
+    n, t_steps = 300, 40
+    runner = _fixed(False, n)
+    fn = runner.act_fn
+    ro = runner.collect(t_steps)
+    mode = E.RNG_PARTITIONABLE
+    subs = E.chain_advance(E.words_tensor(list(E.key_words(4)), "cuda"), mode, 1 + 2 * t_steps)
+    boards, status = E.env_init(subs[0], n, 0, n, mode)
+    for t in range(t_steps):
+        assert torch.equal(ro.boards[t], boards)
+        logits, values = fn.forward_logits(E.expand_obs(boards, torch.float32))
+        rm = torch.empty(n, dtype=torch.uint8, device="cuda")
+        rr = torch.empty(n, dtype=torch.float32, device="cuda")
+        E.policy_step(boards, status, logits, values, True, True, True, subs[1 + 2 * t], subs[2 + 2 * t], n, 0, mode, None, rm, rr)
+        assert torch.equal(ro.meta[t], rm) and torch.equal(ro.rewards[t], rr) and torch.equal(ro.values[t], values)
+    assert torch.equal(ro.final_boards, boards) and torch.equal(ro.final_status, status)
+    dones = (ro.meta >> 6) & 1
+    assert ro.boards.shape == (t_steps, n) and int(dones.sum()) >= 0
+
+
+def test_fixed_horizon_graph_equals_eager_and_envs_persist():
+    eager, graphed = _fixed(False), _fixed(True)
+    total_done = 0
+    for _ in range(3):  # state and key chain carry over from one collect() to the next
+        a, b = eager.collect(64), graphed.collect(64)
+        for name in ("boards", "meta", "rewards", "log_probs", "values", "final_boards", "final_status"):
+            assert torch.equal(getattr(a, name), getattr(b, name)), name
+        total_done += int(((a.meta >> 6) & 1).sum())
+        assert torch.equal(a.final_boards, eager.boards)
+    assert total_done > 0, "192 steps of 300 envs must finish (and auto-reset) some episodes"
+    assert (eager.key == graphed.key).all()
+
+
+def test_fixed_horizon_gae_bootstraps_running_episodes():
+    import numpy as np
+    from oracle import pgx2048_oracle as O
+    runner = _fixed(False, n=64)
+    ro = runner.collect(16)
+    boot = runner.bootstrap_values()
+    adv, ret, _ = ro.gae(0.99, 0.95, bootstrap=boot)
+    r, v = ro.rewards.cpu().numpy(), ro.values.cpu().numpy()
+    d = ((ro.meta >> 6) & 1).cpu().numpy().astype(bool)
+    b = boot.cpu().numpy()
+    want = np.zeros_like(r)
+    g32, gl32 = np.float32(0.99), np.float32(0.99 * 0.95)
+    for e in range(64):  # the reference recurrence (data_loader.py:103-130) per env, seeded with the bootstrap value
+        last_v, last_g = b[e], np.float32(0)
+        for t in range(15, -1, -1):
+            if d[t, e]:
+                last_v, last_g = np.float32(0), np.float32(0)
+            delta = np.float32(np.float32(r[t, e] + np.float32(g32 * last_v)) - v[t, e])
+            last_g = np.float32(delta + np.float32(gl32 * last_g))
+            want[t, e] = last_g
+            last_v = v[t, e]
+    np.testing.assert_array_equal(adv.cpu().numpy(), want)
+    np.testing.assert_array_equal(ret.cpu().numpy(), want + v)
+    assert O is not None
+
+
+def test_fixed_horizon_checkpoint_resumes_env_state_and_key_chain():
+    a = _fixed(False, n=100)
+    a.collect(20)
+    saved = a.state_dict()
+    want = a.collect(20)
+    b = _fixed(True, n=100, seed=99)  # different seed, then overwritten by the checkpoint
+    b.collect(7)
+    b.load_state_dict(saved)
+    got = b.collect(20)
+    for name in ("boards", "meta", "rewards", "log_probs", "values", "final_boards"):
+        assert torch.equal(getattr(want, name), getattr(got, name)), name
+    with pytest.raises(ValueError):
+        _fixed(False, n=50).load_state_dict(saved)
