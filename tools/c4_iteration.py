@@ -63,17 +63,34 @@ def main():
                                                           max_samples_per_epoch=args.max_samples, shuffle_on_reset=True))
     report["gae_normalise"] = {"seconds": t_gae, "steps_per_sec": kept / t_gae}
 
-    net = torch.nn.Sequential(torch.nn.Flatten(), torch.nn.Linear(496, 256), torch.nn.ReLU(), torch.nn.Linear(256, 5)).cuda()
+    class StandIn(torch.nn.Module):
+        """Per-cell input embedding like the reference agent's (Linear(31, d_model, bias=False), ppo_agent.py:60),
+        mean over the 16 cells, one hidden layer, 4 logits + 1 value.  Takes observations or bitboards."""
+
+        def __init__(self):
+            super().__init__()
+            self.input_embedding = torch.nn.Linear(31, 256, bias=False)
+            self.head = torch.nn.Sequential(torch.nn.ReLU(), torch.nn.Linear(256, 256), torch.nn.ReLU(), torch.nn.Linear(256, 5))
+
+        def forward(self, batch):
+            if "boards" in batch:
+                emb = g2048.ppo.embed_boards(self.input_embedding.weight, batch["boards"])
+            else:
+                emb = self.input_embedding(batch["observations"])
+            return self.head(emb.mean(dim=1))
+
+    net = StandIn().cuda()
     opt = torch.optim.Adam(net.parameters(), lr=1e-4)
 
-    def epochs(update: bool):
+    def epochs(update: bool, source=None):
+        source = batches if source is None else source
         n = 0
         for _ in range(args.epochs):
-            batches.reset_epoch()
-            for b in batches:
-                n += b["observations"].shape[0]
+            source.reset_epoch()
+            for b in source:
+                n += b["actions"].shape[0]
                 if update:
-                    out = net(b["observations"])
+                    out = net(b)
                     logits = out[:, :4] - 1e8 * (1 - b["action_masks"].float())
                     logp = torch.distributions.Categorical(logits=logits).log_prob(b["actions"])
                     ratio = torch.exp(logp - b["log_probs"])
@@ -88,6 +105,14 @@ def main():
     _, t_update = timed(lambda: epochs(True))
     report["minibatches"] = {"seconds_gather_only": t_feed, "samples": n_samples, "samples_per_sec": n_samples / t_feed,
                              "seconds_with_stand_in_update": t_update}
+    # the same epochs with bitboards instead of observations: the embedding becomes a row gather
+    batches_b = g2048.DevicePPOBatches(packed, 0.99, 0.95, batch_size=args.minibatch, max_samples_per_epoch=args.max_samples,
+                                       shuffle_on_reset=True, obs_dtype=None)
+    epochs(True, batches_b)  # warm-up of the embedding kernels
+    _, t_feed_b = timed(lambda: epochs(False, batches_b))
+    _, t_update_b = timed(lambda: epochs(True, batches_b))
+    report["minibatches_boards"] = {"seconds_gather_only": t_feed_b, "seconds_with_stand_in_update": t_update_b,
+                                    "bytes_per_sample": 8 + 8 + 4 + 16, "bytes_per_sample_observations": 1984 + 8 + 4 + 16}
 
     # bit-exact board check on a 4 096-env sample: replay the recorded actions through the oracle's step, with the
     # oracle's own spawn draws from the same keys, and compare every recorded pre-step board, reward and done flag
