@@ -345,13 +345,13 @@ def main():
     int_peak = blocks * threads * iters * 48 / min(p_times) / 1e12  # 16 rounds x 3 instr per iteration
     achieved = ALG_INSTR[args.policy] * k_steps / k_time / 1e12
     roofline = {
-        "kernel": "play_kernel (g2048_play)", "bound": "int_issue", "achieved": achieved, "peak": int_peak,
+        "kernel": "play3_kernel (g2048_play: row tables in shared memory)", "bound": "int_issue", "achieved": achieved, "peak": int_peak,
         "unit": "Tinstr/s", "frac": achieved / int_peak,
         # dram__bytes_read.sum + dram__bytes_write.sum of one play3_kernel launch (profiles/r01_play_tables_kernel.csv):
         # the 192 KiB of tables per CTA come from L2, per-episode results are not written in this leg
         "traffic": 229632,
         "note": (f"algorithmic {ALG_INSTR[args.policy]} int instr per env-step (SURVEY 8d) x {k_steps} env-steps per launch / "
-                 f"{k_time * 1e3:.2f} ms; peak = live probe of the ADD/SHF/LOP3 Threefry mix on this GPU (of measured); "
+                 f"{k_time * 1e3:.2f} ms; peak = live probe of the ADD/SHF/LOP3 Threefry mix on this GPU, measured in this run; "
                  "the kernel keeps env state in registers, so HBM traffic is ~16 B per episode and not the bound"),
         "kernel_ms": k_time * 1e3, "kernel_env_steps": k_steps,
     }
