@@ -43,7 +43,7 @@ constexpr int G4_VEC = G4_TILE / (4 * G4_STREAM_THREADS);
 constexpr int G4_INFLIGHT = 2;  // float4 groups of each of the four streams a thread has in flight per pass
 constexpr int G4_PASSES = G4_VEC / G4_INFLIGHT;
 static_assert(G4_VEC * 4 * G4_STREAM_THREADS == G4_TILE && G4_PASSES * G4_INFLIGHT == G4_VEC, "tile shape");
-static_assert(G4_BLOCKS <= 64, "the prefix warp takes at most two blocks per lane");
+constexpr int G4_BLOCKS_PER_LANE = (G4_BLOCKS + 31) / 32;  // of the prefix warp
 
 struct G4Scratch {  // same layout as the previous generation: ticket, then flags[n_tiles], heads[n_tiles]
     unsigned int ticket;
@@ -54,7 +54,7 @@ struct G4Stage {
     float g[G4_TILE];                // delta -> advantages, in place
     uint32_t ballot[4 * G4_BLOCKS];  // done bits, four ballots per 128-step block
     uint32_t pref[G4_BLOCKS + 1];    // exclusive prefix of the blocks' done counts
-    uint32_t pad[3];
+    uint32_t pad[3 - (G4_BLOCKS % 4)];
 };
 static_assert(sizeof(G4Stage) % 16 == 0, "the second stage's deltas must stay 16-byte aligned");
 
@@ -114,23 +114,30 @@ __device__ __forceinline__ void g4_load_tile(G4Stage& st, int64_t tile, const fl
         }
     }
     g4_stream_barrier();
-    if (warp == 0) {  // exclusive prefix over the blocks' done counts; lane l takes blocks l and 32 + l
-        uint32_t c0 = 0, c1 = 0;
-        if (lane < G4_BLOCKS)
-            c0 = __popc(st.ballot[4 * lane]) + __popc(st.ballot[4 * lane + 1]) + __popc(st.ballot[4 * lane + 2]) + __popc(st.ballot[4 * lane + 3]);
-        if (32 + lane < G4_BLOCKS) {
-            const int b = 32 + lane;
-            c1 = __popc(st.ballot[4 * b]) + __popc(st.ballot[4 * b + 1]) + __popc(st.ballot[4 * b + 2]) + __popc(st.ballot[4 * b + 3]);
+    if (warp == 0) {  // exclusive prefix over the blocks' done counts; lane l takes G4_BLOCKS_PER_LANE consecutive blocks
+        uint32_t c[G4_BLOCKS_PER_LANE];
+        uint32_t sum = 0;
+#pragma unroll
+        for (int q = 0; q < G4_BLOCKS_PER_LANE; ++q) {
+            const int blk = lane * G4_BLOCKS_PER_LANE + q;
+            c[q] = blk < G4_BLOCKS ? __popc(st.ballot[4 * blk]) + __popc(st.ballot[4 * blk + 1]) + __popc(st.ballot[4 * blk + 2]) +
+                                         __popc(st.ballot[4 * blk + 3])
+                                   : 0u;
+            sum += c[q];
         }
-        uint32_t i0 = c0, i1 = c1;
+        uint32_t incl = sum;
         for (int off = 1; off < 32; off <<= 1) {
-            const uint32_t y0 = __shfl_up_sync(0xFFFFFFFFu, i0, off), y1 = __shfl_up_sync(0xFFFFFFFFu, i1, off);
-            if (lane >= off) { i0 += y0; i1 += y1; }
+            const uint32_t y = __shfl_up_sync(0xFFFFFFFFu, incl, off);
+            if (lane >= off) incl += y;
         }
-        const uint32_t total0 = __shfl_sync(0xFFFFFFFFu, i0, 31);
-        if (lane < G4_BLOCKS) st.pref[lane] = i0 - c0;
-        if (32 + lane < G4_BLOCKS) st.pref[32 + lane] = total0 + i1 - c1;
-        if (lane == 31) st.pref[G4_BLOCKS] = total0 + i1;
+        uint32_t run = incl - sum;
+#pragma unroll
+        for (int q = 0; q < G4_BLOCKS_PER_LANE; ++q) {
+            const int blk = lane * G4_BLOCKS_PER_LANE + q;
+            if (blk < G4_BLOCKS) st.pref[blk] = run;
+            run += c[q];
+        }
+        if (lane == 31) st.pref[G4_BLOCKS] = incl;
     }
 }
 
