@@ -46,7 +46,6 @@ constexpr int GAE3_INFLIGHT = (GAE3_VEC_PER_THREAD % 3 == 0) ? 3 : 2;  // float4
 constexpr int GAE3_PASSES = GAE3_VEC_PER_THREAD / GAE3_INFLIGHT;
 static_assert(GAE3_WARPS == 4 || GAE3_WARPS == 8, "four or eight warps per CTA");
 static_assert(GAE3_VEC_PER_THREAD * 4 * GAE3_THREADS == GAE3_TILE && GAE3_PASSES * GAE3_INFLIGHT == GAE3_VEC_PER_THREAD, "tile shape");
-static_assert(GAE3_BLOCKS <= 64, "the prefix warp takes at most two blocks per lane");
 // warp roles in phase 2 (rotated over the warp schedulers with the ticket)
 constexpr int GAE3_ROLE_FIRST = GAE3_WARPS == 4 ? 1 : 4, GAE3_ROLE_TAIL = GAE3_WARPS == 4 ? 2 : 5;
 constexpr int GAE3_WALK_SLOTS = GAE3_WARPS - 2;
@@ -96,79 +95,14 @@ gae_flat3_kernel(const float* __restrict__ rewards, const float* __restrict__ va
     // Only the CTAs that are in phase 1 have loads in flight, too few bytes to keep HBM busy.  So the inputs of the
     // tile that will be taken `prefetch_tiles` tickets from now (about when this CTA's SM slot frees up) are pulled
     // into L2 now: phase 1 then runs at L2 latency and DRAM sees a steady stream that no CTA waits for.
-    if (prefetch_tiles > 0 && warp == GAE3_WARPS - 1) {
-        const int64_t pt = tile - prefetch_tiles;  // a full tile if it exists (only the last tile can be short)
-        if (pt >= 0) {
-            const char* pr = reinterpret_cast<const char*>(rewards + pt * GAE3_TILE);
-            const char* pv = reinterpret_cast<const char*>(values + pt * GAE3_TILE);
-            const char* pd = reinterpret_cast<const char*>(dones + pt * GAE3_TILE);
-            for (int i = lane * 128; i < GAE3_TILE * 4; i += 32 * 128) {
-                asm volatile("prefetch.global.L2 [%0];" ::"l"(pr + i));
-                asm volatile("prefetch.global.L2::evict_last [%0];" ::"l"(pv + i));
-            }
-            for (int i = lane * 128; i < GAE3_TILE; i += 32 * 128) asm volatile("prefetch.global.L2 [%0];" ::"l"(pd + i));
-        }
-    }
+    if (prefetch_tiles > 0 && warp == GAE3_WARPS - 1 && tile - prefetch_tiles >= 0)  // a full tile if it exists
+        gae_tile_prefetch<GAE3_TILE>(rewards, values, dones, tile - prefetch_tiles, lane);
 
-    const uint64_t keep = l2_policy_evict_last(), once = l2_policy_evict_first();
-    // ---- phase 1: delta into shared memory, done bits into ordered masks --------------------------------
-    // thread t owns the 4 consecutive steps 4*(q*256 + t) .. +3 of group q; a warp covers 128 steps
-#pragma unroll
-    for (int h = 0; h < GAE3_PASSES; ++h) {
-        float4 r[GAE3_INFLIGHT], v[GAE3_INFLIGHT];
-        uint32_t d[GAE3_INFLIGHT];
-        float vnext[GAE3_INFLIGHT];
-#pragma unroll
-        for (int k = 0; k < GAE3_INFLIGHT; ++k) {
-            const int i = 4 * ((h * GAE3_INFLIGHT + k) * GAE3_THREADS + tid);
-            const int valid = max(0, min(4, len - i));
-            r[k] = gae_load4_hint<ALIGNED>(rewards, lo + i, valid, once);
-            v[k] = gae_load4_hint<ALIGNED>(values, lo + i, valid, keep);  // read again in phase 3
-            d[k] = gae_load_done4<ALIGNED>(dones, lo + i, valid);
-            // V of the step after this lane's four: the next lane has it, except for lane 31
-            vnext[k] = (lane == 31 && lo + i + 4 < n && i + 4 <= len + 3) ? __ldg(values + lo + i + 4) : 0.0f;
-        }
-#pragma unroll
-        for (int k = 0; k < GAE3_INFLIGHT; ++k) {
-            const int q = h * GAE3_INFLIGHT + k;
-            const int i = 4 * (q * GAE3_THREADS + tid);
-            const float from_next_lane = __shfl_down_sync(0xFFFFFFFFu, v[k].x, 1);
-            const float v4 = (lane == 31) ? vnext[k] : from_next_lane;  // 0 past the end of the buffer
-            const bool d0 = (d[k] & 0xFFu) != 0, d1 = (d[k] & 0xFF00u) != 0, d2 = (d[k] & 0xFF0000u) != 0,
-                       d3 = (d[k] & 0xFF000000u) != 0;
-            float4 delta;
-            delta.x = (r[k].x + gamma * (d0 ? 0.0f : v[k].y)) - v[k].x;
-            delta.y = (r[k].y + gamma * (d1 ? 0.0f : v[k].z)) - v[k].y;
-            delta.z = (r[k].z + gamma * (d2 ? 0.0f : v[k].w)) - v[k].z;
-            delta.w = (r[k].w + gamma * (d3 ? 0.0f : v4)) - v[k].w;
-            *reinterpret_cast<float4*>(&s.g[i]) = delta;
-            const uint32_t b0 = __ballot_sync(0xFFFFFFFFu, d0), b1 = __ballot_sync(0xFFFFFFFFu, d1),
-                           b2 = __ballot_sync(0xFFFFFFFFu, d2), b3 = __ballot_sync(0xFFFFFFFFu, d3);
-            if (lane < 4)  // the four ballots of this 128-step block, as they are (gae3_locate interleaves them)
-                s.ballot[4 * (q * GAE3_WARPS + warp) + lane] = lane == 0 ? b0 : (lane == 1 ? b1 : (lane == 2 ? b2 : b3));
-        }
-    }
+    // ---- phase 1: delta into shared memory, done bits into ballots ---------------------------------------------
+    gae_tile_deltas<ALIGNED, GAE3_TILE, GAE3_THREADS, GAE3_INFLIGHT>(s.g, s.ballot, rewards, values, dones, n, lo, len, gamma, tid);
     __syncthreads();
     GAE3_STAMP(2);
-    // exclusive prefix over the blocks' done counts (one warp; lane l takes blocks l and 32 + l)
-    if (warp == 0) {
-        uint32_t c0 = 0, c1 = 0;
-        if (lane < GAE3_BLOCKS)
-            c0 = __popc(s.ballot[4 * lane]) + __popc(s.ballot[4 * lane + 1]) + __popc(s.ballot[4 * lane + 2]) + __popc(s.ballot[4 * lane + 3]);
-        if (32 + lane < GAE3_BLOCKS) {
-            const int b = 32 + lane;
-            c1 = __popc(s.ballot[4 * b]) + __popc(s.ballot[4 * b + 1]) + __popc(s.ballot[4 * b + 2]) + __popc(s.ballot[4 * b + 3]);
-        }
-        uint32_t i0 = c0, i1 = c1;
-        for (int off = 1; off < 32; off <<= 1) {
-            const uint32_t y0 = __shfl_up_sync(0xFFFFFFFFu, i0, off), y1 = __shfl_up_sync(0xFFFFFFFFu, i1, off);
-            if (lane >= off) { i0 += y0; i1 += y1; }
-        }
-        const uint32_t total0 = __shfl_sync(0xFFFFFFFFu, i0, 31);
-        if (lane < GAE3_BLOCKS) s.pref[lane] = i0 - c0;
-        if (32 + lane < GAE3_BLOCKS) s.pref[32 + lane] = total0 + i1 - c1;
-        if (lane == 31) s.pref[GAE3_BLOCKS] = total0 + i1;
-    }
+    if (warp == 0) gae_tile_prefix<GAE3_BLOCKS>(s.ballot, s.pref, lane);
     __syncthreads();
     const int n_done = (int)s.pref[GAE3_BLOCKS];
     GAE3_STAMP(3);
@@ -233,47 +167,7 @@ gae_flat3_kernel(const float* __restrict__ rewards, const float* __restrict__ va
 
     // ---- phase 3: returns, stores, moments -------------------------------------------------------------------
     double m[4] = {0.0, 0.0, 0.0, 0.0};
-#pragma unroll
-    for (int h = 0; h < GAE3_PASSES; ++h) {
-        float4 v[GAE3_INFLIGHT];
-#pragma unroll
-        for (int k = 0; k < GAE3_INFLIGHT; ++k) {
-            const int i = 4 * ((h * GAE3_INFLIGHT + k) * GAE3_THREADS + tid);
-            v[k] = gae_load4_hint<ALIGNED>(values, lo + i, max(0, min(4, len - i)), once);  // L2 hit, last use
-        }
-#pragma unroll
-        for (int k = 0; k < GAE3_INFLIGHT; ++k) {
-            const int i = 4 * ((h * GAE3_INFLIGHT + k) * GAE3_THREADS + tid);
-            const int valid = max(0, min(4, len - i));
-            if (valid > 0) {
-                const float4 a = *reinterpret_cast<const float4*>(&s.g[i]);
-                const float4 rt = make_float4(a.x + v[k].x, a.y + v[k].y, a.z + v[k].z, a.w + v[k].w);
-                if (ALIGNED && valid == 4) {
-                    __stcs(reinterpret_cast<float4*>(adv + lo + i), a);
-                    __stcs(reinterpret_cast<float4*>(ret + lo + i), rt);
-                } else {
-                    const float aa[4] = {a.x, a.y, a.z, a.w}, rr[4] = {rt.x, rt.y, rt.z, rt.w};
-                    for (int j = 0; j < valid; ++j) {
-                        adv[lo + i + j] = aa[j];
-                        ret[lo + i + j] = rr[j];
-                    }
-                }
-                const float aa[4] = {a.x, a.y, a.z, a.w}, rr[4] = {rt.x, rt.y, rt.z, rt.w};
-#pragma unroll
-                for (int j = 0; j < 4; ++j) {
-                    if (j < valid) {
-#ifndef G2048_GAE3_SKIP_MOMENTS  // timing experiment only
-                        const double da = (double)aa[j], dr = (double)rr[j];
-                        m[0] += da;
-                        m[1] = __fma_rn(da, da, m[1]);  // the product of two floats is exact in double either way
-                        m[2] += dr;
-                        m[3] = __fma_rn(dr, dr, m[3]);
-#endif
-                    }
-                }
-            }
-        }
-    }
+    gae_tile_store<ALIGNED, GAE3_TILE, GAE3_THREADS, GAE3_INFLIGHT>(s.g, values, lo, len, adv, ret, m, tid);
     GAE3_STAMP(5);
     if (moments) {
 #pragma unroll

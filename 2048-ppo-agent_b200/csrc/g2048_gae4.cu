@@ -39,11 +39,7 @@ constexpr int G4_THREADS = G4_STREAM_THREADS + 32 * G4_WALK_WARPS;  // 384
 #endif
 constexpr int G4_TILE = G4_TILE_STEPS;
 constexpr int G4_BLOCKS = G4_TILE / 128;
-constexpr int G4_VEC = G4_TILE / (4 * G4_STREAM_THREADS);
 constexpr int G4_INFLIGHT = 2;  // float4 groups of each of the four streams a thread has in flight per pass
-constexpr int G4_PASSES = G4_VEC / G4_INFLIGHT;
-static_assert(G4_VEC * 4 * G4_STREAM_THREADS == G4_TILE && G4_PASSES * G4_INFLIGHT == G4_VEC, "tile shape");
-constexpr int G4_BLOCKS_PER_LANE = (G4_BLOCKS + 31) / 32;  // of the prefix warp
 
 struct G4Scratch {  // same layout as the previous generation: ticket, then flags[n_tiles], heads[n_tiles]
     unsigned int ticket;
@@ -74,121 +70,22 @@ template <bool ALIGNED>
 __device__ __forceinline__ void g4_load_tile(G4Stage& st, int64_t tile, const float* __restrict__ rewards,
                                              const float* __restrict__ values, const uint8_t* __restrict__ dones, int64_t n,
                                              float gamma, int tid) {
-    const int lane = tid & 31, warp = tid >> 5;
     const int64_t lo = tile * G4_TILE;
     const int len = (int)min((int64_t)G4_TILE, n - lo);
-    const uint64_t keep = l2_policy_evict_last(), once = l2_policy_evict_first();
-#pragma unroll
-    for (int h = 0; h < G4_PASSES; ++h) {
-        float4 r[G4_INFLIGHT], v[G4_INFLIGHT];
-        uint32_t d[G4_INFLIGHT];
-        float vnext[G4_INFLIGHT];
-#pragma unroll
-        for (int k = 0; k < G4_INFLIGHT; ++k) {
-            const int i = 4 * ((h * G4_INFLIGHT + k) * G4_STREAM_THREADS + tid);
-            const int valid = max(0, min(4, len - i));
-            r[k] = gae_load4_hint<ALIGNED>(rewards, lo + i, valid, once);
-            v[k] = gae_load4_hint<ALIGNED>(values, lo + i, valid, keep);  // read again when the tile is stored
-            d[k] = gae_load_done4<ALIGNED>(dones, lo + i, valid);
-            // V of the step after this lane's four: the next lane has it, except for lane 31
-            vnext[k] = (lane == 31 && lo + i + 4 < n && i + 4 <= len + 3) ? __ldg(values + lo + i + 4) : 0.0f;
-        }
-#pragma unroll
-        for (int k = 0; k < G4_INFLIGHT; ++k) {
-            const int q = h * G4_INFLIGHT + k;
-            const int i = 4 * (q * G4_STREAM_THREADS + tid);
-            const float from_next_lane = __shfl_down_sync(0xFFFFFFFFu, v[k].x, 1);
-            const float v4 = (lane == 31) ? vnext[k] : from_next_lane;  // 0 past the end of the buffer
-            const bool d0 = (d[k] & 0xFFu) != 0, d1 = (d[k] & 0xFF00u) != 0, d2 = (d[k] & 0xFF0000u) != 0,
-                       d3 = (d[k] & 0xFF000000u) != 0;
-            float4 delta;
-            delta.x = (r[k].x + gamma * (d0 ? 0.0f : v[k].y)) - v[k].x;
-            delta.y = (r[k].y + gamma * (d1 ? 0.0f : v[k].z)) - v[k].y;
-            delta.z = (r[k].z + gamma * (d2 ? 0.0f : v[k].w)) - v[k].z;
-            delta.w = (r[k].w + gamma * (d3 ? 0.0f : v4)) - v[k].w;
-            *reinterpret_cast<float4*>(&st.g[i]) = delta;
-            const uint32_t b0 = __ballot_sync(0xFFFFFFFFu, d0), b1 = __ballot_sync(0xFFFFFFFFu, d1),
-                           b2 = __ballot_sync(0xFFFFFFFFu, d2), b3 = __ballot_sync(0xFFFFFFFFu, d3);
-            if (lane < 4)
-                st.ballot[4 * (q * G4_STREAM_WARPS + warp) + lane] = lane == 0 ? b0 : (lane == 1 ? b1 : (lane == 2 ? b2 : b3));
-        }
-    }
+    gae_tile_deltas<ALIGNED, G4_TILE, G4_STREAM_THREADS, G4_INFLIGHT>(st.g, st.ballot, rewards, values, dones, n, lo, len, gamma, tid);
     g4_stream_barrier();
-    if (warp == 0) {  // exclusive prefix over the blocks' done counts; lane l takes G4_BLOCKS_PER_LANE consecutive blocks
-        uint32_t c[G4_BLOCKS_PER_LANE];
-        uint32_t sum = 0;
-#pragma unroll
-        for (int q = 0; q < G4_BLOCKS_PER_LANE; ++q) {
-            const int blk = lane * G4_BLOCKS_PER_LANE + q;
-            c[q] = blk < G4_BLOCKS ? __popc(st.ballot[4 * blk]) + __popc(st.ballot[4 * blk + 1]) + __popc(st.ballot[4 * blk + 2]) +
-                                         __popc(st.ballot[4 * blk + 3])
-                                   : 0u;
-            sum += c[q];
-        }
-        uint32_t incl = sum;
-        for (int off = 1; off < 32; off <<= 1) {
-            const uint32_t y = __shfl_up_sync(0xFFFFFFFFu, incl, off);
-            if (lane >= off) incl += y;
-        }
-        uint32_t run = incl - sum;
-#pragma unroll
-        for (int q = 0; q < G4_BLOCKS_PER_LANE; ++q) {
-            const int blk = lane * G4_BLOCKS_PER_LANE + q;
-            if (blk < G4_BLOCKS) st.pref[blk] = run;
-            run += c[q];
-        }
-        if (lane == 31) st.pref[G4_BLOCKS] = incl;
-    }
+    if (tid < 32) gae_tile_prefix<G4_BLOCKS>(st.ballot, st.pref, tid);
 }
 
-// phase 3 of one tile (streamer threads only): advantages from st.g, V again from global (an L2 hit as long as it
-// happens right at the start of the iteration after the walk: measured, lines survive about one iteration in L2 --
-// a variant that spread these loads over the whole iteration, fused with the next tile's loads, was 13 % slower),
-// returns, moments
+// phase 3 of one tile (streamer threads only), right at the start of the iteration after the walk: measured, lines
+// survive about one iteration in L2 -- a variant that spread V's second read over the whole iteration, fused with
+// the next tile's loads, was 13 % slower
 template <bool ALIGNED>
 __device__ __forceinline__ void g4_store_tile(const G4Stage& st, int64_t tile, const float* __restrict__ values, int64_t n,
                                               float* __restrict__ adv, float* __restrict__ ret, double (&m)[4], int tid) {
     const int64_t lo = tile * G4_TILE;
     const int len = (int)min((int64_t)G4_TILE, n - lo);
-    const uint64_t once = l2_policy_evict_first();
-#pragma unroll
-    for (int h = 0; h < G4_PASSES; ++h) {
-        float4 v[G4_INFLIGHT];
-#pragma unroll
-        for (int k = 0; k < G4_INFLIGHT; ++k) {
-            const int i = 4 * ((h * G4_INFLIGHT + k) * G4_STREAM_THREADS + tid);
-            v[k] = gae_load4_hint<ALIGNED>(values, lo + i, max(0, min(4, len - i)), once);  // last use of the line
-        }
-#pragma unroll
-        for (int k = 0; k < G4_INFLIGHT; ++k) {
-            const int i = 4 * ((h * G4_INFLIGHT + k) * G4_STREAM_THREADS + tid);
-            const int valid = max(0, min(4, len - i));
-            if (valid > 0) {
-                const float4 a = *reinterpret_cast<const float4*>(&st.g[i]);
-                const float4 rt = make_float4(a.x + v[k].x, a.y + v[k].y, a.z + v[k].z, a.w + v[k].w);
-                const float aa[4] = {a.x, a.y, a.z, a.w}, rr[4] = {rt.x, rt.y, rt.z, rt.w};
-                if (ALIGNED && valid == 4) {
-                    __stcs(reinterpret_cast<float4*>(adv + lo + i), a);
-                    __stcs(reinterpret_cast<float4*>(ret + lo + i), rt);
-                } else {
-                    for (int j = 0; j < valid; ++j) {
-                        adv[lo + i + j] = aa[j];
-                        ret[lo + i + j] = rr[j];
-                    }
-                }
-#pragma unroll
-                for (int j = 0; j < 4; ++j) {
-                    if (j < valid) {
-                        const double da = (double)aa[j], dr = (double)rr[j];
-                        m[0] += da;
-                        m[1] = __fma_rn(da, da, m[1]);  // the product of two floats is exact in double either way
-                        m[2] += dr;
-                        m[3] = __fma_rn(dr, dr, m[3]);
-                    }
-                }
-            }
-        }
-    }
+    gae_tile_store<ALIGNED, G4_TILE, G4_STREAM_THREADS, G4_INFLIGHT>(st.g, values, lo, len, adv, ret, m, tid);
 }
 
 // phase 2 of one tile (walker warps only; wwarp = 0..3)
@@ -265,15 +162,7 @@ gae_flat4_kernel(const float* __restrict__ rewards, const float* __restrict__ va
     };
     auto prefetch = [&](int64_t tile) {  // inputs of the tile `prefetch_tiles` tickets ahead into L2 (one warp)
         const int64_t pt = tile - prefetch_tiles;
-        if (prefetch_tiles <= 0 || pt < 0) return;
-        const char* pr = reinterpret_cast<const char*>(rewards + pt * G4_TILE);
-        const char* pv = reinterpret_cast<const char*>(values + pt * G4_TILE);
-        const char* pd = reinterpret_cast<const char*>(dones + pt * G4_TILE);
-        for (int i = lane * 128; i < G4_TILE * 4; i += 32 * 128) {
-            asm volatile("prefetch.global.L2 [%0];" ::"l"(pr + i));
-            asm volatile("prefetch.global.L2::evict_last [%0];" ::"l"(pv + i));
-        }
-        for (int i = lane * 128; i < G4_TILE; i += 32 * 128) asm volatile("prefetch.global.L2 [%0];" ::"l"(pd + i));
+        if (prefetch_tiles > 0 && pt >= 0) gae_tile_prefetch<G4_TILE>(rewards, values, dones, pt, lane);
     };
 
     // ---- prologue: the first tile into stage 0 ---------------------------------------------------------------

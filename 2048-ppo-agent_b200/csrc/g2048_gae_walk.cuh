@@ -1,5 +1,6 @@
-// Device helpers shared by the flat-GAE kernels (g2048_gae3.cu, g2048_gae4.cu): the in-place backward walk over one
-// episode's deltas in shared memory, the ordered-done-list lookup, and the 128-bit loads of phase 1.
+// Device code shared by the flat-GAE kernels (g2048_gae3.cu, g2048_gae4.cu): the in-place backward walk over one
+// episode's deltas in shared memory, the ordered-done-list lookup, the hinted 128-bit loads, and the three tile
+// phases (deltas + done ballots, block prefix, store + moments).
 #pragma once
 #include <cstdint>
 
@@ -147,6 +148,155 @@ __device__ __forceinline__ uint32_t gae_load_done4(const uint8_t* __restrict__ p
         if (valid > 3) w |= (uint32_t)__ldg(p + gi + 3) << 24;
     }
     return w;
+}
+
+
+// ------------------------------------------------------------------------------------------------------------------
+// Tile phases shared by the one-tile-per-CTA kernel (g2048_gae3.cu) and the pipelined one (g2048_gae4.cu).
+// THREADS threads cooperate on a TILE-step tile; thread t owns the 4 consecutive steps 4*(q*THREADS + t) .. +3 of
+// group q, so a warp covers one 128-step block per group; INFLIGHT groups are loaded before the first is used.
+// ------------------------------------------------------------------------------------------------------------------
+
+// inputs of tile `pt` (a full tile) into L2, one warp; V with evict-last priority because it is read twice
+template <int TILE>
+__device__ __forceinline__ void gae_tile_prefetch(const float* __restrict__ rewards, const float* __restrict__ values,
+                                                  const uint8_t* __restrict__ dones, int64_t pt, int lane) {
+    const char* pr = reinterpret_cast<const char*>(rewards + pt * TILE);
+    const char* pv = reinterpret_cast<const char*>(values + pt * TILE);
+    const char* pd = reinterpret_cast<const char*>(dones + pt * TILE);
+    for (int i = lane * 128; i < TILE * 4; i += 32 * 128) {
+        asm volatile("prefetch.global.L2 [%0];" ::"l"(pr + i));
+        asm volatile("prefetch.global.L2::evict_last [%0];" ::"l"(pv + i));
+    }
+    for (int i = lane * 128; i < TILE; i += 32 * 128) asm volatile("prefetch.global.L2 [%0];" ::"l"(pd + i));
+}
+
+// phase 1: delta = (r + gamma * V[t+1] * !done) - V into g[], the four done ballots of every 128-step block into
+// ballot[] (ballot j of block b has bit l set iff step 128*b + 4*l + j is a done).  lo = first step of the tile,
+// len = its length (< TILE only for the last tile of the buffer).
+template <bool ALIGNED, int TILE, int THREADS, int INFLIGHT>
+__device__ __forceinline__ void gae_tile_deltas(float* __restrict__ g, uint32_t* __restrict__ ballot,
+                                                const float* __restrict__ rewards, const float* __restrict__ values,
+                                                const uint8_t* __restrict__ dones, int64_t n, int64_t lo, int len, float gamma,
+                                                int tid) {
+    constexpr int VEC = TILE / (4 * THREADS), PASSES = VEC / INFLIGHT, WARPS = THREADS / 32;
+    static_assert(VEC * 4 * THREADS == TILE && PASSES * INFLIGHT == VEC, "tile shape");
+    const int lane = tid & 31, warp = tid >> 5;
+    const uint64_t keep = l2_policy_evict_last(), once = l2_policy_evict_first();
+#pragma unroll
+    for (int h = 0; h < PASSES; ++h) {
+        float4 r[INFLIGHT], v[INFLIGHT];
+        uint32_t d[INFLIGHT];
+        float vnext[INFLIGHT];
+#pragma unroll
+        for (int k = 0; k < INFLIGHT; ++k) {
+            const int i = 4 * ((h * INFLIGHT + k) * THREADS + tid);
+            const int valid = max(0, min(4, len - i));
+            r[k] = gae_load4_hint<ALIGNED>(rewards, lo + i, valid, once);
+            v[k] = gae_load4_hint<ALIGNED>(values, lo + i, valid, keep);  // read again when the tile is stored
+            d[k] = gae_load_done4<ALIGNED>(dones, lo + i, valid);
+            // V of the step after this lane's four: the next lane has it, except for lane 31
+            vnext[k] = (lane == 31 && lo + i + 4 < n && i + 4 <= len + 3) ? __ldg(values + lo + i + 4) : 0.0f;
+        }
+#pragma unroll
+        for (int k = 0; k < INFLIGHT; ++k) {
+            const int q = h * INFLIGHT + k;
+            const int i = 4 * (q * THREADS + tid);
+            const float from_next_lane = __shfl_down_sync(0xFFFFFFFFu, v[k].x, 1);
+            const float v4 = (lane == 31) ? vnext[k] : from_next_lane;  // 0 past the end of the buffer
+            const bool d0 = (d[k] & 0xFFu) != 0, d1 = (d[k] & 0xFF00u) != 0, d2 = (d[k] & 0xFF0000u) != 0,
+                       d3 = (d[k] & 0xFF000000u) != 0;
+            float4 delta;
+            delta.x = (r[k].x + gamma * (d0 ? 0.0f : v[k].y)) - v[k].x;
+            delta.y = (r[k].y + gamma * (d1 ? 0.0f : v[k].z)) - v[k].y;
+            delta.z = (r[k].z + gamma * (d2 ? 0.0f : v[k].w)) - v[k].z;
+            delta.w = (r[k].w + gamma * (d3 ? 0.0f : v4)) - v[k].w;
+            *reinterpret_cast<float4*>(&g[i]) = delta;
+            const uint32_t b0 = __ballot_sync(0xFFFFFFFFu, d0), b1 = __ballot_sync(0xFFFFFFFFu, d1),
+                           b2 = __ballot_sync(0xFFFFFFFFu, d2), b3 = __ballot_sync(0xFFFFFFFFu, d3);
+            if (lane < 4)  // as they are: gae_locate interleaves them when an episode looks its end up
+                ballot[4 * (q * WARPS + warp) + lane] = lane == 0 ? b0 : (lane == 1 ? b1 : (lane == 2 ? b2 : b3));
+        }
+    }
+}
+
+// exclusive prefix over the blocks' done counts, by ONE warp after all ballots are written; pref[BLOCKS] = n_done
+template <int BLOCKS>
+__device__ __forceinline__ void gae_tile_prefix(const uint32_t* __restrict__ ballot, uint32_t* __restrict__ pref, int lane) {
+    constexpr int PER_LANE = (BLOCKS + 31) / 32;
+    uint32_t c[PER_LANE];
+    uint32_t sum = 0;
+#pragma unroll
+    for (int q = 0; q < PER_LANE; ++q) {
+        const int blk = lane * PER_LANE + q;
+        c[q] = blk < BLOCKS ? __popc(ballot[4 * blk]) + __popc(ballot[4 * blk + 1]) + __popc(ballot[4 * blk + 2]) +
+                                  __popc(ballot[4 * blk + 3])
+                            : 0u;
+        sum += c[q];
+    }
+    uint32_t incl = sum;
+    for (int off = 1; off < 32; off <<= 1) {
+        const uint32_t y = __shfl_up_sync(0xFFFFFFFFu, incl, off);
+        if (lane >= off) incl += y;
+    }
+    uint32_t run = incl - sum;
+#pragma unroll
+    for (int q = 0; q < PER_LANE; ++q) {
+        const int blk = lane * PER_LANE + q;
+        if (blk < BLOCKS) pref[blk] = run;
+        run += c[q];
+    }
+    if (lane == 31) pref[BLOCKS] = incl;
+}
+
+// phase 3: advantages from g[], V again from global (an L2 hit: loaded evict-last in phase 1, released here),
+// returns = adv + V, 128-bit streaming stores, fp64 moment sums m = {sum adv, sum adv^2, sum ret, sum ret^2}
+template <bool ALIGNED, int TILE, int THREADS, int INFLIGHT>
+__device__ __forceinline__ void gae_tile_store(const float* __restrict__ g, const float* __restrict__ values, int64_t lo,
+                                               int len, float* __restrict__ adv, float* __restrict__ ret, double (&m)[4],
+                                               int tid) {
+    constexpr int VEC = TILE / (4 * THREADS), PASSES = VEC / INFLIGHT;
+    const uint64_t once = l2_policy_evict_first();
+#pragma unroll
+    for (int h = 0; h < PASSES; ++h) {
+        float4 v[INFLIGHT];
+#pragma unroll
+        for (int k = 0; k < INFLIGHT; ++k) {
+            const int i = 4 * ((h * INFLIGHT + k) * THREADS + tid);
+            v[k] = gae_load4_hint<ALIGNED>(values, lo + i, max(0, min(4, len - i)), once);
+        }
+#pragma unroll
+        for (int k = 0; k < INFLIGHT; ++k) {
+            const int i = 4 * ((h * INFLIGHT + k) * THREADS + tid);
+            const int valid = max(0, min(4, len - i));
+            if (valid > 0) {
+                const float4 a = *reinterpret_cast<const float4*>(&g[i]);
+                const float4 rt = make_float4(a.x + v[k].x, a.y + v[k].y, a.z + v[k].z, a.w + v[k].w);
+                const float aa[4] = {a.x, a.y, a.z, a.w}, rr[4] = {rt.x, rt.y, rt.z, rt.w};
+                if (ALIGNED && valid == 4) {
+                    __stcs(reinterpret_cast<float4*>(adv + lo + i), a);
+                    __stcs(reinterpret_cast<float4*>(ret + lo + i), rt);
+                } else {
+                    for (int j = 0; j < valid; ++j) {
+                        adv[lo + i + j] = aa[j];
+                        ret[lo + i + j] = rr[j];
+                    }
+                }
+#pragma unroll
+                for (int j = 0; j < 4; ++j) {
+                    if (j < valid) {
+#ifndef G2048_GAE_SKIP_MOMENTS  // timing experiment only (tools/probes)
+                        const double da = (double)aa[j], dr = (double)rr[j];
+                        m[0] += da;
+                        m[1] = __fma_rn(da, da, m[1]);  // the product of two floats is exact in double either way
+                        m[2] += dr;
+                        m[3] = __fma_rn(dr, dr, m[3]);
+#endif
+                    }
+                }
+            }
+        }
+    }
 }
 
 }  // namespace g2048
