@@ -384,6 +384,23 @@ def main():
         "api": "g2048_play_host (C ABI, host buffers): key H2D + chain kernel + play kernel + D2H of final boards, lengths, "
                "scores (pinned host memory) and the statistics block + synchronise, per call; device workspace cached by the library",
     }
+    # the same call when only the episode statistics are wanted (what run_actions_max_tile returns): 256 B come back
+    so_times, so_steps = [], 0
+    for i in range(1 + min(args.steps, 5)):
+        barrier()
+        t0 = time.perf_counter()
+        N.call("g2048_play_host", policy_id, SEED + i, None, batch_global, lo, n, mode, None, None, None, h_stats.ctypes.data)
+        dt = time.perf_counter() - t0
+        if i >= 1:
+            so_times.append(dt)
+            so_steps += int(h_stats[1])
+    ts = torch.tensor([sum(so_times)], dtype=torch.float64, device=dev)
+    ss = torch.tensor([so_steps], dtype=torch.int64, device=dev)
+    if world > 1:
+        dist.all_reduce(ts, op=dist.ReduceOp.MAX)
+        dist.all_reduce(ss, op=dist.ReduceOp.SUM)
+    e2e["statistics_only"] = {"value": float(ss.item()) / float(ts.item()), "unit": "env-steps/s",
+                              "d2h_bytes_per_step": int(8 * N.PLAY_STATS_WORDS)}
 
     extras = {}
     if not args.no_extras and rank == 0:
