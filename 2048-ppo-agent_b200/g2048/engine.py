@@ -336,30 +336,39 @@ def unpack_flat_meta(meta: torch.Tensor):
     return actions, masks, term
 
 
-def gather_minibatch(indices: torch.Tensor, packed: dict, adv: torch.Tensor | None, ret: torch.Tensor | None,
-                     obs_dtype=torch.float32) -> dict:
-    """Minibatch `indices` (int64, device) of a flat packed buffer (RolloutBuffer.get_packed()) as the
-    tensors a PPO update consumes; one observation kernel + one scalar-gather kernel.  obs_dtype=None: no
-    observations -- the batch carries the gathered bitboards under "boards" for ppo.board_embedding."""
-    m = indices.shape[0]
-    dev = indices.device
-    out = dict(
+def minibatch_buffers(m: int, device, obs_dtype=torch.float32, with_gae: bool = True) -> dict:
+    """Output tensors of gather_minibatch for m samples (pass them back through `out=` to reuse them)."""
+    dev = device
+    return dict(
         observations=torch.empty((m, 16, 31), dtype=obs_dtype, device=dev) if obs_dtype is not None else None,
         actions=torch.empty(m, dtype=torch.int64, device=dev),
         action_masks=torch.empty((m, 4), dtype=torch.bool, device=dev),
         log_probs=torch.empty(m, dtype=torch.float32, device=dev),
         values=torch.empty(m, dtype=torch.float32, device=dev),
-        advantages=torch.empty(m, dtype=torch.float32, device=dev) if adv is not None else None,
-        returns=torch.empty(m, dtype=torch.float32, device=dev) if ret is not None else None,
+        advantages=torch.empty(m, dtype=torch.float32, device=dev) if with_gae else None,
+        returns=torch.empty(m, dtype=torch.float32, device=dev) if with_gae else None,
+        boards=torch.empty(m, dtype=torch.int64, device=dev) if obs_dtype is None else None,
     )
+
+
+def gather_minibatch(indices: torch.Tensor, packed: dict, adv: torch.Tensor | None, ret: torch.Tensor | None,
+                     obs_dtype=torch.float32, out: dict | None = None) -> dict:
+    """Minibatch `indices` (int64, device) of a flat packed buffer (RolloutBuffer.get_packed()) as the
+    tensors a PPO update consumes; one observation kernel + one scalar-gather kernel.  obs_dtype=None: no
+    observations -- the batch carries the gathered bitboards under "boards" for ppo.board_embedding.
+    out: tensors from minibatch_buffers() of the same size to write into instead of allocating."""
+    m = indices.shape[0]
+    if out is None:
+        out = minibatch_buffers(m, indices.device, obs_dtype, adv is not None)
+    else:
+        out = dict(out)
     call("g2048_gather_minibatch", ptr(indices), m, ptr(packed["boards"]), ptr(packed["meta"]), ptr(packed["log_probs"]),
          ptr(packed["values"]), ptr(adv), ptr(ret), _OBS_DTYPES[obs_dtype or torch.float32], ptr(out["observations"]), ptr(out["actions"]),
          ptr(out["action_masks"]), ptr(out["log_probs"]), ptr(out["values"]), ptr(out["advantages"]), ptr(out["returns"]),
          stream_ptr())
     if obs_dtype is None:
-        del out["observations"]
-        out["boards"] = packed["boards"][indices]
-    return out
+        torch.index_select(packed["boards"], 0, indices, out=out["boards"])
+    return {k: v for k, v in out.items() if v is not None}
 
 
 # ------------------------------------------------------------------------------------------- embedding

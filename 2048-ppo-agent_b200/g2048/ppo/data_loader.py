@@ -55,14 +55,15 @@ class DevicePPOBatches:
     per epoch (``max_samples_per_epoch`` / ``shuffle_on_reset``, :73-101) and the batch shuffle follow the
     reference's semantics; batches are dicts of DEVICE tensors with the item keys of ``PPODataset``
     (``actions`` are int64 indices -- the trainer's ``argmax`` of the one-hot, ppo_trainer.py:381).
-    ``obs_dtype=None`` leaves the observations out altogether: batches carry the 8-byte bitboards under
+    ``reuse_buffers=True`` writes the batches into two alternating sets of tensors (valid until the batch after the
+    next).  ``obs_dtype=None`` leaves the observations out altogether: batches carry the 8-byte bitboards under
     ``boards`` for ``board_embedding.forward_from_boards`` (the embedding becomes a row gather).
     """
 
     def __init__(self, packed: dict, gamma: float = 0.99, lambda_gae: float = 0.95, batch_size: int = 32,
                  shuffle: bool = True, drop_last: bool = True, max_samples_per_epoch: int = None,
                  shuffle_on_reset: bool = False, obs_dtype=torch.float32, generator: torch.Generator = None,
-                 group=None):
+                 group=None, reuse_buffers: bool = False):
         self.packed = packed
         self.batch_size = batch_size
         self.shuffle = shuffle
@@ -71,6 +72,10 @@ class DevicePPOBatches:
         self.shuffle_on_reset = shuffle_on_reset
         self.obs_dtype = obs_dtype
         self.generator = generator
+        # reuse_buffers: full-size batches are written into two alternating sets of tensors instead of fresh ones (a
+        # batch stays valid until the batch after the next is produced) -- saves eight allocations per minibatch
+        self.reuse_buffers = reuse_buffers
+        self._buffers, self._turn = [None, None], 0
         self.device = packed["rewards"].device
         self.total_length = packed["rewards"].shape[0]
         self.dones = meta_to_dones(packed["meta"]) if self.total_length else packed["meta"]
@@ -103,7 +108,13 @@ class DevicePPOBatches:
 
     def batch(self, indices: torch.Tensor) -> Dict[str, torch.Tensor]:
         """The minibatch of the given buffer positions (int64 device tensor)."""
-        return E.gather_minibatch(indices.contiguous(), self.packed, self.advantages, self.returns, self.obs_dtype)
+        out = None
+        if self.reuse_buffers and indices.shape[0] == self.batch_size:
+            self._turn ^= 1
+            if self._buffers[self._turn] is None:
+                self._buffers[self._turn] = E.minibatch_buffers(self.batch_size, self.device, self.obs_dtype)
+            out = self._buffers[self._turn]
+        return E.gather_minibatch(indices.contiguous(), self.packed, self.advantages, self.returns, self.obs_dtype, out=out)
 
     def __iter__(self):
         order = self._randperm(self.length) if self.shuffle else torch.arange(self.length, device=self.device)

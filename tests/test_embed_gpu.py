@@ -152,3 +152,28 @@ def test_validation():
         embed_boards(torch.zeros(256, 30, device="cuda"), boards)
     with pytest.raises(ValueError):
         E.embed_boards_grad(boards, torch.zeros(4, 16, 6, device="cuda"))
+
+
+def test_reused_minibatch_buffers_hold_the_same_batches():
+    import g2048
+    runner = g2048.BatchRunner(init_seed=5, act_fn=g2048.act_randomly)
+    buf = g2048.RolloutBuffer(31, 16, 4)
+    buf.store_packed(runner.run_packed_batch(64))
+    for obs_dtype in (torch.float32, None):
+        gens = [torch.Generator(device="cuda") for _ in range(2)]
+        for g in gens:
+            g.manual_seed(2)
+        fresh = g2048.DevicePPOBatches(buf.get_packed(), batch_size=100, drop_last=False, obs_dtype=obs_dtype, generator=gens[0])
+        reused = g2048.DevicePPOBatches(buf.get_packed(), batch_size=100, drop_last=False, obs_dtype=obs_dtype, generator=gens[1],
+                                        reuse_buffers=True)
+        previous, ptrs = None, set()
+        for a, b in zip(fresh, reused):
+            assert a.keys() == b.keys()
+            for k in a:
+                assert torch.equal(a[k], b[k]), k
+            if previous is not None and previous[1]["actions"].shape[0] == 100:  # the batch before stays valid
+                for k in previous[0]:
+                    assert torch.equal(previous[0][k], previous[1][k]), k
+            previous = (a, b)
+            ptrs.add(b["actions"].data_ptr())
+        assert len(ptrs) <= 3  # two alternating sets (+ a fresh one for the short last batch)

@@ -102,12 +102,16 @@ def main():
         return n
 
     n_samples, t_feed = timed(lambda: epochs(False))
+    batches_r = g2048.DevicePPOBatches(packed, 0.99, 0.95, batch_size=args.minibatch, max_samples_per_epoch=args.max_samples,
+                                       shuffle_on_reset=True, reuse_buffers=True)
+    epochs(False, batches_r)
+    _, t_feed_r = timed(lambda: epochs(False, batches_r))
     _, t_update = timed(lambda: epochs(True))
     report["minibatches"] = {"seconds_gather_only": t_feed, "samples": n_samples, "samples_per_sec": n_samples / t_feed,
-                             "seconds_with_stand_in_update": t_update}
+                             "seconds_with_stand_in_update": t_update, "seconds_gather_only_reused_buffers": t_feed_r}
     # the same epochs with bitboards instead of observations: the embedding becomes a row gather
     batches_b = g2048.DevicePPOBatches(packed, 0.99, 0.95, batch_size=args.minibatch, max_samples_per_epoch=args.max_samples,
-                                       shuffle_on_reset=True, obs_dtype=None)
+                                       shuffle_on_reset=True, obs_dtype=None, reuse_buffers=True)
     epochs(True, batches_b)  # warm-up of the embedding kernels
     _, t_feed_b = timed(lambda: epochs(False, batches_b))
     _, t_update_b = timed(lambda: epochs(True, batches_b))
