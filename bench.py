@@ -477,9 +477,11 @@ def secondary_measurements(E, N, torch, dev, flush_buf) -> dict:
                   log_probs=torch.rand(n_buf, device=dev), values=torch.rand(n_buf, device=dev))
     g_adv, g_ret = torch.rand(n_buf, device=dev), torch.rand(n_buf, device=dev)
     idx = torch.randperm(n_buf, device=dev)[:m].contiguous()
-    t = timed(lambda: E.gather_minibatch(idx, packed, g_adv, g_ret))
+    mb_out = E.minibatch_buffers(m, dev)
+    t = timed(lambda: E.gather_minibatch(idx, packed, g_adv, g_ret, out=mb_out))
     add("gather_minibatch (expand_obs_tma<float> + gather_scalars)", m * (8 + 8 + 1 + 16 + 1984 + 8 + 4 + 16), t,
-        "65536 random samples: 33 B gathered + 2012 B written per sample; includes the output allocations")
+        "65536 random samples: 33 B gathered + 2012 B written per sample; two launches into reused output tensors; 134 MB in all, a launch-bound size")
+    del mb_out
     del packed, g_adv, g_ret, idx
 
     # packed boards -> input embedding: 2^18 boards, d_model 256 (configs/model/transformer_combined.yaml)
