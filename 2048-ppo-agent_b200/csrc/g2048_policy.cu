@@ -18,16 +18,20 @@ policy_step_kernel(u64* __restrict__ boards, uint8_t* __restrict__ status, const
                    const uint32_t* __restrict__ sub_act, const uint32_t* __restrict__ sub_step, uint32_t batch_global,
                    uint32_t env_lo, int64_t n, u64* __restrict__ rec_boards, uint8_t* __restrict__ rec_meta,
                    float* __restrict__ rec_rewards, float* __restrict__ rec_log_probs, float* __restrict__ rec_values,
-                   int32_t* __restrict__ actions_out, const int32_t* __restrict__ step_index) {
-    const int64_t i = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
-    if (i >= n) return;
+                   int32_t* __restrict__ actions_out, const int32_t* __restrict__ step_index,
+                   const int64_t* __restrict__ env_ids, int64_t n_envs) {
+    const int64_t row = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
+    if (row >= n) return;
+    // live-env compaction: thread `row` serves env env_ids[row] of the shard; logits / values are compact (one row per
+    // live env), state, records and the RNG counter use the env's own index
+    const int64_t i = env_ids ? env_ids[row] : row;
     if (step_index) {
         // graph-replay form: the step number lives in device memory; sub keys of step t sit 4 words further per
         // step (act key, step key), the record slot n entries further
         const int64_t t = *step_index;
         sub_act += 4 * t;
         sub_step += 4 * t;
-        const int64_t at = t * n;
+        const int64_t at = t * n_envs;  // record rows are n_envs long whatever the number of live rows
         if (rec_boards) rec_boards += at;
         if (rec_meta) rec_meta += at;
         if (rec_rewards) rec_rewards += at;
@@ -39,7 +43,7 @@ policy_step_kernel(u64* __restrict__ boards, uint8_t* __restrict__ status, const
     // by a fresh one but still carries terminated=True; the wrapper clears it before stepping.
     if (auto_reset && (s.status & G2048_STATUS_DONE)) s.status &= ~(uint32_t)G2048_STATUS_DONE;
     const uint32_t lm = s.status & G2048_STATUS_MASK;
-    const Logits4 l = prepare_logits(logits[i], lm, use_mask != 0);
+    const Logits4 l = prepare_logits(logits[row], lm, use_mask != 0);
     int a;
     if (sample) {
         a = sample_categorical<MODE>(env_key<MODE>(sub_act, batch_global, env_lo, i), l);
@@ -69,7 +73,7 @@ policy_step_kernel(u64* __restrict__ boards, uint8_t* __restrict__ status, const
     if (rec_meta) rec_meta[i] = (uint8_t)((uint32_t)a | (lm << 2) | (done ? 0x40u : 0u));
     if (rec_rewards) rec_rewards[i] = r;
     if (rec_log_probs) rec_log_probs[i] = lp;
-    if (rec_values && values) rec_values[i] = values[i];
+    if (rec_values && values) rec_values[i] = values[row];
     if (actions_out) actions_out[i] = a;
 }
 
@@ -122,8 +126,8 @@ static inline bool aligned16(const void* p) { return ((uintptr_t)p & 15u) == 0; 
 
 static int launch_policy_step(uint64_t* d_boards, uint8_t* d_status, const float* d_logits, const float* d_values,
                               int use_mask, int sample, int auto_reset, const uint32_t* d_sub_act,
-                              const uint32_t* d_sub_step, const int32_t* d_step_index, int64_t batch_global,
-                              int64_t env_lo, int64_t n, int rng_mode, uint64_t* d_rec_boards, uint8_t* d_rec_meta,
+                              const uint32_t* d_sub_step, const int32_t* d_step_index, const int64_t* d_env_ids,
+                              int64_t n_rows, int64_t batch_global, int64_t env_lo, int64_t n, int rng_mode, uint64_t* d_rec_boards, uint8_t* d_rec_meta,
                               float* d_rec_rewards, float* d_rec_log_probs, float* d_rec_values, int32_t* d_actions_out,
                               void* stream) {
     G2048_REQUIRE(valid_mode(rng_mode) && valid_batch(batch_global, env_lo, n), "policy_step: batch");
@@ -131,18 +135,24 @@ static int launch_policy_step(uint64_t* d_boards, uint8_t* d_status, const float
     G2048_REQUIRE(d_boards && d_status && d_logits && d_sub_step && (d_sub_act || !sample), "policy_step: pointers");
     G2048_REQUIRE(aligned16(d_logits), "policy_step: logits must be 16-byte aligned (n,4) float32");
     const uint32_t* sub_act = d_sub_act ? d_sub_act : d_sub_step;
-    const unsigned g = blocks_for(n, 256);
+    if (d_env_ids) {
+        G2048_REQUIRE(n_rows >= 0 && n_rows <= n, "policy_step: more rows than envs");
+        if (n_rows == 0) return G2048_OK;
+    } else {
+        n_rows = n;
+    }
+    const unsigned g = blocks_for(n_rows, 256);
     cudaStream_t st = (cudaStream_t)stream;
     if (rng_mode == G2048_RNG_PARTITIONABLE) {
         policy_step_kernel<G2048_RNG_PARTITIONABLE><<<g, 256, 0, st>>>(
             (u64*)d_boards, d_status, (const float4*)d_logits, d_values, use_mask, sample, auto_reset, sub_act,
-            d_sub_step, (uint32_t)batch_global, (uint32_t)env_lo, n, (u64*)d_rec_boards, d_rec_meta, d_rec_rewards,
-            d_rec_log_probs, d_rec_values, d_actions_out, d_step_index);
+            d_sub_step, (uint32_t)batch_global, (uint32_t)env_lo, n_rows, (u64*)d_rec_boards, d_rec_meta, d_rec_rewards,
+            d_rec_log_probs, d_rec_values, d_actions_out, d_step_index, d_env_ids, n);
     } else {
         policy_step_kernel<G2048_RNG_ORIGINAL><<<g, 256, 0, st>>>(
             (u64*)d_boards, d_status, (const float4*)d_logits, d_values, use_mask, sample, auto_reset, sub_act,
-            d_sub_step, (uint32_t)batch_global, (uint32_t)env_lo, n, (u64*)d_rec_boards, d_rec_meta, d_rec_rewards,
-            d_rec_log_probs, d_rec_values, d_actions_out, d_step_index);
+            d_sub_step, (uint32_t)batch_global, (uint32_t)env_lo, n_rows, (u64*)d_rec_boards, d_rec_meta, d_rec_rewards,
+            d_rec_log_probs, d_rec_values, d_actions_out, d_step_index, d_env_ids, n);
     }
     G2048_CHECK_LAUNCH("policy_step");
     return G2048_OK;
@@ -154,8 +164,21 @@ extern "C" int g2048_policy_step(uint64_t* d_boards, uint8_t* d_status, const fl
                                  int rng_mode, uint64_t* d_rec_boards, uint8_t* d_rec_meta, float* d_rec_rewards,
                                  float* d_rec_log_probs, float* d_rec_values, int32_t* d_actions_out, void* stream) {
     return launch_policy_step(d_boards, d_status, d_logits, d_values, use_mask, sample, auto_reset, d_sub_act, d_sub_step,
-                              nullptr, batch_global, env_lo, n, rng_mode, d_rec_boards, d_rec_meta, d_rec_rewards,
+                              nullptr, nullptr, 0, batch_global, env_lo, n, rng_mode, d_rec_boards, d_rec_meta, d_rec_rewards,
                               d_rec_log_probs, d_rec_values, d_actions_out, stream);
+}
+
+extern "C" int g2048_policy_step_live(uint64_t* d_boards, uint8_t* d_status, const float* d_logits, const float* d_values,
+                                      int use_mask, int sample, int auto_reset, const uint32_t* d_sub_act,
+                                      const uint32_t* d_sub_step, const int64_t* d_env_ids, int64_t n_live,
+                                      int64_t batch_global, int64_t env_lo, int64_t n, int rng_mode, uint64_t* d_rec_boards,
+                                      uint8_t* d_rec_meta, float* d_rec_rewards, float* d_rec_log_probs, float* d_rec_values,
+                                      int32_t* d_actions_out, void* stream) {
+    G2048_REQUIRE(d_env_ids || n_live == 0, "policy_step_live: env ids");
+    if (n_live == 0) return G2048_OK;
+    return launch_policy_step(d_boards, d_status, d_logits, d_values, use_mask, sample, auto_reset, d_sub_act, d_sub_step,
+                              nullptr, d_env_ids, n_live, batch_global, env_lo, n, rng_mode, d_rec_boards, d_rec_meta,
+                              d_rec_rewards, d_rec_log_probs, d_rec_values, d_actions_out, stream);
 }
 
 extern "C" int g2048_policy_step_at(uint64_t* d_boards, uint8_t* d_status, const float* d_logits, const float* d_values,
@@ -165,7 +188,7 @@ extern "C" int g2048_policy_step_at(uint64_t* d_boards, uint8_t* d_status, const
                                     float* d_rec_log_probs, float* d_rec_values, int32_t* d_actions_out, void* stream) {
     G2048_REQUIRE(d_subs && d_step_index, "policy_step_at: sub keys and step index");
     return launch_policy_step(d_boards, d_status, d_logits, d_values, use_mask, sample, auto_reset, d_subs, d_subs + 2,
-                              d_step_index, batch_global, env_lo, n, rng_mode, d_rec_boards, d_rec_meta, d_rec_rewards,
+                              d_step_index, nullptr, 0, batch_global, env_lo, n, rng_mode, d_rec_boards, d_rec_meta, d_rec_rewards,
                               d_rec_log_probs, d_rec_values, d_actions_out, stream);
 }
 

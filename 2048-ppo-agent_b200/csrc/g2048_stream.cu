@@ -146,6 +146,14 @@ extern "C" int g2048_expand_obs(const uint64_t* d_boards, int64_t n, int dtype, 
     return launch_expand_obs(d_boards, n, dtype, d_out, rows, n_cols, nullptr, stream);
 }
 
+// out[i] = one-hot of d_boards[d_indices[i]], i < m (live-env compaction of the network-policy loop; the minibatch
+// gather uses the same kernel)
+extern "C" int g2048_expand_obs_gather(const uint64_t* d_boards, const int64_t* d_indices, int64_t m, int dtype, void* d_out,
+                                       void* stream) {
+    G2048_REQUIRE(d_indices || m == 0, "expand_obs_gather: indices");
+    return launch_expand_obs(d_boards, m, dtype, d_out, 0, 0, d_indices, stream);
+}
+
 // ------------------------------------------------------------------------------------------------
 // minibatch gather (replaces PPODataset.__getitem__ + DataLoader collation,
 // src/ppo/data_loader.py:132-166,217-223, on the packed device buffer)

@@ -63,6 +63,8 @@ _SIGNATURES = {
     "g2048_policy_step": (_INT, [_P, _P, _P, _P, _INT, _INT, _INT, _P, _P, _I64, _I64, _I64, _INT, _P, _P, _P, _P, _P, _P, _P]),
     "g2048_policy_step_at": (_INT, [_P, _P, _P, _P, _INT, _INT, _INT, _P, _P, _I64, _I64, _I64, _INT, _P, _P, _P, _P, _P, _P, _P]),
     "g2048_counter_add": (_INT, [_P, _INT, _P]),
+    "g2048_policy_step_live": (_INT, [_P, _P, _P, _P, _INT, _INT, _INT, _P, _P, _P, _I64, _I64, _I64, _I64, _INT, _P, _P, _P, _P, _P, _P, _P]),
+    "g2048_expand_obs_gather": (_INT, [_P, _P, _I64, _INT, _P, _P]),
     "g2048_sample_logits": (_INT, [_P, _P, _INT, _INT, _P, _I64, _I64, _I64, _INT, _P, _P, _P, _P]),
     "g2048_evaluate_logits": (_INT, [_P, _P, _INT, _P, _I64, _P, _P, _P]),
     "g2048_expand_obs": (_INT, [_P, _I64, _INT, _P, _I64, _I64, _P]),

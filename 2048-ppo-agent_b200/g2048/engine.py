@@ -219,6 +219,20 @@ def policy_step_at(boards, status, logits, values, use_mask: bool, sample: bool,
          ptr(rec_meta), ptr(rec_rewards), ptr(rec_log_probs), ptr(rec_values), ptr(actions_out), stream_ptr())
 
 
+def policy_step_live(boards, status, logits, values, use_mask: bool, sample: bool, auto_reset: bool, sub_act, sub_step,
+                     env_ids: torch.Tensor, batch_global: int, env_lo: int, rng_mode: int, rec_boards=None, rec_meta=None,
+                     rec_rewards=None, rec_log_probs=None, rec_values=None, actions_out=None) -> None:
+    """policy_step for the live envs only: logits / values have one row per entry of env_ids (int64 local env
+    indices); state, RNG counters and record slots are the envs' own."""
+    m, n = env_ids.shape[0], boards.shape[0]
+    assert env_ids.dtype == torch.int64 and logits.dtype == torch.float32 and logits.shape == (m, 4)
+    if values is not None:
+        assert values.dtype == torch.float32 and values.numel() == m
+    call("g2048_policy_step_live", ptr(boards), ptr(status), ptr(logits), ptr(values), int(use_mask), int(sample),
+         int(auto_reset), ptr(sub_act), ptr(sub_step), ptr(env_ids), m, batch_global, env_lo, n, rng_mode, ptr(rec_boards),
+         ptr(rec_meta), ptr(rec_rewards), ptr(rec_log_probs), ptr(rec_values), ptr(actions_out), stream_ptr())
+
+
 def counter_add(counter: torch.Tensor, delta: int = 1) -> None:
     """counter (int32 device scalar) += delta, on the stream."""
     assert counter.dtype == torch.int32
@@ -259,6 +273,15 @@ def expand_obs(boards: torch.Tensor, dtype=torch.float32, rows: int = 0, n_cols:
     if out is None:
         out = torch.empty((n, 16, 31), dtype=dtype, device=boards.device)
     call(entry, ptr(boards), n, _OBS_DTYPES[dtype], ptr(out), rows, n_cols, stream_ptr())
+    return out
+
+
+def expand_obs_gather(boards: torch.Tensor, indices: torch.Tensor, dtype=torch.float32, out=None) -> torch.Tensor:
+    """One-hot (m,16,31) of boards[indices] (int64 indices) without materialising the gathered boards."""
+    m = indices.shape[0]
+    if out is None:
+        out = torch.empty((m, 16, 31), dtype=dtype, device=boards.device)
+    call("g2048_expand_obs_gather", ptr(boards), ptr(indices), m, _OBS_DTYPES[dtype], ptr(out), stream_ptr())
     return out
 
 

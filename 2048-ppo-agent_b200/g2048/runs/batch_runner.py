@@ -66,7 +66,7 @@ class BatchRunner:
     """Runs batches of 2048 envs with an action function (reference: batch_runner.py:10-37)."""
 
     def __init__(self, init_seed: int, act_fn: Callable = None, rng_mode=None, device=None,
-                 shard: tuple[int, int] | None = None, cuda_graph: bool = False):
+                 shard: tuple[int, int] | None = None, cuda_graph: bool = False, compact_live: bool = False):
         """
         init_seed : seed of the runner's key chain (jax.random.key(seed), batch_runner.py:32)
         act_fn    : policy, see the module docstring; may be set later through ``.act_fn``
@@ -77,6 +77,12 @@ class BatchRunner:
                     (observation -> network forward -> sample + env.step + record) as a CUDA graph and replay it,
                     with one host synchronisation per CHUNK_STEPS steps instead of one per step (SURVEY 8f
                     rank 3).  Same records as the eager loop.
+        compact_live: with a ``TorchActionFunction``, ``run_packed_batch`` feeds only the envs that are still alive
+                    to the network (the reference pushes the finished ones through it until the last env ends,
+                    batch_runner.py:117-136 -- about two thirds of the rows of a run to termination).  Env state, RNG
+                    counters and record slots stay per env, so a live env's trajectory does not depend on who else
+                    is alive; records of steps after an env's end are zero instead of repeating its frozen state
+                    (``RolloutBuffer`` never reads them).  The reference-format calls ignore the flag.
         """
         self.device = N.require_cuda() if device is None else torch.device(device)
         self.rng_mode = E.resolve_rng_mode(rng_mode)
@@ -84,6 +90,7 @@ class BatchRunner:
         self.shard = shard
         self._act_fn = act_fn
         self.cuda_graph = cuda_graph
+        self.compact_live = compact_live
         self._graphs = {}  # (batch_size, lo, n, steps, auto_reset) -> captured step of the current act_fn
 
     # -- reference surface ---------------------------------------------------------------------
@@ -114,7 +121,7 @@ class BatchRunner:
         """-> (observations (B,T,4,4,31) bool, actions (B,T) int32, action_masks (B,T,4) bool,
         log_probs (B,T) f32 | None, values (B,T) f32 | None, rewards (B,T) f32, terminations (B,T) bool),
         numpy arrays stacked like batch_runner.py:138-154."""
-        ro = self.run_packed_batch(batch_size)
+        ro = self._run(batch_size, keep_states=False, full_records=True)
         t, b = ro.t_steps, ro.batch_size
         obs = E.expand_obs(ro.boards, torch.bool, rows=t, n_cols=b)
         un = E.unpack_records(ro.meta, ro.rewards, ro.log_probs, ro.values, t, b)
@@ -135,8 +142,9 @@ class BatchRunner:
 
     # -- engine-native results -----------------------------------------------------------------
     def run_packed_batch(self, batch_size: int) -> PackedRollout:
-        """Same run as ``run_actions_batch`` but the records stay packed on the device."""
-        return self._run(batch_size, keep_states=False)
+        """Same run as ``run_actions_batch`` but the records stay packed on the device (with ``compact_live`` the
+        slots of steps after an env's end are zero)."""
+        return self._run(batch_size, keep_states=False, full_records=False)
 
     def run_stats_batch(self, batch_size: int, per_env: bool = True) -> dict:
         """Play to termination and return only per-episode results (final boards, lengths, scores)
@@ -190,7 +198,8 @@ class BatchRunner:
 
         return all_ranks_true(done_count == n, self.device)
 
-    def _run(self, batch_size: int, keep_states: bool):
+    def _run(self, batch_size: int, keep_states: bool, full_records: bool = True):
+        """full_records: the caller reads the records of finished envs too (reference-format outputs)."""
         self._check(batch_size)
         lo, n = self._range(batch_size)
         dev, mode = self.device, self.rng_mode
@@ -201,6 +210,8 @@ class BatchRunner:
         is_net = hasattr(self._act_fn, "forward_logits")
         if self.cuda_graph and is_net and not keep_states:
             return self._run_net_graphed(batch_size, lo, n, boards, status)
+        compact = self.compact_live and is_net and not keep_states and not full_records
+        live_ids = None  # int64 local indices of the envs still alive (compact mode), refreshed when some finish
         counters = torch.zeros(4, dtype=torch.int64, device=dev)
         chunks = []  # (boards, meta, rewards, log_probs, values) per chunk, time-major
         t0 = 0
@@ -210,11 +221,12 @@ class BatchRunner:
             # a run whose envs are all finished at init cannot happen (two tiles on an empty board)
             steps = 1 if keep_states else CHUNK_STEPS
             subs = self.chain.peek(1 + 2 * (t0 + steps))
-            rb = torch.empty((steps, n), dtype=torch.int64, device=dev)
-            rm = torch.empty((steps, n), dtype=torch.uint8, device=dev)
-            rr = torch.empty((steps, n), dtype=torch.float32, device=dev)
-            rl = torch.empty((steps, n), dtype=torch.float32, device=dev) if want_lp else None
-            rv = torch.empty((steps, n), dtype=torch.float32, device=dev) if want_v else None
+            alloc = torch.zeros if compact else torch.empty  # compact mode leaves finished envs' slots untouched
+            rb = alloc((steps, n), dtype=torch.int64, device=dev)
+            rm = alloc((steps, n), dtype=torch.uint8, device=dev)
+            rr = alloc((steps, n), dtype=torch.float32, device=dev)
+            rl = alloc((steps, n), dtype=torch.float32, device=dev) if want_lp else None
+            rv = alloc((steps, n), dtype=torch.float32, device=dev) if want_v else None
             if policy is not None:
                 E.rollout_steps(policy, boards, status, subs[1 + 2 * t0:], steps, t0, batch_size, lo, mode,
                                 rb, rm, rr, rl, counters)
@@ -226,9 +238,15 @@ class BatchRunner:
                 for k in range(steps):
                     t = t0 + k
                     sub_act, sub_step = subs[1 + 2 * t], subs[2 + 2 * t]
-                    step_fn = self._net_step if is_net else self._callable_step
-                    rl_k, rv_k = step_fn(boards, status, sub_act, sub_step, batch_size, lo, mode, rb[k], rm[k], rr[k],
-                                         None if rl is None else rl[k], None if rv is None else rv[k])
+                    if compact:
+                        if live_ids is None:
+                            live_ids = torch.nonzero((status & N.STATUS_DONE) == 0).flatten()
+                        rl_k, rv_k = self._net_step_live(boards, status, live_ids, sub_act, sub_step, batch_size, lo, mode,
+                                                         rb[k], rm[k], rr[k], rl[k], rv[k])
+                    else:
+                        step_fn = self._net_step if is_net else self._callable_step
+                        rl_k, rv_k = step_fn(boards, status, sub_act, sub_step, batch_size, lo, mode, rb[k], rm[k], rr[k],
+                                             None if rl is None else rl[k], None if rv is None else rv[k])
                     if rl_k is None:
                         rl = None  # the policy returns no log-probs (like act_drul)
                     if rv_k is None:
@@ -237,6 +255,8 @@ class BatchRunner:
                         states.append(State(boards.clone(), status.clone(), rr[k].clone()))
                     # the reference checks `all done` after every step (batch_runner.py:117)
                     done_now = int(((status & N.STATUS_DONE) != 0).sum().item())
+                    if compact and live_ids is not None and n - done_now != live_ids.shape[0]:
+                        live_ids = None  # some envs finished on this step: rebuild the list before the next one
                     if self._all_done(done_now, n):
                         steps_used = k + 1
                         rb, rm, rr = rb[:steps_used], rm[:steps_used], rr[:steps_used]
@@ -357,6 +377,15 @@ class BatchRunner:
         rb, rm, rr, rl, rv = (x[:t_total].contiguous() for x in (rb, rm, rr, rl, rv))
         return PackedRollout(rb, rm, rr, rl, rv, g["boards"].clone(), g["status"].clone(), t_total, n,
                              int(lengths.sum().item()))
+
+    def _net_step_live(self, boards, status, live_ids, sub_act, sub_step, batch_size, lo, mode, rb, rm, rr, rl, rv):
+        fn = self._act_fn
+        if live_ids.shape[0]:  # a shard whose envs are all finished waits for the other ranks
+            obs = E.expand_obs_gather(boards, live_ids, fn.obs_dtype)
+            logits, values = fn.forward_logits(obs)
+            E.policy_step_live(boards, status, logits, values, fn.use_mask, fn.sample_actions, False, sub_act, sub_step,
+                               live_ids, batch_size, lo, mode, rb, rm, rr, rl, rv)
+        return rl, rv
 
     def _net_step(self, boards, status, sub_act, sub_step, batch_size, lo, mode, rb, rm, rr, rl, rv):
         fn = self._act_fn

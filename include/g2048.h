@@ -190,6 +190,17 @@ int g2048_policy_step_at(uint64_t* d_boards, uint8_t* d_status, const float* d_l
                          uint64_t* d_rec_boards, uint8_t* d_rec_meta, float* d_rec_rewards, float* d_rec_log_probs,
                          float* d_rec_values, int32_t* d_actions_out, void* stream);
 
+/* The same step for a COMPACT list of live envs (what the reference's loop would not need to feed to the network:
+ * finished envs only repeat their frozen state, src/runs/batch_runner.py:117-136).  Row i < n_live of d_logits /
+ * d_values belongs to env d_env_ids[i] (local index in [0, n)); state, RNG counter and record slot are the env's own,
+ * so the live envs' trajectories do not depend on who else is still alive.  Records of envs not listed stay as
+ * they are. */
+int g2048_policy_step_live(uint64_t* d_boards, uint8_t* d_status, const float* d_logits, const float* d_values,
+                           int use_mask, int sample, int auto_reset, const uint32_t* d_sub_act, const uint32_t* d_sub_step,
+                           const int64_t* d_env_ids, int64_t n_live, int64_t batch_global, int64_t env_lo, int64_t n,
+                           int rng_mode, uint64_t* d_rec_boards, uint8_t* d_rec_meta, float* d_rec_rewards,
+                           float* d_rec_log_probs, float* d_rec_values, int32_t* d_actions_out, void* stream);
+
 /* *d_counter += delta on the stream (one thread): advances the device-resident step number between replays. */
 int g2048_counter_add(int32_t* d_counter, int32_t delta, void* stream);
 
@@ -215,6 +226,9 @@ int g2048_expand_obs(const uint64_t* d_boards, int64_t n, int dtype, void* d_out
 /* First-generation kernel (one 16-byte chunk per thread, plain stores); same arguments. */
 int g2048_expand_obs_v1(const uint64_t* d_boards, int64_t n, int dtype, void* d_out, int64_t rows, int64_t n_cols,
                         void* stream);
+/* d_out[i] = one-hot observation of d_boards[d_indices[i]], i < m (int64 indices) */
+int g2048_expand_obs_gather(const uint64_t* d_boards, const int64_t* d_indices, int64_t m, int dtype, void* d_out,
+                            void* stream);
 
 /* Inverse of g2048_expand_obs: argmax over the 31 channels of every cell (the
  * `observations.argmax(-1)` of src/runs/run_actions_max_tile.py:61-63).  dtype BOOL or F32. */

@@ -44,6 +44,13 @@ def run_all(E, g2048, T=torch, dev="cuda"):
         E.counter_add(step_index, ch - 1)  # last record slot
         E.policy_step_at(boards, status, logits, values, True, True, True, subs[7:].contiguous(), step_index, 1000, 17, mode,
                          rb, rm, rr, rl, T.empty((ch, n), dtype=torch.float32, device=dev))
+        live = torch.nonzero((status & 16) == 0).flatten()[::3].contiguous()
+        if live.numel():
+            E.expand_obs_gather(boards, live, torch.float32)
+            E.expand_obs_gather(boards, live, torch.bool)
+            E.policy_step_live(boards, status, torch.randn(live.numel(), 4, device=dev), torch.randn(live.numel(), device=dev),
+                               True, True, False, subs[5], subs[6], live, 1000, 17, mode, rb[1], rm[1], rr[1], rl[1],
+                               T.zeros((n,), dtype=torch.float32, device=dev))
         E.sample_logits(logits, status, True, True, subs[5], 1000, 17, mode, want_entropy=True)
         E.evaluate_logits(logits, status, True, acts)
         E.unpack_records(rm, rr, rl, None, ch, n)

@@ -177,3 +177,48 @@ def test_fixed_horizon_checkpoint_resumes_env_state_and_key_chain():
         assert torch.equal(getattr(want, name), getattr(got, name)), name
     with pytest.raises(ValueError):
         _fixed(False, n=50).load_state_dict(saved)
+
+
+# ---------------------------------------------------------------------------- live-env compaction
+class RowwiseAgent(torch.nn.Module):
+    """Every output row is computed from its input row with a fixed operation order (elementwise product and a
+    row sum, no GEMM), so a row's logits do not depend on which other rows are in the batch."""
+
+    def __init__(self):
+        super().__init__()
+        g = torch.Generator().manual_seed(11)
+        self.w = torch.nn.Parameter(torch.randn(5, 496, generator=g) * 0.3)
+
+    def forward(self, obs, mask=None):
+        x = obs.reshape(obs.shape[0], 1, 496)
+        out = (x * self.w.unsqueeze(0)).sum(dim=2)
+        return out[:, :4], out[:, 4:5]
+
+
+def test_feeding_only_live_envs_keeps_their_trajectories():
+    import g2048
+    make = lambda compact: g2048.BatchRunner(  # noqa: E731
+        init_seed=21, act_fn=g2048.TorchActionFunction(RowwiseAgent(), use_mask=True, device=torch.device("cuda")),
+        compact_live=compact)
+    full, compact = make(False), make(True)
+    for _ in range(2):
+        a, b = full.run_packed_batch(200), compact.run_packed_batch(200)
+        assert a.t_steps == b.t_steps and a.env_steps == b.env_steps
+        assert torch.equal(a.final_boards, b.final_boards) and torch.equal(a.final_status, b.final_status)
+        la = a.lengths().long()
+        assert torch.equal(la, b.lengths().long())
+        alive = torch.arange(a.t_steps, device="cuda").unsqueeze(1) < la.unsqueeze(0)  # (T, n): steps up to the env's end
+        for name in ("boards", "meta", "rewards", "log_probs", "values"):
+            x, y = getattr(a, name), getattr(b, name)
+            assert torch.equal(x[alive], y[alive]), name
+            assert bool((y[~alive] == 0).all()), name  # untouched slots
+        ba, bb = g2048.RolloutBuffer(31, 16, 4), g2048.RolloutBuffer(31, 16, 4)
+        assert ba.store_packed(a) == bb.store_packed(b)
+        pa, pb = ba.get_packed(), bb.get_packed()
+        for k in pa:
+            assert torch.equal(pa[k], pb[k]), k
+        assert (full.key == compact.key).all()
+    # the reference-format call is unaffected by the flag
+    out_a, out_b = full.run_actions_batch(8), compact.run_actions_batch(8)
+    for x, y in zip(out_a, out_b):
+        assert (x == y).all()

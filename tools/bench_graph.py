@@ -1,4 +1,4 @@
-"""Eager vs CUDA-graph rollout loop with a network policy.
+"""Eager vs CUDA-graph vs live-env-compacting rollout loop with a network policy.
 A small transformer stands in for the reference's PPOAgent (d_model 256, 4 layers); the network is PyTorch either
 way -- what changes is launch overhead and the per-step host synchronisation.  Prints one JSON object."""
 import json
@@ -45,19 +45,21 @@ def main():
     out = {}
     for make, n in ((SmallAgent, 1024), (SmallAgent, 16384), (Agent, 256), (Agent, 4096)):
         row = {}
-        for graph in (False, True):
+        for mode in ("eager", "graph", "compact"):
+            graph = mode == "graph"
             torch.manual_seed(0)
             fn = g2048.TorchActionFunction(make().cuda(), use_mask=True, device=torch.device("cuda"))
-            runner = g2048.BatchRunner(init_seed=2, act_fn=fn, cuda_graph=graph)
+            runner = g2048.BatchRunner(init_seed=2, act_fn=fn, cuda_graph=graph, compact_live=mode == "compact")
             runner.run_packed_batch(n)  # warm-up (+ capture)
             torch.cuda.synchronize()
             t0 = time.perf_counter()
             ro = runner.run_packed_batch(n)
             torch.cuda.synchronize()
             dt = time.perf_counter() - t0
-            row["graph" if graph else "eager"] = {"seconds": dt, "loop_steps": ro.t_steps, "ms_per_loop_step": 1e3 * dt / ro.t_steps,
-                                                  "env_steps_per_sec": ro.env_steps / dt}
+            row[mode] = {"seconds": dt, "loop_steps": ro.t_steps, "ms_per_loop_step": 1e3 * dt / ro.t_steps,
+                         "env_steps_per_sec": ro.env_steps / dt, "live_fraction": ro.env_steps / (ro.t_steps * n)}
         row["speedup"] = row["eager"]["seconds"] / row["graph"]["seconds"] * row["graph"]["loop_steps"] / row["eager"]["loop_steps"]
+        row["speedup_compact"] = row["eager"]["ms_per_loop_step"] / row["compact"]["ms_per_loop_step"]
         out[f"{make.__name__},envs={n}"] = row
     print(json.dumps(out, indent=1))
 
