@@ -227,44 +227,50 @@ __global__ void __launch_bounds__(256)
 rollout_steps_kernel(u64* __restrict__ boards, uint8_t* __restrict__ status, const uint2* __restrict__ subs,
                      int n_steps, uint32_t t0, uint32_t batch_global, uint32_t env_lo, int64_t n,
                      u64* __restrict__ rec_boards, uint8_t* __restrict__ rec_meta, float* __restrict__ rec_rewards,
-                     float* __restrict__ rec_log_probs, unsigned long long* __restrict__ counters) {
-    const int64_t i = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
-    if (i >= n) return;
-    EnvState s{boards[i], status[i]};
-    const uint32_t e = env_lo + (uint32_t)i;
+                     float* __restrict__ rec_log_probs, unsigned long long* __restrict__ counters,
+                     const int64_t* __restrict__ env_ids, int64_t n_rows) {
+    // env_ids (live form): thread `row` serves env env_ids[row]; an env that finishes leaves the loop, and the record
+    // slots of the steps after its end are not written (the reference's records repeat the frozen state there).
+    const int64_t row = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
     unsigned long long live_steps = 0, reward_sum = 0;
-    for (int t = 0; t < n_steps; ++t) {
-        const uint2 sa = __ldg(&subs[2 * t]);
-        const uint2 ss = __ldg(&subs[2 * t + 1]);
-        const uint32_t lm = s.status & G2048_STATUS_MASK;
-        const bool was_done = (s.status & G2048_STATUS_DONE) != 0u;
-        int a;
-        float lp = 0.0f;
-        if (POLICY == G2048_POLICY_RANDOM) {
-            a = act_random<MODE>(split_at<MODE>(Key{sa.x, sa.y}, batch_global, e), lm);
-            lp = act_random_log_prob(lm);
-        } else {
-            a = act_drul(lm);
-        }
-        const u64 pre = s.board;
-        const float r = env_step<MODE>(s, a, split_at<MODE>(Key{ss.x, ss.y}, batch_global, e));
-        const bool done = (s.status & G2048_STATUS_DONE) != 0u;
-        const int64_t o = (int64_t)t * n + i;
-        rec_boards[o] = pre;
-        rec_meta[o] = (uint8_t)((uint32_t)a | (lm << 2) | (done ? 0x40u : 0u));
-        rec_rewards[o] = r;
-        if (rec_log_probs) rec_log_probs[o] = lp;
-        if (!was_done) {
-            live_steps += 1;
-            if (r > 0.0f) reward_sum += (unsigned long long)r;
-            if (done) {
-                atomicAdd(&counters[0], 1ull);
-                atomicMax(&counters[1], (unsigned long long)(t0 + (uint32_t)t + 1u));
+    if (row < n_rows) {  // no early return: every lane of the warp takes part in the shuffles below
+        const int64_t i = env_ids ? env_ids[row] : row;
+        EnvState s{boards[i], status[i]};
+        const uint32_t e = env_lo + (uint32_t)i;
+        for (int t = 0; t < n_steps; ++t) {
+            const uint2 sa = __ldg(&subs[2 * t]);
+            const uint2 ss = __ldg(&subs[2 * t + 1]);
+            const uint32_t lm = s.status & G2048_STATUS_MASK;
+            const bool was_done = (s.status & G2048_STATUS_DONE) != 0u;
+            int a;
+            float lp = 0.0f;
+            if (POLICY == G2048_POLICY_RANDOM) {
+                a = act_random<MODE>(split_at<MODE>(Key{sa.x, sa.y}, batch_global, e), lm);
+                lp = act_random_log_prob(lm);
+            } else {
+                a = act_drul(lm);
             }
+            const u64 pre = s.board;
+            const float r = env_step<MODE>(s, a, split_at<MODE>(Key{ss.x, ss.y}, batch_global, e));
+            const bool done = (s.status & G2048_STATUS_DONE) != 0u;
+            const int64_t o = (int64_t)t * n + i;
+            rec_boards[o] = pre;
+            rec_meta[o] = (uint8_t)((uint32_t)a | (lm << 2) | (done ? 0x40u : 0u));
+            rec_rewards[o] = r;
+            if (rec_log_probs) rec_log_probs[o] = lp;
+            if (!was_done) {
+                live_steps += 1;
+                if (r > 0.0f) reward_sum += (unsigned long long)r;
+                if (done) {
+                    atomicAdd(&counters[0], 1ull);
+                    atomicMax(&counters[1], (unsigned long long)(t0 + (uint32_t)t + 1u));
+                }
+            }
+            if (env_ids && done) break;
         }
+        boards[i] = s.board;
+        status[i] = (uint8_t)s.status;
     }
-    boards[i] = s.board;
-    status[i] = (uint8_t)s.status;
     // warp-aggregate the two sums
     for (int off = 16; off > 0; off >>= 1) {
         live_steps += __shfl_down_sync(0xFFFFFFFFu, live_steps, off);
@@ -537,23 +543,27 @@ extern "C" int g2048_play_host(int policy, uint64_t seed, uint32_t* h_key_io, in
     return rc;
 }
 
-extern "C" int g2048_rollout_steps(int policy, uint64_t* d_boards, uint8_t* d_status, const uint32_t* d_subs,
-                                   int64_t n_steps, int64_t t0, int64_t batch_global, int64_t env_lo, int64_t n,
-                                   int rng_mode, uint64_t* d_rec_boards, uint8_t* d_rec_meta, float* d_rec_rewards,
-                                   float* d_rec_log_probs, uint64_t* d_counters, void* stream) {
+static int launch_rollout_steps(int policy, uint64_t* d_boards, uint8_t* d_status, const uint32_t* d_subs,
+                                int64_t n_steps, int64_t t0, int64_t batch_global, int64_t env_lo, int64_t n,
+                                int rng_mode, const int64_t* d_env_ids, int64_t n_live, uint64_t* d_rec_boards,
+                                uint8_t* d_rec_meta, float* d_rec_rewards, float* d_rec_log_probs, uint64_t* d_counters,
+                                void* stream) {
+    G2048_REQUIRE(!d_env_ids || (n_live >= 0 && n_live <= n), "rollout_steps: live rows");
     G2048_REQUIRE(policy == G2048_POLICY_RANDOM || policy == G2048_POLICY_DRUL, "rollout_steps: policy");
     G2048_REQUIRE(valid_mode(rng_mode) && valid_batch(batch_global, env_lo, n), "rollout_steps: batch");
     G2048_REQUIRE(n_steps >= 0 && n_steps <= 0x7FFFFFFF && t0 >= 0, "rollout_steps: steps");
     if (n == 0 || n_steps == 0) return G2048_OK;
     G2048_REQUIRE(d_boards && d_status && d_subs && d_rec_boards && d_rec_meta && d_rec_rewards && d_counters,
                   "rollout_steps: pointers");
-    const unsigned g = blocks_for(n, 256);
+    const int64_t n_rows = d_env_ids ? n_live : n;
+    if (n_rows == 0) return G2048_OK;
+    const unsigned g = blocks_for(n_rows, 256);
     cudaStream_t st = (cudaStream_t)stream;
 #define CALL_P(M, P)                                                                                          \
     rollout_steps_kernel<M, P><<<g, 256, 0, st>>>((u64*)d_boards, d_status, (const uint2*)d_subs, (int)n_steps,    \
                                                   (uint32_t)t0, (uint32_t)batch_global, (uint32_t)env_lo, n,        \
                                                   (u64*)d_rec_boards, d_rec_meta, d_rec_rewards, d_rec_log_probs,   \
-                                                  (unsigned long long*)d_counters)
+                                                  (unsigned long long*)d_counters, d_env_ids, n_rows)
     if (policy == G2048_POLICY_RANDOM) {
 #define CALL(M) CALL_P(M, G2048_POLICY_RANDOM)
         DISPATCH_MODE(rng_mode, CALL)
@@ -566,6 +576,25 @@ extern "C" int g2048_rollout_steps(int policy, uint64_t* d_boards, uint8_t* d_st
 #undef CALL_P
     G2048_CHECK_LAUNCH("rollout_steps");
     return G2048_OK;
+}
+
+extern "C" int g2048_rollout_steps(int policy, uint64_t* d_boards, uint8_t* d_status, const uint32_t* d_subs,
+                                   int64_t n_steps, int64_t t0, int64_t batch_global, int64_t env_lo, int64_t n,
+                                   int rng_mode, uint64_t* d_rec_boards, uint8_t* d_rec_meta, float* d_rec_rewards,
+                                   float* d_rec_log_probs, uint64_t* d_counters, void* stream) {
+    return launch_rollout_steps(policy, d_boards, d_status, d_subs, n_steps, t0, batch_global, env_lo, n, rng_mode, nullptr, 0,
+                                d_rec_boards, d_rec_meta, d_rec_rewards, d_rec_log_probs, d_counters, stream);
+}
+
+extern "C" int g2048_rollout_steps_live(int policy, uint64_t* d_boards, uint8_t* d_status, const uint32_t* d_subs,
+                                        int64_t n_steps, int64_t t0, int64_t batch_global, int64_t env_lo, int64_t n,
+                                        int rng_mode, const int64_t* d_env_ids, int64_t n_live, uint64_t* d_rec_boards,
+                                        uint8_t* d_rec_meta, float* d_rec_rewards, float* d_rec_log_probs,
+                                        uint64_t* d_counters, void* stream) {
+    G2048_REQUIRE(d_env_ids || n_live == 0, "rollout_steps_live: env ids");
+    if (n_live == 0) return G2048_OK;
+    return launch_rollout_steps(policy, d_boards, d_status, d_subs, n_steps, t0, batch_global, env_lo, n, rng_mode, d_env_ids,
+                                n_live, d_rec_boards, d_rec_meta, d_rec_rewards, d_rec_log_probs, d_counters, stream);
 }
 
 extern "C" int g2048_int_peak_probe(int blocks, int threads, int iters, uint32_t* d_sink, void* stream) {

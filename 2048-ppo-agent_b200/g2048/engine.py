@@ -190,6 +190,16 @@ def rollout_steps(policy: int, boards, status, subs, n_steps: int, t0: int, batc
          rng_mode, ptr(rec_boards), ptr(rec_meta), ptr(rec_rewards), ptr(rec_log_probs), ptr(counters), stream_ptr())
 
 
+def rollout_steps_live(policy: int, boards, status, subs, n_steps: int, t0: int, batch_global: int, env_lo: int,
+                       rng_mode: int, env_ids: torch.Tensor, rec_boards, rec_meta, rec_rewards, rec_log_probs, counters) -> None:
+    """rollout_steps for the envs listed in env_ids (int64 local indices) only; a finished env leaves the loop."""
+    n = boards.shape[0]
+    assert env_ids.dtype == torch.int64
+    call("g2048_rollout_steps_live", policy, ptr(boards), ptr(status), ptr(_i32(subs)), n_steps, t0, batch_global, env_lo, n,
+         rng_mode, ptr(env_ids), env_ids.shape[0], ptr(rec_boards), ptr(rec_meta), ptr(rec_rewards), ptr(rec_log_probs),
+         ptr(counters), stream_ptr())
+
+
 # ------------------------------------------------------------------------------------------- policy logits
 def policy_step(boards, status, logits, values, use_mask: bool, sample: bool, auto_reset: bool, sub_act, sub_step,
                 batch_global: int, env_lo: int, rng_mode: int, rec_boards=None, rec_meta=None, rec_rewards=None,

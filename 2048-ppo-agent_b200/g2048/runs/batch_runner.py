@@ -77,8 +77,9 @@ class BatchRunner:
                     (observation -> network forward -> sample + env.step + record) as a CUDA graph and replay it,
                     with one host synchronisation per CHUNK_STEPS steps instead of one per step (SURVEY 8f
                     rank 3).  Same records as the eager loop.
-        compact_live: with a ``TorchActionFunction``, ``run_packed_batch`` feeds only the envs that are still alive
-                    to the network (the reference pushes the finished ones through it until the last env ends,
+        compact_live: ``run_packed_batch`` steps only the envs that are still alive -- with a ``TorchActionFunction`` only
+                    they go through the network, with the built-in policies the recording kernel's work follows the
+                    live env-steps (the reference pushes the finished ones through it until the last env ends,
                     batch_runner.py:117-136 -- about two thirds of the rows of a run to termination).  Env state, RNG
                     counters and record slots stay per env, so a live env's trajectory does not depend on who else
                     is alive; records of steps after an env's end are zero instead of repeating its frozen state
@@ -210,7 +211,7 @@ class BatchRunner:
         is_net = hasattr(self._act_fn, "forward_logits")
         if self.cuda_graph and is_net and not keep_states:
             return self._run_net_graphed(batch_size, lo, n, boards, status)
-        compact = self.compact_live and is_net and not keep_states and not full_records
+        compact = self.compact_live and (is_net or policy is not None) and not keep_states and not full_records
         live_ids = None  # int64 local indices of the envs still alive (compact mode), refreshed when some finish
         counters = torch.zeros(4, dtype=torch.int64, device=dev)
         chunks = []  # (boards, meta, rewards, log_probs, values) per chunk, time-major
@@ -228,8 +229,13 @@ class BatchRunner:
             rl = alloc((steps, n), dtype=torch.float32, device=dev) if want_lp else None
             rv = alloc((steps, n), dtype=torch.float32, device=dev) if want_v else None
             if policy is not None:
-                E.rollout_steps(policy, boards, status, subs[1 + 2 * t0:], steps, t0, batch_size, lo, mode,
-                                rb, rm, rr, rl, counters)
+                if compact:  # the envs alive at the start of the chunk; one that finishes inside it leaves the loop
+                    live_ids = torch.nonzero((status & N.STATUS_DONE) == 0).flatten()
+                    E.rollout_steps_live(policy, boards, status, subs[1 + 2 * t0:], steps, t0, batch_size, lo, mode,
+                                         live_ids, rb, rm, rr, rl, counters)
+                else:
+                    E.rollout_steps(policy, boards, status, subs[1 + 2 * t0:], steps, t0, batch_size, lo, mode,
+                                    rb, rm, rr, rl, counters)
                 done_total = int(counters[0].item())
                 if keep_states:
                     states.append(State(boards.clone(), status.clone(), rr[0].clone()))

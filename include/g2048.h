@@ -163,6 +163,13 @@ int g2048_rollout_steps(int policy, uint64_t* d_boards, uint8_t* d_status, const
                         int64_t t0, int64_t batch_global, int64_t env_lo, int64_t n, int rng_mode,
                         uint64_t* d_rec_boards, uint8_t* d_rec_meta, float* d_rec_rewards, float* d_rec_log_probs,
                         uint64_t* d_counters, void* stream);
+/* The same steps for a compact list of live envs (local indices, int64): an env that finishes leaves the loop and
+ * the record slots of the steps after its end are not written, so the work is proportional to the live env-steps
+ * instead of (loop steps) x (batch size).  Envs not listed are not touched. */
+int g2048_rollout_steps_live(int policy, uint64_t* d_boards, uint8_t* d_status, const uint32_t* d_subs, int64_t n_steps,
+                             int64_t t0, int64_t batch_global, int64_t env_lo, int64_t n, int rng_mode,
+                             const int64_t* d_env_ids, int64_t n_live, uint64_t* d_rec_boards, uint8_t* d_rec_meta,
+                             float* d_rec_rewards, float* d_rec_log_probs, uint64_t* d_counters, void* stream);
 
 /* ---- policy-logit sampling fused with the step and the rollout-buffer write
  * (src/ppo/torch_action_wrapper.py:84-102 + src/ppo/ppo_agent.py:117-121 + env.step + the

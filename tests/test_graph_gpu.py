@@ -222,3 +222,23 @@ def test_feeding_only_live_envs_keeps_their_trajectories():
     out_a, out_b = full.run_actions_batch(8), compact.run_actions_batch(8)
     for x, y in zip(out_a, out_b):
         assert (x == y).all()
+
+
+@pytest.mark.parametrize("policy", ["random", "drul"])
+def test_recorded_rollout_of_live_envs_only(policy):
+    import g2048
+    act = g2048.act_randomly if policy == "random" else g2048.act_drul
+    full = g2048.BatchRunner(init_seed=33, act_fn=act)
+    live = g2048.BatchRunner(init_seed=33, act_fn=act, compact_live=True)
+    for batch in (77, 3000):
+        a, b = full.run_packed_batch(batch), live.run_packed_batch(batch)
+        assert a.t_steps == b.t_steps and a.env_steps == b.env_steps
+        assert torch.equal(a.final_boards, b.final_boards) and torch.equal(a.final_status, b.final_status)
+        la = a.lengths().long()
+        assert torch.equal(la, b.lengths().long())
+        alive = torch.arange(a.t_steps, device="cuda").unsqueeze(1) < la.unsqueeze(0)
+        for name in ("boards", "meta", "rewards") + (("log_probs",) if policy == "random" else ()):
+            x, y = getattr(a, name), getattr(b, name)
+            assert torch.equal(x[alive], y[alive]), name
+            assert bool((y[~alive] == 0).all()), name
+        assert (full.key == live.key).all()

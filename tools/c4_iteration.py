@@ -49,9 +49,22 @@ def main():
     for _ in g2048.DevicePPOBatches(wb.get_packed(), batch_size=256):
         break
     rollout, t_roll = timed(lambda: runner.run_packed_batch(args.envs))
-    report["rollout"] = {"seconds": t_roll, "loop_steps": rollout.t_steps, "env_steps": rollout.env_steps,
-                         "env_steps_per_sec": rollout.env_steps / t_roll,
-                         "record_bytes": int(rollout.t_steps * args.envs * 17)}
+    # A/B on throw-away runners, each warmed up at full size (allocator, lazy loading): every env stepped until the
+    # last one ends (the reference's loop) against only the live ones
+    ab = {}
+    for name, flag in (("all_envs", False), ("live_envs_only", True)):
+        r2 = g2048.BatchRunner(init_seed=5, act_fn=g2048.act_randomly, compact_live=flag)
+        r2.run_packed_batch(args.envs)
+        ro2, ab[name] = timed(lambda: r2.run_packed_batch(args.envs))
+        ab[name + "_env_steps"] = ro2.env_steps
+        del ro2, r2
+    assert ab["all_envs_env_steps"] == ab["live_envs_only_env_steps"]
+    t_roll_live = ab["live_envs_only"]
+    report["rollout"] = {"seconds_first_call_at_this_size": t_roll, "seconds": ab["all_envs"], "loop_steps": rollout.t_steps,
+                         "env_steps": rollout.env_steps, "env_steps_per_sec": rollout.env_steps / ab["all_envs"],
+                         "record_bytes": int(rollout.t_steps * args.envs * 17),
+                         "seconds_warm_all_envs": ab["all_envs"], "seconds_warm_live_envs_only": t_roll_live,
+                         "live_fraction": rollout.env_steps / (rollout.t_steps * args.envs)}
 
     buf = g2048.RolloutBuffer(31, 16, 4)
     kept, t_store = timed(lambda: buf.store_packed(rollout))
@@ -142,6 +155,7 @@ def main():
         boards, masks, done, rew = CO.env_step(boards, masks, done, actions, step_keys, 1)
         ok &= np.array_equal(rew, rec_r[t]) and np.array_equal(done, (rec_m[t] >> 6) & 1)
     report["bit_exact_board_check"] = {"envs": sample, "steps": t_chk, "identical": bool(ok)}
+    t_roll = ab["all_envs"]  # warm; the first call at a new size also pays cudaMalloc for ~2 GB of record buffers
     total = t_roll + t_store + t_gae + t_feed
     report["product_path_seconds"] = total
     report["share"] = {k: round(v / total, 3) for k, v in (("rollout", t_roll), ("store", t_store), ("gae", t_gae), ("minibatches", t_feed))}
