@@ -63,6 +63,30 @@ def pack_boards(exponents) -> np.ndarray:
     return (b << (np.arange(16, dtype=np.uint64) * np.uint64(4))).sum(axis=-1).astype(np.uint64).view(np.int64)
 
 
+_STAGE = {}  # device index -> pinned uint8 staging buffer of to_host(), grown on demand
+
+
+def to_host(x: torch.Tensor) -> np.ndarray:
+    """A fresh numpy array with the tensor's contents.  Large tensors go through a pinned staging buffer kept per
+    device: a pageable device-to-host copy of C1's 130 MB of observations ran at 2 GB/s and was 80 % of
+    run_actions_batch; staged, the transfer takes 2.5 ms and the copy into the caller's array the rest."""
+    nbytes = x.numel() * x.element_size()
+    if not x.is_cuda or nbytes < (1 << 20):
+        return x.cpu().numpy()
+    key = x.device.index
+    stage = _STAGE.get(key)
+    if stage is None or stage.numel() < nbytes:
+        stage = _STAGE[key] = torch.empty(max(nbytes, 1 << 24), dtype=torch.uint8, pin_memory=True)
+    view = stage[:nbytes].view(x.dtype).view(x.shape)
+    view.copy_(x.contiguous(), non_blocking=True)
+    torch.cuda.current_stream(x.device).synchronize()
+    if torch.get_num_threads() > 1:
+        out = torch.empty(x.shape, dtype=x.dtype)  # the caller's array; torch's CPU copy is multi-threaded,
+        out.copy_(view)                            # which also spreads the first-touch page faults (C1: 44 -> 19 ms)
+        return out.numpy()
+    return view.numpy().copy()  # one thread (e.g. OMP_NUM_THREADS=1 under torchrun): numpy's memcpy is the faster one
+
+
 def _i32(t):
     assert t.dtype == torch.int32, t.dtype
     return t

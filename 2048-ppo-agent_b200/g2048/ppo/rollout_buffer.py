@@ -143,11 +143,11 @@ class RolloutBuffer:
         if isinstance(self.observation_length, (tuple, list)):
             obs = obs.view(n, *self.observation_length, self.observation_dim)
         return {
-            "observations": obs.cpu().numpy(),
-            "actions": onehot.cpu().numpy(),
-            "action_masks": masks.cpu().numpy(),
-            "rewards": p["rewards"].cpu().numpy(),
-            "values": p["values"].cpu().numpy(),
-            "log_probs": p["log_probs"].cpu().numpy(),
-            "terminations": term.cpu().numpy(),
+            "observations": E.to_host(obs),
+            "actions": E.to_host(onehot),
+            "action_masks": E.to_host(masks),
+            "rewards": E.to_host(p["rewards"]),
+            "values": E.to_host(p["values"]),
+            "log_probs": E.to_host(p["log_probs"]),
+            "terminations": E.to_host(term),
         }

@@ -92,7 +92,6 @@ class BatchRunner:
         self._act_fn = act_fn
         self.cuda_graph = cuda_graph
         self.compact_live = compact_live
-        self._stage = None  # pinned host staging buffer of _to_host, grown on demand
         self._graphs = {}  # (batch_size, lo, n, steps, auto_reset) -> captured step of the current act_fn
 
     # -- reference surface ---------------------------------------------------------------------
@@ -127,9 +126,9 @@ class BatchRunner:
         t, b = ro.t_steps, ro.batch_size
         obs = E.expand_obs(ro.boards, torch.bool, rows=t, n_cols=b)
         un = E.unpack_records(ro.meta, ro.rewards, ro.log_probs, ro.values, t, b)
-        to_np = lambda x: None if x is None else self._to_host(x)  # noqa: E731
+        to_np = lambda x: None if x is None else E.to_host(x)  # noqa: E731
         return (
-            self._to_host(obs).reshape(b, t, 4, 4, 31),
+            E.to_host(obs).reshape(b, t, 4, 4, 31),
             to_np(un["actions"]),
             to_np(un["action_masks"]),
             to_np(un["log_probs"]),
@@ -137,24 +136,6 @@ class BatchRunner:
             to_np(un["rewards"]),
             to_np(un["terminations"]),
         )
-
-    def _to_host(self, x: torch.Tensor) -> np.ndarray:
-        """A fresh numpy array with the tensor's contents.  Large tensors go through a pinned staging buffer that the
-        runner keeps (a pageable device-to-host copy of C1's 130 MB of observations ran at 2 GB/s and was 80 % of
-        run_actions_batch; staged, the copy takes 2.5 ms and the host-side copy into the caller's array the rest)."""
-        nbytes = x.numel() * x.element_size()
-        if nbytes < (1 << 20):
-            return x.cpu().numpy()
-        if self._stage is None or self._stage.numel() < nbytes:
-            self._stage = torch.empty(max(nbytes, 1 << 24), dtype=torch.uint8, pin_memory=True)
-        view = self._stage[:nbytes].view(x.dtype).view(x.shape)
-        view.copy_(x.contiguous(), non_blocking=True)
-        torch.cuda.current_stream(x.device).synchronize()
-        if torch.get_num_threads() > 1:
-            out = torch.empty(x.shape, dtype=x.dtype)  # the caller's array; torch's CPU copy is multi-threaded,
-            out.copy_(view)                            # which also spreads the first-touch page faults (C1: 44 -> 19 ms)
-            return out.numpy()
-        return view.numpy().copy()  # one thread (e.g. OMP_NUM_THREADS=1 under torchrun): numpy's memcpy is the faster one
 
     def run_rollout_batch(self, batch_size: int) -> list:
         """-> list[State], the init state first (batch_runner.py:156-195)."""
