@@ -18,12 +18,16 @@ from ..env_definitions import BOARD_FLAT_DIM, OBS_DIM
 
 class TorchActionFunction:
     def __init__(self, agent, use_mask: bool = False, sample_actions: bool = True,
-                 device: torch.device = torch.device("cpu"), rng_mode=None, obs_dtype=torch.float32):
+                 device: torch.device = torch.device("cpu"), rng_mode=None, obs_dtype=torch.float32,
+                 autocast_dtype=None):
         """
         agent          : module with forward(obs (B,16,31) float, mask|None) -> (logits (B,4), values (B,1))
         use_mask       : apply PPOAgent's mask rule `logits - 1e8 * (1 - mask)` (ppo_agent.py:117-121)
         sample_actions : categorical sample, else argmax
         device         : where the network runs; the sampling kernels always run on the CUDA device
+        autocast_dtype : e.g. torch.bfloat16 -- run the network forward under torch.autocast (tensor-core GEMMs);
+                         logits and values are converted back to float32 before the sampling kernel, which
+                         always computes mask rule, log-softmax and draws in float32
         """
         self.cuda_device = N.require_cuda()
         self.device = torch.device(device)
@@ -32,6 +36,7 @@ class TorchActionFunction:
         self.sample_actions = sample_actions
         self.rng_mode = E.resolve_rng_mode(rng_mode)
         self.obs_dtype = obs_dtype
+        self.autocast_dtype = autocast_dtype
 
     @torch.no_grad()
     def forward_logits(self, obs: torch.Tensor):
@@ -40,7 +45,12 @@ class TorchActionFunction:
         x = obs.view(-1, BOARD_FLAT_DIM, OBS_DIM)
         if x.device != self.device:
             x = x.to(self.device)
-        logits, values = self.agent(x.float() if x.dtype != torch.float32 and self.obs_dtype == torch.float32 else x, None)
+        x = x.float() if x.dtype != torch.float32 and self.obs_dtype == torch.float32 else x
+        if self.autocast_dtype is not None:
+            with torch.autocast(self.device.type, dtype=self.autocast_dtype):
+                logits, values = self.agent(x, None)
+        else:
+            logits, values = self.agent(x, None)
         logits = logits.float().to(self.cuda_device).contiguous()
         values = values.float().reshape(-1).to(self.cuda_device).contiguous()
         return logits, values

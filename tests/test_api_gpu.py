@@ -445,3 +445,26 @@ def test_single_legal_action_is_respected(G):
         keys = G.keys.split(G.keys.key(5), 4)
         actions, _, _ = fn(keys, obs, np.eye(4, dtype=bool))
         assert actions.cpu().tolist() == [0, 1, 2, 3]
+
+
+def test_torch_action_function_autocast_keeps_float32_sampling():
+    import g2048
+
+    class Agent(torch.nn.Module):
+        def __init__(self):
+            super().__init__()
+            torch.manual_seed(1)
+            self.lin = torch.nn.Linear(496, 5)
+            self.seen = None
+
+        def forward(self, obs, mask=None):
+            out = self.lin(obs.flatten(1))
+            self.seen = out.dtype
+            return out[:, :4], out[:, 4:]
+
+    agent = Agent()
+    fn = g2048.TorchActionFunction(agent, use_mask=True, device=torch.device("cuda"), autocast_dtype=torch.bfloat16)
+    ro = g2048.BatchRunner(init_seed=2, act_fn=fn).run_packed_batch(32)
+    assert agent.seen == torch.bfloat16  # the GEMM ran under autocast
+    assert ro.log_probs.dtype == torch.float32 and ro.values.dtype == torch.float32
+    assert bool(torch.isfinite(ro.log_probs).all()) and ro.env_steps > 0
