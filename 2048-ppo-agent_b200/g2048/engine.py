@@ -7,6 +7,7 @@ Boards travel as ``torch.int64`` tensors holding the uint64 bitboard bits; keys 
 from __future__ import annotations
 
 import os
+import threading
 
 import numpy as np
 import torch
@@ -64,6 +65,7 @@ def pack_boards(exponents) -> np.ndarray:
 
 
 _STAGE = {}  # device index -> pinned uint8 staging buffer of to_host(), grown on demand
+_STAGE_LOCK = threading.Lock()  # one staged copy at a time: the buffer is shared by every caller of the process
 
 
 def to_host(x: torch.Tensor) -> np.ndarray:
@@ -74,17 +76,18 @@ def to_host(x: torch.Tensor) -> np.ndarray:
     if not x.is_cuda or nbytes < (1 << 20):
         return x.cpu().numpy()
     key = x.device.index
-    stage = _STAGE.get(key)
-    if stage is None or stage.numel() < nbytes:
-        stage = _STAGE[key] = torch.empty(max(nbytes, 1 << 24), dtype=torch.uint8, pin_memory=True)
-    view = stage[:nbytes].view(x.dtype).view(x.shape)
-    view.copy_(x.contiguous(), non_blocking=True)
-    torch.cuda.current_stream(x.device).synchronize()
-    if torch.get_num_threads() > 1:
-        out = torch.empty(x.shape, dtype=x.dtype)  # the caller's array; torch's CPU copy is multi-threaded,
-        out.copy_(view)                            # which also spreads the first-touch page faults (C1: 44 -> 19 ms)
-        return out.numpy()
-    return view.numpy().copy()  # one thread (e.g. OMP_NUM_THREADS=1 under torchrun): numpy's memcpy is the faster one
+    with _STAGE_LOCK:
+        stage = _STAGE.get(key)
+        if stage is None or stage.numel() < nbytes:
+            stage = _STAGE[key] = torch.empty(max(nbytes, 1 << 24), dtype=torch.uint8, pin_memory=True)
+        view = stage[:nbytes].view(x.dtype).view(x.shape)
+        view.copy_(x.contiguous(), non_blocking=True)
+        torch.cuda.current_stream(x.device).synchronize()
+        if torch.get_num_threads() > 1:
+            out = torch.empty(x.shape, dtype=x.dtype)  # the caller's array; torch's CPU copy is multi-threaded,
+            out.copy_(view)                            # which also spreads the first-touch page faults (C1: 44 -> 19 ms)
+            return out.numpy()
+        return view.numpy().copy()  # one thread (e.g. OMP_NUM_THREADS=1 under torchrun): numpy's memcpy is the faster one
 
 
 def _i32(t):
