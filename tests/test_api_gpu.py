@@ -468,3 +468,33 @@ def test_torch_action_function_autocast_keeps_float32_sampling():
     assert agent.seen == torch.bfloat16  # the GEMM ran under autocast
     assert ro.log_probs.dtype == torch.float32 and ro.values.dtype == torch.float32
     assert bool(torch.isfinite(ro.log_probs).all()) and ro.env_steps > 0
+
+
+def test_collect_rollouts_matches_the_trainers_python_loops():
+    """ppo_trainer.py:185-227 on the reference-format arrays vs the packed path."""
+    import g2048
+    from g2048.ppo import collect_rollouts
+
+    ref_runner = g2048.BatchRunner(init_seed=6, act_fn=g2048.act_randomly)
+    ref_buffer = g2048.RolloutBuffer(31, 16, 4)
+    want_r, want_l = [], []
+    for _ in range(3):
+        obs, actions, masks, log_probs, values, rewards, terms = ref_runner.run_actions_batch(40)
+        b, t = obs.shape[:2]
+        onehot = np.zeros((b, t, 4), np.float32)
+        onehot[np.arange(b)[:, None], np.arange(t)[None, :], actions] = 1.0
+        ref_buffer.store_batch(observations=obs, actions=onehot, action_masks=masks, rewards=rewards, values=values,
+                               log_probs=log_probs, terminations=terms)
+        for e in range(b):
+            want_r.append(np.max(rewards[e]))
+            want_l.append(np.argmax(terms[e]) + 1 if np.any(terms[e]) else t)
+    for compact in (False, True):
+        runner = g2048.BatchRunner(init_seed=6, act_fn=g2048.act_randomly, compact_live=compact)
+        buffer = g2048.RolloutBuffer(31, 16, 4)
+        out = collect_rollouts(runner, buffer, 40, 3)
+        np.testing.assert_array_equal(out["episode_rewards"], np.asarray(want_r, np.float32))
+        np.testing.assert_array_equal(out["episode_lengths"], np.asarray(want_l))
+        assert out["total_episodes"] == 120 and out["timesteps"] == ref_buffer.buffer_size == buffer.buffer_size
+        a, b2 = ref_buffer.get_buffer_data(), buffer.get_buffer_data()
+        for k in a:
+            np.testing.assert_array_equal(a[k], b2[k])
