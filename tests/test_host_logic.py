@@ -309,3 +309,17 @@ def test_device_logit_sampling_on_host(shim, mode, golden_ppo):
     np.testing.assert_allclose(glp[agree], wlp[agree], rtol=1e-5, atol=1e-6)
     dist = torch.distributions.Categorical(logits=torch.from_numpy(O.mask_logits(logits, masks)))
     np.testing.assert_allclose(gent, dist.entropy().numpy(), rtol=1e-5, atol=1e-6)
+
+
+def test_header_is_plain_c():
+    """The boundary is a C ABI: include/g2048.h must compile as C99 and as C++ on its own."""
+    import shutil
+    import subprocess
+    from pathlib import Path
+
+    header = Path(__file__).resolve().parent.parent / "include" / "g2048.h"
+    for compiler, flags in (("gcc", ["-std=c99", "-x", "c"]), ("g++", ["-std=c++17", "-x", "c++"])):
+        if shutil.which(compiler) is None:
+            pytest.skip(f"{compiler} not available")
+        res = subprocess.run([compiler, *flags, "-Wall", "-Wextra", "-Werror", "-fsyntax-only", str(header)], capture_output=True, text=True)
+        assert res.returncode == 0, res.stderr
