@@ -3,6 +3,7 @@
 // registers of the one thread that owns it; HBM sees only records and per-episode results.
 #include "g2048_board.cuh"
 #include "g2048_common.cuh"
+#include "g2048_hostcopy.cuh"
 #include "g2048_env.cuh"
 
 namespace g2048 {
@@ -474,6 +475,7 @@ extern "C" int g2048_play_host(int policy, uint64_t seed, uint32_t* h_key_io, in
         cudaStream_t stream = nullptr;
         uint8_t* buf = nullptr;
         size_t bytes = 0;
+        StagedCopier copier;  // result arrays in pageable memory (numpy) go through pinned staging buffers
     };
     static thread_local Workspace ws;
     int rc = G2048_OK;
@@ -485,6 +487,7 @@ extern "C" int g2048_play_host(int policy, uint64_t seed, uint32_t* h_key_io, in
     if (ws.device != dev) {  // first call on this thread, or the thread switched device
         ws = Workspace();
         TRY(cudaStreamCreateWithFlags(&ws.stream, cudaStreamNonBlocking), "play_host: stream");
+        if ((rc = ws.copier.init())) return rc;
         ws.device = dev;
     }
     cudaStream_t st = ws.stream;
@@ -520,9 +523,9 @@ extern "C" int g2048_play_host(int policy, uint64_t seed, uint32_t* h_key_io, in
         if (rc) return rc;
         // results are copied optimistically; a batch that outlived its keys is replayed below
         TRY(cudaMemcpyAsync(stats, d_stats, sizeof(stats), cudaMemcpyDeviceToHost, st), "play_host: d2h stats");
-        if (d_boards && n) TRY(cudaMemcpyAsync(h_final_boards, d_boards, n * sizeof(uint64_t), cudaMemcpyDeviceToHost, st), "play_host: d2h");
-        if (d_len && n) TRY(cudaMemcpyAsync(h_lengths, d_len, n * sizeof(uint32_t), cudaMemcpyDeviceToHost, st), "play_host: d2h");
-        if (d_score && n) TRY(cudaMemcpyAsync(h_scores, d_score, n * sizeof(uint32_t), cudaMemcpyDeviceToHost, st), "play_host: d2h");
+        if (d_boards && n && (rc = ws.copier.d2h(h_final_boards, d_boards, n * sizeof(uint64_t), st))) return rc;
+        if (d_len && n && (rc = ws.copier.d2h(h_lengths, d_len, n * sizeof(uint32_t), st))) return rc;
+        if (d_score && n && (rc = ws.copier.d2h(h_scores, d_score, n * sizeof(uint32_t), st))) return rc;
         TRY(cudaStreamSynchronize(st), "play_host: sync");
         if (stats[3] == 0 || max_steps >= (1 << 20)) break;
         max_steps *= 4;  // some episode outlived the chain: replay with a longer one

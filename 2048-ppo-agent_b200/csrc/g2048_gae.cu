@@ -7,9 +7,8 @@
 // (no FMA contraction: the library is built with --fmad=false).  Results are therefore bit-identical
 // to the reference, not merely within tolerance.  The kernels are HBM-bound streams:
 // 9 B read + 8 B written per step.
-#include <cstring>
-
 #include "g2048_common.cuh"
+#include "g2048_hostcopy.cuh"
 
 namespace g2048 {
 
@@ -354,8 +353,8 @@ extern "C" int g2048_normalize(float* d_x, int64_t n, const double* d_moments, i
 // Host-buffer form.  The caller's arrays are ordinary pageable memory (numpy).  The first version allocated and freed
 // seven device buffers per call and used plain cudaMemcpy (the driver stages pageable memory itself, synchronously):
 // 18.8 ms for 1e6 steps, 102 ms for 3.1e7 around 3 ms of kernels.  Now the calling thread keeps a workspace -- one
-// stream, a grow-only device buffer and two pinned 16 MiB staging buffers -- and the copies are pipelined through the
-// staging buffers (host memcpy of chunk k+1 while chunk k is on the bus): 1.5 ms and 74 ms
+// stream, a grow-only device buffer and a StagedCopier (g2048_hostcopy.cuh) -- and the copies are pipelined through its
+// pinned staging buffers: 1.5 ms and 74 ms
 // (tools/probes/gae_host_bench.py; the large case is bound by the single-threaded host memcpy of 527 MB).
 namespace {
 
@@ -364,48 +363,8 @@ struct GaeHostWorkspace {
     cudaStream_t stream = nullptr;
     uint8_t* dev = nullptr;
     size_t dev_bytes = 0;
-    uint8_t* pin[2] = {nullptr, nullptr};
-    cudaEvent_t ev[2] = {nullptr, nullptr};
+    StagedCopier copier;
 };
-constexpr size_t GAE_HOST_STAGE = 16u << 20;
-
-int staged_h2d(GaeHostWorkspace& w, void* d_dst, const void* h_src, size_t bytes) {
-    int k = 0;
-    for (size_t off = 0; off < bytes; k ^= 1) {
-        const size_t c = bytes - off < GAE_HOST_STAGE ? bytes - off : GAE_HOST_STAGE;
-        int rc = check_cuda(cudaEventSynchronize(w.ev[k]), "gae_host: staging");  // the copy that last used this buffer
-        if (rc) return rc;
-        memcpy(w.pin[k], (const char*)h_src + off, c);
-        rc = check_cuda(cudaMemcpyAsync((char*)d_dst + off, w.pin[k], c, cudaMemcpyHostToDevice, w.stream), "gae_host: h2d");
-        if (!rc) rc = check_cuda(cudaEventRecord(w.ev[k], w.stream), "gae_host: staging");
-        if (rc) return rc;
-        off += c;
-    }
-    return G2048_OK;
-}
-
-int staged_d2h(GaeHostWorkspace& w, void* h_dst, const void* d_src, size_t bytes) {
-    int k = 0;
-    size_t prev_off = 0, prev_c = 0;
-    for (size_t off = 0; off < bytes || prev_c; k ^= 1) {
-        size_t c = 0;
-        if (off < bytes) {  // chunk i onto the bus ...
-            c = bytes - off < GAE_HOST_STAGE ? bytes - off : GAE_HOST_STAGE;
-            int rc = check_cuda(cudaMemcpyAsync(w.pin[k], (const char*)d_src + off, c, cudaMemcpyDeviceToHost, w.stream), "gae_host: d2h");
-            if (!rc) rc = check_cuda(cudaEventRecord(w.ev[k], w.stream), "gae_host: staging");
-            if (rc) return rc;
-        }
-        if (prev_c) {  // ... while chunk i-1 goes from its staging buffer to the caller's array
-            const int rc = check_cuda(cudaEventSynchronize(w.ev[k ^ 1]), "gae_host: staging");
-            if (rc) return rc;
-            memcpy((char*)h_dst + prev_off, w.pin[k ^ 1], prev_c);
-        }
-        prev_off = off;
-        prev_c = c;
-        off += c;
-    }
-    return G2048_OK;
-}
 
 }  // namespace
 
@@ -421,10 +380,7 @@ extern "C" int g2048_gae_host(const float* h_rewards, const float* h_values, con
     if (ws.device != dev) {  // first call on this thread, or the thread switched device
         ws = GaeHostWorkspace();
         TRY(cudaStreamCreateWithFlags(&ws.stream, cudaStreamNonBlocking), "gae_host: stream");
-        for (int k = 0; k < 2; ++k) {
-            TRY(cudaMallocHost((void**)&ws.pin[k], GAE_HOST_STAGE), "gae_host: pinned staging");
-            TRY(cudaEventCreateWithFlags(&ws.ev[k], cudaEventDisableTiming), "gae_host: event");
-        }
+        if ((rc = ws.copier.init())) return rc;
         ws.device = dev;
     }
     const auto align256 = [](size_t x) { return (x + 255) & ~(size_t)255; };
@@ -445,16 +401,16 @@ extern "C" int g2048_gae_host(const float* h_rewards, const float* h_values, con
           *d_t = (float*)(ws.dev + off_t);
     uint8_t* d_d = ws.dev + off_d;
     TRY(cudaMemsetAsync(ws.dev, 0, off_r, ws.stream), "gae_host: memset");  // moments + scratch
-    if ((rc = staged_h2d(ws, d_r, h_rewards, (size_t)n * 4))) return rc;
-    if ((rc = staged_h2d(ws, d_v, h_values, (size_t)n * 4))) return rc;
-    if ((rc = staged_h2d(ws, d_d, h_dones, (size_t)n))) return rc;
+    if ((rc = ws.copier.h2d(d_r, h_rewards, (size_t)n * 4, ws.stream))) return rc;
+    if ((rc = ws.copier.h2d(d_v, h_values, (size_t)n * 4, ws.stream))) return rc;
+    if ((rc = ws.copier.h2d(d_d, h_dones, (size_t)n, ws.stream))) return rc;
     if ((rc = g2048_gae_flat(d_r, d_v, d_d, n, gamma, lambda_gae, d_a, d_t, d_s, d_m, ws.stream))) return rc;
     if (normalize) {
         if ((rc = g2048_normalize(d_a, n, d_m, 1, ws.stream))) return rc;
         if ((rc = g2048_normalize(d_t, n, d_m, 3, ws.stream))) return rc;
     }
-    if ((rc = staged_d2h(ws, h_adv, d_a, (size_t)n * 4))) return rc;
-    if ((rc = staged_d2h(ws, h_ret, d_t, (size_t)n * 4))) return rc;
+    if ((rc = ws.copier.d2h(h_adv, d_a, (size_t)n * 4, ws.stream))) return rc;
+    if ((rc = ws.copier.d2h(h_ret, d_t, (size_t)n * 4, ws.stream))) return rc;
     TRY(cudaStreamSynchronize(ws.stream), "gae_host: sync");
 #undef TRY
     return G2048_OK;

@@ -1,0 +1,79 @@
+// Host <-> device copies for the `*_host` entry points.  Callers hand in ordinary (pageable) arrays -- numpy, malloc --
+// and a plain cudaMemcpy of pageable memory is staged by the driver, synchronously, at a few GB/s.  StagedCopier keeps
+// two pinned 16 MiB buffers per calling thread and pipelines the transfer through them (host memcpy of chunk k+1 while
+// chunk k is on the bus).  Memory the caller already pinned (cudaHostAlloc / cudaHostRegister) is copied directly.
+#pragma once
+#include <cuda_runtime.h>
+
+#include <cstring>
+
+#include "g2048_common.cuh"
+
+namespace g2048 {
+
+struct StagedCopier {
+    static constexpr size_t STAGE = 16u << 20;
+    uint8_t* pin[2] = {nullptr, nullptr};
+    cudaEvent_t ev[2] = {nullptr, nullptr};
+
+    int init() {
+        for (int k = 0; k < 2; ++k) {
+            int rc = check_cuda(cudaMallocHost((void**)&pin[k], STAGE), "host copy: pinned staging");
+            if (!rc) rc = check_cuda(cudaEventCreateWithFlags(&ev[k], cudaEventDisableTiming), "host copy: event");
+            if (rc) return rc;
+        }
+        return G2048_OK;
+    }
+
+    static bool is_pinned(const void* p) {
+        cudaPointerAttributes attr;
+        if (cudaPointerGetAttributes(&attr, p) != cudaSuccess) {
+            cudaGetLastError();  // older runtimes report unregistered memory as an error: clear it
+            return false;
+        }
+        return attr.type == cudaMemoryTypeHost;
+    }
+
+    int h2d(void* d_dst, const void* h_src, size_t bytes, cudaStream_t st) {
+        if (is_pinned(h_src)) return check_cuda(cudaMemcpyAsync(d_dst, h_src, bytes, cudaMemcpyHostToDevice, st), "host copy: h2d");
+        int k = 0;
+        for (size_t off = 0; off < bytes; k ^= 1) {
+            const size_t c = bytes - off < STAGE ? bytes - off : STAGE;
+            int rc = check_cuda(cudaEventSynchronize(ev[k]), "host copy: staging");  // the copy that last used this buffer
+            if (rc) return rc;
+            memcpy(pin[k], (const char*)h_src + off, c);
+            rc = check_cuda(cudaMemcpyAsync((char*)d_dst + off, pin[k], c, cudaMemcpyHostToDevice, st), "host copy: h2d");
+            if (!rc) rc = check_cuda(cudaEventRecord(ev[k], st), "host copy: staging");
+            if (rc) return rc;
+            off += c;
+        }
+        return G2048_OK;
+    }
+
+    // On return the data of a PAGEABLE destination is in place; a pinned destination is only enqueued (synchronise `st`).
+    int d2h(void* h_dst, const void* d_src, size_t bytes, cudaStream_t st) {
+        if (is_pinned(h_dst)) return check_cuda(cudaMemcpyAsync(h_dst, d_src, bytes, cudaMemcpyDeviceToHost, st), "host copy: d2h");
+        int k = 0;
+        size_t prev_off = 0, prev_c = 0;
+        for (size_t off = 0; off < bytes || prev_c; k ^= 1) {
+            size_t c = 0;
+            if (off < bytes) {  // chunk i onto the bus ...
+                c = bytes - off < STAGE ? bytes - off : STAGE;
+                int rc = check_cuda(cudaMemcpyAsync(pin[k], (const char*)d_src + off, c, cudaMemcpyDeviceToHost, st), "host copy: d2h");
+                if (!rc) rc = check_cuda(cudaEventRecord(ev[k], st), "host copy: staging");
+                if (rc) return rc;
+            }
+            if (prev_c) {  // ... while chunk i-1 goes from its staging buffer to the caller's array
+                const int rc = check_cuda(cudaEventSynchronize(ev[k ^ 1]), "host copy: staging");
+                if (rc) return rc;
+                memcpy((char*)h_dst + prev_off, pin[k ^ 1], prev_c);
+            }
+            prev_off = off;
+            prev_c = c;
+            off += c;
+        }
+        return G2048_OK;
+    }
+};
+
+}  // namespace g2048
