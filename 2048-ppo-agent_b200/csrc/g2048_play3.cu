@@ -23,6 +23,10 @@ namespace g2048 {
 #ifndef G2048_PLAY3_THREADS
 #define G2048_PLAY3_THREADS 512
 #endif
+#ifndef G2048_PLAY3_EPILOGUE_BATCH
+#define G2048_PLAY3_EPILOGUE_BATCH 16
+#endif
+constexpr int PLAY3_EPILOGUE_BATCH = G2048_PLAY3_EPILOGUE_BATCH;  // parked finished episodes per epilogue run
 constexpr int PLAY3_THREADS = G2048_PLAY3_THREADS;  // one CTA per SM; 512 / 768 / 1024 threads measured within 3 % of each other, 512 best (shorter tail)
 constexpr int PLAY3_TABLE_BYTES = 65536 * 2 + 65536;
 constexpr int PLAY3_SMEM_BYTES = PLAY3_TABLE_BYTES + G2048_PLAY_STATS_WORDS * 8;
@@ -96,10 +100,57 @@ play3_kernel(const uint2* __restrict__ subs, int64_t n_subs, uint32_t batch_glob
     uint32_t st_episodes = 0, st_cut = 0, st_ovf = 0, st_longest = 0;
     unsigned long long st_steps = 0, st_score = 0, st_tile = 0, st_tile2 = 0;
 
+    // Episode epilogue (score from the final board, result stores, statistics: ~150 instructions).  Lanes finish
+    // one at a time -- a warp meets a finished episode on roughly every fourth step -- so running the epilogue on the
+    // spot means running it with one active lane, ~4 % of the kernel's instructions.  A finished lane parks its final
+    // state in a second register set instead and takes the next env at once; the epilogue runs for all parked lanes
+    // together when PLAY3_EPILOGUE_BATCH of them have gathered (or a parked lane finishes again, or at the end).
+    // 2^21 envs, random policy: 25.76 G env-steps/s with the epilogue on the spot, 26.22 batched by 8, 26.32 by 16 or 32.
+    u64 pk_board = 0ull;
+    uint32_t pk_t = 0, pk_fours = 0, pk_e = 0;
+    bool pk_has = false, pk_cut = false, pk_seen15 = false;
+    bool fin_live = false, fin_cut = false;  // the live registers hold a finished episode that is not parked yet
+    auto epilogue = [&]() {
+        if (pk_has) {
+            const uint32_t score = board_potential(pk_board) - 4u * pk_fours;
+            if (final_boards) final_boards[pk_e] = pk_board;
+            if (lengths) lengths[pk_e] = pk_t;
+            if (scores) scores[pk_e] = score;
+            const uint32_t me = max_exponent(pk_board);
+            const unsigned long long tile = 1ull << me;
+            st_episodes += 1;
+            st_steps += pk_t;
+            st_score += score;
+            st_cut += pk_cut ? 1u : 0u;
+            st_ovf += pk_seen15 ? 1u : 0u;
+            st_longest = max(st_longest, pk_t);
+            st_tile += tile;
+            st_tile2 += tile * tile;
+            atomicAdd(&s_stats[16 + me], 1ull);
+            pk_has = false;
+        }
+    };
+
     while (true) {
         // ---- hand the next envs of the queue to the lanes that have none --------------------------
         const unsigned want = __ballot_sync(0xFFFFFFFFu, phase == PHASE_NONE);
         if (want) {
+            // park what the lanes that just finished still hold (all lanes are converged here)
+            const unsigned fresh = __ballot_sync(0xFFFFFFFFu, fin_live);
+            if (fresh) {
+                const unsigned parked = __ballot_sync(0xFFFFFFFFu, pk_has);
+                if ((fresh & parked) != 0u || __popc(fresh | parked) >= PLAY3_EPILOGUE_BATCH) epilogue();
+                if (fin_live) {
+                    pk_board = board;
+                    pk_t = t;
+                    pk_fours = fours;
+                    pk_e = e;
+                    pk_cut = fin_cut;
+                    pk_seen15 = seen15;
+                    pk_has = true;
+                    fin_live = false;
+                }
+            }
             if (!exhausted) {
                 const int cnt = __popc(want);
                 unsigned long long base = 0;
@@ -191,25 +242,13 @@ play3_kernel(const uint2* __restrict__ subs, int64_t n_subs, uint32_t batch_glob
         const bool done = lm == 0u;
         const bool cut = !done && t >= max_steps;
         if ((t & 255u) == 0u || done || cut) seen15 |= has_max_nibble(board);
-        if (done || cut) {
-            const uint32_t score = board_potential(board) - 4u * fours;
-            if (final_boards) final_boards[e] = board;
-            if (lengths) lengths[e] = t;
-            if (scores) scores[e] = score;
-            const uint32_t me = max_exponent(board);
-            const unsigned long long tile = 1ull << me;
-            st_episodes += 1;
-            st_steps += t;
-            st_score += score;
-            st_cut += cut ? 1u : 0u;
-            st_ovf += seen15 ? 1u : 0u;
-            st_longest = max(st_longest, t);
-            st_tile += tile;
-            st_tile2 += tile * tile;
-            atomicAdd(&s_stats[16 + me], 1ull);
+        if (done || cut) {  // the final state stays in board / t / fours / e / seen15 until it is parked at the loop top
+            fin_live = true;
+            fin_cut = cut;
             phase = PHASE_NONE;
         }
     }
+    epilogue();  // whatever is still parked (a finished lane always passes the loop top, and is parked, before the loop ends)
 
     atomicAdd(&s_stats[0], (unsigned long long)st_episodes);
     atomicAdd(&s_stats[1], st_steps);
