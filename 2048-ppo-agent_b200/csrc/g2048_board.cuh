@@ -131,20 +131,19 @@ __device__ __forceinline__ uint32_t legal_mask(u64 x) {
     return (left ? 1u : 0u) | (up ? 2u : 0u) | (right ? 4u : 0u) | (down ? 8u : 0u);
 }
 
-// index (0-based cell) of the k-th (1-based) set flag of `flags` (nibble-lsb flags), branch free
+// index (0-based cell) of the k-th (1-based) set flag of `flags` (one flag per cell, at the nibble's lsb), 1 <= k <= number
+// of flags.  Prefix counts by one multiply: nibble i of w * 0x11111111 is the number of flags among cells 0..i of that
+// half (at most 8, so no carry crosses a nibble); adding 8 - k sets bit 3 of exactly the nibbles whose prefix count has
+// reached k, and the lowest of them is the cell.  (13 instructions; the popcount bisection it replaces took 25.)
 __device__ __forceinline__ int kth_flag_cell(u64 flags, int k) {
-    uint32_t lo = (uint32_t)flags, hi = (uint32_t)(flags >> 32);
-    int base = 0;
-    int c = __popc(lo);
-    uint32_t w = lo;
-    if (k > c) { k -= c; w = hi; base = 8; }
-    c = __popc(w & 0xFFFFu);
-    if (k > c) { k -= c; w >>= 16; base += 4; }
-    c = __popc(w & 0xFFu);
-    if (k > c) { k -= c; w >>= 8; base += 2; }
-    c = (int)(w & 1u);
-    if (k > c) { base += 1; }
-    return base;
+    const uint32_t lo = (uint32_t)flags, hi = (uint32_t)(flags >> 32);
+    const int c = __popc(lo);
+    const bool upper = k > c;
+    const uint32_t w = upper ? hi : lo;
+    const uint32_t kk = (uint32_t)(upper ? k - c : k);  // 1..8
+    const uint32_t prefix = w * 0x11111111u;
+    const uint32_t reached = (prefix + (8u - kk) * 0x11111111u) & 0x88888888u;
+    return (upper ? 8 : 0) + ((__ffs((int)reached) - 1) >> 2);
 }
 
 // Pgx _add_random_num given the two 32-bit draws behind uniform(k1) and uniform(k2):

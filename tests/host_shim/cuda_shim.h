@@ -35,6 +35,7 @@ static inline uint32_t __byte_perm(uint32_t a, uint32_t b, uint32_t sel) {
 static inline int __popc(uint32_t x) { return __builtin_popcount(x); }
 static inline int __popcll(unsigned long long x) { return __builtin_popcountll(x); }
 static inline int __ffsll(long long x) { return __builtin_ffsll(x); }
+static inline int __ffs(int x) { return __builtin_ffs(x); }
 static inline int __clz(int x) { return x ? __builtin_clz((unsigned)x) : 32; }
 static inline float __fsub_rn(float a, float b) { volatile float r = a - b; return r; }
 static inline float __fadd_rn(float a, float b) { volatile float r = a + b; return r; }

@@ -55,6 +55,15 @@ static void sample_t(const float* logits, const uint8_t* status, int use_mask, i
 }
 
 extern "C" {
+// every 16-cell flag mask x every valid k: the cell kth_flag_cell picks
+void shim_kth_flag_cell_all(int32_t* out /* [65536][16], -1 where k exceeds the number of flags */) {
+    for (uint32_t mask = 0; mask < 65536u; ++mask) {
+        unsigned long long flags = 0;
+        for (int i = 0; i < 16; ++i) if (mask >> i & 1u) flags |= 1ull << (4 * i);
+        const int count = __builtin_popcount(mask);
+        for (int k = 1; k <= 16; ++k) out[mask * 16 + (k - 1)] = k <= count ? kth_flag_cell(flags, k) : -1;
+    }
+}
 void shim_threefry(uint32_t k0, uint32_t k1, uint32_t x0, uint32_t x1, uint32_t* out) {
     Key y = threefry2x32(Key{k0, k1}, x0, x1);
     out[0] = y.a;

@@ -208,6 +208,21 @@ def _unpack(x):
     return ((x[:, None] >> (np.arange(16, dtype=np.uint64) * np.uint64(4))) & np.uint64(15)).astype(np.uint8)
 
 
+def test_kth_flag_cell_exhaustively(shim):
+    """The multiply-based prefix count behind the spawn position, for all 65 536 empty-cell masks and every k."""
+    got = np.zeros((65536, 16), np.int32)
+    shim.shim_kth_flag_cell_all(_p(got))
+    masks = np.arange(65536, dtype=np.uint32)
+    bits = ((masks[:, None] >> np.arange(16)) & 1).astype(np.int32)  # (65536, 16)
+    prefix = bits.cumsum(axis=1)
+    want = np.full((65536, 16), -1, np.int32)
+    for k in range(1, 17):
+        hit = (prefix == k) & (bits == 1)  # the k-th set flag
+        has = hit.any(axis=1)
+        want[has, k - 1] = hit[has].argmax(axis=1)
+    np.testing.assert_array_equal(got, want)
+
+
 def test_device_rng_on_host_matches_oracle(shim):
     out = np.zeros(2, np.uint32)
     shim.shim_threefry(C.c_uint32(0x13198A2E), C.c_uint32(0x03707344), C.c_uint32(0x243F6A88), C.c_uint32(0x85A308D3), _p(out))
