@@ -32,7 +32,7 @@ constexpr int PLAY3_TABLE_BYTES = 65536 * 2 + 65536;
 constexpr int PLAY3_SMEM_BYTES = PLAY3_TABLE_BYTES + G2048_PLAY_STATS_WORDS * 8;
 
 __device__ uint16_t g_row_left[65536];  // row slid and merged toward nibble 0
-__device__ uint8_t g_row_flags[65536];  // bit 0: the row changes when moved toward nibble 0, bit 1: toward nibble 3
+__device__ uint8_t g_row_flags[65536];  // bit 0: the row changes when moved toward nibble 0, bit 2: toward nibble 3
 
 __device__ __forceinline__ uint32_t row_left_scalar(uint32_t row) {
     uint32_t tiles[4];
@@ -65,7 +65,7 @@ __global__ void build_row_tables_kernel() {
     const uint32_t left = row_left_scalar(row);
     const uint32_t right = row_mirror_scalar(row_left_scalar(row_mirror_scalar(row)));
     g_row_left[row] = (uint16_t)left;
-    g_row_flags[row] = (uint8_t)((left != row ? 1u : 0u) | (right != row ? 2u : 0u));
+    g_row_flags[row] = (uint8_t)((left != row ? 1u : 0u) | (right != row ? 4u : 0u));  // bits 0 and 2: see the legal mask below
 }
 
 template <int MODE, int POLICY>
@@ -232,7 +232,7 @@ play3_kernel(const uint2* __restrict__ subs, int64_t n_subs, uint32_t batch_glob
         const uint32_t tlo = (uint32_t)boardT, thi = (uint32_t)(boardT >> 32);
         const uint32_t fb = s_flags[blo & 0xFFFFu] | s_flags[blo >> 16] | s_flags[bhi & 0xFFFFu] | s_flags[bhi >> 16];
         const uint32_t ft = s_flags[tlo & 0xFFFFu] | s_flags[tlo >> 16] | s_flags[thi & 0xFFFFu] | s_flags[thi >> 16];
-        lm = (fb & 1u) | ((ft & 1u) << 1) | ((fb & 2u) << 1) | ((ft & 2u) << 2);  // Left, Up, Right, Down
+        lm = fb | (ft << 1);  // rows give Left (bit 0) and Right (bit 2), columns the same bits one up: Up (1), Down (3)
 
         if (!playing) {
             phase += 1;  // INIT0 -> INIT1 -> PLAY

@@ -132,7 +132,7 @@ int g2048_play_swar(int policy, const uint32_t* d_subs, int64_t n_subs, int64_t 
                     uint32_t* d_scores, uint64_t* d_stats, void* stream);
 
 /* Test hook for the shared-memory tables of g2048_play_tables: for each 16-bit row (four nibbles, nibble 0 =
- * column 0) the row slid/merged toward column 0 and the flags (bit 0: moves left, bit 1: moves right). */
+ * column 0) the row slid/merged toward column 0 and the flags (bit 0: moves left, bit 2: moves right). */
 int g2048_row_table_lookup(const uint16_t* d_rows, int64_t n, uint16_t* d_left, uint8_t* d_flags, void* stream);
 
 /* First-generation play kernel (lanes park until six are free, per-step reward loop): identical

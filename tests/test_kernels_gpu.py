@@ -367,7 +367,8 @@ def test_row_tables_match_the_oracle_for_every_row(E):
     got_l = np.stack([(left[ok] >> (4 * c)) & 15 for c in range(4)], axis=1)
     np.testing.assert_array_equal(got_l, want_l[:, :4])
     np.testing.assert_array_equal(flags[ok] & 1, (want_l[:, :4] != cells[ok]).any(axis=1))
-    np.testing.assert_array_equal((flags[ok] >> 1) & 1, (want_r[:, :4] != cells[ok]).any(axis=1))
+    np.testing.assert_array_equal((flags[ok] >> 2) & 1, (want_r[:, :4] != cells[ok]).any(axis=1))
+    assert not (flags & ~np.uint8(5)).any()
 
 
 @pytest.mark.parametrize("mode", MODES)
