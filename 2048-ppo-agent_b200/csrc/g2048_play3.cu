@@ -122,7 +122,7 @@ play3_kernel(const uint2* __restrict__ subs, int64_t n_subs, uint32_t batch_glob
             st_steps += pk_t;
             st_score += score;
             st_cut += pk_cut ? 1u : 0u;
-            st_ovf += pk_seen15 ? 1u : 0u;
+            st_ovf += (pk_seen15 || has_max_nibble(pk_board)) ? 1u : 0u;
             st_longest = max(st_longest, pk_t);
             st_tile += tile;
             st_tile2 += tile * tile;
@@ -241,7 +241,7 @@ play3_kernel(const uint2* __restrict__ subs, int64_t n_subs, uint32_t batch_glob
         ++t;
         const bool done = lm == 0u;
         const bool cut = !done && t >= max_steps;
-        if ((t & 255u) == 0u || done || cut) seen15 |= has_max_nibble(board);
+        if ((t & 255u) == 0u) seen15 |= has_max_nibble(board);  // the final board is checked in the epilogue
         if (done || cut) {  // the final state stays in board / t / fours / e / seen15 until it is parked at the loop top
             fin_live = true;
             fin_cut = cut;
