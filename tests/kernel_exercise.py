@@ -34,6 +34,9 @@ def run_all(E, g2048, T=torch, dev="cuda"):
         rr = T.empty((ch, n), dtype=torch.float32, device=dev)
         rl = T.empty((ch, n), dtype=torch.float32, device=dev)
         E.rollout_steps(0, boards, status, subs[3:], ch, 0, 1000, 17, mode, rb, rm, rr, rl, counters)
+        live_all = torch.nonzero((status & 16) == 0).flatten()[1::2].contiguous()
+        if live_all.numel():
+            E.rollout_steps_live(1, boards, status, subs[3:], ch, 0, 1000, 17, mode, live_all, rb, rm, rr, None, counters)
         logits = torch.randn(n, 4, device=dev)
         values = torch.randn(n, device=dev)
         rv = T.empty(n, dtype=torch.float32, device=dev)
