@@ -49,10 +49,14 @@ class GuardedTorch:
             return inner.view(torch.bool).view(shape)
         return inner.view(dtype).view(shape)
 
-    def empty(self, *shape, dtype=torch.float32, device=None):
+    def empty(self, *shape, dtype=torch.float32, device=None, **kw):
+        if kw or device is None or torch.device(device).type != "cuda":  # host tensors (pinned staging buffers ...)
+            return torch.empty(*shape, dtype=dtype, device=device, **kw)
         return self._carve(shape[0] if len(shape) == 1 else shape, dtype, device, False)
 
-    def zeros(self, *shape, dtype=torch.float32, device=None):
+    def zeros(self, *shape, dtype=torch.float32, device=None, **kw):
+        if kw or device is None or torch.device(device).type != "cuda":
+            return torch.zeros(*shape, dtype=dtype, device=device, **kw)
         return self._carve(shape[0] if len(shape) == 1 else shape, dtype, device, True)
 
     def empty_like(self, t):
