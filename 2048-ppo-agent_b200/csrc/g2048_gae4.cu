@@ -39,7 +39,14 @@ constexpr int G4_THREADS = G4_STREAM_THREADS + 32 * G4_WALK_WARPS;  // 384
 #endif
 constexpr int G4_TILE = G4_TILE_STEPS;
 constexpr int G4_BLOCKS = G4_TILE / 128;
-constexpr int G4_INFLIGHT = 2;  // float4 groups of each of the four streams a thread has in flight per pass
+#ifndef G4_STORE_GROUPS_INFLIGHT
+#define G4_STORE_GROUPS_INFLIGHT 2
+#endif
+constexpr int G4_STORE_INFLIGHT = G4_STORE_GROUPS_INFLIGHT;  // the same for the store phase, which only loads V
+#ifndef G4_GROUPS_INFLIGHT
+#define G4_GROUPS_INFLIGHT 2
+#endif
+constexpr int G4_INFLIGHT = G4_GROUPS_INFLIGHT;  // float4 groups a streamer thread loads before it uses the first (4: 56 registers spill)
 
 struct G4Scratch {  // same layout as the previous generation: ticket, then flags[n_tiles], heads[n_tiles]
     unsigned int ticket;
@@ -85,7 +92,7 @@ __device__ __forceinline__ void g4_store_tile(const G4Stage& st, int64_t tile, c
                                               float* __restrict__ adv, float* __restrict__ ret, double (&m)[4], int tid) {
     const int64_t lo = tile * G4_TILE;
     const int len = (int)min((int64_t)G4_TILE, n - lo);
-    gae_tile_store<ALIGNED, G4_TILE, G4_STREAM_THREADS, G4_INFLIGHT>(st.g, values, lo, len, adv, ret, m, tid);
+    gae_tile_store<ALIGNED, G4_TILE, G4_STREAM_THREADS, G4_STORE_INFLIGHT>(st.g, values, lo, len, adv, ret, m, tid);
 }
 
 // phase 2 of one tile (walker warps only; wwarp = 0..3)
