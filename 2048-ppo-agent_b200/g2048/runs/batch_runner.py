@@ -170,6 +170,53 @@ class BatchRunner:
         out["summary"] = st
         return out
 
+    def run_eval_batch(self, batch_size: int) -> dict:
+        """Network policy, results only: play ``batch_size`` envs to termination with the ``TorchActionFunction`` and
+        return per-episode ``final_boards`` / ``lengths`` / ``scores`` and a ``summary`` like ``run_stats_batch`` -- no
+        records are kept (evaluating an agent over many games, run/viz_ppo_agent.py style, needs none), and only the
+        envs that are still alive go through the network.  Same trajectories and key chain as ``run_packed_batch``."""
+        self._check(batch_size)
+        fn = self._act_fn
+        if not hasattr(fn, "forward_logits"):
+            raise ValueError("run_eval_batch needs a TorchActionFunction; use run_stats_batch for act_randomly / act_drul")
+        lo, n = self._range(batch_size)
+        dev, mode = self.device, self.rng_mode
+        boards, status = E.env_init(self.chain.peek(1)[0], batch_size, lo, n, mode)
+        lengths = torch.zeros(n, dtype=torch.int32, device=dev)
+        scores = torch.zeros(n, dtype=torch.float32, device=dev)
+        rewards = torch.zeros(n, dtype=torch.float32, device=dev)
+        live_ids = torch.arange(n, dtype=torch.int64, device=dev)
+        t = 0
+        while True:
+            subs = self.chain.peek(1 + 2 * (t + 1))
+            if live_ids.shape[0]:
+                obs = E.expand_obs_gather(boards, live_ids, fn.obs_dtype)
+                logits, values = fn.forward_logits(obs)
+                rewards.zero_()
+                E.policy_step_live(boards, status, logits, values, fn.use_mask, fn.sample_actions, False, subs[1 + 2 * t],
+                                   subs[2 + 2 * t], live_ids, batch_size, lo, mode, None, None, rewards)
+                lengths[live_ids] += 1
+                scores += rewards.clamp_(min=0.0)  # the illegal-action penalty (-1) is not part of the game score
+            t += 1
+            done_now = int(((status & N.STATUS_DONE) != 0).sum().item())
+            if n - done_now != live_ids.shape[0]:
+                live_ids = torch.nonzero((status & N.STATUS_DONE) == 0).flatten()
+            if self._all_done(done_now, n):
+                break
+        if self.shard is not None and self.shard[1] > 1:
+            from ..dist import allreduce_max_int
+
+            t = allreduce_max_int(t, self.device)
+        self.chain.consume(1 + 2 * t)
+        exps = torch.stack([(boards >> (4 * c)) & 15 for c in range(16)], dim=1).amax(dim=1)
+        hist = torch.bincount(exps, minlength=16)
+        tiles = (2.0 ** exps.double())
+        summary = {"episodes": n, "env_steps": int(lengths.sum().item()), "score_sum": int(scores.double().sum().item()),
+                   "longest": int(lengths.max().item()) if n else 0, "loop_steps": t,
+                   "max_tile_hist": {1 << e: int(c) for e, c in enumerate(hist.tolist()) if c},
+                   "mean_max_tile": float(tiles.mean().item()) if n else 0.0}
+        return {"final_boards": boards, "lengths": lengths, "scores": scores.to(torch.int32), "summary": summary}
+
     # -- internals -----------------------------------------------------------------------------
     def _check(self, batch_size: int) -> None:
         if self._act_fn is None:

@@ -242,3 +242,24 @@ def test_recorded_rollout_of_live_envs_only(policy):
             assert torch.equal(x[alive], y[alive]), name
             assert bool((y[~alive] == 0).all()), name
         assert (full.key == live.key).all()
+
+
+def test_eval_batch_keeps_only_results_and_matches_the_recorded_run():
+    import g2048
+    make = lambda: g2048.BatchRunner(  # noqa: E731
+        init_seed=8, act_fn=g2048.TorchActionFunction(RowwiseAgent(), use_mask=True, sample_actions=False, device=torch.device("cuda")))
+    rec, ev = make(), make()
+    for batch in (33, 400):
+        ro = rec.run_packed_batch(batch)
+        out = ev.run_eval_batch(batch)
+        la = ro.lengths()
+        assert torch.equal(out["final_boards"], ro.final_boards) and torch.equal(out["lengths"], la)
+        alive = torch.arange(ro.t_steps, device="cuda").unsqueeze(1) < la.long().unsqueeze(0)
+        want_scores = (ro.rewards.clamp(min=0) * alive).sum(dim=0).to(torch.int32)
+        assert torch.equal(out["scores"], want_scores)
+        s = out["summary"]
+        assert s["episodes"] == batch and s["env_steps"] == ro.env_steps and s["loop_steps"] == ro.t_steps
+        assert sum(s["max_tile_hist"].values()) == batch
+        assert (rec.key == ev.key).all()
+    with pytest.raises(ValueError):
+        g2048.BatchRunner(init_seed=1, act_fn=g2048.act_drul).run_eval_batch(4)
