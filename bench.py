@@ -482,6 +482,14 @@ def secondary_measurements(E, N, torch, dev, flush_buf) -> dict:
     add("gather_minibatch (expand_obs_tma<float> + gather_scalars)", m * (8 + 8 + 1 + 16 + 1984 + 8 + 4 + 16), t,
         "65536 random samples: 33 B gathered + 2012 B written per sample; two launches into reused output tensors; 134 MB in all, a launch-bound size")
     del mb_out
+    # the same at a size that is not launch-bound (2^19 samples, 1.07 GB): what the two kernels do once they are busy
+    m_big = 1 << 19
+    idx_big = torch.randint(0, n_buf, (m_big,), device=dev)
+    mb_big = E.minibatch_buffers(m_big, dev)
+    t = timed(lambda: E.gather_minibatch(idx_big, packed, g_adv, g_ret, out=mb_big))
+    add("gather_minibatch, 2^19 samples", m_big * (8 + 8 + 1 + 16 + 1984 + 8 + 4 + 16), t,
+        "same kernels, 8 x the samples: 1.07 GB written")
+    del mb_big, idx_big
     del packed, g_adv, g_ret, idx
 
     # packed boards -> input embedding: 2^18 boards, d_model 256 (configs/model/transformer_combined.yaml)
@@ -531,6 +539,16 @@ def secondary_measurements(E, N, torch, dev, flush_buf) -> dict:
     t = timed(lambda: N.call("g2048_gae_time_major", N.ptr(rr), N.ptr(vv), N.ptr(mm), t_steps, b, None, 0.99, 0.95,
                              N.ptr(adv2), N.ptr(ret2), N.ptr(mom), N.stream_ptr()))
     add("gae_time_major_kernel", t_steps * b * 17, t, "C3: 128 x 65536 steps; launch-bound size (143 MB), also reported in us")
+    del rr, vv, mm, adv2, ret2
+    b4 = 4 * b
+    rr = torch.rand((t_steps, b4), device=dev)
+    vv = torch.rand((t_steps, b4), device=dev)
+    mm = ((torch.rand((t_steps, b4), device=dev) < 1 / 300).to(torch.uint8) << 6)
+    adv2 = torch.empty((t_steps, b4), dtype=torch.float32, device=dev)
+    ret2 = torch.empty((t_steps, b4), dtype=torch.float32, device=dev)
+    t = timed(lambda: N.call("g2048_gae_time_major", N.ptr(rr), N.ptr(vv), N.ptr(mm), t_steps, b4, None, 0.99, 0.95,
+                             N.ptr(adv2), N.ptr(ret2), N.ptr(mom), N.stream_ptr()))
+    add("gae_time_major_kernel, 4 x C3", t_steps * b4 * 17, t, "128 x 262144 steps (570 MB): the same kernel once the launch is amortised")
 
     # PPO rollout step (C3): synthetic logits stand in for the policy network, which is outside the product path
     mode = E.RNG_PARTITIONABLE
