@@ -28,7 +28,11 @@ template <> struct ObsOne<__nv_bfloat16> {
 };
 template <> struct ObsOne<uint8_t> { static __device__ uint8_t one() { return 1; } static __device__ uint8_t zero() { return 0; } };
 
-template <typename T>
+// AHEAD: fetch the boards of a whole round of images before the per-image loop.  With a gather (or the time-major
+// index map) every board is its own memory round trip, and inside the loop those round trips run one after the
+// other: 2^19-sample minibatch gather 4.2 -> 4.4 TB/s.  The contiguous expansion (boards share cache lines) loses
+// 3 % to the extra registers, so it keeps the in-loop loads.
+template <typename T, bool AHEAD>
 __global__ void __launch_bounds__(OBS_THREADS)
 expand_obs_tma_kernel(const u64* __restrict__ boards, int64_t n, T* __restrict__ out, int64_t rows, int64_t n_cols,
                       const int64_t* __restrict__ indices) {
@@ -52,8 +56,29 @@ expand_obs_tma_kernel(const u64* __restrict__ boards, int64_t n, T* __restrict__
 #pragma unroll
         for (int p = 0; p < PER_LANE; ++p) old_pos[j][p] = -1;
 
+    auto board_of = [&](int64_t src) -> u64 {
+        if (rows > 0) {  // out is env-major (col, row); boards are time-major (row, col)
+            const int64_t col = src / rows;
+            src = (src - col * rows) * n_cols + col;
+        }
+        if (indices) src = __ldg(&indices[src]);  // gather: out[i] = onehot(boards[indices[i]])
+        return __ldg(&boards[src]);
+    };
     int64_t img = (int64_t)blockIdx.x * OBS_WARPS + warp;
     while (img < n_images) {
+        u64 round_boards[AHEAD ? OBS_NBUF : 1][PER_LANE];
+        if (AHEAD) {
+#pragma unroll
+            for (int j = 0; j < OBS_NBUF; ++j) {
+                const int64_t first = (img + (int64_t)j * warps_total) * G;
+#pragma unroll
+                for (int p = 0; p < PER_LANE; ++p) {
+                    const int c = lane + 32 * p;
+                    const int64_t src = first + (c >> 4);
+                    round_boards[j][p] = (c < CELLS && src < n) ? board_of(src) : 0ull;
+                }
+            }
+        }
 #pragma unroll
         for (int j = 0; j < OBS_NBUF; ++j) {
             if (img >= n_images) break;  // warp-uniform
@@ -71,13 +96,7 @@ expand_obs_tma_kernel(const u64* __restrict__ boards, int64_t n, T* __restrict__
                     const int g = c >> 4, cell = c & 15;
                     int pos = -1;
                     if (g < in_image) {
-                        int64_t src = first + g;
-                        if (rows > 0) {  // out is env-major (col, row); boards are time-major (row, col)
-                            const int64_t col = src / rows;
-                            src = (src - col * rows) * n_cols + col;
-                        }
-                        if (indices) src = __ldg(&indices[src]);  // gather: out[i] = onehot(boards[indices[i]])
-                        const u64 b = __ldg(&boards[src]);
+                        const u64 b = AHEAD ? round_boards[j][p] : board_of(first + g);
                         pos = g * 496 + 31 * cell + (int)((b >> (4 * cell)) & 15ull);
                         buf[pos] = ObsOne<T>::one();
                     }
@@ -112,31 +131,38 @@ static int launch_expand_obs(const uint64_t* d_boards, int64_t n, int dtype, voi
     cudaStream_t st = (cudaStream_t)stream;
     static bool configured = false;
     if (!configured) {
-        int rc = check_cuda(cudaFuncSetAttribute(expand_obs_tma_kernel<float>, cudaFuncAttributeMaxDynamicSharedMemorySize, OBS_SMEM_BYTES), "expand_obs: smem attribute");
-        if (!rc) rc = check_cuda(cudaFuncSetAttribute(expand_obs_tma_kernel<__nv_bfloat16>, cudaFuncAttributeMaxDynamicSharedMemorySize, OBS_SMEM_BYTES), "expand_obs: smem attribute");
-        if (!rc) rc = check_cuda(cudaFuncSetAttribute(expand_obs_tma_kernel<uint8_t>, cudaFuncAttributeMaxDynamicSharedMemorySize, OBS_SMEM_BYTES), "expand_obs: smem attribute");
+        int rc = G2048_OK;
+#define G2048_OBS_SMEM(T, A) \
+    if (!rc) rc = check_cuda(cudaFuncSetAttribute(expand_obs_tma_kernel<T, A>, cudaFuncAttributeMaxDynamicSharedMemorySize, OBS_SMEM_BYTES), "expand_obs: smem attribute")
+        G2048_OBS_SMEM(float, false); G2048_OBS_SMEM(float, true);
+        G2048_OBS_SMEM(__nv_bfloat16, false); G2048_OBS_SMEM(__nv_bfloat16, true);
+        G2048_OBS_SMEM(uint8_t, false); G2048_OBS_SMEM(uint8_t, true);
+#undef G2048_OBS_SMEM
         if (rc) return rc;
         configured = true;
     }
+    const bool ahead = d_indices != nullptr || rows > 0;  // every board is its own round trip
     auto grid_for = [&](int64_t images) {
         const int64_t need = (images + OBS_WARPS - 1) / OBS_WARPS;
         const int64_t cap = (int64_t)sms * 3;  // 3 resident CTAs of 62 KiB per SM, persistent loop
         return (unsigned)(need < cap ? need : cap);
     };
+#define G2048_OBS_LAUNCH(T, images)                                                                                     \
+    do {                                                                                                                \
+        if (ahead)                                                                                                      \
+            expand_obs_tma_kernel<T, true><<<grid_for(images), OBS_THREADS, OBS_SMEM_BYTES, st>>>(                      \
+                (const u64*)d_boards, n, (T*)d_out, rows, n_cols, d_indices);                                           \
+        else                                                                                                            \
+            expand_obs_tma_kernel<T, false><<<grid_for(images), OBS_THREADS, OBS_SMEM_BYTES, st>>>(                     \
+                (const u64*)d_boards, n, (T*)d_out, rows, n_cols, d_indices);                                           \
+    } while (0)
     switch (dtype) {
-        case G2048_OBS_F32:
-            expand_obs_tma_kernel<float><<<grid_for(n), OBS_THREADS, OBS_SMEM_BYTES, st>>>((const u64*)d_boards, n, (float*)d_out, rows, n_cols, d_indices);
-            break;
-        case G2048_OBS_BF16:
-            expand_obs_tma_kernel<__nv_bfloat16><<<grid_for((n + 1) / 2), OBS_THREADS, OBS_SMEM_BYTES, st>>>(
-                (const u64*)d_boards, n, (__nv_bfloat16*)d_out, rows, n_cols, d_indices);
-            break;
-        case G2048_OBS_BOOL:
-            expand_obs_tma_kernel<uint8_t><<<grid_for((n + 3) / 4), OBS_THREADS, OBS_SMEM_BYTES, st>>>((const u64*)d_boards, n, (uint8_t*)d_out, rows, n_cols, d_indices);
-            break;
-        default:
-            return fail_arg("expand_obs: dtype");
+        case G2048_OBS_F32: G2048_OBS_LAUNCH(float, n); break;
+        case G2048_OBS_BF16: G2048_OBS_LAUNCH(__nv_bfloat16, (n + 1) / 2); break;
+        case G2048_OBS_BOOL: G2048_OBS_LAUNCH(uint8_t, (n + 3) / 4); break;
+        default: return fail_arg("expand_obs: dtype");
     }
+#undef G2048_OBS_LAUNCH
     G2048_CHECK_LAUNCH("expand_obs");
     return G2048_OK;
 }
