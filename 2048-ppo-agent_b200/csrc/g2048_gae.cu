@@ -355,7 +355,8 @@ extern "C" int g2048_normalize(float* d_x, int64_t n, const double* d_moments, i
 // 18.8 ms for 1e6 steps, 102 ms for 3.1e7 around 3 ms of kernels.  Now the calling thread keeps a workspace -- one
 // stream, a grow-only device buffer and a StagedCopier (g2048_hostcopy.cuh) -- and the copies are pipelined through its
 // pinned staging buffers: 1.5 ms and 74 ms
-// (tools/probes/gae_host_bench.py; the large case is bound by the single-threaded host memcpy of 527 MB).
+// (tools/probes/gae_host_bench.py; in the large case the time goes to first-touch page faults of the caller's freshly
+// allocated 248 MB of outputs -- copying the staging chunks on four threads changed nothing).
 namespace {
 
 struct GaeHostWorkspace {
