@@ -28,14 +28,39 @@ template <> struct ObsOne<__nv_bfloat16> {
 };
 template <> struct ObsOne<uint8_t> { static __device__ uint8_t one() { return 1; } static __device__ uint8_t zero() { return 0; } };
 
+// The per-sample scalars of a minibatch (g2048_gather_minibatch): gathered by the observation kernel itself, after its
+// last bulk store has been issued and before it waits for the stores to drain, so the minibatch is ONE launch.
+struct GatherScalars {
+    const uint8_t* meta;
+    const float *log_probs, *values, *adv, *ret;
+    int64_t* o_actions;
+    uchar4* o_masks;
+    float *o_log_probs, *o_values, *o_adv, *o_ret;
+};
+
+__device__ __forceinline__ void gather_scalars_at(const GatherScalars& g, const int64_t* __restrict__ idx, int64_t i) {
+    const int64_t s = __ldg(&idx[i]);
+    const uint32_t mt = g.meta ? g.meta[s] : 0u;
+    const float lp = (g.o_log_probs && g.log_probs) ? g.log_probs[s] : 0.0f;
+    const float vl = (g.o_values && g.values) ? g.values[s] : 0.0f;
+    const float ad = (g.o_adv && g.adv) ? g.adv[s] : 0.0f;
+    const float rt = (g.o_ret && g.ret) ? g.ret[s] : 0.0f;
+    if (g.o_actions) g.o_actions[i] = (int64_t)(mt & 3u);
+    if (g.o_masks) g.o_masks[i] = make_uchar4((mt >> 2) & 1u, (mt >> 3) & 1u, (mt >> 4) & 1u, (mt >> 5) & 1u);
+    if (g.o_log_probs && g.log_probs) g.o_log_probs[i] = lp;
+    if (g.o_values && g.values) g.o_values[i] = vl;
+    if (g.o_adv && g.adv) g.o_adv[i] = ad;
+    if (g.o_ret && g.ret) g.o_ret[i] = rt;
+}
+
 // AHEAD: fetch the boards of a whole round of images before the per-image loop.  With a gather (or the time-major
 // index map) every board is its own memory round trip, and inside the loop those round trips run one after the
 // other: 2^19-sample minibatch gather 4.2 -> 4.4 TB/s.  The contiguous expansion (boards share cache lines) loses
 // 3 % to the extra registers, so it keeps the in-loop loads.
-template <typename T, bool AHEAD>
+template <typename T, bool AHEAD, bool SCALARS = false>
 __global__ void __launch_bounds__(OBS_THREADS)
 expand_obs_tma_kernel(const u64* __restrict__ boards, int64_t n, T* __restrict__ out, int64_t rows, int64_t n_cols,
-                      const int64_t* __restrict__ indices) {
+                      const int64_t* __restrict__ indices, const GatherScalars sc = GatherScalars{}) {
     constexpr int G = OBS_IMAGE_BYTES / (496 * (int)sizeof(T));  // boards per image
     constexpr int CELLS = 16 * G;
     constexpr int PER_LANE = (CELLS + 31) / 32;
@@ -112,6 +137,10 @@ expand_obs_tma_kernel(const u64* __restrict__ boards, int64_t n, T* __restrict__
             img += warps_total;
         }
     }
+    if (SCALARS) {  // the minibatch's per-sample scalars, while the last bulk stores drain
+        for (int64_t i = (int64_t)blockIdx.x * OBS_THREADS + threadIdx.x; i < n; i += (int64_t)gridDim.x * OBS_THREADS)
+            gather_scalars_at(sc, indices, i);
+    }
     if (lane == 0) bulk_wait_all<0>();
 }
 
@@ -122,8 +151,9 @@ using namespace g2048;
 static inline bool aligned16(const void* p) { return ((uintptr_t)p & 15u) == 0; }
 
 static int launch_expand_obs(const uint64_t* d_boards, int64_t n, int dtype, void* d_out, int64_t rows, int64_t n_cols,
-                             const int64_t* d_indices, void* stream) {
+                             const int64_t* d_indices, void* stream, const GatherScalars* scalars = nullptr) {
     G2048_REQUIRE(n >= 0 && rows >= 0 && (rows == 0 || (n_cols > 0 && rows * n_cols == n)), "expand_obs: shape");
+    G2048_REQUIRE(!scalars || (d_indices && rows == 0), "expand_obs: scalars need an index list");
     if (n == 0) return G2048_OK;
     G2048_REQUIRE(d_boards && d_out && aligned16(d_out), "expand_obs: pointers (out must be 16-byte aligned)");
     const int sms = sm_count();
@@ -138,6 +168,10 @@ static int launch_expand_obs(const uint64_t* d_boards, int64_t n, int dtype, voi
         G2048_OBS_SMEM(__nv_bfloat16, false); G2048_OBS_SMEM(__nv_bfloat16, true);
         G2048_OBS_SMEM(uint8_t, false); G2048_OBS_SMEM(uint8_t, true);
 #undef G2048_OBS_SMEM
+#define G2048_OBS_SMEM_S(T) \
+    if (!rc) rc = check_cuda(cudaFuncSetAttribute(expand_obs_tma_kernel<T, true, true>, cudaFuncAttributeMaxDynamicSharedMemorySize, OBS_SMEM_BYTES), "expand_obs: smem attribute")
+        G2048_OBS_SMEM_S(float); G2048_OBS_SMEM_S(__nv_bfloat16); G2048_OBS_SMEM_S(uint8_t);
+#undef G2048_OBS_SMEM_S
         if (rc) return rc;
         configured = true;
     }
@@ -149,7 +183,10 @@ static int launch_expand_obs(const uint64_t* d_boards, int64_t n, int dtype, voi
     };
 #define G2048_OBS_LAUNCH(T, images)                                                                                     \
     do {                                                                                                                \
-        if (ahead)                                                                                                      \
+        if (scalars)                                                                                                    \
+            expand_obs_tma_kernel<T, true, true><<<grid_for(images), OBS_THREADS, OBS_SMEM_BYTES, st>>>(                \
+                (const u64*)d_boards, n, (T*)d_out, rows, n_cols, d_indices, *scalars);                                 \
+        else if (ahead)                                                                                                 \
             expand_obs_tma_kernel<T, true><<<grid_for(images), OBS_THREADS, OBS_SMEM_BYTES, st>>>(                      \
                 (const u64*)d_boards, n, (T*)d_out, rows, n_cols, d_indices);                                           \
         else                                                                                                            \
@@ -193,14 +230,8 @@ gather_scalars_kernel(const int64_t* __restrict__ idx, int64_t m, const uint8_t*
                       float* __restrict__ o_adv, float* __restrict__ o_ret) {
     const int64_t i = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
     if (i >= m) return;
-    const int64_t s = __ldg(&idx[i]);
-    const uint32_t mt = meta ? meta[s] : 0u;
-    if (o_actions) o_actions[i] = (int64_t)(mt & 3u);
-    if (o_masks) o_masks[i] = make_uchar4((mt >> 2) & 1u, (mt >> 3) & 1u, (mt >> 4) & 1u, (mt >> 5) & 1u);
-    if (o_log_probs && log_probs) o_log_probs[i] = log_probs[s];
-    if (o_values && values) o_values[i] = values[s];
-    if (o_adv && adv) o_adv[i] = adv[s];
-    if (o_ret && ret) o_ret[i] = ret[s];
+    gather_scalars_at(GatherScalars{meta, log_probs, values, adv, ret, o_actions, o_masks, o_log_probs, o_values, o_adv, o_ret},
+                      idx, i);
 }
 }  // namespace g2048
 
@@ -212,10 +243,11 @@ extern "C" int g2048_gather_minibatch(const int64_t* d_indices, int64_t m, const
     G2048_REQUIRE(m >= 0, "gather_minibatch: m");
     if (m == 0) return G2048_OK;
     G2048_REQUIRE(d_indices, "gather_minibatch: indices");
-    if (d_obs) {
+    if (d_obs) {  // one launch: the observation kernel gathers the scalars while its last stores drain
         G2048_REQUIRE(d_boards, "gather_minibatch: boards");
-        int rc = launch_expand_obs(d_boards, m, obs_dtype, d_obs, 0, 0, d_indices, stream);
-        if (rc) return rc;
+        const g2048::GatherScalars sc{d_meta, d_log_probs, d_values, d_adv, d_ret, d_actions, (uchar4*)d_masks,
+                                      d_old_log_probs, d_old_values, d_out_adv, d_out_ret};
+        return launch_expand_obs(d_boards, m, obs_dtype, d_obs, 0, 0, d_indices, stream, &sc);
     }
     g2048::gather_scalars_kernel<<<blocks_for(m, 256), 256, 0, (cudaStream_t)stream>>>(
         d_indices, m, d_meta, d_log_probs, d_values, d_adv, d_ret, d_actions, (uchar4*)d_masks, d_old_log_probs,

@@ -479,8 +479,8 @@ def secondary_measurements(E, N, torch, dev, flush_buf) -> dict:
     idx = torch.randperm(n_buf, device=dev)[:m].contiguous()
     mb_out = E.minibatch_buffers(m, dev)
     t = timed(lambda: E.gather_minibatch(idx, packed, g_adv, g_ret, out=mb_out))
-    add("gather_minibatch (expand_obs_tma<float> + gather_scalars)", m * (8 + 8 + 1 + 16 + 1984 + 8 + 4 + 16), t,
-        "65536 random samples: 33 B gathered + 2012 B written per sample; two launches into reused output tensors; 134 MB in all, a launch-bound size")
+    add("gather_minibatch (expand_obs_tma<float, gathered, with scalars>)", m * (8 + 8 + 1 + 16 + 1984 + 8 + 4 + 16), t,
+        "65536 random samples: 33 B gathered + 2012 B written per sample; ONE launch (the observation kernel gathers the scalars while its last bulk stores drain) into reused output tensors; 134 MB in all, a launch-bound size")
     del mb_out
     # the same at a size that is not launch-bound (2^19 samples, 1.07 GB): what the two kernels do once they are busy
     m_big = 1 << 19
@@ -488,7 +488,7 @@ def secondary_measurements(E, N, torch, dev, flush_buf) -> dict:
     mb_big = E.minibatch_buffers(m_big, dev)
     t = timed(lambda: E.gather_minibatch(idx_big, packed, g_adv, g_ret, out=mb_big))
     add("gather_minibatch, 2^19 samples", m_big * (8 + 8 + 1 + 16 + 1984 + 8 + 4 + 16), t,
-        "same kernels, 8 x the samples: 1.07 GB written")
+        "same kernel, 8 x the samples: 1.07 GB written")
     del mb_big, idx_big
     del packed, g_adv, g_ret, idx
 
@@ -527,6 +527,32 @@ def secondary_measurements(E, N, torch, dev, flush_buf) -> dict:
     add("gae_flat4_kernel (pipelined)", n_g * 17, t, "2^26 steps, done rate 1/300 (episodes ~300 steps); 9 B read + 8 B written per step (SURVEY 8d); includes zeroing the scratch; walks hidden behind the neighbouring tiles' traffic, see DESIGN.md")
     t = timed(lambda: N.call("g2048_normalize", N.ptr(adv), n_g, N.ptr(mom), 1, N.stream_ptr()))
     add("normalize_kernel", n_g * 8, t, "2^26 steps in place; 4 B read + 4 B written per step")
+    # the same buffer size with the episode lengths of real play instead of a constant done rate (whose geometric
+    # lengths have a long tail: the longest of a tile's ~27 episodes is ~4 x the mean, and a tile's walk lasts as
+    # long as its longest episode): lengths of 2^18 DRUL games (C2's policy, mean ~207 steps), tiled to 2^26 steps
+    try:
+        key_g = E.words_tensor([0, 2048], dev)
+        subs_g = E.chain_advance(key_g, E.RNG_PARTITIONABLE, 1 + 2 * 2048)
+        lens = E.play(N.POLICY_DRUL, subs_g, 1 << 18, 0, 1 << 18, E.RNG_PARTITIONABLE)["lengths"].to(torch.int64)
+        ends = torch.cumsum(lens, 0) - 1
+        period = int(ends[-1].item()) + 1
+        reps_g = (n_g + period - 1) // period
+        d_real = torch.zeros(reps_g * period, dtype=torch.uint8, device=dev)
+        d_real.view(reps_g, period)[:, ends] = 1
+        d_real = d_real[:n_g].contiguous()
+
+        def gae_real():
+            scratch.zero_()
+            N.call("g2048_gae_flat", N.ptr(r), N.ptr(v), N.ptr(d_real), n_g, 0.99, 0.95, N.ptr(adv), N.ptr(ret), N.ptr(scratch),
+                   N.ptr(mom), N.stream_ptr())
+
+        t = timed(gae_real)
+        add("gae_flat4_kernel, episode lengths of real play", n_g * 17, t,
+            f"2^26 steps; episode lengths of 2^18 DRUL games (mean {float(lens.float().mean()):.0f}, longest {int(lens.max())} steps) "
+            "repeated; same kernel and bytes as the row above, which draws dones at a constant rate (geometric lengths)")
+        del d_real, lens, ends
+    except Exception as exc:  # noqa: BLE001 -- an extra row must not cost the bench line
+        rows.append({"kernel": "gae_flat4_kernel, episode lengths of real play", "error": repr(exc)})
     del r, v, d, adv, ret
 
     # GAE on time-major records: C3 (128 steps x 65536 envs)
