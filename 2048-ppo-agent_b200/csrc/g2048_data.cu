@@ -4,6 +4,7 @@
 #include <cuda_bf16.h>
 
 #include "g2048_common.cuh"
+#include "g2048_rng.cuh"
 
 namespace g2048 {
 
@@ -289,6 +290,38 @@ row_moments_kernel(const double* __restrict__ x, int64_t n, double* __restrict__
     }
 }
 
+
+// ------------------------------------------------------------------------------------------------
+// Keyed pseudo-random bijection of [0, n) evaluated at m points: the random subset of the buffer an
+// epoch trains on and the epoch's shuffle (torch.randperm(total_length)[:length], src/ppo/data_loader.py:73-101)
+// in O(m) instead of a sort of all n positions.  Balanced Feistel network, 4 rounds, over 2h bits with
+// 4^h >= n (so 4^h < 4n); round function = low h bits of the first word of Threefry-2x32(key; (right half,
+// round)); images >= n go through the network again (cycle walking, < 4 passes expected), which restricts the
+// bijection of [0, 4^h) to one of [0, n).  Integer work, 8 B written per index.
+// ------------------------------------------------------------------------------------------------
+__device__ __forceinline__ uint64_t feistel_pass(Key k, uint64_t x, int h, uint32_t mask) {
+    uint32_t left = (uint32_t)(x >> h), right = (uint32_t)x & mask;
+#pragma unroll
+    for (uint32_t r = 0; r < 4; ++r) {
+        const uint32_t f = threefry2x32(k, right, r).a & mask;
+        const uint32_t nl = right;
+        right = left ^ f;
+        left = nl;
+    }
+    return ((uint64_t)left << h) | (uint64_t)right;
+}
+
+__global__ void __launch_bounds__(256)
+random_subset_kernel(Key k, uint64_t n, int h, int64_t first, int64_t m, int64_t* __restrict__ out) {
+    const int64_t i = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
+    if (i >= m) return;
+    const uint32_t mask = (h >= 32) ? 0xFFFFFFFFu : ((1u << h) - 1u);
+    uint64_t x = (uint64_t)(first + i);
+    do {
+        x = feistel_pass(k, x, h, mask);
+    } while (x >= n);
+    out[i] = (int64_t)x;
+}
 }  // namespace g2048
 
 using namespace g2048;
@@ -418,5 +451,18 @@ extern "C" int g2048_row_moments(const double* d_x, int64_t n_features, int64_t 
     G2048_REQUIRE(d_x && d_out, "row_moments: pointers");
     row_moments_kernel<<<(unsigned)n_features, 1024, 0, (cudaStream_t)stream>>>(d_x, n, d_out);
     G2048_CHECK_LAUNCH("row_moments");
+    return G2048_OK;
+}
+
+extern "C" int g2048_random_subset(uint32_t key0, uint32_t key1, int64_t n, int64_t first, int64_t m, int64_t* d_out,
+                                   void* stream) {
+    G2048_REQUIRE(n >= 0 && first >= 0 && m >= 0 && first + m <= n && n <= (1ll << 62), "random_subset: range");
+    if (m == 0) return G2048_OK;
+    G2048_REQUIRE(d_out, "random_subset: pointers");
+    int h = 1;
+    while (h < 31 && (1ull << (2 * h)) < (uint64_t)n) ++h;  // 4^h >= n
+    random_subset_kernel<<<blocks_for(m, 256), 256, 0, (cudaStream_t)stream>>>(Key{key0, key1}, (uint64_t)n, h, first, m,
+                                                                              d_out);
+    G2048_CHECK_LAUNCH("random_subset");
     return G2048_OK;
 }

@@ -41,6 +41,7 @@ _I64 = C.c_int64
 _INT = C.c_int
 _DBL = C.c_double
 _U64 = C.c_uint64
+_U32 = C.c_uint32
 
 _SIGNATURES = {
     "g2048_version": (_INT, []),
@@ -78,6 +79,7 @@ _SIGNATURES = {
     "g2048_compact_records": (_INT, [_P, _P, _P, _P, _P, _I64, _I64, _P, _P, _I64, _P, _P, _P, _P, _P, _P]),
     "g2048_unpack_flat_meta": (_INT, [_P, _I64, _P, _P, _P, _P]),
     "g2048_gather_minibatch": (_INT, [_P, _I64, _P, _P, _P, _P, _P, _P, _INT, _P, _P, _P, _P, _P, _P, _P, _P]),
+    "g2048_random_subset": (_INT, [_U32, _U32, _I64, _I64, _I64, _P, _P]),
     "g2048_embed_boards": (_INT, [_P, _I64, _P, _P, _INT, _INT, _P, _P]),
     "g2048_embed_boards_bulk": (_INT, [_P, _I64, _P, _P, _INT, _INT, _P, _P]),
     "g2048_embed_boards_plain": (_INT, [_P, _I64, _P, _P, _INT, _INT, _P, _P]),

@@ -396,6 +396,18 @@ def unpack_flat_meta(meta: torch.Tensor):
     return actions, masks, term
 
 
+def random_subset(n: int, m: int, key, device, first: int = 0, out: torch.Tensor | None = None) -> torch.Tensor:
+    """P(first), ..., P(first + m - 1) for the keyed pseudo-random bijection P of [0, n) (g2048_random_subset):
+    m distinct random buffer positions in O(m) -- torch.randperm(n)[:m] without sorting n keys.  key: two uint32
+    words (or one int seed)."""
+    N.require_cuda()
+    k0, k1 = (0, int(key)) if isinstance(key, int) else (int(key[0]), int(key[1]))
+    if out is None:
+        out = torch.empty(m, dtype=torch.int64, device=device)
+    call("g2048_random_subset", k0 & 0xFFFFFFFF, k1 & 0xFFFFFFFF, n, first, m, ptr(out), stream_ptr())
+    return out
+
+
 def minibatch_buffers(m: int, device, obs_dtype=torch.float32, with_gae: bool = True) -> dict:
     """Output tensors of gather_minibatch for m samples (pass them back through `out=` to reuse them)."""
     dev = device
@@ -414,7 +426,7 @@ def minibatch_buffers(m: int, device, obs_dtype=torch.float32, with_gae: bool = 
 def gather_minibatch(indices: torch.Tensor, packed: dict, adv: torch.Tensor | None, ret: torch.Tensor | None,
                      obs_dtype=torch.float32, out: dict | None = None) -> dict:
     """Minibatch `indices` (int64, device) of a flat packed buffer (RolloutBuffer.get_packed()) as the
-    tensors a PPO update consumes; one observation kernel + one scalar-gather kernel.  obs_dtype=None: no
+    tensors a PPO update consumes, in one launch (the observation kernel gathers the scalars too).  obs_dtype=None: no
     observations -- the batch carries the gathered bitboards under "boards" for ppo.board_embedding.
     out: tensors from minibatch_buffers() of the same size to write into instead of allocating."""
     m = indices.shape[0]

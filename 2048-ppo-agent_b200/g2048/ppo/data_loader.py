@@ -91,11 +91,19 @@ class DevicePPOBatches:
             self.length = max_samples_per_epoch
             self.active_indices = self._sample_indices()
 
-    def _randperm(self, n: int) -> torch.Tensor:
-        return torch.randperm(n, device=self.device, generator=self.generator)
+    def _randperm(self, n: int, m: int = None) -> torch.Tensor:
+        """m (default n) distinct random positions of [0, n).  With an explicit torch generator: torch.randperm on
+        the device.  Otherwise ``g2048_random_subset`` -- a keyed bijection evaluated at m points, O(m) instead of a
+        sort of n keys (C4: 3.1e7 positions, 300 000 wanted: 2.8 ms -> a few microseconds) -- with the key drawn from
+        torch's global CPU generator, so ``torch.manual_seed`` makes the epochs reproducible as in the reference."""
+        m = n if m is None else m
+        if self.generator is not None:
+            return torch.randperm(n, device=self.device, generator=self.generator)[:m]
+        key = torch.randint(0, 1 << 32, (2,), dtype=torch.int64)
+        return E.random_subset(n, m, (int(key[0]), int(key[1])), self.device)
 
     def _sample_indices(self) -> torch.Tensor:
-        return self._randperm(self.total_length)[: self.length]
+        return self._randperm(self.total_length, self.length)
 
     def reset_epoch(self):
         if self.shuffle_on_reset and self.active_indices is not None:

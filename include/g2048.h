@@ -284,6 +284,14 @@ int g2048_gather_minibatch(const int64_t* d_indices, int64_t m, const uint64_t* 
                            int obs_dtype, void* d_obs, int64_t* d_actions, uint8_t* d_masks, float* d_old_log_probs,
                            float* d_old_values, float* d_out_adv, float* d_out_ret, void* stream);
 
+/* Random subset / shuffle of buffer positions (replaces torch.randperm(total_length)[:length] and the DataLoader's
+ * shuffle, src/ppo/data_loader.py:73-101,217-223): d_out[i] = P(first + i) for i < m, where P is a pseudo-random
+ * bijection of [0, n) selected by the key -- a 4-round Feistel network over 2h bits (4^h >= n) whose round function
+ * is Threefry-2x32(key; (right half, round)), restricted to [0, n) by cycle walking.  Distinct inputs give distinct
+ * positions, so first = 0, m = n is a full shuffle and m < n a subset without replacement, in O(m) work.
+ * first + m <= n <= 2^62. */
+int g2048_random_subset(uint32_t key0, uint32_t key1, int64_t n, int64_t first, int64_t m, int64_t* d_out, void* stream);
+
 /* ---- packed boards -> input embedding (src/ppo/ppo_agent.py:60,108) */
 
 /* out[i, c, :] = table[exponent of cell c of board i, :] -- what Linear(31 -> d_model, bias=False) returns for the

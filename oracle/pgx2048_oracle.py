@@ -455,3 +455,27 @@ def running_stats_merge(n_a, mean_a, var_a, n_b, mean_b, var_b):
     mean = (mean_a * n_a + mean_b * n_b) / total
     var = (var_b * n_b + n_a * var_a + delta2 * (n_a * n_b) / total) / total
     return total, mean, var
+
+
+def random_subset(key, n: int, first: int, m: int):
+    """The keyed bijection of [0, n) behind the product's g2048_random_subset, restated (the reference draws its
+    subsets with torch.randperm(total_length)[:length], data_loader.py:73-101: same distribution, different stream):
+    4-round balanced Feistel network over 2h bits, 4^h >= n, round function = low h bits of the first word of
+    Threefry-2x32(key; (right half, round)), cycle walking for images >= n."""
+    h = 1
+    while h < 31 and (1 << (2 * h)) < n:
+        h += 1
+    mask = np.uint64((1 << h) - 1)
+    x = np.arange(first, first + m, dtype=np.uint64)
+    todo = np.ones(m, dtype=bool)
+    while todo.any():
+        cur = x[todo]
+        left = (cur >> np.uint64(h)).astype(np.uint64)
+        right = cur & mask
+        for r in range(4):
+            f = threefry2x32(key[0], key[1], right.astype(U32), np.full(right.shape, r, dtype=U32))[0].astype(np.uint64) & mask
+            left, right = right, left ^ f
+        cur = (left << np.uint64(h)) | right
+        x[todo] = cur
+        todo[todo] = cur >= np.uint64(n)
+    return x.astype(np.int64)

@@ -102,6 +102,8 @@ def run_all(E, g2048, T=torch, dev="cuda"):
     idx = torch.randperm(5000, device=dev)[:777].contiguous()
     for dt in (torch.float32, torch.bfloat16):
         E.gather_minibatch(idx, packed, torch.rand(5000, device=dev), torch.rand(5000, device=dev), obs_dtype=dt)
+    E.random_subset(5000, 777, (1, 2), dev, first=13)
+    E.random_subset(1, 1, 9, dev)
     eb = packed["boards"][:301].contiguous()
     for dt, d_model in ((torch.float32, 256), (torch.bfloat16, 256), (torch.float32, 12), (torch.bfloat16, 8)):
         table = torch.randn(31, d_model, device=dev).to(dt)

@@ -385,6 +385,17 @@ def test_device_minibatches_equal_the_reference_format_dataset(G):
     assert not torch.equal(first, sub.active_indices)
     batch = next(iter(sub))
     assert batch["observations"].dtype == torch.bfloat16 and float(batch["observations"].float().sum()) == 64 * 16
+    # without an explicit generator the subset and the shuffle come from g2048_random_subset, keyed from torch's
+    # global generator: distinct positions, every sample of the subset exactly once per epoch, reproducible
+    assert len(torch.unique(sub.active_indices)) == 640 and int(sub.active_indices.max()) < n
+    torch.manual_seed(77)
+    a = G.DevicePPOBatches(packed, batch_size=64, max_samples_per_epoch=640, obs_dtype=None)
+    order_a = torch.cat([b["boards"] for b in a])
+    torch.manual_seed(77)
+    b2 = G.DevicePPOBatches(packed, batch_size=64, max_samples_per_epoch=640, obs_dtype=None)
+    assert torch.equal(a.active_indices, b2.active_indices)
+    assert torch.equal(order_a, torch.cat([b["boards"] for b in b2]))
+    assert torch.equal(torch.sort(order_a).values, torch.sort(packed["boards"][a.active_indices]).values)
 
 
 # ------------------------------------------------------------------------------------- policy network path

@@ -655,3 +655,21 @@ def test_no_cpu_fallback_errors_are_loud(E):
         E.play(0, torch.zeros((2, 2), dtype=torch.int32, device="cuda"), 4, 0, 4, 1)  # n_subs < 3
     with pytest.raises(RuntimeError):
         E.env_init(u32([1, 2]), 4, 3, 2, 1)  # env_lo + n > batch
+
+
+@pytest.mark.parametrize("n,first,m", [(1, 0, 1), (5, 0, 5), (17, 3, 14), (4097, 0, 4097), (100003, 777, 50001),
+                                         (31_000_000, 0, 300_000), ((1 << 40) + 12345, 1 << 39, 70001)])
+def test_random_subset_matches_oracle(E, n, first, m):
+    """g2048_random_subset vs the oracle's restatement, bit-exact; the outputs are distinct positions of [0, n)."""
+    key = (0x9E3779B9, n & 0xFFFFFFFF)
+    got = E.random_subset(n, m, key, "cuda", first=first).cpu().numpy()
+    np.testing.assert_array_equal(got, O.random_subset(key, n, first, m))
+    assert got.min() >= 0 and got.max() < n and len(np.unique(got)) == m
+    if first == 0 and m == n:
+        assert np.array_equal(np.sort(got), np.arange(n))
+
+
+def test_random_subset_rejects_bad_ranges(E):
+    for n, first, m in ((10, 5, 6), (-1, 0, 0), (10, -1, 2)):
+        with pytest.raises(RuntimeError):
+            E.random_subset(n, m, 1, "cuda", first=first)

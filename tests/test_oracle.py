@@ -259,3 +259,22 @@ def test_logprob_formula_matches_reference(golden_ppo):
         lse = m + np.log(np.exp(lg - m).sum(-1, keepdims=True))
         lp = (lg - lse)[np.arange(lg.shape[0]), g[f"{pre}_actions"]]
         np.testing.assert_allclose(lp, g[f"{pre}_log_probs"], rtol=1e-5, atol=1e-6)
+
+
+def test_random_subset_is_a_keyed_bijection():
+    """oracle.random_subset (the restatement of g2048_random_subset): every n gives a permutation of [0, n), windows
+    of it are its slices, different keys give different permutations, and a subset covers the range evenly."""
+    for n in (1, 2, 3, 4, 5, 16, 17, 255, 256, 257, 4097, 100003):
+        full = O.random_subset((11, 22), n, 0, n)
+        assert np.array_equal(np.sort(full), np.arange(n)), n
+        if n > 20:
+            np.testing.assert_array_equal(O.random_subset((11, 22), n, 7, 9), full[7:16])
+            assert not np.array_equal(full, O.random_subset((11, 23), n, 0, n))
+    n, m = 31_000_000, 300_000  # C4's buffer and configs/trainer/default.yaml max_samples_per_epoch
+    sub = O.random_subset((0, 2048), n, 0, m)
+    assert len(np.unique(sub)) == m and sub.min() >= 0 and sub.max() < n
+    hist = np.bincount(sub * 100 // n, minlength=100)  # 3 000 expected per bin, sigma ~ 55
+    assert np.abs(hist - m / 100).max() < 6 * np.sqrt(m / 100)
+    # no visible order: consecutive outputs are uncorrelated
+    c = np.corrcoef(sub[:-1].astype(np.float64), sub[1:].astype(np.float64))[0, 1]
+    assert abs(c) < 0.01
