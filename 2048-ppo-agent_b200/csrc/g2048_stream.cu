@@ -30,12 +30,17 @@ template <> struct ObsOne<uint8_t> { static __device__ uint8_t one() { return 1;
 
 // The per-sample scalars of a minibatch (g2048_gather_minibatch): gathered by the observation kernel itself, after its
 // last bulk store has been issued and before it waits for the stores to drain, so the minibatch is ONE launch.
+// (Tried and dropped: fetching them along with the boards inside the image loop, one scalar per idle lane, a round
+// ahead of its use -- the scattered 4-byte stores between an image's flips and its fence.proxy.async slowed the loop
+// from 243 to 385 us at 2^19 samples.  As a phase of their own the 2.6e6 random sector reads take ~40 us there.)
 struct GatherScalars {
     const uint8_t* meta;
     const float *log_probs, *values, *adv, *ret;
     int64_t* o_actions;
     uchar4* o_masks;
     float *o_log_probs, *o_values, *o_adv, *o_ret;
+    const unsigned long long* boards;  // stand-alone scalar kernel only (no observations: the batch carries bitboards)
+    unsigned long long* o_boards;
 };
 
 __device__ __forceinline__ void gather_scalars_at(const GatherScalars& g, const int64_t* __restrict__ idx, int64_t i) {
@@ -51,6 +56,7 @@ __device__ __forceinline__ void gather_scalars_at(const GatherScalars& g, const 
     if (g.o_values && g.values) g.o_values[i] = vl;
     if (g.o_adv && g.adv) g.o_adv[i] = ad;
     if (g.o_ret && g.ret) g.o_ret[i] = rt;
+    if (g.o_boards && g.boards) g.o_boards[i] = g.boards[s];
 }
 
 // AHEAD: fetch the boards of a whole round of images before the per-image loop.  With a gather (or the time-major
@@ -227,10 +233,12 @@ gather_scalars_kernel(const int64_t* __restrict__ idx, int64_t m, const uint8_t*
                       const float* __restrict__ log_probs, const float* __restrict__ values,
                       const float* __restrict__ adv, const float* __restrict__ ret, int64_t* __restrict__ o_actions,
                       uchar4* __restrict__ o_masks, float* __restrict__ o_log_probs, float* __restrict__ o_values,
-                      float* __restrict__ o_adv, float* __restrict__ o_ret) {
+                      float* __restrict__ o_adv, float* __restrict__ o_ret, const unsigned long long* __restrict__ boards,
+                      unsigned long long* __restrict__ o_boards) {
     const int64_t i = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
     if (i >= m) return;
-    gather_scalars_at(GatherScalars{meta, log_probs, values, adv, ret, o_actions, o_masks, o_log_probs, o_values, o_adv, o_ret},
+    gather_scalars_at(GatherScalars{meta, log_probs, values, adv, ret, o_actions, o_masks, o_log_probs, o_values, o_adv, o_ret,
+                                    boards, o_boards},
                       idx, i);
 }
 }  // namespace g2048
@@ -239,19 +247,20 @@ extern "C" int g2048_gather_minibatch(const int64_t* d_indices, int64_t m, const
                                       const uint8_t* d_meta, const float* d_log_probs, const float* d_values,
                                       const float* d_adv, const float* d_ret, int obs_dtype, void* d_obs,
                                       int64_t* d_actions, uint8_t* d_masks, float* d_old_log_probs, float* d_old_values,
-                                      float* d_out_adv, float* d_out_ret, void* stream) {
+                                      float* d_out_adv, float* d_out_ret, uint64_t* d_out_boards, void* stream) {
     G2048_REQUIRE(m >= 0, "gather_minibatch: m");
     if (m == 0) return G2048_OK;
     G2048_REQUIRE(d_indices, "gather_minibatch: indices");
+    G2048_REQUIRE(d_boards || !(d_obs || d_out_boards), "gather_minibatch: boards");
     if (d_obs) {  // one launch: the observation kernel gathers the scalars while its last stores drain
-        G2048_REQUIRE(d_boards, "gather_minibatch: boards");
         const g2048::GatherScalars sc{d_meta, d_log_probs, d_values, d_adv, d_ret, d_actions, (uchar4*)d_masks,
-                                      d_old_log_probs, d_old_values, d_out_adv, d_out_ret};
+                                      d_old_log_probs, d_old_values, d_out_adv, d_out_ret,
+                                      (const unsigned long long*)d_boards, (unsigned long long*)d_out_boards};
         return launch_expand_obs(d_boards, m, obs_dtype, d_obs, 0, 0, d_indices, stream, &sc);
     }
     g2048::gather_scalars_kernel<<<blocks_for(m, 256), 256, 0, (cudaStream_t)stream>>>(
         d_indices, m, d_meta, d_log_probs, d_values, d_adv, d_ret, d_actions, (uchar4*)d_masks, d_old_log_probs,
-        d_old_values, d_out_adv, d_out_ret);
+        d_old_values, d_out_adv, d_out_ret, (const unsigned long long*)d_boards, (unsigned long long*)d_out_boards);
     G2048_CHECK_LAUNCH("gather_minibatch");
     return G2048_OK;
 }

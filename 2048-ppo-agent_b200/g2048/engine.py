@@ -437,9 +437,7 @@ def gather_minibatch(indices: torch.Tensor, packed: dict, adv: torch.Tensor | No
     call("g2048_gather_minibatch", ptr(indices), m, ptr(packed["boards"]), ptr(packed["meta"]), ptr(packed["log_probs"]),
          ptr(packed["values"]), ptr(adv), ptr(ret), _OBS_DTYPES[obs_dtype or torch.float32], ptr(out["observations"]), ptr(out["actions"]),
          ptr(out["action_masks"]), ptr(out["log_probs"]), ptr(out["values"]), ptr(out["advantages"]), ptr(out["returns"]),
-         stream_ptr())
-    if obs_dtype is None:
-        torch.index_select(packed["boards"], 0, indices, out=out["boards"])
+         ptr(out["boards"]) if obs_dtype is None else None, stream_ptr())
     return {k: v for k, v in out.items() if v is not None}
 
 

@@ -278,11 +278,13 @@ int g2048_unpack_flat_meta(const uint8_t* d_meta, int64_t n, float* d_actions_on
  * DataLoader's collation, src/ppo/data_loader.py:132-166,217-223): for i < m, s = d_indices[i]:
  *   d_obs[i]  = one-hot (16,31) of d_boards[s] in obs_dtype (G2048_OBS_*), 16-byte aligned, may be NULL
  *   d_actions[i] int64 action index, d_masks[i] uint8 (4), d_old_log_probs / d_old_values /
- *   d_out_adv / d_out_ret float32 gathered from the corresponding source arrays.  Any output may be NULL. */
+ *   d_out_adv / d_out_ret float32 gathered from the corresponding source arrays, d_out_boards[i] = d_boards[s]
+ *   (for callers that embed the bitboards directly instead of reading observations).  Any output may be NULL.
+ *   One launch either way: the observation kernel gathers the scalars itself; without d_obs a small kernel does. */
 int g2048_gather_minibatch(const int64_t* d_indices, int64_t m, const uint64_t* d_boards, const uint8_t* d_meta,
                            const float* d_log_probs, const float* d_values, const float* d_adv, const float* d_ret,
                            int obs_dtype, void* d_obs, int64_t* d_actions, uint8_t* d_masks, float* d_old_log_probs,
-                           float* d_old_values, float* d_out_adv, float* d_out_ret, void* stream);
+                           float* d_old_values, float* d_out_adv, float* d_out_ret, uint64_t* d_out_boards, void* stream);
 
 /* Random subset / shuffle of buffer positions (replaces torch.randperm(total_length)[:length] and the DataLoader's
  * shuffle, src/ppo/data_loader.py:73-101,217-223): d_out[i] = P(first + i) for i < m, where P is a pseudo-random
