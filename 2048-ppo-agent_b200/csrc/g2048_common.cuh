@@ -37,6 +37,14 @@ struct DeviceInfo {
 // SM count of the current device (cached per device)
 int sm_count();
 
+// One-time per-device set-up (cudaFuncSetAttribute is per device): `flags` is a static bool[64] of the call site.
+// Returns a pointer to the current device's flag, or nullptr when there is no usable device.
+inline bool* device_once_flag(bool (&flags)[64]) {
+    int dev = 0;
+    if (cudaGetDevice(&dev) != cudaSuccess || dev < 0 || dev >= 64) return nullptr;
+    return &flags[dev];
+}
+
 inline unsigned blocks_for(int64_t n, int threads) { return (unsigned)((n + threads - 1) / threads); }
 
 }  // namespace g2048

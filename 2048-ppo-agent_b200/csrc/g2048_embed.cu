@@ -247,11 +247,13 @@ static int embed_forward(bool bulk, const uint64_t* d_boards, int64_t n, const i
     const int sms = sm_count();
     if (sms <= 0) return fail_arg("embed_boards: no device");
     auto kernel = bulk ? embed_boards_kernel : embed_boards_plain_kernel;
-    static int configured[2] = {48 * 1024, 48 * 1024};  // dynamic shared memory each kernel is already allowed
-    if (smem > configured[bulk]) {
+    static int configured[64][2];  // dynamic shared memory each kernel is already allowed, per device (0: the default 48 KiB)
+    int dev = 0;
+    G2048_REQUIRE(cudaGetDevice(&dev) == cudaSuccess && dev >= 0 && dev < 64, "embed_boards: device");
+    if (smem > 48 * 1024 && smem > configured[dev][bulk]) {
         int rc = check_cuda(cudaFuncSetAttribute(kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, smem), "embed_boards: smem attribute");
         if (rc) return rc;
-        configured[bulk] = smem;
+        configured[dev][bulk] = smem;
     }
     const int per_cta = bulk ? EMBED_THREADS : EMBED_THREADS / 32;
     const int64_t need = (n * 16 + per_cta - 1) / per_cta;

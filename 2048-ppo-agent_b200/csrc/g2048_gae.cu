@@ -311,10 +311,11 @@ extern "C" int g2048_gae_flat_v1(const float* d_rewards, const float* d_values, 
     G2048_REQUIRE(d_rewards && d_values && d_dones && d_adv && d_ret && d_scan_state, "gae_flat: pointers");
     const int64_t n_tiles = (n + GAE_TILE - 1) / GAE_TILE;
     G2048_REQUIRE(n_tiles <= 0x7FFFFFFFll, "gae_flat: too many steps");
-    static bool carveout_set = false;  // 14 CTAs of 15.5 KiB per SM need the shared-memory-heavy L1 split
-    if (!carveout_set) {
+    static bool carveout_on[64] = {false};  // 14 CTAs of 15.5 KiB per SM need the shared-memory-heavy L1 split
+    bool* carveout_set = device_once_flag(carveout_on);
+    if (carveout_set && !*carveout_set) {
         cudaFuncSetAttribute(gae_flat_kernel, cudaFuncAttributePreferredSharedMemoryCarveout, cudaSharedmemCarveoutMaxShared);
-        carveout_set = true;
+        *carveout_set = true;
     }
     gae_flat_kernel<<<(unsigned)n_tiles, GAE_THREADS, 0, (cudaStream_t)stream>>>(
         d_rewards, d_values, d_dones, n, n_tiles, (float)gamma, (float)(gamma * lambda_gae), d_adv, d_ret,

@@ -203,11 +203,13 @@ extern "C" int g2048_gae_flat_tiled(const float* d_rewards, const float* d_value
     // 128-bit accesses need 16-byte aligned float arrays and a 4-byte aligned done array
     const bool aligned = aligned16(d_rewards) && aligned16(d_values) && aligned16(d_adv) && aligned16(d_ret) &&
                          ((uintptr_t)d_dones & 3u) == 0;
-    static bool configured = false;
-    if (!configured) {  // several CTAs of ~26 KiB per SM need the shared-memory-heavy L1 split
+    static bool configured_on[64] = {false};
+    bool* configured = device_once_flag(configured_on);
+    if (!configured) return fail_arg("no CUDA device");
+    if (!*configured) {  // several CTAs of ~26 KiB per SM need the shared-memory-heavy L1 split
         cudaFuncSetAttribute(gae_flat3_kernel<true>, cudaFuncAttributePreferredSharedMemoryCarveout, cudaSharedmemCarveoutMaxShared);
         cudaFuncSetAttribute(gae_flat3_kernel<false>, cudaFuncAttributePreferredSharedMemoryCarveout, cudaSharedmemCarveoutMaxShared);
-        configured = true;
+        *configured = true;
     }
     cudaStream_t st = (cudaStream_t)stream;
     // prefetch distance in tiles (G2048_GAE_PREFETCH overrides, 0 = off).  Swept on B200 with tools/probes/probe_gae3.cu

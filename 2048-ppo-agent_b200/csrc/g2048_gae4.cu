@@ -250,12 +250,14 @@ extern "C" int g2048_gae_flat_pipelined(const float* d_rewards, const float* d_v
                          ((uintptr_t)d_dones & 3u) == 0;
     const int sms = sm_count();
     if (sms <= 0) return fail_arg("gae_flat: no device");
-    static bool configured = false;
-    if (!configured) {
+    static bool configured_on[64] = {false};
+    bool* configured = device_once_flag(configured_on);
+    if (!configured) return fail_arg("no CUDA device");
+    if (!*configured) {
         int rc = check_cuda(cudaFuncSetAttribute(gae_flat4_kernel<true>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)sizeof(G4Smem)), "gae_flat: smem attribute");
         if (!rc) rc = check_cuda(cudaFuncSetAttribute(gae_flat4_kernel<false>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)sizeof(G4Smem)), "gae_flat: smem attribute");
         if (rc) return rc;
-        configured = true;
+        *configured = true;
     }
     static int prefetch_tiles = -1;
     if (prefetch_tiles < 0) {

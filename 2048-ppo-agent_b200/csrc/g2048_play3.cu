@@ -299,12 +299,14 @@ static int launch_play3(const uint32_t* d_subs, int64_t n_subs, int64_t batch_gl
                         uint64_t* d_stats, cudaStream_t st) {
     int rc = ensure_row_tables(st);
     if (rc) return rc;
-    static bool configured = false;
-    if (!configured) {
+    static bool configured_on[64] = {false};
+    bool* configured = device_once_flag(configured_on);
+    if (!configured) return fail_arg("no CUDA device");
+    if (!*configured) {
         rc = check_cuda(cudaFuncSetAttribute(play3_kernel<MODE, POLICY>, cudaFuncAttributeMaxDynamicSharedMemorySize,
                                              PLAY3_SMEM_BYTES), "play: shared memory attribute");
         if (rc) return rc;
-        configured = true;
+        *configured = true;
     }
     const int sms = sm_count();
     if (sms <= 0) return fail_arg("play: no device");

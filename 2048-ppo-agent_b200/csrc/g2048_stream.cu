@@ -165,8 +165,10 @@ static int launch_expand_obs(const uint64_t* d_boards, int64_t n, int dtype, voi
     const int sms = sm_count();
     if (sms <= 0) return fail_arg("expand_obs: no device");
     cudaStream_t st = (cudaStream_t)stream;
-    static bool configured = false;
-    if (!configured) {
+    static bool configured_on[64] = {false};
+    bool* configured = device_once_flag(configured_on);
+    if (!configured) return fail_arg("no CUDA device");
+    if (!*configured) {
         int rc = G2048_OK;
 #define G2048_OBS_SMEM(T, A) \
     if (!rc) rc = check_cuda(cudaFuncSetAttribute(expand_obs_tma_kernel<T, A>, cudaFuncAttributeMaxDynamicSharedMemorySize, OBS_SMEM_BYTES), "expand_obs: smem attribute")
@@ -179,7 +181,7 @@ static int launch_expand_obs(const uint64_t* d_boards, int64_t n, int dtype, voi
         G2048_OBS_SMEM_S(float); G2048_OBS_SMEM_S(__nv_bfloat16); G2048_OBS_SMEM_S(uint8_t);
 #undef G2048_OBS_SMEM_S
         if (rc) return rc;
-        configured = true;
+        *configured = true;
     }
     const bool ahead = d_indices != nullptr || rows > 0;  // every board is its own round trip
     auto grid_for = [&](int64_t images) {
