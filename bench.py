@@ -456,11 +456,17 @@ def secondary_measurements(E, N, torch, dev, flush_buf) -> dict:
         return statistics.mean(ts)
 
     rows = []
+    # dram bytes per launch of the same rows, from the committed ncu --set full capture (tools/profile_hbm.py)
+    try:
+        traffic = json.loads((ROOT / "profiles" / "hbm_traffic.json").read_text())["rows"]
+    except Exception:  # noqa: BLE001 -- the capture is evidence, not a dependency
+        traffic = {}
 
     def add(name, bytes_per_launch, seconds, note):
         gbs = bytes_per_launch / seconds / 1e9
         rows.append({"kernel": name, "bound": "hbm", "achieved": gbs, "peak": hbm_peak, "unit": "GB/s",
-                     "frac": gbs / hbm_peak, "traffic": None, "us": seconds * 1e6, "note": note})
+                     "frac": gbs / hbm_peak, "traffic": traffic.get(name, {}).get("traffic"),
+                     "algorithmic_bytes": bytes_per_launch, "us": seconds * 1e6, "note": note})
 
     # observation expansion: C3-sized rollout record (65536 envs x 16 steps of boards -> float32 one-hot)
     n_b = 1 << 20
