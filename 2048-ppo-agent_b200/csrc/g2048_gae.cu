@@ -205,11 +205,22 @@ gae_flat_kernel(const float* __restrict__ rewards, const float* __restrict__ val
 // are in flight even at B = 64 K (one lane per env is all the parallelism there is); coalesced along B.
 // (A variant with two register sets -- next 16 steps' loads in flight during the current 16 steps' stores -- needed
 // 150 registers and was slower: 45 vs 36 us for 128 x 65 536 steps, tools/probes/tm_bench.py; 4.9 TB/s at 128 x 262 144.
-// Unroll 8: 45 us, 16: 36 us, 32: 43 us.)
-constexpr int GAE_TM_UNROLL = 16;
-constexpr int GAE_TM_THREADS = 64;
+// Unroll 8: 45 us, 16: 36 us, 32: 43 us.  ncu then showed 56 instructions per step, a third of them predicates and
+// 64-bit index arithmetic: with a predicate-free path for full batches, row pointers stepped by n and fma for the
+// squared moments 36 -> 33 us (94 -> 64 registers); unroll 8 / 32 and 32-thread CTAs re-measured: 36 / 37 / 37 us.)
+#ifndef G2048_TM_UNROLL
+#define G2048_TM_UNROLL 16
+#endif
+#ifndef G2048_TM_THREADS
+#define G2048_TM_THREADS 64
+#endif
+#ifndef G2048_TM_MIN_CTAS
+#define G2048_TM_MIN_CTAS 1
+#endif
+constexpr int GAE_TM_UNROLL = G2048_TM_UNROLL;
+constexpr int GAE_TM_THREADS = G2048_TM_THREADS;
 
-__global__ void __launch_bounds__(GAE_TM_THREADS)
+__global__ void __launch_bounds__(GAE_TM_THREADS, G2048_TM_MIN_CTAS)
 gae_time_major_kernel(const float* __restrict__ rewards, const float* __restrict__ values,
                       const uint8_t* __restrict__ meta, int64_t t_steps, int64_t n,
                       const float* __restrict__ bootstrap, float gamma, float gamma_lambda, float* __restrict__ adv,
@@ -220,13 +231,60 @@ gae_time_major_kernel(const float* __restrict__ rewards, const float* __restrict
     if (e < n) {
         float last_v = bootstrap ? bootstrap[e] : 0.0f;
         float last_gae = 0.0f;
+        // one step of the reference's loop (data_loader.py:110-128) in its fp32 order; the squares go through fma --
+        // the product of two floats is exact in double, so mul + add and fma give the same sums
+        auto step = [&](float r, float v, uint32_t d, float* __restrict__ pa, float* __restrict__ pr) {
+            if (d & 0x40u) {
+                last_v = 0.0f;
+                last_gae = 0.0f;
+            }
+            const float delta = (r + gamma * last_v) - v;
+            last_gae = delta + gamma_lambda * last_gae;
+            const float rt = last_gae + v;
+            __stcs(pa, last_gae);
+            __stcs(pr, rt);
+            last_v = v;
+            const double da = (double)last_gae, dr = (double)rt;
+            m[0] += da;
+            m[1] = __fma_rn(da, da, m[1]);
+            m[2] += dr;
+            m[3] = __fma_rn(dr, dr, m[3]);
+        };
         int64_t t = t_steps - 1;
-        while (t >= 0) {
+        // full batches: no per-step bounds test, one row pointer per array stepped back by n (ncu on the previous
+        // form: 56 instructions per step, a third of them predicates and 64-bit index arithmetic)
+        while (t >= GAE_TM_UNROLL - 1) {
+            const int64_t row = t * n + e;
+            const float* pr = rewards + row;
+            const float* pv = values + row;
+            const uint8_t* pd = meta + row;
             float r[GAE_TM_UNROLL], v[GAE_TM_UNROLL];
-            uint8_t d[GAE_TM_UNROLL];
-            const int cnt = (int)min((int64_t)GAE_TM_UNROLL, t + 1);
+            uint32_t d[GAE_TM_UNROLL];
 #pragma unroll
             for (int k = 0; k < GAE_TM_UNROLL; ++k) {
+                r[k] = __ldcs(pr);
+                v[k] = __ldcs(pv);
+                d[k] = __ldcs(pd);
+                pr -= n;
+                pv -= n;
+                pd -= n;
+            }
+            float* pa = adv + row;
+            float* pt = ret + row;
+#pragma unroll
+            for (int k = 0; k < GAE_TM_UNROLL; ++k) {
+                step(r[k], v[k], d[k], pa, pt);
+                pa -= n;
+                pt -= n;
+            }
+            t -= GAE_TM_UNROLL;
+        }
+        if (t >= 0) {  // fewer than a batch left (the oldest steps): the same batch, predicated
+            const int cnt = (int)t + 1;
+            float r[GAE_TM_UNROLL], v[GAE_TM_UNROLL];
+            uint32_t d[GAE_TM_UNROLL];
+#pragma unroll
+            for (int k = 0; k < GAE_TM_UNROLL - 1; ++k) {
                 if (k < cnt) {
                     const int64_t i = (t - k) * n + e;
                     r[k] = __ldcs(&rewards[i]);
@@ -235,26 +293,12 @@ gae_time_major_kernel(const float* __restrict__ rewards, const float* __restrict
                 }
             }
 #pragma unroll
-            for (int k = 0; k < GAE_TM_UNROLL; ++k) {
+            for (int k = 0; k < GAE_TM_UNROLL - 1; ++k) {
                 if (k < cnt) {
-                    if (d[k] & 0x40u) {
-                        last_v = 0.0f;
-                        last_gae = 0.0f;
-                    }
-                    const float delta = (r[k] + gamma * last_v) - v[k];
-                    last_gae = delta + gamma_lambda * last_gae;
-                    const float rt = last_gae + v[k];
                     const int64_t i = (t - k) * n + e;
-                    __stcs(&adv[i], last_gae);
-                    __stcs(&ret[i], rt);
-                    last_v = v[k];
-                    m[0] += (double)last_gae;
-                    m[1] += (double)last_gae * (double)last_gae;
-                    m[2] += (double)rt;
-                    m[3] += (double)rt * (double)rt;
+                    step(r[k], v[k], d[k], adv + i, ret + i);
                 }
             }
-            t -= cnt;
         }
     }
     if (moments) {
