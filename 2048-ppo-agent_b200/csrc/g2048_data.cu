@@ -3,6 +3,8 @@
 // Every kernel streams: coalesced reads, 128-bit coalesced stores, no re-reads.
 #include <cuda_bf16.h>
 
+#include <algorithm>
+
 #include "g2048_common.cuh"
 #include "g2048_rng.cuh"
 
@@ -322,6 +324,43 @@ random_subset_kernel(Key k, uint64_t n, int h, int64_t first, int64_t m, int64_t
     } while (x >= n);
     out[i] = (int64_t)x;
 }
+
+// ------------------------------------------------------------------------------------------------
+// RolloutBuffer.store_batch for ARBITRARY per-step rows (rollout_buffer.py:128-187 is generic in the observation
+// and action shapes; only 2048 one-hot observations can be packed as bitboards).  Sources are env-major
+// (n_envs, t_steps, row_bytes): the kept steps 0..first_done of an env are one contiguous run in the source and in
+// the flat destination, so the compaction is one segment copy per env -- row_bytes * (1 read + 1 write) per kept step.
+// ------------------------------------------------------------------------------------------------
+// first nonzero flag + 1 per env, 0 if there is none; one warp per env, 32 steps per ballot
+__global__ void __launch_bounds__(256)
+first_done_rows_kernel(const uint8_t* __restrict__ term, int64_t n_envs, int64_t t_steps, uint32_t* __restrict__ lengths) {
+    const int64_t e = ((int64_t)blockIdx.x * blockDim.x + threadIdx.x) >> 5;
+    const int lane = threadIdx.x & 31;
+    if (e >= n_envs) return;  // warp-uniform
+    const uint8_t* row = term + e * t_steps;
+    uint32_t len = 0;
+    for (int64_t base = 0; base < t_steps; base += 32) {
+        const int64_t t = base + lane;
+        const unsigned hit = __ballot_sync(0xFFFFFFFFu, t < t_steps && row[t] != 0);
+        if (hit) {
+            len = (uint32_t)(base + __ffs((int)hit));
+            break;
+        }
+    }
+    if (lane == 0) lengths[e] = len;
+}
+
+template <typename V>
+__global__ void __launch_bounds__(256)
+compact_rows_kernel(const V* __restrict__ src, int64_t env_stride, int64_t row_units, const uint32_t* __restrict__ lengths,
+                    const long long* __restrict__ offsets, int64_t out_base, V* __restrict__ dst) {
+    const int64_t e = blockIdx.x;
+    const int64_t units = (int64_t)lengths[e] * row_units;  // V-sized units to copy for this env
+    const V* s = src + e * env_stride;
+    V* d = dst + (out_base + offsets[e]) * row_units;
+    for (int64_t i = (int64_t)blockIdx.y * blockDim.x + threadIdx.x; i < units; i += (int64_t)gridDim.y * blockDim.x)
+        d[i] = __ldcs(&s[i]);
+}
 }  // namespace g2048
 
 using namespace g2048;
@@ -464,5 +503,41 @@ extern "C" int g2048_random_subset(uint32_t key0, uint32_t key1, int64_t n, int6
     random_subset_kernel<<<blocks_for(m, 256), 256, 0, (cudaStream_t)stream>>>(Key{key0, key1}, (uint64_t)n, h, first, m,
                                                                               d_out);
     G2048_CHECK_LAUNCH("random_subset");
+    return G2048_OK;
+}
+
+extern "C" int g2048_first_done_rows(const uint8_t* d_terminations, int64_t n_envs, int64_t t_steps, uint32_t* d_lengths,
+                                     void* stream) {
+    G2048_REQUIRE(n_envs >= 0 && t_steps >= 0, "first_done_rows: shape");
+    if (n_envs == 0) return G2048_OK;
+    G2048_REQUIRE(d_lengths && (d_terminations || t_steps == 0), "first_done_rows: pointers");
+    first_done_rows_kernel<<<blocks_for(n_envs * 32, 256), 256, 0, (cudaStream_t)stream>>>(d_terminations, n_envs, t_steps,
+                                                                                          d_lengths);
+    G2048_CHECK_LAUNCH("first_done_rows");
+    return G2048_OK;
+}
+
+extern "C" int g2048_compact_rows(const void* d_src, int64_t n_envs, int64_t t_steps, int64_t row_bytes,
+                                  const uint32_t* d_lengths, const int64_t* d_offsets, int64_t out_base, void* d_dst,
+                                  void* stream) {
+    G2048_REQUIRE(n_envs >= 0 && t_steps >= 0 && row_bytes > 0 && out_base >= 0 && n_envs <= 0x7FFFFFFFll, "compact_rows: shape");
+    if (n_envs == 0 || t_steps == 0) return G2048_OK;
+    G2048_REQUIRE(d_src && d_dst && d_lengths && d_offsets, "compact_rows: pointers");
+    // widest unit that divides the row and both base addresses (segments start at multiples of the row size)
+    const uintptr_t bits = (uintptr_t)d_src | (uintptr_t)d_dst | (uintptr_t)row_bytes;
+    const int64_t env_bytes = t_steps * row_bytes;
+    const unsigned chunks = (unsigned)std::min<int64_t>(64, (env_bytes / 16 + 255) / 256 + 1);  // CTAs per env
+    const dim3 grid((unsigned)n_envs, chunks);
+    cudaStream_t st = (cudaStream_t)stream;
+    if ((bits & 15u) == 0)
+        compact_rows_kernel<uint4><<<grid, 256, 0, st>>>((const uint4*)d_src, env_bytes / 16, row_bytes / 16, d_lengths,
+                                                         (const long long*)d_offsets, out_base, (uint4*)d_dst);
+    else if ((bits & 3u) == 0)
+        compact_rows_kernel<uint32_t><<<grid, 256, 0, st>>>((const uint32_t*)d_src, env_bytes / 4, row_bytes / 4, d_lengths,
+                                                            (const long long*)d_offsets, out_base, (uint32_t*)d_dst);
+    else
+        compact_rows_kernel<uint8_t><<<grid, 256, 0, st>>>((const uint8_t*)d_src, env_bytes, row_bytes, d_lengths,
+                                                           (const long long*)d_offsets, out_base, (uint8_t*)d_dst);
+    G2048_CHECK_LAUNCH("compact_rows");
     return G2048_OK;
 }

@@ -77,6 +77,8 @@ _SIGNATURES = {
     "g2048_episode_lengths": (_INT, [_P, _I64, _I64, _P, _P]),
     "g2048_exclusive_scan": (_INT, [_P, _I64, _P, _P]),
     "g2048_compact_records": (_INT, [_P, _P, _P, _P, _P, _I64, _I64, _P, _P, _I64, _P, _P, _P, _P, _P, _P]),
+    "g2048_first_done_rows": (_INT, [_P, _I64, _I64, _P, _P]),
+    "g2048_compact_rows": (_INT, [_P, _I64, _I64, _I64, _P, _P, _I64, _P, _P]),
     "g2048_unpack_flat_meta": (_INT, [_P, _I64, _P, _P, _P, _P]),
     "g2048_gather_minibatch": (_INT, [_P, _I64, _P, _P, _P, _P, _P, _P, _INT, _P, _P, _P, _P, _P, _P, _P, _P, _P]),
     "g2048_random_subset": (_INT, [_U32, _U32, _I64, _I64, _I64, _P, _P]),

@@ -378,6 +378,26 @@ def compact_records(rec_boards, rec_meta, rec_rewards, rec_log_probs, rec_values
          ptr(log_probs), ptr(values), stream_ptr())
 
 
+def first_done_rows(terminations: torch.Tensor) -> torch.Tensor:
+    """(n_envs, t_steps) uint8/bool env-major -> int32 (n_envs,): first done + 1, 0 if the env never terminates."""
+    n_envs, t_steps = terminations.shape
+    term = terminations if terminations.dtype == torch.uint8 else terminations.to(torch.uint8)
+    out = torch.empty(n_envs, dtype=torch.int32, device=terminations.device)
+    call("g2048_first_done_rows", ptr(term.contiguous()), n_envs, t_steps, ptr(out), stream_ptr())
+    return out
+
+
+def compact_rows(src: torch.Tensor, lengths: torch.Tensor, offsets: torch.Tensor, total: int) -> torch.Tensor:
+    """Env-major (n_envs, t_steps, *row) -> flat (total, *row): the rows t < lengths[e] of every env, env after env."""
+    n_envs, t_steps = src.shape[:2]
+    row_bytes = src[0, 0].numel() * src.element_size() if src.dim() > 2 else src.element_size()
+    out = torch.empty((total, *src.shape[2:]), dtype=src.dtype, device=src.device)
+    if total:
+        call("g2048_compact_rows", ptr(src.contiguous()), n_envs, t_steps, row_bytes, ptr(lengths), ptr(offsets), 0, ptr(out),
+             stream_ptr())
+    return out
+
+
 def meta_dones(meta: torch.Tensor) -> torch.Tensor:
     """Packed meta bytes -> uint8 done flags only (no one-hot actions / masks are materialised)."""
     n = meta.shape[0]

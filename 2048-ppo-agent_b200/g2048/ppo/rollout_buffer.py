@@ -9,6 +9,11 @@ env-major), and the reference-format arrays are produced on demand by ``g2048_ex
 
 ``store_packed(rollout)`` takes a ``BatchRunner.run_packed_batch`` result without leaving the
 device; ``store_batch(...)`` keeps the reference's numpy signature.
+
+The reference class does not depend on the environment: any observation / action shape can be stored
+(its own tests use 4- and 10-dimensional observations).  Batches that are not 2048 one-hot observations with
+one-hot actions take the generic device path -- ``g2048_first_done_rows`` + ``g2048_compact_rows``, one contiguous
+segment copy per env and field -- and are kept as float32 / bool rows; ``get_packed()`` is then unavailable.
 """
 from __future__ import annotations
 
@@ -30,8 +35,19 @@ class RolloutBuffer:
 
     def reset(self):
         """Resets the buffer to its initial state."""
-        self._parts = []  # list of (boards, meta, rewards, values, log_probs) flat device tensors
+        # ("packed", (boards, meta, rewards, values, log_probs)) or ("generic", dict of the seven reference fields),
+        # flat device tensors either way
+        self._parts = []
         self.buffer_size = 0
+        # the reference's per-step Python lists (rollout_buffer.py:47-56), kept as attributes for code that looks at
+        # them; the data itself lives on the device and is read with get_buffer_data() / get_packed()
+        self.observation_buffer = []
+        self.action_buffer = []
+        self.action_mask_buffer = []
+        self.reward_buffer = []
+        self.value_buffer = []
+        self.log_prob_buffer = []
+        self.termination_buffer = []
 
     # -- reference validation (rollout_buffer.py:58-126), same messages -------------------------
     def _validate_and_reshape_observations(self, observations: np.ndarray) -> np.ndarray:
@@ -71,22 +87,33 @@ class RolloutBuffer:
         return self._compact(rollout.boards, rollout.meta, rollout.rewards, rollout.log_probs, rollout.values, t, b)
 
     def store_batch(self, observations, actions, action_masks, rewards, values, log_probs, terminations):
-        """Reference signature (rollout_buffer.py:128-187): env-major (B, T, ...) numpy arrays,
-        observations one-hot, actions one-hot (B,T,action_dim) or indices (B,T)."""
+        """Reference signature (rollout_buffer.py:128-187): env-major (B, T, ...) numpy arrays.  2048 one-hot
+        observations with one-hot (B,T,4) actions (or action indices (B,T)) are packed as bitboards; anything else
+        is stored row by row through the generic compaction kernels."""
         observations = self._validate_and_reshape_observations(np.asarray(observations))
         dev = N.require_cuda()
         b, t = observations.shape[:2]
         if b == 0 or t == 0:
             return 0
-        if self.observation_dim != 31 or int(np.prod(observations.shape[2:-1])) != 16:
-            raise ValueError("this buffer packs 2048 observations: (..., 16, 31) one-hot")
-        obs_t = torch.from_numpy(np.ascontiguousarray(observations)).to(dev)
-        if obs_t.dtype not in (torch.bool, torch.uint8, torch.float32):
-            obs_t = obs_t.to(torch.float32)
-        boards = E.pack_obs(obs_t.contiguous()).view(b, t)
         actions = np.asarray(actions)
+        action_masks = np.asarray(action_masks)
+        packable = (self.observation_dim == 31 and int(np.prod(observations.shape[2:-1])) == 16 and self.action_dim == 4
+                    and action_masks.shape == (b, t, 4)
+                    and (actions.shape == (b, t) and np.issubdtype(actions.dtype, np.integer)
+                         or actions.shape == (b, t, 4) and bool((((actions == 0) | (actions == 1)).all(-1)
+                                                                 & (actions.sum(-1) == 1)).all())))
+        if packable:
+            obs_t = torch.from_numpy(np.ascontiguousarray(observations)).to(dev)
+            if obs_t.dtype not in (torch.bool, torch.uint8, torch.float32):
+                obs_t = obs_t.to(torch.float32)
+            boards = E.pack_obs(obs_t.contiguous())
+            # bitboards hold one-hot cells only: anything else (test data, soft observations) stays as rows
+            packable = bool(torch.equal(E.expand_obs(boards, torch.float32).view(obs_t.shape), obs_t.to(torch.float32)))
+        if not packable:
+            return self._store_rows(observations, actions, action_masks, rewards, values, log_probs, terminations, dev)
+        boards = boards.view(b, t)
         act_idx = actions.argmax(-1) if actions.ndim == 3 else actions
-        mask_bits = (np.asarray(action_masks).astype(np.uint8) * np.array([1, 2, 4, 8], np.uint8)).sum(-1)
+        mask_bits = (action_masks.astype(np.uint8) * np.array([1, 2, 4, 8], np.uint8)).sum(-1)
         meta = (act_idx.astype(np.uint8) & 3) | (mask_bits.astype(np.uint8) << 2) | (np.asarray(terminations).astype(np.uint8) << 6)
         tm = lambda a, dt: torch.from_numpy(np.ascontiguousarray(np.asarray(a).T.astype(dt))).to(dev)  # noqa: E731
         return self._compact(
@@ -94,6 +121,34 @@ class RolloutBuffer:
             None if log_probs is None else tm(log_probs, np.float32),
             None if values is None else tm(values, np.float32), t, b,
         )
+
+    def _store_rows(self, observations, actions, action_masks, rewards, values, log_probs, terminations, dev) -> int:
+        """The generic path: every field is uploaded as it is (env-major) and the steps 0..first_done of each env are
+        copied into flat device tensors (rollout_buffer.py:164-187), one segment per env and field."""
+        b, t = observations.shape[:2]
+        up = lambda a, dt: torch.from_numpy(np.ascontiguousarray(np.asarray(a).astype(dt, copy=False))).to(dev)  # noqa: E731
+        zeros = np.zeros((b, t), np.float32)
+        term = up(np.asarray(terminations).reshape(b, t) != 0, np.uint8)
+        lengths = E.first_done_rows(term)
+        offsets = E.exclusive_scan(lengths)
+        total = int(offsets[-1].item())
+        if total == 0:
+            return 0
+        fields = {
+            "observations": up(observations, np.float32),
+            "actions": up(actions, np.float32),
+            "action_masks": up(action_masks != 0, np.uint8),
+            "rewards": up(rewards, np.float32),
+            "values": up(zeros if values is None else values, np.float32),
+            "log_probs": up(zeros if log_probs is None else log_probs, np.float32),
+            "terminations": term,
+        }
+        for name, x in fields.items():
+            if x.shape[:2] != (b, t):
+                raise ValueError(f"{name} must start with (batch_size, time_steps) = {(b, t)}, got {tuple(x.shape)}")
+        self._parts.append(("generic", {k: E.compact_rows(x, lengths, offsets, total) for k, x in fields.items()}))
+        self.buffer_size += total
+        return total
 
     def _compact(self, rec_boards, rec_meta, rec_rewards, rec_log_probs, rec_values, t, b) -> int:
         dev = rec_meta.device
@@ -110,44 +165,56 @@ class RolloutBuffer:
         values = torch.zeros(total, dtype=torch.float32, device=dev)
         E.compact_records(rec_boards, rec_meta, rec_rewards, rec_log_probs, rec_values, t, b, lengths, offsets, 0,
                           boards, meta, rewards, log_probs, values)
-        self._parts.append((boards, meta, rewards, values, log_probs))
+        self._parts.append(("packed", (boards, meta, rewards, values, log_probs)))
         self.buffer_size += total
         return total
 
     # -- reading --------------------------------------------------------------------------------
     def get_packed(self) -> dict:
         """Flat device tensors: boards int64, meta uint8, rewards / values / log_probs float32."""
+        if any(kind != "packed" for kind, _ in self._parts):
+            raise ValueError("this buffer holds generic rows (not 2048 one-hot observations): there is no packed form, "
+                             "use get_buffer_data()")
         if not self._parts:
             dev = N.require_cuda()
             z = lambda dt: torch.empty(0, dtype=dt, device=dev)  # noqa: E731
             return dict(boards=z(torch.int64), meta=z(torch.uint8), rewards=z(torch.float32),
                         values=z(torch.float32), log_probs=z(torch.float32))
         if len(self._parts) > 1:
-            self._parts = [tuple(torch.cat([p[i] for p in self._parts]) for i in range(5))]
-        boards, meta, rewards, values, log_probs = self._parts[0]
+            self._parts = [("packed", tuple(torch.cat([p[i] for _, p in self._parts]) for i in range(5)))]
+        boards, meta, rewards, values, log_probs = self._parts[0][1]
         return dict(boards=boards, meta=meta, rewards=rewards, values=values, log_probs=log_probs)
+
+    def _obs_dims(self) -> tuple:
+        if isinstance(self.observation_length, (tuple, list)):
+            return (*self.observation_length, self.observation_dim)
+        return (self.observation_length, self.observation_dim)
+
+    def _part_fields(self, kind: str, part) -> dict:
+        """Device tensors of one part in the reference's layout."""
+        if kind == "generic":
+            return part
+        boards, meta, rewards, values, log_probs = part
+        onehot, masks, term = E.unpack_flat_meta(meta)
+        return {"observations": E.expand_obs(boards, torch.float32).view(boards.shape[0], *self._obs_dims()),
+                "actions": onehot, "action_masks": masks, "rewards": rewards, "values": values, "log_probs": log_probs,
+                "terminations": term}
 
     def get_buffer_data(self):
         """Reference format (rollout_buffer.py:198-206): dict of numpy arrays."""
-        p = self.get_packed()
-        n = p["boards"].shape[0]
-        if n == 0:
+        if not self._parts:
             return {
                 "observations": np.array([], dtype=np.float32), "actions": np.array([], dtype=np.float32),
                 "action_masks": np.array([], dtype=bool), "rewards": np.array([], dtype=np.float32),
                 "values": np.array([], dtype=np.float32), "log_probs": np.array([], dtype=np.float32),
                 "terminations": np.array([], dtype=bool),
             }
-        obs = E.expand_obs(p["boards"], torch.float32)
-        onehot, masks, term = E.unpack_flat_meta(p["meta"])
-        if isinstance(self.observation_length, (tuple, list)):
-            obs = obs.view(n, *self.observation_length, self.observation_dim)
-        return {
-            "observations": E.to_host(obs),
-            "actions": E.to_host(onehot),
-            "action_masks": E.to_host(masks),
-            "rewards": E.to_host(p["rewards"]),
-            "values": E.to_host(p["values"]),
-            "log_probs": E.to_host(p["log_probs"]),
-            "terminations": E.to_host(term),
-        }
+        if all(kind == "packed" for kind, _ in self._parts):
+            self.get_packed()  # one part
+        parts = [self._part_fields(kind, part) for kind, part in self._parts]
+        out = {}
+        for name in ("observations", "actions", "action_masks", "rewards", "values", "log_probs", "terminations"):
+            x = parts[0][name] if len(parts) == 1 else torch.cat([p[name] for p in parts])
+            a = E.to_host(x)
+            out[name] = a.astype(bool) if name in ("action_masks", "terminations") and a.dtype != bool else a
+        return out

@@ -269,6 +269,16 @@ int g2048_compact_records(const uint64_t* d_rec_boards, const uint8_t* d_rec_met
                           uint64_t* d_boards, uint8_t* d_meta, float* d_rewards, float* d_log_probs, float* d_values,
                           void* stream);
 
+/* RolloutBuffer.store_batch for arbitrary per-step rows (src/ppo/rollout_buffer.py:128-187 does not depend on the
+ * observation or action shape; g2048_compact_records is the form for packed 2048 records).
+ * g2048_first_done_rows: d_terminations (n_envs, t_steps) uint8 env-major -> d_lengths[e] = index of the first nonzero
+ * flag + 1, or 0 when the env never terminates (:168-175: such an env stores nothing).
+ * g2048_compact_rows: d_src (n_envs, t_steps, row_bytes) env-major; the rows t < d_lengths[e] of env e are copied to
+ * d_dst + (out_base + d_offsets[e]) * row_bytes (d_offsets = exclusive scan of d_lengths).  One call per field. */
+int g2048_first_done_rows(const uint8_t* d_terminations, int64_t n_envs, int64_t t_steps, uint32_t* d_lengths, void* stream);
+int g2048_compact_rows(const void* d_src, int64_t n_envs, int64_t t_steps, int64_t row_bytes, const uint32_t* d_lengths,
+                       const int64_t* d_offsets, int64_t out_base, void* d_dst, void* stream);
+
 /* flat packed meta -> reference-format columns: actions one-hot f32 (N,4), masks uint8 (N,4),
  * terminations uint8 (N) (src/ppo/ppo_trainer.py:197-202, rollout_buffer.py:199-205) */
 int g2048_unpack_flat_meta(const uint8_t* d_meta, int64_t n, float* d_actions_onehot, uint8_t* d_masks,

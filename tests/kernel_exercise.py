@@ -102,6 +102,16 @@ def run_all(E, g2048, T=torch, dev="cuda"):
     idx = torch.randperm(5000, device=dev)[:777].contiguous()
     for dt in (torch.float32, torch.bfloat16):
         E.gather_minibatch(idx, packed, torch.rand(5000, device=dev), torch.rand(5000, device=dev), obs_dtype=dt)
+    for shape, dt in (((333, 41, 3), torch.uint8), ((333, 41, 5), torch.float32), ((333, 41, 4, 4), torch.float32)):
+        term = torch.rand(333, 41, device=dev) < 0.05
+        lens = E.first_done_rows(term)
+        offs = E.exclusive_scan(lens)
+        total = int(offs[-1])
+        dst = T.empty((total, *shape[2:]), dtype=dt, device=dev)
+        src = torch.zeros(shape, dtype=dt, device=dev)
+        row_bytes = src[0, 0].numel() * src.element_size()
+        if total:
+            E.N.call("g2048_compact_rows", E.N.ptr(src), 333, 41, row_bytes, E.N.ptr(lens), E.N.ptr(offs), 0, E.N.ptr(dst), E.N.stream_ptr())
     E.random_subset(5000, 777, (1, 2), dev, first=13)
     E.random_subset(1, 1, 9, dev)
     eb = packed["boards"][:301].contiguous()

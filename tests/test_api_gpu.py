@@ -283,6 +283,68 @@ def test_rollout_buffer_semantics_of_the_reference_tests(G):
         rb.store_batch(np.zeros((b, t, 7, 31)), z, z, z, z, z, term)
 
 
+def test_rollout_buffer_is_generic_in_observation_and_action_shapes(G):
+    """The reference buffer stores any (B, T, ...) rows (its tests use 4- and 10-dimensional observations,
+    test_rollout_buffer.py:60-125): the generic device path against the oracle's restatement of store_batch."""
+    rng = np.random.default_rng(5)
+    for obs_len, obs_dim, act_dim, b, t in ((5, 4, 2, 7, 9), ((2, 3), 10, 3, 33, 70), (16, 31, 4, 4, 40), (1, 1, 1, 3, 1)):
+        rb = G.RolloutBuffer(obs_dim, obs_len, act_dim)
+        for name in ("observation", "action", "action_mask", "reward", "value", "log_prob", "termination"):
+            assert getattr(rb, name + "_buffer") == []  # the reference's list attributes exist (and reset() clears them)
+        dims = (*obs_len, obs_dim) if isinstance(obs_len, tuple) else (obs_len, obs_dim)
+        want = {k: [] for k in ("observations", "actions", "action_masks", "rewards", "values", "log_probs", "terminations")}
+        for call in range(3):
+            obs = rng.standard_normal((b, t, *dims)).astype(np.float32)
+            act = rng.random((b, t, act_dim)).astype(np.float32)
+            masks = rng.random((b, t, act_dim)) < 0.5
+            r, v, lp = (rng.standard_normal((b, t)).astype(np.float32) for _ in range(3))
+            term = rng.random((b, t)) < 0.08
+            term[0] = False          # an env that never terminates stores nothing
+            if b > 1:
+                term[1, 0] = True    # termination at the first step: one step kept
+            flat_obs = obs.reshape(b, t, -1) if call == 1 else obs  # flattened input is reshaped (rollout_buffer.py:99-110)
+            kept = rb.store_batch(flat_obs, act, masks, r, v, lp, term)
+            e, st = O.store_batch_indices(term)
+            assert kept == len(e)
+            for k, a in (("observations", obs), ("actions", act), ("action_masks", masks), ("rewards", r), ("values", v),
+                         ("log_probs", lp), ("terminations", term)):
+                want[k].append(a[e, st])
+        data = rb.get_buffer_data()
+        assert rb.buffer_size == sum(len(x) for x in want["rewards"]) == len(data["rewards"])
+        for k, parts in want.items():
+            np.testing.assert_array_equal(data[k], np.concatenate(parts), err_msg=k)
+        assert data["observations"].dtype == np.float32 and data["actions"].dtype == np.float32
+        assert data["action_masks"].dtype == bool and data["terminations"].dtype == bool
+        assert data["observations"].shape[1:] == dims
+        with pytest.raises(ValueError, match="generic rows"):
+            rb.get_packed()
+        rb.reset()
+        assert rb.buffer_size == 0 and rb.get_buffer_data()["rewards"].shape == (0,)
+
+
+def test_rollout_buffer_mixes_packed_and_generic_batches(G):
+    """2048 batches are packed as bitboards, a batch with soft observations (or actions that are not one-hot) falls
+    back to rows; get_buffer_data concatenates both in store order."""
+    ro = G.BatchRunner(9, G.act_randomly).run_actions_batch(8)
+    obs, actions, masks, log_probs, values, rewards, terms = ro
+    b, t = actions.shape
+    onehot = np.eye(4, dtype=np.float32)[actions]
+    zeros = np.zeros((b, t), np.float32)
+    rb = G.RolloutBuffer(31, (4, 4), 4)
+    n1 = rb.store_batch(obs, onehot, masks, rewards, zeros, log_probs, terms)
+    assert rb._parts[-1][0] == "packed"
+    soft = obs.astype(np.float32) * 0.5
+    n2 = rb.store_batch(soft, onehot, masks, rewards, zeros, log_probs, terms)
+    assert rb._parts[-1][0] == "generic" and n1 == n2 == rb.buffer_size // 2
+    data = rb.get_buffer_data()
+    e, st = O.store_batch_indices(terms)
+    np.testing.assert_array_equal(data["observations"][:n1], obs[e, st].astype(np.float32))
+    np.testing.assert_array_equal(data["observations"][n1:], soft[e, st])
+    np.testing.assert_array_equal(data["actions"], np.concatenate([onehot[e, st]] * 2))
+    np.testing.assert_array_equal(data["action_masks"], np.concatenate([masks[e, st]] * 2))
+    assert data["observations"].shape == (2 * n1, 4, 4, 31)
+
+
 def test_store_packed_equals_store_batch(G):
     runner = G.BatchRunner(5, G.act_randomly)
     ro = runner.run_packed_batch(48)

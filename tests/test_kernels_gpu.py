@@ -673,3 +673,22 @@ def test_random_subset_rejects_bad_ranges(E):
     for n, first, m in ((10, 5, 6), (-1, 0, 0), (10, -1, 2)):
         with pytest.raises(RuntimeError):
             E.random_subset(n, m, 1, "cuda", first=first)
+
+
+@pytest.mark.parametrize("row_shape,dtype", [((), torch.uint8), ((3,), torch.uint8), ((1,), torch.float32), ((5, 4), torch.float32),
+                                             ((16, 31), torch.float32), ((7,), torch.int16)])
+def test_compact_rows_matches_store_batch_indices(E, row_shape, dtype):
+    """g2048_first_done_rows + g2048_compact_rows (byte, 4-byte and 16-byte copy widths) vs the oracle's store_batch."""
+    rng = np.random.default_rng(len(row_shape) + 17)
+    for n_envs, t_steps in ((1, 1), (5, 33), (130, 64), (257, 100)):
+        term = rng.random((n_envs, t_steps)) < 0.03
+        term[0] = False
+        src = torch.from_numpy(rng.integers(0, 200, (n_envs, t_steps, *row_shape))).to(dtype).cuda()
+        lengths = E.first_done_rows(torch.from_numpy(term).cuda())
+        e, st = O.store_batch_indices(term)
+        want_len = np.array([np.flatnonzero(r)[0] + 1 if r.any() else 0 for r in term])
+        np.testing.assert_array_equal(lengths.cpu().numpy(), want_len)
+        offsets = E.exclusive_scan(lengths)
+        assert int(offsets[-1]) == len(e)
+        out = E.compact_rows(src, lengths, offsets, len(e))
+        np.testing.assert_array_equal(out.cpu().numpy(), src.cpu().numpy()[e, st])
