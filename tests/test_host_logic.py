@@ -338,3 +338,26 @@ def test_header_is_plain_c():
             pytest.skip(f"{compiler} not available")
         res = subprocess.run([compiler, *flags, "-Wall", "-Wextra", "-Werror", "-fsyntax-only", str(header)], capture_output=True, text=True)
         assert res.returncode == 0, res.stderr
+
+
+def test_reference_learner_modules_are_found_behind_the_drop_in(tmp_path):
+    """G2048_REFERENCE_ROOT: modules this package does not provide (the reference's learner) are imported from a
+    reference checkout, while every module on the hot path still resolves to this package."""
+    import subprocess
+    import sys
+    from pathlib import Path
+
+    root = Path(__file__).resolve().parent.parent
+    fake = tmp_path / "checkout"
+    (fake / "src" / "ppo").mkdir(parents=True)
+    (fake / "src" / "optim").mkdir()
+    (fake / "src" / "ppo" / "ppo_agent.py").write_text("from ..env_definitions import OBS_DIM\nfrom .rollout_buffer import RolloutBuffer\nWHO = 'reference learner'\n")
+    (fake / "src" / "ppo" / "rollout_buffer.py").write_text("raise RuntimeError('the drop-in must shadow this module')\n")
+    (fake / "src" / "optim" / "__init__.py").write_text("NAME = 'reference optim'\n")
+    code = ("import src.ppo.ppo_agent as a, src.optim as o, src.ppo.rollout_buffer as r\n"
+            "assert a.WHO == 'reference learner' and a.OBS_DIM == 31 and o.NAME == 'reference optim'\n"
+            "assert a.RolloutBuffer is r.RolloutBuffer and 'g2048' in r.RolloutBuffer.__module__\n"
+            "print('ok')\n")
+    env = dict(__import__("os").environ, G2048_REFERENCE_ROOT=str(fake), PYTHONPATH=str(root / "2048-ppo-agent_b200"))
+    res = subprocess.run([sys.executable, "-c", code], capture_output=True, text=True, env=env, timeout=300)
+    assert res.returncode == 0 and res.stdout.strip() == "ok", res.stderr[-2000:]
