@@ -132,6 +132,37 @@ class DevicePPOBatches:
             yield self.batch(order[b * self.batch_size: (b + 1) * self.batch_size])
 
 
+class _LazySamples:
+    """What ``PPODataset.__getitems__`` hands to the DataLoader's collate function: the positions of one batch.
+    ``_collate`` (the collate function of ``create_ppo_dataloader``) turns it into the batch with one indexed read
+    per field; to any other collate function it looks like the list of per-sample dicts ``__getitem__`` returns."""
+
+    def __init__(self, dataset: "PPODataset", positions: torch.Tensor):
+        self.dataset = dataset
+        self.positions = positions
+
+    def __len__(self) -> int:
+        return self.positions.shape[0]
+
+    def __getitem__(self, i):
+        return self.dataset._item(self.positions[i])
+
+    def __iter__(self):
+        return (self.dataset._item(p) for p in self.positions)
+
+    def collated(self) -> Dict[str, torch.Tensor]:
+        return self.dataset._item(self.positions)
+
+
+def _collate(batch):
+    """Collate function of ``create_ppo_dataloader``: same batches as torch's default collation of the per-sample
+    dicts (data_loader.py:217-223 builds a plain DataLoader), without the per-sample Python work -- a 2 048-sample
+    batch is nine indexed reads instead of 2 048 dicts of nine tensors each."""
+    if isinstance(batch, _LazySamples):
+        return batch.collated()
+    return torch.utils.data.default_collate(batch)
+
+
 class PPODataset(Dataset):
     """Dataset over RolloutBuffer data with GAE advantages and returns (data_loader.py:8-166)."""
 
@@ -183,8 +214,17 @@ class PPODataset(Dataset):
     def __len__(self) -> int:
         return self.length
 
+    def __getitems__(self, indices) -> _LazySamples:
+        """Batched fetch (torch's DataLoader calls this with the indices of one batch)."""
+        idx = torch.as_tensor(indices, dtype=torch.long)
+        return _LazySamples(self, self.active_indices[idx] if self.active_indices is not None else idx)
+
     def __getitem__(self, idx: int) -> Dict[str, torch.Tensor]:
         actual_idx = self.active_indices[idx] if self.active_indices is not None else idx
+        return self._item(actual_idx)
+
+    def _item(self, actual_idx) -> Dict[str, torch.Tensor]:
+        """The fields at buffer position(s) actual_idx (an int or an index tensor)."""
         return {
             "observations": self.observations[actual_idx],
             "actions": self.actions[actual_idx],
@@ -204,4 +244,5 @@ def create_ppo_dataloader(buffer_data: Dict[str, np.ndarray], gamma: float = 0.9
     """Same factory as data_loader.py:169-223."""
     dataset = PPODataset(buffer_data, gamma=gamma, lambda_gae=lambda_gae,
                          max_samples_per_epoch=max_samples_per_epoch, shuffle_on_reset=shuffle_on_reset)
-    return DataLoader(dataset, batch_size=batch_size, shuffle=shuffle, drop_last=drop_last, num_workers=num_workers)
+    return DataLoader(dataset, batch_size=batch_size, shuffle=shuffle, drop_last=drop_last, num_workers=num_workers,
+                      collate_fn=_collate)

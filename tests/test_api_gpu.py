@@ -395,6 +395,31 @@ def test_ppo_dataset_matches_reference_fixture(G, golden_ppo):
     assert batch["observations"].shape == (64, 16, 31) and batch["advantages"].shape == (64,)
 
 
+def test_dataloader_batches_equal_default_collation(G):
+    """create_ppo_dataloader fetches a batch with one indexed read per field (PPODataset.__getitems__ + its collate
+    function); the batches are those torch's default collation of the per-sample dicts gives, also for a DataLoader
+    a caller builds around the dataset with the default collate function."""
+    from torch.utils.data import DataLoader
+
+    rng = np.random.default_rng(3)
+    n = 1000
+    data = {"observations": rng.random((n, 16, 31)).astype(np.float32), "actions": np.eye(4, dtype=np.float32)[rng.integers(0, 4, n)],
+            "action_masks": rng.random((n, 4)) < 0.7, "rewards": rng.random(n).astype(np.float32),
+            "values": rng.standard_normal(n).astype(np.float32), "log_probs": -rng.random(n).astype(np.float32),
+            "terminations": rng.random(n) < 0.02}
+    for max_samples in (None, 300):
+        torch.manual_seed(1)
+        fast = G.create_ppo_dataloader(data, batch_size=64, shuffle=False, drop_last=False, max_samples_per_epoch=max_samples)
+        plain = DataLoader(fast.dataset, batch_size=64, shuffle=False, drop_last=False)  # default collate: per-sample path
+        assert fast.batch_size == 64 and len(fast) == len(plain) == -(-(max_samples or n) // 64)
+        for a, b in zip(fast, plain):
+            assert a.keys() == b.keys()
+            for k in a:
+                assert a[k].dtype == b[k].dtype and torch.equal(a[k], b[k]), k
+        item = fast.dataset[5]
+        assert item["observations"].shape == (16, 31) and item["advantages"].shape == ()
+
+
 def test_compute_gae_on_a_real_packed_buffer(G):
     ro = G.BatchRunner(9, G.act_randomly).run_packed_batch(256)
     rb = G.RolloutBuffer(31, 16, 4)
