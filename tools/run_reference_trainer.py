@@ -31,6 +31,10 @@ def main():
     ap.add_argument("--batches", type=int, default=2)
     ap.add_argument("--minibatch", type=int, default=2048)
     ap.add_argument("--epochs", type=int, default=2)
+    ap.add_argument("--device", default="cuda:0", help="where the reference's trainer keeps the agent (its default is cpu)")
+    ap.add_argument("--default-agent", action="store_true",
+                    help="configs/model/transformer_combined.yaml: d_model 256, 8 heads, 4 layers, ff 1024, hidden 512, cls")
+    ap.add_argument("--no-mask", action="store_true")
     args = ap.parse_args()
     if args.stage:
         for rel in FILES:
@@ -57,15 +61,19 @@ def main():
     assert str(SCRATCH) in origin["PPOTrainer"] and "2048-ppo-agent_b200" in origin["BatchRunner"], origin
 
     torch.manual_seed(0)
-    dev = torch.device("cuda:0")
-    agent = PPOAgent(hidden_dim=128, d_model=64, nhead=4, num_layers=2, dim_feedforward=128, dropout=0.0, reduction="cls")
+    dev = torch.device(args.device)
+    if args.default_agent:
+        agent = PPOAgent(hidden_dim=512, d_model=256, nhead=8, num_layers=4, dim_feedforward=1024, dropout=0.1, reduction="cls")
+    else:
+        agent = PPOAgent(hidden_dim=128, d_model=64, nhead=4, num_layers=2, dim_feedforward=128, dropout=0.0, reduction="cls")
     optim = dict(opt_name="adamw", max_lr=4e-4, betas=(0.9, 0.999), eps=1e-6, weight_decay=0.01, warmup_steps_ratio=0.025,
                  scheduler_names=["constant", "constant"], blacklist_weight_modules=["norm", "embedding"])
     os.chdir(ROOT / "refcheck")  # the trainer writes tensorboard logs to ./logs
     trainer = PPOTrainer(agent=agent, batch_runner=BatchRunner(init_seed=0), rollout_buffer=RolloutBuffer(31, 16, 4),
-                         optimizer_param_dict=optim, max_steps=1000, use_action_mask=True, device=dev,
+                         optimizer_param_dict=optim, max_steps=1000, use_action_mask=not args.no_mask, device=dev,
                          mixed_precision="bfloat16", max_samples_per_epoch=300000, shuffle_on_reset=True)
-    report = {"modules": origin, "envs": args.envs, "batches": args.batches}
+    report = {"modules": origin, "envs": args.envs, "batches": args.batches, "device": str(dev), "default_agent": args.default_agent,
+              "use_action_mask": not args.no_mask}
     torch.cuda.synchronize()
     t0 = time.perf_counter()
     try:
