@@ -2,6 +2,8 @@
 // lock-step recorded rollout.  All state of an env (board, mask, keys, counters) lives in the
 // registers of the one thread that owns it; HBM sees only records and per-episode results.
 #include "g2048_board.cuh"
+#include <cstdlib>
+
 #include "g2048_common.cuh"
 #include "g2048_hostcopy.cuh"
 #include "g2048_env.cuh"
@@ -460,6 +462,16 @@ extern "C" int g2048_play_v1(int policy, const uint32_t* d_subs, int64_t n_subs,
 #undef ARGS
 }
 
+// device-side address of a host pointer in pinned, mapped memory; nullptr for pageable memory
+static void* mapped_device_pointer(const void* host) {
+    cudaPointerAttributes attr;
+    if (cudaPointerGetAttributes(&attr, host) != cudaSuccess) {
+        cudaGetLastError();  // older drivers report pageable memory as an error: clear it
+        return nullptr;
+    }
+    return attr.type == cudaMemoryTypeHost ? attr.devicePointer : nullptr;
+}
+
 extern "C" int g2048_play_host(int policy, uint64_t seed, uint32_t* h_key_io, int64_t batch_global, int64_t env_lo,
                                int64_t n, int rng_mode, uint64_t* h_final_boards, uint32_t* h_lengths,
                                uint32_t* h_scores, uint64_t* h_stats) {
@@ -478,6 +490,7 @@ extern "C" int g2048_play_host(int policy, uint64_t seed, uint32_t* h_key_io, in
         StagedCopier copier;  // result arrays in pageable memory (numpy) go through pinned staging buffers
     };
     static thread_local Workspace ws;
+    static const bool zero_copy = [] { const char* e = getenv("G2048_PLAY_HOST_ZEROCOPY"); return !(e && e[0] == '0'); }();
     int rc = G2048_OK;
     int dev = 0;
     uint64_t stats[G2048_PLAY_STATS_WORDS];
@@ -514,6 +527,16 @@ extern "C" int g2048_play_host(int policy, uint64_t seed, uint32_t* h_key_io, in
         uint64_t* d_boards = h_final_boards ? (uint64_t*)(ws.buf + off_boards) : nullptr;
         uint32_t* d_len = h_lengths ? (uint32_t*)(ws.buf + off_len) : nullptr;
         uint32_t* d_score = h_scores ? (uint32_t*)(ws.buf + off_score) : nullptr;
+        // A result array in pinned (page-locked, mapped) host memory is written by the kernel itself: an episode's
+        // 16 bytes of results leave over PCIe when the episode ends, overlapped with the rest of the batch, instead
+        // of 32 MiB of copies after the kernel (G2048_PLAY_HOST_ZEROCOPY=0 restores the copies).
+        bool zc_boards = false, zc_len = false, zc_score = false;
+        if (zero_copy) {
+            void* m = nullptr;
+            if (d_boards && (m = mapped_device_pointer(h_final_boards))) { d_boards = (uint64_t*)m; zc_boards = true; }
+            if (d_len && (m = mapped_device_pointer(h_lengths))) { d_len = (uint32_t*)m; zc_len = true; }
+            if (d_score && (m = mapped_device_pointer(h_scores))) { d_score = (uint32_t*)m; zc_score = true; }
+        }
         TRY(cudaMemcpyAsync(d_key, key, sizeof(key), cudaMemcpyHostToDevice, st), "play_host: h2d key");
         TRY(cudaMemsetAsync(d_work, 0, 768, st), "play_host: memset");  // work + stats
         rc = g2048_chain_advance(d_key, rng_mode, n_subs, d_subs, st);
@@ -523,9 +546,9 @@ extern "C" int g2048_play_host(int policy, uint64_t seed, uint32_t* h_key_io, in
         if (rc) return rc;
         // results are copied optimistically; a batch that outlived its keys is replayed below
         TRY(cudaMemcpyAsync(stats, d_stats, sizeof(stats), cudaMemcpyDeviceToHost, st), "play_host: d2h stats");
-        if (d_boards && n && (rc = ws.copier.d2h(h_final_boards, d_boards, n * sizeof(uint64_t), st))) return rc;
-        if (d_len && n && (rc = ws.copier.d2h(h_lengths, d_len, n * sizeof(uint32_t), st))) return rc;
-        if (d_score && n && (rc = ws.copier.d2h(h_scores, d_score, n * sizeof(uint32_t), st))) return rc;
+        if (d_boards && !zc_boards && n && (rc = ws.copier.d2h(h_final_boards, d_boards, n * sizeof(uint64_t), st))) return rc;
+        if (d_len && !zc_len && n && (rc = ws.copier.d2h(h_lengths, d_len, n * sizeof(uint32_t), st))) return rc;
+        if (d_score && !zc_score && n && (rc = ws.copier.d2h(h_scores, d_score, n * sizeof(uint32_t), st))) return rc;
         TRY(cudaStreamSynchronize(st), "play_host: sync");
         if (stats[3] == 0 || max_steps >= (1 << 20)) break;
         max_steps *= 4;  // some episode outlived the chain: replay with a longer one

@@ -195,13 +195,19 @@ def play_stats_dict(stats: torch.Tensor) -> dict:
 
 
 def play_host(policy: int, seed: int, batch_global: int, rng_mode: int, env_lo: int = 0, n: int | None = None,
-              key: np.ndarray | None = None, per_env: bool = True):
-    """The host-buffer C entry point (numpy in / numpy out; copies and syncs inside the call)."""
+              key: np.ndarray | None = None, per_env: bool = True, pinned: bool = False):
+    """The host-buffer C entry point (numpy in / numpy out; copies and syncs inside the call).
+    pinned=True: the result arrays are page-locked host memory, which the play kernel writes directly (no copies
+    after the kernel); they are views of torch pinned tensors and stay valid as long as they are referenced."""
     N.require_cuda()
     n = batch_global - env_lo if n is None else n
-    boards = np.empty(n, np.uint64) if per_env else None
-    lengths = np.empty(n, np.uint32) if per_env else None
-    scores = np.empty(n, np.uint32) if per_env else None
+    if pinned:
+        mk = lambda dt, view: torch.empty(n, dtype=dt, pin_memory=True).numpy().view(view)  # noqa: E731
+    else:
+        mk = lambda dt, view: np.empty(n, view)  # noqa: E731
+    boards = mk(torch.int64, np.uint64) if per_env else None
+    lengths = mk(torch.int32, np.uint32) if per_env else None
+    scores = mk(torch.int32, np.uint32) if per_env else None
     stats = np.zeros(N.PLAY_STATS_WORDS, np.uint64)
     key_io = None if key is None else np.ascontiguousarray(key, np.uint32)
     as_p = lambda a: None if a is None else a.ctypes.data  # noqa: E731

@@ -381,9 +381,26 @@ def main():
     e2e = {
         "value": float(se.item()) / float(te.item()), "unit": "env-steps/s",
         "h2d_bytes_per_step": 8, "d2h_bytes_per_step": int(16 * n + 8 * N.PLAY_STATS_WORDS),
-        "api": "g2048_play_host (C ABI, host buffers): key H2D + chain kernel + play kernel + D2H of final boards, lengths, "
-               "scores (pinned host memory) and the statistics block + synchronise, per call; device workspace cached by the library",
+        "api": "g2048_play_host (C ABI, host buffers): key H2D + chain kernel + play kernel + device-to-host transfer of final "
+               "boards, lengths, scores and the statistics block + synchronise, per call; the result arrays are pinned host "
+               "memory, which the kernel writes directly over PCIe as episodes end (pageable arrays are copied after the "
+               "kernel through staging buffers: e2e.pageable_results); device workspace cached by the library",
+        # the host arrays really hold the batch: their lengths add up to the statistics block's env-step count
+        "results_checked": bool(int(h_len.sum(dtype=np.uint64)) == int(h_stats[1]) and int(h_score.sum(dtype=np.uint64)) == int(h_stats[2])),
     }
+    if rank == 0 and world == 1:  # the same call with ordinary numpy result arrays
+        p_boards, p_len, p_score = np.empty(n, np.uint64), np.empty(n, np.uint32), np.empty(n, np.uint32)
+        pg_times, pg_steps = [], 0
+        for i in range(3):
+            t0 = time.perf_counter()
+            N.call("g2048_play_host", policy_id, SEED + i, None, batch_global, lo, n, mode, p_boards.ctypes.data,
+                   p_len.ctypes.data, p_score.ctypes.data, h_stats.ctypes.data)
+            dt = time.perf_counter() - t0
+            if i >= 1:
+                pg_times.append(dt)
+                pg_steps += int(h_stats[1])
+        e2e["pageable_results"] = {"value": pg_steps / sum(pg_times), "unit": "env-steps/s",
+                                   "results_checked": bool(int(p_len.sum(dtype=np.uint64)) == int(h_stats[1]))}
     # the same call when only the episode statistics are wanted (what run_actions_max_tile returns): 256 B come back
     so_times, so_steps = [], 0
     for i in range(1 + min(args.steps, 5)):

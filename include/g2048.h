@@ -144,7 +144,8 @@ int g2048_play_v1(int policy, const uint32_t* d_subs, int64_t n_subs, int64_t ba
 /* Host-buffer form of the same call (the reference-facing entry: run_actions_max_tile's inner
  * run).  seed -> jax.random.key(seed); h_key_io (2 words, may be NULL) overrides the seed with an
  * explicit chain key and receives the key the reference's runner would hold afterwards.
- * h_* outputs may be NULL.  Copies H2D/D2H and synchronises. */
+ * h_* outputs may be NULL.  Copies H2D/D2H and synchronises.  A result array in pinned (page-locked, mapped) host
+ * memory is written by the kernel itself while the batch runs; pageable arrays are filled by staged copies after it. */
 int g2048_play_host(int policy, uint64_t seed, uint32_t* h_key_io, int64_t batch_global, int64_t env_lo, int64_t n,
                     int rng_mode, uint64_t* h_final_boards, uint32_t* h_lengths, uint32_t* h_scores,
                     uint64_t* h_stats);

@@ -344,6 +344,22 @@ def test_play_host_entry_point(E, golden_hist):
     np.testing.assert_array_equal(out["lengths"], ref["lengths"])
 
 
+def test_play_host_pinned_results_are_written_by_the_kernel(E):
+    """Pinned (mapped) result arrays take the zero-copy path of g2048_play_host: same results as pageable arrays and as
+    the oracle, including a batch large enough for the table kernel and a second call into the same arrays."""
+    for policy, seed, n, mode in ((E.POLICY_RANDOM, 11, 40000, 1), (E.POLICY_DRUL, 12, 3000, 0)):
+        a = E.play_host(policy, seed, n, mode, pinned=True)
+        b = E.play_host(policy, seed, n, mode, pinned=False)
+        ref = CO.play(seed, n, policy, mode, max_steps=4096)
+        for k in ("final_boards", "lengths", "scores"):
+            np.testing.assert_array_equal(a[k], b[k], err_msg=k)
+        np.testing.assert_array_equal(E.boards_numpy(torch.from_numpy(a["final_boards"].view(np.int64))), ref["final_boards"])
+        np.testing.assert_array_equal(a["lengths"], ref["lengths"])
+        np.testing.assert_array_equal(a["scores"], ref["scores"])
+        np.testing.assert_array_equal(a["stats"], b["stats"])
+        assert int(a["lengths"].sum()) == int(a["stats"][1])
+
+
 @pytest.mark.parametrize("entry", PLAY_ENTRIES)
 def test_play_reports_cut_short(E, entry):
     key = u32([0, 1])
