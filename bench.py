@@ -621,6 +621,24 @@ def secondary_measurements(E, N, torch, dev, flush_buf) -> dict:
 
     t = timed(ppo_rollout, reps=3)
 
+    # the same 257 launches replayed as ONE CUDA graph: what the kernels cost once the Python / ctypes launch overhead
+    # (two launches per step from the interpreter) is out of the way -- how FixedHorizonRunner(cuda_graph=True) runs them
+    t_graph = None
+    try:
+        side = torch.cuda.Stream()
+        side.wait_stream(torch.cuda.current_stream())
+        with torch.cuda.stream(side):
+            ppo_rollout()
+        torch.cuda.current_stream().wait_stream(side)
+        torch.cuda.synchronize()
+        graph = torch.cuda.CUDAGraph()
+        with torch.cuda.graph(graph):
+            ppo_rollout()
+        t_graph = timed(graph.replay, reps=3)
+        del graph
+    except Exception as exc:  # noqa: BLE001 -- an extra number must not cost the bench line
+        t_graph = f"unavailable: {exc!r}"
+
     # the policy network's forward pass at the same batch (PyTorch / cuBLAS, outside the product path): a stand-in
     # with the reference's default layer shapes (configs/model/transformer_combined.yaml: d_model 256, 8 heads,
     # 4 layers, ff 1024, hidden 512, CLS reduction, 17 tokens), bf16 autocast as in configs/trainer/default.yaml
@@ -661,6 +679,10 @@ def secondary_measurements(E, N, torch, dev, flush_buf) -> dict:
                   "(policy network = PyTorch/cuBLAS, outside the product path and not timed)",
         "env_steps_per_sec": t_steps * b / t, "ms_per_rollout": t * 1e3,
         "per_step_us": t * 1e6 / t_steps, "launches_per_rollout": 2 * t_steps + 1,
+        "graph_replay": ({"ms_per_rollout": t_graph * 1e3, "per_step_us": t_graph * 1e6 / t_steps,
+                          "env_steps_per_sec": t_steps * b / t_graph,
+                          "note": "the same launches captured once and replayed as a CUDA graph (no interpreter between them)"}
+                         if isinstance(t_graph, float) else t_graph),
         "policy_forward_ms_per_step": fwd_ms,
         "policy_forward_note": "same-shaped PyTorch Transformer (3.96 M parameters, bf16 autocast, 65536 x 17 tokens), for scale only",
         "kernels": "per step: expand_obs<f32> (network input) + policy_step (mask, sample, log-prob, env step, auto-reset, record write); then gae_time_major",
