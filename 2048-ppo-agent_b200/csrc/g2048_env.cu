@@ -472,9 +472,9 @@ static void* mapped_device_pointer(const void* host) {
     return attr.type == cudaMemoryTypeHost ? attr.devicePointer : nullptr;
 }
 
-extern "C" int g2048_play_host(int policy, uint64_t seed, uint32_t* h_key_io, int64_t batch_global, int64_t env_lo,
-                               int64_t n, int rng_mode, uint64_t* h_final_boards, uint32_t* h_lengths,
-                               uint32_t* h_scores, uint64_t* h_stats) {
+static int play_host_impl(int policy, uint64_t seed, uint32_t* h_key_io, int64_t batch_global, int64_t env_lo,
+                          int64_t n, int rng_mode, uint64_t* h_final_boards, uint32_t* h_lengths,
+                          uint32_t* h_scores, G2048EpisodeResult* h_results, uint64_t* h_stats) {
     G2048_REQUIRE(policy == G2048_POLICY_RANDOM || policy == G2048_POLICY_DRUL, "play_host: policy");
     G2048_REQUIRE(valid_mode(rng_mode) && valid_batch(batch_global, env_lo, n), "play_host: batch");
     uint32_t key[2] = {(uint32_t)(seed >> 32), (uint32_t)(seed & 0xFFFFFFFFull)};
@@ -512,7 +512,8 @@ extern "C" int g2048_play_host(int policy, uint64_t seed, uint32_t* h_key_io, in
         const size_t off_boards = off_subs + align256((size_t)n_subs * 8);
         const size_t off_len = off_boards + align256(h_final_boards ? (size_t)n * 8 : 0);
         const size_t off_score = off_len + align256(h_lengths ? (size_t)n * 4 : 0);
-        const size_t total = off_score + align256(h_scores ? (size_t)n * 4 : 0);
+        const size_t off_res = off_score + align256(h_scores ? (size_t)n * 4 : 0);
+        const size_t total = off_res + align256(h_results ? (size_t)n * sizeof(G2048EpisodeResult) : 0);
         if (total > ws.bytes) {
             if (ws.buf) cudaFree(ws.buf);
             ws.buf = nullptr;
@@ -527,12 +528,14 @@ extern "C" int g2048_play_host(int policy, uint64_t seed, uint32_t* h_key_io, in
         uint64_t* d_boards = h_final_boards ? (uint64_t*)(ws.buf + off_boards) : nullptr;
         uint32_t* d_len = h_lengths ? (uint32_t*)(ws.buf + off_len) : nullptr;
         uint32_t* d_score = h_scores ? (uint32_t*)(ws.buf + off_score) : nullptr;
+        G2048EpisodeResult* d_res = h_results ? (G2048EpisodeResult*)(ws.buf + off_res) : nullptr;
         // A result array in pinned (page-locked, mapped) host memory is written by the kernel itself: an episode's
         // 16 bytes of results leave over PCIe when the episode ends, overlapped with the rest of the batch, instead
         // of 32 MiB of copies after the kernel (G2048_PLAY_HOST_ZEROCOPY=0 restores the copies).
-        bool zc_boards = false, zc_len = false, zc_score = false;
+        bool zc_boards = false, zc_len = false, zc_score = false, zc_res = false;
         if (zero_copy) {
             void* m = nullptr;
+            if (d_res && (m = mapped_device_pointer(h_results)) && ((uintptr_t)m & 15u) == 0) { d_res = (G2048EpisodeResult*)m; zc_res = true; }
             if (d_boards && (m = mapped_device_pointer(h_final_boards))) { d_boards = (uint64_t*)m; zc_boards = true; }
             if (d_len && (m = mapped_device_pointer(h_lengths))) { d_len = (uint32_t*)m; zc_len = true; }
             if (d_score && (m = mapped_device_pointer(h_scores))) { d_score = (uint32_t*)m; zc_score = true; }
@@ -541,14 +544,18 @@ extern "C" int g2048_play_host(int policy, uint64_t seed, uint32_t* h_key_io, in
         TRY(cudaMemsetAsync(d_work, 0, 768, st), "play_host: memset");  // work + stats
         rc = g2048_chain_advance(d_key, rng_mode, n_subs, d_subs, st);
         if (rc) return rc;
-        rc = g2048_play(policy, d_subs, n_subs, batch_global, env_lo, n, rng_mode, d_work, d_boards, d_len, d_score,
-                        d_stats, st);
+        if (h_results)  // one 16-byte record per env: a third of the stores (and of the PCIe packets when they go to the host)
+            rc = g2048_play_packed(policy, d_subs, n_subs, batch_global, env_lo, n, rng_mode, d_work, d_res, d_stats, st);
+        else
+            rc = g2048_play(policy, d_subs, n_subs, batch_global, env_lo, n, rng_mode, d_work, d_boards, d_len, d_score,
+                            d_stats, st);
         if (rc) return rc;
         // results are copied optimistically; a batch that outlived its keys is replayed below
         TRY(cudaMemcpyAsync(stats, d_stats, sizeof(stats), cudaMemcpyDeviceToHost, st), "play_host: d2h stats");
         if (d_boards && !zc_boards && n && (rc = ws.copier.d2h(h_final_boards, d_boards, n * sizeof(uint64_t), st))) return rc;
         if (d_len && !zc_len && n && (rc = ws.copier.d2h(h_lengths, d_len, n * sizeof(uint32_t), st))) return rc;
         if (d_score && !zc_score && n && (rc = ws.copier.d2h(h_scores, d_score, n * sizeof(uint32_t), st))) return rc;
+        if (d_res && !zc_res && n && (rc = ws.copier.d2h(h_results, d_res, n * sizeof(G2048EpisodeResult), st))) return rc;
         TRY(cudaStreamSynchronize(st), "play_host: sync");
         if (stats[3] == 0 || max_steps >= (1 << 20)) break;
         max_steps *= 4;  // some episode outlived the chain: replay with a longer one
@@ -567,6 +574,19 @@ extern "C" int g2048_play_host(int policy, uint64_t seed, uint32_t* h_key_io, in
     }
 #undef TRY
     return rc;
+}
+
+extern "C" int g2048_play_host(int policy, uint64_t seed, uint32_t* h_key_io, int64_t batch_global, int64_t env_lo,
+                               int64_t n, int rng_mode, uint64_t* h_final_boards, uint32_t* h_lengths,
+                               uint32_t* h_scores, uint64_t* h_stats) {
+    return play_host_impl(policy, seed, h_key_io, batch_global, env_lo, n, rng_mode, h_final_boards, h_lengths, h_scores,
+                          nullptr, h_stats);
+}
+
+extern "C" int g2048_play_host_packed(int policy, uint64_t seed, uint32_t* h_key_io, int64_t batch_global, int64_t env_lo,
+                                      int64_t n, int rng_mode, G2048EpisodeResult* h_results, uint64_t* h_stats) {
+    return play_host_impl(policy, seed, h_key_io, batch_global, env_lo, n, rng_mode, nullptr, nullptr, nullptr, h_results,
+                          h_stats);
 }
 
 static int launch_rollout_steps(int policy, uint64_t* d_boards, uint8_t* d_status, const uint32_t* d_subs,

@@ -29,7 +29,7 @@ template <int MODE, int POLICY>
 __global__ void __launch_bounds__(PLAY2_THREADS)
 play2_kernel(const uint2* __restrict__ subs, int64_t n_subs, uint32_t batch_global, uint32_t env_lo, uint32_t n,
              unsigned long long* __restrict__ work, u64* __restrict__ final_boards, uint32_t* __restrict__ lengths,
-             uint32_t* __restrict__ scores, unsigned long long* __restrict__ stats) {
+             uint32_t* __restrict__ scores, unsigned long long* __restrict__ stats, uint4* __restrict__ results) {
     __shared__ unsigned long long s_stats[G2048_PLAY_STATS_WORDS];
     for (int i = threadIdx.x; i < G2048_PLAY_STATS_WORDS; i += blockDim.x) s_stats[i] = 0ull;
     __syncthreads();
@@ -121,6 +121,7 @@ play2_kernel(const uint2* __restrict__ subs, int64_t n_subs, uint32_t batch_glob
             if (final_boards) final_boards[e] = board;
             if (lengths) lengths[e] = t;
             if (scores) scores[e] = score;
+            if (results) results[e] = make_uint4((uint32_t)board, (uint32_t)(board >> 32), t, score);  // G2048EpisodeResult
             const uint32_t me = max_exponent(board);
             const unsigned long long tile = 1ull << me;
             st_episodes += 1;
@@ -157,7 +158,7 @@ play2_kernel(const uint2* __restrict__ subs, int64_t n_subs, uint32_t batch_glob
 template <int MODE, int POLICY>
 static int launch_play2(const uint32_t* d_subs, int64_t n_subs, int64_t batch_global, int64_t env_lo, int64_t n,
                         uint64_t* d_work, uint64_t* d_final_boards, uint32_t* d_lengths, uint32_t* d_scores,
-                        uint64_t* d_stats, cudaStream_t st) {
+                        uint64_t* d_stats, cudaStream_t st, void* d_results) {
     int per_sm = 0;
     int rc = check_cuda(
         cudaOccupancyMaxActiveBlocksPerMultiprocessor(&per_sm, play2_kernel<MODE, POLICY>, PLAY2_THREADS, 0),
@@ -170,7 +171,8 @@ static int launch_play2(const uint32_t* d_subs, int64_t n_subs, int64_t batch_gl
     if (grid > needed) grid = needed;
     play2_kernel<MODE, POLICY><<<(unsigned)grid, PLAY2_THREADS, 0, st>>>(
         (const uint2*)d_subs, n_subs, (uint32_t)batch_global, (uint32_t)env_lo, (uint32_t)n,
-        (unsigned long long*)d_work, (u64*)d_final_boards, d_lengths, d_scores, (unsigned long long*)d_stats);
+        (unsigned long long*)d_work, (u64*)d_final_boards, d_lengths, d_scores, (unsigned long long*)d_stats,
+        (uint4*)d_results);
     return check_cuda(cudaGetLastError(), "play");
 }
 
@@ -182,6 +184,34 @@ using namespace g2048;
 // copying 192 KiB of tables into shared memory needs a long-running launch to amortise.
 constexpr int64_t PLAY_TABLES_MIN_ENVS = 32768;
 
+// the SWAR kernel with every output form (d_results: one 16-byte G2048EpisodeResult per env, may be NULL)
+static int play_swar_impl(int policy, const uint32_t* d_subs, int64_t n_subs, int64_t batch_global, int64_t env_lo, int64_t n,
+                          int rng_mode, uint64_t* d_work, uint64_t* d_final_boards, uint32_t* d_lengths, uint32_t* d_scores,
+                          uint64_t* d_stats, void* d_results, void* stream) {
+    G2048_REQUIRE(policy == G2048_POLICY_RANDOM || policy == G2048_POLICY_DRUL, "play: policy");
+    G2048_REQUIRE(rng_mode == G2048_RNG_ORIGINAL || rng_mode == G2048_RNG_PARTITIONABLE, "play: rng_mode");
+    G2048_REQUIRE(batch_global > 0 && batch_global <= 0x7FFFFFFFll && env_lo >= 0 && n >= 0 && env_lo + n <= batch_global,
+                  "play: batch");
+    G2048_REQUIRE(n_subs >= 3 && d_subs && d_work && d_stats, "play: pointers");
+    G2048_REQUIRE(((uintptr_t)d_results & 15u) == 0, "play: results must be 16-byte aligned");
+    if (n == 0) return G2048_OK;
+    cudaStream_t st = (cudaStream_t)stream;
+#define ARGS d_subs, n_subs, batch_global, env_lo, n, d_work, d_final_boards, d_lengths, d_scores, d_stats, st, d_results
+    if (policy == G2048_POLICY_RANDOM) {
+        if (rng_mode == G2048_RNG_PARTITIONABLE) return launch_play2<G2048_RNG_PARTITIONABLE, G2048_POLICY_RANDOM>(ARGS);
+        return launch_play2<G2048_RNG_ORIGINAL, G2048_POLICY_RANDOM>(ARGS);
+    }
+    if (rng_mode == G2048_RNG_PARTITIONABLE) return launch_play2<G2048_RNG_PARTITIONABLE, G2048_POLICY_DRUL>(ARGS);
+    return launch_play2<G2048_RNG_ORIGINAL, G2048_POLICY_DRUL>(ARGS);
+#undef ARGS
+}
+
+namespace g2048 {
+int play_tables_impl(int policy, const uint32_t* d_subs, int64_t n_subs, int64_t batch_global, int64_t env_lo, int64_t n,
+                     int rng_mode, uint64_t* d_work, uint64_t* d_final_boards, uint32_t* d_lengths, uint32_t* d_scores,
+                     uint64_t* d_stats, void* d_results, void* stream);  // g2048_play3.cu
+}
+
 extern "C" int g2048_play(int policy, const uint32_t* d_subs, int64_t n_subs, int64_t batch_global, int64_t env_lo,
                           int64_t n, int rng_mode, uint64_t* d_work, uint64_t* d_final_boards, uint32_t* d_lengths,
                           uint32_t* d_scores, uint64_t* d_stats, void* stream) {
@@ -192,23 +222,22 @@ extern "C" int g2048_play(int policy, const uint32_t* d_subs, int64_t n_subs, in
                            d_lengths, d_scores, d_stats, stream);
 }
 
+// Same run, per-env results as ONE 16-byte record per env (G2048EpisodeResult) instead of three arrays: one store
+// per finished episode -- the form g2048_play_host uses when the kernel writes straight into pinned host memory.
+extern "C" int g2048_play_packed(int policy, const uint32_t* d_subs, int64_t n_subs, int64_t batch_global, int64_t env_lo,
+                                 int64_t n, int rng_mode, uint64_t* d_work, G2048EpisodeResult* d_results, uint64_t* d_stats,
+                                 void* stream) {
+    if (n >= PLAY_TABLES_MIN_ENVS)
+        return g2048::play_tables_impl(policy, d_subs, n_subs, batch_global, env_lo, n, rng_mode, d_work, nullptr, nullptr,
+                                       nullptr, d_stats, d_results, stream);
+    return play_swar_impl(policy, d_subs, n_subs, batch_global, env_lo, n, rng_mode, d_work, nullptr, nullptr, nullptr,
+                          d_stats, d_results, stream);
+}
+
 // SWAR kernel entry (no tables, any batch size): same arguments and results as g2048_play.
 extern "C" int g2048_play_swar(int policy, const uint32_t* d_subs, int64_t n_subs, int64_t batch_global,
                                int64_t env_lo, int64_t n, int rng_mode, uint64_t* d_work, uint64_t* d_final_boards,
                                uint32_t* d_lengths, uint32_t* d_scores, uint64_t* d_stats, void* stream) {
-    G2048_REQUIRE(policy == G2048_POLICY_RANDOM || policy == G2048_POLICY_DRUL, "play: policy");
-    G2048_REQUIRE(rng_mode == G2048_RNG_ORIGINAL || rng_mode == G2048_RNG_PARTITIONABLE, "play: rng_mode");
-    G2048_REQUIRE(batch_global > 0 && batch_global <= 0x7FFFFFFFll && env_lo >= 0 && n >= 0 && env_lo + n <= batch_global,
-                  "play: batch");
-    G2048_REQUIRE(n_subs >= 3 && d_subs && d_work && d_stats, "play: pointers");
-    if (n == 0) return G2048_OK;
-    cudaStream_t st = (cudaStream_t)stream;
-#define ARGS d_subs, n_subs, batch_global, env_lo, n, d_work, d_final_boards, d_lengths, d_scores, d_stats, st
-    if (policy == G2048_POLICY_RANDOM) {
-        if (rng_mode == G2048_RNG_PARTITIONABLE) return launch_play2<G2048_RNG_PARTITIONABLE, G2048_POLICY_RANDOM>(ARGS);
-        return launch_play2<G2048_RNG_ORIGINAL, G2048_POLICY_RANDOM>(ARGS);
-    }
-    if (rng_mode == G2048_RNG_PARTITIONABLE) return launch_play2<G2048_RNG_PARTITIONABLE, G2048_POLICY_DRUL>(ARGS);
-    return launch_play2<G2048_RNG_ORIGINAL, G2048_POLICY_DRUL>(ARGS);
-#undef ARGS
+    return play_swar_impl(policy, d_subs, n_subs, batch_global, env_lo, n, rng_mode, d_work, d_final_boards, d_lengths,
+                          d_scores, d_stats, nullptr, stream);
 }

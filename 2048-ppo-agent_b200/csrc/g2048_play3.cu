@@ -72,7 +72,7 @@ template <int MODE, int POLICY>
 __global__ void __launch_bounds__(PLAY3_THREADS, 1)
 play3_kernel(const uint2* __restrict__ subs, int64_t n_subs, uint32_t batch_global, uint32_t env_lo, uint32_t n,
              unsigned long long* __restrict__ work, u64* __restrict__ final_boards, uint32_t* __restrict__ lengths,
-             uint32_t* __restrict__ scores, unsigned long long* __restrict__ stats) {
+             uint32_t* __restrict__ scores, unsigned long long* __restrict__ stats, uint4* __restrict__ results) {
     extern __shared__ __align__(16) uint8_t smem_raw[];
     const uint16_t* s_left = reinterpret_cast<const uint16_t*>(smem_raw);
     const uint8_t* s_flags = smem_raw + 65536 * 2;
@@ -116,6 +116,7 @@ play3_kernel(const uint2* __restrict__ subs, int64_t n_subs, uint32_t batch_glob
             if (final_boards) final_boards[pk_e] = pk_board;
             if (lengths) lengths[pk_e] = pk_t;
             if (scores) scores[pk_e] = score;
+            if (results) results[pk_e] = make_uint4((uint32_t)pk_board, (uint32_t)(pk_board >> 32), pk_t, score);  // G2048EpisodeResult
             const uint32_t me = max_exponent(pk_board);
             const unsigned long long tile = 1ull << me;
             st_episodes += 1;
@@ -296,7 +297,7 @@ __global__ void row_table_lookup_kernel(const uint16_t* __restrict__ rows, int64
 template <int MODE, int POLICY>
 static int launch_play3(const uint32_t* d_subs, int64_t n_subs, int64_t batch_global, int64_t env_lo, int64_t n,
                         uint64_t* d_work, uint64_t* d_final_boards, uint32_t* d_lengths, uint32_t* d_scores,
-                        uint64_t* d_stats, cudaStream_t st) {
+                        uint64_t* d_stats, cudaStream_t st, void* d_results) {
     int rc = ensure_row_tables(st);
     if (rc) return rc;
     static bool configured_on[64] = {false};
@@ -315,8 +316,31 @@ static int launch_play3(const uint32_t* d_subs, int64_t n_subs, int64_t batch_gl
     if (grid > needed) grid = needed;
     play3_kernel<MODE, POLICY><<<(unsigned)grid, PLAY3_THREADS, PLAY3_SMEM_BYTES, st>>>(
         (const uint2*)d_subs, n_subs, (uint32_t)batch_global, (uint32_t)env_lo, (uint32_t)n,
-        (unsigned long long*)d_work, (u64*)d_final_boards, d_lengths, d_scores, (unsigned long long*)d_stats);
+        (unsigned long long*)d_work, (u64*)d_final_boards, d_lengths, d_scores, (unsigned long long*)d_stats,
+        (uint4*)d_results);
     return check_cuda(cudaGetLastError(), "play");
+}
+
+// the table kernel with every output form (d_results: one 16-byte G2048EpisodeResult per env, may be NULL)
+int play_tables_impl(int policy, const uint32_t* d_subs, int64_t n_subs, int64_t batch_global, int64_t env_lo, int64_t n,
+                     int rng_mode, uint64_t* d_work, uint64_t* d_final_boards, uint32_t* d_lengths, uint32_t* d_scores,
+                     uint64_t* d_stats, void* d_results, void* stream) {
+    G2048_REQUIRE(policy == G2048_POLICY_RANDOM || policy == G2048_POLICY_DRUL, "play: policy");
+    G2048_REQUIRE(rng_mode == G2048_RNG_ORIGINAL || rng_mode == G2048_RNG_PARTITIONABLE, "play: rng_mode");
+    G2048_REQUIRE(batch_global > 0 && batch_global <= 0x7FFFFFFFll && env_lo >= 0 && n >= 0 && env_lo + n <= batch_global,
+                  "play: batch");
+    G2048_REQUIRE(n_subs >= 3 && d_subs && d_work && d_stats, "play: pointers");
+    G2048_REQUIRE(((uintptr_t)d_results & 15u) == 0, "play: results must be 16-byte aligned");
+    if (n == 0) return G2048_OK;
+    cudaStream_t st = (cudaStream_t)stream;
+#define ARGS d_subs, n_subs, batch_global, env_lo, n, d_work, d_final_boards, d_lengths, d_scores, d_stats, st, d_results
+    if (policy == G2048_POLICY_RANDOM) {
+        if (rng_mode == G2048_RNG_PARTITIONABLE) return launch_play3<G2048_RNG_PARTITIONABLE, G2048_POLICY_RANDOM>(ARGS);
+        return launch_play3<G2048_RNG_ORIGINAL, G2048_POLICY_RANDOM>(ARGS);
+    }
+    if (rng_mode == G2048_RNG_PARTITIONABLE) return launch_play3<G2048_RNG_PARTITIONABLE, G2048_POLICY_DRUL>(ARGS);
+    return launch_play3<G2048_RNG_ORIGINAL, G2048_POLICY_DRUL>(ARGS);
+#undef ARGS
 }
 
 }  // namespace g2048
@@ -340,19 +364,6 @@ extern "C" int g2048_row_table_lookup(const uint16_t* d_rows, int64_t n, uint16_
 extern "C" int g2048_play_tables(int policy, const uint32_t* d_subs, int64_t n_subs, int64_t batch_global,
                                  int64_t env_lo, int64_t n, int rng_mode, uint64_t* d_work, uint64_t* d_final_boards,
                                  uint32_t* d_lengths, uint32_t* d_scores, uint64_t* d_stats, void* stream) {
-    G2048_REQUIRE(policy == G2048_POLICY_RANDOM || policy == G2048_POLICY_DRUL, "play: policy");
-    G2048_REQUIRE(rng_mode == G2048_RNG_ORIGINAL || rng_mode == G2048_RNG_PARTITIONABLE, "play: rng_mode");
-    G2048_REQUIRE(batch_global > 0 && batch_global <= 0x7FFFFFFFll && env_lo >= 0 && n >= 0 && env_lo + n <= batch_global,
-                  "play: batch");
-    G2048_REQUIRE(n_subs >= 3 && d_subs && d_work && d_stats, "play: pointers");
-    if (n == 0) return G2048_OK;
-    cudaStream_t st = (cudaStream_t)stream;
-#define ARGS d_subs, n_subs, batch_global, env_lo, n, d_work, d_final_boards, d_lengths, d_scores, d_stats, st
-    if (policy == G2048_POLICY_RANDOM) {
-        if (rng_mode == G2048_RNG_PARTITIONABLE) return launch_play3<G2048_RNG_PARTITIONABLE, G2048_POLICY_RANDOM>(ARGS);
-        return launch_play3<G2048_RNG_ORIGINAL, G2048_POLICY_RANDOM>(ARGS);
-    }
-    if (rng_mode == G2048_RNG_PARTITIONABLE) return launch_play3<G2048_RNG_PARTITIONABLE, G2048_POLICY_DRUL>(ARGS);
-    return launch_play3<G2048_RNG_ORIGINAL, G2048_POLICY_DRUL>(ARGS);
-#undef ARGS
+    return play_tables_impl(policy, d_subs, n_subs, batch_global, env_lo, n, rng_mode, d_work, d_final_boards, d_lengths,
+                            d_scores, d_stats, nullptr, stream);
 }

@@ -60,6 +60,8 @@ _SIGNATURES = {
     "g2048_row_table_lookup": (_INT, [_P, _I64, _P, _P, _P]),
     "g2048_play_v1": (_INT, [_INT, _P, _I64, _I64, _I64, _I64, _INT, _P, _P, _P, _P, _P, _P]),
     "g2048_play_host": (_INT, [_INT, _U64, _P, _I64, _I64, _I64, _INT, _P, _P, _P, _P]),
+    "g2048_play_host_packed": (_INT, [_INT, _U64, _P, _I64, _I64, _I64, _INT, _P, _P]),
+    "g2048_play_packed": (_INT, [_INT, _P, _I64, _I64, _I64, _I64, _INT, _P, _P, _P, _P]),
     "g2048_rollout_steps": (_INT, [_INT, _P, _P, _P, _I64, _I64, _I64, _I64, _I64, _INT, _P, _P, _P, _P, _P, _P]),
     "g2048_rollout_steps_live": (_INT, [_INT, _P, _P, _P, _I64, _I64, _I64, _I64, _I64, _INT, _P, _I64, _P, _P, _P, _P, _P, _P]),
     "g2048_policy_step": (_INT, [_P, _P, _P, _P, _INT, _INT, _INT, _P, _P, _I64, _I64, _I64, _INT, _P, _P, _P, _P, _P, _P, _P]),

@@ -194,23 +194,44 @@ def play_stats_dict(stats: torch.Tensor) -> dict:
     return out
 
 
+EPISODE_RESULT = np.dtype([("board", "<u8"), ("length", "<u4"), ("score", "<u4")])  # G2048EpisodeResult (include/g2048.h)
+
+
+def play_packed(policy: int, subs: torch.Tensor, batch_global: int, env_lo: int, n: int, rng_mode: int,
+                stats: torch.Tensor | None = None):
+    """g2048_play with one 16-byte record per env: returns dict(results (n, 2) int64 device tensor -- word 0 the final
+    bitboard, word 1 = length | score << 32 --, stats)."""
+    dev = subs.device
+    work = torch.zeros(2, dtype=torch.int64, device=dev)
+    if stats is None:
+        stats = torch.zeros(N.PLAY_STATS_WORDS, dtype=torch.int64, device=dev)
+    results = torch.empty((n, 2), dtype=torch.int64, device=dev)
+    call("g2048_play_packed", policy, ptr(_i32(subs)), subs.shape[0], batch_global, env_lo, n, rng_mode, ptr(work),
+         ptr(results), ptr(stats), stream_ptr())
+    return dict(results=results, stats=stats)
+
+
 def play_host(policy: int, seed: int, batch_global: int, rng_mode: int, env_lo: int = 0, n: int | None = None,
               key: np.ndarray | None = None, per_env: bool = True, pinned: bool = False):
     """The host-buffer C entry point (numpy in / numpy out; copies and syncs inside the call).
-    pinned=True: the result arrays are page-locked host memory, which the play kernel writes directly (no copies
-    after the kernel); they are views of torch pinned tensors and stay valid as long as they are referenced."""
+    pinned=True: the per-env results are one array of 16-byte records (EPISODE_RESULT) in page-locked host memory,
+    which the play kernel writes directly, one PCIe write per finished episode and no copies after the kernel
+    (g2048_play_host_packed); final_boards / lengths / scores are strided views of it and stay valid as long as they
+    are referenced."""
     N.require_cuda()
     n = batch_global - env_lo if n is None else n
-    if pinned:
-        mk = lambda dt, view: torch.empty(n, dtype=dt, pin_memory=True).numpy().view(view)  # noqa: E731
-    else:
-        mk = lambda dt, view: np.empty(n, view)  # noqa: E731
-    boards = mk(torch.int64, np.uint64) if per_env else None
-    lengths = mk(torch.int32, np.uint32) if per_env else None
-    scores = mk(torch.int32, np.uint32) if per_env else None
     stats = np.zeros(N.PLAY_STATS_WORDS, np.uint64)
     key_io = None if key is None else np.ascontiguousarray(key, np.uint32)
     as_p = lambda a: None if a is None else a.ctypes.data  # noqa: E731
+    if pinned and per_env:
+        records = torch.empty((n, 2), dtype=torch.int64, pin_memory=True).numpy().view(EPISODE_RESULT).reshape(n)
+        call("g2048_play_host_packed", policy, int(seed) & 0xFFFFFFFFFFFFFFFF, as_p(key_io), batch_global, env_lo, n, rng_mode,
+             as_p(records), as_p(stats))
+        return dict(final_boards=records["board"], lengths=records["length"], scores=records["score"], stats=stats,
+                    key=key_io, records=records)
+    boards = np.empty(n, np.uint64) if per_env else None
+    lengths = np.empty(n, np.uint32) if per_env else None
+    scores = np.empty(n, np.uint32) if per_env else None
     call("g2048_play_host", policy, int(seed) & 0xFFFFFFFFFFFFFFFF, as_p(key_io), batch_global, env_lo, n, rng_mode,
          as_p(boards), as_p(lengths), as_p(scores), as_p(stats))
     return dict(final_boards=boards, lengths=lengths, scores=scores, stats=stats, key=key_io)

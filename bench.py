@@ -358,17 +358,16 @@ def main():
 
     # ---- end to end through the host-buffer C entry point ------------------------------------------
     e2e_times, e2e_steps = [], 0
-    # host result buffers in pinned memory (what a caller that cares about transfer time would pass)
-    pin = lambda count, dt: torch.empty(count, dtype=dt, pin_memory=True).numpy()  # noqa: E731
-    h_boards = pin(n, torch.int64).view(np.uint64)
-    h_len = pin(n, torch.int32).view(np.uint32)
-    h_score = pin(n, torch.int32).view(np.uint32)
+    # host result buffer in pinned memory (what a caller that cares about transfer time passes): one 16-byte record per
+    # env (G2048EpisodeResult: board, length, score), written by the play kernel itself as episodes end
+    records = torch.empty((n, 2), dtype=torch.int64, pin_memory=True).numpy().view(E.EPISODE_RESULT).reshape(n)
+    h_len, h_score = records["length"], records["score"]
     h_stats = np.zeros(N.PLAY_STATS_WORDS, np.uint64)
     for i in range(2 + min(args.steps, 5)):
         barrier()
         t0 = time.perf_counter()
-        N.call("g2048_play_host", policy_id, SEED + i, None, batch_global, lo, n, mode, h_boards.ctypes.data,
-               h_len.ctypes.data, h_score.ctypes.data, h_stats.ctypes.data)
+        N.call("g2048_play_host_packed", policy_id, SEED + i, None, batch_global, lo, n, mode, records.ctypes.data,
+               h_stats.ctypes.data)
         dt = time.perf_counter() - t0
         if i >= 2:
             e2e_times.append(dt)
@@ -381,10 +380,11 @@ def main():
     e2e = {
         "value": float(se.item()) / float(te.item()), "unit": "env-steps/s",
         "h2d_bytes_per_step": 8, "d2h_bytes_per_step": int(16 * n + 8 * N.PLAY_STATS_WORDS),
-        "api": "g2048_play_host (C ABI, host buffers): key H2D + chain kernel + play kernel + device-to-host transfer of final "
-               "boards, lengths, scores and the statistics block + synchronise, per call; the result arrays are pinned host "
-               "memory, which the kernel writes directly over PCIe as episodes end (pageable arrays are copied after the "
-               "kernel through staging buffers: e2e.pageable_results); device workspace cached by the library",
+        "api": "g2048_play_host_packed (C ABI, host buffers): key H2D + chain kernel + play kernel + device-to-host transfer of "
+               "every env's final board, length and score (one 16-byte record per env) and the statistics block + synchronise, "
+               "per call; the record array is pinned host memory, which the kernel writes directly over PCIe as episodes end "
+               "(g2048_play_host with three pageable numpy arrays, copied after the kernel through staging buffers: "
+               "e2e.pageable_results); device workspace cached by the library",
         # the host arrays really hold the batch: their lengths add up to the statistics block's env-step count
         "results_checked": bool(int(h_len.sum(dtype=np.uint64)) == int(h_stats[1]) and int(h_score.sum(dtype=np.uint64)) == int(h_stats[2])),
     }

@@ -131,6 +131,19 @@ int g2048_play_swar(int policy, const uint32_t* d_subs, int64_t n_subs, int64_t 
                     int64_t n, int rng_mode, uint64_t* d_work, uint64_t* d_final_boards, uint32_t* d_lengths,
                     uint32_t* d_scores, uint64_t* d_stats, void* stream);
 
+/* Per-env results of a play-to-termination run as one 16-byte record (little-endian; a numpy structured dtype
+ * {"board": "<u8", "length": "<u4", "score": "<u4"} views an array of them). */
+typedef struct G2048EpisodeResult {
+    uint64_t board;  /* final bitboard */
+    uint32_t length; /* env-steps played */
+    uint32_t score;  /* sum of the merge rewards */
+} G2048EpisodeResult;
+
+/* g2048_play with the per-env results as ONE record per env instead of three arrays (d_results: n records, 16-byte
+ * aligned, may be NULL): a finished episode is a single 16-byte store.  Same dispatch, statistics and key usage. */
+int g2048_play_packed(int policy, const uint32_t* d_subs, int64_t n_subs, int64_t batch_global, int64_t env_lo, int64_t n,
+                      int rng_mode, uint64_t* d_work, G2048EpisodeResult* d_results, uint64_t* d_stats, void* stream);
+
 /* Test hook for the shared-memory tables of g2048_play_tables: for each 16-bit row (four nibbles, nibble 0 =
  * column 0) the row slid/merged toward column 0 and the flags (bit 0: moves left, bit 2: moves right). */
 int g2048_row_table_lookup(const uint16_t* d_rows, int64_t n, uint16_t* d_left, uint8_t* d_flags, void* stream);
@@ -149,6 +162,12 @@ int g2048_play_v1(int policy, const uint32_t* d_subs, int64_t n_subs, int64_t ba
 int g2048_play_host(int policy, uint64_t seed, uint32_t* h_key_io, int64_t batch_global, int64_t env_lo, int64_t n,
                     int rng_mode, uint64_t* h_final_boards, uint32_t* h_lengths, uint32_t* h_scores,
                     uint64_t* h_stats);
+
+/* g2048_play_host with the per-env results as one G2048EpisodeResult per env (h_results: n records, may be NULL).
+ * In pinned host memory the records are written by the kernel as episodes end -- one 16-byte PCIe write per episode
+ * instead of three small ones, which is what keeps eight GPUs behind shared PCIe uplinks from slowing each other. */
+int g2048_play_host_packed(int policy, uint64_t seed, uint32_t* h_key_io, int64_t batch_global, int64_t env_lo, int64_t n,
+                           int rng_mode, G2048EpisodeResult* h_results, uint64_t* h_stats);
 
 /* Lock-step recorded rollout: `n_steps` loop steps of src/runs/batch_runner.py:117-136 for
  * act_randomly / act_drul in one kernel, state kept in registers in between.

@@ -125,6 +125,8 @@ def run_all(E, g2048, T=torch, dev="cuda"):
     sink = T.empty(4 * 64, dtype=torch.int32, device=dev)
     E.int_peak_probe(4, 64, 10, sink)
     E.play_host(0, 3, 500, 1)
+    E.play_host(1, 3, 500, 0, pinned=True)
+    E.play_packed(0, E.chain_advance(E.words_tensor([0, 5], dev), 1, 1 + 2 * 700), 777, 100, 300, 1)
     E.gae_host(np.random.rand(7000).astype(np.float32), np.random.rand(7000).astype(np.float32),
                (np.random.rand(7000) < 0.01).astype(np.uint8), 0.99, 0.95, True)
     runner = g2048.BatchRunner(1, g2048.act_randomly)

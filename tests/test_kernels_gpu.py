@@ -358,6 +358,13 @@ def test_play_host_pinned_results_are_written_by_the_kernel(E):
         np.testing.assert_array_equal(a["scores"], ref["scores"])
         np.testing.assert_array_equal(a["stats"], b["stats"])
         assert int(a["lengths"].sum()) == int(a["stats"][1])
+        # the packed device entry and the packed host entry with a pageable record array (staged copy)
+        subs = E.chain_advance(E.words_tensor(list(E.key_words(seed)), "cuda"), mode, 1 + 2 * 4096)
+        rec = E.play_packed(policy, subs, n, 0, n, mode)["results"].cpu().numpy().view(E.EPISODE_RESULT).reshape(n)
+        np.testing.assert_array_equal(rec, a["records"])
+        pageable = np.zeros(n, E.EPISODE_RESULT)
+        E.N.call("g2048_play_host_packed", policy, seed, None, n, 0, n, mode, pageable.ctypes.data, None)
+        np.testing.assert_array_equal(pageable, a["records"])
 
 
 @pytest.mark.parametrize("entry", PLAY_ENTRIES)
