@@ -301,28 +301,11 @@ row_moments_kernel(const double* __restrict__ x, int64_t n, double* __restrict__
 // round)); images >= n go through the network again (cycle walking, < 4 passes expected), which restricts the
 // bijection of [0, 4^h) to one of [0, n).  Integer work, 8 B written per index.
 // ------------------------------------------------------------------------------------------------
-__device__ __forceinline__ uint64_t feistel_pass(Key k, uint64_t x, int h, uint32_t mask) {
-    uint32_t left = (uint32_t)(x >> h), right = (uint32_t)x & mask;
-#pragma unroll
-    for (uint32_t r = 0; r < 4; ++r) {
-        const uint32_t f = threefry2x32(k, right, r).a & mask;
-        const uint32_t nl = right;
-        right = left ^ f;
-        left = nl;
-    }
-    return ((uint64_t)left << h) | (uint64_t)right;
-}
-
 __global__ void __launch_bounds__(256)
 random_subset_kernel(Key k, uint64_t n, int h, int64_t first, int64_t m, int64_t* __restrict__ out) {
     const int64_t i = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
     if (i >= m) return;
-    const uint32_t mask = (h >= 32) ? 0xFFFFFFFFu : ((1u << h) - 1u);
-    uint64_t x = (uint64_t)(first + i);
-    do {
-        x = feistel_pass(k, x, h, mask);
-    } while (x >= n);
-    out[i] = (int64_t)x;
+    out[i] = (int64_t)feistel_position(k, (uint64_t)(first + i), h, n);
 }
 
 // ------------------------------------------------------------------------------------------------
@@ -498,8 +481,7 @@ extern "C" int g2048_random_subset(uint32_t key0, uint32_t key1, int64_t n, int6
     G2048_REQUIRE(n >= 0 && first >= 0 && m >= 0 && first + m <= n && n <= (1ll << 62), "random_subset: range");
     if (m == 0) return G2048_OK;
     G2048_REQUIRE(d_out, "random_subset: pointers");
-    int h = 1;
-    while (h < 31 && (1ull << (2 * h)) < (uint64_t)n) ++h;  // 4^h >= n
+    const int h = feistel_half_bits((uint64_t)n);  // 4^h >= n
     random_subset_kernel<<<blocks_for(m, 256), 256, 0, (cudaStream_t)stream>>>(Key{key0, key1}, (uint64_t)n, h, first, m,
                                                                               d_out);
     G2048_CHECK_LAUNCH("random_subset");

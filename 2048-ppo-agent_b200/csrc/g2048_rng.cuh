@@ -117,4 +117,33 @@ __device__ __forceinline__ float unit_float_tiny(uint32_t bits) {
     return fmaxf(tiny, __fadd_rn(__fmul_rn(f, 1.0f), tiny));
 }
 
+// ---- keyed pseudo-random bijection of [0, n) (g2048_random_subset, g2048_data.cu) ---------------------------------
+// Balanced Feistel network, 4 rounds, over 2h bits with 4^h >= n; round function = low h bits of the first word of
+// Threefry-2x32(key; (right half, round)); images >= n go through the network again (cycle walking).
+inline int feistel_half_bits(uint64_t n) {
+    int h = 1;
+    while (h < 31 && (1ull << (2 * h)) < n) ++h;
+    return h;
+}
+
+__device__ __forceinline__ uint64_t feistel_pass(Key k, uint64_t x, int h, uint32_t mask) {
+    uint32_t left = (uint32_t)(x >> h), right = (uint32_t)x & mask;
+#pragma unroll
+    for (uint32_t r = 0; r < 4; ++r) {
+        const uint32_t f = threefry2x32(k, right, r).a & mask;
+        const uint32_t nl = right;
+        right = left ^ f;
+        left = nl;
+    }
+    return ((uint64_t)left << h) | (uint64_t)right;
+}
+
+__device__ __forceinline__ uint64_t feistel_position(Key k, uint64_t x, int h, uint64_t n) {
+    const uint32_t mask = (h >= 32) ? 0xFFFFFFFFu : ((1u << h) - 1u);
+    do {
+        x = feistel_pass(k, x, h, mask);
+    } while (x >= n);
+    return x;
+}
+
 }  // namespace g2048

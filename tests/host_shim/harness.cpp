@@ -110,4 +110,9 @@ void shim_move(const uint64_t* boards, const int32_t* actions, int64_t n, uint64
         masks[i] = (uint8_t)(legal_mask(boards[i]) | (ovf ? 0x20 : 0));
     }
 }
+// the keyed bijection behind g2048_random_subset: positions P(first), ..., P(first + m - 1) of [0, n)
+void shim_random_subset(uint32_t k0, uint32_t k1, uint64_t n, uint64_t first, int64_t m, int64_t* out) {
+    const int h = feistel_half_bits(n);
+    for (int64_t i = 0; i < m; ++i) out[i] = (int64_t)feistel_position(Key{k0, k1}, first + (uint64_t)i, h, n);
+}
 }

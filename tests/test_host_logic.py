@@ -223,6 +223,17 @@ def test_kth_flag_cell_exhaustively(shim):
     np.testing.assert_array_equal(got, want)
 
 
+def test_device_random_subset_on_host_matches_oracle(shim):
+    """feistel_position (g2048_rng.cuh, what random_subset_kernel evaluates per index) against the oracle's restatement."""
+    for n, first, m in ((1, 0, 1), (5, 0, 5), (17, 3, 14), (4097, 0, 4097), (100003, 777, 5000), (31_000_000, 0, 20000),
+                        ((1 << 40) + 12345, 1 << 39, 3000)):
+        key = (0x9E3779B9, n & 0xFFFFFFFF)
+        got = np.zeros(m, np.int64)
+        shim.shim_random_subset(C.c_uint32(key[0]), C.c_uint32(key[1]), C.c_uint64(n), C.c_uint64(first), C.c_int64(m), _p(got))
+        np.testing.assert_array_equal(got, O.random_subset(key, n, first, m))
+        assert len(np.unique(got)) == m and got.min() >= 0 and got.max() < n
+
+
 def test_device_rng_on_host_matches_oracle(shim):
     out = np.zeros(2, np.uint32)
     shim.shim_threefry(C.c_uint32(0x13198A2E), C.c_uint32(0x03707344), C.c_uint32(0x243F6A88), C.c_uint32(0x85A308D3), _p(out))
