@@ -372,3 +372,45 @@ def test_reference_learner_modules_are_found_behind_the_drop_in(tmp_path):
     env = dict(__import__("os").environ, G2048_REFERENCE_ROOT=str(fake), PYTHONPATH=str(root / "2048-ppo-agent_b200"))
     res = subprocess.run([sys.executable, "-c", code], capture_output=True, text=True, env=env, timeout=300)
     assert res.returncode == 0 and res.stdout.strip() == "ok", res.stderr[-2000:]
+
+
+def test_batched_fetch_collates_like_the_default_collate():
+    """_LazySamples / _collate (what create_ppo_dataloader's DataLoader uses) against torch's default collation of the
+    per-sample dicts, on a stand-in dataset (PPODataset itself needs the GPU for its GAE)."""
+    import torch
+    from torch.utils.data import DataLoader, Dataset
+
+    from g2048.ppo.data_loader import _collate, _LazySamples
+
+    class Stub(Dataset):
+        def __init__(self):
+            g = torch.Generator().manual_seed(0)
+            self.fields = {"observations": torch.rand(100, 16, 31, generator=g), "actions": torch.rand(100, 4, generator=g),
+                           "terminations": torch.rand(100, generator=g) < 0.1, "returns": torch.rand(100, generator=g)}
+            self.active_indices = torch.randperm(100, generator=g)[:40]
+
+        def __len__(self):
+            return 40
+
+        def _item(self, pos):
+            return {k: v[pos] for k, v in self.fields.items()}
+
+        def __getitem__(self, i):
+            return self._item(self.active_indices[i])
+
+        def __getitems__(self, indices):
+            return _LazySamples(self, self.active_indices[torch.as_tensor(indices, dtype=torch.long)])
+
+    ds = Stub()
+    fast = DataLoader(ds, batch_size=16, shuffle=False, collate_fn=_collate)
+    slow = DataLoader(ds, batch_size=16, shuffle=False)  # default collate iterates the lazy samples one by one
+    n = 0
+    for a, b in zip(fast, slow):
+        assert a.keys() == b.keys()
+        for k in a:
+            assert a[k].dtype == b[k].dtype and torch.equal(a[k], b[k]), k
+        n += a["returns"].shape[0]
+    assert n == 40
+    lazy = ds.__getitems__([3, 1, 2])
+    assert len(lazy) == 3 and torch.equal(lazy[1]["returns"], ds[1]["returns"])
+    assert torch.equal(_collate([ds[0], ds[1]])["returns"], torch.stack([ds[0]["returns"], ds[1]["returns"]]))
