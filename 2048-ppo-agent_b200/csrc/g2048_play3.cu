@@ -68,11 +68,30 @@ __global__ void build_row_tables_kernel() {
     g_row_flags[row] = (uint8_t)((left != row ? 1u : 0u) | (right != row ? 4u : 0u));  // bits 0 and 2: see the legal mask below
 }
 
-template <int MODE, int POLICY>
+// Recording form (REC = true; src/runs/batch_runner.py:117-154 + src/ppo/rollout_buffer.py:164-187): the lane also
+// writes the trajectory of every env it plays.  A lane plays its envs one after the other, so its records are one
+// sequential stream: lane L owns slots [L * cap, (L + 1) * cap) of an arena and appends, per env-step, the pre-step
+// board (8 B) and a meta byte (action | pre-step legal mask << 2 | post-step done << 6 | "the spawn was a 4-tile" << 7),
+// and after an env's last step its final board (one extra slot).  env_slot[e] is the slot of env e's step 0, so an
+// episode is the contiguous slot range [env_slot[e], env_slot[e] + length[e]] -- what g2048_play_record_compact turns
+// into the env-major flat buffer RolloutBuffer keeps, deriving the per-step reward from consecutive boards
+// (reward_t = potential(board_{t+1}) - potential(board_t) - 4 * [4-tile spawned at t], see board_potential) so that
+// the play loop itself computes no reward.  ~12 instructions and two stores per env-step on top of play3_kernel.
+// A lane only takes a new env while a whole episode (max_steps + 1 slots) still fits into its region; a lane that
+// cannot retires, and envs nobody could take are reported through stats[0] < n (the caller retries with a larger arena).
+struct PlayRecordArena {
+    u64* boards;                   // arena slots: pre-step boards (+ final board of each episode)
+    uint8_t* meta;                 // arena slots: meta bytes
+    unsigned long long cap;        // slots per lane
+    unsigned long long* env_slot;  // (n) slot of step 0 of env i
+};
+
+template <int MODE, int POLICY, bool REC>
 __global__ void __launch_bounds__(PLAY3_THREADS, 1)
 play3_kernel(const uint2* __restrict__ subs, int64_t n_subs, uint32_t batch_global, uint32_t env_lo, uint32_t n,
              unsigned long long* __restrict__ work, u64* __restrict__ final_boards, uint32_t* __restrict__ lengths,
-             uint32_t* __restrict__ scores, unsigned long long* __restrict__ stats, uint4* __restrict__ results) {
+             uint32_t* __restrict__ scores, unsigned long long* __restrict__ stats, uint4* __restrict__ results,
+             const PlayRecordArena rec) {
     extern __shared__ __align__(16) uint8_t smem_raw[];
     const uint16_t* s_left = reinterpret_cast<const uint16_t*>(smem_raw);
     const uint8_t* s_flags = smem_raw + 65536 * 2;
@@ -99,6 +118,12 @@ play3_kernel(const uint2* __restrict__ subs, int64_t n_subs, uint32_t batch_glob
 
     uint32_t st_episodes = 0, st_cut = 0, st_ovf = 0, st_longest = 0;
     unsigned long long st_steps = 0, st_score = 0, st_tile = 0, st_tile2 = 0;
+    // recording: next free slot of this lane's arena region and the end of the region
+    unsigned long long slot = 0, slot_end = 0;
+    if (REC) {
+        slot = ((unsigned long long)blockIdx.x * PLAY3_THREADS + threadIdx.x) * rec.cap;
+        slot_end = slot + rec.cap;
+    }
 
     // Episode epilogue (score from the final board, result stores, statistics: ~150 instructions).  Lanes finish
     // one at a time -- a warp meets a finished episode on roughly every fourth step -- so running the epilogue on the
@@ -134,8 +159,11 @@ play3_kernel(const uint2* __restrict__ subs, int64_t n_subs, uint32_t batch_glob
 
     while (true) {
         // ---- hand the next envs of the queue to the lanes that have none --------------------------
-        const unsigned want = __ballot_sync(0xFFFFFFFFu, phase == PHASE_NONE);
-        if (want) {
+        const unsigned idle = __ballot_sync(0xFFFFFFFFu, phase == PHASE_NONE);
+        // a recording lane takes a new env only while a whole episode still fits into its arena region
+        const bool can_take = !REC || slot + (unsigned long long)max_steps + 1ull <= slot_end;
+        const unsigned want = REC ? __ballot_sync(0xFFFFFFFFu, phase == PHASE_NONE && can_take) : idle;
+        if (idle) {
             // park what the lanes that just finished still hold (all lanes are converged here)
             const unsigned fresh = __ballot_sync(0xFFFFFFFFu, fin_live);
             if (fresh) {
@@ -152,13 +180,13 @@ play3_kernel(const uint2* __restrict__ subs, int64_t n_subs, uint32_t batch_glob
                     fin_live = false;
                 }
             }
-            if (!exhausted) {
+            if (!exhausted && want) {
                 const int cnt = __popc(want);
                 unsigned long long base = 0;
                 if (lane == 0) base = atomicAdd(work, (unsigned long long)cnt);
                 base = __shfl_sync(0xFFFFFFFFu, base, 0);
                 if (base + (unsigned long long)cnt >= (unsigned long long)n) exhausted = true;
-                if (phase == PHASE_NONE) {
+                if (phase == PHASE_NONE && (!REC || can_take)) {
                     const unsigned long long mine = base + (unsigned long long)__popc(want & ((1u << lane) - 1u));
                     if (mine < (unsigned long long)n) {
                         e = (uint32_t)mine;
@@ -205,6 +233,8 @@ play3_kernel(const uint2* __restrict__ subs, int64_t n_subs, uint32_t batch_glob
         const uint32_t bits_val = bits_scalar<MODE>(k2);
 
         // ---- move: four table lookups on the board (Left/Right) or its transpose (Up/Down) -----------------
+        const u64 pre_board = board;   // REC: what the record of this step holds
+        const uint32_t pre_lm = lm;
         const bool vertical = (action & 1) != 0, rev = action >= 2;
         u64 src = vertical ? boardT : board;
         if (rev) src = mirror_rows(src);
@@ -243,10 +273,20 @@ play3_kernel(const uint2* __restrict__ subs, int64_t n_subs, uint32_t batch_glob
         const bool done = lm == 0u;
         const bool cut = !done && t >= max_steps;
         if ((t & 255u) == 0u) seen15 |= has_max_nibble(board);  // the final board is checked in the epilogue
+        if (REC) {  // the lane's own sequential stream: consecutive steps fill consecutive bytes of the same sectors
+            rec.boards[slot] = pre_board;
+            rec.meta[slot] = (uint8_t)((uint32_t)action | (pre_lm << 2) | (done ? 0x40u : 0u) | ((uint32_t)(val & 2ull) << 6));
+            ++slot;
+        }
         if (done || cut) {  // the final state stays in board / t / fours / e / seen15 until it is parked at the loop top
             fin_live = true;
             fin_cut = cut;
             phase = PHASE_NONE;
+            if (REC) {  // the episode's last board closes its slot range (the reward of the last step needs it)
+                rec.boards[slot] = board;
+                rec.env_slot[e] = slot - (unsigned long long)t;
+                ++slot;
+            }
         }
     }
     epilogue();  // whatever is still parked (a finished lane always passes the loop top, and is parked, before the loop ends)
@@ -294,30 +334,34 @@ __global__ void row_table_lookup_kernel(const uint16_t* __restrict__ rows, int64
     flags[i] = g_row_flags[rows[i]];
 }
 
-template <int MODE, int POLICY>
+// CTAs of a table-kernel launch over n envs (one per SM, persistent); the recording form sizes its arena by it
+static int64_t play3_grid(int64_t n, int sms) {
+    const int64_t needed = (n + PLAY3_THREADS - 1) / PLAY3_THREADS;
+    return needed < sms ? needed : sms;
+}
+
+template <int MODE, int POLICY, bool REC>
 static int launch_play3(const uint32_t* d_subs, int64_t n_subs, int64_t batch_global, int64_t env_lo, int64_t n,
                         uint64_t* d_work, uint64_t* d_final_boards, uint32_t* d_lengths, uint32_t* d_scores,
-                        uint64_t* d_stats, cudaStream_t st, void* d_results) {
+                        uint64_t* d_stats, cudaStream_t st, void* d_results, PlayRecordArena rec = PlayRecordArena{}) {
     int rc = ensure_row_tables(st);
     if (rc) return rc;
     static bool configured_on[64] = {false};
     bool* configured = device_once_flag(configured_on);
     if (!configured) return fail_arg("no CUDA device");
     if (!*configured) {
-        rc = check_cuda(cudaFuncSetAttribute(play3_kernel<MODE, POLICY>, cudaFuncAttributeMaxDynamicSharedMemorySize,
+        rc = check_cuda(cudaFuncSetAttribute(play3_kernel<MODE, POLICY, REC>, cudaFuncAttributeMaxDynamicSharedMemorySize,
                                              PLAY3_SMEM_BYTES), "play: shared memory attribute");
         if (rc) return rc;
         *configured = true;
     }
     const int sms = sm_count();
     if (sms <= 0) return fail_arg("play: no device");
-    int64_t grid = sms;  // one 1 024-thread CTA per SM, persistent
-    const int64_t needed = (n + PLAY3_THREADS - 1) / PLAY3_THREADS;
-    if (grid > needed) grid = needed;
-    play3_kernel<MODE, POLICY><<<(unsigned)grid, PLAY3_THREADS, PLAY3_SMEM_BYTES, st>>>(
+    const int64_t grid = play3_grid(n, sms);  // one CTA per SM, persistent
+    play3_kernel<MODE, POLICY, REC><<<(unsigned)grid, PLAY3_THREADS, PLAY3_SMEM_BYTES, st>>>(
         (const uint2*)d_subs, n_subs, (uint32_t)batch_global, (uint32_t)env_lo, (uint32_t)n,
         (unsigned long long*)d_work, (u64*)d_final_boards, d_lengths, d_scores, (unsigned long long*)d_stats,
-        (uint4*)d_results);
+        (uint4*)d_results, rec);
     return check_cuda(cudaGetLastError(), "play");
 }
 
@@ -335,12 +379,97 @@ int play_tables_impl(int policy, const uint32_t* d_subs, int64_t n_subs, int64_t
     cudaStream_t st = (cudaStream_t)stream;
 #define ARGS d_subs, n_subs, batch_global, env_lo, n, d_work, d_final_boards, d_lengths, d_scores, d_stats, st, d_results
     if (policy == G2048_POLICY_RANDOM) {
-        if (rng_mode == G2048_RNG_PARTITIONABLE) return launch_play3<G2048_RNG_PARTITIONABLE, G2048_POLICY_RANDOM>(ARGS);
-        return launch_play3<G2048_RNG_ORIGINAL, G2048_POLICY_RANDOM>(ARGS);
+        if (rng_mode == G2048_RNG_PARTITIONABLE) return launch_play3<G2048_RNG_PARTITIONABLE, G2048_POLICY_RANDOM, false>(ARGS);
+        return launch_play3<G2048_RNG_ORIGINAL, G2048_POLICY_RANDOM, false>(ARGS);
     }
-    if (rng_mode == G2048_RNG_PARTITIONABLE) return launch_play3<G2048_RNG_PARTITIONABLE, G2048_POLICY_DRUL>(ARGS);
-    return launch_play3<G2048_RNG_ORIGINAL, G2048_POLICY_DRUL>(ARGS);
+    if (rng_mode == G2048_RNG_PARTITIONABLE) return launch_play3<G2048_RNG_PARTITIONABLE, G2048_POLICY_DRUL, false>(ARGS);
+    return launch_play3<G2048_RNG_ORIGINAL, G2048_POLICY_DRUL, false>(ARGS);
 #undef ARGS
+}
+
+// ---- recording form: arena sizing, launch, compaction into the env-major flat buffer ---------------------------------
+
+// slots per lane: room for one whole episode (max_steps + 1) beyond the lane's expected share of the batch's records
+static int64_t play_record_lane_slots(int64_t n, int64_t max_steps, int64_t mean_steps, int sms) {
+    const int64_t lanes = play3_grid(n, sms) * PLAY3_THREADS;
+    const int64_t envs_per_lane = (n + lanes - 1) / lanes;
+    // share: mean episode (+1 slot for its final board) x envs per lane, +25 % and two mean episodes of slack for the
+    // imbalance between lanes (a lane that runs out retires; the others take its envs)
+    const int64_t share = (envs_per_lane * (mean_steps + 1) * 5) / 4 + 2 * (mean_steps + 1);
+    return share + max_steps + 1;
+}
+
+int play_record_impl(int policy, const uint32_t* d_subs, int64_t n_subs, int64_t batch_global, int64_t env_lo, int64_t n,
+                     int rng_mode, uint64_t* d_work, uint64_t* d_arena_boards, uint8_t* d_arena_meta, int64_t arena_slots,
+                     uint64_t* d_env_slot, uint64_t* d_final_boards, uint32_t* d_lengths, uint32_t* d_scores,
+                     uint64_t* d_stats, void* stream) {
+    G2048_REQUIRE(policy == G2048_POLICY_RANDOM || policy == G2048_POLICY_DRUL, "play_record: policy");
+    G2048_REQUIRE(rng_mode == G2048_RNG_ORIGINAL || rng_mode == G2048_RNG_PARTITIONABLE, "play_record: rng_mode");
+    G2048_REQUIRE(batch_global > 0 && batch_global <= 0x7FFFFFFFll && env_lo >= 0 && n >= 0 && env_lo + n <= batch_global,
+                  "play_record: batch");
+    G2048_REQUIRE(n_subs >= 3 && d_subs && d_work && d_stats, "play_record: pointers");
+    if (n == 0) return G2048_OK;
+    G2048_REQUIRE(d_arena_boards && d_arena_meta && d_env_slot && d_lengths, "play_record: record pointers");
+    const int sms = sm_count();
+    if (sms <= 0) return fail_arg("play_record: no device");
+    const int64_t lanes = play3_grid(n, sms) * PLAY3_THREADS;
+    const int64_t max_steps = (n_subs - 1) / 2;
+    PlayRecordArena rec;
+    rec.boards = (u64*)d_arena_boards;
+    rec.meta = d_arena_meta;
+    rec.cap = (unsigned long long)(arena_slots / lanes);
+    rec.env_slot = (unsigned long long*)d_env_slot;
+    G2048_REQUIRE((int64_t)rec.cap >= max_steps + 1, "play_record: arena smaller than one episode per lane");
+    cudaStream_t st = (cudaStream_t)stream;
+#define ARGS d_subs, n_subs, batch_global, env_lo, n, d_work, d_final_boards, d_lengths, d_scores, d_stats, st, nullptr, rec
+    if (policy == G2048_POLICY_RANDOM) {
+        if (rng_mode == G2048_RNG_PARTITIONABLE) return launch_play3<G2048_RNG_PARTITIONABLE, G2048_POLICY_RANDOM, true>(ARGS);
+        return launch_play3<G2048_RNG_ORIGINAL, G2048_POLICY_RANDOM, true>(ARGS);
+    }
+    if (rng_mode == G2048_RNG_PARTITIONABLE) return launch_play3<G2048_RNG_PARTITIONABLE, G2048_POLICY_DRUL, true>(ARGS);
+    return launch_play3<G2048_RNG_ORIGINAL, G2048_POLICY_DRUL, true>(ARGS);
+#undef ARGS
+}
+
+// One warp per env: the episode's slot range -> its segment of the flat buffer (HBM-bound: 9 B read + up to 21 B
+// written per env-step; the potentials behind the rewards cost nothing next to that).
+template <int POLICY>
+__global__ void __launch_bounds__(256)
+play_record_compact_kernel(const u64* __restrict__ arena_boards, const uint8_t* __restrict__ arena_meta,
+                           const unsigned long long* __restrict__ env_slot, const uint32_t* __restrict__ lengths,
+                           const int64_t* __restrict__ offsets, int64_t n, int64_t out_base, u64* __restrict__ o_boards,
+                           uint8_t* __restrict__ o_meta, float* __restrict__ o_rewards, float* __restrict__ o_log_probs,
+                           float* __restrict__ o_values, float* __restrict__ o_max_reward) {
+    const int lane = threadIdx.x & 31;
+    const int64_t warps = (int64_t)gridDim.x * (blockDim.x >> 5);
+    for (int64_t e = (int64_t)blockIdx.x * (blockDim.x >> 5) + (threadIdx.x >> 5); e < n; e += warps) {
+        const uint32_t len = lengths[e];
+        const unsigned long long src = env_slot[e];
+        const int64_t dst = out_base + offsets[e];
+        uint32_t best = 0;  // the trainer's "episode reward" = max_t reward (src/ppo/ppo_trainer.py:218-227)
+        for (uint32_t t0 = 0; t0 < len; t0 += 32u) {
+            const uint32_t t = t0 + (uint32_t)lane;
+            // boards t and t + 1: the neighbour lane holds the second one, lane 31 (and the last step) loads it
+            const u64 b0 = (t <= len) ? arena_boards[src + t] : 0ull;
+            u64 b1 = __shfl_down_sync(0xFFFFFFFFu, b0, 1);
+            if (lane == 31 && t < len) b1 = arena_boards[src + t + 1];
+            if (t < len) {
+                const uint32_t m = arena_meta[src + t];
+                const uint32_t gained = board_potential(b1) - board_potential(b0) - ((m & 0x80u) ? 4u : 0u);
+                const int64_t o = dst + t;
+                best = max(best, gained);
+                if (o_boards) o_boards[o] = b0;
+                if (o_meta) o_meta[o] = (uint8_t)(m & 0x7Fu);
+                if (o_rewards) o_rewards[o] = (float)gained;
+                if (o_log_probs) o_log_probs[o] = (POLICY == G2048_POLICY_RANDOM) ? act_random_log_prob((m >> 2) & 15u) : 0.0f;
+                if (o_values) o_values[o] = 0.0f;
+            }
+        }
+        if (o_max_reward) {
+            for (int off = 16; off > 0; off >>= 1) best = max(best, __shfl_xor_sync(0xFFFFFFFFu, best, off));
+            if (lane == 0) o_max_reward[e] = (float)best;
+        }
+    }
 }
 
 }  // namespace g2048
@@ -366,4 +495,47 @@ extern "C" int g2048_play_tables(int policy, const uint32_t* d_subs, int64_t n_s
                                  uint32_t* d_lengths, uint32_t* d_scores, uint64_t* d_stats, void* stream) {
     return play_tables_impl(policy, d_subs, n_subs, batch_global, env_lo, n, rng_mode, d_work, d_final_boards, d_lengths,
                             d_scores, d_stats, nullptr, stream);
+}
+
+// ---- recording form (see PlayRecordArena above) ---------------------------------------------------------------------
+extern "C" int64_t g2048_play_record_arena_slots(int64_t n, int64_t n_subs, int64_t mean_steps) {
+    if (n <= 0 || n_subs < 3 || mean_steps < 0) return -1;
+    const int sms = sm_count();
+    if (sms <= 0) return -1;
+    const int64_t lanes = play3_grid(n, sms) * PLAY3_THREADS;
+    return lanes * play_record_lane_slots(n, (n_subs - 1) / 2, mean_steps, sms);
+}
+
+extern "C" int g2048_play_record(int policy, const uint32_t* d_subs, int64_t n_subs, int64_t batch_global, int64_t env_lo,
+                                 int64_t n, int rng_mode, uint64_t* d_work, uint64_t* d_arena_boards, uint8_t* d_arena_meta,
+                                 int64_t arena_slots, uint64_t* d_env_slot, uint64_t* d_final_boards, uint32_t* d_lengths,
+                                 uint32_t* d_scores, uint64_t* d_stats, void* stream) {
+    return play_record_impl(policy, d_subs, n_subs, batch_global, env_lo, n, rng_mode, d_work, d_arena_boards, d_arena_meta,
+                            arena_slots, d_env_slot, d_final_boards, d_lengths, d_scores, d_stats, stream);
+}
+
+extern "C" int g2048_play_record_compact(int policy, const uint64_t* d_arena_boards, const uint8_t* d_arena_meta,
+                                         const uint64_t* d_env_slot, const uint32_t* d_lengths, const int64_t* d_offsets,
+                                         int64_t n, int64_t out_base, uint64_t* d_boards, uint8_t* d_meta, float* d_rewards,
+                                         float* d_log_probs, float* d_values, float* d_max_reward, void* stream) {
+    G2048_REQUIRE(policy == G2048_POLICY_RANDOM || policy == G2048_POLICY_DRUL, "play_record_compact: policy");
+    G2048_REQUIRE(n >= 0 && out_base >= 0, "play_record_compact: sizes");
+    if (n == 0) return G2048_OK;
+    G2048_REQUIRE(d_arena_boards && d_arena_meta && d_env_slot && d_lengths && d_offsets, "play_record_compact: pointers");
+    const int sms = sm_count();
+    if (sms <= 0) return fail_arg("play_record_compact: no device");
+    const int64_t need = (n + 7) / 8;  // 8 warps (envs) per CTA
+    const int64_t cap = (int64_t)sms * 32;  // grid-stride beyond 8 resident CTAs per SM x 4
+    const unsigned grid = (unsigned)(need < cap ? need : cap);
+    cudaStream_t st = (cudaStream_t)stream;
+    if (policy == G2048_POLICY_RANDOM)
+        play_record_compact_kernel<G2048_POLICY_RANDOM><<<grid, 256, 0, st>>>(
+            (const u64*)d_arena_boards, d_arena_meta, (const unsigned long long*)d_env_slot, d_lengths, d_offsets, n, out_base,
+            (u64*)d_boards, d_meta, d_rewards, d_log_probs, d_values, d_max_reward);
+    else
+        play_record_compact_kernel<G2048_POLICY_DRUL><<<grid, 256, 0, st>>>(
+            (const u64*)d_arena_boards, d_arena_meta, (const unsigned long long*)d_env_slot, d_lengths, d_offsets, n, out_base,
+            (u64*)d_boards, d_meta, d_rewards, d_log_probs, d_values, d_max_reward);
+    G2048_CHECK_LAUNCH("play_record_compact");
+    return G2048_OK;
 }

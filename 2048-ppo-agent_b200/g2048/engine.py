@@ -211,6 +211,50 @@ def play_packed(policy: int, subs: torch.Tensor, batch_global: int, env_lo: int,
     return dict(results=results, stats=stats)
 
 
+MEAN_STEPS_HINT = {POLICY_RANDOM: 128, POLICY_DRUL: 224}  # only sizes the recording arena (observed means: ~118 / ~207)
+
+
+def play_record(policy: int, subs: torch.Tensor, batch_global: int, env_lo: int, n: int, rng_mode: int,
+                mean_steps: int | None = None, stats: torch.Tensor | None = None) -> dict:
+    """g2048_play that also records every env's trajectory into a per-lane arena (one launch of the persistent table
+    kernel).  Returns dict(arena_boards, arena_meta, env_slot, final_boards, lengths, scores, stats); pass it to
+    play_record_compact for the env-major flat buffer.  If stats["episodes"] < n the arena was too small (raise
+    mean_steps)."""
+    dev = subs.device
+    mean = MEAN_STEPS_HINT[policy] if mean_steps is None else int(mean_steps)
+    slots = int(N.lib.g2048_play_record_arena_slots(n, subs.shape[0], mean))
+    if slots <= 0:
+        raise RuntimeError(f"g2048_play_record_arena_slots({n}, {subs.shape[0]}, {mean}) failed")
+    work = torch.zeros(2, dtype=torch.int64, device=dev)
+    if stats is None:
+        stats = torch.zeros(N.PLAY_STATS_WORDS, dtype=torch.int64, device=dev)
+    out = dict(
+        arena_boards=torch.empty(slots, dtype=torch.int64, device=dev), arena_meta=torch.empty(slots, dtype=torch.uint8, device=dev),
+        env_slot=torch.empty(n, dtype=torch.int64, device=dev), final_boards=torch.empty(n, dtype=torch.int64, device=dev),
+        lengths=torch.zeros(n, dtype=torch.int32, device=dev), scores=torch.empty(n, dtype=torch.int32, device=dev),
+        stats=stats, policy=policy)
+    call("g2048_play_record", policy, ptr(_i32(subs)), subs.shape[0], batch_global, env_lo, n, rng_mode, ptr(work),
+         ptr(out["arena_boards"]), ptr(out["arena_meta"]), slots, ptr(out["env_slot"]), ptr(out["final_boards"]),
+         ptr(out["lengths"]), ptr(out["scores"]), ptr(stats), stream_ptr())
+    return out
+
+
+def play_record_compact(rec: dict, offsets: torch.Tensor, total: int) -> dict:
+    """Arena of play_record -> flat env-major packed buffer (boards, meta, rewards, log_probs, values; max_rewards per env), `total` =
+    offsets[-1] steps; offsets = exclusive_scan(rec["lengths"])."""
+    dev = offsets.device
+    n = rec["lengths"].shape[0]
+    flat = dict(boards=torch.empty(total, dtype=torch.int64, device=dev), meta=torch.empty(total, dtype=torch.uint8, device=dev),
+                rewards=torch.empty(total, dtype=torch.float32, device=dev),
+                log_probs=torch.empty(total, dtype=torch.float32, device=dev),
+                values=torch.empty(total, dtype=torch.float32, device=dev),
+                max_rewards=torch.empty(n, dtype=torch.float32, device=dev))
+    call("g2048_play_record_compact", rec["policy"], ptr(rec["arena_boards"]), ptr(rec["arena_meta"]), ptr(rec["env_slot"]),
+         ptr(rec["lengths"]), ptr(offsets), n, 0, ptr(flat["boards"]), ptr(flat["meta"]), ptr(flat["rewards"]),
+         ptr(flat["log_probs"]), ptr(flat["values"]), ptr(flat["max_rewards"]), stream_ptr())
+    return flat
+
+
 def play_host(policy: int, seed: int, batch_global: int, rng_mode: int, env_lo: int = 0, n: int | None = None,
               key: np.ndarray | None = None, per_env: bool = True, pinned: bool = False):
     """The host-buffer C entry point (numpy in / numpy out; copies and syncs inside the call).

@@ -4,7 +4,8 @@ Per batch the reference runs ``run_actions_batch`` (numpy, reference format), on
 Python double loop (:197-202), stores the batch (:205-213) and walks every env once more for its episode
 statistics (:218-227: ``episode_reward = max_t reward``, ``episode_length = first done + 1``).  Here the records stay
 packed on the device: ``run_packed_batch`` -> ``RolloutBuffer.store_packed`` (the one-hot encoding only exists in
-``get_buffer_data()`` if somebody asks for it), the two statistics are one reduction each.
+``get_buffer_data()`` if somebody asks for it), the two statistics are one reduction each.  With act_randomly /
+act_drul the batch is ``run_flat_batch`` -> ``store_flat``: the recording play kernel writes the buffer's own layout.
 """
 from __future__ import annotations
 
@@ -23,7 +24,14 @@ def collect_rollouts(batch_runner, rollout_buffer, batch_size: int, num_batches:
         rollout_buffer.reset()
     rewards, lengths = [], []
     with torch.no_grad():
+        fused = getattr(batch_runner.act_fn, "policy_id", None) is not None
         for _ in range(num_batches):
+            if fused:  # every env is played to termination by the lane that owns it: episode = its flat segment
+                fr = batch_runner.run_flat_batch(batch_size)
+                rollout_buffer.store_flat(fr)
+                lengths.append(fr.lengths.long())
+                rewards.append(fr.max_rewards)
+                continue
             ro = batch_runner.run_packed_batch(batch_size)
             rollout_buffer.store_packed(ro)
             length = ro.lengths().long()

@@ -86,6 +86,16 @@ class RolloutBuffer:
         t, b = rollout.t_steps, rollout.batch_size
         return self._compact(rollout.boards, rollout.meta, rollout.rewards, rollout.log_probs, rollout.values, t, b)
 
+    def store_flat(self, rollout) -> int:
+        """Append a ``FlatRollout`` (``BatchRunner.run_flat_batch``): the records are already laid out env after env,
+        steps 0..first_done of each -- exactly what ``store_packed`` would have produced -- so nothing is copied."""
+        total = int(rollout.boards.shape[0])
+        if total == 0:
+            return 0
+        self._parts.append(("packed", (rollout.boards, rollout.meta, rollout.rewards, rollout.values, rollout.log_probs)))
+        self.buffer_size += total
+        return total
+
     def store_batch(self, observations, actions, action_masks, rewards, values, log_probs, terminations):
         """Reference signature (rollout_buffer.py:128-187): env-major (B, T, ...) numpy arrays.  2048 one-hot
         observations with one-hot (B,T,4) actions (or action indices (B,T)) are packed as bitboards; anything else

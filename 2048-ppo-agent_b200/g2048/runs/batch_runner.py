@@ -62,6 +62,33 @@ class PackedRollout:
         return E.episode_lengths(self.meta, self.t_steps, self.batch_size)
 
 
+@dataclass
+class FlatRollout:
+    """A finished run of a built-in policy as the env-major ragged buffer ``RolloutBuffer`` keeps: the steps
+    0..first_done of env 0, then those of env 1, ... (``offsets[e]`` = first flat index of env e, ``lengths[e]`` its
+    number of steps).  Produced by ONE launch of the recording play kernel + one compaction kernel; identical, bit
+    for bit, to ``RolloutBuffer.store_packed(run_packed_batch(...))``.
+
+    boards int64 pre-step bitboards, meta uint8 (action | mask << 2 | done << 6), rewards / log_probs / values float32
+    (log_probs of act_drul and all values are zero, as ``store_packed`` stores them).
+    """
+
+    boards: torch.Tensor
+    meta: torch.Tensor
+    rewards: torch.Tensor
+    log_probs: torch.Tensor
+    values: torch.Tensor
+    lengths: torch.Tensor
+    offsets: torch.Tensor
+    final_boards: torch.Tensor
+    scores: torch.Tensor
+    max_rewards: torch.Tensor  # per env: max_t reward (the trainer's "episode reward")
+    t_steps: int  # loop steps of the reference's run = the longest episode (over all shards)
+    batch_size: int
+    env_steps: int
+    summary: dict
+
+
 class BatchRunner:
     """Runs batches of 2048 envs with an action function (reference: batch_runner.py:10-37)."""
 
@@ -93,6 +120,7 @@ class BatchRunner:
         self.cuda_graph = cuda_graph
         self.compact_live = compact_live
         self._graphs = {}  # (batch_size, lo, n, steps, auto_reset) -> captured step of the current act_fn
+        self._mean_steps = {}  # policy id -> mean episode length of the last recorded batch (sizes the next arena)
 
     # -- reference surface ---------------------------------------------------------------------
     @property
@@ -169,6 +197,39 @@ class BatchRunner:
         out["stats"] = stats
         out["summary"] = st
         return out
+
+    def run_flat_batch(self, batch_size: int) -> FlatRollout:
+        """``run_packed_batch`` + ``RolloutBuffer.store_packed`` for act_randomly / act_drul in two launches: the
+        persistent table kernel plays every env to termination and appends its records to the playing lane's own
+        arena region (``g2048_play_record``; no lane ever steps a finished env), and one HBM-bound pass lays the
+        episodes out env after env (``g2048_play_record_compact``)."""
+        self._check(batch_size)
+        policy = getattr(self._act_fn, "policy_id", None)
+        if policy is None:
+            raise ValueError("run_flat_batch needs act_randomly or act_drul; use run_packed_batch for other policies")
+        lo, n = self._range(batch_size)
+        max_steps, mean_steps = 2048, self._mean_steps.get(policy)
+        while True:
+            subs = self.chain.peek(1 + 2 * max_steps)
+            rec = E.play_record(policy, subs, batch_size, lo, n, self.rng_mode, mean_steps)
+            local = E.play_stats_dict(rec["stats"])
+            if local["cut_short"]:
+                max_steps *= 4  # an episode outlived the keys that were generated: replay with more
+                continue
+            if local["episodes"] < n:  # some lane regions filled up before the queue was empty: a larger arena
+                mean_steps = 2 * (E.MEAN_STEPS_HINT[policy] if mean_steps is None else mean_steps)
+                continue
+            break
+        if n:
+            self._mean_steps[policy] = max(16, -(-local["env_steps"] // n))
+        stats = self._reduce_stats(rec["stats"])
+        st = E.play_stats_dict(stats)
+        self.chain.consume(1 + 2 * st["longest"])
+        offsets = E.exclusive_scan(rec["lengths"])
+        total = local["env_steps"]
+        flat = E.play_record_compact(rec, offsets, total)
+        return FlatRollout(flat["boards"], flat["meta"], flat["rewards"], flat["log_probs"], flat["values"], rec["lengths"],
+                           offsets, rec["final_boards"], rec["scores"], flat["max_rewards"], st["longest"], n, total, st)
 
     def run_eval_batch(self, batch_size: int) -> dict:
         """Network policy, results only: play ``batch_size`` envs to termination with the ``TorchActionFunction`` and

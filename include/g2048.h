@@ -144,6 +144,35 @@ typedef struct G2048EpisodeResult {
 int g2048_play_packed(int policy, const uint32_t* d_subs, int64_t n_subs, int64_t batch_global, int64_t env_lo, int64_t n,
                       int rng_mode, uint64_t* d_work, G2048EpisodeResult* d_results, uint64_t* d_stats, void* stream);
 
+/* ---- recorded play to termination: g2048_play that also keeps every env's trajectory (the rollout-buffer write of
+ * src/runs/batch_runner.py:117-154 + src/ppo/rollout_buffer.py:164-187 fused into the persistent table kernel).
+ * A lane plays its envs one after the other, so it appends their records to its own region of an ARENA
+ * (d_arena_boards: uint64 per slot, d_arena_meta: uint8 per slot; arena_slots slots, at least
+ * g2048_play_record_arena_slots(n, n_subs, mean_steps) of them, mean_steps = the caller's estimate of the mean episode
+ * length -- it only sizes the lanes' regions).  Per env-step one slot: the pre-step board and a meta byte (bits 0-1
+ * action, 2-5 pre-step legal mask, 6 post-step done, 7 "the spawn of this step was a 4-tile"); after an env's last
+ * step one more slot with its final board.  d_env_slot[i] (uint64, n) = slot of step 0 of env env_lo + i, so its
+ * episode is slots [d_env_slot[i], d_env_slot[i] + d_lengths[i]].  d_lengths is required; the other per-env outputs
+ * and d_stats are those of g2048_play.  If the arena is too small for the batch some envs are not played:
+ * d_stats[0] (episodes) < n then, and the caller retries with more slots.
+ *
+ * g2048_play_record_compact turns the arena into the env-major flat buffer RolloutBuffer keeps (what
+ * g2048_rollout_steps + g2048_compact_records produce, bit for bit): flat index = out_base + d_offsets[i] + t for
+ * t < d_lengths[i] (d_offsets = exclusive scan of d_lengths).  d_boards pre-step boards, d_meta bits 0-6 of the meta
+ * byte, d_rewards = potential(board t+1) - potential(board t) - 4 * bit 7 (= the sum of the merged tiles' values,
+ * Pgx's reward), d_log_probs = log(1 / #legal actions) for G2048_POLICY_RANDOM and 0 for DRUL, d_values = 0.
+ * d_max_reward (n, float32) = max over the env's steps of the reward (the trainer's "episode reward",
+ * src/ppo/ppo_trainer.py:218-227).  Any output may be NULL. */
+int64_t g2048_play_record_arena_slots(int64_t n, int64_t n_subs, int64_t mean_steps);
+int g2048_play_record(int policy, const uint32_t* d_subs, int64_t n_subs, int64_t batch_global, int64_t env_lo, int64_t n,
+                      int rng_mode, uint64_t* d_work, uint64_t* d_arena_boards, uint8_t* d_arena_meta, int64_t arena_slots,
+                      uint64_t* d_env_slot, uint64_t* d_final_boards, uint32_t* d_lengths, uint32_t* d_scores,
+                      uint64_t* d_stats, void* stream);
+int g2048_play_record_compact(int policy, const uint64_t* d_arena_boards, const uint8_t* d_arena_meta,
+                              const uint64_t* d_env_slot, const uint32_t* d_lengths, const int64_t* d_offsets, int64_t n,
+                              int64_t out_base, uint64_t* d_boards, uint8_t* d_meta, float* d_rewards, float* d_log_probs,
+                              float* d_values, float* d_max_reward, void* stream);
+
 /* Test hook for the shared-memory tables of g2048_play_tables: for each 16-bit row (four nibbles, nibble 0 =
  * column 0) the row slid/merged toward column 0 and the flags (bit 0: moves left, bit 2: moves right). */
 int g2048_row_table_lookup(const uint16_t* d_rows, int64_t n, uint16_t* d_left, uint8_t* d_flags, void* stream);

@@ -27,6 +27,10 @@ def run_all(E, g2048, T=torch, dev="cuda"):
         for policy in (0, 1):
             E.play(policy, subs, 3001, 0, 3001, mode, entry="g2048_play_tables")
             E.play(policy, subs, 3001, 1234, 1, mode, entry="g2048_play_tables")
+        for policy in (0, 1):  # recording form: arena + compaction into the flat buffer
+            rec = E.play_record(policy, subs, 3001, 100, 777, mode)
+            offs_r = E.exclusive_scan(rec["lengths"])
+            E.play_record_compact(rec, offs_r, int(offs_r[-1].item()))
         counters = T.zeros(4, dtype=torch.int64, device=dev)
         n, ch = 333, 5
         rb = T.empty((ch, n), dtype=torch.int64, device=dev)
@@ -130,6 +134,7 @@ def run_all(E, g2048, T=torch, dev="cuda"):
     E.gae_host(np.random.rand(7000).astype(np.float32), np.random.rand(7000).astype(np.float32),
                (np.random.rand(7000) < 0.01).astype(np.uint8), 0.99, 0.95, True)
     runner = g2048.BatchRunner(1, g2048.act_randomly)
+    runner.run_flat_batch(333)
     ro = runner.run_packed_batch(50)
     buf = g2048.RolloutBuffer(31, 16, 4)
     buf.store_packed(ro)
