@@ -9,6 +9,7 @@ from __future__ import annotations
 import ctypes as C
 import os
 import re
+import threading
 from pathlib import Path
 
 import torch
@@ -131,18 +132,43 @@ def require_cuda() -> torch.device:
     return torch.device("cuda", torch.cuda.current_device())
 
 
+# The GPU a call runs on is the GPU its tensors live on, not whatever device happens to be current: ptr() notes the
+# device of every CUDA tensor handed to the call being assembled, stream_ptr() returns THAT device's current stream,
+# and call() makes the device current around the C entry point (which launches on the current device and keys its
+# per-device caches -- SM count, function attributes, host workspaces -- off cudaGetDevice).  So
+# BatchRunner(device="cuda:1") works in a process whose current device is 0.
+_call_ctx = threading.local()
+
+
 def ptr(t: torch.Tensor | None) -> int | None:
     """Device (or host) pointer of a contiguous tensor, None passes NULL."""
     if t is None:
         return None
     if not t.is_contiguous():
         raise ValueError("g2048 kernels need contiguous tensors")
+    if t.is_cuda:
+        seen = getattr(_call_ctx, "device", None)
+        if seen is None:
+            _call_ctx.device = t.device.index
+        elif seen != t.device.index:
+            _call_ctx.device = None
+            raise ValueError(f"one g2048 call got tensors on cuda:{seen} and cuda:{t.device.index}")
     return t.data_ptr()
 
 
 def stream_ptr() -> int:
-    return torch.cuda.current_stream().cuda_stream
+    """Current stream of the device the call's tensors live on (of the current device for host-buffer calls)."""
+    dev = getattr(_call_ctx, "device", None)
+    return torch.cuda.current_stream(dev).cuda_stream
 
 
 def call(name: str, *args) -> None:
-    check(getattr(lib, name)(*args), name)
+    dev = getattr(_call_ctx, "device", None)
+    _call_ctx.device = None
+    fn = getattr(lib, name)
+    if dev is not None and dev != torch.cuda.current_device():
+        with torch.cuda.device(dev):
+            rc = fn(*args)
+    else:
+        rc = fn(*args)
+    check(rc, name)

@@ -37,9 +37,14 @@ def resolve_rng_mode(mode=None) -> int:
 
 
 def key_words(seed: int) -> tuple[int, int]:
-    """jax.random.key(seed) -> (hi, lo) uint32 words."""
-    seed = int(seed) & 0xFFFFFFFFFFFFFFFF
-    return (seed >> 32) & 0xFFFFFFFF, seed & 0xFFFFFFFF
+    """jax.random.key(seed) -> (hi, lo) uint32 words, as the reference gets them (src/runs/batch_runner.py:32 with jax's
+    default 32-bit mode): the seed becomes an int32 array, so the high word -- a logical shift by 32 -- is always 0 and
+    the low word is the seed's two's-complement bits (seed=-1 -> (0, 0xFFFFFFFF)); a seed outside [-2^31, 2^32) does
+    not fit and raises OverflowError there, so it does here."""
+    seed = int(seed)
+    if not -(1 << 31) <= seed < (1 << 32):
+        raise OverflowError(f"seed {seed} does not fit in 32 bits (jax.random.key without x64 rejects it too)")
+    return 0, seed & 0xFFFFFFFF
 
 
 def words_tensor(words, device) -> torch.Tensor:
@@ -222,7 +227,8 @@ def play_record(policy: int, subs: torch.Tensor, batch_global: int, env_lo: int,
     mean_steps)."""
     dev = subs.device
     mean = MEAN_STEPS_HINT[policy] if mean_steps is None else int(mean_steps)
-    slots = int(N.lib.g2048_play_record_arena_slots(n, subs.shape[0], mean))
+    with torch.cuda.device(dev):  # the arena follows the SM count of the GPU that will run the kernel
+        slots = int(N.lib.g2048_play_record_arena_slots(n, subs.shape[0], mean))
     if slots <= 0:
         raise RuntimeError(f"g2048_play_record_arena_slots({n}, {subs.shape[0]}, {mean}) failed")
     work = torch.zeros(2, dtype=torch.int64, device=dev)
@@ -269,14 +275,14 @@ def play_host(policy: int, seed: int, batch_global: int, rng_mode: int, env_lo: 
     as_p = lambda a: None if a is None else a.ctypes.data  # noqa: E731
     if pinned and per_env:
         records = torch.empty((n, 2), dtype=torch.int64, pin_memory=True).numpy().view(EPISODE_RESULT).reshape(n)
-        call("g2048_play_host_packed", policy, int(seed) & 0xFFFFFFFFFFFFFFFF, as_p(key_io), batch_global, env_lo, n, rng_mode,
+        call("g2048_play_host_packed", policy, key_words(seed)[1], as_p(key_io), batch_global, env_lo, n, rng_mode,
              as_p(records), as_p(stats))
         return dict(final_boards=records["board"], lengths=records["length"], scores=records["score"], stats=stats,
                     key=key_io, records=records)
     boards = np.empty(n, np.uint64) if per_env else None
     lengths = np.empty(n, np.uint32) if per_env else None
     scores = np.empty(n, np.uint32) if per_env else None
-    call("g2048_play_host", policy, int(seed) & 0xFFFFFFFFFFFFFFFF, as_p(key_io), batch_global, env_lo, n, rng_mode,
+    call("g2048_play_host", policy, key_words(seed)[1], as_p(key_io), batch_global, env_lo, n, rng_mode,
          as_p(boards), as_p(lengths), as_p(scores), as_p(stats))
     return dict(final_boards=boards, lengths=lengths, scores=scores, stats=stats, key=key_io)
 

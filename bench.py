@@ -1,11 +1,15 @@
 #!/usr/bin/env python
 """Benchmark of the rollout hot path (contract: python bench.py --gpus N --steps K --warmup W).
 
-A "step" is one pass of the hot path over one batch: BASELINE.json's C5 workload -- a batch of 2048
-envs is played to termination under the random policy (act_randomly) by the persistent
+A "step" is one pass of the hot path over one batch: BASELINE.json's C5 workload -- a batch of 2^24
+(16 M) 2048 envs is played to termination under the random policy (act_randomly) by the persistent
 `g2048_play` kernel (key chain generated on the device inside the step), followed by the episode
-statistics reduction (NCCL all-reduce when N > 1).  Envs are sharded over the ranks with global env
-indices (weak scaling: 2^21 envs per GPU, 2^24 = C5's 16 M at N = 8).
+statistics reduction (one NCCL collective when N > 1).  The batch is sharded over the ranks with
+global env indices: the default is C5 as BASELINE.json states it -- the SAME 16 M envs at N = 1, 2,
+4, 8 ("scaling": "strong"); `--scaling weak --envs-per-gpu E` keeps the per-GPU work fixed instead,
+and every line also carries a short weak-scaling measurement (`weak_scaling`, 2^21 envs per GPU --
+round 1's configuration).  At every N each rank checks a window of its own shard against the
+oracle and the pass flags are all-reduced into `parity`.
 
 Prints ONE JSON line.  `value` is device-timed with everything resident in HBM; `e2e` is the same
 metric through the host-buffer C entry point `g2048_play_host` (its own allocations, H2D/D2H copies
@@ -35,12 +39,16 @@ for _p in (str(ROOT), str(ROOT / "2048-ppo-agent_b200")):
     if _p not in sys.path:
         sys.path.insert(0, _p)
 
-ENVS_PER_GPU = 1 << 21
+TOTAL_ENVS = 1 << 24   # C5: 16 M envs, sharded over the ranks (strong scaling, the default)
+ENVS_PER_GPU = 1 << 21  # --scaling weak, and the `weak_scaling` leg of every line
 SEED = 2048
-MAX_STEPS = 1024  # loop steps of keys generated per batch (random episodes stay below ~600; checked via cut_short)
-ALG_INSTR = {"random": 990, "drul": 620}  # 74 int instr per Threefry block x 10 (5) + ~250 game logic
+MAX_STEPS = 2048  # loop steps of keys generated per batch (random episodes stay below ~700; checked via cut_short)
+# SURVEY 8(d)'s paper count (74 int instr per Threefry block x 10 (5) + ~250 game logic); the roofline uses the
+# MEASURED thread instructions per env-step of the shipped kernels instead when profiles/inst_counts.json is there
+ALG_INSTR = {"random": 990, "drul": 620}
 CPU_SAMPLE_ENVS = 1 << 17
 REF_SAMPLE_ENVS = 1 << 16
+PARITY_WINDOW = 4096  # envs of its own shard that every rank checks against the oracle
 
 
 def parse_args():
@@ -50,6 +58,9 @@ def parse_args():
     ap.add_argument("--warmup", type=int, default=3)
     ap.add_argument("--impl", default="g2048", choices=["g2048", "reference"])
     ap.add_argument("--policy", default="random", choices=["random", "drul"])
+    ap.add_argument("--scaling", default="strong", choices=["strong", "weak"],
+                    help="strong: --envs envs in all, sharded over the GPUs (C5); weak: --envs-per-gpu envs on every GPU")
+    ap.add_argument("--envs", type=int, default=TOTAL_ENVS)
     ap.add_argument("--envs-per-gpu", type=int, default=ENVS_PER_GPU)
     ap.add_argument("--no-extras", action="store_true", help="skip the secondary kernel measurements")
     return ap.parse_args()
@@ -156,12 +167,34 @@ def oracle_play_rate(seed: int, batch_global: int, n_sample: int, policy: int, m
     return total_steps / dt, threads, reps, out
 
 
+# ------------------------------------------------------------------------------------------ workload
+def batch_shape(args, world: int, rank: int):
+    """-> (batch_global, env_lo, n): the envs of the global batch this rank plays."""
+    if args.scaling == "strong":
+        batch_global = args.envs
+        lo, hi = batch_global * rank // world, batch_global * (rank + 1) // world
+        return batch_global, lo, hi - lo
+    return args.envs_per_gpu * world, args.envs_per_gpu * rank, args.envs_per_gpu
+
+
+def workload_config(args, world: int):
+    batch_global, _, n0 = batch_shape(args, world, 0)
+    how = (f"{batch_global} envs in all, sharded over {world} GPU(s) (BASELINE.json configs[4]: 16M envs across 1/2/4/8 B200)"
+           if args.scaling == "strong" else f"{args.envs_per_gpu} envs per GPU")
+    return {
+        "workload": f"C5 throughput sweep: {args.policy}-policy 2048 envs played to termination + episode-stats reduction; {how}",
+        "policy": args.policy, "scaling": args.scaling, "global_batch": batch_global, "envs_per_gpu": n0,
+        "rng": "threefry2x32 partitionable (jax 0.5.3 default)", "seed": SEED,
+        "l2": "L2 flushed (512 MiB write) between timed steps; the kernel's inputs are 32 KiB of keys, env state lives in registers",
+    }
+
+
 # ------------------------------------------------------------------------------------------ reference arm
 def run_reference(args, rank: int):
     if rank != 0:
         return
     policy = 0 if args.policy == "random" else 1
-    batch_global = args.envs_per_gpu * args.gpus
+    batch_global, _, _ = batch_shape(args, args.gpus, 0)
     n_sample = min(REF_SAMPLE_ENVS, batch_global)
     from oracle import c_oracle as CO
 
@@ -180,8 +213,8 @@ def run_reference(args, rank: int):
     line = {
         "impl": "reference", "metric": "env_steps_per_sec", "value": value, "unit": "env-steps/s", "n_gpus": args.gpus,
         "steps": args.steps, "warmup": args.warmup, "ms_per_step": 1e3 * sum(times) / len(times),
-        "higher_is_better": True, "scaling": "weak", "vs_baseline": None, "dtype": "u8/u32 integer", "data": "synthetic",
-        "config": workload_config(args, batch_global),
+        "higher_is_better": True, "scaling": args.scaling, "vs_baseline": None, "dtype": "u8/u32 integer", "data": "synthetic",
+        "config": workload_config(args, args.gpus),
         "cpu_baseline": {"value": value, "unit": "env-steps/s", "cores": CO.num_threads(), "kind": "port", "sample": sample},
         "e2e": {"value": value, "unit": "env-steps/s", "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0},
         "gpu_launches": 0,
@@ -189,14 +222,12 @@ def run_reference(args, rank: int):
     print(json.dumps(line))
 
 
-def workload_config(args, batch_global):
-    return {
-        "workload": f"C5 throughput sweep: {args.policy}-policy 2048 envs played to termination + episode-stats reduction "
-                    f"(BASELINE.json configs[4]; {args.envs_per_gpu} envs per GPU, 2^24 at 8 GPUs)",
-        "policy": args.policy, "envs_per_gpu": args.envs_per_gpu, "global_batch": batch_global,
-        "rng": "threefry2x32 partitionable (jax 0.5.3 default)", "seed": SEED,
-        "l2": "L2 flushed (512 MiB write) between timed steps; the kernel's inputs are 32 KiB of keys, env state lives in registers",
-    }
+def measured_inst_counts():
+    """profiles/inst_counts.json: smsp__thread_inst_executed.sum per env-step of the shipped play kernels (ncu)."""
+    try:
+        return json.loads((ROOT / "profiles" / "inst_counts.json").read_text())
+    except Exception:  # noqa: BLE001 -- evidence, not a dependency
+        return {}
 
 
 # ------------------------------------------------------------------------------------------ our arm
@@ -227,47 +258,8 @@ def main():
 
     policy_id = E.POLICY_RANDOM if args.policy == "random" else E.POLICY_DRUL
     mode = E.RNG_PARTITIONABLE
-    n = args.envs_per_gpu
-    batch_global = n * world
-    lo = n * rank
     n_subs = 1 + 2 * MAX_STEPS
-
     flush_buf = torch.empty(512 << 20, dtype=torch.uint8, device=dev)
-    stats_all = []
-    launches = {"ours": 0}
-
-    # the inputs of a step (one 8-byte chain key per batch) are resident in HBM before the timed region
-    step_keys = [E.words_tensor(list(E.key_words(SEED + i)), dev) for i in range(args.warmup + args.steps)]
-
-    # The key chain of a batch is sequential (one thread, ~0.14 us per split), so it is generated on a side
-    # stream one batch ahead, overlapping the previous batch's play kernel; the first batch waits for it.
-    side = torch.cuda.Stream(device=dev)
-    chains = {}
-
-    def prefetch_chain(i: int):
-        if i < len(step_keys) and i not in chains:
-            with torch.cuda.stream(side):  # depends only on step_keys, which were ready before the timed region
-                subs_i = E.chain_advance(step_keys[i], mode, n_subs)
-                ev = torch.cuda.Event()
-                ev.record(side)
-            chains[i] = (subs_i, ev)
-            launches["ours"] += 1
-
-    def one_step(i: int, per_env: bool = False):
-        """key chain (prefetched on the side stream) + persistent play kernel + stats reduction, all on the device."""
-        prefetch_chain(i)
-        subs, ev = chains.pop(i)
-        torch.cuda.current_stream().wait_event(ev)
-        out = E.play(policy_id, subs, batch_global, lo, n, mode, per_env=per_env)
-        subs.record_stream(torch.cuda.current_stream())
-        launches["ours"] += 1
-        prefetch_chain(i + 1)
-        if world > 1:
-            longest = out["stats"][5:6].clone()
-            dist.all_reduce(out["stats"], op=dist.ReduceOp.SUM)
-            dist.all_reduce(longest, op=dist.ReduceOp.MAX)
-            out["stats"][5] = longest[0]
-        return out
 
     def barrier():
         torch.cuda.synchronize()
@@ -275,58 +267,123 @@ def main():
             dist.barrier()
         torch.cuda.synchronize()
 
+    def reduce_stats(stats):
+        """ONE collective per step: all-gather the 256-byte statistics blocks, reduce locally (sum; slot 5 is a max)."""
+        if world == 1:
+            return stats
+        gathered = torch.empty((world, N.PLAY_STATS_WORDS), dtype=torch.int64, device=dev)
+        dist.all_gather_into_tensor(gathered, stats)
+        out = gathered.sum(dim=0)
+        out[5] = gathered[:, 5].max()
+        return out
+
+    def timed_play_loop(batch_global, lo, n, warmup, steps, sampler=None):
+        """warmup + steps batches; per step: key chain (prefetched on a side stream one batch ahead) + persistent play
+        kernel + statistics reduction, device-timed with CUDA events (L2 flushed before each step).  Returns
+        (seconds of the timed steps (max over ranks), reduced statistics of the timed steps, launches, seconds inside
+        the play kernel)."""
+        # the inputs of a step (one 8-byte chain key per batch) are resident in HBM before the timed region
+        step_keys = [E.words_tensor(list(E.key_words(SEED + i)), dev) for i in range(warmup + steps)]
+        side = torch.cuda.Stream(device=dev)
+        chains, launches = {}, {"n": 0}
+
+        def prefetch_chain(i: int):
+            # The key chain of a batch is sequential (one thread, ~0.14 us per split): it is generated on a side stream
+            # one batch ahead, overlapping the previous batch's play kernel; the first batch waits for it.
+            if i < len(step_keys) and i not in chains:
+                with torch.cuda.stream(side):  # depends only on step_keys, which were ready before the timed region
+                    subs_i = E.chain_advance(step_keys[i], mode, n_subs)
+                    ev = torch.cuda.Event()
+                    ev.record(side)
+                chains[i] = (subs_i, ev)
+                launches["n"] += 1
+
+        kernel_events = []
+
+        def one_step(i: int):
+            prefetch_chain(i)
+            subs, ev = chains.pop(i)
+            torch.cuda.current_stream().wait_event(ev)
+            k0, k1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+            k0.record()
+            out = E.play(policy_id, subs, batch_global, lo, n, mode, per_env=False)
+            k1.record()
+            kernel_events.append((k0, k1))
+            subs.record_stream(torch.cuda.current_stream())
+            launches["n"] += 1
+            prefetch_chain(i + 1)
+            return reduce_stats(out["stats"])
+
+        for i in range(warmup):
+            one_step(i)
+        barrier()
+        launches["n"] = 0
+        kernel_events.clear()
+        events, stats_all = [], []
+        barrier()
+        if sampler is not None:
+            sampler.begin()
+        for i in range(steps):
+            flush_buf.fill_(i & 0xFF)  # L2 flush, outside the timed events
+            a, b = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+            a.record()
+            stats_all.append(one_step(warmup + i))
+            b.record()
+            events.append((a, b))
+        barrier()
+        if sampler is not None:
+            sampler.end()
+        elapsed = sum(a.elapsed_time(b) for a, b in events) * 1e-3
+        t = torch.tensor([elapsed], dtype=torch.float64, device=dev)
+        if world > 1:
+            dist.all_reduce(t, op=dist.ReduceOp.MAX)
+        kernel_s = sum(a.elapsed_time(b) for a, b in kernel_events) * 1e-3
+        return float(t.item()), [E.play_stats_dict(s) for s in stats_all], launches["n"], kernel_s
+
+    # ---- the timed region -----------------------------------------------------------------------------------------
+    batch_global, lo, n = batch_shape(args, world, rank)
     sampler = ClockSampler(local_rank)
     if rank == 0:
         sampler.start()
-    for i in range(args.warmup):
-        one_step(i)
-    barrier()
-
-    launches["ours"] = 0
-    events = []
-    barrier()
-    sampler.begin()
-    for i in range(args.steps):
-        flush_buf.fill_(i & 0xFF)  # L2 flush, outside the timed events
-        a, b = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
-        a.record()
-        out = one_step(args.warmup + i)
-        b.record()
-        events.append((a, b))
-        stats_all.append(out["stats"])
-    barrier()
-    sampler.end()
+    elapsed, summaries, gpu_launches, kernel_s = timed_play_loop(batch_global, lo, n, args.warmup, args.steps, sampler)
     clocks = sampler.stop() if rank == 0 else None
-    gpu_launches = launches["ours"]
-    elapsed = sum(a.elapsed_time(b) for a, b in events) * 1e-3
-    t = torch.tensor([elapsed], dtype=torch.float64, device=dev)
-    if world > 1:
-        dist.all_reduce(t, op=dist.ReduceOp.MAX)
-    elapsed = float(t.item())
-    summaries = [E.play_stats_dict(s) for s in stats_all]
-    total_env_steps = sum(s["env_steps"] for s in summaries)  # after the all-reduce: whole-job totals
+    total_env_steps = sum(s["env_steps"] for s in summaries)  # after the reduction: whole-job totals
     assert all(s["episodes"] == batch_global and s["cut_short"] == 0 and s["overflowed"] == 0 for s in summaries), summaries[0]
     value = total_env_steps / elapsed
 
-    # ---- dominant kernel alone (play), CUDA events on the launching stream ------------------------
-    key = E.words_tensor(list(E.key_words(SEED)), dev)
-    subs = E.chain_advance(key, mode, n_subs)
-    E.play(policy_id, subs, batch_global, lo, n, mode, per_env=False)
-    torch.cuda.synchronize()
-    k_times, k_steps = [], 0
-    for _ in range(5):
-        flush_buf.fill_(1)
-        a, b = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
-        work = torch.zeros(2, dtype=torch.int64, device=dev)
-        stats = torch.zeros(N.PLAY_STATS_WORDS, dtype=torch.int64, device=dev)
-        a.record()
-        N.call("g2048_play", policy_id, N.ptr(subs), n_subs, batch_global, lo, n, mode, N.ptr(work), None, None, None,
-               N.ptr(stats), N.stream_ptr())
-        b.record()
-        torch.cuda.synchronize()
-        k_times.append(a.elapsed_time(b) * 1e-3)
-        k_steps = int(stats[1].item())
-    k_time = statistics.mean(k_times)
+    # ---- parity of THIS rank's shard against the oracle, at every N -------------------------------------------------
+    from oracle import c_oracle as CO
+
+    CO.set_num_threads(max(1, (os.cpu_count() or 1) // world))
+    key0 = E.words_tensor(list(E.key_words(SEED)), dev)
+    subs0 = E.chain_advance(key0, mode, n_subs)
+    win = min(PARITY_WINDOW, n)
+    w_lo = lo + (n - win) // 2  # a window in the middle of the shard: its env indices are the GLOBAL ones
+    chk = E.play(policy_id, subs0, batch_global, w_lo, win, mode, per_env=True)
+    ref = CO.play(SEED, batch_global, policy_id, 1, env_lo=w_lo, env_hi=w_lo + win, max_steps=MAX_STEPS)
+    same = bool(np.array_equal(chk["lengths"].cpu().numpy(), ref["lengths"])
+                and np.array_equal(E.boards_numpy(chk["final_boards"]), ref["final_boards"])
+                and np.array_equal(chk["scores"].cpu().numpy(), ref["scores"]))
+    flags = torch.tensor([int(same), win], dtype=torch.int64, device=dev)
+    per_rank = [flags.clone() for _ in range(world)]
+    if world > 1:
+        dist.all_gather(per_rank, flags)
+    parity = {"ok": all(int(f[0]) == 1 for f in per_rank), "ranks_ok": [bool(int(f[0])) for f in per_rank],
+              "parity_checked_envs": [int(f[1]) for f in per_rank],
+              "what": "final boards, lengths and scores of a window of each rank's own shard (global env indices), first timed "
+                      "batch's seed, CUDA kernel vs the oracle's C restatement"}
+    assert parity["ok"], f"a shard differs from the oracle: {parity}"
+
+    # ---- dominant kernel (play), timed INSIDE the step loop above; instruction count per env-step as measured ---------
+    steps_per_launch = total_env_steps / args.steps / world  # this is the whole job's mean; shards are equal to <0.1 %
+    k_time = kernel_s / args.steps
+    counts = measured_inst_counts()
+
+    def instr_per_step(policy_name):
+        c = counts.get(policy_name, {})
+        if "thread_inst_per_env_step" in c:
+            return float(c["thread_inst_per_env_step"]), f"measured: {c.get('source', 'profiles/inst_counts.json')}"
+        return float(ALG_INSTR[policy_name]), "SURVEY 8(d) paper count (profiles/inst_counts.json absent)"
 
     # integer-issue peak: Threefry instruction mix, 4 independent chains per thread, full occupancy
     sms = N.lib.g2048_device_sm_count()
@@ -343,17 +400,20 @@ def main():
         torch.cuda.synchronize()
         p_times.append(a.elapsed_time(b) * 1e-3)
     int_peak = blocks * threads * iters * 48 / min(p_times) / 1e12  # 16 rounds x 3 instr per iteration
-    achieved = ALG_INSTR[args.policy] * k_steps / k_time / 1e12
+    ipe, ipe_src = instr_per_step(args.policy)
+    achieved = ipe * steps_per_launch / k_time / 1e12
     roofline = {
         "kernel": "play3_kernel (g2048_play: row tables in shared memory)", "bound": "int_issue", "achieved": achieved, "peak": int_peak,
         "unit": "Tinstr/s", "frac": achieved / int_peak,
-        # dram__bytes_read.sum + dram__bytes_write.sum of one play3_kernel launch (profiles/r01_play_tables_kernel.csv):
-        # the 192 KiB of tables per CTA come from L2, per-episode results are not written in this leg
-        "traffic": 229632,
-        "note": (f"algorithmic {ALG_INSTR[args.policy]} int instr per env-step (SURVEY 8d) x {k_steps} env-steps per launch / "
-                 f"{k_time * 1e3:.2f} ms; peak = live probe of the ADD/SHF/LOP3 Threefry mix on this GPU, measured in this run; "
-                 "the kernel keeps env state in registers, so HBM traffic is ~16 B per episode and not the bound"),
-        "kernel_ms": k_time * 1e3, "kernel_env_steps": k_steps,
+        # dram__bytes_read.sum + dram__bytes_write.sum of one launch of the shipped kernel (ncu --set full), if committed
+        "traffic": counts.get(args.policy, {}).get("dram_bytes_per_launch"),
+        "instr_per_env_step": ipe, "instr_source": ipe_src,
+        "paper_count_frac": ALG_INSTR[args.policy] * steps_per_launch / k_time / 1e12 / int_peak,
+        "note": (f"{ipe:.1f} thread instructions per env-step x {steps_per_launch:.0f} env-steps per launch / {k_time * 1e3:.3f} ms "
+                 "(CUDA events around the play launch inside the timed step loop, mean over the timed steps); peak = live probe "
+                 "of the ADD/SHF/LOP3 Threefry mix on this GPU, measured in this run; the kernel keeps env state in registers, "
+                 "so HBM traffic is ~16 B per episode and not the bound"),
+        "kernel_ms": k_time * 1e3, "kernel_env_steps": steps_per_launch,
     }
 
     # ---- end to end through the host-buffer C entry point ------------------------------------------
@@ -384,10 +444,11 @@ def main():
                "every env's final board, length and score (one 16-byte record per env) and the statistics block + synchronise, "
                "per call; the record array is pinned host memory, which the kernel writes directly over PCIe as episodes end "
                "(g2048_play_host with three pageable numpy arrays, copied after the kernel through staging buffers: "
-               "e2e.pageable_results); device workspace cached by the library",
+               "e2e.pageable_results); device workspace cached by the library; bytes are per rank",
         # the host arrays really hold the batch: their lengths add up to the statistics block's env-step count
         "results_checked": bool(int(h_len.sum(dtype=np.uint64)) == int(h_stats[1]) and int(h_score.sum(dtype=np.uint64)) == int(h_stats[2])),
     }
+    del records, h_len, h_score
     if rank == 0 and world == 1:  # the same call with ordinary numpy result arrays
         p_boards, p_len, p_score = np.empty(n, np.uint64), np.empty(n, np.uint32), np.empty(n, np.uint32)
         pg_times, pg_steps = [], 0
@@ -401,6 +462,7 @@ def main():
                 pg_steps += int(h_stats[1])
         e2e["pageable_results"] = {"value": pg_steps / sum(pg_times), "unit": "env-steps/s",
                                    "results_checked": bool(int(p_len.sum(dtype=np.uint64)) == int(h_stats[1]))}
+        del p_boards, p_len, p_score
     # the same call when only the episode statistics are wanted (what run_actions_max_tile returns): 256 B come back
     so_times, so_steps = [], 0
     for i in range(1 + min(args.steps, 5)):
@@ -419,9 +481,36 @@ def main():
     e2e["statistics_only"] = {"value": float(ss.item()) / float(ts.item()), "unit": "env-steps/s",
                               "d2h_bytes_per_step": int(8 * N.PLAY_STATS_WORDS)}
 
+    # ---- the other scaling mode, short: per-GPU work fixed at 2^21 envs (round 1's bench line) -----------------------
+    other = None
+    if not args.no_extras and args.scaling == "strong":
+        w_global, w_lo2, w_n = ENVS_PER_GPU * world, ENVS_PER_GPU * rank, ENVS_PER_GPU
+        w_steps = min(args.steps, 10)
+        w_elapsed, w_sum, _, w_kernel = timed_play_loop(w_global, w_lo2, w_n, 3, w_steps)
+        w_env_steps = sum(s_["env_steps"] for s_ in w_sum)
+        assert all(s_["episodes"] == w_global and s_["cut_short"] == 0 for s_ in w_sum)
+        other = {"scaling": "weak", "envs_per_gpu": ENVS_PER_GPU, "global_batch": w_global, "steps": w_steps,
+                 "value": w_env_steps / w_elapsed, "unit": "env-steps/s", "ms_per_step": 1e3 * w_elapsed / w_steps,
+                 "kernel_ms": 1e3 * w_kernel / w_steps}
+
     extras = {}
     if not args.no_extras and rank == 0:
         extras = secondary_measurements(E, N, torch, dev, flush_buf)
+        # the DRUL row of the integer roofline (C2's kernel), same probe peak
+        try:
+            d_ipe, d_src = instr_per_step("drul")
+            c2 = extras["c2_drul"]
+            d_ach = d_ipe * c2["env_steps_per_sec"] / 1e12
+            extras["roofline_drul"] = {"kernel": "play3_kernel<DRUL> (C2: 2^20 envs)", "bound": "int_issue", "achieved": d_ach,
+                                       "peak": int_peak, "unit": "Tinstr/s", "frac": d_ach / int_peak,
+                                       "instr_per_env_step": d_ipe, "instr_source": d_src,
+                                       "traffic": counts.get("drul", {}).get("dram_bytes_per_launch")}
+        except Exception as exc:  # noqa: BLE001
+            extras["roofline_drul"] = {"error": repr(exc)}
+        try:
+            extras["c4_iteration"] = c4_iteration(E, N, torch, dev, measured_hbm_peak()[0])
+        except Exception as exc:  # noqa: BLE001 -- an extra leg must not cost the bench line
+            extras["c4_iteration"] = {"error": repr(exc)}
 
     cpu_baseline = None
     if rank == 0 and world == 1:
@@ -432,8 +521,8 @@ def main():
             "sample": f"envs [0,{n_sample}) of the same {batch_global}-env batch (seed {SEED}), {reps} repetitions, "
                       "oracle C restatement with OpenMP on all host threads (Pgx/JAX not installable here)",
         }
-        # the sample doubles as a parity check of the benchmarked workload itself
-        chk = E.play(policy_id, subs, batch_global, 0, n_sample, mode, per_env=True)
+        # the sample doubles as a second parity check of the benchmarked workload itself
+        chk = E.play(policy_id, subs0, batch_global, 0, n_sample, mode, per_env=True)
         assert np.array_equal(chk["lengths"].cpu().numpy(), ref["lengths"]), "bench workload differs from the oracle"
         assert np.array_equal(E.boards_numpy(chk["final_boards"]), ref["final_boards"]), "bench workload differs from the oracle"
         cpu_baseline["parity_checked_envs"] = n_sample
@@ -442,10 +531,11 @@ def main():
         line = {
             "metric": "env_steps_per_sec", "value": value, "unit": "env-steps/s", "n_gpus": world, "steps": args.steps,
             "warmup": args.warmup, "ms_per_step": 1e3 * elapsed / args.steps, "higher_is_better": True,
-            "scaling": "weak", "vs_baseline": None, "dtype": "u64 bitboard / u32 Threefry (integer)", "data": "synthetic",
-            "config": workload_config(args, batch_global), "clocks": clocks, "e2e": e2e, "gpu_launches": gpu_launches,
-            "roofline": roofline, "cpu_baseline": cpu_baseline,
+            "scaling": args.scaling, "vs_baseline": None, "dtype": "u64 bitboard / u32 Threefry (integer)", "data": "synthetic",
+            "config": workload_config(args, world), "clocks": clocks, "e2e": e2e, "gpu_launches": gpu_launches,
+            "roofline": roofline, "cpu_baseline": cpu_baseline, "parity": parity,
             "env_steps_per_step": total_env_steps / args.steps, "mean_episode_length": total_env_steps / args.steps / batch_global,
+            "weak_scaling": other,
         }
         line.update(extras)
         print(json.dumps(line))
@@ -714,6 +804,142 @@ def secondary_measurements(E, N, torch, dev, flush_buf) -> dict:
           "seconds": dt, "loop_steps": int(out[0].shape[1]), "env_steps": int(first_done.sum()),
           "env_steps_per_sec": float(first_done.sum() / dt), "output_bytes": int(sum(a.nbytes for a in out if a is not None))}
     return {"roofline_hbm": rows, "hbm_peak_source": peak_src, "ppo_rollout": ppo, "c2_drul": c2, "c1_reference_api": c1}
+
+
+def c4_iteration(E, N, torch, dev, hbm_peak) -> dict:
+    """BASELINE.json configs[3]: the data path of one full PPO iteration at 262 144 envs, phase by phase (the learner's
+    GEMMs are PyTorch/cuBLAS and outside the product path; a random policy stands in for the network so that the
+    rollout is the product's own kernels): recorded rollout to termination + rollout-buffer write, GAE + normalisation,
+    4 epochs of 2048-sample minibatches (300 000 samples per epoch, configs/trainer/default.yaml), and the bit-exact
+    board check on a 4 096-env sample."""
+    import numpy as np
+
+    import g2048
+    from oracle import c_oracle as CO
+
+    n_envs, epochs, minibatch, max_samples = 1 << 18, 4, 2048, 300_000
+    mode = E.RNG_PARTITIONABLE
+
+    def wall(fn):
+        torch.cuda.synchronize()
+        t0 = time.perf_counter()
+        out = fn()
+        torch.cuda.synchronize()
+        return out, time.perf_counter() - t0
+
+    def dev_time(fn, reps=3):
+        fn()
+        torch.cuda.synchronize()
+        ts = []
+        for _ in range(reps):
+            a, b = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+            a.record()
+            fn()
+            b.record()
+            torch.cuda.synchronize()
+            ts.append(a.elapsed_time(b) * 1e-3)
+        return min(ts)
+
+    report = {"config": f"C4: {n_envs} envs to termination (random policy records), GAE, {epochs} epochs x {max_samples} samples in "
+                        f"minibatches of {minibatch}"}
+    # -- rollout + store: the recording play kernel writes the buffer's own layout (run_flat_batch -> store_flat) --------
+    runner = g2048.BatchRunner(init_seed=4, act_fn=g2048.act_randomly)
+    runner.run_flat_batch(n_envs)  # warm-up at full size: allocator, table build, arena sizing hint
+    runner = g2048.BatchRunner(init_seed=4, act_fn=g2048.act_randomly)
+    buf = g2048.RolloutBuffer(31, 16, 4)
+    flat, t_flat = wall(lambda: runner.run_flat_batch(n_envs))
+    _, t_store = wall(lambda: buf.store_flat(flat))
+    steps = flat.env_steps
+    # the two kernels alone, device-timed
+    subs = E.chain_advance(E.words_tensor(list(E.key_words(4)), dev), mode, 1 + 2 * 2048)
+    rec = {}
+    t_rec = dev_time(lambda: rec.update(E.play_record(E.POLICY_RANDOM, subs, n_envs, 0, n_envs, mode, mean_steps=steps // n_envs + 1)))
+    offsets = E.exclusive_scan(rec["lengths"])
+    t_cmp = dev_time(lambda: E.play_record_compact(rec, offsets, steps))
+    t_plain = dev_time(lambda: E.play(E.POLICY_RANDOM, subs, n_envs, 0, n_envs, mode, per_env=True))
+    cmp_bytes = steps * (9 + 21)
+    report["rollout_and_store"] = {
+        "seconds": t_flat + t_store, "env_steps": steps, "env_steps_per_sec": steps / (t_flat + t_store),
+        "api": "BatchRunner.run_flat_batch + RolloutBuffer.store_flat (wall clock, two host synchronisations)",
+        "play_record_kernel_ms": t_rec * 1e3, "play_record_env_steps_per_sec": steps / t_rec,
+        "play_kernel_without_records_ms": t_plain * 1e3, "recording_overhead": t_rec / t_plain - 1.0,
+        "compact_kernel_ms": t_cmp * 1e3,
+        "compact_roofline": {"bound": "hbm", "achieved": cmp_bytes / t_cmp / 1e9, "peak": hbm_peak, "unit": "GB/s",
+                             "frac": cmp_bytes / t_cmp / 1e9 / hbm_peak, "algorithmic_bytes": cmp_bytes,
+                             "note": "9 B read (board + meta) + 21 B written (board, meta, reward, log-prob, value) per kept step"},
+        "arena_bytes": int(rec["arena_boards"].numel() * 9),
+    }
+    del rec
+    # round 1's path for the same batch: lock-step recorder (every env stepped until the last one ends) + store_packed
+    r1 = g2048.BatchRunner(init_seed=4, act_fn=g2048.act_randomly)
+    r1.run_packed_batch(n_envs)
+    r1 = g2048.BatchRunner(init_seed=4, act_fn=g2048.act_randomly)
+    ro, t_lock = wall(lambda: r1.run_packed_batch(n_envs))
+    b1 = g2048.RolloutBuffer(31, 16, 4)
+    _, t_store1 = wall(lambda: b1.store_packed(ro))
+    p0, p1 = buf.get_packed(), b1.get_packed()
+    report["lock_step_recorder_plus_store_packed"] = {
+        "seconds": t_lock + t_store1, "env_steps_per_sec": steps / (t_lock + t_store1), "loop_steps": ro.t_steps,
+        "live_fraction": steps / (ro.t_steps * n_envs),
+        "flat_buffer_identical": bool(all(torch.equal(p0[k], p1[k]) for k in p0))}
+    del ro, b1, p1, r1
+    # -- GAE + normalisation + the epoch's subset ---------------------------------------------------------------------------
+    packed = buf.get_packed()
+    packed["values"].copy_(torch.randn_like(packed["values"]))  # stand-in critic outputs
+    kw = dict(batch_size=minibatch, max_samples_per_epoch=max_samples, shuffle_on_reset=True, reuse_buffers=True)
+    g2048.DevicePPOBatches(packed, 0.99, 0.95, **kw)
+    batches, t_gae = wall(lambda: g2048.DevicePPOBatches(packed, 0.99, 0.95, **kw))
+    report["gae_normalise"] = {"seconds": t_gae, "steps_per_sec": steps / t_gae,
+                               "achieved_gbs_of_algorithmic_33B_per_step": steps * 33 / t_gae / 1e9}
+
+    def run_epochs(source):
+        k = 0
+        for _ in range(epochs):
+            source.reset_epoch()
+            for b in source:
+                k += b["actions"].shape[0]
+        return k
+
+    run_epochs(batches)
+    n_samples, t_feed = wall(lambda: run_epochs(batches))
+    per_sample = 8 + 8 + 1 + 16 + 1984 + 8 + 4 + 16
+    report["minibatches"] = {"seconds": t_feed, "samples": n_samples, "samples_per_sec": n_samples / t_feed,
+                             "achieved_gbs": n_samples * per_sample / t_feed / 1e9, "frac_of_hbm": n_samples * per_sample / t_feed / 1e9 / hbm_peak,
+                             "note": "float32 observations; g2048_random_subset + g2048_gather_minibatch per minibatch, reused output tensors"}
+    batches_b = g2048.DevicePPOBatches(packed, 0.99, 0.95, obs_dtype=None, **kw)
+    run_epochs(batches_b)
+    _, t_feed_b = wall(lambda: run_epochs(batches_b))
+    report["minibatches_boards"] = {"seconds": t_feed_b, "note": "bitboards instead of observations (embedding as a row gather)"}
+    # -- bit-exact board check on a 4 096-env sample: replay the recorded actions through the oracle's step, with the
+    #    oracle's own spawn draws from the same keys; every recorded pre-step board, reward and done flag must agree
+    sample, t_chk = 4096, 200
+    _, o_subs = CO.chain(np.array(E.key_words(4), np.uint32), 1, 1 + 2 * t_chk)
+    boards, masks = CO.env_init(CO.split(o_subs[0], n_envs, 1)[:sample], 1)
+    done = np.zeros(sample, np.uint8)
+    offs = flat.offsets[: sample + 1].cpu().numpy()
+    lens = flat.lengths[:sample].cpu().numpy().astype(np.int64)
+    hi = int(offs[-1])
+    f_boards = E.boards_numpy(flat.boards[:hi])
+    f_meta = flat.meta[:hi].cpu().numpy()
+    f_rew = flat.rewards[:hi].cpu().numpy()
+    ok = True
+    for t in range(t_chk):
+        live = lens > t
+        pos = offs[:-1][live] + t
+        ok &= bool(np.array_equal(f_boards[pos], boards[live]))
+        actions = np.zeros(sample, np.int32)
+        actions[live] = f_meta[pos] & 3
+        step_keys = CO.split(o_subs[2 + 2 * t], n_envs, 1)[:sample]
+        boards, masks, done, rew = CO.env_step(boards, masks, done, actions, step_keys, 1)
+        ok &= bool(np.array_equal(rew[live], f_rew[pos]) and np.array_equal(done[live], (f_meta[pos] >> 6) & 1))
+        ok &= bool(done[~live].all())  # an env whose record has ended is finished in the oracle too
+    report["bit_exact_board_check"] = {"envs": sample, "steps": t_chk, "identical": bool(ok),
+                                       "what": "pre-step boards, rewards and done flags of the flat buffer vs the oracle's env.step "
+                                               "replayed with the recorded actions and its own spawn draws"}
+    total = t_flat + t_store + t_gae + t_feed
+    report["product_path_seconds"] = total
+    report["share"] = {k: round(v / total, 3) for k, v in (("rollout_and_store", t_flat + t_store), ("gae", t_gae), ("minibatches", t_feed))}
+    return report
 
 
 if __name__ == "__main__":

@@ -123,7 +123,13 @@ def test_rng_mode_resolution(monkeypatch):
     assert E.resolve_rng_mode("original") == E.RNG_ORIGINAL and E.resolve_rng_mode(True) == E.RNG_PARTITIONABLE
     monkeypatch.setenv("G2048_THREEFRY_PARTITIONABLE", "0")
     assert E.resolve_rng_mode(None) == E.RNG_ORIGINAL
-    assert E.key_words(42) == (0, 42) and E.key_words((7 << 32) | 9) == (7, 9)
+    # jax.random.key(seed) in jax's default 32-bit mode: the high word is always 0, negative seeds keep their
+    # two's-complement bits, anything that does not fit 32 bits raises (golden: jax.random.key(-1) -> [0, 4294967295])
+    assert E.key_words(42) == (0, 42) and E.key_words(-1) == (0, 0xFFFFFFFF) and E.key_words(0xFFFFFFFF) == (0, 0xFFFFFFFF)
+    assert E.key_words(-(1 << 31)) == (0, 0x80000000)
+    for bad in ((7 << 32) | 9, 1 << 32, -(1 << 31) - 1):
+        with pytest.raises(OverflowError):
+            E.key_words(bad)
     b = np.arange(16)[None, :] % 16
     np.testing.assert_array_equal(E.boards_numpy(torch.from_numpy(E.pack_boards(b))), b)
 

@@ -147,4 +147,4 @@ def test_store_flat_feeds_the_training_pipeline(G):
     for k in da:
         np.testing.assert_array_equal(da[k], db[k])
     n_batches = sum(1 for _ in G.DevicePPOBatches(pa, batch_size=512))
-    assert n_batches == -(-ba.buffer_size // 512)
+    assert n_batches == ba.buffer_size // 512  # drop_last
