@@ -432,7 +432,8 @@ int play_record_impl(int policy, const uint32_t* d_subs, int64_t n_subs, int64_t
 }
 
 // One warp per env: the episode's slot range -> its segment of the flat buffer (HBM-bound: 9 B read + up to 21 B
-// written per env-step; the potentials behind the rewards cost nothing next to that).
+// written per env-step; the potentials behind the rewards cost nothing next to that).  A warp takes 128 steps per
+// iteration -- the mean episode is about that long -- with every load of the iteration issued before the first use.
 template <int POLICY>
 __global__ void __launch_bounds__(256)
 play_record_compact_kernel(const u64* __restrict__ arena_boards, const uint8_t* __restrict__ arena_meta,
@@ -440,6 +441,7 @@ play_record_compact_kernel(const u64* __restrict__ arena_boards, const uint8_t* 
                            const int64_t* __restrict__ offsets, int64_t n, int64_t out_base, u64* __restrict__ o_boards,
                            uint8_t* __restrict__ o_meta, float* __restrict__ o_rewards, float* __restrict__ o_log_probs,
                            float* __restrict__ o_values, float* __restrict__ o_max_reward) {
+    constexpr int K = 4;  // 32-step groups per iteration
     const int lane = threadIdx.x & 31;
     const int64_t warps = (int64_t)gridDim.x * (blockDim.x >> 5);
     for (int64_t e = (int64_t)blockIdx.x * (blockDim.x >> 5) + (threadIdx.x >> 5); e < n; e += warps) {
@@ -447,22 +449,37 @@ play_record_compact_kernel(const u64* __restrict__ arena_boards, const uint8_t* 
         const unsigned long long src = env_slot[e];
         const int64_t dst = out_base + offsets[e];
         uint32_t best = 0;  // the trainer's "episode reward" = max_t reward (src/ppo/ppo_trainer.py:218-227)
-        for (uint32_t t0 = 0; t0 < len; t0 += 32u) {
-            const uint32_t t = t0 + (uint32_t)lane;
-            // boards t and t + 1: the neighbour lane holds the second one, lane 31 (and the last step) loads it
-            const u64 b0 = (t <= len) ? arena_boards[src + t] : 0ull;
-            u64 b1 = __shfl_down_sync(0xFFFFFFFFu, b0, 1);
-            if (lane == 31 && t < len) b1 = arena_boards[src + t + 1];
-            if (t < len) {
-                const uint32_t m = arena_meta[src + t];
-                const uint32_t gained = board_potential(b1) - board_potential(b0) - ((m & 0x80u) ? 4u : 0u);
-                const int64_t o = dst + t;
-                best = max(best, gained);
-                if (o_boards) o_boards[o] = b0;
-                if (o_meta) o_meta[o] = (uint8_t)(m & 0x7Fu);
-                if (o_rewards) o_rewards[o] = (float)gained;
-                if (o_log_probs) o_log_probs[o] = (POLICY == G2048_POLICY_RANDOM) ? act_random_log_prob((m >> 2) & 15u) : 0.0f;
-                if (o_values) o_values[o] = 0.0f;
+        for (uint32_t t0 = 0; t0 < len; t0 += 32u * K) {
+            // slots t0 .. t0 + 32 K (one more board than steps: the reward of a step needs the next board)
+            u64 b[K + 1];
+            uint32_t m[K];
+#pragma unroll
+            for (int k = 0; k < K; ++k) {
+                const uint32_t t = t0 + 32u * k + (uint32_t)lane;
+                b[k] = (t <= len) ? __ldg(&arena_boards[src + t]) : 0ull;
+                m[k] = (t < len) ? (uint32_t)__ldg(&arena_meta[src + t]) : 0u;
+            }
+            {
+                const uint32_t t = t0 + 32u * K;  // lane 0 fetches the board after the iteration's last step
+                b[K] = (lane == 0 && t <= len) ? __ldg(&arena_boards[src + t]) : 0ull;
+            }
+#pragma unroll
+            for (int k = 0; k < K; ++k) {
+                const uint32_t t = t0 + 32u * k + (uint32_t)lane;
+                u64 b1 = __shfl_down_sync(0xFFFFFFFFu, b[k], 1);
+                const u64 first_of_next = __shfl_sync(0xFFFFFFFFu, b[k + 1], 0);
+                if (lane == 31) b1 = first_of_next;
+                if (t < len) {
+                    const uint32_t gained = board_potential(b1) - board_potential(b[k]) - ((m[k] & 0x80u) ? 4u : 0u);
+                    const int64_t o = dst + t;
+                    best = max(best, gained);
+                    if (o_boards) o_boards[o] = b[k];
+                    if (o_meta) o_meta[o] = (uint8_t)(m[k] & 0x7Fu);
+                    if (o_rewards) o_rewards[o] = (float)gained;
+                    if (o_log_probs)
+                        o_log_probs[o] = (POLICY == G2048_POLICY_RANDOM) ? act_random_log_prob((m[k] >> 2) & 15u) : 0.0f;
+                    if (o_values) o_values[o] = 0.0f;
+                }
             }
         }
         if (o_max_reward) {

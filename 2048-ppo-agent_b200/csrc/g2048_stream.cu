@@ -41,9 +41,28 @@ struct GatherScalars {
     float *o_log_probs, *o_values, *o_adv, *o_ret;
     const unsigned long long* boards;  // stand-alone scalar kernel only (no observations: the batch carries bitboards)
     unsigned long long* o_boards;
+    // sample-record form (g2048_pack_samples): every field of a sample sits in ONE 32-byte sector -- two 16-byte loads
+    // per sample instead of one sector per source array; the pointers above are ignored when this is set
+    const uint4* records;
 };
 
+// G2048SampleRecord (include/g2048.h): {board u64, meta u32, reward f32 | log_prob, value, advantage, return f32}
+__device__ __forceinline__ void gather_record_at(const GatherScalars& g, const int64_t* __restrict__ idx, int64_t i) {
+    const int64_t s = __ldg(&idx[i]);
+    const uint4 h0 = __ldg(&g.records[2 * s]);
+    const uint4 h1 = __ldg(&g.records[2 * s + 1]);
+    const uint32_t mt = h0.z;
+    if (g.o_actions) g.o_actions[i] = (int64_t)(mt & 3u);
+    if (g.o_masks) g.o_masks[i] = make_uchar4((mt >> 2) & 1u, (mt >> 3) & 1u, (mt >> 4) & 1u, (mt >> 5) & 1u);
+    if (g.o_log_probs) g.o_log_probs[i] = __uint_as_float(h1.x);
+    if (g.o_values) g.o_values[i] = __uint_as_float(h1.y);
+    if (g.o_adv) g.o_adv[i] = __uint_as_float(h1.z);
+    if (g.o_ret) g.o_ret[i] = __uint_as_float(h1.w);
+    if (g.o_boards) g.o_boards[i] = ((unsigned long long)h0.y << 32) | (unsigned long long)h0.x;
+}
+
 __device__ __forceinline__ void gather_scalars_at(const GatherScalars& g, const int64_t* __restrict__ idx, int64_t i) {
+    if (g.records) return gather_record_at(g, idx, i);
     const int64_t s = __ldg(&idx[i]);
     const uint32_t mt = g.meta ? g.meta[s] : 0u;
     const float lp = (g.o_log_probs && g.log_probs) ? g.log_probs[s] : 0.0f;
@@ -66,7 +85,7 @@ __device__ __forceinline__ void gather_scalars_at(const GatherScalars& g, const 
 template <typename T, bool AHEAD, bool SCALARS = false>
 __global__ void __launch_bounds__(OBS_THREADS)
 expand_obs_tma_kernel(const u64* __restrict__ boards, int64_t n, T* __restrict__ out, int64_t rows, int64_t n_cols,
-                      const int64_t* __restrict__ indices, const GatherScalars sc = GatherScalars{}) {
+                      const int64_t* __restrict__ indices, const GatherScalars sc = GatherScalars{}, int board_stride = 1) {
     constexpr int G = OBS_IMAGE_BYTES / (496 * (int)sizeof(T));  // boards per image
     constexpr int CELLS = 16 * G;
     constexpr int PER_LANE = (CELLS + 31) / 32;
@@ -93,7 +112,7 @@ expand_obs_tma_kernel(const u64* __restrict__ boards, int64_t n, T* __restrict__
             src = (src - col * rows) * n_cols + col;
         }
         if (indices) src = __ldg(&indices[src]);  // gather: out[i] = onehot(boards[indices[i]])
-        return __ldg(&boards[src]);
+        return __ldg(&boards[src * board_stride]);  // stride 4: the board of a 32-byte sample record
     };
     int64_t img = (int64_t)blockIdx.x * OBS_WARPS + warp;
     while (img < n_images) {
@@ -157,7 +176,8 @@ using namespace g2048;
 static inline bool aligned16(const void* p) { return ((uintptr_t)p & 15u) == 0; }
 
 static int launch_expand_obs(const uint64_t* d_boards, int64_t n, int dtype, void* d_out, int64_t rows, int64_t n_cols,
-                             const int64_t* d_indices, void* stream, const GatherScalars* scalars = nullptr) {
+                             const int64_t* d_indices, void* stream, const GatherScalars* scalars = nullptr,
+                             int board_stride = 1) {
     G2048_REQUIRE(n >= 0 && rows >= 0 && (rows == 0 || (n_cols > 0 && rows * n_cols == n)), "expand_obs: shape");
     G2048_REQUIRE(!scalars || (d_indices && rows == 0), "expand_obs: scalars need an index list");
     if (n == 0) return G2048_OK;
@@ -193,7 +213,7 @@ static int launch_expand_obs(const uint64_t* d_boards, int64_t n, int dtype, voi
     do {                                                                                                                \
         if (scalars)                                                                                                    \
             expand_obs_tma_kernel<T, true, true><<<grid_for(images), OBS_THREADS, OBS_SMEM_BYTES, st>>>(                \
-                (const u64*)d_boards, n, (T*)d_out, rows, n_cols, d_indices, *scalars);                                 \
+                (const u64*)d_boards, n, (T*)d_out, rows, n_cols, d_indices, *scalars, board_stride);                   \
         else if (ahead)                                                                                                 \
             expand_obs_tma_kernel<T, true><<<grid_for(images), OBS_THREADS, OBS_SMEM_BYTES, st>>>(                      \
                 (const u64*)d_boards, n, (T*)d_out, rows, n_cols, d_indices);                                           \
@@ -240,8 +260,12 @@ gather_scalars_kernel(const int64_t* __restrict__ idx, int64_t m, const uint8_t*
     const int64_t i = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
     if (i >= m) return;
     gather_scalars_at(GatherScalars{meta, log_probs, values, adv, ret, o_actions, o_masks, o_log_probs, o_values, o_adv, o_ret,
-                                    boards, o_boards},
+                                    boards, o_boards, nullptr},
                       idx, i);
+}
+__global__ void __launch_bounds__(256) gather_records_kernel(const int64_t* __restrict__ idx, int64_t m, const GatherScalars sc) {
+    const int64_t i = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
+    if (i < m) gather_record_at(sc, idx, i);
 }
 }  // namespace g2048
 
@@ -257,12 +281,89 @@ extern "C" int g2048_gather_minibatch(const int64_t* d_indices, int64_t m, const
     if (d_obs) {  // one launch: the observation kernel gathers the scalars while its last stores drain
         const g2048::GatherScalars sc{d_meta, d_log_probs, d_values, d_adv, d_ret, d_actions, (uchar4*)d_masks,
                                       d_old_log_probs, d_old_values, d_out_adv, d_out_ret,
-                                      (const unsigned long long*)d_boards, (unsigned long long*)d_out_boards};
+                                      (const unsigned long long*)d_boards, (unsigned long long*)d_out_boards, nullptr};
         return launch_expand_obs(d_boards, m, obs_dtype, d_obs, 0, 0, d_indices, stream, &sc);
     }
     g2048::gather_scalars_kernel<<<blocks_for(m, 256), 256, 0, (cudaStream_t)stream>>>(
         d_indices, m, d_meta, d_log_probs, d_values, d_adv, d_ret, d_actions, (uchar4*)d_masks, d_old_log_probs,
         d_old_values, d_out_adv, d_out_ret, (const unsigned long long*)d_boards, (unsigned long long*)d_out_boards);
     G2048_CHECK_LAUNCH("gather_minibatch");
+    return G2048_OK;
+}
+
+// ------------------------------------------------------------------------------------------------
+// sample records: the training view of the flat buffer, one 32-byte sector per sample
+// ------------------------------------------------------------------------------------------------
+namespace g2048 {
+
+// x -> (x - mean) / (std_unbiased + 1e-8) exactly as normalize_kernel (g2048_gae.cu) computes it
+struct NormParams {
+    float mean, denom;
+};
+__device__ __forceinline__ NormParams norm_params(const double* __restrict__ moments, int which) {
+    const double cnt = moments[0];
+    const double sum = moments[which], sumsq = moments[which + 1];
+    const double mean_d = sum / cnt;
+    const double var_d = (sumsq - sum * mean_d) / (cnt - 1.0);
+    return NormParams{(float)mean_d, (float)sqrt(var_d > 0.0 ? var_d : 0.0) + 1e-8f};
+}
+
+__global__ void __launch_bounds__(256)
+pack_samples_kernel(const u64* __restrict__ boards, const uint8_t* __restrict__ meta, const float* __restrict__ rewards,
+                    const float* __restrict__ log_probs, const float* __restrict__ values, const float* __restrict__ adv,
+                    const float* __restrict__ ret, int64_t n, const double* __restrict__ moments, uint4* __restrict__ records) {
+    NormParams na{0.0f, 1.0f}, nr{0.0f, 1.0f};
+    if (moments) {
+        na = norm_params(moments, 1);
+        nr = norm_params(moments, 3);
+    }
+    const int64_t stride = (int64_t)gridDim.x * blockDim.x;
+    for (int64_t i = (int64_t)blockIdx.x * blockDim.x + threadIdx.x; i < n; i += stride) {
+        const u64 b = boards[i];
+        float a = adv ? adv[i] : 0.0f, r = ret ? ret[i] : 0.0f;
+        if (moments) {
+            a = (a - na.mean) / na.denom;
+            r = (r - nr.mean) / nr.denom;
+        }
+        records[2 * i] = make_uint4((uint32_t)b, (uint32_t)(b >> 32), (uint32_t)meta[i],
+                                    __float_as_uint(rewards ? rewards[i] : 0.0f));
+        records[2 * i + 1] = make_uint4(__float_as_uint(log_probs ? log_probs[i] : 0.0f), __float_as_uint(values ? values[i] : 0.0f),
+                                        __float_as_uint(a), __float_as_uint(r));
+    }
+}
+
+}  // namespace g2048
+
+extern "C" int g2048_pack_samples(const uint64_t* d_boards, const uint8_t* d_meta, const float* d_rewards,
+                                  const float* d_log_probs, const float* d_values, const float* d_adv, const float* d_ret,
+                                  int64_t n, const double* d_moments, G2048SampleRecord* d_records, void* stream) {
+    G2048_REQUIRE(n >= 0, "pack_samples: n");
+    if (n == 0) return G2048_OK;
+    G2048_REQUIRE(d_boards && d_meta && d_records && aligned16(d_records), "pack_samples: pointers (records 16-byte aligned)");
+    const int sms = sm_count();
+    if (sms <= 0) return fail_arg("pack_samples: no device");
+    int64_t g = (n + 255) / 256;
+    const int64_t cap = (int64_t)sms * 8 * 4;
+    if (g > cap) g = cap;
+    g2048::pack_samples_kernel<<<(unsigned)g, 256, 0, (cudaStream_t)stream>>>(
+        (const g2048::u64*)d_boards, d_meta, d_rewards, d_log_probs, d_values, d_adv, d_ret, n, d_moments, (uint4*)d_records);
+    G2048_CHECK_LAUNCH("pack_samples");
+    return G2048_OK;
+}
+
+extern "C" int g2048_gather_samples(const int64_t* d_indices, int64_t m, const G2048SampleRecord* d_records, int obs_dtype,
+                                    void* d_obs, int64_t* d_actions, uint8_t* d_masks, float* d_old_log_probs,
+                                    float* d_old_values, float* d_out_adv, float* d_out_ret, uint64_t* d_out_boards,
+                                    void* stream) {
+    G2048_REQUIRE(m >= 0, "gather_samples: m");
+    if (m == 0) return G2048_OK;
+    G2048_REQUIRE(d_indices && d_records && aligned16(d_records), "gather_samples: pointers (records 16-byte aligned)");
+    const g2048::GatherScalars sc{nullptr, nullptr, nullptr, nullptr, nullptr, d_actions, (uchar4*)d_masks, d_old_log_probs,
+                                  d_old_values, d_out_adv, d_out_ret, nullptr, (unsigned long long*)d_out_boards,
+                                  (const uint4*)d_records};
+    if (d_obs)  // the observation kernel reads the board out of the record (stride 4 words) and gathers the rest at its end
+        return launch_expand_obs((const uint64_t*)d_records, m, obs_dtype, d_obs, 0, 0, d_indices, stream, &sc, 4);
+    g2048::gather_records_kernel<<<blocks_for(m, 256), 256, 0, (cudaStream_t)stream>>>(d_indices, m, sc);
+    G2048_CHECK_LAUNCH("gather_samples");
     return G2048_OK;
 }

@@ -538,6 +538,37 @@ def gather_minibatch(indices: torch.Tensor, packed: dict, adv: torch.Tensor | No
     return {k: v for k, v in out.items() if v is not None}
 
 
+SAMPLE_RECORD = np.dtype([("board", "<u8"), ("meta", "<u4"), ("reward", "<f4"), ("log_prob", "<f4"), ("value", "<f4"),
+                          ("advantage", "<f4"), ("ret", "<f4")])  # G2048SampleRecord (include/g2048.h), 32 bytes
+
+
+def pack_samples(packed: dict, adv: torch.Tensor | None, ret: torch.Tensor | None, moments: torch.Tensor | None = None,
+                 out: torch.Tensor | None = None) -> torch.Tensor:
+    """Flat packed buffer (+ advantages / returns) -> (n, 4) int64 tensor of 32-byte sample records
+    (G2048SampleRecord).  moments (the fp64 block gae_flat fills): normalise advantages and returns on the way, exactly as
+    normalize_ would."""
+    n = packed["boards"].shape[0]
+    if out is None:
+        out = torch.empty((n, 4), dtype=torch.int64, device=packed["boards"].device)
+    call("g2048_pack_samples", ptr(packed["boards"]), ptr(packed["meta"]), ptr(packed.get("rewards")), ptr(packed.get("log_probs")),
+         ptr(packed.get("values")), ptr(adv), ptr(ret), n, ptr(moments), ptr(out), stream_ptr())
+    return out
+
+
+def gather_samples(indices: torch.Tensor, records: torch.Tensor, obs_dtype=torch.float32, out: dict | None = None,
+                   with_gae: bool = True) -> dict:
+    """gather_minibatch reading 32-byte sample records (pack_samples): one sector per sample."""
+    m = indices.shape[0]
+    if out is None:
+        out = minibatch_buffers(m, indices.device, obs_dtype, with_gae)
+    else:
+        out = dict(out)
+    call("g2048_gather_samples", ptr(indices), m, ptr(records), _OBS_DTYPES[obs_dtype or torch.float32], ptr(out["observations"]),
+         ptr(out["actions"]), ptr(out["action_masks"]), ptr(out["log_probs"]), ptr(out["values"]), ptr(out["advantages"]),
+         ptr(out["returns"]), ptr(out["boards"]) if obs_dtype is None else None, stream_ptr())
+    return {k: v for k, v in out.items() if v is not None}
+
+
 # ------------------------------------------------------------------------------------------- embedding
 def embed_boards(boards: torch.Tensor, table: torch.Tensor, indices: torch.Tensor | None = None, out=None,
                  entry: str = "g2048_embed_boards") -> torch.Tensor:

@@ -53,7 +53,8 @@ class KeyChain:
             words = np.array(E.key_words(int(seed_or_key)), dtype=np.uint32)
         else:
             words = np.asarray(seed_or_key, dtype=np.uint32).reshape(2).copy()
-        self._base_key = words  # chain key at absolute position self._base_pos
+        self._base_key = words  # chain key at absolute position self._base_pos - self._pending
+        self._pending = 0  # splits consumed since _base_key was last materialised (see `key`)
         self._base_pos = 0  # number of splits consumed so far
         self._subs = torch.empty((0, 2), dtype=torch.int32, device=self.device)  # subs from _base_pos on
         self._tip = E.words_tensor(words, self.device)  # chain key after all generated subs
@@ -67,13 +68,12 @@ class KeyChain:
         return self._subs[:n]
 
     def consume(self, n: int) -> None:
+        """Advance by n splits.  Nothing runs on the device: the sub keys were generated ahead by peek(), and the
+        chain key itself (``key``) is only replayed when somebody asks for it."""
         if n <= 0:
             return
         self.peek(n)
-        # the chain key after n more splits: replay from the base key (cheap, and only done here)
-        base = E.words_tensor(self._base_key, self.device)
-        E.chain_advance(base, self.rng_mode, n)
-        self._base_key = E.words_numpy(base).copy()
+        self._pending += n
         self._base_pos += n
         self._subs = self._subs[n:]
 
@@ -84,6 +84,13 @@ class KeyChain:
 
     @property
     def key(self) -> np.ndarray:
+        """The chain key after everything consumed so far (the reference runner's ``self.key``): replayed from the last
+        materialised key over the pending splits -- one small kernel and one 8-byte read, off the rollout's path."""
+        if self._pending:
+            base = E.words_tensor(self._base_key, self.device)
+            E.chain_advance(base, self.rng_mode, self._pending)
+            self._base_key = E.words_numpy(base).copy()
+            self._pending = 0
         return self._base_key.copy()
 
     @property

@@ -591,18 +591,27 @@ def secondary_measurements(E, N, torch, dev, flush_buf) -> dict:
     g_adv, g_ret = torch.rand(n_buf, device=dev), torch.rand(n_buf, device=dev)
     idx = torch.randperm(n_buf, device=dev)[:m].contiguous()
     mb_out = E.minibatch_buffers(m, dev)
+    # sample records: every field of a sample in one 32-byte sector (g2048_pack_samples, once per iteration)
+    packed["rewards"] = g_adv
+    mom_p = torch.tensor([n_buf, 0.5 * n_buf, 0.34 * n_buf, 0.5 * n_buf, 0.34 * n_buf, 0.0], dtype=torch.float64, device=dev)
+    records = torch.empty((n_buf, 4), dtype=torch.int64, device=dev)
+    t = timed(lambda: E.pack_samples(packed, g_adv, g_ret, mom_p, out=records))
+    add("pack_samples_kernel", n_buf * (25 + 32), t, "2^22 steps: 25 B read (board, meta, reward, log-prob, value, advantage, return) + one 32 B sample record written per step, normalisation applied on the way")
+    per_sample = 8 + 32 + 1984 + 8 + 4 + 16
+    t = timed(lambda: E.gather_samples(idx, records, out=mb_out))
+    add("gather_samples (expand_obs_tma<float, gathered, sample records>)", m * per_sample, t,
+        "65536 random samples: 8 B index + ONE 32 B record read + 2012 B written per sample; one launch into reused output tensors; 134 MB in all, a launch-bound size")
     t = timed(lambda: E.gather_minibatch(idx, packed, g_adv, g_ret, out=mb_out))
-    add("gather_minibatch (expand_obs_tma<float, gathered, with scalars>)", m * (8 + 8 + 1 + 16 + 1984 + 8 + 4 + 16), t,
-        "65536 random samples: 33 B gathered + 2012 B written per sample; ONE launch (the observation kernel gathers the scalars while its last bulk stores drain) into reused output tensors; 134 MB in all, a launch-bound size")
+    add("gather_minibatch (round 1: one source array per field)", m * (8 + 8 + 1 + 16 + 1984 + 8 + 4 + 16), t,
+        "the same minibatch gathered from the six flat arrays (one sector per array and sample)")
     del mb_out
-    # the same at a size that is not launch-bound (2^19 samples, 1.07 GB): what the two kernels do once they are busy
+    # the same at a size that is not launch-bound (2^19 samples, 1.07 GB): what the kernel does once it is busy
     m_big = 1 << 19
     idx_big = torch.randint(0, n_buf, (m_big,), device=dev)
     mb_big = E.minibatch_buffers(m_big, dev)
-    t = timed(lambda: E.gather_minibatch(idx_big, packed, g_adv, g_ret, out=mb_big))
-    add("gather_minibatch, 2^19 samples", m_big * (8 + 8 + 1 + 16 + 1984 + 8 + 4 + 16), t,
-        "same kernel, 8 x the samples: 1.07 GB written")
-    del mb_big, idx_big
+    t = timed(lambda: E.gather_samples(idx_big, records, out=mb_big))
+    add("gather_samples, 2^19 samples", m_big * per_sample, t, "same kernel, 8 x the samples: 1.07 GB written")
+    del mb_big, idx_big, records
     del packed, g_adv, g_ret, idx
 
     # packed boards -> input embedding: 2^18 boards, d_model 256 (configs/model/transformer_combined.yaml)
@@ -890,7 +899,10 @@ def c4_iteration(E, N, torch, dev, hbm_peak) -> dict:
     g2048.DevicePPOBatches(packed, 0.99, 0.95, **kw)
     batches, t_gae = wall(lambda: g2048.DevicePPOBatches(packed, 0.99, 0.95, **kw))
     report["gae_normalise"] = {"seconds": t_gae, "steps_per_sec": steps / t_gae,
-                               "achieved_gbs_of_algorithmic_33B_per_step": steps * 33 / t_gae / 1e9}
+                               "algorithmic_bytes_per_step": 17 + 25 + 32,
+                               "achieved_gbs": steps * (17 + 25 + 32) / t_gae / 1e9, "frac_of_hbm": steps * (17 + 25 + 32) / t_gae / 1e9 / hbm_peak,
+                               "note": "g2048_gae_flat (9 B read + 8 B written per step) + g2048_pack_samples (25 B read, 32 B sample "
+                                       "record written, normalisation applied on the way) + the first epoch's g2048_random_subset; wall clock"}
 
     def run_epochs(source):
         k = 0
@@ -901,12 +913,18 @@ def c4_iteration(E, N, torch, dev, hbm_peak) -> dict:
         return k
 
     run_epochs(batches)
-    n_samples, t_feed = wall(lambda: run_epochs(batches))
-    per_sample = 8 + 8 + 1 + 16 + 1984 + 8 + 4 + 16
+    n_samples, t_feed_each = wall(lambda: run_epochs(batches))
+    batches_e = g2048.DevicePPOBatches(packed, 0.99, 0.95, epoch_prefetch=True, **kw)
+    run_epochs(batches_e)
+    _, t_feed = wall(lambda: run_epochs(batches_e))
+    per_sample = 8 + 32 + 1984 + 8 + 4 + 16
     report["minibatches"] = {"seconds": t_feed, "samples": n_samples, "samples_per_sec": n_samples / t_feed,
                              "achieved_gbs": n_samples * per_sample / t_feed / 1e9, "frac_of_hbm": n_samples * per_sample / t_feed / 1e9 / hbm_peak,
-                             "note": "float32 observations; g2048_random_subset + g2048_gather_minibatch per minibatch, reused output tensors"}
-    batches_b = g2048.DevicePPOBatches(packed, 0.99, 0.95, obs_dtype=None, **kw)
+                             "seconds_one_launch_per_minibatch": t_feed_each,
+                             "note": "float32 observations; per epoch one g2048_random_subset + ONE g2048_gather_samples launch for all "
+                                     "of the epoch's samples (DevicePPOBatches(epoch_prefetch=True)), minibatches are views; "
+                                     "seconds_one_launch_per_minibatch = the same with a gather launch per minibatch"}
+    batches_b = g2048.DevicePPOBatches(packed, 0.99, 0.95, obs_dtype=None, epoch_prefetch=True, **kw)
     run_epochs(batches_b)
     _, t_feed_b = wall(lambda: run_epochs(batches_b))
     report["minibatches_boards"] = {"seconds": t_feed_b, "note": "bitboards instead of observations (embedding as a row gather)"}

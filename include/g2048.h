@@ -345,6 +345,25 @@ int g2048_gather_minibatch(const int64_t* d_indices, int64_t m, const uint64_t* 
                            int obs_dtype, void* d_obs, int64_t* d_actions, uint8_t* d_masks, float* d_old_log_probs,
                            float* d_old_values, float* d_out_adv, float* d_out_ret, uint64_t* d_out_boards, void* stream);
 
+/* Sample records: the training view of the flat buffer with every field of a sample in ONE 32-byte sector, so that a
+ * random minibatch costs one sector per sample instead of one per source array (six).  g2048_pack_samples builds them
+ * in one pass that also applies the global normalisation of src/ppo/data_loader.py:61-67 to advantages and returns
+ * (d_moments as written by g2048_gae_flat; NULL = store d_adv / d_ret as they are), replacing the two g2048_normalize
+ * passes; g2048_gather_samples is g2048_gather_minibatch reading them.  d_rewards / d_log_probs / d_values / d_adv /
+ * d_ret may be NULL (stored as 0). */
+typedef struct G2048SampleRecord {
+    uint64_t board;   /* pre-step bitboard */
+    uint32_t meta;    /* low byte: action | legal mask << 2 | done << 6 */
+    float reward;
+    float log_prob, value, advantage, ret; /* second 16-byte half */
+} G2048SampleRecord;
+int g2048_pack_samples(const uint64_t* d_boards, const uint8_t* d_meta, const float* d_rewards, const float* d_log_probs,
+                       const float* d_values, const float* d_adv, const float* d_ret, int64_t n, const double* d_moments,
+                       G2048SampleRecord* d_records, void* stream);
+int g2048_gather_samples(const int64_t* d_indices, int64_t m, const G2048SampleRecord* d_records, int obs_dtype, void* d_obs,
+                         int64_t* d_actions, uint8_t* d_masks, float* d_old_log_probs, float* d_old_values, float* d_out_adv,
+                         float* d_out_ret, uint64_t* d_out_boards, void* stream);
+
 /* Random subset / shuffle of buffer positions (replaces torch.randperm(total_length)[:length] and the DataLoader's
  * shuffle, src/ppo/data_loader.py:73-101,217-223): d_out[i] = P(first + i) for i < m, where P is a pseudo-random
  * bijection of [0, n) selected by the key -- a 4-round Feistel network over 2h bits (4^h >= n) whose round function
