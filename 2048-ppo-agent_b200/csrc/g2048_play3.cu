@@ -29,7 +29,19 @@ namespace g2048 {
 constexpr int PLAY3_EPILOGUE_BATCH = G2048_PLAY3_EPILOGUE_BATCH;  // parked finished episodes per epilogue run
 constexpr int PLAY3_THREADS = G2048_PLAY3_THREADS;  // one CTA per SM; 512 / 768 / 1024 threads measured within 3 % of each other, 512 best (shorter tail)
 constexpr int PLAY3_TABLE_BYTES = 65536 * 2 + 65536;
-constexpr int PLAY3_SMEM_BYTES = PLAY3_TABLE_BYTES + G2048_PLAY_STATS_WORDS * 8;
+#ifndef G2048_PLAY3_TAIL_STEPS
+#define G2048_PLAY3_TAIL_STEPS 8
+#endif
+constexpr int PLAY3_TAIL_STEPS = G2048_PLAY3_TAIL_STEPS;  // steps between two compactions of the CTA's live envs in the tail
+// what moves with an env when the tail compaction hands it to another lane (32 bytes)
+struct TailEntry {
+    unsigned long long board;
+    unsigned long long slot;  // recording: the env's next arena slot (it keeps writing into its first lane's region)
+    uint32_t e, t, fours, flags;  // flags: bits 0-1 phase, bit 2 seen15
+};
+constexpr int PLAY3_STATS_BYTES = G2048_PLAY_STATS_WORDS * 8;
+constexpr int PLAY3_CTL_BYTES = 16;  // tail flag, two alternating live-env counters
+constexpr int PLAY3_SMEM_BYTES = PLAY3_TABLE_BYTES + PLAY3_STATS_BYTES + PLAY3_CTL_BYTES + PLAY3_THREADS * (int)sizeof(TailEntry);
 
 __device__ uint16_t g_row_left[65536];  // row slid and merged toward nibble 0
 __device__ uint8_t g_row_flags[65536];  // bit 0: the row changes when moved toward nibble 0, bit 2: toward nibble 3
@@ -96,6 +108,9 @@ play3_kernel(const uint2* __restrict__ subs, int64_t n_subs, uint32_t batch_glob
     const uint16_t* s_left = reinterpret_cast<const uint16_t*>(smem_raw);
     const uint8_t* s_flags = smem_raw + 65536 * 2;
     unsigned long long* s_stats = reinterpret_cast<unsigned long long*>(smem_raw + PLAY3_TABLE_BYTES);
+    volatile unsigned* s_tail_flag = reinterpret_cast<volatile unsigned*>(smem_raw + PLAY3_TABLE_BYTES + PLAY3_STATS_BYTES);
+    unsigned* s_tail_cnt = reinterpret_cast<unsigned*>(smem_raw + PLAY3_TABLE_BYTES + PLAY3_STATS_BYTES) + 1;  // [2]
+    TailEntry* s_pool = reinterpret_cast<TailEntry*>(smem_raw + PLAY3_TABLE_BYTES + PLAY3_STATS_BYTES + PLAY3_CTL_BYTES);
 
     {  // tables: global (L2) -> shared, 12 x 16 bytes per thread
         const uint4* src_left = reinterpret_cast<const uint4*>(g_row_left);
@@ -104,6 +119,7 @@ play3_kernel(const uint2* __restrict__ subs, int64_t n_subs, uint32_t batch_glob
         for (int i = threadIdx.x; i < 65536 * 2 / 16; i += PLAY3_THREADS) dst[i] = __ldg(&src_left[i]);
         for (int i = threadIdx.x; i < 65536 / 16; i += PLAY3_THREADS) dst[65536 * 2 / 16 + i] = __ldg(&src_flags[i]);
         for (int i = threadIdx.x; i < G2048_PLAY_STATS_WORDS; i += PLAY3_THREADS) s_stats[i] = 0ull;
+        if (threadIdx.x < 4) reinterpret_cast<unsigned*>(smem_raw + PLAY3_TABLE_BYTES + PLAY3_STATS_BYTES)[threadIdx.x] = 0u;
     }
     __syncthreads();
 
@@ -157,54 +173,36 @@ play3_kernel(const uint2* __restrict__ subs, int64_t n_subs, uint32_t batch_glob
         }
     };
 
-    while (true) {
-        // ---- hand the next envs of the queue to the lanes that have none --------------------------
-        const unsigned idle = __ballot_sync(0xFFFFFFFFu, phase == PHASE_NONE);
-        // a recording lane takes a new env only while a whole episode still fits into its arena region
-        const bool can_take = !REC || slot + (unsigned long long)max_steps + 1ull <= slot_end;
-        const unsigned want = REC ? __ballot_sync(0xFFFFFFFFu, phase == PHASE_NONE && can_take) : idle;
-        if (idle) {
-            // park what the lanes that just finished still hold (all lanes are converged here)
-            const unsigned fresh = __ballot_sync(0xFFFFFFFFu, fin_live);
-            if (fresh) {
-                const unsigned parked = __ballot_sync(0xFFFFFFFFu, pk_has);
-                if ((fresh & parked) != 0u || __popc(fresh | parked) >= PLAY3_EPILOGUE_BATCH) epilogue();
-                if (fin_live) {
-                    pk_board = board;
-                    pk_t = t;
-                    pk_fours = fours;
-                    pk_e = e;
-                    pk_cut = fin_cut;
-                    pk_seen15 = seen15;
-                    pk_has = true;
-                    fin_live = false;
-                }
+    // park what the lanes that just finished still hold (call converged)
+    auto park_finished = [&]() {
+        const unsigned fresh = __ballot_sync(0xFFFFFFFFu, fin_live);
+        if (fresh) {
+            const unsigned parked = __ballot_sync(0xFFFFFFFFu, pk_has);
+            if ((fresh & parked) != 0u || __popc(fresh | parked) >= PLAY3_EPILOGUE_BATCH) epilogue();
+            if (fin_live) {
+                pk_board = board;
+                pk_t = t;
+                pk_fours = fours;
+                pk_e = e;
+                pk_cut = fin_cut;
+                pk_seen15 = seen15;
+                pk_has = true;
+                fin_live = false;
             }
-            if (!exhausted && want) {
-                const int cnt = __popc(want);
-                unsigned long long base = 0;
-                if (lane == 0) base = atomicAdd(work, (unsigned long long)cnt);
-                base = __shfl_sync(0xFFFFFFFFu, base, 0);
-                if (base + (unsigned long long)cnt >= (unsigned long long)n) exhausted = true;
-                if (phase == PHASE_NONE && (!REC || can_take)) {
-                    const unsigned long long mine = base + (unsigned long long)__popc(want & ((1u << lane) - 1u));
-                    if (mine < (unsigned long long)n) {
-                        e = (uint32_t)mine;
-                        board = 0ull;
-                        boardT = 0ull;
-                        lm = 0;
-                        t = 0;
-                        fours = 0;
-                        seen15 = false;
-                        phase = PHASE_INIT0;
-                    }
-                }
-            }
-            if (__ballot_sync(0xFFFFFFFFu, phase != PHASE_NONE) == 0u) break;
         }
-        if (phase == PHASE_NONE) continue;  // only at the tail of the launch, when the queue is empty
+    };
+    // exact legal mask: "row can move left / right" for the 4 rows and the 4 columns
+    auto legal_from_tables = [&](u64 b, u64 bT) -> uint32_t {
+        const uint32_t blo = (uint32_t)b, bhi = (uint32_t)(b >> 32);
+        const uint32_t tlo = (uint32_t)bT, thi = (uint32_t)(bT >> 32);
+        const uint32_t fb = s_flags[blo & 0xFFFFu] | s_flags[blo >> 16] | s_flags[bhi & 0xFFFFu] | s_flags[bhi >> 16];
+        const uint32_t ft = s_flags[tlo & 0xFFFFu] | s_flags[tlo >> 16] | s_flags[thi & 0xFFFFu] | s_flags[thi >> 16];
+        return fb | (ft << 1);  // rows give Left (bit 0) and Right (bit 2), columns the same bits one up: Up (1), Down (3)
+    };
 
-        // ---- keys: identical to g2048_play.cu ----------------------------------------------------------
+    // ---- one loop iteration of a lane that holds an env: a game step, or one of the two init spawns -------------------
+    auto step = [&]() {
+        // keys: identical to g2048_play.cu
         const bool playing = phase == PHASE_PLAY;
         const uint2 ss = __ldg(&subs[2 + 2 * (int64_t)t]);
         int action;
@@ -258,16 +256,11 @@ play3_kernel(const uint2* __restrict__ subs, int64_t n_subs, uint32_t batch_glob
         board = nb | (val << (4 * cell));      // the chosen cell is empty (or, on a full board, only reachable
         boardT = nbT | (val << (4 * cellT));   //  through illegal actions which these policies never take)
         fours += (val == 2ull) ? 1u : 0u;
-        // ---- exact legal mask: "row can move left / right" for the 4 rows and the 4 columns -------------------
-        const uint32_t blo = (uint32_t)board, bhi = (uint32_t)(board >> 32);
-        const uint32_t tlo = (uint32_t)boardT, thi = (uint32_t)(boardT >> 32);
-        const uint32_t fb = s_flags[blo & 0xFFFFu] | s_flags[blo >> 16] | s_flags[bhi & 0xFFFFu] | s_flags[bhi >> 16];
-        const uint32_t ft = s_flags[tlo & 0xFFFFu] | s_flags[tlo >> 16] | s_flags[thi & 0xFFFFu] | s_flags[thi >> 16];
-        lm = fb | (ft << 1);  // rows give Left (bit 0) and Right (bit 2), columns the same bits one up: Up (1), Down (3)
+        lm = legal_from_tables(board, boardT);
 
         if (!playing) {
             phase += 1;  // INIT0 -> INIT1 -> PLAY
-            continue;
+            return;
         }
         ++t;
         const bool done = lm == 0u;
@@ -287,6 +280,88 @@ play3_kernel(const uint2* __restrict__ subs, int64_t n_subs, uint32_t batch_glob
                 rec.env_slot[e] = slot - (unsigned long long)t;
                 ++slot;
             }
+        }
+    };
+
+    // ---- main phase: every lane that finishes an episode takes the next env of the queue at once ---------------------
+    while (true) {
+        const unsigned idle = __ballot_sync(0xFFFFFFFFu, phase == PHASE_NONE);
+        // a recording lane takes a new env only while a whole episode still fits into its arena region
+        const bool can_take = !REC || slot + (unsigned long long)max_steps + 1ull <= slot_end;
+        const unsigned want = REC ? __ballot_sync(0xFFFFFFFFu, phase == PHASE_NONE && can_take) : idle;
+        if (idle) {
+            park_finished();
+            if (!exhausted && want) {
+                const int cnt = __popc(want);
+                unsigned long long base = 0;
+                if (lane == 0) base = atomicAdd(work, (unsigned long long)cnt);
+                base = __shfl_sync(0xFFFFFFFFu, base, 0);
+                if (base + (unsigned long long)cnt >= (unsigned long long)n) exhausted = true;
+                if (phase == PHASE_NONE && (!REC || can_take)) {
+                    const unsigned long long mine = base + (unsigned long long)__popc(want & ((1u << lane) - 1u));
+                    if (mine < (unsigned long long)n) {
+                        e = (uint32_t)mine;
+                        board = 0ull;
+                        boardT = 0ull;
+                        lm = 0;
+                        t = 0;
+                        fours = 0;
+                        seen15 = false;
+                        phase = PHASE_INIT0;
+                    }
+                }
+            }
+            // The queue is empty (or, recording, no idle lane of this warp can take an env any more): tell the CTA.
+            if (exhausted || (REC && want == 0u && idle == 0xFFFFFFFFu)) *s_tail_flag = 1;
+        }
+        // Tail of the launch.  From here on no lane gets a new env and the warps thin out: a warp with one live lane
+        // costs as many issue slots per step as a full one, and with ~3.5 episodes per lane (C4: 2^18 envs) almost half
+        // of all env-steps are played in this phase.  Once any warp of the CTA has seen the queue empty, all of them
+        // (each looks at the flag once per iteration) switch to rounds of PLAY3_TAIL_STEPS steps with a CTA-wide
+        // compaction in between: the live envs move through shared memory into the lowest lanes of the CTA, warps
+        // without envs only wait at the barrier, and the cost of a step follows the number of live envs.
+        if (*s_tail_flag) break;
+        if (phase != PHASE_NONE) step();
+    }
+    unsigned round = 0;
+    while (true) {
+        park_finished();
+        // ---- compaction: live envs -> pool -> lanes 0 .. total-1 of the CTA ----------------------------------------
+        unsigned* cnt = &s_tail_cnt[round & 1u];
+        const unsigned livemask = __ballot_sync(0xFFFFFFFFu, phase != PHASE_NONE);
+        unsigned base = 0;
+        if (livemask) {
+            if (lane == 0) base = atomicAdd(cnt, (unsigned)__popc(livemask));
+            base = __shfl_sync(0xFFFFFFFFu, base, 0);
+        }
+        if (phase != PHASE_NONE) {
+            const unsigned at = base + (unsigned)__popc(livemask & ((1u << lane) - 1u));
+            s_pool[at] = TailEntry{board, slot, e, t, fours, phase | (seen15 ? 4u : 0u)};
+        }
+        __syncthreads();
+        const unsigned total = *(volatile unsigned*)cnt;
+        if (threadIdx.x == 0) s_tail_cnt[(round + 1u) & 1u] = 0u;  // next round's counter: untouched until after the barrier below
+        if (total == 0u) break;  // uniform over the CTA
+        if (threadIdx.x < total) {
+            const TailEntry en = s_pool[threadIdx.x];
+            board = en.board;
+            slot = en.slot;
+            e = en.e;
+            t = en.t;
+            fours = en.fours;
+            phase = en.flags & 3u;
+            seen15 = (en.flags & 4u) != 0u;
+            boardT = transpose_board(board);
+            lm = legal_from_tables(board, boardT);
+        } else {
+            phase = PHASE_NONE;
+        }
+        __syncthreads();  // every entry has been read before the next round writes the pool
+        ++round;
+        for (int it = 0; it < PLAY3_TAIL_STEPS; ++it) {
+            if (__ballot_sync(0xFFFFFFFFu, phase != PHASE_NONE) == 0u) break;  // nothing left in this warp: wait at the barrier
+            if (phase != PHASE_NONE) step();
+            if (__ballot_sync(0xFFFFFFFFu, fin_live)) park_finished();
         }
     }
     epilogue();  // whatever is still parked (a finished lane always passes the loop top, and is parked, before the loop ends)
@@ -444,13 +519,17 @@ play_record_compact_kernel(const u64* __restrict__ arena_boards, const uint8_t* 
     constexpr int K = 4;  // 32-step groups per iteration
     const int lane = threadIdx.x & 31;
     const int64_t warps = (int64_t)gridDim.x * (blockDim.x >> 5);
+    // log(1 / #legal) for 1..4 legal actions, computed once (the lock-step recorder's act_random_log_prob, bit for bit)
+    float lp_of[5];
+#pragma unroll
+    for (int k = 0; k < 5; ++k) lp_of[k] = (POLICY == G2048_POLICY_RANDOM) ? act_random_log_prob(k == 0 ? 0u : (1u << k) - 1u) : 0.0f;
     for (int64_t e = (int64_t)blockIdx.x * (blockDim.x >> 5) + (threadIdx.x >> 5); e < n; e += warps) {
         const uint32_t len = lengths[e];
         const unsigned long long src = env_slot[e];
         const int64_t dst = out_base + offsets[e];
         uint32_t best = 0;  // the trainer's "episode reward" = max_t reward (src/ppo/ppo_trainer.py:218-227)
         for (uint32_t t0 = 0; t0 < len; t0 += 32u * K) {
-            // slots t0 .. t0 + 32 K (one more board than steps: the reward of a step needs the next board)
+            // slots t0 .. t0 + 32 K (one more board than steps: the reward of a step needs the next board's potential)
             u64 b[K + 1];
             uint32_t m[K];
 #pragma unroll
@@ -463,21 +542,26 @@ play_record_compact_kernel(const u64* __restrict__ arena_boards, const uint8_t* 
                 const uint32_t t = t0 + 32u * K;  // lane 0 fetches the board after the iteration's last step
                 b[K] = (lane == 0 && t <= len) ? __ldg(&arena_boards[src + t]) : 0ull;
             }
+            uint32_t pot[K + 1];  // one potential per board: the neighbour's comes by shuffle
+#pragma unroll
+            for (int k = 0; k <= K; ++k) pot[k] = board_potential(b[k]);
 #pragma unroll
             for (int k = 0; k < K; ++k) {
                 const uint32_t t = t0 + 32u * k + (uint32_t)lane;
-                u64 b1 = __shfl_down_sync(0xFFFFFFFFu, b[k], 1);
-                const u64 first_of_next = __shfl_sync(0xFFFFFFFFu, b[k + 1], 0);
-                if (lane == 31) b1 = first_of_next;
+                uint32_t p1 = __shfl_down_sync(0xFFFFFFFFu, pot[k], 1);
+                const uint32_t first_of_next = __shfl_sync(0xFFFFFFFFu, pot[k + 1], 0);
+                if (lane == 31) p1 = first_of_next;
                 if (t < len) {
-                    const uint32_t gained = board_potential(b1) - board_potential(b[k]) - ((m[k] & 0x80u) ? 4u : 0u);
+                    const uint32_t gained = p1 - pot[k] - ((m[k] & 0x80u) ? 4u : 0u);
                     const int64_t o = dst + t;
                     best = max(best, gained);
                     if (o_boards) o_boards[o] = b[k];
                     if (o_meta) o_meta[o] = (uint8_t)(m[k] & 0x7Fu);
                     if (o_rewards) o_rewards[o] = (float)gained;
-                    if (o_log_probs)
-                        o_log_probs[o] = (POLICY == G2048_POLICY_RANDOM) ? act_random_log_prob((m[k] >> 2) & 15u) : 0.0f;
+                    if (o_log_probs) {
+                        const int legal = __popc((m[k] >> 2) & 15u);
+                        o_log_probs[o] = legal == 1 ? lp_of[1] : (legal == 2 ? lp_of[2] : (legal == 3 ? lp_of[3] : (legal == 4 ? lp_of[4] : lp_of[0])));
+                    }
                     if (o_values) o_values[o] = 0.0f;
                 }
             }

@@ -39,6 +39,9 @@ policy_step_kernel(u64* __restrict__ boards, uint8_t* __restrict__ status, const
         if (rec_values) rec_values += at;
     }
     EnvState s{boards[i], status[i]};
+    // live-env list that was built a few steps ago: an env that has finished since then is skipped (its state is frozen
+    // and the record slots after its end stay untouched, as if it had left the list)
+    if (env_ids && !auto_reset && (s.status & G2048_STATUS_DONE)) return;
     // pgx.experimental.auto_reset: a state that finished on the previous step was already replaced
     // by a fresh one but still carries terminated=True; the wrapper clears it before stepping.
     if (auto_reset && (s.status & G2048_STATUS_DONE)) s.status &= ~(uint32_t)G2048_STATUS_DONE;

@@ -5,6 +5,7 @@
 #include <cuda_bf16.h>
 
 #include "g2048_common.cuh"
+#include "g2048_env.cuh"
 #include "g2048_tma.cuh"
 
 namespace g2048 {
@@ -288,6 +289,229 @@ extern "C" int g2048_gather_minibatch(const int64_t* d_indices, int64_t m, const
         d_indices, m, d_meta, d_log_probs, d_values, d_adv, d_ret, d_actions, (uchar4*)d_masks, d_old_log_probs,
         d_old_values, d_out_adv, d_out_ret, (const unsigned long long*)d_boards, (unsigned long long*)d_out_boards);
     G2048_CHECK_LAUNCH("gather_minibatch");
+    return G2048_OK;
+}
+
+// ------------------------------------------------------------------------------------------------
+// network-policy loop step fused with the NEXT step's observation (one launch per loop step)
+// ------------------------------------------------------------------------------------------------
+// g2048_policy_step (g2048_policy.cu) followed by g2048_expand_obs of the stepped boards, in one kernel: a warp owns 32
+// envs -- each lane samples its action from the network's logits, steps its env and writes its record exactly as
+// policy_step_kernel does -- and then expands the 32 NEW boards (handed from lane to lane by shuffles, they never
+// leave the registers) into the observation tensor of the next forward pass through the same shared-memory image ring
+// and bulk stores as expand_obs_tma_kernel.  Removes one launch per step and the 8 + 9 bytes per env of the state's
+// round trip through HBM between the two kernels; the stores of a tile overlap the next tile's sampling.
+namespace g2048 {
+
+struct PolicyStepObsArgs {
+    u64* boards;
+    uint8_t* status;
+    const float4* logits;
+    const float* values;
+    int use_mask, sample, auto_reset;
+    const uint32_t* subs;        // act sub key of step t at words [4t, 4t+2), step sub key at [4t+2, 4t+4)
+    int32_t* step_index;         // t (device memory; NULL: t = 0)
+    int advance_step;            // the last CTA to finish adds 1 to *step_index (graph replay: no separate counter kernel)
+    uint32_t batch_global, env_lo;
+    int64_t n;
+    u64* rec_boards;             // record bases; slot t * n is written
+    uint8_t* rec_meta;
+    float *rec_rewards, *rec_log_probs, *rec_values;
+    int32_t* actions_out;
+    unsigned long long* counters;  // [0] += envs that terminated on this step, [1] += reward > 0 sum (may be NULL)
+};
+
+__device__ unsigned g_step_ticket = 0u;  // CTAs of the running policy_step_obs launch that have read the step number and finished
+
+template <int MODE, typename T>
+__global__ void __launch_bounds__(OBS_THREADS)
+policy_step_obs_kernel(const PolicyStepObsArgs a, T* __restrict__ obs) {
+    constexpr int G = OBS_IMAGE_BYTES / (496 * (int)sizeof(T));  // boards per image
+    constexpr int CELLS = 16 * G;
+    constexpr int PER_LANE = (CELLS + 31) / 32;
+    constexpr int IMAGES = 32 / G;  // images per 32-env tile
+    extern __shared__ __align__(128) uint8_t s_img_raw[];  // [OBS_WARPS][OBS_NBUF][OBS_IMAGE_BYTES]
+
+    const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
+    uint8_t* ring = s_img_raw + (size_t)warp * OBS_NBUF * OBS_IMAGE_BYTES;
+    for (int i = lane; i < OBS_NBUF * OBS_IMAGE_BYTES / 16; i += 32)
+        reinterpret_cast<uint4*>(ring)[i] = make_uint4(0u, 0u, 0u, 0u);
+    __syncwarp();
+    int old_pos[OBS_NBUF][PER_LANE];
+#pragma unroll
+    for (int j = 0; j < OBS_NBUF; ++j)
+#pragma unroll
+        for (int p = 0; p < PER_LANE; ++p) old_pos[j][p] = -1;
+
+    const int64_t t = a.step_index ? (int64_t)*a.step_index : 0;
+    const uint32_t* sub_act = a.subs + 4 * t;
+    const uint32_t* sub_step = sub_act + 2;
+    const int64_t at = t * a.n;
+    const int64_t n_tiles = (a.n + 31) / 32;
+    unsigned long long done_new = 0, reward_sum = 0;
+
+    // warp w of CTA b takes tiles w * gridDim + b, + OBS_WARPS * gridDim, ...: every CTA (hence every SM) gets its share
+    for (int64_t tile = (int64_t)warp * gridDim.x + blockIdx.x; tile < n_tiles; tile += (int64_t)OBS_WARPS * gridDim.x) {
+        const int64_t i = tile * 32 + lane;
+        const bool valid = i < a.n;
+        u64 nb = 0ull;
+        if (valid) {  // ---- policy_step_kernel's body for env i --------------------------------------------------
+            EnvState s{a.boards[i], a.status[i]};
+            const bool was_done = (s.status & G2048_STATUS_DONE) != 0u;
+            if (a.auto_reset && was_done) s.status &= ~(uint32_t)G2048_STATUS_DONE;
+            const uint32_t lm = s.status & G2048_STATUS_MASK;
+            const Logits4 l = prepare_logits(a.logits[i], lm, a.use_mask != 0);
+            int act;
+            if (a.sample) {
+                act = sample_categorical<MODE>(env_key<MODE>(sub_act, a.batch_global, a.env_lo, i), l);
+            } else {
+                act = argmax4(l);
+            }
+            const float picked = act == 0 ? l.v[0] : (act == 1 ? l.v[1] : (act == 2 ? l.v[2] : l.v[3]));
+            const float lp = picked - log_sum_exp4(l);
+            const u64 pre = s.board;
+            const Key step_key = env_key<MODE>(sub_step, a.batch_global, a.env_lo, i);
+            float r;
+            if (a.auto_reset) {
+                Key k1, k2;
+                split2<MODE>(step_key, k1, k2);
+                r = env_step<MODE>(s, act, k1);
+                if (s.status & G2048_STATUS_DONE) {
+                    const EnvState fresh = env_init<MODE>(k2);
+                    s.board = fresh.board;
+                    s.status = fresh.status | G2048_STATUS_DONE | (s.status & G2048_STATUS_OVERFLOW);
+                }
+            } else {
+                r = env_step<MODE>(s, act, step_key);
+            }
+            a.boards[i] = s.board;
+            a.status[i] = (uint8_t)s.status;
+            const bool done = (s.status & G2048_STATUS_DONE) != 0u;
+            if (a.rec_boards) a.rec_boards[at + i] = pre;
+            if (a.rec_meta) a.rec_meta[at + i] = (uint8_t)((uint32_t)act | (lm << 2) | (done ? 0x40u : 0u));
+            if (a.rec_rewards) a.rec_rewards[at + i] = r;
+            if (a.rec_log_probs) a.rec_log_probs[at + i] = lp;
+            if (a.rec_values && a.values) a.rec_values[at + i] = a.values[i];
+            if (a.actions_out) a.actions_out[i] = act;
+            if (done && (a.auto_reset || !was_done)) done_new += 1;
+            if (r > 0.0f) reward_sum += (unsigned long long)r;
+            nb = s.board;
+        }
+        // ---- the observation of the next forward pass: the tile's new boards, image by image ------------------------
+        const int in_tile = (int)min((int64_t)32, a.n - tile * 32);
+#pragma unroll
+        for (int j0 = 0; j0 < IMAGES; j0 += OBS_NBUF) {
+#pragma unroll
+            for (int jj = 0; jj < OBS_NBUF; ++jj) {
+                const int j = j0 + jj;                 // image of the tile; buffer jj of the ring (IMAGES % OBS_NBUF == 0)
+                const int in_image = min(G, in_tile - j * G);  // warp-uniform
+                T* buf = reinterpret_cast<T*>(ring + jj * OBS_IMAGE_BYTES);
+                if (in_image > 0) {
+                    if (lane == 0) bulk_wait_read<OBS_NBUF - 1>();  // the store issued OBS_NBUF images ago is done with buf
+                    __syncwarp();
+                }
+#pragma unroll
+                for (int p = 0; p < PER_LANE; ++p) {
+                    const int c = lane + 32 * p;  // cell index inside the image
+                    const int g = c >> 4, cell = c & 15;
+                    const u64 b = __shfl_sync(0xFFFFFFFFu, nb, (j * G + g) & 31);  // every lane takes part
+                    if (in_image > 0 && c < CELLS) {
+                        if (old_pos[jj][p] >= 0) buf[old_pos[jj][p]] = ObsOne<T>::zero();
+                        int pos = -1;
+                        if (g < in_image) {
+                            pos = g * 496 + 31 * cell + (int)((b >> (4 * cell)) & 15ull);
+                            buf[pos] = ObsOne<T>::one();
+                        }
+                        old_pos[jj][p] = pos;
+                    }
+                }
+                if (in_image > 0) {
+                    fence_proxy_async();  // generic-proxy writes above -> visible to the bulk copy
+                    __syncwarp();
+                    if (lane == 0) {
+                        bulk_store(obs + (tile * 32 + (int64_t)j * G) * 496, buf, (uint32_t)(in_image * 496 * (int)sizeof(T)));
+                        bulk_commit();
+                    }
+                }
+            }
+        }
+    }
+    if (a.counters) {
+        for (int off = 16; off > 0; off >>= 1) {
+            done_new += __shfl_down_sync(0xFFFFFFFFu, done_new, off);
+            reward_sum += __shfl_down_sync(0xFFFFFFFFu, reward_sum, off);
+        }
+        if (lane == 0) {
+            if (done_new) atomicAdd(&a.counters[0], done_new);
+            if (reward_sum) atomicAdd(&a.counters[1], reward_sum);
+        }
+    }
+    if (lane == 0) bulk_wait_all<0>();
+    if (a.step_index && a.advance_step) {  // every CTA read t at its start; the last one to get here moves it on
+        __syncthreads();
+        if (threadIdx.x == 0) {
+            __threadfence();
+            if (atomicAdd(&g_step_ticket, 1u) == gridDim.x - 1u) {
+                g_step_ticket = 0u;
+                *a.step_index = (int32_t)t + 1;
+            }
+        }
+    }
+}
+
+}  // namespace g2048
+
+extern "C" int g2048_policy_step_obs(uint64_t* d_boards, uint8_t* d_status, const float* d_logits, const float* d_values,
+                                     int use_mask, int sample, int auto_reset, const uint32_t* d_subs,
+                                     int32_t* d_step_index, int advance_step, int64_t batch_global, int64_t env_lo, int64_t n,
+                                     int rng_mode, uint64_t* d_rec_boards, uint8_t* d_rec_meta, float* d_rec_rewards,
+                                     float* d_rec_log_probs, float* d_rec_values, int32_t* d_actions_out, int obs_dtype,
+                                     void* d_obs_next, uint64_t* d_counters, void* stream) {
+    G2048_REQUIRE(rng_mode == G2048_RNG_ORIGINAL || rng_mode == G2048_RNG_PARTITIONABLE, "policy_step_obs: rng_mode");
+    G2048_REQUIRE(batch_global > 0 && batch_global <= 0x7FFFFFFFll && env_lo >= 0 && n >= 0 && env_lo + n <= batch_global,
+                  "policy_step_obs: batch");
+    if (n == 0) return G2048_OK;
+    G2048_REQUIRE(d_boards && d_status && d_logits && d_subs && d_obs_next, "policy_step_obs: pointers");
+    G2048_REQUIRE(aligned16(d_logits) && aligned16(d_obs_next), "policy_step_obs: logits and observations must be 16-byte aligned");
+    const int sms = sm_count();
+    if (sms <= 0) return fail_arg("policy_step_obs: no device");
+    static bool configured_on[64] = {false};
+    bool* configured = device_once_flag(configured_on);
+    if (!configured) return fail_arg("no CUDA device");
+    if (!*configured) {
+        int rc = G2048_OK;
+#define G2048_PSO_SMEM(M, T) \
+    if (!rc) rc = check_cuda(cudaFuncSetAttribute(g2048::policy_step_obs_kernel<M, T>, cudaFuncAttributeMaxDynamicSharedMemorySize, OBS_SMEM_BYTES), "policy_step_obs: smem attribute")
+        G2048_PSO_SMEM(0, float); G2048_PSO_SMEM(1, float); G2048_PSO_SMEM(0, __nv_bfloat16); G2048_PSO_SMEM(1, __nv_bfloat16);
+        G2048_PSO_SMEM(0, uint8_t); G2048_PSO_SMEM(1, uint8_t);
+#undef G2048_PSO_SMEM
+        if (rc) return rc;
+        *configured = true;
+    }
+    const g2048::PolicyStepObsArgs args{(g2048::u64*)d_boards, d_status, (const float4*)d_logits, d_values, use_mask, sample,
+                                        auto_reset, d_subs, d_step_index, advance_step, (uint32_t)batch_global, (uint32_t)env_lo, n,
+                                        (g2048::u64*)d_rec_boards, d_rec_meta, d_rec_rewards, d_rec_log_probs, d_rec_values,
+                                        d_actions_out, (unsigned long long*)d_counters};
+    const int64_t n_tiles = (n + 31) / 32;
+    const int64_t need = (n_tiles + OBS_WARPS - 1) / OBS_WARPS;
+    const int64_t cap = (int64_t)sms * 3;  // 3 resident CTAs of 62 KiB per SM
+    const unsigned grid = (unsigned)(need < cap ? need : cap);
+    cudaStream_t st = (cudaStream_t)stream;
+#define G2048_PSO_LAUNCH(T)                                                                                            \
+    do {                                                                                                               \
+        if (rng_mode == G2048_RNG_PARTITIONABLE)                                                                       \
+            g2048::policy_step_obs_kernel<1, T><<<grid, OBS_THREADS, OBS_SMEM_BYTES, st>>>(args, (T*)d_obs_next);      \
+        else                                                                                                           \
+            g2048::policy_step_obs_kernel<0, T><<<grid, OBS_THREADS, OBS_SMEM_BYTES, st>>>(args, (T*)d_obs_next);      \
+    } while (0)
+    switch (obs_dtype) {
+        case G2048_OBS_F32: G2048_PSO_LAUNCH(float); break;
+        case G2048_OBS_BF16: G2048_PSO_LAUNCH(__nv_bfloat16); break;
+        case G2048_OBS_BOOL: G2048_PSO_LAUNCH(uint8_t); break;
+        default: return fail_arg("policy_step_obs: dtype");
+    }
+#undef G2048_PSO_LAUNCH
+    G2048_CHECK_LAUNCH("policy_step_obs");
     return G2048_OK;
 }
 

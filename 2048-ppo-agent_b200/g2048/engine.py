@@ -347,6 +347,27 @@ def policy_step_live(boards, status, logits, values, use_mask: bool, sample: boo
          ptr(rec_meta), ptr(rec_rewards), ptr(rec_log_probs), ptr(rec_values), ptr(actions_out), stream_ptr())
 
 
+def policy_step_obs(boards, status, logits, values, use_mask: bool, sample: bool, auto_reset: bool, subs, step_index,
+                    batch_global: int, env_lo: int, rng_mode: int, obs_next: torch.Tensor, rec_boards=None, rec_meta=None,
+                    rec_rewards=None, rec_log_probs=None, rec_values=None, actions_out=None, counters=None,
+                    advance_step: bool = False) -> None:
+    """policy_step_at fused with expand_obs of the stepped boards: `obs_next` (n,16,31) receives the observation the
+    network reads on the next step.  step_index None: t = 0 -- `subs` starts at this step's act sub key and the record
+    tensors are this step's rows.  counters: int64[2] (accumulated): envs that terminated on this step, reward sum.
+    advance_step: the kernel itself adds 1 to step_index when it is done (graph replay without a counter kernel)."""
+    n = boards.shape[0]
+    assert logits.dtype == torch.float32 and logits.shape == (n, 4) and subs.dtype == torch.int32
+    assert obs_next.shape == (n, 16, 31) and obs_next.is_contiguous()
+    if values is not None:
+        assert values.dtype == torch.float32 and values.numel() == n
+    if step_index is not None:
+        assert step_index.dtype == torch.int32
+    call("g2048_policy_step_obs", ptr(boards), ptr(status), ptr(logits), ptr(values), int(use_mask), int(sample),
+         int(auto_reset), ptr(subs), ptr(step_index), int(advance_step), batch_global, env_lo, n, rng_mode, ptr(rec_boards),
+         ptr(rec_meta), ptr(rec_rewards), ptr(rec_log_probs), ptr(rec_values), ptr(actions_out), _OBS_DTYPES[obs_next.dtype], ptr(obs_next),
+         ptr(counters), stream_ptr())
+
+
 def counter_add(counter: torch.Tensor, delta: int = 1) -> None:
     """counter (int32 device scalar) += delta, on the stream."""
     assert counter.dtype == torch.int32

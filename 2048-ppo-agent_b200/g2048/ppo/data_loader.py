@@ -186,9 +186,10 @@ class DevicePPOBatches:
             if self._epoch_buffers is None:
                 self._epoch_buffers = E.minibatch_buffers(used, self.device, self.obs_dtype)
             epoch = self._gather(order[:used].contiguous(), self._epoch_buffers)
-            for b in range(n_batches):
-                lo, hi = b * self.batch_size, min((b + 1) * self.batch_size, used)
-                yield {k: v[lo:hi] for k, v in epoch.items()}
+            keys = list(epoch)
+            parts = [epoch[k].split(self.batch_size) for k in keys]  # views, one C++ call per field
+            for views in zip(*parts):
+                yield dict(zip(keys, views))
             return
         for b in range(n_batches):
             yield self.batch(order[b * self.batch_size: (b + 1) * self.batch_size])

@@ -36,6 +36,7 @@ from ..state import State
 ENV_ID = "2048"
 CHUNK_STEPS = 64
 GRAPH_SYNC_STEPS = 8  # graph replays between `all done` tests; divides CHUNK_STEPS
+NET_SYNC_STEPS = 8    # eager network-policy loop: steps per chunk; the host looks at the device's done counter once per chunk
 
 
 @dataclass
@@ -319,7 +320,9 @@ class BatchRunner:
         is_net = hasattr(self._act_fn, "forward_logits")
         if self.cuda_graph and is_net and not keep_states:
             return self._run_net_graphed(batch_size, lo, n, boards, status)
-        compact = self.compact_live and (is_net or policy is not None) and not keep_states and not full_records
+        if is_net and not keep_states:
+            return self._run_net(batch_size, lo, n, boards, status, compact=self.compact_live and not full_records)
+        compact = self.compact_live and policy is not None and not keep_states and not full_records
         live_ids = None  # int64 local indices of the envs still alive (compact mode), refreshed when some finish
         counters = torch.zeros(4, dtype=torch.int64, device=dev)
         chunks = []  # (boards, meta, rewards, log_probs, values) per chunk, time-major
@@ -408,6 +411,57 @@ class BatchRunner:
             env_steps = int(E.episode_lengths(rm, t_total, n).sum().item())
         return PackedRollout(rb, rm, rr, rl, rv, boards, status, t_total, n, env_steps)
 
+    # -- eager network-policy loop: one fused launch per step, one host synchronisation per chunk ----------------------
+    def _run_net(self, batch_size: int, lo: int, n: int, boards, status, compact: bool) -> PackedRollout:
+        """src/runs/batch_runner.py:117-136 with a ``TorchActionFunction``: per loop step the network forward (PyTorch)
+        and ONE kernel -- ``g2048_policy_step_obs``: mask rule, categorical draw, log-prob, env.step, record write and the
+        observation of the next forward pass, written from registers.  The reference tests ``all done`` after every
+        step (a blocking read-back); here the kernel keeps the count of finished envs on the device and the host reads
+        it once per NET_SYNC_STEPS steps -- stepping a finished batch is a no-op (frozen envs), and the loop steps past
+        the last env's end are cut off afterwards.  compact: only the envs alive at the start of a chunk go through
+        the network (``g2048_expand_obs_gather`` + ``g2048_policy_step_live``, which skips envs that finished inside
+        the chunk)."""
+        fn, dev, mode = self._act_fn, self.device, self.rng_mode
+        counters = torch.zeros(2, dtype=torch.int64, device=dev)
+        obs = None if compact else E.expand_obs(boards, fn.obs_dtype)
+        alloc = torch.zeros if compact else torch.empty  # compact mode leaves the slots of finished envs untouched
+        chunks, t0 = [], 0
+        while True:
+            steps = NET_SYNC_STEPS
+            subs = self.chain.peek(1 + 2 * (t0 + steps))
+            rb = alloc((steps, n), dtype=torch.int64, device=dev)
+            rm = alloc((steps, n), dtype=torch.uint8, device=dev)
+            rr, rl, rv = (alloc((steps, n), dtype=torch.float32, device=dev) for _ in range(3))
+            if compact:
+                live_ids = torch.nonzero((status & N.STATUS_DONE) == 0).flatten()  # once per chunk
+            for k in range(steps):
+                t = t0 + k
+                if compact:
+                    self._net_step_live(boards, status, live_ids, subs[1 + 2 * t], subs[2 + 2 * t], batch_size, lo, mode,
+                                        rb[k], rm[k], rr[k], rl[k], rv[k])
+                else:
+                    logits, values = fn.forward_logits(obs)
+                    E.policy_step_obs(boards, status, logits, values, fn.use_mask, fn.sample_actions, False, subs[1 + 2 * t:],
+                                      None, batch_size, lo, mode, obs, rb[k], rm[k], rr[k], rl[k], rv[k], counters=counters)
+            chunks.append((rb, rm, rr, rl, rv))
+            t0 += steps
+            if compact:
+                done_now = int(((status & N.STATUS_DONE) != 0).sum().item())
+            else:
+                done_now = int(counters[0].item())  # maintained by the kernel: the one read-back of the chunk
+            if self._all_done(done_now, n):
+                break
+        rb, rm, rr, rl, rv = (torch.cat([c[i] for c in chunks]) for i in range(5))
+        lengths = E.episode_lengths(rm, t0, n)
+        t_total = int(lengths.max().item()) if n else 0
+        if self.shard is not None and self.shard[1] > 1:
+            from ..dist import allreduce_max_int
+
+            t_total = allreduce_max_int(t_total, self.device)
+        self.chain.consume(1 + 2 * t_total)
+        rb, rm, rr, rl, rv = (x[:t_total].contiguous() for x in (rb, rm, rr, rl, rv))
+        return PackedRollout(rb, rm, rr, rl, rv, boards, status, t_total, n, int(lengths.sum().item()))
+
     # -- CUDA-graph form of the network-policy loop (SURVEY 8f rank 3) ---------------------------
     def _captured_step(self, batch_size: int, lo: int, n: int, steps: int = CHUNK_STEPS, auto_reset: bool = False) -> dict:
         """Static buffers + one captured graph: expand_obs -> forward -> policy_step_at -> counter_add.
@@ -434,16 +488,21 @@ class BatchRunner:
         )
 
         def step():
-            E.expand_obs(g["boards"], fn.obs_dtype, out=g["obs"])
+            # g["obs"] holds the observation of the current state (refresh_obs() before the first replay): the fused
+            # kernel writes the next one from registers and moves the device-resident step number on itself
             logits, values = fn.forward_logits(g["obs"])
-            E.policy_step_at(g["boards"], g["status"], logits, values, fn.use_mask, fn.sample_actions, auto_reset, g["subs"],
-                             g["step_index"], batch_size, lo, mode, g["rb"], g["rm"], g["rr"], g["rl"], g["rv"])
-            E.counter_add(g["step_index"], 1)
+            E.policy_step_obs(g["boards"], g["status"], logits, values, fn.use_mask, fn.sample_actions, auto_reset, g["subs"],
+                              g["step_index"], batch_size, lo, mode, g["obs"], g["rb"], g["rm"], g["rr"], g["rl"], g["rv"],
+                              counters=g["counters"], advance_step=True)
+
+        g["counters"] = torch.zeros(2, dtype=torch.int64, device=dev)
+        g["refresh_obs"] = lambda: E.expand_obs(g["boards"], fn.obs_dtype, out=g["obs"])
 
         # warm-up on a side stream (lazy module loading, cuBLAS workspaces, autotuning) before the capture
         side = torch.cuda.Stream(device=dev)
         side.wait_stream(torch.cuda.current_stream(dev))
         with torch.cuda.stream(side):
+            g["refresh_obs"]()
             for _ in range(3):
                 g["step_index"].zero_()
                 step()
@@ -461,6 +520,8 @@ class BatchRunner:
         g = self._captured_step(batch_size, lo, n)
         g["boards"].copy_(boards)
         g["status"].copy_(status)
+        g["refresh_obs"]()
+        g["counters"].zero_()
         chunks, t0 = [], 0
         while True:
             subs = self.chain.peek(1 + 2 * (t0 + CHUNK_STEPS))
@@ -474,7 +535,7 @@ class BatchRunner:
                 for _ in range(GRAPH_SYNC_STEPS):
                     g["graph"].replay()
                 used += GRAPH_SYNC_STEPS
-                done_now = int(((g["status"] & N.STATUS_DONE) != 0).sum().item())
+                done_now = int(g["counters"][0].item())  # kept by the kernel: no reduction kernels on the loop's path
                 finished = self._all_done(done_now, n)
             chunks.append(tuple(g[k][:used].clone() for k in ("rb", "rm", "rr", "rl", "rv")))
             t0 += used

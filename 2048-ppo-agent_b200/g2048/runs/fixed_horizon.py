@@ -10,9 +10,9 @@ unfinished episodes -- as the new mode the fused kernels make cheap.  This is it
     rollout = runner.collect(128)                       # (T, n) time-major packed records on the device
     adv, ret, moments = rollout.gae(0.99, 0.95, bootstrap=runner.bootstrap_values())
 
-Per step: one ``g2048_expand_obs`` launch, the network forward (PyTorch), one ``g2048_policy_step`` launch (mask
-rule, sampling with jax-compatible draws, log-prob, env step, auto-reset, record write); with ``cuda_graph=True`` the
-step is captured once and replayed.  The key chain advances like the reference's: one sub key for the initial
+Per step: the network forward (PyTorch) and ONE ``g2048_policy_step_obs`` launch (mask rule, sampling with
+jax-compatible draws, log-prob, env step, auto-reset, record write and the observation of the next forward pass, written
+from registers); with ``cuda_graph=True`` the step is captured once and replayed.  The key chain advances like the reference's: one sub key for the initial
 ``env.init``, then two per step (act, step).  ``state_dict()`` holds the key chain AND the env state (SURVEY 8f
 rank 4: the reference checkpoints neither, src/ppo/ppo_trainer.py:511-530).
 """
@@ -90,16 +90,17 @@ class FixedHorizonRunner:
                 self.boards, self.status, self._graph = g["boards"], g["status"], g
             g["subs"].copy_(subs)
             g["step_index"].zero_()
+            g["refresh_obs"]()  # the env state may have been replaced since the last replay (load_state_dict)
             for _ in range(t_steps):
                 g["graph"].replay()
             rb, rm, rr, rl, rv = (g[k].clone() for k in ("rb", "rm", "rr", "rl", "rv"))
         else:
             rb, rm, rr, rl, rv = self._records(t_steps)
-            for t in range(t_steps):
-                obs = E.expand_obs(self.boards, fn.obs_dtype)
+            obs = E.expand_obs(self.boards, fn.obs_dtype)
+            for t in range(t_steps):  # per step: the forward pass and ONE launch (step + record + next observation)
                 logits, values = fn.forward_logits(obs)
-                E.policy_step(self.boards, self.status, logits, values, fn.use_mask, fn.sample_actions, True,
-                              subs[2 * t], subs[2 * t + 1], self.batch_size, self.lo, mode, rb[t], rm[t], rr[t], rl[t], rv[t])
+                E.policy_step_obs(self.boards, self.status, logits, values, fn.use_mask, fn.sample_actions, True, subs[2 * t:],
+                                  None, self.batch_size, self.lo, mode, obs, rb[t], rm[t], rr[t], rl[t], rv[t])
         r.chain.consume(2 * t_steps)
         return FixedRollout(rb, rm, rr, rl, rv, self.boards.clone(), self.status.clone(), t_steps, self.n)
 

@@ -711,6 +711,15 @@ def secondary_measurements(E, N, torch, dev, flush_buf) -> dict:
     obs = torch.empty((b, 16, 31), dtype=torch.float32, device=dev)
 
     def ppo_rollout():
+        # one launch per step: sample + env.step + auto-reset + record + the observation of the next forward pass
+        N.call("g2048_expand_obs", N.ptr(pb), b, N.OBS_F32, N.ptr(obs), 0, 0, N.stream_ptr())
+        for k in range(t_steps):
+            E.policy_step_obs(pb, ps, logits, values, True, True, True, subs[1 + 2 * k:], None, b, 0, mode, obs,
+                              rec_b[k], rec_m[k], rec_r[k], rec_l[k], rec_v[k])
+        N.call("g2048_gae_time_major", N.ptr(rec_r), N.ptr(rec_v), N.ptr(rec_m), t_steps, b, None, 0.99, 0.95,
+               N.ptr(adv2), N.ptr(ret2), N.ptr(mom), N.stream_ptr())
+
+    def ppo_rollout_two_launches():  # round 1's form: expand_obs + policy_step per step
         for k in range(t_steps):
             N.call("g2048_expand_obs", N.ptr(pb), b, N.OBS_F32, N.ptr(obs), 0, 0, N.stream_ptr())
             E.policy_step(pb, ps, logits, values, True, True, True, subs[1 + 2 * k], subs[2 + 2 * k], b, 0, mode,
@@ -719,6 +728,7 @@ def secondary_measurements(E, N, torch, dev, flush_buf) -> dict:
                N.ptr(adv2), N.ptr(ret2), N.ptr(mom), N.stream_ptr())
 
     t = timed(ppo_rollout, reps=3)
+    t_two = timed(ppo_rollout_two_launches, reps=3)
 
     # the same 257 launches replayed as ONE CUDA graph: what the kernels cost once the Python / ctypes launch overhead
     # (two launches per step from the interpreter) is out of the way -- how FixedHorizonRunner(cuda_graph=True) runs them
@@ -777,14 +787,17 @@ def secondary_measurements(E, N, torch, dev, flush_buf) -> dict:
         "config": "C3: 65536 envs x 128 steps, auto-reset, masked categorical sampling from synthetic logits "
                   "(policy network = PyTorch/cuBLAS, outside the product path and not timed)",
         "env_steps_per_sec": t_steps * b / t, "ms_per_rollout": t * 1e3,
-        "per_step_us": t * 1e6 / t_steps, "launches_per_rollout": 2 * t_steps + 1,
+        "per_step_us": t * 1e6 / t_steps, "launches_per_rollout": t_steps + 2,
+        "per_step_us_two_launches_per_step": t_two * 1e6 / t_steps,
+        "hbm_floor_us_per_step": (b * (1984 + 21 + 20 + 18)) / measured_hbm_peak()[0] / 1e3,
         "graph_replay": ({"ms_per_rollout": t_graph * 1e3, "per_step_us": t_graph * 1e6 / t_steps,
                           "env_steps_per_sec": t_steps * b / t_graph,
                           "note": "the same launches captured once and replayed as a CUDA graph (no interpreter between them)"}
                          if isinstance(t_graph, float) else t_graph),
         "policy_forward_ms_per_step": fwd_ms,
         "policy_forward_note": "same-shaped PyTorch Transformer (3.96 M parameters, bf16 autocast, 65536 x 17 tokens), for scale only",
-        "kernels": "per step: expand_obs<f32> (network input) + policy_step (mask, sample, log-prob, env step, auto-reset, record write); then gae_time_major",
+        "kernels": "per step ONE launch: policy_step_obs (mask, sample, log-prob, env step, auto-reset, record write, and the float32 "
+                   "observation of the next forward pass written from registers); then gae_time_major",
     }
     # C2: DRUL corner policy, 2^20 envs to termination, score / max-tile statistics reduced on the device
     import g2048
@@ -853,14 +866,14 @@ def c4_iteration(E, N, torch, dev, hbm_peak) -> dict:
                         f"minibatches of {minibatch}"}
     # -- rollout + store: the recording play kernel writes the buffer's own layout (run_flat_batch -> store_flat) --------
     runner = g2048.BatchRunner(init_seed=4, act_fn=g2048.act_randomly)
-    runner.run_flat_batch(n_envs)  # warm-up at full size: allocator, table build, arena sizing hint
-    runner = g2048.BatchRunner(init_seed=4, act_fn=g2048.act_randomly)
+    runner.run_flat_batch(n_envs)  # warm-up at full size: allocator, table build, arena sizing hint, key chain generated ahead
+    key_before = runner.key  # the chain key the timed batch starts from (for the oracle replay below)
     buf = g2048.RolloutBuffer(31, 16, 4)
     flat, t_flat = wall(lambda: runner.run_flat_batch(n_envs))
     _, t_store = wall(lambda: buf.store_flat(flat))
     steps = flat.env_steps
     # the two kernels alone, device-timed
-    subs = E.chain_advance(E.words_tensor(list(E.key_words(4)), dev), mode, 1 + 2 * 2048)
+    subs = E.chain_advance(E.words_tensor(key_before, dev), mode, 1 + 2 * 2048)
     rec = {}
     t_rec = dev_time(lambda: rec.update(E.play_record(E.POLICY_RANDOM, subs, n_envs, 0, n_envs, mode, mean_steps=steps // n_envs + 1)))
     offsets = E.exclusive_scan(rec["lengths"])
@@ -881,8 +894,7 @@ def c4_iteration(E, N, torch, dev, hbm_peak) -> dict:
     del rec
     # round 1's path for the same batch: lock-step recorder (every env stepped until the last one ends) + store_packed
     r1 = g2048.BatchRunner(init_seed=4, act_fn=g2048.act_randomly)
-    r1.run_packed_batch(n_envs)
-    r1 = g2048.BatchRunner(init_seed=4, act_fn=g2048.act_randomly)
+    r1.run_packed_batch(n_envs)  # the same first batch as the warm-up above, so the second one is the timed batch's twin
     ro, t_lock = wall(lambda: r1.run_packed_batch(n_envs))
     b1 = g2048.RolloutBuffer(31, 16, 4)
     _, t_store1 = wall(lambda: b1.store_packed(ro))
@@ -931,7 +943,7 @@ def c4_iteration(E, N, torch, dev, hbm_peak) -> dict:
     # -- bit-exact board check on a 4 096-env sample: replay the recorded actions through the oracle's step, with the
     #    oracle's own spawn draws from the same keys; every recorded pre-step board, reward and done flag must agree
     sample, t_chk = 4096, 200
-    _, o_subs = CO.chain(np.array(E.key_words(4), np.uint32), 1, 1 + 2 * t_chk)
+    _, o_subs = CO.chain(np.asarray(key_before, np.uint32), 1, 1 + 2 * t_chk)
     boards, masks = CO.env_init(CO.split(o_subs[0], n_envs, 1)[:sample], 1)
     done = np.zeros(sample, np.uint8)
     offs = flat.offsets[: sample + 1].cpu().numpy()

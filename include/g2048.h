@@ -257,6 +257,21 @@ int g2048_policy_step_live(uint64_t* d_boards, uint8_t* d_status, const float* d
                            int rng_mode, uint64_t* d_rec_boards, uint8_t* d_rec_meta, float* d_rec_rewards,
                            float* d_rec_log_probs, float* d_rec_values, int32_t* d_actions_out, void* stream);
 
+/* One launch per loop step of the network-policy rollout: g2048_policy_step_at for step t = *d_step_index (NULL: t = 0,
+ * d_subs then points at this step's act sub key) FUSED with g2048_expand_obs of the stepped boards -- d_obs_next
+ * (n,16,31) in obs_dtype (G2048_OBS_*) receives the observation of the NEXT forward pass, written from registers: the
+ * new boards are handed from lane to lane by shuffles and go through the same shared-memory image ring and bulk stores
+ * as g2048_expand_obs.  Same records, state and draws as g2048_policy_step_at.  d_counters (uint64[2], may be NULL,
+ * ACCUMULATED): [0] envs that terminated on this step, [1] sum of the rewards > 0 -- so the host can test "all done"
+ * without a reduction kernel.  advance_step != 0 (with d_step_index): the kernel adds 1 to *d_step_index once all its
+ * CTAs are done, so a captured graph of {network forward, this launch} can be replayed step after step with nothing
+ * else in it (one such launch at a time per device: the CTA ticket is a library global). */
+int g2048_policy_step_obs(uint64_t* d_boards, uint8_t* d_status, const float* d_logits, const float* d_values, int use_mask,
+                          int sample, int auto_reset, const uint32_t* d_subs, int32_t* d_step_index, int advance_step,
+                          int64_t batch_global, int64_t env_lo, int64_t n, int rng_mode, uint64_t* d_rec_boards,
+                          uint8_t* d_rec_meta, float* d_rec_rewards, float* d_rec_log_probs, float* d_rec_values,
+                          int32_t* d_actions_out, int obs_dtype, void* d_obs_next, uint64_t* d_counters, void* stream);
+
 /* *d_counter += delta on the stream (one thread): advances the device-resident step number between replays. */
 int g2048_counter_add(int32_t* d_counter, int32_t delta, void* stream);
 

@@ -51,6 +51,10 @@ def run_all(E, g2048, T=torch, dev="cuda"):
         E.counter_add(step_index, ch - 1)  # last record slot
         E.policy_step_at(boards, status, logits, values, True, True, True, subs[7:].contiguous(), step_index, 1000, 17, mode,
                          rb, rm, rr, rl, T.empty((ch, n), dtype=torch.float32, device=dev))
+        for dt in (torch.float32, torch.bfloat16, torch.bool):  # fused step + next observation
+            obs_next = T.empty((n, 16, 31), dtype=dt, device=dev)
+            E.policy_step_obs(boards, status, logits, values, True, True, True, subs[7:].contiguous(), None, 1000, 17, mode,
+                              obs_next, rb[0], rm[0], rr[0], rl[0], rv, acts, T.zeros(2, dtype=torch.int64, device=dev))
         live = torch.nonzero((status & 16) == 0).flatten()[::3].contiguous()
         if live.numel():
             E.expand_obs_gather(boards, live, torch.float32)
