@@ -1,0 +1,242 @@
+// GAE as a segmented affine REVERSE SCAN (BASELINE.json north_star: "warp shuffles handle the reverse-scan GAE over the
+// time dimension"; src/ppo/data_loader.py:103-130).  Opt-in companion of g2048_gae_flat: that kernel walks every episode
+// with the reference's exact fp32 operation order (bit-identical, 0.65-0.74 of HBM because a walking lane moves no
+// bytes); this one re-associates the recurrence and is a pure stream -- results agree within the 1e-5 relative
+// tolerance north_star states for GAE (tests/test_gae_scan_gpu.py), not bit for bit.
+//
+//   gae_t = delta_t + a_t * gae_{t+1},   a_t = done_t ? 0 : gamma * lambda,
+//   delta_t = (r_t + gamma * (done_t ? 0 : V_{t+1})) - V_t
+//
+// i.e. gae_t = f_t(gae_{t+1}) with the affine map f_t(x) = a_t x + delta_t; maps compose associatively
+// ((a1,b1) o (a2,b2) = (a1 a2, a1 b2 + b1)), so the suffix compositions F_t = f_t o f_{t+1} o ... are a scan:
+//   * a thread composes its 8 consecutive steps serially (registers, 128-bit loads),
+//   * a warp scans the 32 thread aggregates with shuffles (5 steps), the 16 warp aggregates go through shared memory,
+//   * tiles (4 096 steps, one per CTA, taken from the END of the buffer by ticket) are chained by decoupled look-back:
+//     a tile publishes its aggregate (A, B) and, once it knows the gae entering it, the gae of its first step.  A tile
+//     that contains a `done` has A == 0 exactly, so its first-step gae is B and is published at once -- with episodes of
+//     a few hundred steps the chain is never longer than one tile and no CTA waits for another's look-back.
+// 9 B read + 8 B written per step; fp64 moment sums for the normalisation in the same pass.
+#include "g2048_common.cuh"
+
+namespace g2048 {
+
+constexpr int SCAN_THREADS = 512;
+constexpr int SCAN_ITEMS = 8;
+constexpr int SCAN_TILE = SCAN_THREADS * SCAN_ITEMS;  // 4 096 steps
+constexpr int SCAN_WARPS = SCAN_THREADS / 32;
+
+struct ScanHeader {
+    unsigned int ticket;
+    unsigned int pad[3];
+};
+// per tile: word = flag << 32 | float bits (flag 1: B of the tile aggregate, A in `a`; flag 2: gae of the tile's first step)
+struct ScanTile {
+    unsigned long long word;
+    float a;
+    float pad;
+};
+constexpr unsigned SCAN_AGG = 1u, SCAN_INCL = 2u;
+
+struct Affine {
+    float a, b;
+};
+// apply `inner` first, then `outer`
+__device__ __forceinline__ Affine compose(Affine outer, Affine inner) {
+    return Affine{outer.a * inner.a, outer.a * inner.b + outer.b};
+}
+
+template <bool ALIGNED>
+__global__ void __launch_bounds__(SCAN_THREADS)
+gae_scan_kernel(const float* __restrict__ rewards, const float* __restrict__ values, const uint8_t* __restrict__ dones,
+                int64_t n, int64_t n_tiles, float gamma, float gamma_lambda, float* __restrict__ adv,
+                float* __restrict__ ret, ScanHeader* header, double* __restrict__ moments) {
+    __shared__ Affine s_warp[SCAN_WARPS];
+    __shared__ float s_carry;
+    __shared__ unsigned int s_ticket;
+    __shared__ double s_red[4 * SCAN_WARPS];
+
+    ScanTile* tiles = reinterpret_cast<ScanTile*>(header + 1);
+    if (threadIdx.x == 0) s_ticket = atomicAdd(&header->ticket, 1u);
+    __syncthreads();
+    const int64_t tile = n_tiles - 1 - (int64_t)s_ticket;  // memory-order index: later tiles start first
+    const int64_t lo = tile * SCAN_TILE;
+    const int64_t first = lo + (int64_t)threadIdx.x * SCAN_ITEMS;  // this thread's first step
+    const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
+
+    // ---- loads: 8 consecutive steps per thread -------------------------------------------------------------------
+    float r[SCAN_ITEMS], v[SCAN_ITEMS + 1];
+    bool d[SCAN_ITEMS];
+    const bool full = first + SCAN_ITEMS <= n;
+    if (ALIGNED && full) {
+        const float4 r0 = *reinterpret_cast<const float4*>(rewards + first), r1 = *reinterpret_cast<const float4*>(rewards + first + 4);
+        const float4 v0 = *reinterpret_cast<const float4*>(values + first), v1 = *reinterpret_cast<const float4*>(values + first + 4);
+        const uint2 dd = *reinterpret_cast<const uint2*>(dones + first);
+        r[0] = r0.x; r[1] = r0.y; r[2] = r0.z; r[3] = r0.w; r[4] = r1.x; r[5] = r1.y; r[6] = r1.z; r[7] = r1.w;
+        v[0] = v0.x; v[1] = v0.y; v[2] = v0.z; v[3] = v0.w; v[4] = v1.x; v[5] = v1.y; v[6] = v1.z; v[7] = v1.w;
+#pragma unroll
+        for (int k = 0; k < 4; ++k) {
+            d[k] = ((dd.x >> (8 * k)) & 0xFFu) != 0u;
+            d[4 + k] = ((dd.y >> (8 * k)) & 0xFFu) != 0u;
+        }
+    } else {
+#pragma unroll
+        for (int k = 0; k < SCAN_ITEMS; ++k) {
+            const bool in = first + k < n;
+            r[k] = in ? rewards[first + k] : 0.0f;
+            v[k] = in ? values[first + k] : 0.0f;
+            d[k] = in ? dones[first + k] != 0 : true;  // past the end: a = 0, delta = 0 -- contributes nothing
+        }
+    }
+    v[SCAN_ITEMS] = (first + SCAN_ITEMS < n) ? values[first + SCAN_ITEMS] : 0.0f;  // V of the step after mine (0 past the end)
+
+    // ---- per-step maps and the thread's aggregate (composition of its 8 steps, first step outermost) -------------------
+    float a[SCAN_ITEMS], b[SCAN_ITEMS];
+    Affine mine{1.0f, 0.0f};
+#pragma unroll
+    for (int k = SCAN_ITEMS - 1; k >= 0; --k) {
+        const float next_v = d[k] ? 0.0f : v[k + 1];
+        a[k] = d[k] ? 0.0f : gamma_lambda;
+        b[k] = (r[k] + gamma * next_v) - v[k];
+        mine = compose(Affine{a[k], b[k]}, mine);
+    }
+    // ---- warp: inclusive suffix scan over lanes (lane L: composition of lanes L .. 31) --------------------------------
+    Affine incl = mine;
+#pragma unroll
+    for (int off = 1; off < 32; off <<= 1) {
+        Affine other;
+        other.a = __shfl_down_sync(0xFFFFFFFFu, incl.a, off);
+        other.b = __shfl_down_sync(0xFFFFFFFFu, incl.b, off);
+        if (lane + off < 32) incl = compose(incl, other);
+    }
+    if (lane == 0) s_warp[warp] = incl;
+    // what follows my steps inside the warp: the inclusive value of the next lane
+    Affine after;
+    after.a = __shfl_down_sync(0xFFFFFFFFu, incl.a, 1);
+    after.b = __shfl_down_sync(0xFFFFFFFFu, incl.b, 1);
+    if (lane == 31) after = Affine{1.0f, 0.0f};
+    __syncthreads();
+    // ... and the warps after mine
+    Affine later{1.0f, 0.0f};
+    for (int w = SCAN_WARPS - 1; w > warp; --w) later = compose(s_warp[w], later);
+    after = compose(after, later);  // everything between my last step and the end of the tile
+
+    // ---- chain the tiles: publish, look back -----------------------------------------------------------------------
+    if (threadIdx.x == 0) {
+        const Affine whole = compose(incl, later);  // thread 0: lanes 0..31 of warp 0, then warps 1..15
+        volatile unsigned long long* my_word = &tiles[tile].word;
+        const bool last_tile = tile == n_tiles - 1;
+        float x = 0.0f;  // gae of the first step of the next tile (0 past the end of the buffer)
+        if (whole.a == 0.0f || last_tile) {
+            // nothing of what follows reaches my first step: its gae is known now
+            *my_word = ((unsigned long long)SCAN_INCL << 32) | (unsigned long long)__float_as_uint(whole.b);
+        } else {
+            tiles[tile].a = whole.a;
+            __threadfence();
+            *my_word = ((unsigned long long)SCAN_AGG << 32) | (unsigned long long)__float_as_uint(whole.b);
+        }
+        if (!last_tile) {
+            Affine acc{1.0f, 0.0f};  // composition of the tiles between me and the one whose first-step gae is known
+            for (int64_t j = tile + 1;; ++j) {
+                if (j == n_tiles) {
+                    x = acc.b;  // ran off the end of the buffer: gae entering it is 0
+                    break;
+                }
+                volatile unsigned long long* w = &tiles[j].word;
+                unsigned long long word;
+                do {
+                    word = *w;
+                } while ((unsigned)(word >> 32) == 0u);  // tile j holds an earlier ticket: it is running
+                const float val = __uint_as_float((unsigned)word);
+                if ((unsigned)(word >> 32) == SCAN_INCL) {
+                    x = acc.a * val + acc.b;
+                    break;
+                }
+                __threadfence();
+                acc = compose(acc, Affine{*(volatile float*)&tiles[j].a, val});
+            }
+            if (whole.a != 0.0f)
+                *my_word = ((unsigned long long)SCAN_INCL << 32) | (unsigned long long)__float_as_uint(whole.a * x + whole.b);
+        }
+        s_carry = x;
+    }
+    __syncthreads();
+    const float x = s_carry;
+
+    // ---- apply: the gae entering my steps, then the reference's own recurrence over them ----------------------------
+    float g = after.a * x + after.b;
+    float o_adv[SCAN_ITEMS], o_ret[SCAN_ITEMS];
+    double acc4[4] = {0.0, 0.0, 0.0, 0.0};
+#pragma unroll
+    for (int k = SCAN_ITEMS - 1; k >= 0; --k) {
+        g = b[k] + a[k] * g;
+        o_adv[k] = g;
+        o_ret[k] = g + v[k];
+        if (first + k < n) {
+            acc4[0] += (double)g;
+            acc4[1] += (double)g * (double)g;
+            acc4[2] += (double)o_ret[k];
+            acc4[3] += (double)o_ret[k] * (double)o_ret[k];
+        }
+    }
+    if (ALIGNED && full) {
+        *reinterpret_cast<float4*>(adv + first) = make_float4(o_adv[0], o_adv[1], o_adv[2], o_adv[3]);
+        *reinterpret_cast<float4*>(adv + first + 4) = make_float4(o_adv[4], o_adv[5], o_adv[6], o_adv[7]);
+        *reinterpret_cast<float4*>(ret + first) = make_float4(o_ret[0], o_ret[1], o_ret[2], o_ret[3]);
+        *reinterpret_cast<float4*>(ret + first + 4) = make_float4(o_ret[4], o_ret[5], o_ret[6], o_ret[7]);
+    } else {
+#pragma unroll
+        for (int k = 0; k < SCAN_ITEMS; ++k) {
+            if (first + k < n) {
+                adv[first + k] = o_adv[k];
+                ret[first + k] = o_ret[k];
+            }
+        }
+    }
+    if (moments) {
+#pragma unroll
+        for (int k = 0; k < 4; ++k) {
+            double s = acc4[k];
+            for (int off = 16; off > 0; off >>= 1) s += __shfl_down_sync(0xFFFFFFFFu, s, off);
+            if (lane == 0) s_red[k * SCAN_WARPS + warp] = s;
+        }
+        __syncthreads();
+        if (threadIdx.x < 4) {
+            double s = 0.0;
+            for (int w = 0; w < SCAN_WARPS; ++w) s += s_red[threadIdx.x * SCAN_WARPS + w];
+            atomicAdd(&moments[1 + threadIdx.x], s);
+        }
+        if (threadIdx.x == 4) atomicAdd(&moments[0], (double)min((int64_t)SCAN_TILE, n - lo));
+    }
+}
+
+}  // namespace g2048
+
+using namespace g2048;
+
+extern "C" int64_t g2048_gae_scan_scratch_bytes(int64_t n) {
+    const int64_t n_tiles = (n + SCAN_TILE - 1) / SCAN_TILE;
+    return (int64_t)sizeof(ScanHeader) + n_tiles * (int64_t)sizeof(ScanTile);
+}
+
+extern "C" int g2048_gae_flat_scan(const float* d_rewards, const float* d_values, const uint8_t* d_dones, int64_t n, double gamma,
+                                   double lambda_gae, float* d_adv, float* d_ret, void* d_scan_state, double* d_moments,
+                                   void* stream) {
+    G2048_REQUIRE(n >= 0, "gae_flat_scan: n");
+    if (n == 0) return G2048_OK;
+    G2048_REQUIRE(d_rewards && d_values && d_dones && d_adv && d_ret && d_scan_state, "gae_flat_scan: pointers");
+    G2048_REQUIRE(((uintptr_t)d_scan_state & 15u) == 0, "gae_flat_scan: scratch must be 16-byte aligned");
+    const int64_t n_tiles = (n + SCAN_TILE - 1) / SCAN_TILE;
+    const auto a16 = [](const void* p) { return ((uintptr_t)p & 15u) == 0; };
+    const bool aligned = a16(d_rewards) && a16(d_values) && a16(d_adv) && a16(d_ret) && ((uintptr_t)d_dones & 7u) == 0;
+    cudaStream_t st = (cudaStream_t)stream;
+    if (aligned)
+        gae_scan_kernel<true><<<(unsigned)n_tiles, SCAN_THREADS, 0, st>>>(d_rewards, d_values, d_dones, n, n_tiles, (float)gamma,
+                                                                          (float)(gamma * lambda_gae), d_adv, d_ret,
+                                                                          (ScanHeader*)d_scan_state, d_moments);
+    else
+        gae_scan_kernel<false><<<(unsigned)n_tiles, SCAN_THREADS, 0, st>>>(d_rewards, d_values, d_dones, n, n_tiles, (float)gamma,
+                                                                           (float)(gamma * lambda_gae), d_adv, d_ret,
+                                                                           (ScanHeader*)d_scan_state, d_moments);
+    G2048_CHECK_LAUNCH("gae_flat_scan");
+    return G2048_OK;
+}

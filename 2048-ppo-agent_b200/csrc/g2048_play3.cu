@@ -284,7 +284,8 @@ play3_kernel(const uint2* __restrict__ subs, int64_t n_subs, uint32_t batch_glob
     };
 
     // ---- main phase: every lane that finishes an episode takes the next env of the queue at once ---------------------
-    while (true) {
+    bool tail_seen = false;  // warp-uniform
+    for (unsigned iter = 0;; ++iter) {
         const unsigned idle = __ballot_sync(0xFFFFFFFFu, phase == PHASE_NONE);
         // a recording lane takes a new env only while a whole episode still fits into its arena region
         const bool can_take = !REC || slot + (unsigned long long)max_steps + 1ull <= slot_end;
@@ -312,15 +313,19 @@ play3_kernel(const uint2* __restrict__ subs, int64_t n_subs, uint32_t batch_glob
                 }
             }
             // The queue is empty (or, recording, no idle lane of this warp can take an env any more): tell the CTA.
-            if (exhausted || (REC && want == 0u && idle == 0xFFFFFFFFu)) *s_tail_flag = 1;
+            if (exhausted || (REC && want == 0u && idle == 0xFFFFFFFFu)) {
+                *s_tail_flag = 1;
+                tail_seen = true;
+            }
         }
         // Tail of the launch.  From here on no lane gets a new env and the warps thin out: a warp with one live lane
         // costs as many issue slots per step as a full one, and with ~3.5 episodes per lane (C4: 2^18 envs) almost half
         // of all env-steps are played in this phase.  Once any warp of the CTA has seen the queue empty, all of them
-        // (each looks at the flag once per iteration) switch to rounds of PLAY3_TAIL_STEPS steps with a CTA-wide
+        // (each looks at the flag every eighth iteration) switch to rounds of PLAY3_TAIL_STEPS steps with a CTA-wide
         // compaction in between: the live envs move through shared memory into the lowest lanes of the CTA, warps
         // without envs only wait at the barrier, and the cost of a step follows the number of live envs.
-        if (*s_tail_flag) break;
+        if ((iter & 7u) == 0u && *s_tail_flag) tail_seen = true;
+        if (tail_seen) break;
         if (phase != PHASE_NONE) step();
     }
     unsigned round = 0;
@@ -519,6 +524,18 @@ play_record_compact_kernel(const u64* __restrict__ arena_boards, const uint8_t* 
     constexpr int K = 4;  // 32-step groups per iteration
     const int lane = threadIdx.x & 31;
     const int64_t warps = (int64_t)gridDim.x * (blockDim.x >> 5);
+    // potential of a pair of cells (one byte of the board): 8 shared-memory lookups per board instead of 16 x 6 instructions
+    __shared__ uint32_t s_pot[256];
+    {
+        const uint32_t lo = threadIdx.x & 15u, hi = (threadIdx.x >> 4) & 15u;
+        s_pot[threadIdx.x & 255] = (lo ? ((lo - 1u) << lo) : 0u) + (hi ? ((hi - 1u) << hi) : 0u);
+    }
+    __syncthreads();
+    auto potential = [&](u64 x) -> uint32_t {
+        const uint32_t a = (uint32_t)x, c = (uint32_t)(x >> 32);
+        return s_pot[a & 255u] + s_pot[(a >> 8) & 255u] + s_pot[(a >> 16) & 255u] + s_pot[a >> 24] +
+               s_pot[c & 255u] + s_pot[(c >> 8) & 255u] + s_pot[(c >> 16) & 255u] + s_pot[c >> 24];
+    };
     // log(1 / #legal) for 1..4 legal actions, computed once (the lock-step recorder's act_random_log_prob, bit for bit)
     float lp_of[5];
 #pragma unroll
@@ -544,7 +561,7 @@ play_record_compact_kernel(const u64* __restrict__ arena_boards, const uint8_t* 
             }
             uint32_t pot[K + 1];  // one potential per board: the neighbour's comes by shuffle
 #pragma unroll
-            for (int k = 0; k <= K; ++k) pot[k] = board_potential(b[k]);
+            for (int k = 0; k <= K; ++k) pot[k] = potential(b[k]);
 #pragma unroll
             for (int k = 0; k < K; ++k) {
                 const uint32_t t = t0 + 32u * k + (uint32_t)lane;

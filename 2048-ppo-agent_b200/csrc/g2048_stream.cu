@@ -115,20 +115,30 @@ expand_obs_tma_kernel(const u64* __restrict__ boards, int64_t n, T* __restrict__
         if (indices) src = __ldg(&indices[src]);  // gather: out[i] = onehot(boards[indices[i]])
         return __ldg(&boards[src * board_stride]);  // stride 4: the board of a 32-byte sample record
     };
-    int64_t img = (int64_t)blockIdx.x * OBS_WARPS + warp;
-    while (img < n_images) {
-        u64 round_boards[AHEAD ? OBS_NBUF : 1][PER_LANE];
-        if (AHEAD) {
+    // boards of one round of OBS_NBUF images (image j of the round starting at `base` is base + j * warps_total)
+    auto load_round = [&](int64_t base, u64 (&dst)[OBS_NBUF][PER_LANE]) {
 #pragma unroll
-            for (int j = 0; j < OBS_NBUF; ++j) {
-                const int64_t first = (img + (int64_t)j * warps_total) * G;
+        for (int j = 0; j < OBS_NBUF; ++j) {
+            const int64_t first = (base + (int64_t)j * warps_total) * G;
 #pragma unroll
-                for (int p = 0; p < PER_LANE; ++p) {
-                    const int c = lane + 32 * p;
-                    const int64_t src = first + (c >> 4);
-                    round_boards[j][p] = (c < CELLS && src < n) ? board_of(src) : 0ull;
-                }
+            for (int p = 0; p < PER_LANE; ++p) {
+                const int c = lane + 32 * p;
+                const int64_t src = first + (c >> 4);
+                dst[j][p] = (c < CELLS && src < n) ? board_of(src) : 0ull;
             }
+        }
+    };
+    int64_t img = (int64_t)blockIdx.x * OBS_WARPS + warp;
+    // AHEAD: the boards of the NEXT round are fetched while the current round's images are written -- with a gather every
+    // board is two dependent memory round trips (index, board), ~1.5 us that a warp used to spend waiting at the top of
+    // every round (37 rounds per warp at 2^19 samples: a quarter of the kernel).
+    u64 cur_boards[AHEAD ? OBS_NBUF : 1][PER_LANE];
+    if (AHEAD && img < n_images) load_round(img, cur_boards);
+    while (img < n_images) {
+        u64 next_boards[AHEAD ? OBS_NBUF : 1][PER_LANE];
+        if (AHEAD) {
+            const int64_t next = img + (int64_t)OBS_NBUF * warps_total;
+            if (next < n_images) load_round(next, next_boards);
         }
 #pragma unroll
         for (int j = 0; j < OBS_NBUF; ++j) {
@@ -147,7 +157,7 @@ expand_obs_tma_kernel(const u64* __restrict__ boards, int64_t n, T* __restrict__
                     const int g = c >> 4, cell = c & 15;
                     int pos = -1;
                     if (g < in_image) {
-                        const u64 b = AHEAD ? round_boards[j][p] : board_of(first + g);
+                        const u64 b = AHEAD ? cur_boards[j][p] : board_of(first + g);
                         pos = g * 496 + 31 * cell + (int)((b >> (4 * cell)) & 15ull);
                         buf[pos] = ObsOne<T>::one();
                     }
@@ -161,6 +171,12 @@ expand_obs_tma_kernel(const u64* __restrict__ boards, int64_t n, T* __restrict__
                 bulk_commit();
             }
             img += warps_total;
+        }
+        if (AHEAD) {
+#pragma unroll
+            for (int j = 0; j < OBS_NBUF; ++j)
+#pragma unroll
+                for (int p = 0; p < PER_LANE; ++p) cur_boards[j][p] = next_boards[j][p];
         }
     }
     if (SCALARS) {  // the minibatch's per-sample scalars, while the last bulk stores drain

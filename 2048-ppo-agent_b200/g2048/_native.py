@@ -102,6 +102,8 @@ _SIGNATURES = {
     "g2048_gae_flat_v1": (_INT, [_P, _P, _P, _I64, _DBL, _DBL, _P, _P, _P, _P, _P]),
     "g2048_gae_flat_pipelined": (_INT, [_P, _P, _P, _I64, _DBL, _DBL, _P, _P, _P, _P, _P]),
     "g2048_gae_flat_tiled": (_INT, [_P, _P, _P, _I64, _DBL, _DBL, _P, _P, _P, _P, _P]),
+    "g2048_gae_scan_scratch_bytes": (_I64, [_I64]),
+    "g2048_gae_flat_scan": (_INT, [_P, _P, _P, _I64, _DBL, _DBL, _P, _P, _P, _P, _P]),
     "g2048_gae_time_major": (_INT, [_P, _P, _P, _I64, _I64, _P, _DBL, _DBL, _P, _P, _P, _P]),
     "g2048_normalize": (_INT, [_P, _I64, _P, _INT, _P]),
     "g2048_gae_host": (_INT, [_P, _P, _P, _I64, _DBL, _DBL, _INT, _P, _P]),

@@ -441,6 +441,15 @@ int g2048_gae_flat_v1(const float* d_rewards, const float* d_values, const uint8
                       double lambda_gae, float* d_adv, float* d_ret, void* d_scan_state, double* d_moments,
                       void* stream);
 
+/* g2048_gae_flat as a segmented affine REVERSE SCAN (north_star's "warp shuffles handle the reverse-scan GAE"): same
+ * arguments and moments, its own scratch (g2048_gae_scan_scratch_bytes(n) bytes, 16-byte aligned, zeroed by the caller).
+ * The recurrence is re-associated (thread / warp-shuffle / CTA / decoupled look-back over 4 096-step tiles), so the
+ * results agree with the reference loop within the 1e-5 relative tolerance north_star states for GAE, NOT bit for bit --
+ * opt-in; g2048_gae_flat stays the bit-identical default.  A pure stream: no lane ever walks an episode. */
+int64_t g2048_gae_scan_scratch_bytes(int64_t n);
+int g2048_gae_flat_scan(const float* d_rewards, const float* d_values, const uint8_t* d_dones, int64_t n, double gamma,
+                        double lambda_gae, float* d_adv, float* d_ret, void* d_scan_state, double* d_moments, void* stream);
+
 /* Time-major (T,B) buffer, one lane per env, exactly the reference's operation order per env;
  * d_bootstrap (n) float32 or NULL is V(s_T) for envs whose last step is not done (fixed-horizon
  * rollouts with auto-reset; the reference itself never bootstraps). */

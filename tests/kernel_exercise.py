@@ -90,7 +90,7 @@ def run_all(E, g2048, T=torch, dev="cuda"):
         r = torch.rand(n, device=dev)
         v = torch.rand(n, device=dev)
         d = (torch.rand(n, device=dev) < 0.01).to(torch.uint8)
-        for entry in ("g2048_gae_flat", "g2048_gae_flat_pipelined", "g2048_gae_flat_tiled", "g2048_gae_flat_v1"):
+        for entry in ("g2048_gae_flat", "g2048_gae_flat_pipelined", "g2048_gae_flat_tiled", "g2048_gae_flat_v1", "g2048_gae_flat_scan"):
             adv, ret, mom = E.gae_flat(r, v, d, 0.99, 0.95, entry=entry)
             E.gae_flat(r, v, d, 0.99, 0.95, want_moments=False, entry=entry)
         E.normalize_(adv, mom, 1)

@@ -68,13 +68,16 @@ def test_runner_paths_agree_with_the_fused_step():
     import g2048
 
     class RowwiseAgent(torch.nn.Module):
+        """Every output row is computed from its input row with a fixed operation order (elementwise product and a row
+        sum over the LAST dimension, no GEMM), so a row's logits do not depend on which other rows are in the batch."""
+
         def __init__(self):
             super().__init__()
             g = torch.Generator().manual_seed(3)
-            self.w = torch.nn.Parameter(torch.randn(496, 5, generator=g) * 0.3)
+            self.w = torch.nn.Parameter(torch.randn(5, 496, generator=g) * 0.3)
 
-        def forward(self, obs, mask):
-            out = (obs.reshape(obs.shape[0], 496, 1) * self.w).sum(dim=1)  # row-wise: independent of the batch shape
+        def forward(self, obs, mask=None):
+            out = (obs.reshape(obs.shape[0], 1, 496) * self.w.unsqueeze(0)).sum(dim=2)
             return out[:, :4], out[:, 4:5]
 
     def make(**kw):
