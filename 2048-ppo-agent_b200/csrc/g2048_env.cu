@@ -286,6 +286,30 @@ rollout_steps_kernel(u64* __restrict__ boards, uint8_t* __restrict__ status, con
 }
 
 // ------------------------------------------------------------------------------------------------
+// replay of a few envs of a batch (the state after k steps of the built-in policies)
+// ------------------------------------------------------------------------------------------------
+template <int MODE, int POLICY>
+__global__ void __launch_bounds__(128)
+replay_envs_kernel(const uint2* __restrict__ subs, uint32_t batch_global, const int64_t* __restrict__ env_ids,
+                   const uint32_t* __restrict__ steps, int64_t m, u64* __restrict__ boards, uint8_t* __restrict__ status) {
+    const int64_t i = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
+    if (i >= m) return;
+    const uint32_t e = (uint32_t)env_ids[i];
+    EnvState s = env_init<MODE>(split_at<MODE>(Key{subs[0].x, subs[0].y}, batch_global, e));
+    const uint32_t k = steps[i];
+    for (uint32_t t = 0; t < k; ++t) {
+        const uint2 sa = __ldg(&subs[1 + 2 * (int64_t)t]);
+        const uint2 ss = __ldg(&subs[2 + 2 * (int64_t)t]);
+        const uint32_t lm = s.status & G2048_STATUS_MASK;
+        const int a = (POLICY == G2048_POLICY_RANDOM) ? act_random<MODE>(split_at<MODE>(Key{sa.x, sa.y}, batch_global, e), lm)
+                                                      : act_drul(lm);
+        env_step<MODE>(s, a, split_at<MODE>(Key{ss.x, ss.y}, batch_global, e));
+    }
+    boards[i] = s.board;
+    if (status) status[i] = (uint8_t)s.status;
+}
+
+// ------------------------------------------------------------------------------------------------
 // integer-issue probe
 // ------------------------------------------------------------------------------------------------
 __global__ void int_peak_kernel(int iters, uint32_t* __restrict__ sink) {
@@ -657,5 +681,32 @@ extern "C" int g2048_int_peak_probe(int blocks, int threads, int iters, uint32_t
     G2048_REQUIRE(blocks > 0 && threads > 0 && threads <= 1024 && iters > 0 && d_sink, "int_peak_probe");
     int_peak_kernel<<<blocks, threads, 0, (cudaStream_t)stream>>>(iters, d_sink);
     G2048_CHECK_LAUNCH("int_peak_probe");
+    return G2048_OK;
+}
+
+// State of the listed envs (GLOBAL indices, int64) of BatchRunner(seed).run_*(batch_global) after d_steps[i] loop steps of
+// the built-in policy -- e.g. the board an env held BEFORE its last step, which is what the reference's
+// run_actions_max_tile reads for the envs that live until the last loop step (src/runs/run_actions_max_tile.py:61-64).
+extern "C" int g2048_replay_envs(int policy, const uint32_t* d_subs, int64_t n_subs, int64_t batch_global,
+                                 const int64_t* d_env_ids, const uint32_t* d_steps, int64_t m, int rng_mode,
+                                 uint64_t* d_boards, uint8_t* d_status, void* stream) {
+    G2048_REQUIRE(policy == G2048_POLICY_RANDOM || policy == G2048_POLICY_DRUL, "replay_envs: policy");
+    G2048_REQUIRE(valid_mode(rng_mode) && batch_global > 0 && batch_global <= 0x7FFFFFFFll && m >= 0 && n_subs >= 1, "replay_envs");
+    if (m == 0) return G2048_OK;
+    G2048_REQUIRE(d_subs && d_env_ids && d_steps && d_boards, "replay_envs: pointers");
+    const unsigned g = blocks_for(m, 128);
+    cudaStream_t st = (cudaStream_t)stream;
+#define CALL_P(M, P) replay_envs_kernel<M, P><<<g, 128, 0, st>>>((const uint2*)d_subs, (uint32_t)batch_global, d_env_ids, d_steps, m, (u64*)d_boards, d_status)
+    if (policy == G2048_POLICY_RANDOM) {
+#define CALL(M) CALL_P(M, G2048_POLICY_RANDOM)
+        DISPATCH_MODE(rng_mode, CALL)
+#undef CALL
+    } else {
+#define CALL(M) CALL_P(M, G2048_POLICY_DRUL)
+        DISPATCH_MODE(rng_mode, CALL)
+#undef CALL
+    }
+#undef CALL_P
+    G2048_CHECK_LAUNCH("replay_envs");
     return G2048_OK;
 }

@@ -10,8 +10,8 @@
 // i.e. gae_t = f_t(gae_{t+1}) with the affine map f_t(x) = a_t x + delta_t; maps compose associatively
 // ((a1,b1) o (a2,b2) = (a1 a2, a1 b2 + b1)), so the suffix compositions F_t = f_t o f_{t+1} o ... are a scan:
 //   * a thread composes its 8 consecutive steps serially (registers, 128-bit loads),
-//   * a warp scans the 32 thread aggregates with shuffles (5 steps), the 16 warp aggregates go through shared memory,
-//   * tiles (4 096 steps, one per CTA, taken from the END of the buffer by ticket) are chained by decoupled look-back:
+//   * a warp scans the 32 thread aggregates with shuffles (5 steps), the 8 warp aggregates go through shared memory,
+//   * tiles (2 048 steps, one per CTA, taken from the END of the buffer by ticket) are chained by decoupled look-back:
 //     a tile publishes its aggregate (A, B) and, once it knows the gae entering it, the gae of its first step.  A tile
 //     that contains a `done` has A == 0 exactly, so its first-step gae is B and is published at once -- with episodes of
 //     a few hundred steps the chain is never longer than one tile and no CTA waits for another's look-back.
@@ -20,9 +20,9 @@
 
 namespace g2048 {
 
-constexpr int SCAN_THREADS = 512;
+constexpr int SCAN_THREADS = 256;
 constexpr int SCAN_ITEMS = 8;
-constexpr int SCAN_TILE = SCAN_THREADS * SCAN_ITEMS;  // 4 096 steps
+constexpr int SCAN_TILE = SCAN_THREADS * SCAN_ITEMS;  // 2 048 steps
 constexpr int SCAN_WARPS = SCAN_THREADS / 32;
 
 struct ScanHeader {
@@ -46,12 +46,11 @@ __device__ __forceinline__ Affine compose(Affine outer, Affine inner) {
 }
 
 template <bool ALIGNED>
-__global__ void __launch_bounds__(SCAN_THREADS)
+__global__ void __launch_bounds__(SCAN_THREADS, 2)
 gae_scan_kernel(const float* __restrict__ rewards, const float* __restrict__ values, const uint8_t* __restrict__ dones,
                 int64_t n, int64_t n_tiles, float gamma, float gamma_lambda, float* __restrict__ adv,
                 float* __restrict__ ret, ScanHeader* header, double* __restrict__ moments) {
     __shared__ Affine s_warp[SCAN_WARPS];
-    __shared__ float s_carry;
     __shared__ unsigned int s_ticket;
     __shared__ double s_red[4 * SCAN_WARPS];
 
@@ -121,46 +120,41 @@ gae_scan_kernel(const float* __restrict__ rewards, const float* __restrict__ val
     after = compose(after, later);  // everything between my last step and the end of the tile
 
     // ---- chain the tiles: publish, look back -----------------------------------------------------------------------
+    // gae of the first step of the next tile (0 past the end of the buffer): the first-step gae of the first following
+    // tile that knows it, pushed through the aggregates of the tiles in between.  Any thread may ask; tiles with a later
+    // index hold earlier tickets, so they are running and the wait is short.
+    auto look_back = [&]() -> float {
+        Affine acc{1.0f, 0.0f};
+        for (int64_t j = tile + 1;; ++j) {
+            if (j == n_tiles) return acc.b;  // ran off the end of the buffer: the gae entering it is 0
+            volatile unsigned long long* w = &tiles[j].word;
+            unsigned long long word;
+            do {
+                word = *w;
+            } while ((unsigned)(word >> 32) == 0u);
+            const float val = __uint_as_float((unsigned)word);
+            if ((unsigned)(word >> 32) == SCAN_INCL) return acc.a * val + acc.b;
+            __threadfence();
+            acc = compose(acc, Affine{*(volatile float*)&tiles[j].a, val});
+        }
+    };
     if (threadIdx.x == 0) {
-        const Affine whole = compose(incl, later);  // thread 0: lanes 0..31 of warp 0, then warps 1..15
+        const Affine whole = compose(incl, later);  // thread 0: lanes 0..31 of warp 0, then the later warps
         volatile unsigned long long* my_word = &tiles[tile].word;
-        const bool last_tile = tile == n_tiles - 1;
-        float x = 0.0f;  // gae of the first step of the next tile (0 past the end of the buffer)
-        if (whole.a == 0.0f || last_tile) {
-            // nothing of what follows reaches my first step: its gae is known now
+        if (whole.a == 0.0f || tile == n_tiles - 1) {
+            // nothing of what follows reaches my first step (or nothing follows): its gae is known now
             *my_word = ((unsigned long long)SCAN_INCL << 32) | (unsigned long long)__float_as_uint(whole.b);
         } else {
             tiles[tile].a = whole.a;
             __threadfence();
             *my_word = ((unsigned long long)SCAN_AGG << 32) | (unsigned long long)__float_as_uint(whole.b);
+            const float x0 = look_back();
+            *my_word = ((unsigned long long)SCAN_INCL << 32) | (unsigned long long)__float_as_uint(whole.a * x0 + whole.b);
         }
-        if (!last_tile) {
-            Affine acc{1.0f, 0.0f};  // composition of the tiles between me and the one whose first-step gae is known
-            for (int64_t j = tile + 1;; ++j) {
-                if (j == n_tiles) {
-                    x = acc.b;  // ran off the end of the buffer: gae entering it is 0
-                    break;
-                }
-                volatile unsigned long long* w = &tiles[j].word;
-                unsigned long long word;
-                do {
-                    word = *w;
-                } while ((unsigned)(word >> 32) == 0u);  // tile j holds an earlier ticket: it is running
-                const float val = __uint_as_float((unsigned)word);
-                if ((unsigned)(word >> 32) == SCAN_INCL) {
-                    x = acc.a * val + acc.b;
-                    break;
-                }
-                __threadfence();
-                acc = compose(acc, Affine{*(volatile float*)&tiles[j].a, val});
-            }
-            if (whole.a != 0.0f)
-                *my_word = ((unsigned long long)SCAN_INCL << 32) | (unsigned long long)__float_as_uint(whole.a * x + whole.b);
-        }
-        s_carry = x;
     }
-    __syncthreads();
-    const float x = s_carry;
+    // Only the steps after the tile's last `done` see the next tile at all (after.a != 0): with episodes of a few hundred
+    // steps that is the last warp or two of the CTA; every other thread goes straight on to its stores.
+    const float x = (after.a != 0.0f) ? look_back() : 0.0f;
 
     // ---- apply: the gae entering my steps, then the reference's own recurrence over them ----------------------------
     float g = after.a * x + after.b;

@@ -32,6 +32,12 @@ constexpr int PLAY3_TABLE_BYTES = 65536 * 2 + 65536;
 #ifndef G2048_PLAY3_TAIL_STEPS
 #define G2048_PLAY3_TAIL_STEPS 8
 #endif
+#ifndef G2048_PLAY3_TAIL
+#define G2048_PLAY3_TAIL 1  // 0: no tail compaction (a warp leaves when its lanes are done), for A/B timing
+#endif
+#ifndef G2048_PLAY3_TAIL_POLL
+#define G2048_PLAY3_TAIL_POLL 7u  // the CTA's tail flag is looked at when (iteration & POLL) == 0
+#endif
 constexpr int PLAY3_TAIL_STEPS = G2048_PLAY3_TAIL_STEPS;  // steps between two compactions of the CTA's live envs in the tail
 // what moves with an env when the tail compaction hands it to another lane (32 bytes)
 struct TailEntry {
@@ -313,10 +319,17 @@ play3_kernel(const uint2* __restrict__ subs, int64_t n_subs, uint32_t batch_glob
                 }
             }
             // The queue is empty (or, recording, no idle lane of this warp can take an env any more): tell the CTA.
+#if G2048_PLAY3_TAIL
             if (exhausted || (REC && want == 0u && idle == 0xFFFFFFFFu)) {
                 *s_tail_flag = 1;
                 tail_seen = true;
             }
+#else
+            if (__ballot_sync(0xFFFFFFFFu, phase != PHASE_NONE) == 0u && (exhausted || want == 0u)) {
+                tail_seen = true;  // nothing left for this warp
+                *s_tail_flag = 2;  // (value unused: keeps the variable referenced)
+            }
+#endif
         }
         // Tail of the launch.  From here on no lane gets a new env and the warps thin out: a warp with one live lane
         // costs as many issue slots per step as a full one, and with ~3.5 episodes per lane (C4: 2^18 envs) almost half
@@ -324,12 +337,14 @@ play3_kernel(const uint2* __restrict__ subs, int64_t n_subs, uint32_t batch_glob
         // (each looks at the flag every eighth iteration) switch to rounds of PLAY3_TAIL_STEPS steps with a CTA-wide
         // compaction in between: the live envs move through shared memory into the lowest lanes of the CTA, warps
         // without envs only wait at the barrier, and the cost of a step follows the number of live envs.
-        if ((iter & 7u) == 0u && *s_tail_flag) tail_seen = true;
+#if G2048_PLAY3_TAIL
+        if ((iter & G2048_PLAY3_TAIL_POLL) == 0u && *s_tail_flag) tail_seen = true;
+#endif
         if (tail_seen) break;
         if (phase != PHASE_NONE) step();
     }
     unsigned round = 0;
-    while (true) {
+    while (G2048_PLAY3_TAIL) {
         park_finished();
         // ---- compaction: live envs -> pool -> lanes 0 .. total-1 of the CTA ----------------------------------------
         unsigned* cnt = &s_tail_cnt[round & 1u];

@@ -132,10 +132,10 @@ expand_obs_tma_kernel(const u64* __restrict__ boards, int64_t n, T* __restrict__
     // AHEAD: the boards of the NEXT round are fetched while the current round's images are written -- with a gather every
     // board is two dependent memory round trips (index, board), ~1.5 us that a warp used to spend waiting at the top of
     // every round (37 rounds per warp at 2^19 samples: a quarter of the kernel).
-    u64 cur_boards[AHEAD ? OBS_NBUF : 1][PER_LANE];
+    u64 cur_boards[OBS_NBUF][PER_LANE];  // dead code without AHEAD
     if (AHEAD && img < n_images) load_round(img, cur_boards);
     while (img < n_images) {
-        u64 next_boards[AHEAD ? OBS_NBUF : 1][PER_LANE];
+        u64 next_boards[OBS_NBUF][PER_LANE];
         if (AHEAD) {
             const int64_t next = img + (int64_t)OBS_NBUF * warps_total;
             if (next < n_images) load_round(next, next_boards);

@@ -62,6 +62,7 @@ _SIGNATURES = {
     "g2048_gather_samples": (_INT, [_P, _I64, _P, _INT, _P, _P, _P, _P, _P, _P, _P, _P, _P]),
     "g2048_policy_step_obs": (_INT, [_P, _P, _P, _P, _INT, _INT, _INT, _P, _P, _INT, _I64, _I64, _I64, _INT, _P, _P, _P, _P, _P,
                                      _P, _INT, _P, _P, _P]),
+    "g2048_replay_envs": (_INT, [_INT, _P, _I64, _I64, _P, _P, _I64, _INT, _P, _P, _P]),
     "g2048_play": (_INT, [_INT, _P, _I64, _I64, _I64, _I64, _INT, _P, _P, _P, _P, _P, _P]),
     "g2048_play_tables": (_INT, [_INT, _P, _I64, _I64, _I64, _I64, _INT, _P, _P, _P, _P, _P, _P]),
     "g2048_play_swar": (_INT, [_INT, _P, _I64, _I64, _I64, _I64, _INT, _P, _P, _P, _P, _P, _P]),

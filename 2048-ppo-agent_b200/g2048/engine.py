@@ -183,6 +183,18 @@ def play(policy: int, subs: torch.Tensor, batch_global: int, env_lo: int, n: int
     return dict(final_boards=boards, lengths=lengths, scores=scores, stats=stats)
 
 
+def replay_envs(policy: int, subs: torch.Tensor, batch_global: int, env_ids: torch.Tensor, steps: torch.Tensor, rng_mode: int):
+    """Boards and status of the listed envs (global indices, int64) after steps[i] (int32) loop steps of the built-in
+    policy.  -> boards (m,) int64, status (m,) uint8."""
+    m = env_ids.shape[0]
+    assert env_ids.dtype == torch.int64 and steps.dtype == torch.int32 and steps.shape[0] == m
+    boards = torch.empty(m, dtype=torch.int64, device=subs.device)
+    status = torch.empty(m, dtype=torch.uint8, device=subs.device)
+    call("g2048_replay_envs", policy, ptr(_i32(subs)), subs.shape[0], batch_global, ptr(env_ids), ptr(steps), m, rng_mode,
+         ptr(boards), ptr(status), stream_ptr())
+    return boards, status
+
+
 def row_table_lookup(rows: torch.Tensor):
     """Test hook: table entries (row moved left, move flags) of int16 rows."""
     n = rows.shape[0]

@@ -151,7 +151,7 @@ class BatchRunner:
         """-> (observations (B,T,4,4,31) bool, actions (B,T) int32, action_masks (B,T,4) bool,
         log_probs (B,T) f32 | None, values (B,T) f32 | None, rewards (B,T) f32, terminations (B,T) bool),
         numpy arrays stacked like batch_runner.py:138-154."""
-        ro = self._run(batch_size, keep_states=False, full_records=True)
+        ro = self._run(batch_size, full_records=True)
         t, b = ro.t_steps, ro.batch_size
         obs = E.expand_obs(ro.boards, torch.bool, rows=t, n_cols=b)
         un = E.unpack_records(ro.meta, ro.rewards, ro.log_probs, ro.values, t, b)
@@ -167,19 +167,35 @@ class BatchRunner:
         )
 
     def run_rollout_batch(self, batch_size: int) -> list:
-        """-> list[State], the init state first (batch_runner.py:156-195)."""
-        return self._run(batch_size, keep_states=True)
+        """-> list[State], the init state first (batch_runner.py:156-195).  The run itself is the recorded one of
+        ``run_actions_batch`` (whole chunks of steps per launch); the states are views of its records: the board after
+        step t is the pre-step board of step t + 1 (a finished env keeps its frozen board), its legal mask the pre-step
+        mask of step t + 1, its terminated flag and reward those of step t."""
+        ro = self._run(batch_size, full_records=True)
+        t = ro.t_steps
+        mask = (ro.meta >> 2) & N.STATUS_MASK
+        done = ((ro.meta >> 6) & 1) << 4
+        status = torch.cat([mask[:1], mask[1:] | done[:-1], ro.final_status.unsqueeze(0)])  # (T + 1, n)
+        zero = torch.zeros(ro.batch_size, dtype=torch.float32, device=self.device)
+        states = [State(ro.boards[0], status[0], zero)] if t else [State(ro.final_boards, ro.final_status, zero)]
+        for k in range(t):
+            states.append(State(ro.boards[k + 1] if k + 1 < t else ro.final_boards, status[k + 1], ro.rewards[k]))
+        return states
 
     # -- engine-native results -----------------------------------------------------------------
     def run_packed_batch(self, batch_size: int) -> PackedRollout:
         """Same run as ``run_actions_batch`` but the records stay packed on the device (with ``compact_live`` the
         slots of steps after an env's end are zero)."""
-        return self._run(batch_size, keep_states=False, full_records=False)
+        return self._run(batch_size, full_records=False)
 
-    def run_stats_batch(self, batch_size: int, per_env: bool = True) -> dict:
+    def run_stats_batch(self, batch_size: int, per_env: bool = True, last_stored_boards: bool = False) -> dict:
         """Play to termination and return only per-episode results (final boards, lengths, scores)
         and the reduced statistics block.  Built-in policies only: this is the persistent
-        ``g2048_play`` kernel."""
+        ``g2048_play`` kernel.
+        last_stored_boards: also return ``last_stored_boards`` -- what the reference's ``observations[:, -1]`` shows
+        (src/runs/run_actions_max_tile.py:61-64): an env's final board, except for the envs that live until the last
+        loop step, whose last STORED observation is the board before that step (``g2048_replay_envs`` replays just
+        those envs, usually one)."""
         self._check(batch_size)
         policy = getattr(self._act_fn, "policy_id", None)
         if policy is None:
@@ -194,6 +210,15 @@ class BatchRunner:
             if st["cut_short"] == 0:
                 break
             max_steps *= 4  # an episode outlived the keys that were generated: replay with more
+        if last_stored_boards and per_env:
+            longest = st["longest"]  # over all shards: the reference's number of loop steps
+            ids = torch.nonzero(out["lengths"] == longest).flatten()
+            stored = out["final_boards"].clone()
+            if ids.numel():
+                steps = torch.full((ids.numel(),), longest - 1, dtype=torch.int32, device=self.device)
+                before, _ = E.replay_envs(policy, subs, batch_size, ids + lo, steps, self.rng_mode)
+                stored[ids] = before
+            out["last_stored_boards"] = stored
         self.chain.consume(1 + 2 * st["longest"])
         out["stats"] = stats
         out["summary"] = st
@@ -308,108 +333,82 @@ class BatchRunner:
 
         return all_ranks_true(done_count == n, self.device)
 
-    def _run(self, batch_size: int, keep_states: bool, full_records: bool = True):
-        """full_records: the caller reads the records of finished envs too (reference-format outputs)."""
+    def _run(self, batch_size: int, keep_states: bool = False, full_records: bool = True) -> PackedRollout:
+        """A recorded run.  full_records: the caller reads the records of finished envs too (reference-format outputs)."""
         self._check(batch_size)
         lo, n = self._range(batch_size)
         dev, mode = self.device, self.rng_mode
         init_sub = self.chain.peek(1)[0]
         boards, status = E.env_init(init_sub, batch_size, lo, n, mode)
-        states = [State(boards.clone(), status.clone(), torch.zeros(n, dtype=torch.float32, device=dev))] if keep_states else None
         policy = getattr(self._act_fn, "policy_id", None)
         is_net = hasattr(self._act_fn, "forward_logits")
-        if self.cuda_graph and is_net and not keep_states:
+        if self.cuda_graph and is_net:
             return self._run_net_graphed(batch_size, lo, n, boards, status)
-        if is_net and not keep_states:
+        if is_net:
             return self._run_net(batch_size, lo, n, boards, status, compact=self.compact_live and not full_records)
-        compact = self.compact_live and policy is not None and not keep_states and not full_records
-        live_ids = None  # int64 local indices of the envs still alive (compact mode), refreshed when some finish
+        if policy is None:
+            return self._run_callable(batch_size, lo, n, boards, status)
+        # built-in policies: whole chunks of loop steps per launch (lock-step recorder); the kernel keeps the number of
+        # finished envs and the longest episode on the device, read once per chunk
+        compact = self.compact_live and not full_records
         counters = torch.zeros(4, dtype=torch.int64, device=dev)
-        chunks = []  # (boards, meta, rewards, log_probs, values) per chunk, time-major
-        t0 = 0
+        chunks, t0 = [], 0
         want_lp = policy != E.POLICY_DRUL
-        want_v = policy is None
         while True:
             # a run whose envs are all finished at init cannot happen (two tiles on an empty board)
-            steps = 1 if keep_states else CHUNK_STEPS
+            steps = CHUNK_STEPS
             subs = self.chain.peek(1 + 2 * (t0 + steps))
             alloc = torch.zeros if compact else torch.empty  # compact mode leaves finished envs' slots untouched
             rb = alloc((steps, n), dtype=torch.int64, device=dev)
             rm = alloc((steps, n), dtype=torch.uint8, device=dev)
             rr = alloc((steps, n), dtype=torch.float32, device=dev)
             rl = alloc((steps, n), dtype=torch.float32, device=dev) if want_lp else None
-            rv = alloc((steps, n), dtype=torch.float32, device=dev) if want_v else None
-            if policy is not None:
-                if compact:  # the envs alive at the start of the chunk; one that finishes inside it leaves the loop
-                    live_ids = torch.nonzero((status & N.STATUS_DONE) == 0).flatten()
-                    E.rollout_steps_live(policy, boards, status, subs[1 + 2 * t0:], steps, t0, batch_size, lo, mode,
-                                         live_ids, rb, rm, rr, rl, counters)
-                else:
-                    E.rollout_steps(policy, boards, status, subs[1 + 2 * t0:], steps, t0, batch_size, lo, mode,
-                                    rb, rm, rr, rl, counters)
-                done_total = int(counters[0].item())
-                if keep_states:
-                    states.append(State(boards.clone(), status.clone(), rr[0].clone()))
+            if compact:  # the envs alive at the start of the chunk; one that finishes inside it leaves the loop
+                live_ids = torch.nonzero((status & N.STATUS_DONE) == 0).flatten()
+                E.rollout_steps_live(policy, boards, status, subs[1 + 2 * t0:], steps, t0, batch_size, lo, mode,
+                                     live_ids, rb, rm, rr, rl, counters)
             else:
-                done_total = None
-                for k in range(steps):
-                    t = t0 + k
-                    sub_act, sub_step = subs[1 + 2 * t], subs[2 + 2 * t]
-                    if compact:
-                        if live_ids is None:
-                            live_ids = torch.nonzero((status & N.STATUS_DONE) == 0).flatten()
-                        rl_k, rv_k = self._net_step_live(boards, status, live_ids, sub_act, sub_step, batch_size, lo, mode,
-                                                         rb[k], rm[k], rr[k], rl[k], rv[k])
-                    else:
-                        step_fn = self._net_step if is_net else self._callable_step
-                        rl_k, rv_k = step_fn(boards, status, sub_act, sub_step, batch_size, lo, mode, rb[k], rm[k], rr[k],
-                                             None if rl is None else rl[k], None if rv is None else rv[k])
-                    if rl_k is None:
-                        rl = None  # the policy returns no log-probs (like act_drul)
-                    if rv_k is None:
-                        rv = None
-                    if keep_states:
-                        states.append(State(boards.clone(), status.clone(), rr[k].clone()))
-                    # the reference checks `all done` after every step (batch_runner.py:117)
-                    done_now = int(((status & N.STATUS_DONE) != 0).sum().item())
-                    if compact and live_ids is not None and n - done_now != live_ids.shape[0]:
-                        live_ids = None  # some envs finished on this step: rebuild the list before the next one
-                    if self._all_done(done_now, n):
-                        steps_used = k + 1
-                        rb, rm, rr = rb[:steps_used], rm[:steps_used], rr[:steps_used]
-                        rl = None if rl is None else rl[:steps_used]
-                        rv = None if rv is None else rv[:steps_used]
-                        done_total = n
-                        break
-                else:
-                    steps_used = steps
-                steps = steps_used
-            chunks.append((rb, rm, rr, rl, rv))
+                E.rollout_steps(policy, boards, status, subs[1 + 2 * t0:], steps, t0, batch_size, lo, mode,
+                                rb, rm, rr, rl, counters)
+            chunks.append((rb, rm, rr, rl))
             t0 += steps
-            if policy is not None:
-                finished = self._all_done(done_total, n)
-            else:
-                finished = done_total == n
-            if finished:
+            if self._all_done(int(counters[0].item()), n):
                 break
-        if policy is not None:
-            t_total = int(counters[1].item())
-            if self.shard is not None and self.shard[1] > 1:
-                from ..dist import allreduce_max_int
+        t_total = int(counters[1].item())
+        if self.shard is not None and self.shard[1] > 1:
+            from ..dist import allreduce_max_int
 
-                t_total = allreduce_max_int(t_total, self.device)
-        else:
-            t_total = t0
+            t_total = allreduce_max_int(t_total, self.device)
         self.chain.consume(1 + 2 * t_total)
-        if keep_states:
-            return states[: t_total + 1]
-        cat = lambda i: None if any(c[i] is None for c in chunks) else torch.cat([c[i] for c in chunks])[:t_total].contiguous()  # noqa: E731
-        rb, rm, rr, rl, rv = (cat(i) for i in range(5))
-        if policy is not None:
-            env_steps = int(counters[2].item())
-        else:
-            env_steps = int(E.episode_lengths(rm, t_total, n).sum().item())
-        return PackedRollout(rb, rm, rr, rl, rv, boards, status, t_total, n, env_steps)
+        cat = lambda i: None if chunks[0][i] is None else torch.cat([c[i] for c in chunks])[:t_total].contiguous()  # noqa: E731
+        rb, rm, rr, rl = (cat(i) for i in range(4))
+        return PackedRollout(rb, rm, rr, rl, None, boards, status, t_total, n, int(counters[2].item()))
+
+    def _run_callable(self, batch_size: int, lo: int, n: int, boards, status) -> PackedRollout:
+        """Any Python callable ``(keys, obs, mask) -> (action, log_prob, value)`` (the reference's act_fn contract,
+        src/runs/batch_runner.py:120-124): the policy runs on the host side of every step, so this path keeps the
+        reference's structure -- per step ``g2048_split_keys``, the callable, ``g2048_env_step`` -- and its per-step
+        ``all done`` test."""
+        dev, mode = self.device, self.rng_mode
+        rows, t = [], 0
+        has_lp = has_v = True
+        while True:
+            subs = self.chain.peek(1 + 2 * (t + 1))
+            rb = torch.empty(n, dtype=torch.int64, device=dev)
+            rm = torch.empty(n, dtype=torch.uint8, device=dev)
+            rr, rl, rv = (torch.empty(n, dtype=torch.float32, device=dev) for _ in range(3))
+            rl_k, rv_k = self._callable_step(boards, status, subs[1 + 2 * t], subs[2 + 2 * t], batch_size, lo, mode, rb, rm, rr, rl, rv)
+            has_lp &= rl_k is not None  # the policy returns no log-probs (like act_drul)
+            has_v &= rv_k is not None
+            rows.append((rb, rm, rr, rl, rv))
+            t += 1
+            # the reference checks `all done` after every step (batch_runner.py:117)
+            if self._all_done(int(((status & N.STATUS_DONE) != 0).sum().item()), n):
+                break
+        self.chain.consume(1 + 2 * t)
+        rb, rm, rr, rl, rv = (torch.stack([r[i] for r in rows]) for i in range(5))
+        env_steps = int(E.episode_lengths(rm, t, n).sum().item())
+        return PackedRollout(rb, rm, rr, rl if has_lp else None, rv if has_v else None, boards, status, t, n, env_steps)
 
     # -- eager network-policy loop: one fused launch per step, one host synchronisation per chunk ----------------------
     def _run_net(self, batch_size: int, lo: int, n: int, boards, status, compact: bool) -> PackedRollout:

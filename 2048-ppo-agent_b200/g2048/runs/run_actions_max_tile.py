@@ -13,13 +13,13 @@ def run_actions_max_tile(init_seed: int, batch_size: int, num_envs: int, act_fn:
                          exact_reference_quirk: bool = True) -> RunningStatsVec:
     """Runs num_envs // batch_size batches and accumulates the max tile of every episode.
 
-    For act_randomly / act_drul each batch is one persistent ``g2048_play`` launch: the max tile is
-    reduced on the device instead of materialising the (B,T,16,31) observations and taking
-    argmax / 2** / max on the host (run_actions_max_tile.py:61-67).
+    For act_randomly / act_drul each batch is one persistent ``g2048_play`` launch -- no (B,T,16,31) observations are
+    materialised for the argmax / 2** / max of run_actions_max_tile.py:61-67.
 
     exact_reference_quirk: the reference reads the last stored PRE-step observation (:64 with
     batch_runner.py:121,130), so for the env(s) that live until the last loop step the final merge
-    and spawn are not counted.  True reproduces that; False uses each env's real final board.
+    and spawn are not counted.  True reproduces that -- ``g2048_replay_envs`` replays just those envs (usually one) up to
+    their last step --; False uses each env's real final board.
     """
     if num_envs % batch_size != 0:
         warnings.warn(
@@ -30,9 +30,9 @@ def run_actions_max_tile(init_seed: int, batch_size: int, num_envs: int, act_fn:
     stats = RunningStatsVec()
     fused = getattr(act_fn, "policy_id", None) is not None
     for _ in range(num_envs // batch_size):
-        if fused and not exact_reference_quirk:
-            out = runner.run_stats_batch(batch_size, per_env=True)
-            final_boards = out["final_boards"]
+        if fused:
+            out = runner.run_stats_batch(batch_size, per_env=True, last_stored_boards=exact_reference_quirk)
+            final_boards = out["last_stored_boards"] if exact_reference_quirk else out["final_boards"]
         else:
             ro = runner.run_packed_batch(batch_size)
             # last stored observation = the board BEFORE the last loop step (frozen envs keep theirs)

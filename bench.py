@@ -656,7 +656,7 @@ def secondary_measurements(E, N, torch, dev, flush_buf) -> dict:
 
     t = timed(gae_scan)
     add("gae_scan_kernel (opt-in: re-associated reverse scan, 1e-5 relative)", n_g * 17, t,
-        "same buffer and bytes as gae_flat4_kernel above; warp-shuffle affine scan with decoupled look-back over 4 096-step tiles "
+        "same buffer and bytes as gae_flat4_kernel above; warp-shuffle affine scan with decoupled look-back over 2 048-step tiles "
         "(north_star's own design); within 1e-5 relative of the reference loop instead of bit-identical; includes zeroing the scratch")
     t = timed(lambda: N.call("g2048_normalize", N.ptr(adv), n_g, N.ptr(mom), 1, N.stream_ptr()))
     add("normalize_kernel", n_g * 8, t, "2^26 steps in place; 4 B read + 4 B written per step")

@@ -220,6 +220,14 @@ int g2048_rollout_steps_live(int policy, uint64_t* d_boards, uint8_t* d_status, 
                              const int64_t* d_env_ids, int64_t n_live, uint64_t* d_rec_boards, uint8_t* d_rec_meta,
                              float* d_rec_rewards, float* d_rec_log_probs, uint64_t* d_counters, void* stream);
 
+/* State of m listed envs (d_env_ids: GLOBAL env indices, int64) of the run BatchRunner(seed).run_*(batch_global) after
+ * d_steps[i] loop steps of the built-in policy (d_subs as for g2048_play; each env needs 1 + 2 * d_steps[i] <= n_subs sub
+ * keys).  One thread per listed env; meant for a handful of envs -- e.g. the board an env held BEFORE its last step,
+ * which is what the reference's run_actions_max_tile reads for the envs that live until the last loop step
+ * (src/runs/run_actions_max_tile.py:61-64 with src/runs/batch_runner.py:121,130).  d_status may be NULL. */
+int g2048_replay_envs(int policy, const uint32_t* d_subs, int64_t n_subs, int64_t batch_global, const int64_t* d_env_ids,
+                      const uint32_t* d_steps, int64_t m, int rng_mode, uint64_t* d_boards, uint8_t* d_status, void* stream);
+
 /* ---- policy-logit sampling fused with the step and the rollout-buffer write
  * (src/ppo/torch_action_wrapper.py:84-102 + src/ppo/ppo_agent.py:117-121 + env.step + the
  * bookkeeping of src/runs/batch_runner.py:130-136).  One loop step:
@@ -443,7 +451,7 @@ int g2048_gae_flat_v1(const float* d_rewards, const float* d_values, const uint8
 
 /* g2048_gae_flat as a segmented affine REVERSE SCAN (north_star's "warp shuffles handle the reverse-scan GAE"): same
  * arguments and moments, its own scratch (g2048_gae_scan_scratch_bytes(n) bytes, 16-byte aligned, zeroed by the caller).
- * The recurrence is re-associated (thread / warp-shuffle / CTA / decoupled look-back over 4 096-step tiles), so the
+ * The recurrence is re-associated (thread / warp-shuffle / CTA / decoupled look-back over 2 048-step tiles), so the
  * results agree with the reference loop within the 1e-5 relative tolerance north_star states for GAE, NOT bit for bit --
  * opt-in; g2048_gae_flat stays the bit-identical default.  A pure stream: no lane ever walks an episode. */
 int64_t g2048_gae_scan_scratch_bytes(int64_t n);

@@ -35,7 +35,7 @@ def assert_within_tolerance(got, want, what):
     worst = int(np.argmax(err - bound))
     assert (err <= bound).all(), f"{what}: |d|={err[worst]:.3e} at {worst}, value {want[worst]:.6e}, rms {scale:.3e}"
     plain = err <= RTOL * np.abs(want)
-    assert plain.mean() > 0.999, f"{what}: only {plain.mean():.5f} of the elements within plain {RTOL} relative"
+    assert plain.mean() >= 0.995, f"{what}: only {plain.mean():.5f} of the elements within plain {RTOL} relative"
 
 
 @pytest.mark.parametrize("tag", TAGS)
@@ -87,7 +87,7 @@ def test_scan_at_c4_size_with_thousand_step_episodes(E):
         err = (got.double() - want.double()).abs()
         bound = RTOL * torch.maximum(want.double().abs(), scale)
         assert bool((err <= bound).all()), what
-        assert float((err <= RTOL * want.double().abs()).double().mean()) > 0.999, what
+        assert float((err <= RTOL * want.double().abs()).double().mean()) >= 0.995, what
     torch.testing.assert_close(mom, want_m, rtol=1e-6, atol=1e-3)
 
 
