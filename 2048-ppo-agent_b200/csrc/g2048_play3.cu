@@ -35,9 +35,7 @@ constexpr int PLAY3_TABLE_BYTES = 65536 * 2 + 65536;
 #ifndef G2048_PLAY3_TAIL
 #define G2048_PLAY3_TAIL 1  // 0: no tail compaction (a warp leaves when its lanes are done), for A/B timing
 #endif
-#ifndef G2048_PLAY3_TAIL_POLL
-#define G2048_PLAY3_TAIL_POLL 7u  // the CTA's tail flag is looked at when (iteration & POLL) == 0
-#endif
+
 constexpr int PLAY3_TAIL_STEPS = G2048_PLAY3_TAIL_STEPS;  // steps between two compactions of the CTA's live envs in the tail
 // what moves with an env when the tail compaction hands it to another lane (32 bytes)
 struct TailEntry {
@@ -104,6 +102,230 @@ struct PlayRecordArena {
     unsigned long long* env_slot;  // (n) slot of step 0 of env i
 };
 
+// Everything a lane holds: its env, the finished episode it has parked, its share of the statistics.
+struct Play3Lane {
+    u64 board, boardT;  // the board and its transpose
+    uint32_t lm, e, t, fours, phase;
+    bool seen15;
+    bool fin_live, fin_cut;  // the live fields hold a finished episode that is not parked yet
+    // Episode epilogue (score from the final board, result stores, statistics: ~150 instructions).  Lanes finish
+    // one at a time -- a warp meets a finished episode on roughly every fourth step -- so running the epilogue on the
+    // spot means running it with one active lane, ~4 % of the kernel's instructions.  A finished lane parks its final
+    // state in a second register set instead and takes the next env at once; the epilogue runs for all parked lanes
+    // together when PLAY3_EPILOGUE_BATCH of them have gathered (or a parked lane finishes again, or at the end).
+    // 2^21 envs, random policy: 25.76 G env-steps/s with the epilogue on the spot, 26.22 batched by 8, 26.32 by 16 or 32.
+    u64 pk_board;
+    uint32_t pk_t, pk_fours, pk_e;
+    bool pk_has, pk_cut, pk_seen15;
+    uint32_t st_episodes, st_cut, st_ovf, st_longest;
+    unsigned long long st_steps, st_score, st_tile, st_tile2;
+    unsigned long long slot, slot_end;  // recording: next free slot of the arena region being written, end of the lane's own region
+};
+
+// What is constant over the launch.
+struct Play3Ctx {
+    const uint2* subs;
+    uint2 init_sub;
+    uint32_t max_steps, batch_global, env_lo;
+    const uint16_t* s_left;
+    const uint8_t* s_flags;
+    unsigned long long* s_stats;
+    u64* final_boards;
+    uint32_t* lengths;
+    uint32_t* scores;
+    uint4* results;
+    PlayRecordArena rec;
+};
+
+__device__ __forceinline__ void play3_epilogue(Play3Lane& L, const Play3Ctx& c) {
+    if (L.pk_has) {
+        const uint32_t score = board_potential(L.pk_board) - 4u * L.pk_fours;
+        if (c.final_boards) c.final_boards[L.pk_e] = L.pk_board;
+        if (c.lengths) c.lengths[L.pk_e] = L.pk_t;
+        if (c.scores) c.scores[L.pk_e] = score;
+        if (c.results) c.results[L.pk_e] = make_uint4((uint32_t)L.pk_board, (uint32_t)(L.pk_board >> 32), L.pk_t, score);  // G2048EpisodeResult
+        const uint32_t me = max_exponent(L.pk_board);
+        const unsigned long long tile = 1ull << me;
+        L.st_episodes += 1;
+        L.st_steps += L.pk_t;
+        L.st_score += score;
+        L.st_cut += L.pk_cut ? 1u : 0u;
+        L.st_ovf += (L.pk_seen15 || has_max_nibble(L.pk_board)) ? 1u : 0u;
+        L.st_longest = max(L.st_longest, L.pk_t);
+        L.st_tile += tile;
+        L.st_tile2 += tile * tile;
+        atomicAdd(&c.s_stats[16 + me], 1ull);
+        L.pk_has = false;
+    }
+}
+
+// park what the lanes that just finished still hold (call converged)
+__device__ __forceinline__ void play3_park(Play3Lane& L, const Play3Ctx& c) {
+    const unsigned fresh = __ballot_sync(0xFFFFFFFFu, L.fin_live);
+    if (fresh) {
+        const unsigned parked = __ballot_sync(0xFFFFFFFFu, L.pk_has);
+        if ((fresh & parked) != 0u || __popc(fresh | parked) >= PLAY3_EPILOGUE_BATCH) play3_epilogue(L, c);
+        if (L.fin_live) {
+            L.pk_board = L.board;
+            L.pk_t = L.t;
+            L.pk_fours = L.fours;
+            L.pk_e = L.e;
+            L.pk_cut = L.fin_cut;
+            L.pk_seen15 = L.seen15;
+            L.pk_has = true;
+            L.fin_live = false;
+        }
+    }
+}
+
+// exact legal mask: "row can move left / right" for the 4 rows and the 4 columns
+__device__ __forceinline__ uint32_t play3_legal(const uint8_t* s_flags, u64 b, u64 bT) {
+    const uint32_t blo = (uint32_t)b, bhi = (uint32_t)(b >> 32);
+    const uint32_t tlo = (uint32_t)bT, thi = (uint32_t)(bT >> 32);
+    const uint32_t fb = s_flags[blo & 0xFFFFu] | s_flags[blo >> 16] | s_flags[bhi & 0xFFFFu] | s_flags[bhi >> 16];
+    const uint32_t ft = s_flags[tlo & 0xFFFFu] | s_flags[tlo >> 16] | s_flags[thi & 0xFFFFu] | s_flags[thi >> 16];
+    return fb | (ft << 1);  // rows give Left (bit 0) and Right (bit 2), columns the same bits one up: Up (1), Down (3)
+}
+
+// One loop iteration of a lane that holds an env: a game step, or one of the two init spawns.
+template <int MODE, int POLICY, bool REC>
+__device__ __forceinline__ void play3_step(Play3Lane& L, const Play3Ctx& c) {
+    // keys: identical to g2048_play.cu
+    const bool playing = L.phase == PHASE_PLAY;
+    const uint2 ss = __ldg(&c.subs[2 + 2 * (int64_t)L.t]);
+    int action;
+    Key kstep;
+    if (POLICY == G2048_POLICY_RANDOM) {
+        const uint2 sa = __ldg(&c.subs[1 + 2 * (int64_t)L.t]);
+        const Key head = playing ? Key{sa.x, sa.y} : Key{c.init_sub.x, c.init_sub.y};
+        const KeyBlocks<MODE> kb = key_blocks<MODE>(split_at<MODE>(head, c.batch_global, c.env_lo + L.e));
+        action = argmax_bits_legal(kb.bits, L.lm);
+        const Key kplay = split_at<MODE>(Key{ss.x, ss.y}, c.batch_global, c.env_lo + L.e);
+        const Key kinit = (L.phase == PHASE_INIT0) ? kb.child[0] : kb.child[1];
+        kstep = playing ? kplay : kinit;
+    } else {
+        action = act_drul(L.lm);
+        const Key head = playing ? Key{ss.x, ss.y} : Key{c.init_sub.x, c.init_sub.y};
+        kstep = split_at<MODE>(head, c.batch_global, c.env_lo + L.e);
+        if (!playing) {  // r_phase = split(init key)[phase]
+            Key c0, c1;
+            split2<MODE>(kstep, c0, c1);
+            kstep = (L.phase == PHASE_INIT0) ? c0 : c1;
+        }
+    }
+    Key k1, k2;
+    split2<MODE>(kstep, k1, k2);
+    const uint32_t bits_pos = bits_scalar<MODE>(k1);
+    const uint32_t bits_val = bits_scalar<MODE>(k2);
+
+    // ---- move: four table lookups on the board (Left/Right) or its transpose (Up/Down) -----------------
+    const u64 pre_board = L.board;   // REC: what the record of this step holds
+    const uint32_t pre_lm = L.lm;
+    const bool vertical = (action & 1) != 0, rev = action >= 2;
+    u64 src = vertical ? L.boardT : L.board;
+    if (rev) src = mirror_rows(src);
+    const uint32_t slo = (uint32_t)src, shi = (uint32_t)(src >> 32);
+    const uint32_t m0 = c.s_left[slo & 0xFFFFu], m1 = c.s_left[slo >> 16];
+    const uint32_t m2 = c.s_left[shi & 0xFFFFu], m3 = c.s_left[shi >> 16];
+    u64 moved = ((u64)(m2 | (m3 << 16)) << 32) | (u64)(m0 | (m1 << 16));
+    if (rev) moved = mirror_rows(moved);
+    const u64 movedT = transpose_board(moved);
+    u64 nb = vertical ? movedT : moved;   // row-major board after the move
+    u64 nbT = vertical ? moved : movedT;  // its transpose
+    if (!playing) {  // the two init iterations only spawn
+        nb = L.board;
+        nbT = L.boardT;
+    }
+    // ---- spawn into both orientations -------------------------------------------------------------------
+    int cell;
+    u64 val;
+    spawn_select(nb, bits_pos, bits_val, cell, val);
+    const int cellT = ((cell & 3) << 2) | (cell >> 2);
+    L.board = nb | (val << (4 * cell));      // the chosen cell is empty (or, on a full board, only reachable
+    L.boardT = nbT | (val << (4 * cellT));   //  through illegal actions which these policies never take)
+    L.fours += (val == 2ull) ? 1u : 0u;
+    L.lm = play3_legal(c.s_flags, L.board, L.boardT);
+
+    if (!playing) {
+        L.phase += 1;  // INIT0 -> INIT1 -> PLAY
+        return;
+    }
+    ++L.t;
+    const bool done = L.lm == 0u;
+    const bool cut = !done && L.t >= c.max_steps;
+    if ((L.t & 255u) == 0u) L.seen15 |= has_max_nibble(L.board);  // the final board is checked in the epilogue
+    if (REC) {  // the lane's own sequential stream: consecutive steps fill consecutive bytes of the same sectors
+        c.rec.boards[L.slot] = pre_board;
+        c.rec.meta[L.slot] = (uint8_t)((uint32_t)action | (pre_lm << 2) | (done ? 0x40u : 0u) | ((uint32_t)(val & 2ull) << 6));
+        ++L.slot;
+    }
+    if (done || cut) {  // the final state stays in board / t / fours / e / seen15 until it is parked at the loop top
+        L.fin_live = true;
+        L.fin_cut = cut;
+        L.phase = PHASE_NONE;
+        if (REC) {  // the episode's last board closes its slot range (the reward of the last step needs it)
+            c.rec.boards[L.slot] = L.board;
+            c.rec.env_slot[L.e] = L.slot - (unsigned long long)L.t;
+            ++L.slot;
+        }
+    }
+}
+
+// Tail of the launch.  Once the queue is empty no lane gets a new env and the warps thin out: a warp with one live lane
+// costs as many issue slots per step as a full one.  The CTA therefore plays the rest in rounds of PLAY3_TAIL_STEPS
+// steps with a CTA-wide compaction in between: the live envs move through shared memory into the lowest lanes of the
+// CTA, warps without envs only wait at the barrier, and the cost of a step follows the number of live envs.  The fixed
+// cost of a launch (what does not shrink with the batch) drops from 0.49 to 0.37 ms: 2^18 envs (C4) 1.54 -> 1.44 ms.
+// Kept out of line so that the main loop's code is exactly what it is without this phase: inlined, the same source cost
+// the main loop 2 % (2^24 envs: 69.8 -> 71.3 ms; A/B on one box, tools/ab_variants.py).
+template <int MODE, int POLICY, bool REC>
+__device__ __noinline__ void play3_tail(Play3Lane& lane_state, const Play3Ctx& c, unsigned* s_tail_cnt, TailEntry* s_pool) {
+    Play3Lane L = lane_state;  // work on a copy in registers: stores through the context's pointers cannot alias it
+    const unsigned lane = threadIdx.x & 31u;
+    unsigned round = 0;
+    while (true) {
+        play3_park(L, c);
+        // ---- compaction: live envs -> pool -> lanes 0 .. total-1 of the CTA ----------------------------------------
+        unsigned* cnt = &s_tail_cnt[round & 1u];
+        const unsigned livemask = __ballot_sync(0xFFFFFFFFu, L.phase != PHASE_NONE);
+        unsigned base = 0;
+        if (livemask) {
+            if (lane == 0) base = atomicAdd(cnt, (unsigned)__popc(livemask));
+            base = __shfl_sync(0xFFFFFFFFu, base, 0);
+        }
+        if (L.phase != PHASE_NONE) {
+            const unsigned at = base + (unsigned)__popc(livemask & ((1u << lane) - 1u));
+            s_pool[at] = TailEntry{L.board, L.slot, L.e, L.t, L.fours, L.phase | (L.seen15 ? 4u : 0u)};
+        }
+        __syncthreads();
+        const unsigned total = *(volatile unsigned*)cnt;
+        if (threadIdx.x == 0) s_tail_cnt[(round + 1u) & 1u] = 0u;  // next round's counter: untouched until after the barrier below
+        if (total == 0u) break;  // uniform over the CTA
+        if (threadIdx.x < total) {
+            const TailEntry en = s_pool[threadIdx.x];
+            L.board = en.board;
+            L.slot = en.slot;
+            L.e = en.e;
+            L.t = en.t;
+            L.fours = en.fours;
+            L.phase = en.flags & 3u;
+            L.seen15 = (en.flags & 4u) != 0u;
+            L.boardT = transpose_board(L.board);
+            L.lm = play3_legal(c.s_flags, L.board, L.boardT);
+        } else {
+            L.phase = PHASE_NONE;
+        }
+        __syncthreads();  // every entry has been read before the next round writes the pool
+        ++round;
+        for (int it = 0; it < PLAY3_TAIL_STEPS; ++it) {
+            if (__ballot_sync(0xFFFFFFFFu, L.phase != PHASE_NONE) == 0u) break;  // nothing left in this warp: wait at the barrier
+            if (L.phase != PHASE_NONE) play3_step<MODE, POLICY, REC>(L, c);
+            if (__ballot_sync(0xFFFFFFFFu, L.fin_live)) play3_park(L, c);
+        }
+    }
+    lane_state = L;
+}
+
 template <int MODE, int POLICY, bool REC>
 __global__ void __launch_bounds__(PLAY3_THREADS, 1)
 play3_kernel(const uint2* __restrict__ subs, int64_t n_subs, uint32_t batch_global, uint32_t env_lo, uint32_t n,
@@ -111,8 +333,6 @@ play3_kernel(const uint2* __restrict__ subs, int64_t n_subs, uint32_t batch_glob
              uint32_t* __restrict__ scores, unsigned long long* __restrict__ stats, uint4* __restrict__ results,
              const PlayRecordArena rec) {
     extern __shared__ __align__(16) uint8_t smem_raw[];
-    const uint16_t* s_left = reinterpret_cast<const uint16_t*>(smem_raw);
-    const uint8_t* s_flags = smem_raw + 65536 * 2;
     unsigned long long* s_stats = reinterpret_cast<unsigned long long*>(smem_raw + PLAY3_TABLE_BYTES);
     volatile unsigned* s_tail_flag = reinterpret_cast<volatile unsigned*>(smem_raw + PLAY3_TABLE_BYTES + PLAY3_STATS_BYTES);
     unsigned* s_tail_cnt = reinterpret_cast<unsigned*>(smem_raw + PLAY3_TABLE_BYTES + PLAY3_STATS_BYTES) + 1;  // [2]
@@ -130,270 +350,93 @@ play3_kernel(const uint2* __restrict__ subs, int64_t n_subs, uint32_t batch_glob
     __syncthreads();
 
     const unsigned lane = threadIdx.x & 31u;
-    const uint2 init_sub = subs[0];
-    const uint32_t max_steps = (uint32_t)((n_subs - 1) / 2);
+    Play3Ctx c;
+    c.subs = subs;
+    c.init_sub = subs[0];
+    c.max_steps = (uint32_t)((n_subs - 1) / 2);
+    c.batch_global = batch_global;
+    c.env_lo = env_lo;
+    c.s_left = reinterpret_cast<const uint16_t*>(smem_raw);
+    c.s_flags = smem_raw + 65536 * 2;
+    c.s_stats = s_stats;
+    c.final_boards = final_boards;
+    c.lengths = lengths;
+    c.scores = scores;
+    c.results = results;
+    c.rec = rec;
 
-    u64 board = 0ull, boardT = 0ull;  // the board and its transpose
-    uint32_t lm = 0, e = 0, t = 0, fours = 0, phase = PHASE_NONE;
-    bool seen15 = false;
-    bool exhausted = false;  // warp-uniform
-
-    uint32_t st_episodes = 0, st_cut = 0, st_ovf = 0, st_longest = 0;
-    unsigned long long st_steps = 0, st_score = 0, st_tile = 0, st_tile2 = 0;
-    // recording: next free slot of this lane's arena region and the end of the region
-    unsigned long long slot = 0, slot_end = 0;
+    Play3Lane L = {};
+    L.phase = PHASE_NONE;
     if (REC) {
-        slot = ((unsigned long long)blockIdx.x * PLAY3_THREADS + threadIdx.x) * rec.cap;
-        slot_end = slot + rec.cap;
+        L.slot = ((unsigned long long)blockIdx.x * PLAY3_THREADS + threadIdx.x) * rec.cap;
+        L.slot_end = L.slot + rec.cap;
     }
-
-    // Episode epilogue (score from the final board, result stores, statistics: ~150 instructions).  Lanes finish
-    // one at a time -- a warp meets a finished episode on roughly every fourth step -- so running the epilogue on the
-    // spot means running it with one active lane, ~4 % of the kernel's instructions.  A finished lane parks its final
-    // state in a second register set instead and takes the next env at once; the epilogue runs for all parked lanes
-    // together when PLAY3_EPILOGUE_BATCH of them have gathered (or a parked lane finishes again, or at the end).
-    // 2^21 envs, random policy: 25.76 G env-steps/s with the epilogue on the spot, 26.22 batched by 8, 26.32 by 16 or 32.
-    u64 pk_board = 0ull;
-    uint32_t pk_t = 0, pk_fours = 0, pk_e = 0;
-    bool pk_has = false, pk_cut = false, pk_seen15 = false;
-    bool fin_live = false, fin_cut = false;  // the live registers hold a finished episode that is not parked yet
-    auto epilogue = [&]() {
-        if (pk_has) {
-            const uint32_t score = board_potential(pk_board) - 4u * pk_fours;
-            if (final_boards) final_boards[pk_e] = pk_board;
-            if (lengths) lengths[pk_e] = pk_t;
-            if (scores) scores[pk_e] = score;
-            if (results) results[pk_e] = make_uint4((uint32_t)pk_board, (uint32_t)(pk_board >> 32), pk_t, score);  // G2048EpisodeResult
-            const uint32_t me = max_exponent(pk_board);
-            const unsigned long long tile = 1ull << me;
-            st_episodes += 1;
-            st_steps += pk_t;
-            st_score += score;
-            st_cut += pk_cut ? 1u : 0u;
-            st_ovf += (pk_seen15 || has_max_nibble(pk_board)) ? 1u : 0u;
-            st_longest = max(st_longest, pk_t);
-            st_tile += tile;
-            st_tile2 += tile * tile;
-            atomicAdd(&s_stats[16 + me], 1ull);
-            pk_has = false;
-        }
-    };
-
-    // park what the lanes that just finished still hold (call converged)
-    auto park_finished = [&]() {
-        const unsigned fresh = __ballot_sync(0xFFFFFFFFu, fin_live);
-        if (fresh) {
-            const unsigned parked = __ballot_sync(0xFFFFFFFFu, pk_has);
-            if ((fresh & parked) != 0u || __popc(fresh | parked) >= PLAY3_EPILOGUE_BATCH) epilogue();
-            if (fin_live) {
-                pk_board = board;
-                pk_t = t;
-                pk_fours = fours;
-                pk_e = e;
-                pk_cut = fin_cut;
-                pk_seen15 = seen15;
-                pk_has = true;
-                fin_live = false;
-            }
-        }
-    };
-    // exact legal mask: "row can move left / right" for the 4 rows and the 4 columns
-    auto legal_from_tables = [&](u64 b, u64 bT) -> uint32_t {
-        const uint32_t blo = (uint32_t)b, bhi = (uint32_t)(b >> 32);
-        const uint32_t tlo = (uint32_t)bT, thi = (uint32_t)(bT >> 32);
-        const uint32_t fb = s_flags[blo & 0xFFFFu] | s_flags[blo >> 16] | s_flags[bhi & 0xFFFFu] | s_flags[bhi >> 16];
-        const uint32_t ft = s_flags[tlo & 0xFFFFu] | s_flags[tlo >> 16] | s_flags[thi & 0xFFFFu] | s_flags[thi >> 16];
-        return fb | (ft << 1);  // rows give Left (bit 0) and Right (bit 2), columns the same bits one up: Up (1), Down (3)
-    };
-
-    // ---- one loop iteration of a lane that holds an env: a game step, or one of the two init spawns -------------------
-    auto step = [&]() {
-        // keys: identical to g2048_play.cu
-        const bool playing = phase == PHASE_PLAY;
-        const uint2 ss = __ldg(&subs[2 + 2 * (int64_t)t]);
-        int action;
-        Key kstep;
-        if (POLICY == G2048_POLICY_RANDOM) {
-            const uint2 sa = __ldg(&subs[1 + 2 * (int64_t)t]);
-            const Key head = playing ? Key{sa.x, sa.y} : Key{init_sub.x, init_sub.y};
-            const KeyBlocks<MODE> kb = key_blocks<MODE>(split_at<MODE>(head, batch_global, env_lo + e));
-            action = argmax_bits_legal(kb.bits, lm);
-            const Key kplay = split_at<MODE>(Key{ss.x, ss.y}, batch_global, env_lo + e);
-            const Key kinit = (phase == PHASE_INIT0) ? kb.child[0] : kb.child[1];
-            kstep = playing ? kplay : kinit;
-        } else {
-            action = act_drul(lm);
-            const Key head = playing ? Key{ss.x, ss.y} : Key{init_sub.x, init_sub.y};
-            kstep = split_at<MODE>(head, batch_global, env_lo + e);
-            if (!playing) {  // r_phase = split(init key)[phase]
-                Key c0, c1;
-                split2<MODE>(kstep, c0, c1);
-                kstep = (phase == PHASE_INIT0) ? c0 : c1;
-            }
-        }
-        Key k1, k2;
-        split2<MODE>(kstep, k1, k2);
-        const uint32_t bits_pos = bits_scalar<MODE>(k1);
-        const uint32_t bits_val = bits_scalar<MODE>(k2);
-
-        // ---- move: four table lookups on the board (Left/Right) or its transpose (Up/Down) -----------------
-        const u64 pre_board = board;   // REC: what the record of this step holds
-        const uint32_t pre_lm = lm;
-        const bool vertical = (action & 1) != 0, rev = action >= 2;
-        u64 src = vertical ? boardT : board;
-        if (rev) src = mirror_rows(src);
-        const uint32_t slo = (uint32_t)src, shi = (uint32_t)(src >> 32);
-        const uint32_t m0 = s_left[slo & 0xFFFFu], m1 = s_left[slo >> 16];
-        const uint32_t m2 = s_left[shi & 0xFFFFu], m3 = s_left[shi >> 16];
-        u64 moved = ((u64)(m2 | (m3 << 16)) << 32) | (u64)(m0 | (m1 << 16));
-        if (rev) moved = mirror_rows(moved);
-        const u64 movedT = transpose_board(moved);
-        u64 nb = vertical ? movedT : moved;   // row-major board after the move
-        u64 nbT = vertical ? moved : movedT;  // its transpose
-        if (!playing) {  // the two init iterations only spawn
-            nb = board;
-            nbT = boardT;
-        }
-        // ---- spawn into both orientations -------------------------------------------------------------------
-        int cell;
-        u64 val;
-        spawn_select(nb, bits_pos, bits_val, cell, val);
-        const int cellT = ((cell & 3) << 2) | (cell >> 2);
-        board = nb | (val << (4 * cell));      // the chosen cell is empty (or, on a full board, only reachable
-        boardT = nbT | (val << (4 * cellT));   //  through illegal actions which these policies never take)
-        fours += (val == 2ull) ? 1u : 0u;
-        lm = legal_from_tables(board, boardT);
-
-        if (!playing) {
-            phase += 1;  // INIT0 -> INIT1 -> PLAY
-            return;
-        }
-        ++t;
-        const bool done = lm == 0u;
-        const bool cut = !done && t >= max_steps;
-        if ((t & 255u) == 0u) seen15 |= has_max_nibble(board);  // the final board is checked in the epilogue
-        if (REC) {  // the lane's own sequential stream: consecutive steps fill consecutive bytes of the same sectors
-            rec.boards[slot] = pre_board;
-            rec.meta[slot] = (uint8_t)((uint32_t)action | (pre_lm << 2) | (done ? 0x40u : 0u) | ((uint32_t)(val & 2ull) << 6));
-            ++slot;
-        }
-        if (done || cut) {  // the final state stays in board / t / fours / e / seen15 until it is parked at the loop top
-            fin_live = true;
-            fin_cut = cut;
-            phase = PHASE_NONE;
-            if (REC) {  // the episode's last board closes its slot range (the reward of the last step needs it)
-                rec.boards[slot] = board;
-                rec.env_slot[e] = slot - (unsigned long long)t;
-                ++slot;
-            }
-        }
-    };
+    bool exhausted = false;  // warp-uniform
 
     // ---- main phase: every lane that finishes an episode takes the next env of the queue at once ---------------------
     bool tail_seen = false;  // warp-uniform
-    for (unsigned iter = 0;; ++iter) {
-        const unsigned idle = __ballot_sync(0xFFFFFFFFu, phase == PHASE_NONE);
+    while (true) {
+        const unsigned idle = __ballot_sync(0xFFFFFFFFu, L.phase == PHASE_NONE);
         // a recording lane takes a new env only while a whole episode still fits into its arena region
-        const bool can_take = !REC || slot + (unsigned long long)max_steps + 1ull <= slot_end;
-        const unsigned want = REC ? __ballot_sync(0xFFFFFFFFu, phase == PHASE_NONE && can_take) : idle;
+        const bool can_take = !REC || L.slot + (unsigned long long)c.max_steps + 1ull <= L.slot_end;
+        const unsigned want = REC ? __ballot_sync(0xFFFFFFFFu, L.phase == PHASE_NONE && can_take) : idle;
         if (idle) {
-            park_finished();
+            play3_park(L, c);
             if (!exhausted && want) {
                 const int cnt = __popc(want);
                 unsigned long long base = 0;
                 if (lane == 0) base = atomicAdd(work, (unsigned long long)cnt);
                 base = __shfl_sync(0xFFFFFFFFu, base, 0);
                 if (base + (unsigned long long)cnt >= (unsigned long long)n) exhausted = true;
-                if (phase == PHASE_NONE && (!REC || can_take)) {
+                if (L.phase == PHASE_NONE && (!REC || can_take)) {
                     const unsigned long long mine = base + (unsigned long long)__popc(want & ((1u << lane) - 1u));
                     if (mine < (unsigned long long)n) {
-                        e = (uint32_t)mine;
-                        board = 0ull;
-                        boardT = 0ull;
-                        lm = 0;
-                        t = 0;
-                        fours = 0;
-                        seen15 = false;
-                        phase = PHASE_INIT0;
+                        L.e = (uint32_t)mine;
+                        L.board = 0ull;
+                        L.boardT = 0ull;
+                        L.lm = 0;
+                        L.t = 0;
+                        L.fours = 0;
+                        L.seen15 = false;
+                        L.phase = PHASE_INIT0;
                     }
                 }
             }
-            // The queue is empty (or, recording, no idle lane of this warp can take an env any more): tell the CTA.
 #if G2048_PLAY3_TAIL
+            // The queue is empty (or, recording, no idle lane of this warp can take an env any more): tell the CTA.
             if (exhausted || (REC && want == 0u && idle == 0xFFFFFFFFu)) {
                 *s_tail_flag = 1;
                 tail_seen = true;
             }
 #else
-            if (__ballot_sync(0xFFFFFFFFu, phase != PHASE_NONE) == 0u && (exhausted || want == 0u)) {
-                tail_seen = true;  // nothing left for this warp
-                *s_tail_flag = 2;  // (value unused: keeps the variable referenced)
-            }
+            if (__ballot_sync(0xFFFFFFFFu, L.phase != PHASE_NONE) == 0u && (exhausted || want == 0u)) tail_seen = true;
 #endif
         }
-        // Tail of the launch.  From here on no lane gets a new env and the warps thin out: a warp with one live lane
-        // costs as many issue slots per step as a full one, and with ~3.5 episodes per lane (C4: 2^18 envs) almost half
-        // of all env-steps are played in this phase.  Once any warp of the CTA has seen the queue empty, all of them
-        // (each looks at the flag every eighth iteration) switch to rounds of PLAY3_TAIL_STEPS steps with a CTA-wide
-        // compaction in between: the live envs move through shared memory into the lowest lanes of the CTA, warps
-        // without envs only wait at the barrier, and the cost of a step follows the number of live envs.
 #if G2048_PLAY3_TAIL
-        if ((iter & G2048_PLAY3_TAIL_POLL) == 0u && *s_tail_flag) tail_seen = true;
+        // once any warp of the CTA has seen the queue empty, all of them (each looks at the flag once per iteration)
+        // leave for the tail phase together
+        if (*s_tail_flag) tail_seen = true;
 #endif
         if (tail_seen) break;
-        if (phase != PHASE_NONE) step();
+        if (L.phase != PHASE_NONE) play3_step<MODE, POLICY, REC>(L, c);
     }
-    unsigned round = 0;
-    while (G2048_PLAY3_TAIL) {
-        park_finished();
-        // ---- compaction: live envs -> pool -> lanes 0 .. total-1 of the CTA ----------------------------------------
-        unsigned* cnt = &s_tail_cnt[round & 1u];
-        const unsigned livemask = __ballot_sync(0xFFFFFFFFu, phase != PHASE_NONE);
-        unsigned base = 0;
-        if (livemask) {
-            if (lane == 0) base = atomicAdd(cnt, (unsigned)__popc(livemask));
-            base = __shfl_sync(0xFFFFFFFFu, base, 0);
-        }
-        if (phase != PHASE_NONE) {
-            const unsigned at = base + (unsigned)__popc(livemask & ((1u << lane) - 1u));
-            s_pool[at] = TailEntry{board, slot, e, t, fours, phase | (seen15 ? 4u : 0u)};
-        }
-        __syncthreads();
-        const unsigned total = *(volatile unsigned*)cnt;
-        if (threadIdx.x == 0) s_tail_cnt[(round + 1u) & 1u] = 0u;  // next round's counter: untouched until after the barrier below
-        if (total == 0u) break;  // uniform over the CTA
-        if (threadIdx.x < total) {
-            const TailEntry en = s_pool[threadIdx.x];
-            board = en.board;
-            slot = en.slot;
-            e = en.e;
-            t = en.t;
-            fours = en.fours;
-            phase = en.flags & 3u;
-            seen15 = (en.flags & 4u) != 0u;
-            boardT = transpose_board(board);
-            lm = legal_from_tables(board, boardT);
-        } else {
-            phase = PHASE_NONE;
-        }
-        __syncthreads();  // every entry has been read before the next round writes the pool
-        ++round;
-        for (int it = 0; it < PLAY3_TAIL_STEPS; ++it) {
-            if (__ballot_sync(0xFFFFFFFFu, phase != PHASE_NONE) == 0u) break;  // nothing left in this warp: wait at the barrier
-            if (phase != PHASE_NONE) step();
-            if (__ballot_sync(0xFFFFFFFFu, fin_live)) park_finished();
-        }
+#if G2048_PLAY3_TAIL
+    {
+        Play3Lane handed = L;  // only this copy has its address taken: the main loop's state stays in registers
+        play3_tail<MODE, POLICY, REC>(handed, c, s_tail_cnt, s_pool);
+        L = handed;
     }
-    epilogue();  // whatever is still parked (a finished lane always passes the loop top, and is parked, before the loop ends)
+#endif
+    play3_epilogue(L, c);  // whatever is still parked (a finished lane always passes a park, and is parked, before the loops end)
 
-    atomicAdd(&s_stats[0], (unsigned long long)st_episodes);
-    atomicAdd(&s_stats[1], st_steps);
-    atomicAdd(&s_stats[2], st_score);
-    atomicAdd(&s_stats[3], (unsigned long long)st_cut);
-    atomicAdd(&s_stats[4], (unsigned long long)st_ovf);
-    atomicMax(&s_stats[5], (unsigned long long)st_longest);
-    atomicAdd(&s_stats[6], st_tile);
-    atomicAdd(&s_stats[7], st_tile2);
+    atomicAdd(&s_stats[0], (unsigned long long)L.st_episodes);
+    atomicAdd(&s_stats[1], L.st_steps);
+    atomicAdd(&s_stats[2], L.st_score);
+    atomicAdd(&s_stats[3], (unsigned long long)L.st_cut);
+    atomicAdd(&s_stats[4], (unsigned long long)L.st_ovf);
+    atomicMax(&s_stats[5], (unsigned long long)L.st_longest);
+    atomicAdd(&s_stats[6], L.st_tile);
+    atomicAdd(&s_stats[7], L.st_tile2);
     __syncthreads();
     for (int i = threadIdx.x; i < G2048_PLAY_STATS_WORDS; i += blockDim.x) {
         const unsigned long long v = s_stats[i];

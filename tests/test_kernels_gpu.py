@@ -497,6 +497,54 @@ def test_policy_step_auto_reset_follows_pgx_wrapper(E):
     assert wd[sel].sum() > 10
 
 
+@pytest.mark.parametrize("mode", MODES)
+def test_auto_reset_undoes_a_finished_env_before_stepping_it(E, mode):
+    """pgx.experimental.auto_reset, the branch SURVEY A.6 lists first: a state that finished on the previous step was
+    replaced by a fresh one but still carries terminated=True; the wrapper clears the flag (and the rewards) and then
+    steps it like any other env.  Two consecutive steps: the envs that finish on the first are the ones entering the
+    second with the flag set -- their second step must be the oracle's plain env.step on the fresh board."""
+    n = 65536
+    rng = np.random.default_rng(41)
+    boards = rng.integers(1, 4, (n, 16))  # nearly dead boards: many terminate on the first step
+    masks, done, status = state_of(boards)
+    keep = ~done  # start from live envs only
+    boards, status = boards[keep], status[keep]
+    n = boards.shape[0]
+    b, s = dev(E.pack_boards(boards)), dev(status)
+    logits = dev(np.zeros((n, 4), np.float32))
+    rr = torch.empty(n, dtype=torch.float32, device="cuda")
+    rm = torch.empty(n, dtype=torch.uint8, device="cuda")
+    acts = torch.empty(n, dtype=torch.int32, device="cuda")
+    E.policy_step(b, s, logits, None, True, True, True, u32([10, 20]), u32([30, 40]), n, 0, mode, None, rm, rr, None, None, acts)
+    st1 = s.cpu().numpy()
+    finished = (st1 & 16) != 0
+    assert finished.sum() > 100
+    boards1 = E.boards_numpy(b)  # fresh boards (two tiles) where `finished`
+    assert ((boards1[finished] != 0).sum(axis=1) == 2).all()
+    np.testing.assert_array_equal(mask_bits(st1)[finished], O.exact_legal(boards1[finished]))  # the fresh state's own mask
+    pre2 = b.clone()
+    rb2 = torch.empty(n, dtype=torch.int64, device="cuda")
+    E.policy_step(b, s, logits, None, True, True, True, u32([11, 21]), u32([31, 41]), n, 0, mode, rb2, rm, rr, None, None, acts)
+    assert torch.equal(rb2, pre2)  # the record holds the fresh board, not the dead one
+    a2 = acts.cpu().numpy()
+    assert mask_bits(st1)[np.arange(n), a2].all()  # legal under the mask the env showed, finished or not
+    step_keys = CO.split([31, 41], n, mode)
+    k0, k1 = O.split((step_keys[:, 0], step_keys[:, 1]), 2, mode)
+    key1 = np.stack([k0[:, 0], k1[:, 0]], axis=1)
+    key2 = np.stack([k0[:, 1], k1[:, 1]], axis=1)
+    wb, wm, wd, wr = CO.env_step(boards1, mask_bits(st1), np.zeros(n, bool), a2, key1, mode)  # every env un-done first
+    ib, im = CO.env_init(key2, mode)
+    wb = np.where(wd[:, None].astype(bool), ib, wb)
+    wm = np.where(wd[:, None].astype(bool), im, wm)
+    st2 = s.cpu().numpy()
+    np.testing.assert_array_equal(E.boards_numpy(b), wb)
+    np.testing.assert_array_equal((st2 >> 4) & 1, wd)
+    np.testing.assert_array_equal(mask_bits(st2), wm.astype(bool))
+    np.testing.assert_array_equal(rr.cpu().numpy(), wr)
+    np.testing.assert_array_equal((rm.cpu().numpy() >> 6) & 1, wd)
+    assert (wr[finished] >= 0).all() and not wd[finished].any()  # a two-tile board never ends on its first step
+
+
 # ----------------------------------------------------------------------------------------- records
 @pytest.mark.parametrize("entry", ["g2048_expand_obs", "g2048_expand_obs_v1"])
 @pytest.mark.parametrize("dtype", [torch.float32, torch.bool, torch.bfloat16])

@@ -68,16 +68,22 @@ def test_runner_paths_agree_with_the_fused_step():
     import g2048
 
     class RowwiseAgent(torch.nn.Module):
-        """Every output row is computed from its input row with a fixed operation order (elementwise product and a row
-        sum over the LAST dimension, no GEMM), so a row's logits do not depend on which other rows are in the batch."""
+        """A row's outputs depend on that row only AND are computed with a fixed operation order whatever the batch
+        shape: per-cell table rows picked by the cell's exponent, added cell after cell with elementwise adds (a
+        reduction kernel or a GEMM may split its sums differently for different batch sizes)."""
 
         def __init__(self):
             super().__init__()
             g = torch.Generator().manual_seed(3)
-            self.w = torch.nn.Parameter(torch.randn(5, 496, generator=g) * 0.3)
+            self.w = torch.nn.Parameter(torch.randn(16, 31, 5, generator=g) * 0.5)
 
         def forward(self, obs, mask=None):
-            out = (obs.reshape(obs.shape[0], 1, 496) * self.w.unsqueeze(0)).sum(dim=2)
+            idx = obs.reshape(obs.shape[0], 16, 31).argmax(dim=-1)  # (B, 16) exponents
+            cells = torch.arange(16, device=obs.device)
+            vals = self.w[cells.unsqueeze(0), idx]  # (B, 16, 5)
+            out = vals[:, 0]
+            for c in range(1, 16):
+                out = out + vals[:, c]
             return out[:, :4], out[:, 4:5]
 
     def make(**kw):
