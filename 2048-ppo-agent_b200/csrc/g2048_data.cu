@@ -17,6 +17,7 @@ typedef unsigned long long u64;
 // (V <= 16 < 31) overlaps at most two cells, so it holds at most two ones.
 // Algorithmic bytes per board: 8 read + 496*sizeof(T) written (f32: 1992 B).
 // ------------------------------------------------------------------------------------------------
+#ifdef G2048_LEGACY_KERNELS  // first-generation observation kernel: built only into the tests' libg2048_legacy.so
 template <typename T> struct OneHotChunk;
 
 template <> struct OneHotChunk<float> {
@@ -88,6 +89,7 @@ expand_obs_kernel(const u64* __restrict__ boards, int64_t n, uint4* __restrict__
         __stcs(&out[g], OneHotChunk<T>::make(rel0, rel1));
     }
 }
+#endif  // G2048_LEGACY_KERNELS
 
 // ------------------------------------------------------------------------------------------------
 // (T,B) time-major records -> (B,T) env-major reference arrays, 32x32 tiles through shared memory
@@ -350,6 +352,7 @@ using namespace g2048;
 
 static inline bool aligned16(const void* p) { return ((uintptr_t)p & 15u) == 0; }
 
+#ifdef G2048_LEGACY_KERNELS
 extern "C" int g2048_expand_obs_v1(const uint64_t* d_boards, int64_t n, int dtype, void* d_out, int64_t rows,
                                 int64_t n_cols, void* stream) {
     G2048_REQUIRE(n >= 0 && rows >= 0 && (rows == 0 || (n_cols > 0 && rows * n_cols == n)), "expand_obs: shape");
@@ -379,6 +382,7 @@ extern "C" int g2048_expand_obs_v1(const uint64_t* d_boards, int64_t n, int dtyp
     G2048_CHECK_LAUNCH("expand_obs");
     return G2048_OK;
 }
+#endif  // G2048_LEGACY_KERNELS
 
 extern "C" int g2048_unpack_records(const uint8_t* d_rec_meta, const float* d_rec_rewards,
                                     const float* d_rec_log_probs, const float* d_rec_values, int64_t t_steps, int64_t n,

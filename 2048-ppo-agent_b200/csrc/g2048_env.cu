@@ -114,6 +114,7 @@ __global__ void act_kernel(const uint8_t* __restrict__ status, const uint32_t* _
     actions[i] = a;
 }
 
+#ifdef G2048_LEGACY_KERNELS  // first-generation play kernel: built only into the tests' libg2048_legacy.so
 // ------------------------------------------------------------------------------------------------
 // persistent play-to-termination kernel
 // ------------------------------------------------------------------------------------------------
@@ -221,6 +222,7 @@ play_kernel(const uint2* __restrict__ subs, int64_t n_subs, uint32_t batch_globa
         }
     }
 }
+#endif  // G2048_LEGACY_KERNELS
 
 // ------------------------------------------------------------------------------------------------
 // lock-step recorded rollout (trajectory mode)
@@ -447,6 +449,7 @@ extern "C" int g2048_act(int policy, const uint8_t* d_status, const uint32_t* d_
     return G2048_OK;
 }
 
+#ifdef G2048_LEGACY_KERNELS
 template <int MODE, int POLICY>
 static int launch_play(const uint32_t* d_subs, int64_t n_subs, int64_t batch_global, int64_t env_lo, int64_t n,
                        uint64_t* d_work, uint64_t* d_final_boards, uint32_t* d_lengths, uint32_t* d_scores,
@@ -485,6 +488,7 @@ extern "C" int g2048_play_v1(int policy, const uint32_t* d_subs, int64_t n_subs,
     return launch_play<G2048_RNG_ORIGINAL, G2048_POLICY_DRUL>(ARGS);
 #undef ARGS
 }
+#endif  // G2048_LEGACY_KERNELS
 
 // device-side address of a host pointer in pinned, mapped memory; nullptr for pageable memory
 static void* mapped_device_pointer(const void* host) {

@@ -17,8 +17,10 @@ namespace g2048 {
 #endif
 
 constexpr int GAE_TILE = 1024;
+#ifdef G2048_LEGACY_KERNELS
 constexpr int GAE_THREADS = 128;
 constexpr int GAE_ITEMS = GAE_TILE / GAE_THREADS;  // 8 consecutive steps per thread for segment discovery
+#endif
 
 struct GaeScratch {
     unsigned int ticket;
@@ -43,6 +45,7 @@ __device__ __forceinline__ void block_sum4(double v[4], double* s_red /* [4][4] 
     }
 }
 
+#ifdef G2048_LEGACY_KERNELS  // first-generation GAE kernel: built only into the tests' libg2048_legacy.so
 // One CTA per tile of 1024 consecutive steps, tiles taken from the END of the buffer by ticket.
 //   1. coalesced loads of r, V, done into shared memory (+ V of the step after the tile);
 //   2. warp-shuffle prefix sum of per-thread done counts -> ordered list of episode ends;
@@ -200,6 +203,7 @@ gae_flat_kernel(const float* __restrict__ rewards, const float* __restrict__ val
         if (threadIdx.x == 0) atomicAdd(&moments[0], (double)len);
     }
 }
+#endif  // G2048_LEGACY_KERNELS
 
 // Time-major (T,B) records: one lane per env, loads batched 16 steps ahead so that enough bytes
 // are in flight even at B = 64 K (one lane per env is all the parallelism there is); coalesced along B.
@@ -347,6 +351,7 @@ extern "C" int64_t g2048_gae_flat_scratch_bytes(int64_t n) {
     return (int64_t)sizeof(GaeScratch) + n_tiles * 8;
 }
 
+#ifdef G2048_LEGACY_KERNELS
 extern "C" int g2048_gae_flat_v1(const float* d_rewards, const float* d_values, const uint8_t* d_dones, int64_t n,
                               double gamma, double lambda_gae, float* d_adv, float* d_ret, void* d_scan_state,
                               double* d_moments, void* stream) {
@@ -367,6 +372,7 @@ extern "C" int g2048_gae_flat_v1(const float* d_rewards, const float* d_values, 
     G2048_CHECK_LAUNCH("gae_flat");
     return G2048_OK;
 }
+#endif  // G2048_LEGACY_KERNELS
 
 extern "C" int g2048_gae_time_major(const float* d_rewards, const float* d_values, const uint8_t* d_rec_meta,
                                     int64_t t_steps, int64_t n, const float* d_bootstrap, double gamma,

@@ -33,10 +33,13 @@ constexpr int PLAY3_TABLE_BYTES = 65536 * 2 + 65536;
 #define G2048_PLAY3_TAIL_STEPS 8
 #endif
 #ifndef G2048_PLAY3_TAIL
-#define G2048_PLAY3_TAIL 1  // 0: no tail compaction (a warp leaves when its lanes are done), for A/B timing
+// 1: tail compaction (play3_tail below).  Off in the shipped build: it shortens the fixed cost of a launch (2^18 envs:
+// 1.53 -> 1.47 ms) but its presence costs the main loop 0.9 % at 2^24 envs (69.84 -> 70.44 ms) and the recording form
+// more (DRUL, 2^18 envs: 1.91 -> 2.07 ms); the headline workload is the large batch.  A/B: tools/ab_variants.py.
+#define G2048_PLAY3_TAIL 0
 #endif
 
-constexpr int PLAY3_TAIL_STEPS = G2048_PLAY3_TAIL_STEPS;  // steps between two compactions of the CTA's live envs in the tail
+[[maybe_unused]] constexpr int PLAY3_TAIL_STEPS = G2048_PLAY3_TAIL_STEPS;  // steps between two compactions of the CTA's live envs in the tail
 // what moves with an env when the tail compaction hands it to another lane (32 bytes)
 struct TailEntry {
     unsigned long long board;
@@ -275,9 +278,9 @@ __device__ __forceinline__ void play3_step(Play3Lane& L, const Play3Ctx& c) {
 // costs as many issue slots per step as a full one.  The CTA therefore plays the rest in rounds of PLAY3_TAIL_STEPS
 // steps with a CTA-wide compaction in between: the live envs move through shared memory into the lowest lanes of the
 // CTA, warps without envs only wait at the barrier, and the cost of a step follows the number of live envs.  The fixed
-// cost of a launch (what does not shrink with the batch) drops from 0.49 to 0.37 ms: 2^18 envs (C4) 1.54 -> 1.44 ms.
-// Kept out of line so that the main loop's code is exactly what it is without this phase: inlined, the same source cost
-// the main loop 2 % (2^24 envs: 69.8 -> 71.3 ms; A/B on one box, tools/ab_variants.py).
+// cost of a launch (what does not shrink with the batch) drops from 0.49 to 0.37 ms: 2^18 envs (C4) 1.54 -> 1.44 ms
+// inlined, 1.47 ms out of line.  Out of line because inlined the same source cost the main loop 2 % (2^24 envs:
+// 69.8 -> 71.3 ms; A/B on one box, tools/ab_variants.py); see G2048_PLAY3_TAIL above for why it is still off.
 template <int MODE, int POLICY, bool REC>
 __device__ __noinline__ void play3_tail(Play3Lane& lane_state, const Play3Ctx& c, unsigned* s_tail_cnt, TailEntry* s_pool) {
     Play3Lane L = lane_state;  // work on a copy in registers: stores through the context's pointers cannot alias it
@@ -334,9 +337,11 @@ play3_kernel(const uint2* __restrict__ subs, int64_t n_subs, uint32_t batch_glob
              const PlayRecordArena rec) {
     extern __shared__ __align__(16) uint8_t smem_raw[];
     unsigned long long* s_stats = reinterpret_cast<unsigned long long*>(smem_raw + PLAY3_TABLE_BYTES);
+#if G2048_PLAY3_TAIL
     volatile unsigned* s_tail_flag = reinterpret_cast<volatile unsigned*>(smem_raw + PLAY3_TABLE_BYTES + PLAY3_STATS_BYTES);
     unsigned* s_tail_cnt = reinterpret_cast<unsigned*>(smem_raw + PLAY3_TABLE_BYTES + PLAY3_STATS_BYTES) + 1;  // [2]
     TailEntry* s_pool = reinterpret_cast<TailEntry*>(smem_raw + PLAY3_TABLE_BYTES + PLAY3_STATS_BYTES + PLAY3_CTL_BYTES);
+#endif
 
     {  // tables: global (L2) -> shared, 12 x 16 bytes per thread
         const uint4* src_left = reinterpret_cast<const uint4*>(g_row_left);

@@ -115,30 +115,52 @@ expand_obs_tma_kernel(const u64* __restrict__ boards, int64_t n, T* __restrict__
         if (indices) src = __ldg(&indices[src]);  // gather: out[i] = onehot(boards[indices[i]])
         return __ldg(&boards[src * board_stride]);  // stride 4: the board of a 32-byte sample record
     };
-    // boards of one round of OBS_NBUF images (image j of the round starting at `base` is base + j * warps_total)
-    auto load_round = [&](int64_t base, u64 (&dst)[OBS_NBUF][PER_LANE]) {
+    // Source positions and boards of one round of OBS_NBUF images (image j of the round starting at `base` is
+    // base + j * warps_total).  With a gather a board is TWO dependent memory round trips (index, then board): the
+    // positions are fetched two rounds ahead and the boards one round ahead, so that neither load is waited for while
+    // it is in flight -- a warp used to spend ~1.5 us per round at the top of its loop (37 rounds per warp at 2^19
+    // samples: a quarter of the kernel; ncu long_scoreboard 19 per issue).
+    auto load_positions = [&](int64_t base, int64_t (&dst)[OBS_NBUF][PER_LANE]) {
 #pragma unroll
         for (int j = 0; j < OBS_NBUF; ++j) {
             const int64_t first = (base + (int64_t)j * warps_total) * G;
 #pragma unroll
             for (int p = 0; p < PER_LANE; ++p) {
                 const int c = lane + 32 * p;
-                const int64_t src = first + (c >> 4);
-                dst[j][p] = (c < CELLS && src < n) ? board_of(src) : 0ull;
+                int64_t src = first + (c >> 4);
+                const bool in = c < CELLS && src < n;
+                if (in && rows > 0) {  // out is env-major (col, row); boards are time-major (row, col)
+                    const int64_t col = src / rows;
+                    src = (src - col * rows) * n_cols + col;
+                }
+                if (in && indices) src = __ldg(&indices[src]);  // gather: out[i] = onehot(boards[indices[i]])
+                dst[j][p] = in ? src : -1;
             }
         }
     };
+    auto load_boards = [&](const int64_t (&pos)[OBS_NBUF][PER_LANE], u64 (&dst)[OBS_NBUF][PER_LANE]) {
+#pragma unroll
+        for (int j = 0; j < OBS_NBUF; ++j)
+#pragma unroll
+            for (int p = 0; p < PER_LANE; ++p)
+                dst[j][p] = pos[j][p] >= 0 ? __ldg(&boards[pos[j][p] * board_stride]) : 0ull;  // stride 4: sample records
+    };
     int64_t img = (int64_t)blockIdx.x * OBS_WARPS + warp;
-    // AHEAD: the boards of the NEXT round are fetched while the current round's images are written -- with a gather every
-    // board is two dependent memory round trips (index, board), ~1.5 us that a warp used to spend waiting at the top of
-    // every round (37 rounds per warp at 2^19 samples: a quarter of the kernel).
-    u64 cur_boards[OBS_NBUF][PER_LANE];  // dead code without AHEAD
-    if (AHEAD && img < n_images) load_round(img, cur_boards);
+    const int64_t round_stride = (int64_t)OBS_NBUF * warps_total;
+    u64 cur_boards[OBS_NBUF][PER_LANE];     // dead code without AHEAD
+    int64_t next_pos[OBS_NBUF][PER_LANE];   // positions of the round after the current one
+    if (AHEAD) {
+        if (img < n_images) {
+            load_positions(img, next_pos);
+            load_boards(next_pos, cur_boards);
+        }
+        if (img + round_stride < n_images) load_positions(img + round_stride, next_pos);
+    }
     while (img < n_images) {
         u64 next_boards[OBS_NBUF][PER_LANE];
         if (AHEAD) {
-            const int64_t next = img + (int64_t)OBS_NBUF * warps_total;
-            if (next < n_images) load_round(next, next_boards);
+            if (img + round_stride < n_images) load_boards(next_pos, next_boards);            // round r + 1: positions are here
+            if (img + 2 * round_stride < n_images) load_positions(img + 2 * round_stride, next_pos);  // round r + 2
         }
 #pragma unroll
         for (int j = 0; j < OBS_NBUF; ++j) {

@@ -67,7 +67,6 @@ _SIGNATURES = {
     "g2048_play_tables": (_INT, [_INT, _P, _I64, _I64, _I64, _I64, _INT, _P, _P, _P, _P, _P, _P]),
     "g2048_play_swar": (_INT, [_INT, _P, _I64, _I64, _I64, _I64, _INT, _P, _P, _P, _P, _P, _P]),
     "g2048_row_table_lookup": (_INT, [_P, _I64, _P, _P, _P]),
-    "g2048_play_v1": (_INT, [_INT, _P, _I64, _I64, _I64, _I64, _INT, _P, _P, _P, _P, _P, _P]),
     "g2048_play_host": (_INT, [_INT, _U64, _P, _I64, _I64, _I64, _INT, _P, _P, _P, _P]),
     "g2048_play_host_packed": (_INT, [_INT, _U64, _P, _I64, _I64, _I64, _INT, _P, _P]),
     "g2048_play_packed": (_INT, [_INT, _P, _I64, _I64, _I64, _I64, _INT, _P, _P, _P, _P]),
@@ -81,7 +80,6 @@ _SIGNATURES = {
     "g2048_sample_logits": (_INT, [_P, _P, _INT, _INT, _P, _I64, _I64, _I64, _INT, _P, _P, _P, _P]),
     "g2048_evaluate_logits": (_INT, [_P, _P, _INT, _P, _I64, _P, _P, _P]),
     "g2048_expand_obs": (_INT, [_P, _I64, _INT, _P, _I64, _I64, _P]),
-    "g2048_expand_obs_v1": (_INT, [_P, _I64, _INT, _P, _I64, _I64, _P]),
     "g2048_pack_obs": (_INT, [_P, _INT, _I64, _P, _P]),
     "g2048_unpack_status": (_INT, [_P, _I64, _P, _P, _P]),
     "g2048_unpack_records": (_INT, [_P, _P, _P, _P, _I64, _I64, _P, _P, _P, _P, _P, _P, _P]),
@@ -100,7 +98,6 @@ _SIGNATURES = {
     "g2048_embed_boards_grad": (_INT, [_P, _I64, _P, _P, _INT, _INT, _P, _P, _P]),
     "g2048_gae_flat_scratch_bytes": (_I64, [_I64]),
     "g2048_gae_flat": (_INT, [_P, _P, _P, _I64, _DBL, _DBL, _P, _P, _P, _P, _P]),
-    "g2048_gae_flat_v1": (_INT, [_P, _P, _P, _I64, _DBL, _DBL, _P, _P, _P, _P, _P]),
     "g2048_gae_flat_pipelined": (_INT, [_P, _P, _P, _I64, _DBL, _DBL, _P, _P, _P, _P, _P]),
     "g2048_gae_flat_tiled": (_INT, [_P, _P, _P, _I64, _DBL, _DBL, _P, _P, _P, _P, _P]),
     "g2048_gae_scan_scratch_bytes": (_I64, [_I64]),
@@ -116,6 +113,28 @@ for _name, (_res, _args) in _SIGNATURES.items():
     _fn = getattr(lib, _name)  # AttributeError here = the .so is stale / incomplete
     _fn.restype = _res
     _fn.argtypes = _args
+
+
+_extra_entry_points = {}  # name -> ctypes function of another library (tests register their legacy build here)
+
+
+def register_entry_points(path, signatures: dict) -> None:
+    """Make `call(name, ...)` reach entry points of ANOTHER shared library with this one's conventions -- test
+    infrastructure: tests/legacy/libg2048_legacy.so carries the first-generation kernels the product library no longer
+    exports."""
+    other = C.CDLL(str(path))
+    for name, (res, args) in signatures.items():
+        fn = getattr(other, name)
+        fn.restype = res
+        fn.argtypes = args
+        _extra_entry_points[name] = fn
+
+
+LEGACY_SIGNATURES = {  # tests/legacy/g2048_legacy.h
+    "g2048_play_v1": (_INT, [_INT, _P, _I64, _I64, _I64, _I64, _INT, _P, _P, _P, _P, _P, _P]),
+    "g2048_expand_obs_v1": (_INT, [_P, _I64, _INT, _P, _I64, _I64, _P]),
+    "g2048_gae_flat_v1": (_INT, [_P, _P, _P, _I64, _DBL, _DBL, _P, _P, _P, _P, _P]),
+}
 
 
 def declared_symbols() -> list[str]:
@@ -172,7 +191,7 @@ def stream_ptr() -> int:
 def call(name: str, *args) -> None:
     dev = getattr(_call_ctx, "device", None)
     _call_ctx.device = None
-    fn = getattr(lib, name)
+    fn = _extra_entry_points.get(name) or getattr(lib, name)
     if dev is not None and dev != torch.cuda.current_device():
         with torch.cuda.device(dev):
             rc = fn(*args)

@@ -40,17 +40,18 @@ def allreduce_sum_(t: torch.Tensor, group=None) -> torch.Tensor:
 
 
 def allreduce_play_stats(stats: torch.Tensor, group=None) -> torch.Tensor:
-    """Sum the play statistics block over ranks; slot 5 (longest episode) is a max."""
+    """Sum the play statistics block over ranks; slot 5 (longest episode) is a max.  ONE collective: the 256-byte blocks
+    are all-gathered and reduced locally (a SUM and a MAX all-reduce cost two NCCL launches, ~0.05 ms each, per batch)."""
     if not is_dist():
         return stats
     dev = _comm_device(stats)
-    buf = stats.to(dev).clone()
-    longest = buf[5:6].clone()
-    buf[5] = 0
-    dist.all_reduce(buf, op=dist.ReduceOp.SUM, group=group)
-    dist.all_reduce(longest, op=dist.ReduceOp.MAX, group=group)
-    buf[5] = longest[0]
-    return buf.to(stats.device)
+    mine = stats.to(dev).contiguous()
+    world = dist.get_world_size(group)
+    gathered = torch.empty((world, mine.shape[0]), dtype=mine.dtype, device=dev)
+    dist.all_gather_into_tensor(gathered, mine, group=group)
+    out = gathered.sum(dim=0)
+    out[5] = gathered[:, 5].max()
+    return out.to(stats.device)
 
 
 def allreduce_max_int(value: int, device, group=None) -> int:

@@ -168,7 +168,8 @@ STAT_NAMES = ("episodes", "env_steps", "score_sum", "cut_short", "overflowed", "
 def play(policy: int, subs: torch.Tensor, batch_global: int, env_lo: int, n: int, rng_mode: int,
          per_env: bool = True, stats: torch.Tensor | None = None, entry: str = "g2048_play"):
     """Persistent play-to-termination kernel.  Returns dict(final_boards, lengths, scores, stats).
-    entry="g2048_play_v1" runs the first-generation kernel (A/B timing only)."""
+    entry: another entry point with g2048_play's signature (g2048_play_tables, g2048_play_swar; tests also pass the
+    first-generation g2048_play_v1 of their own legacy build, see _native.register_entry_points)."""
     dev = subs.device
     work = torch.zeros(2, dtype=torch.int64, device=dev)
     if stats is None:
@@ -415,7 +416,7 @@ _OBS_DTYPES = {torch.bool: N.OBS_BOOL, torch.uint8: N.OBS_BOOL, torch.float32: N
 def expand_obs(boards: torch.Tensor, dtype=torch.float32, rows: int = 0, n_cols: int = 0, out=None,
                entry: str = "g2048_expand_obs") -> torch.Tensor:
     """One-hot (n,16,31).  rows/n_cols > 0: boards are (rows, n_cols) time-major, output is env-major.
-    entry="g2048_expand_obs_v1" runs the first-generation kernel (A/B timing and tests)."""
+    entry: another entry point with the same signature (the tests' legacy build has g2048_expand_obs_v1)."""
     n = boards.numel()
     if out is None:
         out = torch.empty((n, 16, 31), dtype=dtype, device=boards.device)
@@ -637,7 +638,7 @@ def embed_boards_grad(boards: torch.Tensor, grad_out: torch.Tensor, indices: tor
 def gae_flat(rewards, values, dones, gamma: float, lambda_gae: float, want_moments: bool = True,
              entry: str = "g2048_gae_flat"):
     """-> adv, ret (n,) float32, moments (6,) float64 or None.  dones: uint8/bool (n,).
-    entry="g2048_gae_flat_v1" runs the first-generation kernel; entry="g2048_gae_flat_scan" the re-associated reverse
+    entry: g2048_gae_flat_tiled / _pipelined pin a kernel; entry="g2048_gae_flat_scan" is the re-associated reverse
     scan (a pure stream; within 1e-5 relative of the reference loop instead of bit-identical)."""
     n = rewards.shape[0]
     dev = rewards.device

@@ -177,12 +177,6 @@ int g2048_play_record_compact(int policy, const uint64_t* d_arena_boards, const 
  * column 0) the row slid/merged toward column 0 and the flags (bit 0: moves left, bit 2: moves right). */
 int g2048_row_table_lookup(const uint16_t* d_rows, int64_t n, uint16_t* d_left, uint8_t* d_flags, void* stream);
 
-/* First-generation play kernel (lanes park until six are free, per-step reward loop): identical
- * arguments and results; kept so that the current kernel can be A/B-timed against it. */
-int g2048_play_v1(int policy, const uint32_t* d_subs, int64_t n_subs, int64_t batch_global, int64_t env_lo, int64_t n,
-                  int rng_mode, uint64_t* d_work, uint64_t* d_final_boards, uint32_t* d_lengths, uint32_t* d_scores,
-                  uint64_t* d_stats, void* stream);
-
 /* Host-buffer form of the same call (the reference-facing entry: run_actions_max_tile's inner
  * run).  seed -> jax.random.key(seed); h_key_io (2 words, may be NULL) overrides the seed with an
  * explicit chain key and receives the key the reference's runner would hold afterwards.
@@ -302,9 +296,6 @@ int g2048_evaluate_logits(const float* d_logits, const uint8_t* d_mask_bits, int
 int g2048_expand_obs(const uint64_t* d_boards, int64_t n, int dtype, void* d_out, int64_t rows, int64_t n_cols,
                      void* stream);
 
-/* First-generation kernel (one 16-byte chunk per thread, plain stores); same arguments. */
-int g2048_expand_obs_v1(const uint64_t* d_boards, int64_t n, int dtype, void* d_out, int64_t rows, int64_t n_cols,
-                        void* stream);
 /* d_out[i] = one-hot observation of d_boards[d_indices[i]], i < m (int64 indices) */
 int g2048_expand_obs_gather(const uint64_t* d_boards, const int64_t* d_indices, int64_t m, int dtype, void* d_out,
                             void* stream);
@@ -432,22 +423,17 @@ int64_t g2048_gae_flat_scratch_bytes(int64_t n);
 int g2048_gae_flat(const float* d_rewards, const float* d_values, const uint8_t* d_dones, int64_t n, double gamma,
                    double lambda_gae, float* d_adv, float* d_ret, void* d_scan_state, double* d_moments, void* stream);
 
-/* First-generation kernel (1 024-step tiles, every array staged in shared memory); same arguments.
- * Kept so that the current kernel can be A/B-timed against it. */
 /* The two current kernels behind g2048_gae_flat (same arguments, same scratch, bit-identical outputs):
  *   _tiled      one 6 144-step tile per CTA, phases one after the other; used below 2^23 steps
  *   _pipelined  persistent CTAs holding two 8 192-step tiles: walker warps on tile i while streamer warps store tile
  *               i-1 and load tile i+1; used from 2^23 steps on
- * and the first-generation kernel (_v1), kept for A/B measurements. */
+ * (the first-generation kernel lives in the tests' own build of the library, tests/legacy/g2048_legacy.h). */
 int g2048_gae_flat_tiled(const float* d_rewards, const float* d_values, const uint8_t* d_dones, int64_t n, double gamma,
                          double lambda_gae, float* d_adv, float* d_ret, void* d_scan_state, double* d_moments,
                          void* stream);
 int g2048_gae_flat_pipelined(const float* d_rewards, const float* d_values, const uint8_t* d_dones, int64_t n,
                              double gamma, double lambda_gae, float* d_adv, float* d_ret, void* d_scan_state,
                              double* d_moments, void* stream);
-int g2048_gae_flat_v1(const float* d_rewards, const float* d_values, const uint8_t* d_dones, int64_t n, double gamma,
-                      double lambda_gae, float* d_adv, float* d_ret, void* d_scan_state, double* d_moments,
-                      void* stream);
 
 /* g2048_gae_flat as a segmented affine REVERSE SCAN (north_star's "warp shuffles handle the reverse-scan GAE"): same
  * arguments and moments, its own scratch (g2048_gae_scan_scratch_bytes(n) bytes, 16-byte aligned, zeroed by the caller).

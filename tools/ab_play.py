@@ -4,7 +4,11 @@ from pathlib import Path
 ROOT = Path(__file__).resolve().parent.parent
 sys.path[:0] = [str(ROOT), str(ROOT / "2048-ppo-agent_b200")]
 import numpy as np, torch
+from g2048 import _native as N
 from g2048 import engine as E
+
+# the first-generation kernels live in the tests' build of the library (make -C 2048-ppo-agent_b200/csrc legacy)
+N.register_entry_points(ROOT / "tests" / "legacy" / "libg2048_legacy.so", N.LEGACY_SIGNATURES)
 
 def timed(fn, reps=3):
     fn(); torch.cuda.synchronize()
