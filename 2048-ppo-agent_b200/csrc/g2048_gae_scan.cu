@@ -11,10 +11,17 @@
 // ((a1,b1) o (a2,b2) = (a1 a2, a1 b2 + b1)), so the suffix compositions F_t = f_t o f_{t+1} o ... are a scan:
 //   * a thread composes its 8 consecutive steps serially (registers, 128-bit loads),
 //   * a warp scans the 32 thread aggregates with shuffles (5 steps), the 8 warp aggregates go through shared memory,
-//   * tiles (2 048 steps, taken from the END of the buffer by ticket by persistent CTAs) are chained by decoupled look-back:
-//     a tile publishes its aggregate (A, B) and, once it knows the gae entering it, the gae of its first step.  A tile
-//     that contains a `done` has A == 0 exactly, so its first-step gae is B and is published at once -- with episodes of
-//     a few hundred steps the chain is never longer than one tile and no CTA waits for another's look-back.
+//   * a persistent CTA owns a contiguous RANGE of 2 048-step tiles and walks it from its end to its start, so the gae
+//     entering a tile is the CTA's own carry -- no CTA ever waits for another one.  (Two earlier forms chained the
+//     tiles by decoupled look-back, one tile per CTA or by ticket: every tile's last warps then wait for the
+//     neighbour's publication and the rest of the CTA for them -- `barrier` 14.7 stalls per issue, 0.32-0.46 of HBM,
+//     profiles/r02_new_kernels.csv.)
+//   * what the steps at the END of a range see of the next range is not known while the kernel runs: the carry is kept
+//     as an affine map of that unknown x (coefficient 1 at the range's end, exactly 0 after the first `done` or after
+//     ~1 700 steps of gamma*lambda = 0.94 underflowing), results are written for x = 0, and a second, tiny kernel --
+//     one warp per range -- chains the range aggregates, adds coefficient * x to the few hundred steps whose
+//     coefficient is not zero and adds their share of the moments.  No spin-waits anywhere, hence no co-residency
+//     requirement.
 // 9 B read + 8 B written per step; fp64 moment sums for the normalisation in the same pass.
 #include "g2048_common.cuh"
 
@@ -24,18 +31,15 @@ constexpr int SCAN_THREADS = 256;
 constexpr int SCAN_ITEMS = 8;
 constexpr int SCAN_TILE = SCAN_THREADS * SCAN_ITEMS;  // 2 048 steps
 constexpr int SCAN_WARPS = SCAN_THREADS / 32;
+constexpr int SCAN_MAX_RANGES = 4096;
 
-struct ScanHeader {
-    unsigned int ticket;
-    unsigned int pad[3];
+// per range (persistent CTA): the gae of the range's first step as a map of x = the gae of the next range's first step,
+// and how many steps at the range's end have a non-zero coefficient of x (written for x = 0, left out of the moments)
+struct ScanRange {
+    float a, b;
+    unsigned int pending;
+    unsigned int pad;
 };
-// per tile: word = flag << 32 | float bits (flag 1: B of the tile aggregate, A in `a`; flag 2: gae of the tile's first step)
-struct ScanTile {
-    unsigned long long word;
-    float a;
-    float pad;
-};
-constexpr unsigned SCAN_AGG = 1u, SCAN_INCL = 2u;
 
 struct Affine {
     float a, b;
@@ -48,29 +52,22 @@ __device__ __forceinline__ Affine compose(Affine outer, Affine inner) {
 template <bool ALIGNED>
 __global__ void __launch_bounds__(SCAN_THREADS, 4)
 gae_scan_kernel(const float* __restrict__ rewards, const float* __restrict__ values, const uint8_t* __restrict__ dones,
-                int64_t n, int64_t n_tiles, float gamma, float gamma_lambda, float* __restrict__ adv,
-                float* __restrict__ ret, ScanHeader* header, double* __restrict__ moments) {
+                int64_t n, int64_t n_tiles, int64_t tiles_per_range, float gamma, float gamma_lambda, float* __restrict__ adv,
+                float* __restrict__ ret, ScanRange* __restrict__ ranges, double* __restrict__ moments) {
     __shared__ Affine s_warp[2][SCAN_WARPS];  // double-buffered by tile parity: one barrier per tile
-    __shared__ unsigned int s_ticket[2];
     __shared__ double s_red[4 * SCAN_WARPS];
+    __shared__ unsigned int s_pending;
 
-    ScanTile* tiles = reinterpret_cast<ScanTile*>(header + 1);
     const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
-    // Persistent CTAs: tiles are taken by ticket from the END of the buffer (a tile only ever waits for tiles with
-    // earlier tickets); the ticket of the NEXT tile is drawn while the current one is being processed, so nobody waits
-    // for that atomic (one CTA per tile did: `barrier` was the top stall, 14.7 per issue, 0.41 of HBM), and the moment
-    // sums stay in registers until the CTA is done (5 atomics per CTA instead of per tile).
-    if (threadIdx.x == 0) s_ticket[0] = atomicAdd(&header->ticket, 1u);
-    __syncthreads();
+    if (threadIdx.x == 0) s_pending = 0u;
+    const int64_t tile_lo = (int64_t)blockIdx.x * tiles_per_range;
+    const int64_t tile_hi = min(n_tiles, tile_lo + tiles_per_range);
+    Affine carry{1.0f, 0.0f};  // gae entering the current tile = carry.a * x + carry.b, x = gae of the next range's first step
     double acc4[4] = {0.0, 0.0, 0.0, 0.0};
-    for (unsigned it = 0;; ++it) {
-        const unsigned ticket = s_ticket[it & 1u];
-        if ((int64_t)ticket >= n_tiles) break;  // uniform
-        unsigned next_ticket = 0u;
-        if (threadIdx.x == 0) next_ticket = atomicAdd(&header->ticket, 1u);  // in flight while this tile is loaded
-        const int64_t tile = n_tiles - 1 - (int64_t)ticket;  // memory-order index: later tiles start first
-        const int64_t lo = tile * SCAN_TILE;
-        const int64_t first = lo + (int64_t)threadIdx.x * SCAN_ITEMS;  // this thread's first step
+    unsigned my_pending = 0;
+    unsigned it = 0;
+    for (int64_t tile = tile_hi - 1; tile >= tile_lo; --tile, ++it) {
+        const int64_t first = tile * SCAN_TILE + (int64_t)threadIdx.x * SCAN_ITEMS;  // this thread's first step
 
         // ---- loads: 8 consecutive steps per thread ---------------------------------------------------------------
         float r[SCAN_ITEMS], v[SCAN_ITEMS + 1];
@@ -118,68 +115,42 @@ gae_scan_kernel(const float* __restrict__ rewards, const float* __restrict__ val
             if (lane + off < 32) incl = compose(incl, other);
         }
         if (lane == 0) s_warp[it & 1u][warp] = incl;
-        if (threadIdx.x == 0) s_ticket[(it + 1u) & 1u] = next_ticket;
         // what follows my steps inside the warp: the inclusive value of the next lane
         Affine after;
         after.a = __shfl_down_sync(0xFFFFFFFFu, incl.a, 1);
         after.b = __shfl_down_sync(0xFFFFFFFFu, incl.b, 1);
         if (lane == 31) after = Affine{1.0f, 0.0f};
-        __syncthreads();  // the one barrier of a tile: warp aggregates and the next ticket are visible after it
-        // ... and the warps after mine
-        Affine later{1.0f, 0.0f};
-        for (int w = SCAN_WARPS - 1; w > warp; --w) later = compose(s_warp[it & 1u][w], later);
-        after = compose(after, later);  // everything between my last step and the end of the tile
-
-        // ---- chain the tiles: publish, look back -------------------------------------------------------------------
-        // gae of the first step of the next tile (0 past the end of the buffer): the first-step gae of the first following
-        // tile that knows it, pushed through the aggregates of the tiles in between.  Any thread may ask; tiles with a
-        // later index hold earlier tickets, so they have been started and the wait is short.
-        auto look_back = [&]() -> float {
-            Affine acc{1.0f, 0.0f};
-            for (int64_t j = tile + 1;; ++j) {
-                if (j == n_tiles) return acc.b;  // ran off the end of the buffer: the gae entering it is 0
-                volatile unsigned long long* w = &tiles[j].word;
-                unsigned long long word;
-                do {
-                    word = *w;
-                } while ((unsigned)(word >> 32) == 0u);
-                const float val = __uint_as_float((unsigned)word);
-                if ((unsigned)(word >> 32) == SCAN_INCL) return acc.a * val + acc.b;
-                __threadfence();
-                acc = compose(acc, Affine{*(volatile float*)&tiles[j].a, val});
-            }
-        };
-        if (threadIdx.x == 0) {
-            const Affine whole = compose(incl, later);  // thread 0: lanes 0..31 of warp 0, then the later warps
-            volatile unsigned long long* my_word = &tiles[tile].word;
-            if (whole.a == 0.0f || tile == n_tiles - 1) {
-                // nothing of what follows reaches my first step (or nothing follows): its gae is known now
-                *my_word = ((unsigned long long)SCAN_INCL << 32) | (unsigned long long)__float_as_uint(whole.b);
-            } else {
-                tiles[tile].a = whole.a;
-                __threadfence();
-                *my_word = ((unsigned long long)SCAN_AGG << 32) | (unsigned long long)__float_as_uint(whole.b);
-                const float x0 = look_back();
-                *my_word = ((unsigned long long)SCAN_INCL << 32) | (unsigned long long)__float_as_uint(whole.a * x0 + whole.b);
-            }
+        __syncthreads();  // the one barrier of a tile
+        // ... the warps after mine, and the whole tile (every thread composes the 8 warp aggregates itself: no second barrier)
+        Affine later{1.0f, 0.0f}, whole{1.0f, 0.0f};
+#pragma unroll
+        for (int w = SCAN_WARPS - 1; w >= 0; --w) {
+            const Affine m = s_warp[it & 1u][w];
+            whole = compose(m, whole);
+            if (w > warp) later = compose(m, later);
         }
-        // Only the steps after the tile's last `done` see the next tile at all (after.a != 0): with episodes of a few
-        // hundred steps that is the last warp or two of the CTA; every other thread goes straight on to its stores.
-        const float x = (after.a != 0.0f) ? look_back() : 0.0f;
+        // everything between my last step and the end of the RANGE, as a map of x
+        const Affine entering = compose(compose(after, later), carry);
+        carry = compose(whole, carry);  // ... and what enters the next (earlier) tile
 
-        // ---- apply: the gae entering my steps, then the reference's own recurrence over them ------------------------
-        float g = after.a * x + after.b;
+        // ---- apply: the gae entering my steps for x = 0, then the reference's own recurrence over them -------------------
+        float g = entering.b, coef = entering.a;
         float o_adv[SCAN_ITEMS], o_ret[SCAN_ITEMS];
 #pragma unroll
         for (int k = SCAN_ITEMS - 1; k >= 0; --k) {
             g = b[k] + a[k] * g;
+            coef = a[k] * coef;  // coefficient of x in this step's gae: non-zero only at the end of the range
             o_adv[k] = g;
             o_ret[k] = g + v[k];
             if (first + k < n) {
-                acc4[0] += (double)g;
-                acc4[1] += (double)g * (double)g;
-                acc4[2] += (double)o_ret[k];
-                acc4[3] += (double)o_ret[k] * (double)o_ret[k];
+                if (coef != 0.0f) {
+                    my_pending += 1u;  // finished by gae_scan_fix_kernel, which also adds it to the moments
+                } else {
+                    acc4[0] += (double)g;
+                    acc4[1] += (double)g * (double)g;
+                    acc4[2] += (double)o_ret[k];
+                    acc4[3] += (double)o_ret[k] * (double)o_ret[k];
+                }
             }
         }
         if (ALIGNED && full) {
@@ -197,6 +168,7 @@ gae_scan_kernel(const float* __restrict__ rewards, const float* __restrict__ val
             }
         }
     }
+    if (my_pending) atomicAdd(&s_pending, my_pending);
     if (moments) {
 #pragma unroll
         for (int k = 0; k < 4; ++k) {
@@ -204,13 +176,52 @@ gae_scan_kernel(const float* __restrict__ rewards, const float* __restrict__ val
             for (int off = 16; off > 0; off >>= 1) sum += __shfl_down_sync(0xFFFFFFFFu, sum, off);
             if (lane == 0) s_red[k * SCAN_WARPS + warp] = sum;
         }
-        __syncthreads();
-        if (threadIdx.x < 4) {
-            double sum = 0.0;
-            for (int w = 0; w < SCAN_WARPS; ++w) sum += s_red[threadIdx.x * SCAN_WARPS + w];
-            atomicAdd(&moments[1 + threadIdx.x], sum);
+    }
+    __syncthreads();
+    if (moments && threadIdx.x < 4) {
+        double sum = 0.0;
+        for (int w = 0; w < SCAN_WARPS; ++w) sum += s_red[threadIdx.x * SCAN_WARPS + w];
+        atomicAdd(&moments[1 + threadIdx.x], sum);
+    }
+    if (threadIdx.x == 0) ranges[blockIdx.x] = ScanRange{carry.a, carry.b, s_pending, 0u};
+}
+
+// One warp per range: x = the gae of the next range's first step (chained through the range aggregates until one does
+// not depend on its own successor), then gae += coefficient * x for the `pending` steps at the range's end -- their
+// coefficient is (gamma*lambda)^(distance to the range's end + 1): a step with a non-zero coefficient has no `done`
+// between itself and the end -- and their share of the moment sums.
+__global__ void __launch_bounds__(32)
+gae_scan_fix_kernel(const ScanRange* __restrict__ ranges, int n_ranges, int64_t n, int64_t tiles_per_range, float gamma_lambda,
+                    float* __restrict__ adv, float* __restrict__ ret, double* __restrict__ moments) {
+    const int c = blockIdx.x, lane = threadIdx.x;
+    const unsigned pending = ranges[c].pending;
+    if (lane == 0 && c == 0 && moments) atomicAdd(&moments[0], (double)n);
+    if (pending == 0u) return;
+    Affine acc{1.0f, 0.0f};
+    for (int j = c + 1; j < n_ranges && acc.a != 0.0f; ++j) acc = compose(acc, Affine{ranges[j].a, ranges[j].b});
+    const float x = acc.b;  // past the last range the gae is 0
+    const int64_t end = min(n, (int64_t)(c + 1) * tiles_per_range * SCAN_TILE);  // one past the range's last step
+    double acc4[4] = {0.0, 0.0, 0.0, 0.0};
+    for (unsigned i = (unsigned)lane; i < pending; i += 32u) {
+        const int64_t t = end - 1 - (int64_t)i;
+        const float coef = powf(gamma_lambda, (float)(i + 1u));
+        const float g = adv[t] + coef * x, q = ret[t] + coef * x;
+        if (x != 0.0f) {
+            adv[t] = g;
+            ret[t] = q;
         }
-        if (threadIdx.x == 4 && blockIdx.x == 0) atomicAdd(&moments[0], (double)n);
+        acc4[0] += (double)g;
+        acc4[1] += (double)g * (double)g;
+        acc4[2] += (double)q;
+        acc4[3] += (double)q * (double)q;
+    }
+    if (moments) {
+#pragma unroll
+        for (int k = 0; k < 4; ++k) {
+            double sum = acc4[k];
+            for (int off = 16; off > 0; off >>= 1) sum += __shfl_down_sync(0xFFFFFFFFu, sum, off);
+            if (lane == 0) atomicAdd(&moments[1 + k], sum);
+        }
     }
 }
 
@@ -219,8 +230,8 @@ gae_scan_kernel(const float* __restrict__ rewards, const float* __restrict__ val
 using namespace g2048;
 
 extern "C" int64_t g2048_gae_scan_scratch_bytes(int64_t n) {
-    const int64_t n_tiles = (n + SCAN_TILE - 1) / SCAN_TILE;
-    return (int64_t)sizeof(ScanHeader) + n_tiles * (int64_t)sizeof(ScanTile);
+    (void)n;
+    return (int64_t)SCAN_MAX_RANGES * (int64_t)sizeof(ScanRange);  // one entry per persistent CTA; need not be zeroed
 }
 
 extern "C" int g2048_gae_flat_scan(const float* d_rewards, const float* d_values, const uint8_t* d_dones, int64_t n, double gamma,
@@ -236,16 +247,20 @@ extern "C" int g2048_gae_flat_scan(const float* d_rewards, const float* d_values
     cudaStream_t st = (cudaStream_t)stream;
     const int sms = sm_count();
     if (sms <= 0) return fail_arg("gae_flat_scan: no device");
-    const int64_t resident = (int64_t)sms * 4;  // persistent: four 256-thread CTAs per SM
-    const unsigned grid = (unsigned)(n_tiles < resident ? n_tiles : resident);
+    int64_t want = (int64_t)sms * 4;  // four 256-thread CTAs per SM, each walking its own range of tiles
+    if (want > SCAN_MAX_RANGES) want = SCAN_MAX_RANGES;
+    const int64_t tiles_per_range = (n_tiles + want - 1) / want;
+    const int n_ranges = (int)((n_tiles + tiles_per_range - 1) / tiles_per_range);
+    const float g = (float)gamma, gl = (float)(gamma * lambda_gae);
     if (aligned)
-        gae_scan_kernel<true><<<grid, SCAN_THREADS, 0, st>>>(d_rewards, d_values, d_dones, n, n_tiles, (float)gamma,
-                                                                          (float)(gamma * lambda_gae), d_adv, d_ret,
-                                                                          (ScanHeader*)d_scan_state, d_moments);
+        gae_scan_kernel<true><<<n_ranges, SCAN_THREADS, 0, st>>>(d_rewards, d_values, d_dones, n, n_tiles, tiles_per_range, g, gl,
+                                                                 d_adv, d_ret, (ScanRange*)d_scan_state, d_moments);
     else
-        gae_scan_kernel<false><<<grid, SCAN_THREADS, 0, st>>>(d_rewards, d_values, d_dones, n, n_tiles, (float)gamma,
-                                                                           (float)(gamma * lambda_gae), d_adv, d_ret,
-                                                                           (ScanHeader*)d_scan_state, d_moments);
+        gae_scan_kernel<false><<<n_ranges, SCAN_THREADS, 0, st>>>(d_rewards, d_values, d_dones, n, n_tiles, tiles_per_range, g, gl,
+                                                                  d_adv, d_ret, (ScanRange*)d_scan_state, d_moments);
     G2048_CHECK_LAUNCH("gae_flat_scan");
+    gae_scan_fix_kernel<<<n_ranges, 32, 0, st>>>((const ScanRange*)d_scan_state, n_ranges, n, tiles_per_range, gl, d_adv, d_ret,
+                                                 d_moments);
+    G2048_CHECK_LAUNCH("gae_flat_scan: fix-up");
     return G2048_OK;
 }

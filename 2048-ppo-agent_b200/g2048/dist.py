@@ -47,8 +47,9 @@ def allreduce_play_stats(stats: torch.Tensor, group=None) -> torch.Tensor:
     dev = _comm_device(stats)
     mine = stats.to(dev).contiguous()
     world = dist.get_world_size(group)
-    gathered = torch.empty((world, mine.shape[0]), dtype=mine.dtype, device=dev)
-    dist.all_gather_into_tensor(gathered, mine, group=group)
+    flat = torch.empty(world * mine.shape[0], dtype=mine.dtype, device=dev)  # 1-D: gloo wants the concatenated form
+    dist.all_gather_into_tensor(flat, mine, group=group)
+    gathered = flat.view(world, mine.shape[0])
     out = gathered.sum(dim=0)
     out[5] = gathered[:, 5].max()
     return out.to(stats.device)

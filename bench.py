@@ -271,8 +271,9 @@ def main():
         """ONE collective per step: all-gather the 256-byte statistics blocks, reduce locally (sum; slot 5 is a max)."""
         if world == 1:
             return stats
-        gathered = torch.empty((world, N.PLAY_STATS_WORDS), dtype=torch.int64, device=dev)
-        dist.all_gather_into_tensor(gathered, stats)
+        flat = torch.empty(world * N.PLAY_STATS_WORDS, dtype=torch.int64, device=dev)
+        dist.all_gather_into_tensor(flat, stats)
+        gathered = flat.view(world, N.PLAY_STATS_WORDS)
         out = gathered.sum(dim=0)
         out[5] = gathered[:, 5].max()
         return out
