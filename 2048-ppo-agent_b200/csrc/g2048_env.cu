@@ -500,6 +500,35 @@ static void* mapped_device_pointer(const void* host) {
     return attr.type == cudaMemoryTypeHost ? attr.devicePointer : nullptr;
 }
 
+// Workspace of the calling thread for the *_host play entry points.
+struct PlayHostWorkspace {
+    int device = -1;
+    cudaStream_t stream = nullptr;
+    uint8_t* buf = nullptr;
+    size_t bytes = 0;
+    StagedCopier copier;  // result arrays in pageable memory (numpy) go through pinned staging buffers
+    // everything goes back when the thread moves to another device or calls g2048_release_host_workspace()
+    void release() {
+        if (device < 0) return;
+        int cur = -1;
+        const bool switched = cudaGetDevice(&cur) == cudaSuccess && cur != device && cudaSetDevice(device) == cudaSuccess;
+        if (buf) cudaFree(buf);
+        if (stream) cudaStreamDestroy(stream);
+        copier.release();
+        if (switched) cudaSetDevice(cur);
+        cudaGetLastError();
+        buf = nullptr;
+        stream = nullptr;
+        bytes = 0;
+        device = -1;
+    }
+};
+static thread_local PlayHostWorkspace t_play_host_ws;
+
+namespace g2048 {
+void release_play_host_workspace() { t_play_host_ws.release(); }
+}
+
 static int play_host_impl(int policy, uint64_t seed, uint32_t* h_key_io, int64_t batch_global, int64_t env_lo,
                           int64_t n, int rng_mode, uint64_t* h_final_boards, uint32_t* h_lengths,
                           uint32_t* h_scores, G2048EpisodeResult* h_results, uint64_t* h_stats) {
@@ -510,14 +539,7 @@ static int play_host_impl(int policy, uint64_t seed, uint32_t* h_key_io, int64_t
 
     // Workspace of the calling thread on the current device: one stream and one grow-only device
     // buffer, kept across calls so that a call costs copies and kernels, not cudaMalloc/cudaFree.
-    struct Workspace {
-        int device = -1;
-        cudaStream_t stream = nullptr;
-        uint8_t* buf = nullptr;
-        size_t bytes = 0;
-        StagedCopier copier;  // result arrays in pageable memory (numpy) go through pinned staging buffers
-    };
-    static thread_local Workspace ws;
+    PlayHostWorkspace& ws = t_play_host_ws;
     static const bool zero_copy = [] { const char* e = getenv("G2048_PLAY_HOST_ZEROCOPY"); return !(e && e[0] == '0'); }();
     int rc = G2048_OK;
     int dev = 0;
@@ -535,7 +557,7 @@ static int play_host_impl(int policy, uint64_t seed, uint32_t* h_key_io, int64_t
 #define TRY(expr, where) do { rc = check_cuda((expr), where); if (rc) return rc; } while (0)
     TRY(cudaGetDevice(&dev), "play_host: device");
     if (ws.device != dev) {  // first call on this thread, or the thread switched device
-        ws = Workspace();
+        ws.release();
         TRY(cudaStreamCreateWithFlags(&ws.stream, cudaStreamNonBlocking), "play_host: stream");
         if ((rc = ws.copier.init())) return rc;
         ws.device = dev;

@@ -416,21 +416,50 @@ struct GaeHostWorkspace {
     uint8_t* dev = nullptr;
     size_t dev_bytes = 0;
     StagedCopier copier;
+    // everything goes back when the thread moves to another device or calls g2048_release_host_workspace()
+    void release() {
+        if (device < 0) return;
+        int cur = -1;
+        const bool switched = cudaGetDevice(&cur) == cudaSuccess && cur != device && cudaSetDevice(device) == cudaSuccess;
+        if (dev) cudaFree(dev);
+        if (stream) cudaStreamDestroy(stream);
+        copier.release();
+        if (switched) cudaSetDevice(cur);
+        cudaGetLastError();
+        dev = nullptr;
+        stream = nullptr;
+        dev_bytes = 0;
+        device = -1;
+    }
 };
 
+static thread_local GaeHostWorkspace t_gae_host_ws;
+
 }  // namespace
+
+namespace g2048 {
+void release_play_host_workspace();  // g2048_env.cu
+}
+
+// Frees what the calling thread's *_host entry points keep between calls (a stream, a grow-only device buffer and
+// 2 x 16 MiB of pinned staging memory each).  A thread that used them should call this before it ends.
+extern "C" int g2048_release_host_workspace(void) {
+    t_gae_host_ws.release();
+    g2048::release_play_host_workspace();
+    return G2048_OK;
+}
 
 extern "C" int g2048_gae_host(const float* h_rewards, const float* h_values, const uint8_t* h_dones, int64_t n,
                               double gamma, double lambda_gae, int normalize, float* h_adv, float* h_ret) {
     G2048_REQUIRE(n >= 0, "gae_host: n");
     if (n == 0) return G2048_OK;
     G2048_REQUIRE(h_rewards && h_values && h_dones && h_adv && h_ret, "gae_host: pointers");
-    static thread_local GaeHostWorkspace ws;
+    GaeHostWorkspace& ws = t_gae_host_ws;
     int rc = G2048_OK, dev = 0;
 #define TRY(expr, where) do { rc = check_cuda((expr), where); if (rc) return rc; } while (0)
     TRY(cudaGetDevice(&dev), "gae_host: device");
     if (ws.device != dev) {  // first call on this thread, or the thread switched device
-        ws = GaeHostWorkspace();
+        ws.release();
         TRY(cudaStreamCreateWithFlags(&ws.stream, cudaStreamNonBlocking), "gae_host: stream");
         if ((rc = ws.copier.init())) return rc;
         ws.device = dev;

@@ -50,7 +50,7 @@ __device__ __forceinline__ Affine compose(Affine outer, Affine inner) {
 }
 
 template <bool ALIGNED>
-__global__ void __launch_bounds__(SCAN_THREADS, 4)
+__global__ void __launch_bounds__(SCAN_THREADS, 3)
 gae_scan_kernel(const float* __restrict__ rewards, const float* __restrict__ values, const uint8_t* __restrict__ dones,
                 int64_t n, int64_t n_tiles, int64_t tiles_per_range, float gamma, float gamma_lambda, float* __restrict__ adv,
                 float* __restrict__ ret, ScanRange* __restrict__ ranges, double* __restrict__ moments) {
@@ -66,34 +66,58 @@ gae_scan_kernel(const float* __restrict__ rewards, const float* __restrict__ val
     double acc4[4] = {0.0, 0.0, 0.0, 0.0};
     unsigned my_pending = 0;
     unsigned it = 0;
-    for (int64_t tile = tile_hi - 1; tile >= tile_lo; --tile, ++it) {
-        const int64_t first = tile * SCAN_TILE + (int64_t)threadIdx.x * SCAN_ITEMS;  // this thread's first step
 
-        // ---- loads: 8 consecutive steps per thread ---------------------------------------------------------------
+    // 8 consecutive steps of one tile per thread, as loaded: the NEXT tile's are requested before the current one is
+    // processed, so a CTA always has a tile in flight (without this a tile's loads, its scan and its stores run one after
+    // the other: 0.69 of HBM)
+    struct Raw {
         float r[SCAN_ITEMS], v[SCAN_ITEMS + 1];
-        bool d[SCAN_ITEMS];
-        const bool full = first + SCAN_ITEMS <= n;
-        if (ALIGNED && full) {
+        unsigned dmask;
+    };
+    auto load_tile = [&](int64_t tile, Raw& o) {
+        const int64_t first = tile * SCAN_TILE + (int64_t)threadIdx.x * SCAN_ITEMS;
+        if (ALIGNED && first + SCAN_ITEMS <= n) {
             const float4 r0 = *reinterpret_cast<const float4*>(rewards + first), r1 = *reinterpret_cast<const float4*>(rewards + first + 4);
             const float4 v0 = *reinterpret_cast<const float4*>(values + first), v1 = *reinterpret_cast<const float4*>(values + first + 4);
             const uint2 dd = *reinterpret_cast<const uint2*>(dones + first);
-            r[0] = r0.x; r[1] = r0.y; r[2] = r0.z; r[3] = r0.w; r[4] = r1.x; r[5] = r1.y; r[6] = r1.z; r[7] = r1.w;
-            v[0] = v0.x; v[1] = v0.y; v[2] = v0.z; v[3] = v0.w; v[4] = v1.x; v[5] = v1.y; v[6] = v1.z; v[7] = v1.w;
+            o.r[0] = r0.x; o.r[1] = r0.y; o.r[2] = r0.z; o.r[3] = r0.w; o.r[4] = r1.x; o.r[5] = r1.y; o.r[6] = r1.z; o.r[7] = r1.w;
+            o.v[0] = v0.x; o.v[1] = v0.y; o.v[2] = v0.z; o.v[3] = v0.w; o.v[4] = v1.x; o.v[5] = v1.y; o.v[6] = v1.z; o.v[7] = v1.w;
+            unsigned m = 0;
 #pragma unroll
             for (int k = 0; k < 4; ++k) {
-                d[k] = ((dd.x >> (8 * k)) & 0xFFu) != 0u;
-                d[4 + k] = ((dd.y >> (8 * k)) & 0xFFu) != 0u;
+                m |= (((dd.x >> (8 * k)) & 0xFFu) != 0u ? 1u : 0u) << k;
+                m |= (((dd.y >> (8 * k)) & 0xFFu) != 0u ? 1u : 0u) << (4 + k);
             }
+            o.dmask = m;
         } else {
+            unsigned m = 0;
 #pragma unroll
             for (int k = 0; k < SCAN_ITEMS; ++k) {
                 const bool in = first + k < n;
-                r[k] = in ? rewards[first + k] : 0.0f;
-                v[k] = in ? values[first + k] : 0.0f;
-                d[k] = in ? dones[first + k] != 0 : true;  // past the end: a = 0, delta = 0 -- contributes nothing
+                o.r[k] = in ? rewards[first + k] : 0.0f;
+                o.v[k] = in ? values[first + k] : 0.0f;
+                m |= ((in ? dones[first + k] != 0 : true) ? 1u : 0u) << k;  // past the end: a = 0, delta = 0 -- contributes nothing
             }
+            o.dmask = m;
         }
-        v[SCAN_ITEMS] = (first + SCAN_ITEMS < n) ? values[first + SCAN_ITEMS] : 0.0f;  // V of the step after mine (0 past the end)
+        o.v[SCAN_ITEMS] = (first + SCAN_ITEMS < n) ? values[first + SCAN_ITEMS] : 0.0f;  // V of the step after mine (0 past the end)
+    };
+    Raw cur;
+    load_tile(tile_hi - 1, cur);
+    for (int64_t tile = tile_hi - 1; tile >= tile_lo; --tile, ++it) {
+        const int64_t first = tile * SCAN_TILE + (int64_t)threadIdx.x * SCAN_ITEMS;  // this thread's first step
+        const bool full = first + SCAN_ITEMS <= n;
+        Raw nxt;
+        if (tile > tile_lo) load_tile(tile - 1, nxt);
+        float r[SCAN_ITEMS], v[SCAN_ITEMS + 1];
+        bool d[SCAN_ITEMS];
+#pragma unroll
+        for (int k = 0; k < SCAN_ITEMS; ++k) {
+            r[k] = cur.r[k];
+            v[k] = cur.v[k];
+            d[k] = ((cur.dmask >> k) & 1u) != 0u;
+        }
+        v[SCAN_ITEMS] = cur.v[SCAN_ITEMS];
 
         // ---- per-step maps and the thread's aggregate (composition of its 8 steps, first step outermost) ---------------
         float a[SCAN_ITEMS], b[SCAN_ITEMS];
@@ -136,6 +160,7 @@ gae_scan_kernel(const float* __restrict__ rewards, const float* __restrict__ val
         // ---- apply: the gae entering my steps for x = 0, then the reference's own recurrence over them -------------------
         float g = entering.b, coef = entering.a;
         float o_adv[SCAN_ITEMS], o_ret[SCAN_ITEMS];
+        float part[4] = {0.0f, 0.0f, 0.0f, 0.0f};  // the thread's 8 steps are summed in fp32, tiles and threads in fp64
 #pragma unroll
         for (int k = SCAN_ITEMS - 1; k >= 0; --k) {
             g = b[k] + a[k] * g;
@@ -146,13 +171,15 @@ gae_scan_kernel(const float* __restrict__ rewards, const float* __restrict__ val
                 if (coef != 0.0f) {
                     my_pending += 1u;  // finished by gae_scan_fix_kernel, which also adds it to the moments
                 } else {
-                    acc4[0] += (double)g;
-                    acc4[1] += (double)g * (double)g;
-                    acc4[2] += (double)o_ret[k];
-                    acc4[3] += (double)o_ret[k] * (double)o_ret[k];
+                    part[0] += g;
+                    part[1] += g * g;
+                    part[2] += o_ret[k];
+                    part[3] += o_ret[k] * o_ret[k];
                 }
             }
         }
+#pragma unroll
+        for (int k = 0; k < 4; ++k) acc4[k] += (double)part[k];
         if (ALIGNED && full) {
             *reinterpret_cast<float4*>(adv + first) = make_float4(o_adv[0], o_adv[1], o_adv[2], o_adv[3]);
             *reinterpret_cast<float4*>(adv + first + 4) = make_float4(o_adv[4], o_adv[5], o_adv[6], o_adv[7]);
@@ -167,6 +194,7 @@ gae_scan_kernel(const float* __restrict__ rewards, const float* __restrict__ val
                 }
             }
         }
+        cur = nxt;
     }
     if (my_pending) atomicAdd(&s_pending, my_pending);
     if (moments) {
@@ -247,7 +275,7 @@ extern "C" int g2048_gae_flat_scan(const float* d_rewards, const float* d_values
     cudaStream_t st = (cudaStream_t)stream;
     const int sms = sm_count();
     if (sms <= 0) return fail_arg("gae_flat_scan: no device");
-    int64_t want = (int64_t)sms * 4;  // four 256-thread CTAs per SM, each walking its own range of tiles
+    int64_t want = (int64_t)sms * 3;  // three 256-thread CTAs per SM (two tiles each in flight), each walking its own range of tiles
     if (want > SCAN_MAX_RANGES) want = SCAN_MAX_RANGES;
     const int64_t tiles_per_range = (n_tiles + want - 1) / want;
     const int n_ranges = (int)((n_tiles + tiles_per_range - 1) / tiles_per_range);

@@ -25,6 +25,17 @@ struct StagedCopier {
         return G2048_OK;
     }
 
+    // give the staging buffers and events back (errors ignored: at thread or process exit the context may be gone)
+    void release() {
+        for (int k = 0; k < 2; ++k) {
+            if (pin[k]) cudaFreeHost(pin[k]);
+            if (ev[k]) cudaEventDestroy(ev[k]);
+            pin[k] = nullptr;
+            ev[k] = nullptr;
+        }
+        cudaGetLastError();
+    }
+
     static bool is_pinned(const void* p) {
         cudaPointerAttributes attr;
         if (cudaPointerGetAttributes(&attr, p) != cudaSuccess) {

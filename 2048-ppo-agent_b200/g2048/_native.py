@@ -105,6 +105,7 @@ _SIGNATURES = {
     "g2048_gae_time_major": (_INT, [_P, _P, _P, _I64, _I64, _P, _DBL, _DBL, _P, _P, _P, _P]),
     "g2048_normalize": (_INT, [_P, _I64, _P, _INT, _P]),
     "g2048_gae_host": (_INT, [_P, _P, _P, _I64, _DBL, _DBL, _INT, _P, _P]),
+    "g2048_release_host_workspace": (_INT, []),
     "g2048_row_moments": (_INT, [_P, _I64, _I64, _P, _P]),
     "g2048_int_peak_probe": (_INT, [_INT, _INT, _INT, _P, _P]),
 }

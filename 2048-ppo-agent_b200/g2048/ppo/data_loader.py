@@ -244,12 +244,15 @@ class PPODataset(Dataset):
         self.log_probs = torch.from_numpy(buffer_data["log_probs"]).float()
         self.terminations = torch.from_numpy(buffer_data["terminations"]).bool()
 
-        # advantages and returns: raw (as _compute_gae_returns gives them) and normalised
+        # advantages and returns: ONE device pass for the recurrence (bit-identical to the reference's loop), then the
+        # reference's own host-side normalisation -- the same torch float32 mean / std expressions on the same values
+        # (data_loader.py:61-67), so the normalised arrays are equal to the reference's as well, not merely within 1e-5
         self.raw_advantages, self.raw_returns = self._compute_gae_returns()
-        adv, ret = E.gae_host(self.rewards.numpy(), self.values.numpy(), self.terminations.numpy().astype(np.uint8),
-                              gamma, lambda_gae, True) if len(self.rewards) else (np.zeros(0, np.float32),) * 2
-        self.advantages = torch.from_numpy(adv)
-        self.returns = torch.from_numpy(ret)
+        if len(self.rewards):
+            self.advantages = (self.raw_advantages - self.raw_advantages.mean()) / (self.raw_advantages.std() + 1e-8)
+            self.returns = (self.raw_returns - self.raw_returns.mean()) / (self.raw_returns.std() + 1e-8)
+        else:
+            self.advantages, self.returns = self.raw_advantages, self.raw_returns
 
         self.total_length = len(self.observations)
         if self.max_samples_per_epoch is None or self.max_samples_per_epoch >= self.total_length:

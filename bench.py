@@ -651,14 +651,13 @@ def secondary_measurements(E, N, torch, dev, flush_buf) -> dict:
     scan_scratch = torch.zeros(int(N.lib.g2048_gae_scan_scratch_bytes(n_g)), dtype=torch.uint8, device=dev)
 
     def gae_scan():
-        scan_scratch.zero_()
         N.call("g2048_gae_flat_scan", N.ptr(r), N.ptr(v), N.ptr(d), n_g, 0.99, 0.95, N.ptr(adv), N.ptr(ret), N.ptr(scan_scratch),
                N.ptr(mom), N.stream_ptr())
 
     t = timed(gae_scan)
     add("gae_scan_kernel (opt-in: re-associated reverse scan, 1e-5 relative)", n_g * 17, t,
-        "same buffer and bytes as gae_flat4_kernel above; warp-shuffle affine scan with decoupled look-back over 2 048-step tiles "
-        "(north_star's own design); within 1e-5 relative of the reference loop instead of bit-identical; includes zeroing the scratch")
+        "same buffer and bytes as gae_flat4_kernel above; warp-shuffle affine scan over 2 048-step tiles, one contiguous range of tiles per persistent CTA "
+        "(north_star's own design); within 1e-5 relative of the reference loop instead of bit-identical; two launches (scan + range fix-up)")
     t = timed(lambda: N.call("g2048_normalize", N.ptr(adv), n_g, N.ptr(mom), 1, N.stream_ptr()))
     add("normalize_kernel", n_g * 8, t, "2^26 steps in place; 4 B read + 4 B written per step")
     # the same buffer size with the episode lengths of real play instead of a constant done rate (whose geometric

@@ -436,8 +436,9 @@ int g2048_gae_flat_pipelined(const float* d_rewards, const float* d_values, cons
                              double* d_moments, void* stream);
 
 /* g2048_gae_flat as a segmented affine REVERSE SCAN (north_star's "warp shuffles handle the reverse-scan GAE"): same
- * arguments and moments, its own scratch (g2048_gae_scan_scratch_bytes(n) bytes, 16-byte aligned, zeroed by the caller).
- * The recurrence is re-associated (thread / warp-shuffle / CTA / decoupled look-back over 2 048-step tiles), so the
+ * arguments and moments, its own scratch (g2048_gae_scan_scratch_bytes(n) bytes, 16-byte aligned, need not be zeroed).
+ * The recurrence is re-associated (thread / warp-shuffle / CTA scan of 2 048-step tiles, one contiguous range of tiles
+ * per persistent CTA with the carry in registers, a second small launch for the range boundaries), so the
  * results agree with the reference loop within the 1e-5 relative tolerance north_star states for GAE, NOT bit for bit --
  * opt-in; g2048_gae_flat stays the bit-identical default.  A pure stream: no lane ever walks an episode. */
 int64_t g2048_gae_scan_scratch_bytes(int64_t n);
@@ -458,6 +459,11 @@ int g2048_normalize(float* d_x, int64_t n, const double* d_moments, int which, v
 /* Host-buffer GAE + normalisation (the PPODataset.__init__ path) */
 int g2048_gae_host(const float* h_rewards, const float* h_values, const uint8_t* h_dones, int64_t n, double gamma,
                    double lambda_gae, int normalize, float* h_adv, float* h_ret);
+
+/* The *_host entry points keep, per calling thread, a stream, a grow-only device buffer and 2 x 16 MiB of pinned staging
+ * memory between calls (re-created when the thread switches device).  This frees the calling thread's; a thread that
+ * used *_host entry points should call it before it ends. */
+int g2048_release_host_workspace(void);
 
 /* ---- statistics (src/stats/running_stats_vec.py:55-87) */
 

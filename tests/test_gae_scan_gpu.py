@@ -69,8 +69,10 @@ def test_scan_matches_the_bit_exact_kernel_at_scale(E, n, done_rate):
     assert_within_tolerance(ret.cpu().numpy(), want_r, "ret")
     m = mom.cpu().numpy()
     assert m[0] == n
-    np.testing.assert_allclose(m[1], adv.double().sum().item(), rtol=1e-9, atol=1e-6)
-    np.testing.assert_allclose(m[4], (ret.double() ** 2).sum().item(), rtol=1e-9)
+    # a thread's 8 steps are summed in fp32 before they join the fp64 sums: 1e-6 relative (the sums only feed mean / std)
+    np.testing.assert_allclose(m[1], adv.double().sum().item(), rtol=1e-6, atol=1e-3 * max(1.0, float(adv.abs().double().sum()) * 1e-4))
+    np.testing.assert_allclose(m[2], (adv.double() ** 2).sum().item(), rtol=1e-6)
+    np.testing.assert_allclose(m[4], (ret.double() ** 2).sum().item(), rtol=1e-6)
 
 
 def test_scan_at_c4_size_with_thousand_step_episodes(E):
