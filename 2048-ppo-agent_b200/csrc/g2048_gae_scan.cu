@@ -24,6 +24,7 @@
 //     requirement.
 // 9 B read + 8 B written per step; fp64 moment sums for the normalisation in the same pass.
 #include "g2048_common.cuh"
+#include "g2048_tma.cuh"
 
 namespace g2048 {
 
@@ -49,75 +50,107 @@ __device__ __forceinline__ Affine compose(Affine outer, Affine inner) {
     return Affine{outer.a * inner.a, outer.a * inner.b + outer.b};
 }
 
-template <bool ALIGNED>
+constexpr int SCAN_STAGES = 3;
+// one stage of the shared-memory ring: a tile's rewards, values (+ the 4 values after it) and done flags, as the bulk
+// copy engine delivers them
+struct __align__(128) ScanStage {
+    float r[SCAN_TILE];
+    float v[SCAN_TILE + 4];
+    uint8_t d[SCAN_TILE];
+};
+constexpr int SCAN_SMEM_BYTES = SCAN_STAGES * (int)sizeof(ScanStage);
+
+// STAGED: the tiles come in through the bulk copy engine (cp.async.bulk, SASS UBLKCP) into a three-stage ring in shared
+// memory, two tiles ahead of the one being scanned, so that a CTA keeps ~36 KB of reads in flight whatever its
+// threads are doing -- with loads into registers (also one tile ahead) the in-flight bytes per SM were the limit
+// (Little's law: 24 warps x 2.4 KB = 58 KB against a bandwidth-delay product of ~70 KB per SM): 0.67 of HBM.
+// Needs 16-byte aligned arrays; the unaligned form (views into a larger buffer) loads through registers.
+template <bool STAGED>
 __global__ void __launch_bounds__(SCAN_THREADS, 3)
 gae_scan_kernel(const float* __restrict__ rewards, const float* __restrict__ values, const uint8_t* __restrict__ dones,
                 int64_t n, int64_t n_tiles, int64_t tiles_per_range, float gamma, float gamma_lambda, float* __restrict__ adv,
                 float* __restrict__ ret, ScanRange* __restrict__ ranges, double* __restrict__ moments) {
+    extern __shared__ __align__(128) uint8_t scan_smem[];
+    ScanStage* stages = reinterpret_cast<ScanStage*>(scan_smem);
+    __shared__ __align__(8) uint64_t s_full[SCAN_STAGES];
     __shared__ Affine s_warp[2][SCAN_WARPS];  // double-buffered by tile parity: one barrier per tile
     __shared__ double s_red[4 * SCAN_WARPS];
     __shared__ unsigned int s_pending;
 
     const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
-    if (threadIdx.x == 0) s_pending = 0u;
     const int64_t tile_lo = (int64_t)blockIdx.x * tiles_per_range;
     const int64_t tile_hi = min(n_tiles, tile_lo + tiles_per_range);
+    if (threadIdx.x == 0) {
+        s_pending = 0u;
+        if (STAGED) {
+            for (int k = 0; k < SCAN_STAGES; ++k) mbar_init(&s_full[k], 1);
+            fence_proxy_async();  // the initialised barriers -> visible to the copy engine
+        }
+    }
+    __syncthreads();
+
+    // a tile that ends inside the buffer with room for the 4 extra values is fetched by three bulk copies; the last
+    // tile of the buffer (ragged, or without anything after it) goes through registers
+    auto bulk_ok = [&](int64_t tile) { return STAGED && (tile + 1) * SCAN_TILE + 4 <= n; };
+    auto issue = [&](int64_t tile, unsigned k) {  // thread 0
+        if (tile < tile_lo || !bulk_ok(tile)) return;
+        ScanStage& st = stages[k % SCAN_STAGES];
+        const int64_t lo = tile * SCAN_TILE;
+        mbar_arrive_expect_tx(&s_full[k % SCAN_STAGES], (uint32_t)(SCAN_TILE * 4 + (SCAN_TILE + 4) * 4 + SCAN_TILE));
+        bulk_load(st.r, rewards + lo, SCAN_TILE * 4, &s_full[k % SCAN_STAGES]);
+        bulk_load(st.v, values + lo, (SCAN_TILE + 4) * 4, &s_full[k % SCAN_STAGES]);
+        bulk_load(st.d, dones + lo, SCAN_TILE, &s_full[k % SCAN_STAGES]);
+    };
+    // the ring serves the tiles from ring_top downwards: use j of the ring (tile ring_top - j) goes through stage j % 3
+    // and completes phase j / 3 of that stage's barrier.  Only the last one or two tiles of the BUFFER cannot be
+    // fetched in bulk; they sit at the top of their range and are taken through registers before the ring starts.
+    int64_t ring_top = tile_hi - 1;
+    while (ring_top >= tile_lo && !bulk_ok(ring_top)) --ring_top;
+    if (STAGED && threadIdx.x == 0) {
+        issue(ring_top, 0);
+        issue(ring_top - 1, 1);
+    }
+
     Affine carry{1.0f, 0.0f};  // gae entering the current tile = carry.a * x + carry.b, x = gae of the next range's first step
     double acc4[4] = {0.0, 0.0, 0.0, 0.0};
     unsigned my_pending = 0;
     unsigned it = 0;
-
-    // 8 consecutive steps of one tile per thread, as loaded: the NEXT tile's are requested before the current one is
-    // processed, so a CTA always has a tile in flight (without this a tile's loads, its scan and its stores run one after
-    // the other: 0.69 of HBM)
-    struct Raw {
-        float r[SCAN_ITEMS], v[SCAN_ITEMS + 1];
-        unsigned dmask;
-    };
-    auto load_tile = [&](int64_t tile, Raw& o) {
-        const int64_t first = tile * SCAN_TILE + (int64_t)threadIdx.x * SCAN_ITEMS;
-        if (ALIGNED && first + SCAN_ITEMS <= n) {
-            const float4 r0 = *reinterpret_cast<const float4*>(rewards + first), r1 = *reinterpret_cast<const float4*>(rewards + first + 4);
-            const float4 v0 = *reinterpret_cast<const float4*>(values + first), v1 = *reinterpret_cast<const float4*>(values + first + 4);
-            const uint2 dd = *reinterpret_cast<const uint2*>(dones + first);
-            o.r[0] = r0.x; o.r[1] = r0.y; o.r[2] = r0.z; o.r[3] = r0.w; o.r[4] = r1.x; o.r[5] = r1.y; o.r[6] = r1.z; o.r[7] = r1.w;
-            o.v[0] = v0.x; o.v[1] = v0.y; o.v[2] = v0.z; o.v[3] = v0.w; o.v[4] = v1.x; o.v[5] = v1.y; o.v[6] = v1.z; o.v[7] = v1.w;
-            unsigned m = 0;
-#pragma unroll
-            for (int k = 0; k < 4; ++k) {
-                m |= (((dd.x >> (8 * k)) & 0xFFu) != 0u ? 1u : 0u) << k;
-                m |= (((dd.y >> (8 * k)) & 0xFFu) != 0u ? 1u : 0u) << (4 + k);
-            }
-            o.dmask = m;
-        } else {
-            unsigned m = 0;
-#pragma unroll
-            for (int k = 0; k < SCAN_ITEMS; ++k) {
-                const bool in = first + k < n;
-                o.r[k] = in ? rewards[first + k] : 0.0f;
-                o.v[k] = in ? values[first + k] : 0.0f;
-                m |= ((in ? dones[first + k] != 0 : true) ? 1u : 0u) << k;  // past the end: a = 0, delta = 0 -- contributes nothing
-            }
-            o.dmask = m;
-        }
-        o.v[SCAN_ITEMS] = (first + SCAN_ITEMS < n) ? values[first + SCAN_ITEMS] : 0.0f;  // V of the step after mine (0 past the end)
-    };
-    Raw cur;
-    load_tile(tile_hi - 1, cur);
     for (int64_t tile = tile_hi - 1; tile >= tile_lo; --tile, ++it) {
         const int64_t first = tile * SCAN_TILE + (int64_t)threadIdx.x * SCAN_ITEMS;  // this thread's first step
         const bool full = first + SCAN_ITEMS <= n;
-        Raw nxt;
-        if (tile > tile_lo) load_tile(tile - 1, nxt);
+        const bool ringed = STAGED && tile <= ring_top;
+        const unsigned j = (unsigned)(ring_top - tile);  // use of the ring (meaningful when ringed)
+        // two tiles ahead: its stage was last read one iteration ago, before that iteration's barrier
+        if (ringed && threadIdx.x == 0) issue(tile - 2, j + 2);
+
+        // ---- 8 consecutive steps per thread ----------------------------------------------------------------------
         float r[SCAN_ITEMS], v[SCAN_ITEMS + 1];
         bool d[SCAN_ITEMS];
+        if (ringed) {
+            const ScanStage& st = stages[j % SCAN_STAGES];
+            mbar_wait(&s_full[j % SCAN_STAGES], (j / SCAN_STAGES) & 1u);
+            const int o = threadIdx.x * SCAN_ITEMS;
+            const float4 r0 = *reinterpret_cast<const float4*>(st.r + o), r1 = *reinterpret_cast<const float4*>(st.r + o + 4);
+            const float4 v0 = *reinterpret_cast<const float4*>(st.v + o), v1 = *reinterpret_cast<const float4*>(st.v + o + 4);
+            const uint2 dd = *reinterpret_cast<const uint2*>(st.d + o);
+            r[0] = r0.x; r[1] = r0.y; r[2] = r0.z; r[3] = r0.w; r[4] = r1.x; r[5] = r1.y; r[6] = r1.z; r[7] = r1.w;
+            v[0] = v0.x; v[1] = v0.y; v[2] = v0.z; v[3] = v0.w; v[4] = v1.x; v[5] = v1.y; v[6] = v1.z; v[7] = v1.w;
+            v[SCAN_ITEMS] = st.v[o + SCAN_ITEMS];
 #pragma unroll
-        for (int k = 0; k < SCAN_ITEMS; ++k) {
-            r[k] = cur.r[k];
-            v[k] = cur.v[k];
-            d[k] = ((cur.dmask >> k) & 1u) != 0u;
+            for (int k = 0; k < 4; ++k) {
+                d[k] = ((dd.x >> (8 * k)) & 0xFFu) != 0u;
+                d[4 + k] = ((dd.y >> (8 * k)) & 0xFFu) != 0u;
+            }
+        } else {
+#pragma unroll
+            for (int k = 0; k < SCAN_ITEMS; ++k) {
+                const bool in = first + k < n;
+                r[k] = in ? rewards[first + k] : 0.0f;
+                v[k] = in ? values[first + k] : 0.0f;
+                d[k] = in ? dones[first + k] != 0 : true;  // past the end: a = 0, delta = 0 -- contributes nothing
+            }
+            v[SCAN_ITEMS] = (first + SCAN_ITEMS < n) ? values[first + SCAN_ITEMS] : 0.0f;  // V of the step after mine (0 past the end)
         }
-        v[SCAN_ITEMS] = cur.v[SCAN_ITEMS];
 
         // ---- per-step maps and the thread's aggregate (composition of its 8 steps, first step outermost) ---------------
         float a[SCAN_ITEMS], b[SCAN_ITEMS];
@@ -144,7 +177,7 @@ gae_scan_kernel(const float* __restrict__ rewards, const float* __restrict__ val
         after.a = __shfl_down_sync(0xFFFFFFFFu, incl.a, 1);
         after.b = __shfl_down_sync(0xFFFFFFFFu, incl.b, 1);
         if (lane == 31) after = Affine{1.0f, 0.0f};
-        __syncthreads();  // the one barrier of a tile
+        __syncthreads();  // the one barrier of a tile (also: everybody has read this tile's stage)
         // ... the warps after mine, and the whole tile (every thread composes the 8 warp aggregates itself: no second barrier)
         Affine later{1.0f, 0.0f}, whole{1.0f, 0.0f};
 #pragma unroll
@@ -180,7 +213,7 @@ gae_scan_kernel(const float* __restrict__ rewards, const float* __restrict__ val
         }
 #pragma unroll
         for (int k = 0; k < 4; ++k) acc4[k] += (double)part[k];
-        if (ALIGNED && full) {
+        if (STAGED && full) {
             *reinterpret_cast<float4*>(adv + first) = make_float4(o_adv[0], o_adv[1], o_adv[2], o_adv[3]);
             *reinterpret_cast<float4*>(adv + first + 4) = make_float4(o_adv[4], o_adv[5], o_adv[6], o_adv[7]);
             *reinterpret_cast<float4*>(ret + first) = make_float4(o_ret[0], o_ret[1], o_ret[2], o_ret[3]);
@@ -194,7 +227,6 @@ gae_scan_kernel(const float* __restrict__ rewards, const float* __restrict__ val
                 }
             }
         }
-        cur = nxt;
     }
     if (my_pending) atomicAdd(&s_pending, my_pending);
     if (moments) {
@@ -271,18 +303,27 @@ extern "C" int g2048_gae_flat_scan(const float* d_rewards, const float* d_values
     G2048_REQUIRE(((uintptr_t)d_scan_state & 15u) == 0, "gae_flat_scan: scratch must be 16-byte aligned");
     const int64_t n_tiles = (n + SCAN_TILE - 1) / SCAN_TILE;
     const auto a16 = [](const void* p) { return ((uintptr_t)p & 15u) == 0; };
-    const bool aligned = a16(d_rewards) && a16(d_values) && a16(d_adv) && a16(d_ret) && ((uintptr_t)d_dones & 7u) == 0;
+    const bool aligned = a16(d_rewards) && a16(d_values) && a16(d_adv) && a16(d_ret) && a16(d_dones);  // bulk copies and 128-bit stores
     cudaStream_t st = (cudaStream_t)stream;
     const int sms = sm_count();
     if (sms <= 0) return fail_arg("gae_flat_scan: no device");
-    int64_t want = (int64_t)sms * 3;  // three 256-thread CTAs per SM (two tiles each in flight), each walking its own range of tiles
+    int64_t want = (int64_t)sms * 3;  // three 256-thread CTAs per SM (a 54 KiB ring each: two tiles in flight), each walking its own range of tiles
     if (want > SCAN_MAX_RANGES) want = SCAN_MAX_RANGES;
     const int64_t tiles_per_range = (n_tiles + want - 1) / want;
     const int n_ranges = (int)((n_tiles + tiles_per_range - 1) / tiles_per_range);
     const float g = (float)gamma, gl = (float)(gamma * lambda_gae);
+    static bool configured_on[64] = {false};
+    bool* configured = device_once_flag(configured_on);
+    if (!configured) return fail_arg("no CUDA device");
+    if (!*configured) {
+        const int rc = check_cuda(cudaFuncSetAttribute(gae_scan_kernel<true>, cudaFuncAttributeMaxDynamicSharedMemorySize, SCAN_SMEM_BYTES),
+                                  "gae_flat_scan: shared memory attribute");
+        if (rc) return rc;
+        *configured = true;
+    }
     if (aligned)
-        gae_scan_kernel<true><<<n_ranges, SCAN_THREADS, 0, st>>>(d_rewards, d_values, d_dones, n, n_tiles, tiles_per_range, g, gl,
-                                                                 d_adv, d_ret, (ScanRange*)d_scan_state, d_moments);
+        gae_scan_kernel<true><<<n_ranges, SCAN_THREADS, SCAN_SMEM_BYTES, st>>>(d_rewards, d_values, d_dones, n, n_tiles, tiles_per_range,
+                                                                              g, gl, d_adv, d_ret, (ScanRange*)d_scan_state, d_moments);
     else
         gae_scan_kernel<false><<<n_ranges, SCAN_THREADS, 0, st>>>(d_rewards, d_values, d_dones, n, n_tiles, tiles_per_range, g, gl,
                                                                   d_adv, d_ret, (ScanRange*)d_scan_state, d_moments);

@@ -49,3 +49,40 @@ def test_one_process_can_drive_two_devices():
             results.append([t.cpu() for t in (out["final_boards"], out["lengths"], adv, ret, obs, emb)])
     for a, b in zip(*results):
         assert torch.equal(a, b)
+
+
+@pytest.mark.skipif(torch.cuda.device_count() < 2, reason="needs two GPUs")
+def test_a_runner_on_cuda1_works_while_cuda0_is_current():
+    """`device=` is where the runner's kernels RUN, not only where its tensors live: every libg2048 call goes to the
+    device of the tensors it is given (and to that device's current stream) whatever the process's current device is
+    (g2048/_native.py: ptr / stream_ptr / call)."""
+    import g2048
+    from g2048.ppo import collect_rollouts
+
+    torch.cuda.set_device(0)
+    want = g2048.BatchRunner(init_seed=5, act_fn=g2048.act_randomly, device="cuda:0")
+    got = g2048.BatchRunner(init_seed=5, act_fn=g2048.act_randomly, device="cuda:1")
+    assert torch.cuda.current_device() == 0
+    for batch in (300, 40000):
+        a, b = want.run_flat_batch(batch), got.run_flat_batch(batch)
+        assert b.boards.device == torch.device("cuda", 1) and torch.cuda.current_device() == 0
+        for name in ("boards", "meta", "rewards", "log_probs", "lengths", "final_boards", "scores"):
+            assert torch.equal(getattr(a, name).cpu(), getattr(b, name).cpu()), name
+        pa, pb = want.run_packed_batch(200), got.run_packed_batch(200)
+        assert torch.equal(pa.boards.cpu(), pb.boards.cpu()) and torch.equal(pa.rewards.cpu(), pb.rewards.cpu())
+    assert (want.key == got.key).all()
+    buf = g2048.RolloutBuffer(31, 16, 4)
+    out = collect_rollouts(got, buf, 500, 1)
+    packed = buf.get_packed()
+    assert packed["boards"].device == torch.device("cuda", 1) and out["total_episodes"] == 500
+    batches = g2048.DevicePPOBatches(packed, batch_size=256, epoch_prefetch=True)
+    first = next(iter(batches))
+    assert first["observations"].device == torch.device("cuda", 1) and torch.cuda.current_device() == 0
+    # the same minibatch from the same buffer gathered on cuda:0
+    packed0 = {k: v.to("cuda:0") for k, v in packed.items()}
+    torch.manual_seed(3)
+    ref = next(iter(g2048.DevicePPOBatches(packed0, batch_size=256)))
+    torch.manual_seed(3)
+    mine = next(iter(g2048.DevicePPOBatches(packed, batch_size=256)))
+    for k in ref:
+        assert torch.equal(ref[k].cpu(), mine[k].cpu()), k
