@@ -191,23 +191,39 @@ gae_scan_kernel(const float* __restrict__ rewards, const float* __restrict__ val
         carry = compose(whole, carry);  // ... and what enters the next (earlier) tile
 
         // ---- apply: the gae entering my steps for x = 0, then the reference's own recurrence over them -------------------
-        float g = entering.b, coef = entering.a;
+        float g = entering.b;
         float o_adv[SCAN_ITEMS], o_ret[SCAN_ITEMS];
         float part[4] = {0.0f, 0.0f, 0.0f, 0.0f};  // the thread's 8 steps are summed in fp32, tiles and threads in fp64
+        if (entering.a == 0.0f) {  // nothing of x reaches my steps (everywhere but at the end of a range)
 #pragma unroll
-        for (int k = SCAN_ITEMS - 1; k >= 0; --k) {
-            g = b[k] + a[k] * g;
-            coef = a[k] * coef;  // coefficient of x in this step's gae: non-zero only at the end of the range
-            o_adv[k] = g;
-            o_ret[k] = g + v[k];
-            if (first + k < n) {
-                if (coef != 0.0f) {
-                    my_pending += 1u;  // finished by gae_scan_fix_kernel, which also adds it to the moments
-                } else {
+            for (int k = SCAN_ITEMS - 1; k >= 0; --k) {
+                g = b[k] + a[k] * g;
+                o_adv[k] = g;
+                o_ret[k] = g + v[k];
+                if (first + k < n) {
                     part[0] += g;
                     part[1] += g * g;
                     part[2] += o_ret[k];
                     part[3] += o_ret[k] * o_ret[k];
+                }
+            }
+        } else {
+            float coef = entering.a;
+#pragma unroll
+            for (int k = SCAN_ITEMS - 1; k >= 0; --k) {
+                g = b[k] + a[k] * g;
+                coef = a[k] * coef;  // coefficient of x in this step's gae: non-zero only at the end of the range
+                o_adv[k] = g;
+                o_ret[k] = g + v[k];
+                if (first + k < n) {
+                    if (coef != 0.0f) {
+                        my_pending += 1u;  // finished by gae_scan_fix_kernel, which also adds it to the moments
+                    } else {
+                        part[0] += g;
+                        part[1] += g * g;
+                        part[2] += o_ret[k];
+                        part[3] += o_ret[k] * o_ret[k];
+                    }
                 }
             }
         }

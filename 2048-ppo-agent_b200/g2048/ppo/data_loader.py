@@ -2,9 +2,11 @@
 
 ``compute_gae`` is the device path: flat packed buffer in, advantages and returns out, the
 reverse recurrence of data_loader.py:103-130 run by ``g2048_gae_flat`` (bit-identical to the
-reference's fp32 loop) and the global normalisation of :61-67 by ``g2048_normalize``; under
-``torch.distributed`` the normalisation moments are all-reduced so that a sharded buffer is
-normalised with the global mean / std.
+reference's fp32 loop) and the global normalisation of :61-67 by ``g2048_normalize``.  A buffer
+that is SHARDED over ranks is normalised with the global mean / std when the caller passes the
+process group (``group=torch.distributed.group.WORLD``): the six fp64 moments are all-reduced.  The
+collective is opt-in -- a buffer that lives on one rank of a multi-rank job (rank 0's evaluation
+pass, a per-rank replay buffer) must not wait for peers that never call.
 
 ``PPODataset`` / ``create_ppo_dataloader`` keep the reference's constructor and item schema.
 """
@@ -29,12 +31,10 @@ def compute_gae(rewards: torch.Tensor, values: torch.Tensor, terminations: torch
     """
     dones = terminations if terminations.dtype == torch.uint8 else terminations.to(torch.uint8)
     adv, ret, moments = E.gae_flat(rewards.contiguous(), values.contiguous(), dones.contiguous(), gamma, lambda_gae)
-    if normalize or return_moments:
-        if group is not None or (torch.distributed.is_available() and torch.distributed.is_initialized()
-                                 and torch.distributed.get_world_size() > 1):
-            from ..dist import allreduce_sum_
+    if (normalize or return_moments) and group is not None:
+        from ..dist import allreduce_sum_
 
-            allreduce_sum_(moments, group)
+        allreduce_sum_(moments, group)
     if normalize:
         E.normalize_(adv, moments, 1)
         E.normalize_(ret, moments, 3)
@@ -106,8 +106,7 @@ class DevicePPOBatches:
                                                normalize=True, group=group)
         else:
             self._adv = self._ret = packed["rewards"]
-            if group is not None or (torch.distributed.is_available() and torch.distributed.is_initialized()
-                                     and torch.distributed.get_world_size() > 1):
+            if group is not None:
                 # an empty shard still takes part in the moment all-reduce of its peers (zeros), or they would wait forever
                 from ..dist import allreduce_sum_
 

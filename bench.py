@@ -254,7 +254,10 @@ def main():
     if world > 1:
         # keep stdout for the one JSON line: NCCL's version / debug banner goes to stderr
         os.environ.setdefault("NCCL_DEBUG_FILE", "/dev/stderr")
-        dist.init_process_group("nccl", device_id=dev)
+        import datetime
+
+        # a collective that some rank never joins should fail within minutes, not after NCCL's default 10
+        dist.init_process_group("nccl", device_id=dev, timeout=datetime.timedelta(seconds=300))
 
     policy_id = E.POLICY_RANDOM if args.policy == "random" else E.POLICY_DRUL
     mode = E.RNG_PARTITIONABLE
