@@ -28,8 +28,17 @@
 
 namespace g2048 {
 
-constexpr int SCAN_THREADS = 256;
-constexpr int SCAN_ITEMS = 8;
+#ifndef G2048_SCAN_THREADS
+#define G2048_SCAN_THREADS 256
+#endif
+#ifndef G2048_SCAN_ITEMS
+#define G2048_SCAN_ITEMS 8  // consecutive steps per thread (a multiple of 8)
+#endif
+#ifndef G2048_SCAN_CTAS
+#define G2048_SCAN_CTAS 3  // resident CTAs per SM
+#endif
+constexpr int SCAN_THREADS = G2048_SCAN_THREADS;
+constexpr int SCAN_ITEMS = G2048_SCAN_ITEMS;
 constexpr int SCAN_TILE = SCAN_THREADS * SCAN_ITEMS;  // 2 048 steps
 constexpr int SCAN_WARPS = SCAN_THREADS / 32;
 constexpr int SCAN_MAX_RANGES = 4096;
@@ -66,7 +75,7 @@ constexpr int SCAN_SMEM_BYTES = SCAN_STAGES * (int)sizeof(ScanStage);
 // (Little's law: 24 warps x 2.4 KB = 58 KB against a bandwidth-delay product of ~70 KB per SM): 0.67 of HBM.
 // Needs 16-byte aligned arrays; the unaligned form (views into a larger buffer) loads through registers.
 template <bool STAGED>
-__global__ void __launch_bounds__(SCAN_THREADS, 3)
+__global__ void __launch_bounds__(SCAN_THREADS, G2048_SCAN_CTAS)
 gae_scan_kernel(const float* __restrict__ rewards, const float* __restrict__ values, const uint8_t* __restrict__ dones,
                 int64_t n, int64_t n_tiles, int64_t tiles_per_range, float gamma, float gamma_lambda, float* __restrict__ adv,
                 float* __restrict__ ret, ScanRange* __restrict__ ranges, double* __restrict__ moments) {
@@ -130,16 +139,22 @@ gae_scan_kernel(const float* __restrict__ rewards, const float* __restrict__ val
             const ScanStage& st = stages[j % SCAN_STAGES];
             mbar_wait(&s_full[j % SCAN_STAGES], (j / SCAN_STAGES) & 1u);
             const int o = threadIdx.x * SCAN_ITEMS;
-            const float4 r0 = *reinterpret_cast<const float4*>(st.r + o), r1 = *reinterpret_cast<const float4*>(st.r + o + 4);
-            const float4 v0 = *reinterpret_cast<const float4*>(st.v + o), v1 = *reinterpret_cast<const float4*>(st.v + o + 4);
-            const uint2 dd = *reinterpret_cast<const uint2*>(st.d + o);
-            r[0] = r0.x; r[1] = r0.y; r[2] = r0.z; r[3] = r0.w; r[4] = r1.x; r[5] = r1.y; r[6] = r1.z; r[7] = r1.w;
-            v[0] = v0.x; v[1] = v0.y; v[2] = v0.z; v[3] = v0.w; v[4] = v1.x; v[5] = v1.y; v[6] = v1.z; v[7] = v1.w;
+#pragma unroll
+            for (int q = 0; q < SCAN_ITEMS / 4; ++q) {
+                const float4 rq = *reinterpret_cast<const float4*>(st.r + o + 4 * q);
+                const float4 vq = *reinterpret_cast<const float4*>(st.v + o + 4 * q);
+                r[4 * q] = rq.x; r[4 * q + 1] = rq.y; r[4 * q + 2] = rq.z; r[4 * q + 3] = rq.w;
+                v[4 * q] = vq.x; v[4 * q + 1] = vq.y; v[4 * q + 2] = vq.z; v[4 * q + 3] = vq.w;
+            }
             v[SCAN_ITEMS] = st.v[o + SCAN_ITEMS];
 #pragma unroll
-            for (int k = 0; k < 4; ++k) {
-                d[k] = ((dd.x >> (8 * k)) & 0xFFu) != 0u;
-                d[4 + k] = ((dd.y >> (8 * k)) & 0xFFu) != 0u;
+            for (int q = 0; q < SCAN_ITEMS / 8; ++q) {
+                const uint2 dd = *reinterpret_cast<const uint2*>(st.d + o + 8 * q);
+#pragma unroll
+                for (int k = 0; k < 4; ++k) {
+                    d[8 * q + k] = ((dd.x >> (8 * k)) & 0xFFu) != 0u;
+                    d[8 * q + 4 + k] = ((dd.y >> (8 * k)) & 0xFFu) != 0u;
+                }
             }
         } else {
 #pragma unroll
@@ -230,10 +245,11 @@ gae_scan_kernel(const float* __restrict__ rewards, const float* __restrict__ val
 #pragma unroll
         for (int k = 0; k < 4; ++k) acc4[k] += (double)part[k];
         if (STAGED && full) {
-            *reinterpret_cast<float4*>(adv + first) = make_float4(o_adv[0], o_adv[1], o_adv[2], o_adv[3]);
-            *reinterpret_cast<float4*>(adv + first + 4) = make_float4(o_adv[4], o_adv[5], o_adv[6], o_adv[7]);
-            *reinterpret_cast<float4*>(ret + first) = make_float4(o_ret[0], o_ret[1], o_ret[2], o_ret[3]);
-            *reinterpret_cast<float4*>(ret + first + 4) = make_float4(o_ret[4], o_ret[5], o_ret[6], o_ret[7]);
+#pragma unroll
+            for (int q = 0; q < SCAN_ITEMS / 4; ++q) {
+                *reinterpret_cast<float4*>(adv + first + 4 * q) = make_float4(o_adv[4 * q], o_adv[4 * q + 1], o_adv[4 * q + 2], o_adv[4 * q + 3]);
+                *reinterpret_cast<float4*>(ret + first + 4 * q) = make_float4(o_ret[4 * q], o_ret[4 * q + 1], o_ret[4 * q + 2], o_ret[4 * q + 3]);
+            }
         } else {
 #pragma unroll
             for (int k = 0; k < SCAN_ITEMS; ++k) {
@@ -323,7 +339,7 @@ extern "C" int g2048_gae_flat_scan(const float* d_rewards, const float* d_values
     cudaStream_t st = (cudaStream_t)stream;
     const int sms = sm_count();
     if (sms <= 0) return fail_arg("gae_flat_scan: no device");
-    int64_t want = (int64_t)sms * 3;  // three 256-thread CTAs per SM (a 54 KiB ring each: two tiles in flight), each walking its own range of tiles
+    int64_t want = (int64_t)sms * G2048_SCAN_CTAS;  // three 256-thread CTAs per SM (a 54 KiB ring each: two tiles in flight), each walking its own range of tiles
     if (want > SCAN_MAX_RANGES) want = SCAN_MAX_RANGES;
     const int64_t tiles_per_range = (n_tiles + want - 1) / want;
     const int n_ranges = (int)((n_tiles + tiles_per_range - 1) / tiles_per_range);

@@ -38,6 +38,11 @@ constexpr int PLAY3_TABLE_BYTES = 65536 * 2 + 65536;
 // more (DRUL, 2^18 envs: 1.91 -> 2.07 ms); the headline workload is the large batch.  A/B: tools/ab_variants.py.
 #define G2048_PLAY3_TAIL 0
 #endif
+#ifndef G2048_PLAY3_TAIL_REC
+// 1: tail compaction in the RECORDING form only, inlined (that form runs at C4-like sizes, 3-4 episodes per lane, where
+// the drain is a third of the launch)
+#define G2048_PLAY3_TAIL_REC 0
+#endif
 
 [[maybe_unused]] constexpr int PLAY3_TAIL_STEPS = G2048_PLAY3_TAIL_STEPS;  // steps between two compactions of the CTA's live envs in the tail
 // what moves with an env when the tail compaction hands it to another lane (32 bytes)
@@ -281,8 +286,13 @@ __device__ __forceinline__ void play3_step(Play3Lane& L, const Play3Ctx& c) {
 // cost of a launch (what does not shrink with the batch) drops from 0.49 to 0.37 ms: 2^18 envs (C4) 1.54 -> 1.44 ms
 // inlined, 1.47 ms out of line.  Out of line because inlined the same source cost the main loop 2 % (2^24 envs:
 // 69.8 -> 71.3 ms; A/B on one box, tools/ab_variants.py); see G2048_PLAY3_TAIL above for why it is still off.
+#if G2048_PLAY3_TAIL_REC
+#define G2048_TAIL_INLINE __forceinline__
+#else
+#define G2048_TAIL_INLINE __noinline__
+#endif
 template <int MODE, int POLICY, bool REC>
-__device__ __noinline__ void play3_tail(Play3Lane& lane_state, const Play3Ctx& c, unsigned* s_tail_cnt, TailEntry* s_pool) {
+__device__ G2048_TAIL_INLINE void play3_tail(Play3Lane& lane_state, const Play3Ctx& c, unsigned* s_tail_cnt, TailEntry* s_pool) {
     Play3Lane L = lane_state;  // work on a copy in registers: stores through the context's pointers cannot alias it
     const unsigned lane = threadIdx.x & 31u;
     unsigned round = 0;
@@ -337,7 +347,7 @@ play3_kernel(const uint2* __restrict__ subs, int64_t n_subs, uint32_t batch_glob
              const PlayRecordArena rec) {
     extern __shared__ __align__(16) uint8_t smem_raw[];
     unsigned long long* s_stats = reinterpret_cast<unsigned long long*>(smem_raw + PLAY3_TABLE_BYTES);
-#if G2048_PLAY3_TAIL
+#if G2048_PLAY3_TAIL || G2048_PLAY3_TAIL_REC
     volatile unsigned* s_tail_flag = reinterpret_cast<volatile unsigned*>(smem_raw + PLAY3_TABLE_BYTES + PLAY3_STATS_BYTES);
     unsigned* s_tail_cnt = reinterpret_cast<unsigned*>(smem_raw + PLAY3_TABLE_BYTES + PLAY3_STATS_BYTES) + 1;  // [2]
     TailEntry* s_pool = reinterpret_cast<TailEntry*>(smem_raw + PLAY3_TABLE_BYTES + PLAY3_STATS_BYTES + PLAY3_CTL_BYTES);
@@ -407,26 +417,29 @@ play3_kernel(const uint2* __restrict__ subs, int64_t n_subs, uint32_t batch_glob
                     }
                 }
             }
-#if G2048_PLAY3_TAIL
-            // The queue is empty (or, recording, no idle lane of this warp can take an env any more): tell the CTA.
-            if (exhausted || (REC && want == 0u && idle == 0xFFFFFFFFu)) {
-                *s_tail_flag = 1;
-                tail_seen = true;
-            }
-#else
-            if (__ballot_sync(0xFFFFFFFFu, L.phase != PHASE_NONE) == 0u && (exhausted || want == 0u)) tail_seen = true;
+            constexpr bool TAIL = G2048_PLAY3_TAIL || (G2048_PLAY3_TAIL_REC && REC);
+            if (TAIL) {
+#if G2048_PLAY3_TAIL || G2048_PLAY3_TAIL_REC
+                // The queue is empty (or, recording, no idle lane of this warp can take an env any more): tell the CTA.
+                if (exhausted || (REC && want == 0u && idle == 0xFFFFFFFFu)) {
+                    *s_tail_flag = 1;
+                    tail_seen = true;
+                }
 #endif
+            } else {
+                if (__ballot_sync(0xFFFFFFFFu, L.phase != PHASE_NONE) == 0u && (exhausted || want == 0u)) tail_seen = true;
+            }
         }
-#if G2048_PLAY3_TAIL
+#if G2048_PLAY3_TAIL || G2048_PLAY3_TAIL_REC
         // once any warp of the CTA has seen the queue empty, all of them (each looks at the flag once per iteration)
         // leave for the tail phase together
-        if (*s_tail_flag) tail_seen = true;
+        if ((G2048_PLAY3_TAIL || REC) && *s_tail_flag) tail_seen = true;
 #endif
         if (tail_seen) break;
         if (L.phase != PHASE_NONE) play3_step<MODE, POLICY, REC>(L, c);
     }
-#if G2048_PLAY3_TAIL
-    {
+#if G2048_PLAY3_TAIL || G2048_PLAY3_TAIL_REC
+    if (G2048_PLAY3_TAIL || REC) {
         Play3Lane handed = L;  // only this copy has its address taken: the main loop's state stays in registers
         play3_tail<MODE, POLICY, REC>(handed, c, s_tail_cnt, s_pool);
         L = handed;

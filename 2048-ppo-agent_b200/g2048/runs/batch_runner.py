@@ -271,25 +271,33 @@ class BatchRunner:
         boards, status = E.env_init(self.chain.peek(1)[0], batch_size, lo, n, mode)
         lengths = torch.zeros(n, dtype=torch.int32, device=dev)
         scores = torch.zeros(n, dtype=torch.float32, device=dev)
-        rewards = torch.zeros(n, dtype=torch.float32, device=dev)
-        live_ids = torch.arange(n, dtype=torch.int64, device=dev)
-        t = 0
+        t0 = 0
         while True:
-            subs = self.chain.peek(1 + 2 * (t + 1))
+            # chunks of NET_SYNC_STEPS steps: the live list is built once per chunk, the chunk's rewards and metas are
+            # the only records kept (5 bytes per env-step, dropped after the chunk), one host read per chunk
+            steps = NET_SYNC_STEPS
+            subs = self.chain.peek(1 + 2 * (t0 + steps))
+            live_ids = torch.nonzero((status & N.STATUS_DONE) == 0).flatten()
+            rm = torch.zeros((steps, n), dtype=torch.uint8, device=dev)
+            rr = torch.zeros((steps, n), dtype=torch.float32, device=dev)
+            alive_before = (status & N.STATUS_DONE) == 0
             if live_ids.shape[0]:
-                obs = E.expand_obs_gather(boards, live_ids, fn.obs_dtype)
-                logits, values = fn.forward_logits(obs)
-                rewards.zero_()
-                E.policy_step_live(boards, status, logits, values, fn.use_mask, fn.sample_actions, False, subs[1 + 2 * t],
-                                   subs[2 + 2 * t], live_ids, batch_size, lo, mode, None, None, rewards)
-                lengths[live_ids] += 1
-                scores += rewards.clamp_(min=0.0)  # the illegal-action penalty (-1) is not part of the game score
-            t += 1
+                for k in range(steps):
+                    t = t0 + k
+                    obs = E.expand_obs_gather(boards, live_ids, fn.obs_dtype)
+                    logits, values = fn.forward_logits(obs)
+                    E.policy_step_live(boards, status, logits, values, fn.use_mask, fn.sample_actions, False, subs[1 + 2 * t],
+                                       subs[2 + 2 * t], live_ids, batch_size, lo, mode, None, rm[k], rr[k])
+            # per env: steps played in this chunk = first done + 1 (or all of them), for the envs alive at its start
+            first = E.episode_lengths(rm, steps, n)
+            played = torch.where(first > 0, first, torch.full_like(first, steps))
+            lengths += torch.where(alive_before, played, torch.zeros_like(played))
+            scores += rr.clamp_(min=0.0).sum(dim=0)  # the illegal-action penalty (-1) is not part of the game score
+            t0 += steps
             done_now = int(((status & N.STATUS_DONE) != 0).sum().item())
-            if n - done_now != live_ids.shape[0]:
-                live_ids = torch.nonzero((status & N.STATUS_DONE) == 0).flatten()
             if self._all_done(done_now, n):
                 break
+        t = int(lengths.max().item()) if n else 0  # the reference's number of loop steps: the longest episode
         if self.shard is not None and self.shard[1] > 1:
             from ..dist import allreduce_max_int
 

@@ -251,6 +251,11 @@ def main():
 
     torch.cuda.set_device(local_rank)
     dev = torch.device("cuda", local_rank)
+    # stdout carries exactly ONE line, the JSON: whatever libraries print there meanwhile (NCCL's version banner does, at
+    # the first collective) goes to stderr instead -- file descriptor 1 is pointed at stderr until the line is written
+    sys.stdout.flush()
+    json_fd = os.dup(1)
+    os.dup2(2, 1)
     if world > 1:
         # keep stdout for the one JSON line: NCCL's version / debug banner goes to stderr
         os.environ.setdefault("NCCL_DEBUG_FILE", "/dev/stderr")
@@ -542,7 +547,8 @@ def main():
             "weak_scaling": other,
         }
         line.update(extras)
-        print(json.dumps(line))
+        sys.stdout.flush()
+        os.write(json_fd, (json.dumps(line) + "\n").encode())
     if world > 1:
         dist.barrier()
         dist.destroy_process_group()

@@ -50,6 +50,18 @@ def one():
         n = 1 << 18
         best, mean = timed(lambda: E.play_record(policy, subs, n, 0, n, 1), 5)
         out[f"{pname}_record_2^18"] = {"ms_min": round(best, 4), "ms_mean": round(mean, 4)}
+    # the opt-in GAE scan at the bench's size
+    from g2048 import _native as N
+
+    n_g = 1 << 26
+    r, v = torch.rand(n_g, device=dev), torch.rand(n_g, device=dev)
+    d = (torch.rand(n_g, device=dev) < 1 / 300).to(torch.uint8)
+    adv, ret = torch.empty(n_g, device=dev), torch.empty(n_g, device=dev)
+    scratch = torch.zeros(int(N.lib.g2048_gae_scan_scratch_bytes(n_g)), dtype=torch.uint8, device=dev)
+    mom = torch.zeros(6, dtype=torch.float64, device=dev)
+    best, mean = timed(lambda: N.call("g2048_gae_flat_scan", N.ptr(r), N.ptr(v), N.ptr(d), n_g, 0.99, 0.95, N.ptr(adv), N.ptr(ret),
+                                      N.ptr(scratch), N.ptr(mom), N.stream_ptr()), 5)
+    out["gae_scan_2^26"] = {"ms_min": round(best, 4), "ms_mean": round(mean, 4), "TBs": round(n_g * 17 / best / 1e9, 3)}
     print(json.dumps(out))
 
 
