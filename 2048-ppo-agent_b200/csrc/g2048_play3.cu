@@ -40,8 +40,9 @@ constexpr int PLAY3_TABLE_BYTES = 65536 * 2 + 65536;
 #endif
 #ifndef G2048_PLAY3_TAIL_REC
 // 1: tail compaction in the RECORDING form only, inlined (that form runs at C4-like sizes, 3-4 episodes per lane, where
-// the drain is a third of the launch)
-#define G2048_PLAY3_TAIL_REC 0
+// the drain is a third of the launch): 2^18 envs, random policy 1.64 -> 1.55 ms, DRUL unchanged, and the plain form's code is
+// not touched (A/B on one box, profiles/r02_ab_variants.jsonl)
+#define G2048_PLAY3_TAIL_REC 1
 #endif
 
 [[maybe_unused]] constexpr int PLAY3_TAIL_STEPS = G2048_PLAY3_TAIL_STEPS;  // steps between two compactions of the CTA's live envs in the tail
