@@ -315,93 +315,91 @@ gae_time_major_kernel(const float* __restrict__ rewards, const float* __restrict
     }
 }
 
-// The same recurrence with T split over the warps of a CTA (round 2).  One lane per env leaves 13 warps per SM at C3
-// (65 536 envs) and each of them walks 128 steps with 16 loads in flight: 0.64 of HBM.  Here a CTA is 32 envs x 4
-// warps; warp s holds steps [32 s, 32 s + 32) of a 128-step chunk in registers -- all loads of the chunk are issued at
-// once, four times the bytes in flight -- and the recurrence is handed from warp to warp through shared memory, last
-// segment first, so every env still sees the reference's exact serial fp32 order (bit-identical, like the kernel above).
-constexpr int GAE_TS_SEG = 32;    // steps per warp and chunk (registers)
-constexpr int GAE_TS_WARPS = 4;   // segments per chunk
-constexpr int GAE_TS_CHUNK = GAE_TS_SEG * GAE_TS_WARPS;
+// The same recurrence with the LOADS of a CTA's envs spread over four warps (round 2).  One lane per env leaves 13 warps
+// per SM at C3 (65 536 envs), each walking 128 steps with 16 loads in flight: 0.64 of HBM.  Here a CTA is 32 envs x 4
+// warps: all four fetch a 128-step chunk of the CTA's envs into shared memory (36 KiB: every load of the chunk is in
+// flight at once), then warp 0 runs the recurrence over it from shared memory -- the reference's exact serial fp32
+// order per env, bit-identical like the kernel above -- while warps 1-3 already fetch the chunk before it (T > 128).
+// (First attempt: the chunk in REGISTERS, 32 steps per warp, the carry handed from warp to warp.  With 64 data
+// registers per thread ptxas sank every load to just before its use: 128 serial DRAM round trips per env, 168 us for C3
+// against 34 -- ncu long_scoreboard 15 per issue, profiles/r02_gae_kernels.csv.)
+constexpr int GAE_TS_CHUNK = 128;
+constexpr int GAE_TS_WARPS = 4;
+struct GaeTsStage {
+    float r[GAE_TS_CHUNK][32];
+    float v[GAE_TS_CHUNK][32];
+    uint8_t d[GAE_TS_CHUNK][32];
+};
 
-__global__ void __launch_bounds__(32 * GAE_TS_WARPS, 4)
+__global__ void __launch_bounds__(32 * GAE_TS_WARPS)
 gae_time_major_split_kernel(const float* __restrict__ rewards, const float* __restrict__ values,
                             const uint8_t* __restrict__ meta, int64_t t_steps, int64_t n,
                             const float* __restrict__ bootstrap, float gamma, float gamma_lambda, float* __restrict__ adv,
                             float* __restrict__ ret, double* __restrict__ moments) {
-    __shared__ float s_last_v[32], s_last_gae[32];
-    __shared__ double s_red[4 * GAE_TS_WARPS];
-    const int lane = threadIdx.x & 31, seg = threadIdx.x >> 5;
+    extern __shared__ __align__(16) uint8_t ts_smem[];
+    GaeTsStage* stages = reinterpret_cast<GaeTsStage*>(ts_smem);  // one stage, or two when there is more than one chunk
+    const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
     const int64_t e = (int64_t)blockIdx.x * 32 + lane;
     const bool live = e < n;
-    if (seg == 0) {
-        s_last_v[lane] = (live && bootstrap) ? bootstrap[e] : 0.0f;
-        s_last_gae[lane] = 0.0f;
-    }
-    double m[4] = {0.0, 0.0, 0.0, 0.0};
     const int64_t n_chunks = (t_steps + GAE_TS_CHUNK - 1) / GAE_TS_CHUNK;
+
+    // rows [c * 128, ...) of my env into stage `st`, by `nl` loader warps of which I am number `lw`
+    auto load_chunk = [&](int64_t c, GaeTsStage& st, int lw, int nl) {
+        const int64_t t0 = c * GAE_TS_CHUNK;
+        const int rows = (int)min((int64_t)GAE_TS_CHUNK, t_steps - t0);
+        if (!live) return;
+#pragma unroll 8
+        for (int j = lw; j < rows; j += nl) {
+            const int64_t i = (t0 + j) * n + e;
+            st.r[j][lane] = __ldcs(&rewards[i]);
+            st.v[j][lane] = __ldcs(&values[i]);
+            st.d[j][lane] = __ldcs(&meta[i]);
+        }
+    };
+    load_chunk(n_chunks - 1, stages[(n_chunks - 1) & 1], warp, GAE_TS_WARPS);
+    __syncthreads();
+
+    float last_v = (live && bootstrap) ? bootstrap[e] : 0.0f, last_gae = 0.0f;  // warp 0's carry
+    double m[4] = {0.0, 0.0, 0.0, 0.0};
     for (int64_t c = n_chunks - 1; c >= 0; --c) {
-        // my segment of this chunk: steps t0 .. t0 + cnt - 1 (cnt may be 0 in the last, partial chunk)
-        const int64_t t0 = c * GAE_TS_CHUNK + (int64_t)seg * GAE_TS_SEG;
-        const int cnt = (int)max((int64_t)0, min((int64_t)GAE_TS_SEG, t_steps - t0));
-        float r[GAE_TS_SEG], v[GAE_TS_SEG];
-        uint32_t dbits = 0;
-        if (live) {
-#pragma unroll
-            for (int k = 0; k < GAE_TS_SEG; ++k) {
-                if (k < cnt) {
-                    const int64_t i = (t0 + k) * n + e;
-                    r[k] = __ldcs(&rewards[i]);
-                    v[k] = __ldcs(&values[i]);
-                    dbits |= (((uint32_t)__ldcs(&meta[i]) >> 6) & 1u) << k;
-                }
-            }
-        }
-        // the recurrence, last segment first
-        for (int s = GAE_TS_WARPS - 1; s >= 0; --s) {
-            __syncthreads();  // the carry of segment s + 1 (or of the chunk after this one, or the bootstrap) is in place
-            if (s == seg && live && cnt > 0) {
-                float last_v = s_last_v[lane], last_gae = s_last_gae[lane];
-#pragma unroll
-                for (int k = GAE_TS_SEG - 1; k >= 0; --k) {
-                    if (k < cnt) {
-                        if ((dbits >> k) & 1u) {
-                            last_v = 0.0f;
-                            last_gae = 0.0f;
-                        }
-                        const float delta = (r[k] + gamma * last_v) - v[k];
-                        last_gae = delta + gamma_lambda * last_gae;
-                        const float rt = last_gae + v[k];
-                        const int64_t i = (t0 + k) * n + e;
-                        __stcs(&adv[i], last_gae);
-                        __stcs(&ret[i], rt);
-                        last_v = v[k];
-                        const double da = (double)last_gae, dr = (double)rt;
-                        m[0] += da;
-                        m[1] = __fma_rn(da, da, m[1]);
-                        m[2] += dr;
-                        m[3] = __fma_rn(dr, dr, m[3]);
+        if (warp == 0) {
+            if (live) {
+                const GaeTsStage& st = stages[c & 1];
+                const int64_t t0 = c * GAE_TS_CHUNK;
+                const int rows = (int)min((int64_t)GAE_TS_CHUNK, t_steps - t0);
+                for (int j = rows - 1; j >= 0; --j) {
+                    const float r = st.r[j][lane], v = st.v[j][lane];
+                    if (st.d[j][lane] & 0x40u) {
+                        last_v = 0.0f;
+                        last_gae = 0.0f;
                     }
+                    const float delta = (r + gamma * last_v) - v;
+                    last_gae = delta + gamma_lambda * last_gae;
+                    const float rt = last_gae + v;
+                    const int64_t i = (t0 + j) * n + e;
+                    __stcs(&adv[i], last_gae);
+                    __stcs(&ret[i], rt);
+                    last_v = v;
+                    const double da = (double)last_gae, dr = (double)rt;
+                    m[0] += da;
+                    m[1] = __fma_rn(da, da, m[1]);
+                    m[2] += dr;
+                    m[3] = __fma_rn(dr, dr, m[3]);
                 }
-                s_last_v[lane] = last_v;
-                s_last_gae[lane] = last_gae;
             }
+        } else if (c > 0) {
+            load_chunk(c - 1, stages[(c - 1) & 1], warp - 1, GAE_TS_WARPS - 1);  // the chunk before this one, meanwhile
         }
+        __syncthreads();
     }
-    if (moments) {
+    if (moments && warp == 0) {
 #pragma unroll
         for (int k = 0; k < 4; ++k) {
             double x = m[k];
             for (int off = 16; off > 0; off >>= 1) x += __shfl_down_sync(0xFFFFFFFFu, x, off);
-            if (lane == 0) s_red[k * GAE_TS_WARPS + seg] = x;
+            if (lane == 0) atomicAdd(&moments[1 + k], x);
         }
-        __syncthreads();
-        if (threadIdx.x < 4) {
-            double t = 0.0;
-            for (int w = 0; w < GAE_TS_WARPS; ++w) t += s_red[threadIdx.x * GAE_TS_WARPS + w];
-            atomicAdd(&moments[1 + threadIdx.x], t);
-        }
-        if (threadIdx.x == 4) {
+        if (lane == 0) {
             const int64_t envs = min((int64_t)32, n - (int64_t)blockIdx.x * 32);
             atomicAdd(&moments[0], (double)(envs * t_steps));
         }
@@ -476,12 +474,22 @@ extern "C" int g2048_gae_time_major(const float* d_rewards, const float* d_value
     // T split over the warps of a CTA once there is more than one 32-step segment to hand around (see the kernel);
     // G2048_GAE_TM_SPLIT=0 / 1 forces one form (A/B timing)
     static const int force = [] { const char* e = getenv("G2048_GAE_TM_SPLIT"); return e ? atoi(e) : -1; }();
-    const bool split = force >= 0 ? force != 0 : t_steps > GAE_TS_SEG;
-    if (split)
-        gae_time_major_split_kernel<<<blocks_for(n, 32), 32 * GAE_TS_WARPS, 0, (cudaStream_t)stream>>>(
+    const bool split = force >= 0 ? force != 0 : t_steps >= 32;
+    if (split) {
+        const int smem = (int)sizeof(GaeTsStage) * (t_steps > GAE_TS_CHUNK ? 2 : 1);
+        static bool configured_on[64] = {false};
+        bool* configured = device_once_flag(configured_on);
+        if (!configured) return fail_arg("no CUDA device");
+        if (!*configured) {
+            const int rc = check_cuda(cudaFuncSetAttribute(gae_time_major_split_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize,
+                                                           2 * (int)sizeof(GaeTsStage)), "gae_time_major: shared memory attribute");
+            if (rc) return rc;
+            *configured = true;
+        }
+        gae_time_major_split_kernel<<<blocks_for(n, 32), 32 * GAE_TS_WARPS, smem, (cudaStream_t)stream>>>(
             d_rewards, d_values, d_rec_meta, t_steps, n, d_bootstrap, (float)gamma, (float)(gamma * lambda_gae), d_adv, d_ret,
             d_moments);
-    else
+    } else
         gae_time_major_kernel<<<blocks_for(n, GAE_TM_THREADS), GAE_TM_THREADS, 0, (cudaStream_t)stream>>>(
             d_rewards, d_values, d_rec_meta, t_steps, n, d_bootstrap, (float)gamma, (float)(gamma * lambda_gae), d_adv,
             d_ret, d_moments);
