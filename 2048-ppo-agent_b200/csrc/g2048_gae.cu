@@ -320,6 +320,9 @@ gae_time_major_kernel(const float* __restrict__ rewards, const float* __restrict
 // warps: all four fetch a 128-step chunk of the CTA's envs into shared memory (36 KiB: every load of the chunk is in
 // flight at once), then warp 0 runs the recurrence over it from shared memory -- the reference's exact serial fp32
 // order per env, bit-identical like the kernel above -- while warps 1-3 already fetch the chunk before it (T > 128).
+// NOT the default: it measured slower than one lane per env (C3: 46 vs 34 us; 4 x C3: 150 vs 113 us) -- the recurrence
+// of 32 envs on ONE warp per CTA, a shared-memory load and two global stores inside every dependent step, outweighs the
+// wider load front.  Kept behind G2048_GAE_TM_SPLIT=1 for the record of the experiment.
 // (First attempt: the chunk in REGISTERS, 32 steps per warp, the carry handed from warp to warp.  With 64 data
 // registers per thread ptxas sank every load to just before its use: 128 serial DRAM round trips per env, 168 us for C3
 // against 34 -- ncu long_scoreboard 15 per issue, profiles/r02_gae_kernels.csv.)
@@ -471,10 +474,9 @@ extern "C" int g2048_gae_time_major(const float* d_rewards, const float* d_value
     G2048_REQUIRE(t_steps >= 0 && n >= 0, "gae_time_major: shape");
     if (t_steps == 0 || n == 0) return G2048_OK;
     G2048_REQUIRE(d_rewards && d_values && d_rec_meta && d_adv && d_ret, "gae_time_major: pointers");
-    // T split over the warps of a CTA once there is more than one 32-step segment to hand around (see the kernel);
-    // G2048_GAE_TM_SPLIT=0 / 1 forces one form (A/B timing)
-    static const int force = [] { const char* e = getenv("G2048_GAE_TM_SPLIT"); return e ? atoi(e) : -1; }();
-    const bool split = force >= 0 ? force != 0 : t_steps >= 32;
+    // G2048_GAE_TM_SPLIT=1 selects the form whose loads are spread over four warps (see the kernel): measured SLOWER
+    // than one lane per env (C3 46 vs 34 us, 4 x C3 150 vs 113 us), so it is off unless asked for
+    static const bool split = [] { const char* e = getenv("G2048_GAE_TM_SPLIT"); return e && atoi(e) != 0; }();
     if (split) {
         const int smem = (int)sizeof(GaeTsStage) * (t_steps > GAE_TS_CHUNK ? 2 : 1);
         static bool configured_on[64] = {false};

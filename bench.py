@@ -749,6 +749,34 @@ def secondary_measurements(E, N, torch, dev, flush_buf) -> dict:
 
     t = timed(ppo_rollout, reps=3)
     t_two = timed(ppo_rollout_two_launches, reps=3)
+    # the same loop writing bfloat16 observations (one-hot values are exact in bf16; what TorchActionFunction(obs_dtype=
+    # torch.bfloat16) feeds a network that runs under bf16 autocast anyway): half the bytes per step
+    obs16 = torch.empty((b, 16, 31), dtype=torch.bfloat16, device=dev)
+
+    def ppo_rollout_bf16():
+        N.call("g2048_expand_obs", N.ptr(pb), b, N.OBS_BF16, N.ptr(obs16), 0, 0, N.stream_ptr())
+        for k in range(t_steps):
+            E.policy_step_obs(pb, ps, logits, values, True, True, True, subs[1 + 2 * k:], None, b, 0, mode, obs16,
+                              rec_b[k], rec_m[k], rec_r[k], rec_l[k], rec_v[k])
+        N.call("g2048_gae_time_major", N.ptr(rec_r), N.ptr(rec_v), N.ptr(rec_m), t_steps, b, None, 0.99, 0.95,
+               N.ptr(adv2), N.ptr(ret2), N.ptr(mom), N.stream_ptr())
+
+    t_bf16 = timed(ppo_rollout_bf16, reps=3)
+    t_bf16_graph = None
+    try:
+        side16 = torch.cuda.Stream()
+        side16.wait_stream(torch.cuda.current_stream())
+        with torch.cuda.stream(side16):
+            ppo_rollout_bf16()
+        torch.cuda.current_stream().wait_stream(side16)
+        torch.cuda.synchronize()
+        graph16 = torch.cuda.CUDAGraph()
+        with torch.cuda.graph(graph16):
+            ppo_rollout_bf16()
+        t_bf16_graph = timed(graph16.replay, reps=3)
+        del graph16
+    except Exception as exc:  # noqa: BLE001
+        t_bf16_graph = f"unavailable: {exc!r}"
 
     # the same 257 launches replayed as ONE CUDA graph: what the kernels cost once the Python / ctypes launch overhead
     # (two launches per step from the interpreter) is out of the way -- how FixedHorizonRunner(cuda_graph=True) runs them
@@ -809,6 +837,10 @@ def secondary_measurements(E, N, torch, dev, flush_buf) -> dict:
         "env_steps_per_sec": t_steps * b / t, "ms_per_rollout": t * 1e3,
         "per_step_us": t * 1e6 / t_steps, "launches_per_rollout": t_steps + 2,
         "per_step_us_two_launches_per_step": t_two * 1e6 / t_steps,
+        "bf16_observations": {"per_step_us": t_bf16 * 1e6 / t_steps,
+                              "per_step_us_graph_replay": (t_bf16_graph * 1e6 / t_steps if isinstance(t_bf16_graph, float) else t_bf16_graph),
+                              "hbm_floor_us_per_step": (b * (992 + 21 + 20 + 18)) / measured_hbm_peak()[0] / 1e3,
+                              "note": "the same fused step writing bfloat16 observations (exact for one-hot values): half the bytes"},
         "hbm_floor_us_per_step": (b * (1984 + 21 + 20 + 18)) / measured_hbm_peak()[0] / 1e3,
         "graph_replay": ({"ms_per_rollout": t_graph * 1e3, "per_step_us": t_graph * 1e6 / t_steps,
                           "env_steps_per_sec": t_steps * b / t_graph,
