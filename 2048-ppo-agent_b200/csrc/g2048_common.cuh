@@ -45,6 +45,19 @@ inline bool* device_once_flag(bool (&flags)[64]) {
     return &flags[dev];
 }
 
+// Race check by perturbation (compute-sanitizer's racecheck only sees shared memory; the protocols worth worrying about
+// here go through GLOBAL memory: tile look-back flags, work queues, the step ticket).  A build with -DG2048_RACE_JITTER
+// (make jitter -> tests/legacy/libg2048_jitter.so) delays threads by a pseudo-random 0.2 - 1.2 us at every such
+// hand-over, one call in eight; tests/test_race_jitter_gpu.py requires bit-identical results from it.
+#ifdef __CUDACC__
+__device__ __forceinline__ void race_jitter() {
+#ifdef G2048_RACE_JITTER
+    const unsigned c = (unsigned)clock64() * 2654435761u + threadIdx.x * 40503u + blockIdx.x * 977u;
+    if (((c >> 9) & 7u) == 0u) __nanosleep(200u + (c & 1023u));
+#endif
+}
+#endif
+
 inline unsigned blocks_for(int64_t n, int threads) { return (unsigned)((n + threads - 1) / threads); }
 
 }  // namespace g2048

@@ -86,7 +86,10 @@ gae_flat3_kernel(const float* __restrict__ rewards, const float* __restrict__ va
     const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
 
     GAE3_STAMP(0);
-    if (tid == 0) s.ticket = atomicAdd(&scratch->ticket, 1u);
+    if (tid == 0) {
+        race_jitter();
+        s.ticket = atomicAdd(&scratch->ticket, 1u);
+    }
     __syncthreads();
     const int64_t tile = n_tiles - 1 - (int64_t)s.ticket;  // tiles are taken from the END of the buffer
     const int64_t lo = tile * GAE3_TILE;
@@ -120,6 +123,7 @@ gae_flat3_kernel(const float* __restrict__ rewards, const float* __restrict__ va
 #ifndef G2048_GAE3_SKIP_SIDE_WALKS  // timing experiment only (tools/probes/probe_gae3.cu)
             gae_walk(s.g, gae3_locate(s, 0), -1, 0.0f, gamma_lambda);
 #endif
+            race_jitter();
             heads[tile] = s.g[0];
             __threadfence();
             flags[tile] = 1u;
@@ -132,6 +136,7 @@ gae_flat3_kernel(const float* __restrict__ rewards, const float* __restrict__ va
             if (first_excl < len - 1) {
                 float carry = 0.0f;
                 if (lo + len < n) {
+                    race_jitter();
                     while (flags[tile + 1] == 0u) __nanosleep(100);
                     __threadfence();
                     carry = heads[tile + 1];
@@ -143,7 +148,8 @@ gae_flat3_kernel(const float* __restrict__ rewards, const float* __restrict__ va
                 GAE3_STAMP_ANY(10);  // tail walked
             }
             if (n_done == 0) {
-                heads[tile] = s.g[0];
+                race_jitter();
+            heads[tile] = s.g[0];
                 __threadfence();
                 flags[tile] = 1u;
             }

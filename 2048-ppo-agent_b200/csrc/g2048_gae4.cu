@@ -109,8 +109,10 @@ __device__ __forceinline__ void g4_walk_tile(G4Stage& st, int64_t tile, int64_t 
 #ifndef G4_SKIP_WALKS  // timing experiment only (tools/probes/probe_gae4.cu)
                 gae_walk(st.g, gae_locate(st.ballot, st.pref, G4_BLOCKS, 0), -1, 0.0f, gamma_lambda);
 #endif
+                race_jitter();
                 heads[tile] = st.g[0];
                 __threadfence();
+                race_jitter();
                 flags[tile] = 1u;
             }
             // the steps after the tile's last done belong to an episode that ends in a later tile
@@ -119,8 +121,10 @@ __device__ __forceinline__ void g4_walk_tile(G4Stage& st, int64_t tile, int64_t 
                 if (first_excl < len - 1) {
                     float carry = 0.0f;
                     if (lo + len < n) {
+                        race_jitter();
                         while (flags[tile + 1] == 0u) __nanosleep(100);
                         __threadfence();
+                        race_jitter();
                         carry = heads[tile + 1];
                     }
 #ifndef G4_SKIP_WALKS
@@ -130,8 +134,10 @@ __device__ __forceinline__ void g4_walk_tile(G4Stage& st, int64_t tile, int64_t 
 #endif
                 }
                 if (n_done == 0) {
+                    race_jitter();
                     heads[tile] = st.g[0];
                     __threadfence();
+                    race_jitter();
                     flags[tile] = 1u;
                 }
             }
@@ -164,6 +170,7 @@ gae_flat4_kernel(const float* __restrict__ rewards, const float* __restrict__ va
     const bool streamer = warp < G4_STREAM_WARPS;
 
     auto take_ticket = [&]() {  // tiles are taken from the END of the buffer; -1 when none is left
+        race_jitter();
         const unsigned int t = atomicAdd(&scratch->ticket, 1u);
         s.next_tile = (int64_t)t < n_tiles ? (int)(n_tiles - 1 - (int64_t)t) : -1;
     };

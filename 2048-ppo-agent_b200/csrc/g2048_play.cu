@@ -53,6 +53,7 @@ play2_kernel(const uint2* __restrict__ subs, int64_t n_subs, uint32_t batch_glob
             if (!exhausted) {
                 const int cnt = __popc(want);
                 unsigned long long base = 0;
+                race_jitter();
                 if (lane == 0) base = atomicAdd(work, (unsigned long long)cnt);
                 base = __shfl_sync(0xFFFFFFFFu, base, 0);
                 if (base + (unsigned long long)cnt >= (unsigned long long)n) exhausted = true;

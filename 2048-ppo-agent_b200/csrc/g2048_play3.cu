@@ -307,6 +307,7 @@ __device__ G2048_TAIL_INLINE void play3_tail(Play3Lane& lane_state, const Play3C
             if (lane == 0) base = atomicAdd(cnt, (unsigned)__popc(livemask));
             base = __shfl_sync(0xFFFFFFFFu, base, 0);
         }
+        race_jitter();
         if (L.phase != PHASE_NONE) {
             const unsigned at = base + (unsigned)__popc(livemask & ((1u << lane) - 1u));
             s_pool[at] = TailEntry{L.board, L.slot, L.e, L.t, L.fours, L.phase | (L.seen15 ? 4u : 0u)};
@@ -315,6 +316,7 @@ __device__ G2048_TAIL_INLINE void play3_tail(Play3Lane& lane_state, const Play3C
         const unsigned total = *(volatile unsigned*)cnt;
         if (threadIdx.x == 0) s_tail_cnt[(round + 1u) & 1u] = 0u;  // next round's counter: untouched until after the barrier below
         if (total == 0u) break;  // uniform over the CTA
+        race_jitter();
         if (threadIdx.x < total) {
             const TailEntry en = s_pool[threadIdx.x];
             L.board = en.board;
@@ -401,6 +403,7 @@ play3_kernel(const uint2* __restrict__ subs, int64_t n_subs, uint32_t batch_glob
             if (!exhausted && want) {
                 const int cnt = __popc(want);
                 unsigned long long base = 0;
+                race_jitter();
                 if (lane == 0) base = atomicAdd(work, (unsigned long long)cnt);
                 base = __shfl_sync(0xFFFFFFFFu, base, 0);
                 if (base + (unsigned long long)cnt >= (unsigned long long)n) exhausted = true;

@@ -488,6 +488,7 @@ policy_step_obs_kernel(const PolicyStepObsArgs a, T* __restrict__ obs) {
     if (a.step_index && a.advance_step) {  // every CTA read t at its start; the last one to get here moves it on
         __syncthreads();
         if (threadIdx.x == 0) {
+            race_jitter();
             __threadfence();
             if (atomicAdd(&g_step_ticket, 1u) == gridDim.x - 1u) {
                 g_step_ticket = 0u;
