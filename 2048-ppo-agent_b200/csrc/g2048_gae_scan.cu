@@ -193,14 +193,22 @@ gae_scan_kernel(const float* __restrict__ rewards, const float* __restrict__ val
         after.b = __shfl_down_sync(0xFFFFFFFFu, incl.b, 1);
         if (lane == 31) after = Affine{1.0f, 0.0f};
         __syncthreads();  // the one barrier of a tile (also: everybody has read this tile's stage)
-        // ... the warps after mine, and the whole tile (every thread composes the 8 warp aggregates itself: no second barrier)
-        Affine later{1.0f, 0.0f}, whole{1.0f, 0.0f};
+        // ... the warps after mine, and the whole tile: lane w of every warp takes warp w's aggregate and the (at most 32)
+        // aggregates are suffix-scanned with shuffles -- no second barrier, and a fifth of the instructions of every
+        // thread composing all of them itself
+        Affine agg = (lane < SCAN_WARPS) ? s_warp[it & 1u][lane] : Affine{1.0f, 0.0f};
 #pragma unroll
-        for (int w = SCAN_WARPS - 1; w >= 0; --w) {
-            const Affine m = s_warp[it & 1u][w];
-            whole = compose(m, whole);
-            if (w > warp) later = compose(m, later);
+        for (int off = 1; off < SCAN_WARPS; off <<= 1) {
+            Affine other;
+            other.a = __shfl_down_sync(0xFFFFFFFFu, agg.a, off);
+            other.b = __shfl_down_sync(0xFFFFFFFFu, agg.b, off);
+            if (lane + off < SCAN_WARPS) agg = compose(agg, other);
         }
+        Affine whole, later;  // lane 0 holds warps 0.., lane w + 1 the warps after warp w (identity past the last warp)
+        whole.a = __shfl_sync(0xFFFFFFFFu, agg.a, 0);
+        whole.b = __shfl_sync(0xFFFFFFFFu, agg.b, 0);
+        later.a = __shfl_sync(0xFFFFFFFFu, agg.a, warp + 1);
+        later.b = __shfl_sync(0xFFFFFFFFu, agg.b, warp + 1);
         // everything between my last step and the end of the RANGE, as a map of x
         const Affine entering = compose(compose(after, later), carry);
         carry = compose(whole, carry);  // ... and what enters the next (earlier) tile

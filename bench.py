@@ -842,6 +842,8 @@ def secondary_measurements(E, N, torch, dev, flush_buf) -> dict:
                               "hbm_floor_us_per_step": (b * (992 + 21 + 20 + 18)) / measured_hbm_peak()[0] / 1e3,
                               "note": "the same fused step writing bfloat16 observations (exact for one-hot values): half the bytes"},
         "hbm_floor_us_per_step": (b * (1984 + 21 + 20 + 18)) / measured_hbm_peak()[0] / 1e3,
+        "algorithmic_bytes_per_step": b * (1984 + 21 + 20 + 18),
+        "traffic_per_step": traffic.get("c3: policy_step_obs_kernel<float>", {}).get("traffic"),
         "graph_replay": ({"ms_per_rollout": t_graph * 1e3, "per_step_us": t_graph * 1e6 / t_steps,
                           "env_steps_per_sec": t_steps * b / t_graph,
                           "note": "the same launches captured once and replayed as a CUDA graph (no interpreter between them)"}
@@ -932,6 +934,10 @@ def c4_iteration(E, N, torch, dev, hbm_peak) -> dict:
     t_cmp = dev_time(lambda: E.play_record_compact(rec, offsets, steps))
     t_plain = dev_time(lambda: E.play(E.POLICY_RANDOM, subs, n_envs, 0, n_envs, mode, per_env=True))
     cmp_bytes = steps * (9 + 21)
+    try:  # dram bytes of one launch from the committed ncu capture (tools/profile_hbm.py)
+        captured = json.loads((ROOT / "profiles" / "hbm_traffic.json").read_text())["rows"]
+    except Exception:  # noqa: BLE001 -- evidence, not a dependency
+        captured = {}
     report["rollout_and_store"] = {
         "seconds": t_flat + t_store, "env_steps": steps, "env_steps_per_sec": steps / (t_flat + t_store),
         "api": "BatchRunner.run_flat_batch + RolloutBuffer.store_flat (wall clock, two host synchronisations)",
@@ -940,6 +946,7 @@ def c4_iteration(E, N, torch, dev, hbm_peak) -> dict:
         "compact_kernel_ms": t_cmp * 1e3,
         "compact_roofline": {"bound": "hbm", "achieved": cmp_bytes / t_cmp / 1e9, "peak": hbm_peak, "unit": "GB/s",
                              "frac": cmp_bytes / t_cmp / 1e9 / hbm_peak, "algorithmic_bytes": cmp_bytes,
+                             "traffic": captured.get("c4: play_record_compact_kernel", {}).get("traffic"),
                              "note": "9 B read (board + meta) + 21 B written (board, meta, reward, log-prob, value) per kept step"},
         "arena_bytes": int(rec["arena_boards"].numel() * 9),
     }
