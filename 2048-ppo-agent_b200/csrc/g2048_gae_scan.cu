@@ -286,23 +286,24 @@ gae_scan_kernel(const float* __restrict__ rewards, const float* __restrict__ val
     if (threadIdx.x == 0) ranges[blockIdx.x] = ScanRange{carry.a, carry.b, s_pending, 0u};
 }
 
-// One warp per range: x = the gae of the next range's first step (chained through the range aggregates until one does
+// One CTA per range: x = the gae of the next range's first step (chained through the range aggregates until one does
 // not depend on its own successor), then gae += coefficient * x for the `pending` steps at the range's end -- their
 // coefficient is (gamma*lambda)^(distance to the range's end + 1): a step with a non-zero coefficient has no `done`
 // between itself and the end -- and their share of the moment sums.
-__global__ void __launch_bounds__(32)
+constexpr int SCAN_FIX_THREADS = 256;
+__global__ void __launch_bounds__(SCAN_FIX_THREADS)
 gae_scan_fix_kernel(const ScanRange* __restrict__ ranges, int n_ranges, int64_t n, int64_t tiles_per_range, float gamma_lambda,
                     float* __restrict__ adv, float* __restrict__ ret, double* __restrict__ moments) {
-    const int c = blockIdx.x, lane = threadIdx.x;
+    const int c = blockIdx.x, lane = threadIdx.x & 31;
     const unsigned pending = ranges[c].pending;
-    if (lane == 0 && c == 0 && moments) atomicAdd(&moments[0], (double)n);
+    if (threadIdx.x == 0 && c == 0 && moments) atomicAdd(&moments[0], (double)n);
     if (pending == 0u) return;
     Affine acc{1.0f, 0.0f};
     for (int j = c + 1; j < n_ranges && acc.a != 0.0f; ++j) acc = compose(acc, Affine{ranges[j].a, ranges[j].b});
     const float x = acc.b;  // past the last range the gae is 0
     const int64_t end = min(n, (int64_t)(c + 1) * tiles_per_range * SCAN_TILE);  // one past the range's last step
     double acc4[4] = {0.0, 0.0, 0.0, 0.0};
-    for (unsigned i = (unsigned)lane; i < pending; i += 32u) {
+    for (unsigned i = threadIdx.x; i < pending; i += SCAN_FIX_THREADS) {  // a few hundred steps: one or two per thread
         const int64_t t = end - 1 - (int64_t)i;
         const float coef = powf(gamma_lambda, (float)(i + 1u));
         const float g = adv[t] + coef * x, q = ret[t] + coef * x;
@@ -315,12 +316,19 @@ gae_scan_fix_kernel(const ScanRange* __restrict__ ranges, int n_ranges, int64_t 
         acc4[2] += (double)q;
         acc4[3] += (double)q * (double)q;
     }
-    if (moments) {
+    if (moments) {  // (every thread of the CTA gets here: `pending` is uniform)
+        __shared__ double s_red[4 * (SCAN_FIX_THREADS / 32)];
 #pragma unroll
         for (int k = 0; k < 4; ++k) {
             double sum = acc4[k];
             for (int off = 16; off > 0; off >>= 1) sum += __shfl_down_sync(0xFFFFFFFFu, sum, off);
-            if (lane == 0) atomicAdd(&moments[1 + k], sum);
+            if (lane == 0) s_red[k * (SCAN_FIX_THREADS / 32) + (threadIdx.x >> 5)] = sum;
+        }
+        __syncthreads();
+        if (threadIdx.x < 4) {
+            double sum = 0.0;
+            for (int w = 0; w < SCAN_FIX_THREADS / 32; ++w) sum += s_red[threadIdx.x * (SCAN_FIX_THREADS / 32) + w];
+            atomicAdd(&moments[1 + threadIdx.x], sum);
         }
     }
 }
@@ -368,7 +376,7 @@ extern "C" int g2048_gae_flat_scan(const float* d_rewards, const float* d_values
         gae_scan_kernel<false><<<n_ranges, SCAN_THREADS, 0, st>>>(d_rewards, d_values, d_dones, n, n_tiles, tiles_per_range, g, gl,
                                                                   d_adv, d_ret, (ScanRange*)d_scan_state, d_moments);
     G2048_CHECK_LAUNCH("gae_flat_scan");
-    gae_scan_fix_kernel<<<n_ranges, 32, 0, st>>>((const ScanRange*)d_scan_state, n_ranges, n, tiles_per_range, gl, d_adv, d_ret,
+    gae_scan_fix_kernel<<<n_ranges, SCAN_FIX_THREADS, 0, st>>>((const ScanRange*)d_scan_state, n_ranges, n, tiles_per_range, gl, d_adv, d_ret,
                                                  d_moments);
     G2048_CHECK_LAUNCH("gae_flat_scan: fix-up");
     return G2048_OK;

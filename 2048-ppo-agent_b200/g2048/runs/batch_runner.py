@@ -249,7 +249,7 @@ class BatchRunner:
         if n:
             self._mean_steps[policy] = max(16, -(-local["env_steps"] // n))
         stats = self._reduce_stats(rec["stats"])
-        st = E.play_stats_dict(stats)
+        st = local if stats is rec["stats"] else E.play_stats_dict(stats)  # one read-back per batch unless it is sharded
         self.chain.consume(1 + 2 * st["longest"])
         offsets = E.exclusive_scan(rec["lengths"])
         total = local["env_steps"]
