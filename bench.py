@@ -879,6 +879,24 @@ def secondary_measurements(E, N, torch, dev, flush_buf) -> dict:
     c1 = {"config": "C1: BatchRunner(0, act_randomly).run_actions_batch(1024), reference-format numpy outputs",
           "seconds": dt, "loop_steps": int(out[0].shape[1]), "env_steps": int(first_done.sum()),
           "env_steps_per_sec": float(first_done.sum() / dt), "output_bytes": int(sum(a.nbytes for a in out if a is not None))}
+    # the other reference-API calls at C1's size: run_rollout_batch (list of States, built from the records of a chunked
+    # run) and run_actions_max_tile (persistent play kernel + replay of the longest envs for the reference's quirk)
+    from g2048.runs.run_actions_max_tile import run_actions_max_tile
+
+    def wall(fn):
+        fn()
+        torch.cuda.synchronize()
+        t0 = time.perf_counter()
+        res = fn()
+        torch.cuda.synchronize()
+        return res, time.perf_counter() - t0
+
+    states, t_states = wall(lambda: g2048.BatchRunner(init_seed=0, act_fn=g2048.act_randomly).run_rollout_batch(1024))
+    stats_q, t_mt = wall(lambda: run_actions_max_tile(0, 1024, 4096, g2048.act_randomly))
+    _, t_mt_exact = wall(lambda: run_actions_max_tile(0, 1024, 4096, g2048.act_randomly, exact_reference_quirk=False))
+    c1["run_rollout_batch_1024"] = {"seconds": t_states, "states": len(states), "env_steps_per_sec": float(first_done.sum() / t_states)}
+    c1["run_actions_max_tile_4096_envs_in_batches_of_1024"] = {
+        "seconds": t_mt, "seconds_without_the_reference_quirk": t_mt_exact, "mean_max_tile": float(stats_q.mean[0])}
     return {"roofline_hbm": rows, "hbm_peak_source": peak_src, "ppo_rollout": ppo, "c2_drul": c2, "c1_reference_api": c1}
 
 
