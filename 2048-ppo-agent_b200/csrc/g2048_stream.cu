@@ -4,6 +4,8 @@
 // for the per-thread 16-byte-chunk kernel, which stays available as g2048_expand_obs_v1.
 #include <cuda_bf16.h>
 
+#include <cstdlib>
+
 #include "g2048_common.cuh"
 #include "g2048_env.cuh"
 #include "g2048_tma.cuh"
@@ -597,6 +599,113 @@ pack_samples_kernel(const u64* __restrict__ boards, const uint8_t* __restrict__ 
 
 }  // namespace g2048
 
+namespace g2048 {
+
+// Minibatch gather from sample records, tile form: a warp owns 32 CONSECUTIVE samples.  Lane l fetches the index and
+// then the whole 32-byte record of sample l (all 32 records of the tile are in flight at once, and the next tile's
+// indices and records are requested before this tile's images are written), writes its sample's scalars -- the warp's
+// stores are coalesced -- and the 32 boards go from lane to lane by shuffles into the image ring, as in
+// policy_step_obs_kernel.  Every record is touched ONCE.  (The round-robin form above, reading records: boards four
+// per round, scalars in a phase of their own at the end -- by then 1 GB of observations has passed through L2 and
+// every record comes from DRAM a second time, as a 128-byte line: ncu 126 MB read for 2^19 samples.)
+template <typename T>
+__global__ void __launch_bounds__(OBS_THREADS)
+gather_samples_tile_kernel(const int64_t* __restrict__ indices, int64_t m, const uint4* __restrict__ records,
+                           T* __restrict__ obs, const GatherScalars g) {
+    constexpr int G = OBS_IMAGE_BYTES / (496 * (int)sizeof(T));  // boards per image
+    constexpr int CELLS = 16 * G;
+    constexpr int PER_LANE = (CELLS + 31) / 32;
+    constexpr int IMAGES = 32 / G;  // images per 32-sample tile
+    extern __shared__ __align__(128) uint8_t s_img_raw[];  // [OBS_WARPS][OBS_NBUF][OBS_IMAGE_BYTES]
+
+    const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
+    uint8_t* ring = s_img_raw + (size_t)warp * OBS_NBUF * OBS_IMAGE_BYTES;
+    for (int i = lane; i < OBS_NBUF * OBS_IMAGE_BYTES / 16; i += 32)
+        reinterpret_cast<uint4*>(ring)[i] = make_uint4(0u, 0u, 0u, 0u);
+    __syncwarp();
+    int old_pos[OBS_NBUF][PER_LANE];
+#pragma unroll
+    for (int j = 0; j < OBS_NBUF; ++j)
+#pragma unroll
+        for (int p = 0; p < PER_LANE; ++p) old_pos[j][p] = -1;
+
+    const int64_t n_tiles = (m + 31) / 32;
+    const int64_t stride = (int64_t)OBS_WARPS * gridDim.x;
+    // warp w of CTA b takes tiles w * gridDim + b, + OBS_WARPS * gridDim, ...: every CTA (hence every SM) gets its share
+    int64_t tile = (int64_t)warp * gridDim.x + blockIdx.x;
+    auto fetch = [&](int64_t t, uint4& h0, uint4& h1) {
+        const int64_t i = t * 32 + lane;
+        if (t < n_tiles && i < m) {
+            const int64_t s = __ldg(&indices[i]);
+            h0 = __ldg(&records[2 * s]);
+            h1 = __ldg(&records[2 * s + 1]);
+        } else {
+            h0 = make_uint4(0u, 0u, 0u, 0u);
+            h1 = h0;
+        }
+    };
+    uint4 h0, h1;
+    fetch(tile, h0, h1);
+    for (; tile < n_tiles; tile += stride) {
+        uint4 n0, n1;
+        fetch(tile + stride, n0, n1);  // the next tile's records, in flight while this tile's images are written
+        const int64_t i = tile * 32 + lane;
+        if (i < m) {  // my sample's scalars (G2048SampleRecord): coalesced over the warp
+            const uint32_t mt = h0.z;
+            if (g.o_actions) g.o_actions[i] = (int64_t)(mt & 3u);
+            if (g.o_masks) g.o_masks[i] = make_uchar4((mt >> 2) & 1u, (mt >> 3) & 1u, (mt >> 4) & 1u, (mt >> 5) & 1u);
+            if (g.o_log_probs) g.o_log_probs[i] = __uint_as_float(h1.x);
+            if (g.o_values) g.o_values[i] = __uint_as_float(h1.y);
+            if (g.o_adv) g.o_adv[i] = __uint_as_float(h1.z);
+            if (g.o_ret) g.o_ret[i] = __uint_as_float(h1.w);
+            if (g.o_boards) g.o_boards[i] = ((unsigned long long)h0.y << 32) | (unsigned long long)h0.x;
+        }
+        const u64 nb = ((u64)h0.y << 32) | (u64)h0.x;
+        const int in_tile = (int)min((int64_t)32, m - tile * 32);
+#pragma unroll
+        for (int j0 = 0; j0 < IMAGES; j0 += OBS_NBUF) {
+#pragma unroll
+            for (int jj = 0; jj < OBS_NBUF; ++jj) {
+                const int j = j0 + jj;                 // image of the tile; buffer jj of the ring (IMAGES % OBS_NBUF == 0)
+                const int in_image = min(G, in_tile - j * G);  // warp-uniform
+                T* buf = reinterpret_cast<T*>(ring + jj * OBS_IMAGE_BYTES);
+                if (in_image > 0) {
+                    if (lane == 0) bulk_wait_read<OBS_NBUF - 1>();  // the store issued OBS_NBUF images ago is done with buf
+                    __syncwarp();
+                }
+#pragma unroll
+                for (int p = 0; p < PER_LANE; ++p) {
+                    const int c = lane + 32 * p;  // cell index inside the image
+                    const int gg = c >> 4, cell = c & 15;
+                    const u64 b = __shfl_sync(0xFFFFFFFFu, nb, (j * G + gg) & 31);  // every lane takes part
+                    if (in_image > 0 && c < CELLS) {
+                        if (old_pos[jj][p] >= 0) buf[old_pos[jj][p]] = ObsOne<T>::zero();
+                        int pos = -1;
+                        if (gg < in_image) {
+                            pos = gg * 496 + 31 * cell + (int)((b >> (4 * cell)) & 15ull);
+                            buf[pos] = ObsOne<T>::one();
+                        }
+                        old_pos[jj][p] = pos;
+                    }
+                }
+                if (in_image > 0) {
+                    fence_proxy_async();  // generic-proxy writes above -> visible to the bulk copy
+                    __syncwarp();
+                    if (lane == 0) {
+                        bulk_store(obs + (tile * 32 + (int64_t)j * G) * 496, buf, (uint32_t)(in_image * 496 * (int)sizeof(T)));
+                        bulk_commit();
+                    }
+                }
+            }
+        }
+        h0 = n0;
+        h1 = n1;
+    }
+    if (lane == 0) bulk_wait_all<0>();
+}
+
+}  // namespace g2048
+
 extern "C" int g2048_pack_samples(const uint64_t* d_boards, const uint8_t* d_meta, const float* d_rewards,
                                   const float* d_log_probs, const float* d_values, const float* d_adv, const float* d_ret,
                                   int64_t n, const double* d_moments, G2048SampleRecord* d_records, void* stream) {
@@ -624,8 +733,44 @@ extern "C" int g2048_gather_samples(const int64_t* d_indices, int64_t m, const G
     const g2048::GatherScalars sc{nullptr, nullptr, nullptr, nullptr, nullptr, d_actions, (uchar4*)d_masks, d_old_log_probs,
                                   d_old_values, d_out_adv, d_out_ret, nullptr, (unsigned long long*)d_out_boards,
                                   (const uint4*)d_records};
-    if (d_obs)  // the observation kernel reads the board out of the record (stride 4 words) and gathers the rest at its end
-        return launch_expand_obs((const uint64_t*)d_records, m, obs_dtype, d_obs, 0, 0, d_indices, stream, &sc, 4);
+    if (d_obs) {
+        static const bool round_robin = [] { const char* e = getenv("G2048_GATHER_ROUND_ROBIN"); return e && e[0] == '1'; }();
+        if (round_robin)  // round 2's first form (A/B): the observation kernel reads the board out of the record (stride 4
+                          // words) and gathers the scalars in a phase at its end
+            return launch_expand_obs((const uint64_t*)d_records, m, obs_dtype, d_obs, 0, 0, d_indices, stream, &sc, 4);
+        G2048_REQUIRE(aligned16(d_obs), "gather_samples: observations must be 16-byte aligned");
+        const int sms = sm_count();
+        if (sms <= 0) return fail_arg("gather_samples: no device");
+        static bool configured_on[64] = {false};
+        bool* configured = device_once_flag(configured_on);
+        if (!configured) return fail_arg("no CUDA device");
+        if (!*configured) {
+            int rc = check_cuda(cudaFuncSetAttribute(g2048::gather_samples_tile_kernel<float>, cudaFuncAttributeMaxDynamicSharedMemorySize, OBS_SMEM_BYTES), "gather_samples: smem attribute");
+            if (!rc) rc = check_cuda(cudaFuncSetAttribute(g2048::gather_samples_tile_kernel<__nv_bfloat16>, cudaFuncAttributeMaxDynamicSharedMemorySize, OBS_SMEM_BYTES), "gather_samples: smem attribute");
+            if (!rc) rc = check_cuda(cudaFuncSetAttribute(g2048::gather_samples_tile_kernel<uint8_t>, cudaFuncAttributeMaxDynamicSharedMemorySize, OBS_SMEM_BYTES), "gather_samples: smem attribute");
+            if (rc) return rc;
+            *configured = true;
+        }
+        const int64_t n_tiles = (m + 31) / 32;
+        const int64_t need = (n_tiles + OBS_WARPS - 1) / OBS_WARPS;
+        const int64_t cap = (int64_t)sms * 3;  // 3 resident CTAs of 62 KiB per SM
+        const unsigned grid = (unsigned)(need < cap ? need : cap);
+        cudaStream_t st = (cudaStream_t)stream;
+        switch (obs_dtype) {
+            case G2048_OBS_F32:
+                g2048::gather_samples_tile_kernel<float><<<grid, OBS_THREADS, OBS_SMEM_BYTES, st>>>(d_indices, m, (const uint4*)d_records, (float*)d_obs, sc);
+                break;
+            case G2048_OBS_BF16:
+                g2048::gather_samples_tile_kernel<__nv_bfloat16><<<grid, OBS_THREADS, OBS_SMEM_BYTES, st>>>(d_indices, m, (const uint4*)d_records, (__nv_bfloat16*)d_obs, sc);
+                break;
+            case G2048_OBS_BOOL:
+                g2048::gather_samples_tile_kernel<uint8_t><<<grid, OBS_THREADS, OBS_SMEM_BYTES, st>>>(d_indices, m, (const uint4*)d_records, (uint8_t*)d_obs, sc);
+                break;
+            default: return fail_arg("gather_samples: dtype");
+        }
+        G2048_CHECK_LAUNCH("gather_samples");
+        return G2048_OK;
+    }
     g2048::gather_records_kernel<<<blocks_for(m, 256), 256, 0, (cudaStream_t)stream>>>(d_indices, m, sc);
     G2048_CHECK_LAUNCH("gather_samples");
     return G2048_OK;
