@@ -583,17 +583,37 @@ pack_samples_kernel(const u64* __restrict__ boards, const uint8_t* __restrict__ 
         nr = norm_params(moments, 3);
     }
     const int64_t stride = (int64_t)gridDim.x * blockDim.x;
-    for (int64_t i = (int64_t)blockIdx.x * blockDim.x + threadIdx.x; i < n; i += stride) {
-        const u64 b = boards[i];
-        float a = adv ? adv[i] : 0.0f, r = ret ? ret[i] : 0.0f;
-        if (moments) {
-            a = (a - na.mean) / na.denom;
-            r = (r - nr.mean) / nr.denom;
+    // four steps per thread and iteration, every load issued before the first store: with one step per iteration the
+    // 29 bytes a thread had in flight left the SMs at half of the bandwidth-delay product (ncu: long_scoreboard 25 per issue)
+    constexpr int U = 4;
+    for (int64_t i0 = (int64_t)blockIdx.x * blockDim.x + threadIdx.x; i0 < n; i0 += U * stride) {
+        u64 b[U];
+        uint32_t mt[U];
+        float rw[U], lp[U], vl[U], a[U], r[U];
+#pragma unroll
+        for (int k = 0; k < U; ++k) {
+            const int64_t i = i0 + k * stride;
+            const bool in = i < n;
+            b[k] = in ? boards[i] : 0ull;
+            mt[k] = in ? (uint32_t)meta[i] : 0u;
+            rw[k] = (in && rewards) ? rewards[i] : 0.0f;
+            lp[k] = (in && log_probs) ? log_probs[i] : 0.0f;
+            vl[k] = (in && values) ? values[i] : 0.0f;
+            a[k] = (in && adv) ? adv[i] : 0.0f;
+            r[k] = (in && ret) ? ret[i] : 0.0f;
         }
-        records[2 * i] = make_uint4((uint32_t)b, (uint32_t)(b >> 32), (uint32_t)meta[i],
-                                    __float_as_uint(rewards ? rewards[i] : 0.0f));
-        records[2 * i + 1] = make_uint4(__float_as_uint(log_probs ? log_probs[i] : 0.0f), __float_as_uint(values ? values[i] : 0.0f),
-                                        __float_as_uint(a), __float_as_uint(r));
+#pragma unroll
+        for (int k = 0; k < U; ++k) {
+            const int64_t i = i0 + k * stride;
+            if (i < n) {
+                if (moments) {
+                    a[k] = (a[k] - na.mean) / na.denom;
+                    r[k] = (r[k] - nr.mean) / nr.denom;
+                }
+                records[2 * i] = make_uint4((uint32_t)b[k], (uint32_t)(b[k] >> 32), mt[k], __float_as_uint(rw[k]));
+                records[2 * i + 1] = make_uint4(__float_as_uint(lp[k]), __float_as_uint(vl[k]), __float_as_uint(a[k]), __float_as_uint(r[k]));
+            }
+        }
     }
 }
 
