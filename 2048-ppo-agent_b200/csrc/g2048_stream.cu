@@ -535,7 +535,8 @@ extern "C" int g2048_policy_step_obs(uint64_t* d_boards, uint8_t* d_status, cons
                                         d_actions_out, (unsigned long long*)d_counters};
     const int64_t n_tiles = (n + 31) / 32;
     const int64_t need = (n_tiles + OBS_WARPS - 1) / OBS_WARPS;
-    const int64_t cap = (int64_t)sms * 3;  // 3 resident CTAs of 62 KiB per SM
+    static const int ctas_per_sm = [] { const char* e = getenv("G2048_PSO_CTAS_PER_SM"); const int v = e ? atoi(e) : 0; return v >= 1 && v <= 3 ? v : 3; }();
+    const int64_t cap = (int64_t)sms * ctas_per_sm;  // up to 3 resident CTAs of 62 KiB per SM
     const unsigned grid = (unsigned)(need < cap ? need : cap);
     cudaStream_t st = (cudaStream_t)stream;
 #define G2048_PSO_LAUNCH(T)                                                                                            \
