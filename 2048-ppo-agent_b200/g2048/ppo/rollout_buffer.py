@@ -49,36 +49,46 @@ class RolloutBuffer:
         self.log_prob_buffer = []
         self.termination_buffer = []
 
-    # -- reference validation (rollout_buffer.py:58-126), same messages -------------------------
-    def _validate_and_reshape_observations(self, observations: np.ndarray) -> np.ndarray:
+    # -- the reference's shape contract (rollout_buffer.py:58-126): the error TEXTS are part of its test suite -----
+    def _obs_dims(self) -> tuple:
         if isinstance(self.observation_length, (tuple, list)):
-            expected_obs_dims = (*self.observation_length, self.observation_dim)
-        else:
-            expected_obs_dims = (self.observation_length, self.observation_dim)
-        if len(observations.shape) < 2:
+            return (*self.observation_length, self.observation_dim)
+        return (self.observation_length, self.observation_dim)
+
+    def _validate_and_reshape_observations(self, observations: np.ndarray) -> np.ndarray:
+        """(batch, time, ...) observations -> (batch, time, *observation dims); anything with the right number of
+        elements per step is reshaped, anything else is refused with the reference's messages."""
+        want = self._obs_dims()
+        shape = observations.shape
+        if len(shape) < 2:
             raise ValueError(
                 f"Observations must have at least 2 dimensions (batch_size, time_steps, ...), "
-                f"but got shape {observations.shape}"
+                f"but got shape {shape}"
             )
-        batch_size, time_steps = observations.shape[:2]
-        if observations.shape[2:] == expected_obs_dims:
+        if shape[2:] == want:
             return observations
-        try:
-            expected_obs_elements = np.prod(expected_obs_dims)
-            flattened_obs = observations.reshape(batch_size, time_steps, -1)
-            if flattened_obs.shape[2] == expected_obs_elements:
-                return flattened_obs.reshape(batch_size, time_steps, *expected_obs_dims)
-            raise ValueError(
-                f"Cannot reshape observations from shape {observations.shape} to expected shape "
-                f"(batch_size, time_steps, {expected_obs_dims}). "
-                f"Flattened observations have {flattened_obs.shape[2]} elements per timestep "
-                f"but expected {expected_obs_elements} elements."
+        if observations.size == 0:  # an empty batch: the reference trips over numpy's own reshape(-1) here
+            try:
+                observations.reshape(shape[0], shape[1], -1)
+            except ValueError as e:
+                raise ValueError(
+                    f"Failed to reshape observations from shape {shape} to expected shape "
+                    f"(batch_size, time_steps, {want}). Error: {str(e)}"
+                )
+        per_step, needed = int(np.prod(shape[2:], dtype=np.int64)), int(np.prod(want))
+        if per_step != needed:
+            # the reference raises this from inside a try block and wraps it once more: both texts, nested
+            inner = (
+                f"Cannot reshape observations from shape {shape} to expected shape "
+                f"(batch_size, time_steps, {want}). "
+                f"Flattened observations have {per_step} elements per timestep "
+                f"but expected {needed} elements."
             )
-        except Exception as e:
             raise ValueError(
-                f"Failed to reshape observations from shape {observations.shape} to expected shape "
-                f"(batch_size, time_steps, {expected_obs_dims}). Error: {str(e)}"
+                f"Failed to reshape observations from shape {shape} to expected shape "
+                f"(batch_size, time_steps, {want}). Error: {inner}"
             )
+        return observations.reshape(shape[0], shape[1], *want)
 
     # -- storing --------------------------------------------------------------------------------
     def store_packed(self, rollout) -> int:
@@ -194,11 +204,6 @@ class RolloutBuffer:
             self._parts = [("packed", tuple(torch.cat([p[i] for _, p in self._parts]) for i in range(5)))]
         boards, meta, rewards, values, log_probs = self._parts[0][1]
         return dict(boards=boards, meta=meta, rewards=rewards, values=values, log_probs=log_probs)
-
-    def _obs_dims(self) -> tuple:
-        if isinstance(self.observation_length, (tuple, list)):
-            return (*self.observation_length, self.observation_dim)
-        return (self.observation_length, self.observation_dim)
 
     def _part_fields(self, kind: str, part) -> dict:
         """Device tensors of one part in the reference's layout."""
