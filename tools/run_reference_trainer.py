@@ -35,6 +35,9 @@ def main():
     ap.add_argument("--default-agent", action="store_true",
                     help="configs/model/transformer_combined.yaml: d_model 256, 8 heads, 4 layers, ff 1024, hidden 512, cls")
     ap.add_argument("--no-mask", action="store_true")
+    ap.add_argument("--train-timesteps", type=int, default=0,
+                    help="then run PPOIterationLoop.for_trainer(trainer).train(...) -- this package's version of the trainer's "
+                         "train loop around the reference's own update_policy -- for this many timesteps")
     args = ap.parse_args()
     if args.stage:
         for rel in FILES:
@@ -96,6 +99,29 @@ def main():
     report["parameters_changed"] = bool(any(not torch.equal(a, b.detach()) for a, b in zip(before, agent.parameters())))
     assert report["buffer_size"] > 0 and report["parameters_changed"] and report["episodes_tracked"] == args.envs * args.batches
     assert all(v == v for v in report["update_metrics"].values()), "NaN in the update metrics"
+    if args.train_timesteps > 0:
+        # the reference's train() cannot get past its first collect_rollouts (the deque slice above); the same loop from
+        # this package, driving the SAME trainer object: its agent, optimizer, update_policy, writer and checkpoints
+        from g2048.ppo import PPOIterationLoop
+
+        loop = PPOIterationLoop.for_trainer(trainer)
+        start = loop.total_timesteps
+        t0 = time.perf_counter()
+        records = loop.train(total_timesteps=args.train_timesteps, rollout_batch_size=args.envs, rollout_batches=args.batches,
+                             update_epochs=args.epochs, train_batch_size=args.minibatch, save_freq=args.train_timesteps // 2)
+        torch.cuda.synchronize()
+        report["train_loop"] = {
+            "seconds": time.perf_counter() - t0, "iterations": len(records), "timesteps": loop.total_timesteps - start,
+            "trainer_total_timesteps": int(trainer.total_timesteps), "trainer_total_update_steps": int(trainer.total_update_steps),
+            "checkpoints": sorted(p.name for p in Path(".").glob("*.pt")),
+            "per_iteration": [{"timesteps": r["rollout"]["timesteps"], "mean_episode_length": r["rollout"]["mean_episode_length"],
+                               "mean_max_episode_reward": r["rollout"]["mean_max_episode_reward"],
+                               "policy_loss": float(r["update"]["policy_loss"]), "value_loss": float(r["update"]["value_loss"]),
+                               "kl_divergence": float(r["update"]["kl_divergence"]), "n_updates": int(r["update"]["n_updates"])}
+                              for r in records]}
+        assert trainer.total_timesteps == loop.total_timesteps >= start + args.train_timesteps
+        assert len(trainer.episode_rewards) == min(trainer.episode_rewards.maxlen, args.envs * args.batches * (1 + len(records)))
+        assert "final_model.pt" in report["train_loop"]["checkpoints"]
     print(json.dumps(report, indent=1))
     return 0
 
