@@ -591,10 +591,18 @@ int play_record_impl(int policy, const uint32_t* d_subs, int64_t n_subs, int64_t
 #undef ARGS
 }
 
-// One warp per env: the episode's slot range -> its segment of the flat buffer (HBM-bound: 9 B read + up to 21 B
-// written per env-step; the potentials behind the rewards cost nothing next to that).  A warp takes 128 steps per
-// iteration -- the mean episode is about that long -- with every load of the iteration issued before the first use.
-template <int POLICY>
+// One warp per env: the episode's slot range -> its segment of the flat buffer (9 B read + up to 21 B written per
+// env-step).  A warp takes 128 steps per iteration -- the mean episode is about that long -- with every load of the
+// iteration issued before the first use.  The first form executed 158 instructions per lane-step, a third of them
+// predication (loads guarded by t <= len, five null tests per store group, shuffles inside divergent code); this one
+// clamps the load indices instead (slot `len` holds the final board, so every address is valid), keeps the shuffles
+// in uniform code, tests t < len once, and is compiled a second time for callers that want every output (ALL: the
+// product path) without the pointer tests: 90 instructions per lane-step -- and 249 instead of 255 us for C4's
+// 3.1e7 steps, so instructions were not what bounds it.  Neither are the three other things ncu
+// (gpurun_out r02_compact: l1tex 70 %, long_scoreboard 12.7 per issue, DRAM 45 %) suggested, each built and timed:
+// see the notes in the body.  What is left is the access pattern itself -- seven streams of 0.1 - 1 KB chunks per
+// env, the reads scattered over the lanes' arena regions -- at 3.7 TB/s.
+template <int POLICY, bool ALL>
 __global__ void __launch_bounds__(256)
 play_record_compact_kernel(const u64* __restrict__ arena_boards, const uint8_t* __restrict__ arena_meta,
                            const unsigned long long* __restrict__ env_slot, const uint32_t* __restrict__ lengths,
@@ -602,66 +610,83 @@ play_record_compact_kernel(const u64* __restrict__ arena_boards, const uint8_t* 
                            uint8_t* __restrict__ o_meta, float* __restrict__ o_rewards, float* __restrict__ o_log_probs,
                            float* __restrict__ o_values, float* __restrict__ o_max_reward) {
     constexpr int K = 4;  // 32-step groups per iteration
-    const int lane = threadIdx.x & 31;
+    const uint32_t lane = threadIdx.x & 31u;
     const int64_t warps = (int64_t)gridDim.x * (blockDim.x >> 5);
-    // potential of a pair of cells (one byte of the board): 8 shared-memory lookups per board instead of 16 x 6 instructions
+    // potential of a pair of cells (one byte of the board): 8 shared-memory lookups per board instead of 16 x 6
+    // instructions; log(1 / #legal) by legal mask (the lock-step recorder's act_random_log_prob, bit for bit).
+    // (One copy of the table per bank -- lookups of a warp never conflict, 32 KiB per CTA, one wave of resident CTAs --
+    // was slower as well: 284 vs 249 us.)
     __shared__ uint32_t s_pot[256];
+    __shared__ float s_lp[16];
     {
         const uint32_t lo = threadIdx.x & 15u, hi = (threadIdx.x >> 4) & 15u;
         s_pot[threadIdx.x & 255] = (lo ? ((lo - 1u) << lo) : 0u) + (hi ? ((hi - 1u) << hi) : 0u);
+        if (threadIdx.x < 16) s_lp[threadIdx.x] = (POLICY == G2048_POLICY_RANDOM) ? act_random_log_prob(threadIdx.x) : 0.0f;
     }
     __syncthreads();
+    const char* pot_base = reinterpret_cast<const char*>(s_pot);
+    auto pair = [&](uint32_t byte_times_4) -> uint32_t { return *reinterpret_cast<const uint32_t*>(pot_base + byte_times_4); };
     auto potential = [&](u64 x) -> uint32_t {
         const uint32_t a = (uint32_t)x, c = (uint32_t)(x >> 32);
-        return s_pot[a & 255u] + s_pot[(a >> 8) & 255u] + s_pot[(a >> 16) & 255u] + s_pot[a >> 24] +
-               s_pot[c & 255u] + s_pot[(c >> 8) & 255u] + s_pot[(c >> 16) & 255u] + s_pot[c >> 24];
+        return (pair((a << 2) & 0x3FCu) + pair((a >> 6) & 0x3FCu) + pair((a >> 14) & 0x3FCu) + pair((a >> 22) & 0x3FCu)) +
+               (pair((c << 2) & 0x3FCu) + pair((c >> 6) & 0x3FCu) + pair((c >> 14) & 0x3FCu) + pair((c >> 22) & 0x3FCu));
     };
-    // log(1 / #legal) for 1..4 legal actions, computed once (the lock-step recorder's act_random_log_prob, bit for bit)
-    float lp_of[5];
+    // (A software pipeline over the warp's envs -- header two envs ahead, the first 128 steps' loads one env ahead --
+    // needed 80 registers, three CTAs per SM instead of five, and was slower: 289 vs 249 us for C4's 3.1e7 steps.)
+    struct Header {
+        uint32_t len;
+        const u64* boards;
+        const uint8_t* meta;
+        int64_t dst;
+    };
+    auto load_header = [&](int64_t e) -> Header {
+        if (e >= n) return Header{0u, arena_boards, arena_meta, 0};
+        const unsigned long long slot = env_slot[e];
+        return Header{lengths[e], arena_boards + slot, arena_meta + slot, out_base + offsets[e]};
+    };
+    // (Windows of 32 steps aligned in the DESTINATION -- every store a whole line -- were slower, 267 vs 249 us: the
+    // partial first window costs more loads than the straddling stores cost lines.)
+    // boards t0 .. t0 + 32 K (one more than steps: the reward of a step needs the next board's potential)
+    auto load_records = [&](const Header& h, int32_t t0, u64 (&b)[K + 1], uint32_t (&m)[K]) {
+        const int32_t len = (int32_t)h.len, last = max(len - 1, 0);
 #pragma unroll
-    for (int k = 0; k < 5; ++k) lp_of[k] = (POLICY == G2048_POLICY_RANDOM) ? act_random_log_prob(k == 0 ? 0u : (1u << k) - 1u) : 0.0f;
+        for (int k = 0; k < K; ++k) {
+            const int32_t t = t0 + 32 * k + (int32_t)lane;
+            b[k] = __ldg(h.boards + min(t, len));
+            m[k] = (uint32_t)__ldg(h.meta + min(t, last));
+        }
+        b[K] = __ldg(h.boards + min(t0 + 32 * K, len));  // the board after the iteration's last step: one address, broadcast
+    };
+    auto write_steps = [&](const Header& h, int32_t t0, const u64 (&b)[K + 1], const uint32_t (&m)[K], uint32_t& best) {
+        uint32_t pot[K + 1];
+#pragma unroll
+        for (int k = 0; k <= K; ++k) pot[k] = potential(b[k]);
+#pragma unroll
+        for (int k = 0; k < K; ++k) {
+            const int32_t t = t0 + 32 * k + (int32_t)lane;
+            uint32_t p1 = __shfl_down_sync(0xFFFFFFFFu, pot[k], 1);
+            const uint32_t first_of_next = (k + 1 < K) ? __shfl_sync(0xFFFFFFFFu, pot[k + 1], 0) : pot[K];
+            if (lane == 31u) p1 = first_of_next;
+            if (t < (int32_t)h.len) {
+                const uint32_t gained = p1 - pot[k] - ((m[k] >> 5) & 4u);  // bit 7: the spawned tile was a 4
+                const int64_t o = h.dst + t;
+                best = max(best, gained);
+                if (ALL || o_boards) o_boards[o] = b[k];
+                if (ALL || o_meta) o_meta[o] = (uint8_t)(m[k] & 0x7Fu);
+                if (ALL || o_rewards) o_rewards[o] = (float)gained;
+                if (ALL || o_log_probs) o_log_probs[o] = s_lp[(m[k] >> 2) & 15u];
+                if (ALL || o_values) o_values[o] = 0.0f;
+            }
+        }
+    };
     for (int64_t e = (int64_t)blockIdx.x * (blockDim.x >> 5) + (threadIdx.x >> 5); e < n; e += warps) {
-        const uint32_t len = lengths[e];
-        const unsigned long long src = env_slot[e];
-        const int64_t dst = out_base + offsets[e];
+        const Header h = load_header(e);
         uint32_t best = 0;  // the trainer's "episode reward" = max_t reward (src/ppo/ppo_trainer.py:218-227)
-        for (uint32_t t0 = 0; t0 < len; t0 += 32u * K) {
-            // slots t0 .. t0 + 32 K (one more board than steps: the reward of a step needs the next board's potential)
+        for (int32_t t0 = 0; t0 < (int32_t)h.len; t0 += 32 * K) {
             u64 b[K + 1];
             uint32_t m[K];
-#pragma unroll
-            for (int k = 0; k < K; ++k) {
-                const uint32_t t = t0 + 32u * k + (uint32_t)lane;
-                b[k] = (t <= len) ? __ldg(&arena_boards[src + t]) : 0ull;
-                m[k] = (t < len) ? (uint32_t)__ldg(&arena_meta[src + t]) : 0u;
-            }
-            {
-                const uint32_t t = t0 + 32u * K;  // lane 0 fetches the board after the iteration's last step
-                b[K] = (lane == 0 && t <= len) ? __ldg(&arena_boards[src + t]) : 0ull;
-            }
-            uint32_t pot[K + 1];  // one potential per board: the neighbour's comes by shuffle
-#pragma unroll
-            for (int k = 0; k <= K; ++k) pot[k] = potential(b[k]);
-#pragma unroll
-            for (int k = 0; k < K; ++k) {
-                const uint32_t t = t0 + 32u * k + (uint32_t)lane;
-                uint32_t p1 = __shfl_down_sync(0xFFFFFFFFu, pot[k], 1);
-                const uint32_t first_of_next = __shfl_sync(0xFFFFFFFFu, pot[k + 1], 0);
-                if (lane == 31) p1 = first_of_next;
-                if (t < len) {
-                    const uint32_t gained = p1 - pot[k] - ((m[k] & 0x80u) ? 4u : 0u);
-                    const int64_t o = dst + t;
-                    best = max(best, gained);
-                    if (o_boards) o_boards[o] = b[k];
-                    if (o_meta) o_meta[o] = (uint8_t)(m[k] & 0x7Fu);
-                    if (o_rewards) o_rewards[o] = (float)gained;
-                    if (o_log_probs) {
-                        const int legal = __popc((m[k] >> 2) & 15u);
-                        o_log_probs[o] = legal == 1 ? lp_of[1] : (legal == 2 ? lp_of[2] : (legal == 3 ? lp_of[3] : (legal == 4 ? lp_of[4] : lp_of[0])));
-                    }
-                    if (o_values) o_values[o] = 0.0f;
-                }
-            }
+            load_records(h, t0, b, m);
+            write_steps(h, t0, b, m, best);
         }
         if (o_max_reward) {
             for (int off = 16; off > 0; off >>= 1) best = max(best, __shfl_xor_sync(0xFFFFFFFFu, best, off));
@@ -726,14 +751,17 @@ extern "C" int g2048_play_record_compact(int policy, const uint64_t* d_arena_boa
     const int64_t cap = (int64_t)sms * 32;  // grid-stride beyond 8 resident CTAs per SM x 4
     const unsigned grid = (unsigned)(need < cap ? need : cap);
     cudaStream_t st = (cudaStream_t)stream;
-    if (policy == G2048_POLICY_RANDOM)
-        play_record_compact_kernel<G2048_POLICY_RANDOM><<<grid, 256, 0, st>>>(
-            (const u64*)d_arena_boards, d_arena_meta, (const unsigned long long*)d_env_slot, d_lengths, d_offsets, n, out_base,
-            (u64*)d_boards, d_meta, d_rewards, d_log_probs, d_values, d_max_reward);
-    else
-        play_record_compact_kernel<G2048_POLICY_DRUL><<<grid, 256, 0, st>>>(
-            (const u64*)d_arena_boards, d_arena_meta, (const unsigned long long*)d_env_slot, d_lengths, d_offsets, n, out_base,
-            (u64*)d_boards, d_meta, d_rewards, d_log_probs, d_values, d_max_reward);
+#define G2048_COMPACT_LAUNCH(P, A)                                                                                      \
+    play_record_compact_kernel<P, A><<<grid, 256, 0, st>>>((const u64*)d_arena_boards, d_arena_meta,                    \
+        (const unsigned long long*)d_env_slot, d_lengths, d_offsets, n, out_base, (u64*)d_boards, d_meta, d_rewards,    \
+        d_log_probs, d_values, d_max_reward)
+    const bool all = d_boards && d_meta && d_rewards && d_log_probs && d_values;
+    if (policy == G2048_POLICY_RANDOM) {
+        if (all) G2048_COMPACT_LAUNCH(G2048_POLICY_RANDOM, true); else G2048_COMPACT_LAUNCH(G2048_POLICY_RANDOM, false);
+    } else {
+        if (all) G2048_COMPACT_LAUNCH(G2048_POLICY_DRUL, true); else G2048_COMPACT_LAUNCH(G2048_POLICY_DRUL, false);
+    }
+#undef G2048_COMPACT_LAUNCH
     G2048_CHECK_LAUNCH("play_record_compact");
     return G2048_OK;
 }

@@ -537,7 +537,12 @@ extern "C" int g2048_policy_step_obs(uint64_t* d_boards, uint8_t* d_status, cons
     const int64_t need = (n_tiles + OBS_WARPS - 1) / OBS_WARPS;
     static const int ctas_per_sm = [] { const char* e = getenv("G2048_PSO_CTAS_PER_SM"); const int v = e ? atoi(e) : 0; return v >= 1 && v <= 3 ? v : 3; }();
     const int64_t cap = (int64_t)sms * ctas_per_sm;  // up to 3 resident CTAs of 62 KiB per SM
-    const unsigned grid = (unsigned)(need < cap ? need : cap);
+    // a whole number of CTAs per SM once there is more than one CTA's worth of tiles per SM: 65 536 envs are 256 CTAs of
+    // eight tiles -- two on 108 SMs, one on 40 -- or 296 CTAs of seven (tiles go round-robin over the CTAs): 28.9 -> 28.4 us
+    unsigned grid = (unsigned)(need < cap ? need : cap);
+    if (need > sms && need < cap) grid = (unsigned)(((need + sms - 1) / sms) * sms);
+    static const int grid_override = [] { const char* e = getenv("G2048_PSO_GRID"); return e ? atoi(e) : 0; }();  // probing only
+    if (grid_override > 0) grid = (unsigned)(grid_override < n_tiles ? grid_override : n_tiles);
     cudaStream_t st = (cudaStream_t)stream;
 #define G2048_PSO_LAUNCH(T)                                                                                            \
     do {                                                                                                               \

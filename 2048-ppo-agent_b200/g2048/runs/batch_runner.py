@@ -238,6 +238,7 @@ class BatchRunner:
         while True:
             subs = self.chain.peek(1 + 2 * max_steps)
             rec = E.play_record(policy, subs, batch_size, lo, n, self.rng_mode, mean_steps)
+            offsets = E.exclusive_scan(rec["lengths"])  # queued behind the play kernel BEFORE the host waits for its statistics
             local = E.play_stats_dict(rec["stats"])
             if local["cut_short"]:
                 max_steps *= 4  # an episode outlived the keys that were generated: replay with more
@@ -251,7 +252,6 @@ class BatchRunner:
         stats = self._reduce_stats(rec["stats"])
         st = local if stats is rec["stats"] else E.play_stats_dict(stats)  # one read-back per batch unless it is sharded
         self.chain.consume(1 + 2 * st["longest"])
-        offsets = E.exclusive_scan(rec["lengths"])
         total = local["env_steps"]
         flat = E.play_record_compact(rec, offsets, total)
         return FlatRollout(flat["boards"], flat["meta"], flat["rewards"], flat["log_probs"], flat["values"], rec["lengths"],

@@ -34,3 +34,8 @@ print("us per step (graph replay):", round(min(ts) * 1e3 / T, 2))
 for ctas in (1, 2, 3):
     res = subprocess.run([sys.executable, "-c", CODE], env=dict(os.environ, G2048_PSO_CTAS_PER_SM=str(ctas)), capture_output=True, text=True)
     print("CTAs per SM", ctas, res.stdout.strip() or res.stderr[-400:])
+# an explicit grid (G2048_PSO_GRID): 256 = one CTA per 8 tiles (108 SMs get two CTAs, 40 get one); multiples of 148 spread
+# the 2 048 tiles evenly over the SMs
+for grid in (148, 222, 256, 296, 370, 444):
+    res = subprocess.run([sys.executable, "-c", CODE], env=dict(os.environ, G2048_PSO_GRID=str(grid)), capture_output=True, text=True)
+    print("grid", grid, res.stdout.strip() or res.stderr[-400:])
