@@ -615,7 +615,7 @@ def secondary_measurements(E, N, torch, dev, flush_buf) -> dict:
     add("pack_samples_kernel", n_buf * (25 + 32), t, "2^22 steps: 25 B read (board, meta, reward, log-prob, value, advantage, return) + one 32 B sample record written per step, normalisation applied on the way")
     per_sample = 8 + 32 + 1984 + 8 + 4 + 16
     t = timed(lambda: E.gather_samples(idx, records, out=mb_out))
-    add("gather_samples (expand_obs_tma<float, gathered, sample records>)", m * per_sample, t,
+    add("gather_samples (gather_samples_tile_kernel<float>)", m * per_sample, t,
         "65536 random samples: 8 B index + ONE 32 B record read + 2012 B written per sample; one launch into reused output tensors; 134 MB in all, a launch-bound size")
     t = timed(lambda: E.gather_minibatch(idx, packed, g_adv, g_ret, out=mb_out))
     add("gather_minibatch (round 1: one source array per field)", m * (8 + 8 + 1 + 16 + 1984 + 8 + 4 + 16), t,

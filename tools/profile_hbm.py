@@ -22,9 +22,9 @@ sys.path[:0] = [str(ROOT), str(ROOT / "2048-ppo-agent_b200")]
 ROWS = [
     ("expand_obs_tma_kernel<float>", "expand_obs_tma_kernel"),
     ("pack_samples_kernel", "pack_samples_kernel"),
-    ("gather_samples (expand_obs_tma<float, gathered, sample records>)", "expand_obs_tma_kernel"),
+    ("gather_samples (gather_samples_tile_kernel<float>)", "gather_samples_tile_kernel"),
     ("gather_minibatch (round 1: one source array per field)", "expand_obs_tma_kernel"),
-    ("gather_samples, 2^19 samples", "expand_obs_tma_kernel"),
+    ("gather_samples, 2^19 samples", "gather_samples_tile_kernel"),
     ("embed_boards (float32)", "embed_boards_kernel"),
     ("embed_grad_partial_kernel + reduce (float32)", "embed_grad_partial_kernel"),
     ("embed_boards (bfloat16)", "embed_boards_kernel"),
@@ -38,7 +38,7 @@ ROWS = [
     ("c4: play_record_compact_kernel", "play_record_compact_kernel"),
     ("c3: policy_step_obs_kernel<float>", "policy_step_obs_kernel"),
 ]
-REGEX = "expand_obs_tma_kernel|pack_samples_kernel|embed_boards_kernel|embed_grad_partial_kernel|gae_flat4_kernel|gae_scan_kernel|" \
+REGEX = "expand_obs_tma_kernel|gather_samples_tile_kernel|pack_samples_kernel|embed_boards_kernel|embed_grad_partial_kernel|gae_flat4_kernel|gae_scan_kernel|" \
         "normalize_kernel|gae_time_major_kernel|play_record_compact_kernel|policy_step_obs_kernel"
 
 
