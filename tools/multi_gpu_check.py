@@ -5,7 +5,8 @@
 Every rank runs its shard of the same batches with global env indices; rank 0 also runs the whole batches alone.
 Checked: the all-reduced play statistics equal the single-GPU statistics, the gathered per-env shards equal the
 single-GPU arrays, recorded rollouts (built-in and network policy, also with live-env compaction) agree shard by
-shard, the key chains stay in step, and GAE normalisation with all-reduced moments equals the unsharded one.
+shard, the recording form's flat buffers and sample records concatenate to the single-GPU ones, the key chains stay in
+step, and GAE normalisation with all-reduced moments equals the unsharded one.
 """
 import os
 import sys
@@ -66,6 +67,31 @@ def main():
                 checks.append((f"{policy}: final boards", torch.equal(boards, ref["final_boards"])))
                 checks.append((f"{policy}: lengths", torch.equal(lengths, ref["lengths"])))
                 checks.append((f"{policy}: key chain", bool((single.key == sharded.key).all())))
+
+    # the recording form, sharded: every rank records its own envs; shard after shard the flat buffers ARE the
+    # single-GPU flat buffer (shards are contiguous env ranges), and so are the 32-byte sample records built from it
+    # once the normalisation moments are all-reduced
+    for policy, act in (("random", g2048.act_randomly), ("drul", g2048.act_drul)):
+        sharded = g2048.BatchRunner(init_seed=23, act_fn=act, shard=(rank, world))
+        fr = sharded.run_flat_batch(20_001)
+        buf = g2048.RolloutBuffer(31, 16, 4)
+        buf.store_flat(fr)
+        batches = g2048.DevicePPOBatches(buf.get_packed(), 0.99, 0.95, batch_size=256, group=dist.group.WORLD)
+        fields = {k: gather(getattr(fr, k)) for k in ("boards", "meta", "rewards", "log_probs", "lengths", "final_boards")}
+        records = gather(batches.records)
+        if rank == 0:
+            single = g2048.BatchRunner(init_seed=23, act_fn=act)
+            ref = single.run_flat_batch(20_001)
+            checks.append((f"{policy}: recorded flat buffer", all(torch.equal(fields[k], getattr(ref, k)) for k in fields)))
+            checks.append((f"{policy}: recorded summary", ref.summary == fr.summary))
+            checks.append((f"{policy}: key chain after recording", bool((single.key == sharded.key).all())))
+            ref_buf = g2048.RolloutBuffer(31, 16, 4)
+            ref_buf.store_flat(ref)
+            ref_rec = g2048.DevicePPOBatches(ref_buf.get_packed(), 0.99, 0.95, batch_size=256).records
+            same_ints = torch.equal(records[:, :3], ref_rec[:, :3])  # board, meta + reward, log-prob + value: exact
+            floats = records[:, 3:].contiguous().view(torch.float32)  # normalised advantage and return
+            ref_floats = ref_rec[:, 3:].contiguous().view(torch.float32)
+            checks.append((f"{policy}: sample records of the sharded buffer", same_ints and torch.allclose(floats, ref_floats, rtol=1e-5, atol=1e-6)))
 
     fn = g2048.TorchActionFunction(RowwiseAgent(), use_mask=True, device=dev)
     for compact in (False, True):
