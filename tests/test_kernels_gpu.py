@@ -367,6 +367,28 @@ def test_play_host_pinned_results_are_written_by_the_kernel(E):
         np.testing.assert_array_equal(pageable, a["records"])
 
 
+def test_host_entries_with_multi_megabyte_pageable_arrays(E):
+    """The staged copier splits the host-side memcpy of a chunk over several threads once it has a megabyte or more
+    to move (g2048_hostcopy.cuh): results equal the zero-copy path's, element for element, also for sizes that are not
+    a multiple of the piece or of the 16 MiB staging buffer."""
+    n = 2_500_003  # boards: 20 MB (two staging chunks, the second one short), lengths / scores: 10 MB
+    a = E.play_host(E.POLICY_RANDOM, 21, n, 1, pinned=True)
+    b = E.play_host(E.POLICY_RANDOM, 21, n, 1, pinned=False)
+    for k in ("final_boards", "lengths", "scores"):
+        np.testing.assert_array_equal(a[k], b[k], err_msg=k)
+    np.testing.assert_array_equal(a["stats"], b["stats"])
+    # host-array GAE: 3 x 14 MB in through the same copier, 2 x 14 MB out
+    rng = np.random.default_rng(3)
+    m = 3_500_017
+    r = (rng.integers(0, 64, m) * 4).astype(np.float32)
+    v = rng.standard_normal(m).astype(np.float32)
+    d = (rng.random(m) < 1 / 120).astype(np.uint8)
+    adv, ret = E.gae_host(r, v, d, 0.99, 0.95, False)
+    want_adv, want_ret, _ = E.gae_flat(torch.from_numpy(r).cuda(), torch.from_numpy(v).cuda(), torch.from_numpy(d).cuda(), 0.99, 0.95)
+    np.testing.assert_array_equal(adv, want_adv.cpu().numpy())
+    np.testing.assert_array_equal(ret, want_ret.cpu().numpy())
+
+
 @pytest.mark.parametrize("entry", PLAY_ENTRIES)
 def test_play_reports_cut_short(E, entry):
     key = u32([0, 1])
