@@ -34,6 +34,8 @@ import threading
 import time
 from pathlib import Path
 
+import numpy as np
+
 ROOT = Path(__file__).resolve().parent
 for _p in (str(ROOT), str(ROOT / "2048-ppo-agent_b200")):
     if _p not in sys.path:
@@ -885,6 +887,17 @@ def secondary_measurements(E, N, torch, dev, flush_buf) -> dict:
     c1 = {"config": "C1: BatchRunner(0, act_randomly).run_actions_batch(1024), reference-format numpy outputs",
           "seconds": dt, "loop_steps": int(out[0].shape[1]), "env_steps": int(first_done.sum()),
           "env_steps_per_sec": float(first_done.sum() / dt), "output_bytes": int(sum(a.nbytes for a in out if a is not None))}
+    pin_runner = lambda: g2048.BatchRunner(init_seed=0, act_fn=g2048.act_randomly, pinned_outputs=True)  # noqa: E731
+    keep = pin_runner().run_actions_batch(1024)
+    del keep  # the page-locked blocks are in the host allocator's cache now, as in any loop over batches
+    torch.cuda.synchronize()
+    t0 = time.perf_counter()
+    out_p = pin_runner().run_actions_batch(1024)
+    dt_p = time.perf_counter() - t0
+    c1["pinned_outputs"] = {"seconds": dt_p, "env_steps_per_sec": float(first_done.sum() / dt_p),
+                            "identical": bool(all((a is None and b_ is None) or np.array_equal(a, b_) for a, b_ in zip(out, out_p))),
+                            "note": "BatchRunner(pinned_outputs=True): the returned arrays are page-locked memory written by one transfer each"}
+    del out_p
     # the other reference-API calls at C1's size: run_rollout_batch (list of States, built from the records of a chunked
     # run) and run_actions_max_tile (persistent play kernel + replay of the longest envs for the reference's quirk)
     from g2048.runs.run_actions_max_tile import run_actions_max_tile

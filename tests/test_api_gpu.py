@@ -596,3 +596,18 @@ def test_collect_rollouts_matches_the_trainers_python_loops():
         a, b2 = ref_buffer.get_buffer_data(), buffer.get_buffer_data()
         for k in a:
             np.testing.assert_array_equal(a[k], b2[k])
+
+
+def test_pinned_outputs_are_the_same_arrays_in_page_locked_memory(G):
+    """BatchRunner(pinned_outputs=True): run_actions_batch returns the same values; the large arrays are page-locked
+    memory (one transfer each), ordinary numpy arrays to the caller -- writable, sliceable, alive after the runner."""
+    plain = G.BatchRunner(init_seed=4, act_fn=G.act_randomly).run_actions_batch(300)
+    runner = G.BatchRunner(init_seed=4, act_fn=G.act_randomly, pinned_outputs=True)
+    pinned = runner.run_actions_batch(300)
+    del runner
+    for a, b in zip(plain, pinned):
+        assert (a is None and b is None) or (a.dtype == b.dtype and a.shape == b.shape and np.array_equal(a, b))
+    obs = pinned[0]
+    assert obs.nbytes >= 1 << 20 and torch.from_numpy(obs).is_pinned() and not torch.from_numpy(plain[0]).is_pinned()
+    obs[0, 0] = False  # writable
+    assert not obs[0, 0].any() and plain[0][0, 0].any()
