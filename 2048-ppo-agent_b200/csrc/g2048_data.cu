@@ -145,41 +145,92 @@ episode_lengths_kernel(const uint8_t* __restrict__ meta, int64_t t_steps, int64_
     lengths[e] = len;
 }
 
-// single-CTA exclusive scan (n + 1 outputs).  B is at most a few million: not a hot kernel.
+// Exclusive scan of n uint32 (episode lengths) into n + 1 int64 offsets, three small launches and no scratch memory:
+// chunk sums are parked where the output needs them anyway -- out[(c + 1) * CHUNK] is by definition the sum of
+// chunks 0..c -- one CTA turns them into those running sums, and every chunk then scans its own elements from its
+// base out[c * CHUNK].  (The first form was ONE CTA walking the array 1 024 elements per iteration, four barriers and
+// an unprefetched load each: ~1.5 us per iteration, 0.4 ms for C4's 262 144 envs -- more than the compaction it feeds.)
+constexpr int SCAN_CHUNK = 2048;  // elements per CTA of 256 threads
+
+__device__ __forceinline__ long long warp_inclusive_scan(long long x, int lane) {
+    for (int off = 1; off < 32; off <<= 1) {
+        const long long y = __shfl_up_sync(0xFFFFFFFFu, x, off);
+        if (lane >= off) x += y;
+    }
+    return x;
+}
+
+__global__ void __launch_bounds__(256)
+scan_chunk_sums_kernel(const uint32_t* __restrict__ in, int64_t n, long long* __restrict__ out) {
+    __shared__ long long s_warp[8];
+    const int64_t lo = (int64_t)blockIdx.x * SCAN_CHUNK;
+    const int64_t hi = lo + SCAN_CHUNK < n ? lo + SCAN_CHUNK : n;
+    long long sum = 0;
+    for (int64_t i = lo + threadIdx.x; i < hi; i += 256) sum += (long long)in[i];
+    for (int off = 16; off > 0; off >>= 1) sum += __shfl_down_sync(0xFFFFFFFFu, sum, off);
+    if ((threadIdx.x & 31) == 0) s_warp[threadIdx.x >> 5] = sum;
+    __syncthreads();
+    if (threadIdx.x == 0) {
+        long long total = 0;
+        for (int w = 0; w < 8; ++w) total += s_warp[w];
+        out[hi] = total;  // hi = (c + 1) * CHUNK, or n for the last chunk
+    }
+}
+
+// one CTA: out[pos(j)] (the chunk sums) -> inclusive running sums, pos(j) = min((j + 1) * CHUNK, n); out[0] = 0
 __global__ void __launch_bounds__(1024)
-exclusive_scan_kernel(const uint32_t* __restrict__ in, int64_t n, long long* __restrict__ out) {
+scan_chunk_bases_kernel(long long* __restrict__ out, int64_t n, int64_t chunks) {
     __shared__ long long s_warp[32];
     __shared__ long long s_carry;
-    if (threadIdx.x == 0) s_carry = 0;
+    if (threadIdx.x == 0) {
+        s_carry = 0;
+        out[0] = 0;
+    }
     __syncthreads();
     const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
-    for (int64_t base = 0; base < n; base += 1024) {
-        const int64_t i = base + threadIdx.x;
-        const long long x = (i < n) ? (long long)in[i] : 0;
-        long long incl = x;
-        for (int off = 1; off < 32; off <<= 1) {
-            const long long y = __shfl_up_sync(0xFFFFFFFFu, incl, off);
-            if (lane >= off) incl += y;
-        }
+    for (int64_t base = 0; base < chunks; base += 1024) {
+        const int64_t j = base + threadIdx.x;
+        const int64_t pos = (j + 1) * SCAN_CHUNK < n ? (j + 1) * SCAN_CHUNK : n;
+        const long long x = (j < chunks) ? out[pos] : 0;
+        const long long incl = warp_inclusive_scan(x, lane);
         if (lane == 31) s_warp[warp] = incl;
         __syncthreads();
-        if (warp == 0) {
-            long long w = s_warp[lane];
-            for (int off = 1; off < 32; off <<= 1) {
-                const long long y = __shfl_up_sync(0xFFFFFFFFu, w, off);
-                if (lane >= off) w += y;
-            }
-            s_warp[lane] = w;  // inclusive over warps
-        }
+        if (warp == 0) s_warp[lane] = warp_inclusive_scan(s_warp[lane], lane);
         __syncthreads();
-        const long long carry = s_carry;
-        const long long before = carry + (warp ? s_warp[warp - 1] : 0) + incl - x;
-        if (i < n) out[i] = before;
+        const long long mine = s_carry + (warp ? s_warp[warp - 1] : 0) + incl;
+        if (j < chunks) out[pos] = mine;
         __syncthreads();
-        if (threadIdx.x == 1023) s_carry = before + x;
+        if (threadIdx.x == 1023) s_carry = mine;
         __syncthreads();
     }
-    if (threadIdx.x == 0) out[n] = s_carry;
+}
+
+__global__ void __launch_bounds__(256)
+scan_chunks_kernel(const uint32_t* __restrict__ in, int64_t n, long long* __restrict__ out) {
+    __shared__ long long s_warp[8];
+    const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
+    const int64_t lo = (int64_t)blockIdx.x * SCAN_CHUNK;
+    const long long base = out[lo];  // written by scan_chunk_bases_kernel; this CTA rewrites it with the same value
+    // warp w takes 256 consecutive elements, lane l those at 32 k + l (coalesced): eight warp scans with a running total
+    const int64_t w_lo = lo + warp * 256;
+    long long before[8], running = 0;
+#pragma unroll
+    for (int k = 0; k < 8; ++k) {
+        const int64_t i = w_lo + 32 * k + lane;
+        const long long x = (i < n) ? (long long)in[i] : 0;
+        const long long incl = warp_inclusive_scan(x, lane);
+        before[k] = running + incl - x;
+        running += __shfl_sync(0xFFFFFFFFu, incl, 31);
+    }
+    if (lane == 0) s_warp[warp] = running;
+    __syncthreads();
+    long long prefix = base;
+    for (int w = 0; w < warp; ++w) prefix += s_warp[w];
+#pragma unroll
+    for (int k = 0; k < 8; ++k) {
+        const int64_t i = w_lo + 32 * k + lane;
+        if (i < n) out[i] = prefix + before[k];
+    }
 }
 
 // ragged compaction: flat[out_base + offsets[e] + t] = rec[t][e] for t < lengths[e]
@@ -412,7 +463,12 @@ extern "C" int g2048_episode_lengths(const uint8_t* d_rec_meta, int64_t t_steps,
 
 extern "C" int g2048_exclusive_scan(const uint32_t* d_in, int64_t n, int64_t* d_out, void* stream) {
     G2048_REQUIRE(n >= 0 && d_out && (d_in || n == 0), "exclusive_scan");
-    exclusive_scan_kernel<<<1, 1024, 0, (cudaStream_t)stream>>>(d_in, n, (long long*)d_out);
+    const int64_t chunks = (n + SCAN_CHUNK - 1) / SCAN_CHUNK;
+    G2048_REQUIRE(chunks <= 0x7FFFFFFFll, "exclusive_scan: too long");
+    cudaStream_t st = (cudaStream_t)stream;
+    if (chunks) scan_chunk_sums_kernel<<<(unsigned)chunks, 256, 0, st>>>(d_in, n, (long long*)d_out);
+    scan_chunk_bases_kernel<<<1, 1024, 0, st>>>((long long*)d_out, n, chunks);
+    if (chunks) scan_chunks_kernel<<<(unsigned)chunks, 256, 0, st>>>(d_in, n, (long long*)d_out);
     G2048_CHECK_LAUNCH("exclusive_scan");
     return G2048_OK;
 }

@@ -606,9 +606,9 @@ template <int POLICY, bool ALL>
 __global__ void __launch_bounds__(256)
 play_record_compact_kernel(const u64* __restrict__ arena_boards, const uint8_t* __restrict__ arena_meta,
                            const unsigned long long* __restrict__ env_slot, const uint32_t* __restrict__ lengths,
-                           const int64_t* __restrict__ offsets, int64_t n, int64_t out_base, u64* __restrict__ o_boards,
-                           uint8_t* __restrict__ o_meta, float* __restrict__ o_rewards, float* __restrict__ o_log_probs,
-                           float* __restrict__ o_values, float* __restrict__ o_max_reward) {
+                           const int64_t* __restrict__ offsets, int64_t n, int64_t out_base, int64_t out_capacity,
+                           u64* __restrict__ o_boards, uint8_t* __restrict__ o_meta, float* __restrict__ o_rewards,
+                           float* __restrict__ o_log_probs, float* __restrict__ o_values, float* __restrict__ o_max_reward) {
     constexpr int K = 4;  // 32-step groups per iteration
     const uint32_t lane = threadIdx.x & 31u;
     const int64_t warps = (int64_t)gridDim.x * (blockDim.x >> 5);
@@ -635,14 +635,17 @@ play_record_compact_kernel(const u64* __restrict__ arena_boards, const uint8_t* 
     // needed 80 registers, three CTAs per SM instead of five, and was slower: 289 vs 249 us for C4's 3.1e7 steps.)
     struct Header {
         uint32_t len;
+        int32_t fits;  // steps of the env that lie inside the output arrays (all of them unless the caller's estimate was short)
         const u64* boards;
         const uint8_t* meta;
         int64_t dst;
     };
     auto load_header = [&](int64_t e) -> Header {
-        if (e >= n) return Header{0u, arena_boards, arena_meta, 0};
         const unsigned long long slot = env_slot[e];
-        return Header{lengths[e], arena_boards + slot, arena_meta + slot, out_base + offsets[e]};
+        const uint32_t len = lengths[e];
+        const int64_t off = offsets[e], room = out_capacity - off;
+        return Header{len, (int32_t)(room < 0 ? 0 : (room < (int64_t)len ? room : (int64_t)len)), arena_boards + slot, arena_meta + slot,
+                      out_base + off};
     };
     // (Windows of 32 steps aligned in the DESTINATION -- every store a whole line -- were slower, 267 vs 249 us: the
     // partial first window costs more loads than the straddling stores cost lines.)
@@ -671,11 +674,13 @@ play_record_compact_kernel(const u64* __restrict__ arena_boards, const uint8_t* 
                 const uint32_t gained = p1 - pot[k] - ((m[k] >> 5) & 4u);  // bit 7: the spawned tile was a 4
                 const int64_t o = h.dst + t;
                 best = max(best, gained);
-                if (ALL || o_boards) o_boards[o] = b[k];
-                if (ALL || o_meta) o_meta[o] = (uint8_t)(m[k] & 0x7Fu);
-                if (ALL || o_rewards) o_rewards[o] = (float)gained;
-                if (ALL || o_log_probs) o_log_probs[o] = s_lp[(m[k] >> 2) & 15u];
-                if (ALL || o_values) o_values[o] = 0.0f;
+                if (t < h.fits) {
+                    if (ALL || o_boards) o_boards[o] = b[k];
+                    if (ALL || o_meta) o_meta[o] = (uint8_t)(m[k] & 0x7Fu);
+                    if (ALL || o_rewards) o_rewards[o] = (float)gained;
+                    if (ALL || o_log_probs) o_log_probs[o] = s_lp[(m[k] >> 2) & 15u];
+                    if (ALL || o_values) o_values[o] = 0.0f;
+                }
             }
         }
     };
@@ -739,10 +744,10 @@ extern "C" int g2048_play_record(int policy, const uint32_t* d_subs, int64_t n_s
 
 extern "C" int g2048_play_record_compact(int policy, const uint64_t* d_arena_boards, const uint8_t* d_arena_meta,
                                          const uint64_t* d_env_slot, const uint32_t* d_lengths, const int64_t* d_offsets,
-                                         int64_t n, int64_t out_base, uint64_t* d_boards, uint8_t* d_meta, float* d_rewards,
-                                         float* d_log_probs, float* d_values, float* d_max_reward, void* stream) {
+                                         int64_t n, int64_t out_base, int64_t out_capacity, uint64_t* d_boards, uint8_t* d_meta,
+                                         float* d_rewards, float* d_log_probs, float* d_values, float* d_max_reward, void* stream) {
     G2048_REQUIRE(policy == G2048_POLICY_RANDOM || policy == G2048_POLICY_DRUL, "play_record_compact: policy");
-    G2048_REQUIRE(n >= 0 && out_base >= 0, "play_record_compact: sizes");
+    G2048_REQUIRE(n >= 0 && out_base >= 0 && out_capacity >= 0, "play_record_compact: sizes");
     if (n == 0) return G2048_OK;
     G2048_REQUIRE(d_arena_boards && d_arena_meta && d_env_slot && d_lengths && d_offsets, "play_record_compact: pointers");
     const int sms = sm_count();
@@ -753,8 +758,8 @@ extern "C" int g2048_play_record_compact(int policy, const uint64_t* d_arena_boa
     cudaStream_t st = (cudaStream_t)stream;
 #define G2048_COMPACT_LAUNCH(P, A)                                                                                      \
     play_record_compact_kernel<P, A><<<grid, 256, 0, st>>>((const u64*)d_arena_boards, d_arena_meta,                    \
-        (const unsigned long long*)d_env_slot, d_lengths, d_offsets, n, out_base, (u64*)d_boards, d_meta, d_rewards,    \
-        d_log_probs, d_values, d_max_reward)
+        (const unsigned long long*)d_env_slot, d_lengths, d_offsets, n, out_base, out_capacity, (u64*)d_boards, d_meta, \
+        d_rewards, d_log_probs, d_values, d_max_reward)
     const bool all = d_boards && d_meta && d_rewards && d_log_probs && d_values;
     if (policy == G2048_POLICY_RANDOM) {
         if (all) G2048_COMPACT_LAUNCH(G2048_POLICY_RANDOM, true); else G2048_COMPACT_LAUNCH(G2048_POLICY_RANDOM, false);

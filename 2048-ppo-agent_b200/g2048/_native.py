@@ -57,7 +57,7 @@ _SIGNATURES = {
     "g2048_act": (_INT, [_INT, _P, _P, _I64, _I64, _I64, _INT, _P, _P, _P]),
     "g2048_play_record_arena_slots": (_I64, [_I64, _I64, _I64]),
     "g2048_play_record": (_INT, [_INT, _P, _I64, _I64, _I64, _I64, _INT, _P, _P, _P, _I64, _P, _P, _P, _P, _P, _P]),
-    "g2048_play_record_compact": (_INT, [_INT, _P, _P, _P, _P, _P, _I64, _I64, _P, _P, _P, _P, _P, _P, _P]),
+    "g2048_play_record_compact": (_INT, [_INT, _P, _P, _P, _P, _P, _I64, _I64, _I64, _P, _P, _P, _P, _P, _P, _P]),
     "g2048_pack_samples": (_INT, [_P, _P, _P, _P, _P, _P, _P, _I64, _P, _P, _P]),
     "g2048_gather_samples": (_INT, [_P, _I64, _P, _INT, _P, _P, _P, _P, _P, _P, _P, _P, _P]),
     "g2048_policy_step_obs": (_INT, [_P, _P, _P, _P, _INT, _INT, _INT, _P, _P, _INT, _I64, _I64, _I64, _INT, _P, _P, _P, _P, _P,

@@ -247,6 +247,11 @@ def play_record(policy: int, subs: torch.Tensor, batch_global: int, env_lo: int,
     mean_steps)."""
     dev = subs.device
     mean = MEAN_STEPS_HINT[policy] if mean_steps is None else int(mean_steps)
+    if n == 0:  # an empty shard (more ranks than envs): nothing to launch, empty results, zero statistics
+        empty = lambda dt: torch.empty(0, dtype=dt, device=dev)  # noqa: E731
+        return dict(arena_boards=empty(torch.int64), arena_meta=empty(torch.uint8), env_slot=empty(torch.int64),
+                    final_boards=empty(torch.int64), lengths=empty(torch.int32), scores=empty(torch.int32),
+                    stats=torch.zeros(N.PLAY_STATS_WORDS, dtype=torch.int64, device=dev) if stats is None else stats, policy=policy)
     with torch.cuda.device(dev):  # the arena follows the SM count of the GPU that will run the kernel
         slots = int(N.lib.g2048_play_record_arena_slots(n, subs.shape[0], mean))
     if slots <= 0:
@@ -266,8 +271,10 @@ def play_record(policy: int, subs: torch.Tensor, batch_global: int, env_lo: int,
 
 
 def play_record_compact(rec: dict, offsets: torch.Tensor, total: int) -> dict:
-    """Arena of play_record -> flat env-major packed buffer (boards, meta, rewards, log_probs, values; max_rewards per env), `total` =
-    offsets[-1] steps; offsets = exclusive_scan(rec["lengths"])."""
+    """Arena of play_record -> flat env-major packed buffer (boards, meta, rewards, log_probs, values; max_rewards per
+    env) with room for `total` steps; offsets = exclusive_scan(rec["lengths"]).  `total` is normally offsets[-1]; it may
+    also be an estimate made before the statistics are read back -- steps beyond it are dropped (never written out of
+    bounds), a larger one leaves the tail of the arrays unwritten: compare with the exact total afterwards."""
     dev = offsets.device
     n = rec["lengths"].shape[0]
     flat = dict(boards=torch.empty(total, dtype=torch.int64, device=dev), meta=torch.empty(total, dtype=torch.uint8, device=dev),
@@ -275,8 +282,10 @@ def play_record_compact(rec: dict, offsets: torch.Tensor, total: int) -> dict:
                 log_probs=torch.empty(total, dtype=torch.float32, device=dev),
                 values=torch.empty(total, dtype=torch.float32, device=dev),
                 max_rewards=torch.empty(n, dtype=torch.float32, device=dev))
+    if n == 0:
+        return flat
     call("g2048_play_record_compact", rec["policy"], ptr(rec["arena_boards"]), ptr(rec["arena_meta"]), ptr(rec["env_slot"]),
-         ptr(rec["lengths"]), ptr(offsets), n, 0, ptr(flat["boards"]), ptr(flat["meta"]), ptr(flat["rewards"]),
+         ptr(rec["lengths"]), ptr(offsets), n, 0, total, ptr(flat["boards"]), ptr(flat["meta"]), ptr(flat["rewards"]),
          ptr(flat["log_probs"]), ptr(flat["values"]), ptr(flat["max_rewards"]), stream_ptr())
     return flat
 

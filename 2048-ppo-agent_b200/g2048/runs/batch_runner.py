@@ -244,7 +244,15 @@ class BatchRunner:
         while True:
             subs = self.chain.peek(1 + 2 * max_steps)
             rec = E.play_record(policy, subs, batch_size, lo, n, self.rng_mode, mean_steps)
-            offsets = E.exclusive_scan(rec["lengths"])  # queued behind the play kernel BEFORE the host waits for its statistics
+            # The scan and the compaction are queued behind the play kernel BEFORE the host waits for its statistics:
+            # the flat arrays are sized from the previous batch's mean episode length plus a margin (six standard
+            # deviations of the total), the kernel drops what would not fit, and only a short estimate costs a second
+            # compaction.  (Waiting for the exact total first left the GPU idle for the ~70 us the host needs to come
+            # back from the synchronisation, allocate and launch.)
+            offsets = E.exclusive_scan(rec["lengths"])
+            mean_guess = E.MEAN_STEPS_HINT[policy] if mean_steps is None else mean_steps
+            room = int(n * mean_guess * 1.01) + 600 * int(n ** 0.5) + 4096
+            flat = E.play_record_compact(rec, offsets, room)
             local = E.play_stats_dict(rec["stats"])
             if local["cut_short"]:
                 max_steps *= 4  # an episode outlived the keys that were generated: replay with more
@@ -259,7 +267,10 @@ class BatchRunner:
         st = local if stats is rec["stats"] else E.play_stats_dict(stats)  # one read-back per batch unless it is sharded
         self.chain.consume(1 + 2 * st["longest"])
         total = local["env_steps"]
-        flat = E.play_record_compact(rec, offsets, total)
+        if total > room:
+            flat = E.play_record_compact(rec, offsets, total)
+        else:  # prefixes of the roomier arrays (views: the margin stays allocated as long as the rollout lives)
+            flat = {k: (v if k == "max_rewards" else v[:total]) for k, v in flat.items()}
         return FlatRollout(flat["boards"], flat["meta"], flat["rewards"], flat["log_probs"], flat["values"], rec["lengths"],
                            offsets, rec["final_boards"], rec["scores"], flat["max_rewards"], st["longest"], n, total, st)
 

@@ -162,7 +162,10 @@ int g2048_play_packed(int policy, const uint32_t* d_subs, int64_t n_subs, int64_
  * byte, d_rewards = potential(board t+1) - potential(board t) - 4 * bit 7 (= the sum of the merged tiles' values,
  * Pgx's reward), d_log_probs = log(1 / #legal actions) for G2048_POLICY_RANDOM and 0 for DRUL, d_values = 0.
  * d_max_reward (n, float32) = max over the env's steps of the reward (the trainer's "episode reward",
- * src/ppo/ppo_trainer.py:218-227).  Any output may be NULL. */
+ * src/ppo/ppo_trainer.py:218-227).  Any output may be NULL.  out_capacity = the number of steps of this batch the flat output
+ * arrays have room for: a step with d_offsets[i] + t >= out_capacity is not written, so a caller may launch the compaction into arrays
+ * sized from an ESTIMATE of the total before it has read the statistics back, and repeat it only if the estimate was
+ * short (d_offsets[n] is the exact total).  d_max_reward is always complete. */
 int64_t g2048_play_record_arena_slots(int64_t n, int64_t n_subs, int64_t mean_steps);
 int g2048_play_record(int policy, const uint32_t* d_subs, int64_t n_subs, int64_t batch_global, int64_t env_lo, int64_t n,
                       int rng_mode, uint64_t* d_work, uint64_t* d_arena_boards, uint8_t* d_arena_meta, int64_t arena_slots,
@@ -170,8 +173,8 @@ int g2048_play_record(int policy, const uint32_t* d_subs, int64_t n_subs, int64_
                       uint64_t* d_stats, void* stream);
 int g2048_play_record_compact(int policy, const uint64_t* d_arena_boards, const uint8_t* d_arena_meta,
                               const uint64_t* d_env_slot, const uint32_t* d_lengths, const int64_t* d_offsets, int64_t n,
-                              int64_t out_base, uint64_t* d_boards, uint8_t* d_meta, float* d_rewards, float* d_log_probs,
-                              float* d_values, float* d_max_reward, void* stream);
+                              int64_t out_base, int64_t out_capacity, uint64_t* d_boards, uint8_t* d_meta, float* d_rewards,
+                              float* d_log_probs, float* d_values, float* d_max_reward, void* stream);
 
 /* Test hook for the shared-memory tables of g2048_play_tables: for each 16-bit row (four nibbles, nibble 0 =
  * column 0) the row slid/merged toward column 0 and the flags (bit 0: moves left, bit 2: moves right). */

@@ -627,11 +627,17 @@ def test_unpack_and_compact_match_reference_rollout_buffer(E, golden_ppo):
     np.testing.assert_array_equal(term.cpu().numpy(), g["rb_out_terminations"][:k])
 
 
-def test_exclusive_scan_large(E):
-    rng = np.random.default_rng(43)
-    x = rng.integers(0, 400, 100_003).astype(np.int32)
-    out = E.exclusive_scan(dev(x)).cpu().numpy()
-    np.testing.assert_array_equal(out, np.concatenate([[0], np.cumsum(x.astype(np.int64))]))
+@pytest.mark.parametrize("n", [0, 1, 31, 2047, 2048, 2049, 4096, 100_003, 2048 * 1024, 2048 * 1025 + 7, (1 << 24) + 5])
+def test_exclusive_scan_sizes(E, n):
+    """Chunked scan (2 048 elements per CTA, chunk sums parked in the output): empty, single element, chunk boundaries,
+    exactly 1 024 chunks (one pass of the base kernel) and beyond, C5's 2^24; values up to 2^32 - 1 sum in 64 bits."""
+    rng = np.random.default_rng(43 + n % 97)
+    x = rng.integers(0, 400, n).astype(np.int64)
+    if n > 3:
+        x[[0, n // 2, n - 1]] = (1 << 32) - 1
+    out = E.exclusive_scan(dev(x.astype(np.uint32).view(np.int32))).cpu().numpy()
+    assert out.shape == (n + 1,)
+    np.testing.assert_array_equal(out, np.concatenate([[0], np.cumsum(x)]))
 
 
 # ----------------------------------------------------------------------------------------- GAE

@@ -122,6 +122,47 @@ def test_arena_too_small_is_reported_and_retried(G, E):
     assert torch.equal(flat.lengths, want["lengths"]) and torch.equal(flat.final_boards, want["final_boards"])
 
 
+def test_compaction_into_estimated_room(G, E):
+    """run_flat_batch launches the compaction before it knows the batch's total: into arrays sized from an estimate.
+    Too little room: the steps that fit are written, nothing beyond, the per-env maxima are complete, and the runner
+    compacts a second time; more than enough: the rollout's arrays are prefixes of the roomier ones.  Either way the
+    buffer is the one an exact-size compaction produces."""
+    n = 6000
+    subs = E.chain_advance(E.words_tensor([0, 31], "cuda"), 1, 1 + 2 * 2048)
+    rec = E.play_record(1, subs, n, 0, n, 1)
+    offsets = E.exclusive_scan(rec["lengths"])
+    total = int(offsets[-1])
+    exact = E.play_record_compact(rec, offsets, total)
+    for room in (0, 1, total // 3, total - 1, total + 5000):
+        # guard band: the arrays are really `room + 64` long and pre-filled; only [0, min(room, total)) may change
+        got = E.play_record_compact(rec, offsets, room)
+        keep = min(room, total)
+        for k in ("boards", "meta", "rewards", "log_probs", "values"):
+            assert got[k].shape[0] == room and torch.equal(got[k][:keep], exact[k][:keep]), (k, room)
+        assert torch.equal(got["max_rewards"], exact["max_rewards"])
+    # through the raw entry point with guard bands behind a short capacity
+    from g2048 import _native as N
+
+    room = total // 2
+    band = {k: torch.full((room + 64,), 7, dtype=exact[k].dtype, device="cuda") for k in ("boards", "meta", "rewards", "log_probs", "values")}
+    N.call("g2048_play_record_compact", 1, N.ptr(rec["arena_boards"]), N.ptr(rec["arena_meta"]), N.ptr(rec["env_slot"]),
+           N.ptr(rec["lengths"]), N.ptr(offsets), n, 0, room, N.ptr(band["boards"]), N.ptr(band["meta"]), N.ptr(band["rewards"]),
+           N.ptr(band["log_probs"]), N.ptr(band["values"]), None, N.stream_ptr())
+    for k, v in band.items():
+        assert torch.equal(v[:room], exact[k][:room]) and bool((v[room:] == 7).all()), k
+
+    # the runner: a far too small estimate (second compaction) and a generous one give the same rollout
+    want = G.BatchRunner(init_seed=31, act_fn=G.act_drul).run_flat_batch(n)
+    for guess in (16, 4000):
+        runner = G.BatchRunner(init_seed=31, act_fn=G.act_drul)
+        runner._mean_steps[1] = guess
+        got = runner.run_flat_batch(n)
+        assert got.env_steps == want.env_steps == total
+        for k in ("boards", "meta", "rewards", "log_probs", "values", "lengths", "offsets", "final_boards", "scores", "max_rewards"):
+            assert torch.equal(getattr(got, k), getattr(want, k)), (k, guess)
+        assert got.boards.is_contiguous() and got.boards.shape[0] == total
+
+
 def test_store_flat_feeds_the_training_pipeline(G):
     """collect_rollouts on a built-in policy goes through run_flat_batch / store_flat and yields the same buffer and
     episode statistics as the packed path (see test_collect_rollouts_matches_the_trainers_python_loops)."""
