@@ -58,13 +58,43 @@ class KeyChain:
         self._base_pos = 0  # number of splits consumed so far
         self._subs = torch.empty((0, 2), dtype=torch.int32, device=self.device)  # subs from _base_pos on
         self._tip = E.words_tensor(words, self.device)  # chain key after all generated subs
+        # Generation runs on a stream of its own: the chain is one thread working through ~0.14 us per split, so the
+        # keys of the NEXT batch are produced while the current batch's kernels run (a block ahead at all times) and
+        # only a chain that starts cold is waited for.  _ahead: blocks generated (or being generated) but not yet
+        # joined to _subs, oldest first, each with the event that marks it complete.
+        self._side = None
+        self._ahead: list[tuple[torch.Tensor, torch.cuda.Event]] = []
+
+    def _generate(self, count: int) -> None:
+        """Queue `count` more sub keys on the side stream (ordered behind every earlier block: they share _tip)."""
+        if self._side is None:
+            self._side = torch.cuda.Stream(device=self.device)
+            self._side.wait_stream(torch.cuda.current_stream(self.device))  # _tip was written on the caller's stream
+            # ... and from now on is read and written by kernels of the side stream only: the allocator must not hand
+            # its memory to somebody else while one of them is still running (a chain that is dropped right after its
+            # last batch, e.g. one runner per seed in a loop, leaves a generation in flight)
+            self._tip.record_stream(self._side)
+        with torch.cuda.stream(self._side):
+            block = E.chain_advance(self._tip, self.rng_mode, count)
+            done = torch.cuda.Event()
+            done.record(self._side)
+        self._ahead.append((block, done))
 
     def peek(self, n: int) -> torch.Tensor:
-        have = self._subs.shape[0]
-        if n > have:
-            extra = max(n - have, self.BLOCK)
-            new = E.chain_advance(self._tip, self.rng_mode, extra)
-            self._subs = torch.cat([self._subs, new]) if have else new
+        capturing = torch.cuda.is_current_stream_capturing()
+        current = torch.cuda.current_stream(self.device)
+        while n > self._subs.shape[0]:
+            if not self._ahead:
+                if capturing:
+                    raise RuntimeError("KeyChain.peek inside a CUDA graph capture needs keys that were not generated yet: peek them before the capture")
+                self._generate(n - self._subs.shape[0])
+            block, done = self._ahead.pop(0)
+            current.wait_event(done)
+            block.record_stream(current)
+            self._subs = torch.cat([self._subs, block]) if self._subs.shape[0] else block
+        ahead = self._subs.shape[0] - n + sum(b.shape[0] for b, _ in self._ahead)
+        if not capturing and ahead < max(n, self.BLOCK // 2):  # keep about one more request's worth in the pipeline
+            self._generate(max(n, self.BLOCK))
         return self._subs[:n]
 
     def consume(self, n: int) -> None:

@@ -957,7 +957,8 @@ def c4_iteration(E, N, torch, dev, hbm_peak) -> dict:
                         f"minibatches of {minibatch}"}
     # -- rollout + store: the recording play kernel writes the buffer's own layout (run_flat_batch -> store_flat) --------
     runner = g2048.BatchRunner(init_seed=4, act_fn=g2048.act_randomly)
-    runner.run_flat_batch(n_envs)  # warm-up at full size: allocator, table build, arena sizing hint, key chain generated ahead
+    for _ in range(3):  # warm-up at full size: allocator, table build, arena sizing hint, key chain a block ahead, torch's lazily loaded kernels
+        runner.run_flat_batch(n_envs)
     key_before = runner.key  # the chain key the timed batch starts from (for the oracle replay below)
     buf = g2048.RolloutBuffer(31, 16, 4)
     flat, t_flat = wall(lambda: runner.run_flat_batch(n_envs))

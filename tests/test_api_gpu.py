@@ -611,3 +611,33 @@ def test_pinned_outputs_are_the_same_arrays_in_page_locked_memory(G):
     assert obs.nbytes >= 1 << 20 and torch.from_numpy(obs).is_pinned() and not torch.from_numpy(plain[0]).is_pinned()
     obs[0, 0] = False  # writable
     assert not obs[0, 0].any() and plain[0][0, 0].any()
+
+
+def test_key_chain_generated_ahead_is_the_same_chain(G):
+    """KeyChain produces its sub keys on a side stream, a block ahead of the consumer: any sequence of peeks and
+    consumes sees the keys of one synchronous generation, also when chains are created and dropped in a loop while
+    their last generation is still in flight (the dropped chain's memory must not be reused under it)."""
+    from g2048 import engine as E
+    from g2048.keys import KeyChain
+
+    rng = np.random.default_rng(0)
+    for mode in (0, 1):
+        ref = E.chain_advance(E.words_tensor([0, 7], "cuda"), mode, 150_000).cpu()
+        chain, pos = KeyChain(7, mode), 0
+        for _ in range(40):
+            n = int(rng.integers(1, 9000))
+            assert torch.equal(chain.peek(n).cpu(), ref[pos:pos + n])
+            k = int(rng.integers(0, n + 1))
+            chain.consume(k)
+            pos += k
+        assert chain.position == pos
+        want_key = E.words_tensor([0, 7], "cuda")
+        E.chain_advance(want_key, mode, pos)
+        assert np.array_equal(chain.key, E.words_numpy(want_key))
+    # churn: a fresh chain per iteration, dropped with a generation in flight; every one must still be right
+    first = E.chain_advance(E.words_tensor([0, 9], "cuda"), 1, 300).cpu()
+    for _ in range(200):
+        got = KeyChain(9, 1).peek(300)
+        junk = torch.full((64,), -1, dtype=torch.int32, device="cuda")  # takes freed blocks of the main stream's pool
+        assert torch.equal(got.cpu(), first)
+        del junk
