@@ -34,6 +34,19 @@ def split(k, num: int = 2, rng_mode=None) -> torch.Tensor:
     return E.split_keys(k, num, 0, num, E.resolve_rng_mode(rng_mode))
 
 
+_SIDE_STREAMS: dict = {}  # device index -> the stream every KeyChain of that device generates on
+
+
+def _side_stream(device: torch.device) -> torch.cuda.Stream:
+    """A stream is not free the first time it is used (the driver sets it up at its first launch, a millisecond or
+    two), and torch hands out a different pooled stream per request: one per device, created once, serves all."""
+    index = device.index if device.index is not None else torch.cuda.current_device()
+    stream = _SIDE_STREAMS.get(index)
+    if stream is None:
+        stream = _SIDE_STREAMS[index] = torch.cuda.Stream(device=device)
+    return stream
+
+
 class KeyChain:
     """The runner's ``key, sub = split(key)`` chain, generated ahead of time on the device.
 
@@ -44,7 +57,8 @@ class KeyChain:
     after the run).  ``key`` is the chain key the reference's runner would hold now.
     """
 
-    BLOCK = 8192
+    BLOCK = 8192       # sub keys generated ahead per request once the chain is in steady use
+    COLD_BLOCK = 2048  # least number generated when a peek has to wait for them (1 + 2 * 1 023 loop steps: ~0.3 ms)
 
     def __init__(self, seed_or_key, rng_mode: int, device=None):
         self.device = N.require_cuda() if device is None else torch.device(device)
@@ -58,21 +72,23 @@ class KeyChain:
         self._base_pos = 0  # number of splits consumed so far
         self._subs = torch.empty((0, 2), dtype=torch.int32, device=self.device)  # subs from _base_pos on
         self._tip = E.words_tensor(words, self.device)  # chain key after all generated subs
-        # Generation runs on a stream of its own: the chain is one thread working through ~0.14 us per split, so the
-        # keys of the NEXT batch are produced while the current batch's kernels run (a block ahead at all times) and
-        # only a chain that starts cold is waited for.  _ahead: blocks generated (or being generated) but not yet
-        # joined to _subs, oldest first, each with the event that marks it complete.
+        # Generation runs on a stream of its own (one per device, shared by every chain): the chain is one thread
+        # working through ~0.14 us per split, so once a chain has been consumed from -- a runner that is asked for a
+        # second batch -- the keys of the NEXT batch are produced while the current batch's kernels run, a block ahead
+        # at all times, and only a chain that starts cold is waited for.  _ahead: blocks generated (or being generated)
+        # but not yet joined to _subs, oldest first, each with the event that marks it complete.
         self._side = None
+        self._reused = False
         self._ahead: list[tuple[torch.Tensor, torch.cuda.Event]] = []
 
     def _generate(self, count: int) -> None:
         """Queue `count` more sub keys on the side stream (ordered behind every earlier block: they share _tip)."""
         if self._side is None:
-            self._side = torch.cuda.Stream(device=self.device)
+            self._side = _side_stream(self.device)
             self._side.wait_stream(torch.cuda.current_stream(self.device))  # _tip was written on the caller's stream
             # ... and from now on is read and written by kernels of the side stream only: the allocator must not hand
             # its memory to somebody else while one of them is still running (a chain that is dropped right after its
-            # last batch, e.g. one runner per seed in a loop, leaves a generation in flight)
+            # last batch leaves a generation in flight)
             self._tip.record_stream(self._side)
         with torch.cuda.stream(self._side):
             block = E.chain_advance(self._tip, self.rng_mode, count)
@@ -87,14 +103,15 @@ class KeyChain:
             if not self._ahead:
                 if capturing:
                     raise RuntimeError("KeyChain.peek inside a CUDA graph capture needs keys that were not generated yet: peek them before the capture")
-                self._generate(n - self._subs.shape[0])
+                self._generate(max(n - self._subs.shape[0], self.COLD_BLOCK))
             block, done = self._ahead.pop(0)
             current.wait_event(done)
             block.record_stream(current)
             self._subs = torch.cat([self._subs, block]) if self._subs.shape[0] else block
-        ahead = self._subs.shape[0] - n + sum(b.shape[0] for b, _ in self._ahead)
-        if not capturing and ahead < max(n, self.BLOCK // 2):  # keep about one more request's worth in the pipeline
-            self._generate(max(n, self.BLOCK))
+        if self._reused and not capturing:
+            ahead = self._subs.shape[0] - n + sum(b.shape[0] for b, _ in self._ahead)
+            if ahead < max(n, self.BLOCK // 2):  # keep about one more request's worth in the pipeline
+                self._generate(max(n, self.BLOCK))
         return self._subs[:n]
 
     def consume(self, n: int) -> None:
@@ -106,6 +123,7 @@ class KeyChain:
         self._pending += n
         self._base_pos += n
         self._subs = self._subs[n:]
+        self._reused = True
 
     def next_sub(self) -> torch.Tensor:
         sub = self.peek(1)[0].clone()
