@@ -627,6 +627,23 @@ def test_unpack_and_compact_match_reference_rollout_buffer(E, golden_ppo):
     np.testing.assert_array_equal(term.cpu().numpy(), g["rb_out_terminations"][:k])
 
 
+@pytest.mark.parametrize("t_steps", [1, 15, 16, 17, 33, 200])
+def test_episode_lengths_first_done(E, t_steps):
+    """first done + 1 per env of time-major meta bytes (bit 6), 0 for an env that never terminates; the kernel reads
+    16 steps per round trip, so the step counts straddle its batch size."""
+    rng = np.random.default_rng(t_steps)
+    n = 1000
+    meta = rng.integers(0, 64, (t_steps, n)).astype(np.uint8)  # bits 0-5 arbitrary, bit 6 clear
+    first = rng.integers(0, t_steps + 1, n)  # t_steps = never
+    for e in range(n):
+        if first[e] < t_steps:
+            meta[first[e]:, e] |= (rng.random(t_steps - first[e]) < 0.5).astype(np.uint8) << 6  # later flags may be anything
+            meta[first[e], e] |= 0x40
+    want = np.where(first < t_steps, first + 1, 0).astype(np.uint32)
+    got = E.episode_lengths(dev(meta), t_steps, n).cpu().numpy().view(np.uint32)
+    np.testing.assert_array_equal(got, want)
+
+
 @pytest.mark.parametrize("n", [0, 1, 31, 2047, 2048, 2049, 4096, 100_003, 2048 * 1024, 2048 * 1025 + 7, (1 << 24) + 5])
 def test_exclusive_scan_sizes(E, n):
     """Chunked scan (2 048 elements per CTA, chunk sums parked in the output): empty, single element, chunk boundaries,
