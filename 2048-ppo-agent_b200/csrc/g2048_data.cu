@@ -242,7 +242,12 @@ scan_chunks_kernel(const uint32_t* __restrict__ in, int64_t n, long long* __rest
     }
 }
 
-// ragged compaction: flat[out_base + offsets[e] + t] = rec[t][e] for t < lengths[e]
+// ragged compaction: flat[out_base + offsets[e] + t] = rec[t][e] for t < lengths[e].  The records are time-major
+// (consecutive envs are adjacent), the buffer env-major (consecutive steps are adjacent): a transpose.  A CTA moves a
+// tile of 32 envs x 32 steps through shared memory -- rows read along the envs, columns written along the steps --
+// so both sides are whole segments; dead steps (t >= length) are neither read nor written and a tile without a live
+// step returns at once.  (The first form gave each thread one env and let it write its steps one by one: stores
+// 118 elements apart across a warp, 0.7 TB/s on C4's 262 144 x 390 records.)
 __global__ void __launch_bounds__(256)
 compact_records_kernel(const u64* __restrict__ rec_boards, const uint8_t* __restrict__ rec_meta,
                        const float* __restrict__ rec_rewards, const float* __restrict__ rec_log_probs,
@@ -250,19 +255,56 @@ compact_records_kernel(const u64* __restrict__ rec_boards, const uint8_t* __rest
                        const uint32_t* __restrict__ lengths, const long long* __restrict__ offsets, int64_t out_base,
                        u64* __restrict__ boards, uint8_t* __restrict__ meta, float* __restrict__ rewards,
                        float* __restrict__ log_probs, float* __restrict__ values) {
-    const int64_t e = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
-    if (e >= n) return;
-    const int64_t len = lengths[e];
-    const int64_t t_begin = (int64_t)blockIdx.y * 32;
-    const int64_t t_end = min(min(t_begin + 32, t_steps), len);
-    const int64_t dst0 = out_base + offsets[e];
-    for (int64_t t = t_begin; t < t_end; ++t) {
-        const int64_t i = t * n + e, o = dst0 + t;
-        if (boards) boards[o] = rec_boards[i];
-        if (meta) meta[o] = rec_meta[i];
-        if (rewards) rewards[o] = rec_rewards[i];
-        if (log_probs && rec_log_probs) log_probs[o] = rec_log_probs[i];
-        if (values && rec_values) values[o] = rec_values[i];
+    __shared__ u64 s_boards[32][33];
+    __shared__ float s_rewards[32][33], s_log_probs[32][33], s_values[32][33];
+    __shared__ uint8_t s_meta[32][36];
+    __shared__ uint32_t s_len[32];
+    __shared__ long long s_dst[32];
+    __shared__ uint32_t s_any;
+    const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
+    const int64_t e0 = (int64_t)blockIdx.x * 32, t0 = (int64_t)blockIdx.y * 32;
+    if (warp == 0) {
+        const int64_t e = e0 + lane;
+        const uint32_t len = e < n ? (uint32_t)min((int64_t)lengths[e], t_steps) : 0u;  // never past the recorded steps
+        s_len[lane] = len;
+        s_dst[lane] = e < n ? out_base + offsets[e] : 0;
+        const unsigned live = __ballot_sync(0xFFFFFFFFu, (int64_t)len > t0);
+        if (lane == 0) s_any = live;
+    }
+    __syncthreads();
+    if (s_any == 0u) return;  // every env of the tile ended before its first step
+    const bool has_lp = log_probs && rec_log_probs, has_v = values && rec_values;
+    {   // rows of the tile: lane = env
+        const int64_t e = e0 + lane;
+        const int64_t len = s_len[lane];
+#pragma unroll
+        for (int k = 0; k < 4; ++k) {
+            const int r = warp + 8 * k;
+            const int64_t t = t0 + r;
+            if (t < len) {  // implies e < n and t < t_steps
+                const int64_t i = t * n + e;
+                if (boards) s_boards[r][lane] = rec_boards[i];
+                if (meta) s_meta[r][lane] = rec_meta[i];
+                if (rewards) s_rewards[r][lane] = rec_rewards[i];
+                if (has_lp) s_log_probs[r][lane] = rec_log_probs[i];
+                if (has_v) s_values[r][lane] = rec_values[i];
+            }
+        }
+    }
+    __syncthreads();
+    // columns of the tile: lane = step
+#pragma unroll
+    for (int k = 0; k < 4; ++k) {
+        const int c = warp + 8 * k;
+        const int64_t t = t0 + lane;
+        if (t < (int64_t)s_len[c]) {
+            const int64_t o = s_dst[c] + t;
+            if (boards) boards[o] = s_boards[lane][c];
+            if (meta) meta[o] = s_meta[lane][c];
+            if (rewards) rewards[o] = s_rewards[lane][c];
+            if (has_lp) log_probs[o] = s_log_probs[lane][c];
+            if (has_v) values[o] = s_values[lane][c];
+        }
     }
 }
 
@@ -492,7 +534,7 @@ extern "C" int g2048_compact_records(const uint64_t* d_rec_boards, const uint8_t
     G2048_REQUIRE(d_lengths && d_offsets, "compact_records: lengths/offsets");
     G2048_REQUIRE((!d_boards || d_rec_boards) && (!d_meta || d_rec_meta) && (!d_rewards || d_rec_rewards),
                   "compact_records: sources");
-    const dim3 grid(blocks_for(n, 256), (unsigned)((t_steps + 31) / 32));
+    const dim3 grid(blocks_for(n, 32), (unsigned)((t_steps + 31) / 32));
     G2048_REQUIRE(grid.y <= 65535u, "compact_records: too many steps");
     compact_records_kernel<<<grid, 256, 0, (cudaStream_t)stream>>>(
         (const u64*)d_rec_boards, d_rec_meta, d_rec_rewards, d_rec_log_probs, d_rec_values, t_steps, n, d_lengths,
