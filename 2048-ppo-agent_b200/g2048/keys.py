@@ -57,8 +57,8 @@ class KeyChain:
     after the run).  ``key`` is the chain key the reference's runner would hold now.
     """
 
-    BLOCK = 8192       # sub keys generated ahead per request once the chain is in steady use
     COLD_BLOCK = 2048  # least number generated when a peek has to wait for them (1 + 2 * 1 023 loop steps: ~0.3 ms)
+    TOP_UP = 256       # least number generated behind a consume
 
     def __init__(self, seed_or_key, rng_mode: int, device=None):
         self.device = N.require_cuda() if device is None else torch.device(device)
@@ -67,18 +67,19 @@ class KeyChain:
             words = np.array(E.key_words(int(seed_or_key)), dtype=np.uint32)
         else:
             words = np.asarray(seed_or_key, dtype=np.uint32).reshape(2).copy()
-        self._base_key = words  # chain key at absolute position self._base_pos - self._pending
-        self._pending = 0  # splits consumed since _base_key was last materialised (see `key`)
+        self._base_key = words  # chain key at absolute position self._base_pos - self._replay
+        self._replay = 0  # splits consumed since _base_key was last materialised (see `key`)
         self._base_pos = 0  # number of splits consumed so far
         self._subs = torch.empty((0, 2), dtype=torch.int32, device=self.device)  # subs from _base_pos on
         self._tip = E.words_tensor(words, self.device)  # chain key after all generated subs
         # Generation runs on a stream of its own (one per device, shared by every chain): the chain is one thread
-        # working through ~0.14 us per split, so once a chain has been consumed from -- a runner that is asked for a
-        # second batch -- the keys of the NEXT batch are produced while the current batch's kernels run, a block ahead
-        # at all times, and only a chain that starts cold is waited for.  _ahead: blocks generated (or being generated)
-        # but not yet joined to _subs, oldest first, each with the event that marks it complete.
+        # working through ~0.14 us per split -- for a batch of a thousand envs that is a fifth of the play kernel's own
+        # time -- so the keys a batch consumes are replaced while the next batches run: every consume(k) queues the
+        # generation of k more, two consumes ahead of the peek that will need them, and only a chain that starts cold is
+        # waited for (plus a quarter more, queued behind it, that covers the first consume).  _ahead: blocks generated
+        # (or being generated) but not yet joined to _subs, oldest first, each with the event that marks it complete.
         self._side = None
-        self._reused = False
+        self._window = 0  # the largest peek since the last consume: what the next batch will want to see again
         self._ahead: list[tuple[torch.Tensor, torch.cuda.Event]] = []
 
     def _generate(self, count: int) -> None:
@@ -96,22 +97,24 @@ class KeyChain:
             done.record(self._side)
         self._ahead.append((block, done))
 
+    def _pending(self) -> int:
+        return sum(block.shape[0] for block, _ in self._ahead)
+
     def peek(self, n: int) -> torch.Tensor:
         capturing = torch.cuda.is_current_stream_capturing()
         current = torch.cuda.current_stream(self.device)
+        self._window = max(self._window, n)
         while n > self._subs.shape[0]:
             if not self._ahead:
                 if capturing:
                     raise RuntimeError("KeyChain.peek inside a CUDA graph capture needs keys that were not generated yet: peek them before the capture")
-                self._generate(max(n - self._subs.shape[0], self.COLD_BLOCK))
+                count = max(n - self._subs.shape[0], self.COLD_BLOCK)
+                self._generate(count)       # the caller waits for this one ...
+                self._generate(count // 4)  # ... and this one is ready by the time it has consumed some
             block, done = self._ahead.pop(0)
             current.wait_event(done)
             block.record_stream(current)
             self._subs = torch.cat([self._subs, block]) if self._subs.shape[0] else block
-        if self._reused and not capturing:
-            ahead = self._subs.shape[0] - n + sum(b.shape[0] for b, _ in self._ahead)
-            if ahead < max(n, self.BLOCK // 2):  # keep about one more request's worth in the pipeline
-                self._generate(max(n, self.BLOCK))
         return self._subs[:n]
 
     def consume(self, n: int) -> None:
@@ -119,11 +122,17 @@ class KeyChain:
         chain key itself (``key``) is only replayed when somebody asks for it."""
         if n <= 0:
             return
+        window = self._window
         self.peek(n)
-        self._pending += n
+        self._replay += n
         self._base_pos += n
         self._subs = self._subs[n:]
-        self._reused = True
+        self._window = 0
+        # top up behind the consumer, two consumes deep: the block the next batch has to join was then queued a whole
+        # batch ago and is complete (one deep, it would have been queued microseconds before that batch asks for it)
+        short = window + 2 * n - (self._subs.shape[0] + self._pending())
+        if short > 0 and not torch.cuda.is_current_stream_capturing():
+            self._generate(max(short, self.TOP_UP))
 
     def next_sub(self) -> torch.Tensor:
         sub = self.peek(1)[0].clone()
@@ -134,11 +143,11 @@ class KeyChain:
     def key(self) -> np.ndarray:
         """The chain key after everything consumed so far (the reference runner's ``self.key``): replayed from the last
         materialised key over the pending splits -- one small kernel and one 8-byte read, off the rollout's path."""
-        if self._pending:
+        if self._replay:
             base = E.words_tensor(self._base_key, self.device)
-            E.chain_advance(base, self.rng_mode, self._pending)
+            E.chain_advance(base, self.rng_mode, self._replay)
             self._base_key = E.words_numpy(base).copy()
-            self._pending = 0
+            self._replay = 0
         return self._base_key.copy()
 
     @property

@@ -934,10 +934,13 @@ def c4_iteration(E, N, torch, dev, hbm_peak) -> dict:
     mode = E.RNG_PARTITIONABLE
 
     def wall(fn):
+        # from an idle device to the call's results being complete on the caller's stream.  (Not a device-wide
+        # synchronisation at the end: the runner's key chain tops itself up on a side stream after every batch -- one
+        # thread, ~0.1 ms, next to whatever the caller launches next -- and that is not part of this call's latency.)
         torch.cuda.synchronize()
         t0 = time.perf_counter()
         out = fn()
-        torch.cuda.synchronize()
+        torch.cuda.current_stream().synchronize()
         return out, time.perf_counter() - t0
 
     def dev_time(fn, reps=3):
