@@ -593,13 +593,13 @@ int play_record_impl(int policy, const uint32_t* d_subs, int64_t n_subs, int64_t
 
 // One warp per env: the episode's slot range -> its segment of the flat buffer (9 B read + up to 21 B written per
 // env-step).  A warp takes 128 steps per iteration -- the mean episode is about that long -- with every load of the
-// iteration issued before the first use.  The first form executed 158 instructions per lane-step, a third of them
+// iteration issued before the first use.  The first form executed 171 instructions per lane-step (ncu), many of them
 // predication (loads guarded by t <= len, five null tests per store group, shuffles inside divergent code); this one
 // clamps the load indices instead (slot `len` holds the final board, so every address is valid), keeps the shuffles
 // in uniform code, tests t < len once, and is compiled a second time for callers that want every output (ALL: the
-// product path) without the pointer tests: 90 instructions per lane-step -- and 249 instead of 255 us for C4's
+// product path) without the pointer tests: 139 instructions per lane-step -- and 249 instead of 255 us for C4's
 // 3.1e7 steps, so instructions were not what bounds it.  Neither are the three other things ncu
-// (gpurun_out r02_compact: l1tex 70 %, long_scoreboard 12.7 per issue, DRAM 45 %) suggested, each built and timed:
+// (profiles/r02_compact_ncu.txt: l1tex 70 %, long_scoreboard 12.7 per issue, DRAM 45 %) suggested, each built and timed:
 // see the notes in the body.  What is left is the access pattern itself -- seven streams of 0.1 - 1 KB chunks per
 // env, the reads scattered over the lanes' arena regions -- at 3.7 TB/s.
 template <int POLICY, bool ALL>
