@@ -9,6 +9,7 @@
 // 9 B read + 8 B written per step.
 #include "g2048_common.cuh"
 #include "g2048_hostcopy.cuh"
+#include "g2048_tma.cuh"
 
 namespace g2048 {
 
@@ -315,6 +316,109 @@ gae_time_major_kernel(const float* __restrict__ rewards, const float* __restrict
     }
 }
 
+// The same recurrence fed through a bulk-copy ring (round 2, last form).  What bounds the kernel above at C3 is not
+// bandwidth but phases: a lane issues 16 steps' loads, waits a DRAM round trip, computes, stores, and only then asks
+// for the next 16 -- all 14 warps of an SM in step with each other -- so DRAM sees bursts (ncu: 23 us of kernel for
+// 95 MB, the launch's own 47 MB of dirty lines written back behind it).  Here a CTA of 128 lanes owns 128 envs and
+// its first warp keeps THREE stages of 16 rows (rewards, values, meta: 18 KiB a stage) in flight through cp.async.bulk,
+// one 512- or 128-byte row per copy (a lane per row), completion on an mbarrier per stage; the lanes walk a stage from shared memory while
+// the copy engine fills the other two, so loads, arithmetic and stores overlap without a register for any of it.
+// Same fp32 operation order per env: bit-identical.  Needs n % 128 == 0 and 16-byte aligned rows (else the kernel above).
+// Measured (tools/probes/tm_ring_probe.py, C3 / 4 x C3, steady state): one lane per env 33.7 / 110 us; ring with 64-env
+// CTAs 33.6 / 106; 128-env CTAs 29.5 / 103 (longer rows: fewer DRAM pages per byte); 32 rows a stage 43 / 133.
+#ifndef G2048_TM_RING_ROWS
+#define G2048_TM_RING_ROWS 16
+#endif
+#ifndef G2048_TM_RING_ENVS
+#define G2048_TM_RING_ENVS 128
+#endif
+constexpr int GAE_RING_ROWS = G2048_TM_RING_ROWS;
+constexpr int GAE_RING_STAGES = 3;
+constexpr int GAE_RING_ENVS = G2048_TM_RING_ENVS;
+static_assert(GAE_RING_ENVS % 32 == 0 && GAE_RING_ENVS <= 128, "block_sum4 reduces at most four warps");
+struct GaeRingStage {
+    float r[GAE_RING_ROWS][GAE_RING_ENVS];
+    float v[GAE_RING_ROWS][GAE_RING_ENVS];
+    uint8_t d[GAE_RING_ROWS][GAE_RING_ENVS];
+};
+
+__global__ void __launch_bounds__(GAE_RING_ENVS)
+gae_time_major_ring_kernel(const float* __restrict__ rewards, const float* __restrict__ values,
+                           const uint8_t* __restrict__ meta, int64_t t_steps, int64_t n,
+                           const float* __restrict__ bootstrap, float gamma, float gamma_lambda, float* __restrict__ adv,
+                           float* __restrict__ ret, double* __restrict__ moments) {
+    extern __shared__ __align__(128) uint8_t ring_smem[];
+    GaeRingStage* stages = reinterpret_cast<GaeRingStage*>(ring_smem);
+    __shared__ __align__(8) uint64_t s_full[GAE_RING_STAGES];
+    __shared__ double s_red[16];
+    const int64_t e0 = (int64_t)blockIdx.x * GAE_RING_ENVS;
+    const int64_t e = e0 + threadIdx.x;
+    const int64_t n_batches = (t_steps + GAE_RING_ROWS - 1) / GAE_RING_ROWS;
+    if (threadIdx.x == 0) {
+        for (int k = 0; k < GAE_RING_STAGES; ++k) mbar_init(&s_full[k], 1);
+        fence_proxy_async();  // the initialised barriers -> visible to the copy engine
+    }
+    __syncthreads();
+    // batch b (0 = the newest steps) holds rows [lo, hi), hi = T - 16 b; row t sits at index t - lo of its stage
+    auto issue = [&](int64_t b) {  // warp 0: lane 0 announces the stage's bytes, then one row per lane
+        if (b >= n_batches) return;
+        const int64_t hi = t_steps - b * GAE_RING_ROWS, lo = hi > GAE_RING_ROWS ? hi - GAE_RING_ROWS : 0;
+        const int stage = (int)(b % GAE_RING_STAGES);
+        GaeRingStage& st = stages[stage];
+        if (threadIdx.x == 0) mbar_arrive_expect_tx(&s_full[stage], (uint32_t)((hi - lo) * (GAE_RING_ENVS * 9)));
+        __syncwarp();
+        for (int64_t t = lo + threadIdx.x; t < hi; t += 32) {
+            const int64_t row = t * n + e0;
+            bulk_load(st.r[t - lo], rewards + row, GAE_RING_ENVS * 4, &s_full[stage]);
+            bulk_load(st.v[t - lo], values + row, GAE_RING_ENVS * 4, &s_full[stage]);
+            bulk_load(st.d[t - lo], meta + row, GAE_RING_ENVS, &s_full[stage]);
+        }
+    };
+    if (threadIdx.x < 32) {
+        issue(0);
+        issue(1);
+    }
+    double m[4] = {0.0, 0.0, 0.0, 0.0};
+    float last_v = bootstrap ? bootstrap[e] : 0.0f;
+    float last_gae = 0.0f;
+    for (int64_t b = 0; b < n_batches; ++b) {
+        // two batches ahead: that stage was last read in batch b - 1, before the barrier that ended it
+        if (threadIdx.x < 32) issue(b + 2);
+        const int64_t hi = t_steps - b * GAE_RING_ROWS, lo = hi > GAE_RING_ROWS ? hi - GAE_RING_ROWS : 0;
+        const int stage = (int)(b % GAE_RING_STAGES);
+        const GaeRingStage& st = stages[stage];
+        mbar_wait(&s_full[stage], (uint32_t)((b / GAE_RING_STAGES) & 1));
+        float* pa = adv + (hi - 1) * n + e;
+        float* pr = ret + (hi - 1) * n + e;
+        for (int k = (int)(hi - lo) - 1; k >= 0; --k) {
+            // one step of the reference's loop (data_loader.py:110-128) in its fp32 order, as in gae_time_major_kernel
+            const float r = st.r[k][threadIdx.x], v = st.v[k][threadIdx.x];
+            if (st.d[k][threadIdx.x] & 0x40u) {
+                last_v = 0.0f;
+                last_gae = 0.0f;
+            }
+            const float delta = (r + gamma * last_v) - v;
+            last_gae = delta + gamma_lambda * last_gae;
+            const float rt = last_gae + v;
+            __stcs(pa, last_gae);
+            __stcs(pr, rt);
+            last_v = v;
+            const double da = (double)last_gae, dr = (double)rt;
+            m[0] += da;
+            m[1] = __fma_rn(da, da, m[1]);
+            m[2] += dr;
+            m[3] = __fma_rn(dr, dr, m[3]);
+            pa -= n;
+            pr -= n;
+        }
+        __syncthreads();  // every lane is done with this stage: warp 0 may refill it at the top of the next batch
+    }
+    if (moments) {
+        block_sum4(m, s_red, moments);
+        if (threadIdx.x == 0) atomicAdd(&moments[0], (double)(GAE_RING_ENVS * t_steps));
+    }
+}
+
 // The same recurrence with the LOADS of a CTA's envs spread over four warps (round 2).  One lane per env leaves 13 warps
 // per SM at C3 (65 536 envs), each walking 128 steps with 16 loads in flight: 0.64 of HBM.  Here a CTA is 32 envs x 4
 // warps: all four fetch a 128-step chunk of the CTA's envs into shared memory (36 KiB: every load of the chunk is in
@@ -489,6 +593,27 @@ extern "C" int g2048_gae_time_major(const float* d_rewards, const float* d_value
             *configured = true;
         }
         gae_time_major_split_kernel<<<blocks_for(n, 32), 32 * GAE_TS_WARPS, smem, (cudaStream_t)stream>>>(
+            d_rewards, d_values, d_rec_meta, t_steps, n, d_bootstrap, (float)gamma, (float)(gamma * lambda_gae), d_adv, d_ret,
+            d_moments);
+        G2048_CHECK_LAUNCH("gae_time_major");
+        return G2048_OK;
+    }
+    // the bulk-copy ring form: whole CTAs of 128 envs, rows that the copy engine can address (16-byte aligned)
+    static const bool ring = [] { const char* e = getenv("G2048_GAE_TM_RING"); return !(e && e[0] == '0'); }();
+    const uintptr_t align_bits = (uintptr_t)d_rewards | (uintptr_t)d_values | (uintptr_t)d_rec_meta;
+    if (ring && n % GAE_RING_ENVS == 0 && (align_bits & 15u) == 0) {
+        static bool ring_configured_on[64] = {false};
+        bool* configured = device_once_flag(ring_configured_on);
+        if (!configured) return fail_arg("no CUDA device");
+        if (!*configured) {
+            int rc = check_cuda(cudaFuncSetAttribute(gae_time_major_ring_kernel, cudaFuncAttributePreferredSharedMemoryCarveout,
+                                                     cudaSharedmemCarveoutMaxShared), "gae_time_major: carveout");
+            if (!rc) rc = check_cuda(cudaFuncSetAttribute(gae_time_major_ring_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize,
+                                                          GAE_RING_STAGES * (int)sizeof(GaeRingStage)), "gae_time_major: shared memory attribute");
+            if (rc) return rc;
+            *configured = true;
+        }
+        gae_time_major_ring_kernel<<<(unsigned)(n / GAE_RING_ENVS), GAE_RING_ENVS, GAE_RING_STAGES * sizeof(GaeRingStage), (cudaStream_t)stream>>>(
             d_rewards, d_values, d_rec_meta, t_steps, n, d_bootstrap, (float)gamma, (float)(gamma * lambda_gae), d_adv, d_ret,
             d_moments);
     } else

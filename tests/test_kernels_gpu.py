@@ -698,9 +698,11 @@ def test_gae_flat_matches_oracle_at_scale(E, n, done_rate, entry):
     np.testing.assert_allclose(m[4], (want_r.astype(np.float64) ** 2).sum(), rtol=1e-9)
 
 
-def test_gae_time_major_matches_oracle_per_env(E):
-    rng = np.random.default_rng(47)
-    t_steps, n = 37, 3000
+@pytest.mark.parametrize("t_steps,n", [(37, 3000), (37, 2944), (1, 128), (16, 128), (17, 1024), (48, 256), (129, 2944)])
+def test_gae_time_major_matches_oracle_per_env(E, t_steps, n):
+    """n a multiple of 128 takes the bulk-copy ring kernel (stages of 16 rows: step counts below, at and across the stage
+    size and the ring depth), anything else one lane per env with register-batched loads; both bit-identical."""
+    rng = np.random.default_rng(47 + t_steps)
     r = (rng.integers(0, 16, (t_steps, n)) * 4).astype(np.float32)
     v = rng.standard_normal((t_steps, n)).astype(np.float32)
     d = rng.random((t_steps, n)) < 0.05
@@ -709,7 +711,7 @@ def test_gae_time_major_matches_oracle_per_env(E):
     for bootstrap in (None, boot):
         adv, ret, mom = E.gae_time_major(dev(r), dev(v), dev(meta), t_steps, n, None if bootstrap is None else dev(bootstrap), 0.99, 0.95)
         adv, ret = adv.cpu().numpy(), ret.cpu().numpy()
-        for e in range(0, n, 97):
+        for e in range(0, n, 97 if n > 200 else 7):
             if bootstrap is None:
                 wa, wr = CO.gae(r[:, e], v[:, e], d[:, e], 0.99, 0.95)
             else:  # append the bootstrap state as an extra step and drop it
