@@ -33,13 +33,13 @@ ROWS = [
     ("gae_scan_kernel (opt-in: re-associated reverse scan, 1e-5 relative)", "gae_scan_kernel"),
     ("normalize_kernel", "normalize_kernel"),
     ("gae_flat4_kernel, episode lengths of real play", "gae_flat4_kernel"),
-    ("gae_time_major_kernel", "gae_time_major_kernel"),
-    ("gae_time_major_kernel, 4 x C3", "gae_time_major_kernel"),
+    ("gae_time_major_kernel", "gae_time_major_"),
+    ("gae_time_major_kernel, 4 x C3", "gae_time_major_"),
     ("c4: play_record_compact_kernel", "play_record_compact_kernel"),
     ("c3: policy_step_obs_kernel<float>", "policy_step_obs_kernel"),
 ]
 REGEX = "expand_obs_tma_kernel|gather_samples_tile_kernel|pack_samples_kernel|embed_boards_kernel|embed_grad_partial_kernel|gae_flat4_kernel|gae_scan_kernel|" \
-        "normalize_kernel|gae_time_major_kernel|play_record_compact_kernel|policy_step_obs_kernel"
+        "normalize_kernel|gae_time_major_|play_record_compact_kernel|policy_step_obs_kernel"
 
 
 def run():
