@@ -780,7 +780,8 @@ extern "C" int g2048_gather_samples(const int64_t* d_indices, int64_t m, const G
         const int64_t n_tiles = (m + 31) / 32;
         const int64_t need = (n_tiles + OBS_WARPS - 1) / OBS_WARPS;
         const int64_t cap = (int64_t)sms * 3;  // 3 resident CTAs of 62 KiB per SM
-        const unsigned grid = (unsigned)(need < cap ? need : cap);
+        unsigned grid = (unsigned)(need < cap ? need : cap);
+        if (need > sms && need < cap) grid = (unsigned)(((need + sms - 1) / sms) * sms);  // whole CTAs per SM, as in g2048_policy_step_obs
         cudaStream_t st = (cudaStream_t)stream;
         switch (obs_dtype) {
             case G2048_OBS_F32:
