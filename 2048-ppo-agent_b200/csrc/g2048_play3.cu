@@ -197,6 +197,13 @@ __device__ __forceinline__ uint32_t play3_legal(const uint8_t* s_flags, u64 b, u
 }
 
 // One loop iteration of a lane that holds an env: a game step, or one of the two init spawns.
+// (The draws of an iteration are a pure function of (env, loop step, phase) -- never of the board -- so they can be made
+// one iteration AHEAD, next to the game logic of the current one; in the drain of a launch, where a scheduler has few
+// warps left, the three Threefry blocks that precede the first look at the board are most of a step's latency.  Built
+// and A/B-timed in round 2, bit-exact, and 14 % slower at 2^24 envs (69.7 -> 81.2 ms), 9 % at 2^18: the env a lane has
+// just claimed needs its first draws on the spot, one or two lanes of a warp at a time, every fourth step -- a whole
+// RNG evaluation per claim at one lane's width.  An extra all-lanes "pre" iteration per episode would avoid that
+// divergence for ~1.5 % more work in the dense phase, which is where the headline number lives; not pursued.)
 template <int MODE, int POLICY, bool REC>
 __device__ __forceinline__ void play3_step(Play3Lane& L, const Play3Ctx& c) {
     // keys: identical to g2048_play.cu
