@@ -663,10 +663,14 @@ static int launch_rollout_steps(int policy, uint64_t* d_boards, uint8_t* d_statu
                   "rollout_steps: pointers");
     const int64_t n_rows = d_env_ids ? n_live : n;
     if (n_rows == 0) return G2048_OK;
-    const unsigned g = blocks_for(n_rows, 256);
+    // one warp per CTA while there are fewer warps than schedulers on the GPU: a small batch is latency-bound, and 1 024
+    // envs as four 256-thread CTAs put eight warps on each of four SMs (see launch_play2)
+    const int sms_now = sm_count();
+    const unsigned threads = (sms_now > 0 && n_rows <= (int64_t)sms_now * 4 * 32) ? 32u : 256u;
+    const unsigned g = blocks_for(n_rows, threads);
     cudaStream_t st = (cudaStream_t)stream;
 #define CALL_P(M, P)                                                                                          \
-    rollout_steps_kernel<M, P><<<g, 256, 0, st>>>((u64*)d_boards, d_status, (const uint2*)d_subs, (int)n_steps,    \
+    rollout_steps_kernel<M, P><<<g, threads, 0, st>>>((u64*)d_boards, d_status, (const uint2*)d_subs, (int)n_steps,    \
                                                   (uint32_t)t0, (uint32_t)batch_global, (uint32_t)env_lo, n,        \
                                                   (u64*)d_rec_boards, d_rec_meta, d_rec_rewards, d_rec_log_probs,   \
                                                   (unsigned long long*)d_counters, d_env_ids, n_rows)

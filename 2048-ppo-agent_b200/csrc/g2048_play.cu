@@ -24,6 +24,55 @@
 namespace g2048 {
 
 constexpr int PLAY2_THREADS = 256;
+// 0 restores round 1's launch for A/B timing: 256-thread CTAs at every batch size
+#ifndef G2048_PLAY2_NARROW
+#define G2048_PLAY2_NARROW 1
+#endif
+
+// The random draws of one loop iteration: the four bit words of the action draw (random policy) and the two of the
+// spawn.  A pure function of (env, loop step, phase) -- the keys come from the launch's sub keys and the env index,
+// never from the board.  (Making them one iteration AHEAD, next to the game logic they do not depend on, was built for
+// launches in which a lane takes one env only: bit-exact, and worth 4 % at one warp per SM with the random policy,
+// nothing with DRUL -- the warp issues in order and the two chains sit in different basic blocks.  Not kept; the
+// same idea in the table kernel, where lanes claim envs all the time, was 14 % slower: see play3_step.)
+struct Play2Draws {
+    uint32_t bits[4];
+    uint32_t pos, val;
+};
+
+template <int MODE, int POLICY>
+__device__ __forceinline__ Play2Draws play2_draws(const uint2* __restrict__ subs, uint2 init_sub, uint32_t batch_global,
+                                                  uint32_t env, uint32_t t, uint32_t phase) {
+    Play2Draws r;
+    const bool playing = phase == PHASE_PLAY;
+    const uint2 ss = __ldg(&subs[2 + 2 * (int64_t)t]);
+    Key kstep;
+    if (POLICY == G2048_POLICY_RANDOM) {
+        const uint2 sa = __ldg(&subs[1 + 2 * (int64_t)t]);
+        const Key head = playing ? Key{sa.x, sa.y} : Key{init_sub.x, init_sub.y};
+        const KeyBlocks<MODE> kb = key_blocks<MODE>(split_at<MODE>(head, batch_global, env));
+#pragma unroll
+        for (int i = 0; i < 4; ++i) r.bits[i] = kb.bits[i];
+        const Key kplay = split_at<MODE>(Key{ss.x, ss.y}, batch_global, env);
+        const Key kinit = (phase == PHASE_INIT0) ? kb.child[0] : kb.child[1];
+        kstep = playing ? kplay : kinit;
+    } else {
+#pragma unroll
+        for (int i = 0; i < 4; ++i) r.bits[i] = 0u;
+        const Key head = playing ? Key{ss.x, ss.y} : Key{init_sub.x, init_sub.y};
+        kstep = split_at<MODE>(head, batch_global, env);
+        if (!playing) {  // r_phase = split(init key)[phase]
+            Key c0, c1;
+            split2<MODE>(kstep, c0, c1);
+            kstep = (phase == PHASE_INIT0) ? c0 : c1;
+        }
+    }
+    Key k1, k2;
+    split2<MODE>(kstep, k1, k2);
+    r.pos = bits_scalar<MODE>(k1);
+    r.val = bits_scalar<MODE>(k2);
+    return r;
+}
 
 template <int MODE, int POLICY>
 __global__ void __launch_bounds__(PLAY2_THREADS)
@@ -76,31 +125,9 @@ play2_kernel(const uint2* __restrict__ subs, int64_t n_subs, uint32_t batch_glob
 
         // ---- one iteration: a game step, or one of the two init spawns ------------------------------
         const bool playing = phase == PHASE_PLAY;
-        const uint2 ss = __ldg(&subs[2 + 2 * (int64_t)t]);
-        int action;
-        Key kstep;
-        if (POLICY == G2048_POLICY_RANDOM) {
-            const uint2 sa = __ldg(&subs[1 + 2 * (int64_t)t]);
-            const Key head = playing ? Key{sa.x, sa.y} : Key{init_sub.x, init_sub.y};
-            const KeyBlocks<MODE> kb = key_blocks<MODE>(split_at<MODE>(head, batch_global, env_lo + e));
-            action = argmax_bits_legal(kb.bits, lm);
-            const Key kplay = split_at<MODE>(Key{ss.x, ss.y}, batch_global, env_lo + e);
-            const Key kinit = (phase == PHASE_INIT0) ? kb.child[0] : kb.child[1];
-            kstep = playing ? kplay : kinit;
-        } else {
-            action = act_drul(lm);
-            const Key head = playing ? Key{ss.x, ss.y} : Key{init_sub.x, init_sub.y};
-            kstep = split_at<MODE>(head, batch_global, env_lo + e);
-            if (!playing) {  // r_phase = split(init key)[phase]
-                Key c0, c1;
-                split2<MODE>(kstep, c0, c1);
-                kstep = (phase == PHASE_INIT0) ? c0 : c1;
-            }
-        }
-        Key k1, k2;
-        split2<MODE>(kstep, k1, k2);
-        const uint32_t bits_pos = bits_scalar<MODE>(k1);
-        const uint32_t bits_val = bits_scalar<MODE>(k2);
+        const Play2Draws d = play2_draws<MODE, POLICY>(subs, init_sub, batch_global, env_lo + e, t, phase);
+        const int action = (POLICY == G2048_POLICY_RANDOM) ? argmax_bits_legal(d.bits, lm) : act_drul(lm);
+        const uint32_t bits_pos = d.pos, bits_val = d.val;
 
         uint32_t unused_reward = 0;
         bool unused_ovf = false;
@@ -160,20 +187,23 @@ template <int MODE, int POLICY>
 static int launch_play2(const uint32_t* d_subs, int64_t n_subs, int64_t batch_global, int64_t env_lo, int64_t n,
                         uint64_t* d_work, uint64_t* d_final_boards, uint32_t* d_lengths, uint32_t* d_scores,
                         uint64_t* d_stats, cudaStream_t st, void* d_results) {
-    int per_sm = 0;
-    int rc = check_cuda(
-        cudaOccupancyMaxActiveBlocksPerMultiprocessor(&per_sm, play2_kernel<MODE, POLICY>, PLAY2_THREADS, 0),
-        "play: occupancy");
-    if (rc) return rc;
     const int sms = sm_count();
-    if (sms <= 0 || per_sm <= 0) return fail_arg("play: no device");
+    if (sms <= 0) return fail_arg("play: no device");
+    // A small batch is all latency: one warp per CTA spreads its warps over the SMs and their schedulers -- 1 024 envs
+    // are 32 SMs with one warp each instead of 4 SMs with eight, two to a scheduler and close to its issue rate
+    // (tools/probes/small_batch_probe.py: 1 024 envs 0.49 -> 0.38 ms, 4 096 envs 0.52 -> 0.38 ms, DRUL 0.70 -> 0.60 ms).
+    const int threads = (G2048_PLAY2_NARROW && n <= (int64_t)sms * 4 * 32) ? 32 : PLAY2_THREADS;
+    int per_sm = 0;
+    int rc = check_cuda(cudaOccupancyMaxActiveBlocksPerMultiprocessor(&per_sm, play2_kernel<MODE, POLICY>, threads, 0),
+                        "play: occupancy");
+    if (rc) return rc;
+    if (per_sm <= 0) return fail_arg("play: no device");
     int64_t grid = (int64_t)sms * per_sm;  // one wave of resident CTAs: the kernel is persistent
-    const int64_t needed = (n + PLAY2_THREADS - 1) / PLAY2_THREADS;
+    const int64_t needed = (n + threads - 1) / threads;
     if (grid > needed) grid = needed;
-    play2_kernel<MODE, POLICY><<<(unsigned)grid, PLAY2_THREADS, 0, st>>>(
-        (const uint2*)d_subs, n_subs, (uint32_t)batch_global, (uint32_t)env_lo, (uint32_t)n,
-        (unsigned long long*)d_work, (u64*)d_final_boards, d_lengths, d_scores, (unsigned long long*)d_stats,
-        (uint4*)d_results);
+    play2_kernel<MODE, POLICY><<<(unsigned)grid, threads, 0, st>>>(
+        (const uint2*)d_subs, n_subs, (uint32_t)batch_global, (uint32_t)env_lo, (uint32_t)n, (unsigned long long*)d_work,
+        (u64*)d_final_boards, d_lengths, d_scores, (unsigned long long*)d_stats, (uint4*)d_results);
     return check_cuda(cudaGetLastError(), "play");
 }
 
