@@ -118,8 +118,9 @@ class KeyChain:
         return self._subs[:n]
 
     def consume(self, n: int) -> None:
-        """Advance by n splits.  Nothing runs on the device: the sub keys were generated ahead by peek(), and the
-        chain key itself (``key``) is only replayed when somebody asks for it."""
+        """Advance by n splits.  Nothing runs on the caller's stream: the sub keys were generated ahead, the chain key
+        itself (``key``) is only replayed when somebody asks for it, and the keys that replace the consumed ones are
+        queued on the generation stream."""
         if n <= 0:
             return
         window = self._window
