@@ -22,6 +22,10 @@ constexpr int OBS_WARPS = OBS_THREADS / 32;
 constexpr int OBS_NBUF = 4;          // images in flight per warp
 constexpr int OBS_IMAGE_BYTES = 1984;  // 496 f32 = 1 board, 992 bf16 = 2 boards, 1984 u8 = 4 boards
 constexpr int OBS_SMEM_BYTES = OBS_WARPS * OBS_NBUF * OBS_IMAGE_BYTES;
+// 0: 256-thread CTAs at every size (A/B timing of the one-warp launches of small batches)
+#ifndef G2048_OBS_NARROW
+#define G2048_OBS_NARROW 1
+#endif
 
 template <typename T> struct ObsOne;
 template <> struct ObsOne<float> { static __device__ float one() { return 1.0f; } static __device__ float zero() { return 0.0f; } };
@@ -543,13 +547,23 @@ extern "C" int g2048_policy_step_obs(uint64_t* d_boards, uint8_t* d_status, cons
     if (need > sms && need < cap) grid = (unsigned)(((need + sms - 1) / sms) * sms);
     static const int grid_override = [] { const char* e = getenv("G2048_PSO_GRID"); return e ? atoi(e) : 0; }();  // probing only
     if (grid_override > 0) grid = (unsigned)(grid_override < n_tiles ? grid_override : n_tiles);
+    // Small batches (fewer tiles than the GPU has schedulers): one warp per CTA, one CTA per tile -- a step of 512 envs
+    // is 16 warps, and as two 8-warp CTAs they share two SMs' schedulers and copy engines; spread out, each has its own.
+    // (The kernel's tile loop visits tile blockIdx + warp * gridDim first: with one warp and gridDim = tiles that is all.)
+    unsigned threads = OBS_THREADS;
+    int smem = OBS_SMEM_BYTES;
+    if (G2048_OBS_NARROW && grid_override <= 0 && n_tiles <= (int64_t)sms * 4) {
+        threads = 32;
+        smem = OBS_NBUF * OBS_IMAGE_BYTES;
+        grid = (unsigned)n_tiles;
+    }
     cudaStream_t st = (cudaStream_t)stream;
 #define G2048_PSO_LAUNCH(T)                                                                                            \
     do {                                                                                                               \
         if (rng_mode == G2048_RNG_PARTITIONABLE)                                                                       \
-            g2048::policy_step_obs_kernel<1, T><<<grid, OBS_THREADS, OBS_SMEM_BYTES, st>>>(args, (T*)d_obs_next);      \
+            g2048::policy_step_obs_kernel<1, T><<<grid, threads, smem, st>>>(args, (T*)d_obs_next);                    \
         else                                                                                                           \
-            g2048::policy_step_obs_kernel<0, T><<<grid, OBS_THREADS, OBS_SMEM_BYTES, st>>>(args, (T*)d_obs_next);      \
+            g2048::policy_step_obs_kernel<0, T><<<grid, threads, smem, st>>>(args, (T*)d_obs_next);                    \
     } while (0)
     switch (obs_dtype) {
         case G2048_OBS_F32: G2048_PSO_LAUNCH(float); break;
@@ -782,16 +796,23 @@ extern "C" int g2048_gather_samples(const int64_t* d_indices, int64_t m, const G
         const int64_t cap = (int64_t)sms * 3;  // 3 resident CTAs of 62 KiB per SM
         unsigned grid = (unsigned)(need < cap ? need : cap);
         if (need > sms && need < cap) grid = (unsigned)(((need + sms - 1) / sms) * sms);  // whole CTAs per SM, as in g2048_policy_step_obs
+        unsigned threads = OBS_THREADS;
+        int smem = OBS_SMEM_BYTES;
+        if (G2048_OBS_NARROW && n_tiles <= (int64_t)sms * 4) {  // a minibatch-sized gather: one warp per CTA, one CTA per tile (see g2048_policy_step_obs)
+            threads = 32;
+            smem = OBS_NBUF * OBS_IMAGE_BYTES;
+            grid = (unsigned)n_tiles;
+        }
         cudaStream_t st = (cudaStream_t)stream;
         switch (obs_dtype) {
             case G2048_OBS_F32:
-                g2048::gather_samples_tile_kernel<float><<<grid, OBS_THREADS, OBS_SMEM_BYTES, st>>>(d_indices, m, (const uint4*)d_records, (float*)d_obs, sc);
+                g2048::gather_samples_tile_kernel<float><<<grid, threads, smem, st>>>(d_indices, m, (const uint4*)d_records, (float*)d_obs, sc);
                 break;
             case G2048_OBS_BF16:
-                g2048::gather_samples_tile_kernel<__nv_bfloat16><<<grid, OBS_THREADS, OBS_SMEM_BYTES, st>>>(d_indices, m, (const uint4*)d_records, (__nv_bfloat16*)d_obs, sc);
+                g2048::gather_samples_tile_kernel<__nv_bfloat16><<<grid, threads, smem, st>>>(d_indices, m, (const uint4*)d_records, (__nv_bfloat16*)d_obs, sc);
                 break;
             case G2048_OBS_BOOL:
-                g2048::gather_samples_tile_kernel<uint8_t><<<grid, OBS_THREADS, OBS_SMEM_BYTES, st>>>(d_indices, m, (const uint4*)d_records, (uint8_t*)d_obs, sc);
+                g2048::gather_samples_tile_kernel<uint8_t><<<grid, threads, smem, st>>>(d_indices, m, (const uint4*)d_records, (uint8_t*)d_obs, sc);
                 break;
             default: return fail_arg("gather_samples: dtype");
         }
