@@ -49,14 +49,16 @@ class PPOIterationLoop:
     normalised advantages and returns) and returns any of ``policy_loss``,
     ``value_loss``, ``entropy_loss``, ``total_loss``, ``kl`` as floats or 0-d tensors (``kl`` = mean of
     old_log_prob - new_log_prob, :443).  ``update_policy(batch_size=, n_epochs=) -> dict`` replaces the whole update
-    (the reference trainer's bound method).  ``checkpoint(loop, name)`` is called where the reference saves.
+    (the reference trainer's bound method).  ``checkpoint(loop, name)`` is called where the reference saves.  With a
+    runner that owns a shard of every batch (``BatchRunner(shard=(rank, world))``) pass the ranks' process ``group``: the
+    buffer's advantages and returns are then normalised with the moments of ALL shards (one all-reduce of six numbers).
     """
 
     def __init__(self, batch_runner, rollout_buffer, minibatch_step: Optional[Callable] = None,
                  update_policy: Optional[Callable] = None, gamma: float = 0.99, lambda_gae: float = 0.95,
                  target_kl: float = 0.01, max_samples_per_epoch: Optional[int] = None, shuffle_on_reset: bool = False,
                  obs_dtype=torch.float32, checkpoint: Optional[Callable] = None, log: Optional[Callable] = None,
-                 history: Optional[int] = None, agent=None):
+                 history: Optional[int] = None, agent=None, group=None):
         if (minibatch_step is None) == (update_policy is None):
             raise ValueError("give exactly one of minibatch_step and update_policy")
         self.batch_runner = batch_runner
@@ -69,6 +71,7 @@ class PPOIterationLoop:
         self.checkpoint, self.log = checkpoint, log
         self.trainer = None
         self.agent = agent  # the policy network, if the rollouts use one: put in eval mode before every collection
+        self.group = group  # process group of a buffer SHARDED over ranks: advantages / returns are normalised with the global moments
         if history is None:  # :140-143
             history = max_samples_per_epoch if max_samples_per_epoch is not None else 10000
         self.episode_rewards: deque = deque(maxlen=history)
@@ -163,7 +166,7 @@ class PPOIterationLoop:
         batches = DevicePPOBatches(self.rollout_buffer.get_packed(), gamma=self.gamma, lambda_gae=self.lambda_gae,
                                    batch_size=batch_size, shuffle=True, drop_last=True,
                                    max_samples_per_epoch=self.max_samples_per_epoch, shuffle_on_reset=self.shuffle_on_reset,
-                                   obs_dtype=self.obs_dtype, sample_records=True, epoch_prefetch=True)
+                                   obs_dtype=self.obs_dtype, sample_records=True, epoch_prefetch=True, group=self.group)
         device = batches.device
         sums = torch.zeros(len(METRIC_KEYS), dtype=torch.float64, device=device)
         n_updates, mean_kl = 0, 0.0
